@@ -1,0 +1,1277 @@
+/*
+ * tsl_oracle.c -- CPU restatement (fp64) of the ThinShellLab hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY ("oracle", tier 2).  Only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference legs may load this library; the
+ * product (thinshelllab_b200) never links, imports or calls it.
+ *
+ * Every function restates one reference kernel and cites it (paths relative to
+ * /root/reference/code).  Parity pinning: tests/test_oracle_golden.py checks this
+ * file block by block against tests/golden/*.npz, which were produced by running
+ * the reference's own Python sources under oracle/ti_emu (the Taichi JIT cannot be
+ * installed here; see oracle/gen_goldens.py).  Reference quirks Q1..Q15 of
+ * SURVEY.md section 8a are reproduced on purpose.
+ *
+ * Matrix storage: the reference's dense-backed SparseMatrix (engine/sparse_solver.py:13-38)
+ * is replaced by a 3x3-block CSR over the vertex adjacency graph; add semantics
+ * (frozen mask, boundary-sensitivity accumulation) follow BaseScene.add_H
+ * (engine/BaseScene.py:399-405).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef _OPENMP
+#include <omp.h>
+#define ATOMIC _Pragma("omp atomic")
+#else
+#define ATOMIC
+#endif
+
+typedef struct {
+    int nv;
+    const int *rowptr;   /* [nv+1] block rows */
+    const int *colidx;   /* [nnzb] sorted within a row */
+    double *val;         /* [nnzb][3][3] */
+    const int *frozen;   /* [3 nv] */
+    int counting;        /* BaseScene.counting_z_frozen */
+    const double *z;     /* tmp_z_not_frozen [3 nv] */
+    double *zf;          /* tmp_z_frozen [3 nv] */
+    int missing;         /* number of adds that fell outside the pattern (must stay 0) */
+} orc_mat;
+
+orc_mat *orc_mat_create(int nv, const int *rowptr, const int *colidx, double *val, const int *frozen)
+{
+    orc_mat *A = (orc_mat *)calloc(1, sizeof(orc_mat));
+    A->nv = nv; A->rowptr = rowptr; A->colidx = colidx; A->val = val; A->frozen = frozen;
+    return A;
+}
+void orc_mat_destroy(orc_mat *A) { free(A); }
+void orc_mat_set_counting(orc_mat *A, int counting, const double *z, double *zf)
+{
+    A->counting = counting; A->z = z; A->zf = zf;
+}
+int orc_mat_missing(orc_mat *A) { return A->missing; }
+
+/* SparseMatrix.add (engine/sparse_solver.py:32-38) on the block-CSR pattern */
+static void mat_add_raw(orc_mat *A, int i, int j, double v)
+{
+    int vi = i / 3, a = i % 3, vj = j / 3, b = j % 3;
+    int lo = A->rowptr[vi], hi = A->rowptr[vi + 1] - 1;
+    while (lo <= hi) {
+        int mid = (lo + hi) >> 1;
+        int c = A->colidx[mid];
+        if (c == vj) {
+            ATOMIC
+            A->val[(size_t)mid * 9 + a * 3 + b] += v;
+            return;
+        }
+        if (c < vj) lo = mid + 1; else hi = mid - 1;
+    }
+    ATOMIC
+    A->missing += 1;
+}
+
+/* BaseScene.add_H (engine/BaseScene.py:399-405) */
+static void add_H(orc_mat *A, int i, int j, double v)
+{
+    if (!A->frozen[i] && !A->frozen[j]) {
+        mat_add_raw(A, i, j, v);
+    } else if (A->counting && A->frozen[j] && !A->frozen[i]) {
+        double t = v * A->z[i];
+        ATOMIC
+        A->zf[j] -= t;
+    }
+}
+
+/* mass diagonal: H.H.add(...) bypasses the frozen mask (model_fold_offset.py:468-470,
+ * model_elastic_offset.py:97-99) */
+void orc_add_mass_diag(orc_mat *A, const double *mass, double dt)
+{
+    for (int i = 0; i < A->nv; i++)
+        for (int j = 0; j < 3; j++) mat_add_raw(A, 3 * i + j, 3 * i + j, mass[i] / (dt * dt));
+}
+
+/* ------------------------------------------------------------------ small vector helpers */
+static inline void v_sub(const double *a, const double *b, double *o) { o[0] = a[0] - b[0]; o[1] = a[1] - b[1]; o[2] = a[2] - b[2]; }
+static inline double v_dot(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void v_cross(const double *a, const double *b, double *o)
+{
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+}
+static inline double v_norm(const double *a) { return sqrt(v_dot(a, a)); }
+
+/* ------------------------------------------------------------------ SPD projector
+ * linalg.SPD_Projector (engine/linalg.py:15-148): Householder tridiagonalisation, K shifted
+ * QR sweeps with the hard thresholds 1e-5 / 1e-6 (Q8), then clamp eigenvalues <= 0. */
+#define PMAX 12
+static void spd_householder(double A[PMAX][PMAX], double T[PMAX][PMAX], double Q[PMAX][PMAX], int n)
+{
+    for (int i = 0; i < n - 2; i++) {
+        double b = 0.0;
+        for (int j = i + 1; j < n; j++) b += A[j][i] * A[j][i];
+        b = sqrt(b);
+        if (b < 1e-6) {
+            T[i][i] = -1;
+            for (int j = i + 1; j < n; j++) A[i][j] = 0;
+        } else {
+            T[i][i] = 1;
+            if (A[i + 1][i] < 0) b *= -1;
+            T[i + 1][i] = A[i + 1][i] + b;
+            double c = T[i + 1][i] * T[i + 1][i];
+            for (int j = i + 2; j < n; j++) { T[j][i] = A[j][i]; c += A[j][i] * A[j][i]; }
+            c = sqrt(2 / c);
+            for (int j = i + 1; j < n; j++) T[j][i] *= c;
+            for (int j = i + 1; j < n; j++) T[i][j] = 0;
+            for (int j = i + 1; j < n; j++) {
+                for (int k = i + 1; k < j + 1; k++) T[i][j] += A[j][k] * T[k][i];
+                for (int k = j + 1; k < n; k++) T[i][j] += A[k][j] * T[k][i];
+            }
+            double d = 0.0;
+            for (int j = i + 1; j < n; j++) d += T[i][j] * T[j][i];
+            d *= 0.5;
+            for (int j = i + 1; j < n; j++) { T[i][j] -= T[j][i] * d; A[i][j] = A[j][i] = 0; }
+            A[i + 1][i] = A[i][i + 1] = -b;
+            for (int j = i + 1; j < n; j++)
+                for (int k = i + 1; k < j + 1; k++) A[j][k] -= T[i][j] * T[k][i] + T[i][k] * T[j][i];
+            for (int k = 0; k < n; k++) {
+                double s = 0.0;
+                for (int j = i + 1; j < n; j++) s += Q[k][j] * T[j][i];
+                for (int j = i + 1; j < n; j++) Q[k][j] -= s * T[j][i];
+            }
+        }
+    }
+    A[n - 2][n - 1] = A[n - 1][n - 2];
+}
+
+static void spd_qr(double A[PMAX][PMAX], double T[PMAX][PMAX], double Q[PMAX][PMAX], int n, int K)
+{
+    for (int j = 0; j < K; j++) {
+        int m = 0;
+        for (int i = 0; i < n - 1; i++) if (fabs(A[i + 1][i]) > 1e-5) m = i + 2;
+        if (m == 0) break;
+        double a = A[m - 2][m - 2], b = A[m - 2][m - 1], c = A[m - 1][m - 1];
+        double d = (a - c) / 2;
+        double sd = d > 0 ? 1 : -1;
+        double mu = c;
+        if (fabs(b) > 1e-6) mu -= (sd * b * b) / (fabs(d) + sqrt(d * d + b * b));
+        for (int i = 0; i < n; i++) A[i][i] -= mu;
+        for (int i = 0; i < m - 1; i++) {
+            double a1 = A[i][i], b1 = A[i][i + 1], e1 = A[i + 1][i], d1 = A[i + 1][i + 1];
+            double s = fabs(e1) > 1e-5 ? fabs(e1 / sqrt(a1 * a1 + e1 * e1)) : 0;
+            if (a1 * e1 < 0) s *= -1;
+            double cc = sqrt(fmax(1 - s * s, 0));
+            T[0][i] = s;
+            A[i][i] = a1 * cc + e1 * s;
+            A[i][i + 1] = b1 * cc + d1 * s;
+            A[i + 1][i + 1] = d1 * cc - b1 * s;
+            if (i < n - 2) A[i + 1][i + 2] *= cc;
+        }
+        for (int i = 0; i < m - 1; i++) {
+            double a1 = A[i][i], b1 = A[i][i + 1], d1 = A[i + 1][i + 1];
+            double s = T[0][i];
+            double cc = sqrt(fmax(1 - s * s, 0));
+            A[i][i] = a1 * cc + b1 * s;
+            A[i + 1][i] = s * d1;
+            A[i + 1][i + 1] = cc * d1;
+            for (int r = 0; r < n; r++) {
+                double qa = Q[r][i], qb = Q[r][i + 1];
+                Q[r][i] = qa * cc + qb * s; Q[r][i + 1] = -qa * s + qb * cc;
+            }
+        }
+        for (int i = 0; i < n - 1; i++) A[i][i + 1] = A[i + 1][i];
+        for (int i = 0; i < n; i++) A[i][i] += mu;
+    }
+}
+
+/* SPD_Projector.project (engine/linalg.py:132-148); M is n x n row-major, in place */
+void orc_spd_project(double *M, int n, int K)
+{
+    double A[PMAX][PMAX], T[PMAX][PMAX], Q[PMAX][PMAX];
+    for (int i = 0; i < n; i++)
+        for (int j = 0; j < n; j++) { A[i][j] = M[i * n + j]; T[i][j] = 0; Q[i][j] = (i == j); }
+    spd_householder(A, T, Q, n);
+    spd_qr(A, T, Q, n, K);
+    for (int i = 0; i < n; i++) T[0][i] = A[i][i];
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) A[i][j] = 0;
+    for (int i = 0; i < n; i++) {
+        double v = T[0][i];
+        if (v > 0)
+            for (int j = 0; j < n; j++) {
+                double v2 = v * Q[j][i];
+                for (int k = 0; k < n; k++) A[j][k] += v2 * Q[k][i];
+            }
+    }
+    for (int i = 0; i < n; i++) for (int j = 0; j < n; j++) M[i * n + j] = A[i][j];
+}
+
+/* linalg.SPD_project_2d (engine/linalg.py:6-12).  For a symmetric 2x2 input the SVD sign test
+ * (u_k . v_k < 0  <=>  eigenvalue_k < 0) is an exact eigenvalue clamp; restated in closed form. */
+void orc_spd_project_2d(double *h)
+{
+    double a = h[0], b = 0.5 * (h[1] + h[2]), d = h[3];
+    double tr = a + d, df = a - d;
+    double rt = sqrt(df * df + 4 * b * b);
+    double l1 = 0.5 * (tr + rt), l2 = 0.5 * (tr - rt);
+    if (l2 >= 0) return;              /* already PSD */
+    if (l1 <= 0) { h[0] = h[1] = h[2] = h[3] = 0; return; }
+    /* unit eigenvector of l1 */
+    double vx, vy;
+    if (fabs(b) > 0) { vx = l1 - d; vy = b; }
+    else if (a >= d) { vx = 1; vy = 0; }
+    else { vx = 0; vy = 1; }
+    double nn = sqrt(vx * vx + vy * vy);
+    vx /= nn; vy /= nn;
+    h[0] = l1 * vx * vx; h[1] = h[2] = l1 * vx * vy; h[3] = l1 * vy * vy;
+}
+
+/* ------------------------------------------------------------------ cloth */
+typedef struct {
+    int N, M, NV, NF, offset;
+    double dx, dt, mass, Kl, Ka, Kb;
+    const int *f2v, *cf, *cp;            /* [NF][3] */
+    const double *pos, *prev_pos, *vel;  /* cloth-local [NV][3] */
+    const double *ref_angle;             /* [NF][3] */
+    const double *gravity;               /* [3] */
+    /* derived (prepare_bending) */
+    double *norm_dir;                    /* [NF][3] */
+    double *mat_M, *mat_N;               /* [NF*3][3][3] */
+    double *angle, *heights, *c_i, *d_i; /* [NF][3] */
+    const signed char *neg_override;     /* [NF][3] test hook, see cloth_neg(); NULL in normal use */
+} orc_cloth;
+
+orc_cloth *orc_cloth_create(int N, int M, int offset, double dx, double dt, double mass,
+                            const int *f2v, const int *cf, const int *cp)
+{
+    orc_cloth *c = (orc_cloth *)calloc(1, sizeof(orc_cloth));
+    c->N = N; c->M = M; c->NV = (N + 1) * (M + 1); c->NF = 2 * N * M; c->offset = offset;
+    c->dx = dx; c->dt = dt; c->mass = mass; c->f2v = f2v; c->cf = cf; c->cp = cp;
+    size_t nf = (size_t)c->NF;
+    c->norm_dir = (double *)calloc(nf * 3, 8);
+    c->mat_M = (double *)calloc(nf * 27, 8);
+    c->mat_N = (double *)calloc(nf * 27, 8);
+    c->angle = (double *)calloc(nf * 3, 8);
+    c->heights = (double *)calloc(nf * 3, 8);
+    c->c_i = (double *)calloc(nf * 3, 8);
+    c->d_i = (double *)calloc(nf * 3, 8);
+    return c;
+}
+void orc_cloth_destroy(orc_cloth *c)
+{
+    free(c->norm_dir); free(c->mat_M); free(c->mat_N); free(c->angle); free(c->heights); free(c->c_i); free(c->d_i); free(c);
+}
+void orc_cloth_bind(orc_cloth *c, const double *pos, const double *prev_pos, const double *vel,
+                    const double *ref_angle, const double *gravity, double Kl, double Ka, double Kb)
+{
+    c->pos = pos; c->prev_pos = prev_pos; c->vel = vel; c->ref_angle = ref_angle; c->gravity = gravity;
+    c->Kl = Kl; c->Ka = Ka; c->Kb = Kb;
+}
+void orc_cloth_get_derived(orc_cloth *c, double *norm_dir, double *mat_M, double *mat_N, double *angle,
+                           double *heights, double *c_i, double *d_i)
+{
+    size_t nf = (size_t)c->NF;
+    memcpy(norm_dir, c->norm_dir, nf * 24); memcpy(mat_M, c->mat_M, nf * 216); memcpy(mat_N, c->mat_N, nf * 216);
+    memcpy(angle, c->angle, nf * 24); memcpy(heights, c->heights, nf * 24); memcpy(c_i, c->c_i, nf * 24);
+    memcpy(d_i, c->d_i, nf * 24);
+}
+
+/* Cloth.init_mesh (engine/model_fold_offset.py:929-1018).  f2v/cf/cp must come in zero-filled:
+ * the odd-parity branch never writes counter_face[k][0] (Q2). */
+void orc_cloth_init_mesh(int N, int M, int *f2v, int *cf, int *cp)
+{
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < M; j++) {
+            int k = (i * M + j) * 2;
+            int a = i * (M + 1) + j, b = a + 1, c = a + M + 2, d = a + M + 1;
+            int *f0 = f2v + 3 * k, *f1 = f2v + 3 * (k + 1);
+            int *cf0 = cf + 3 * k, *cf1 = cf + 3 * (k + 1), *cp0 = cp + 3 * k, *cp1 = cp + 3 * (k + 1);
+            if ((i + j) % 2 == 0) {
+                f0[0] = c; f0[1] = b; f0[2] = a;
+                f1[0] = a; f1[1] = d; f1[2] = c;
+                if (i > 0) { cf0[0] = ((i - 1) * M + j) * 2 + 1; cp0[0] = 2; } else cf0[0] = -1;
+                if (j < M - 1) { cf0[2] = k + 2; cp0[2] = 0; } else cf0[2] = -1;
+                if (i < N - 1) { cf1[0] = ((i + 1) * M + j) * 2; cp1[0] = 2; } else cf1[0] = -1;
+                if (j > 0) { cf1[2] = k - 2; cp1[2] = 0; } else cf1[2] = -1;
+            } else {
+                f0[0] = b; f0[1] = a; f0[2] = d;
+                f1[0] = d; f1[1] = c; f1[2] = b;
+                if (i > 0) { cf0[2] = ((i - 1) * M + j) * 2 + 1; cp0[2] = 0; } else cf0[2] = -1;
+                if (j < M - 1) { cf1[0] = k + 3; cp1[0] = 2; } else cf1[0] = -1;
+                if (i < N - 1) { cf1[2] = ((i + 1) * M + j) * 2; cp1[2] = 0; } else cf1[2] = -1;
+                if (j > 0) { cf0[2] = k - 2; cp0[2] = 2; } else cf0[2] = -1;
+            }
+            cf0[1] = k + 1; cp0[1] = 1; cf1[1] = k; cp1[1] = 1;
+        }
+}
+
+/* Cloth.compute_normal_dir (model_fold_offset.py:169-174) */
+void orc_cloth_normals(orc_cloth *c)
+{
+#pragma omp parallel for
+    for (int i = 0; i < c->NF; i++) {
+        const double *a = c->pos + 3 * c->f2v[3 * i], *b = c->pos + 3 * c->f2v[3 * i + 1], *cc = c->pos + 3 * c->f2v[3 * i + 2];
+        double e0[3], e1[3], n[3];
+        v_sub(b, a, e0); v_sub(cc, b, e1); v_cross(e0, e1, n);
+        double l = v_norm(n);
+        c->norm_dir[3 * i] = n[0] / l; c->norm_dir[3 * i + 1] = n[1] / l; c->norm_dir[3 * i + 2] = n[2] / l;
+    }
+}
+
+/* The side test shared by compute_angle / judge_angle (model_fold_offset.py:116,135,144; `% 2` is Q3):
+ *     norm_dir[i2] . (pos[f2v[i1][(l+1)%2]] - pos[f2v[i1][l]]) < 0
+ * For the mis-wired neighbour entries of Q2 (odd-parity quad, l == 2, neighbour k-2) BOTH of those
+ * vertices belong to face i2, so the dot product is exactly 0 in exact arithmetic and the reference's
+ * answer is the sign of fp rounding noise (it differs between numpy, Taichi/LLVM and any GPU).
+ * Canonical rule used by this oracle and by the CUDA path: a topologically degenerate test evaluates
+ * to 0, i.e. "not negative".  `neg_override` lets the golden tests inject the noise signs that the
+ * emulated reference run happened to produce, so every other formula can still be compared exactly. */
+void orc_cloth_set_neg_override(orc_cloth *c, const signed char *ov) { c->neg_override = ov; }
+static int cloth_neg(const orc_cloth *c, int i1, int i2, int l)
+{
+    if (c->neg_override && c->neg_override[3 * i1 + l] >= 0) return c->neg_override[3 * i1 + l];
+    int va = c->f2v[3 * i1 + (l + 1) % 2], vb = c->f2v[3 * i1 + l];
+    int ina = 0, inb = 0;
+    for (int q = 0; q < 3; q++) { if (c->f2v[3 * i2 + q] == va) ina = 1; if (c->f2v[3 * i2 + q] == vb) inb = 1; }
+    if (ina && inb) return 0;
+    double e[3];
+    v_sub(c->pos + 3 * va, c->pos + 3 * vb, e);
+    return v_dot(c->norm_dir + 3 * i2, e) < 0;
+}
+
+/* Cloth.compute_angle (model_fold_offset.py:126-138) */
+static double cloth_angle(const orc_cloth *c, int i1, int i2, int l)
+{
+    double theta = 0.0;
+    if (i2 != -1) {
+        const double *n1 = c->norm_dir + 3 * i1, *n2 = c->norm_dir + 3 * i2;
+        double ct = v_dot(n1, n2);
+        if (ct < 0.999999) theta = acos(ct);
+        else theta = 2 * sqrt(fabs(1.0 - ct)) / sqrt(1 + ct);
+        if (cloth_neg(c, i1, i2, l)) theta = -theta;
+    }
+    return theta;
+}
+/* Cloth.judge_angle (model_fold_offset.py:140-147) */
+static int cloth_judge(const orc_cloth *c, int i1, int i2, int l)
+{
+    int ret = 1;
+    if (i2 != -1) {
+        if (cloth_neg(c, i1, i2, l)) ret = 0;
+    }
+    return ret;
+}
+static inline double bend_dtheta_ref(const orc_cloth *c, double theta, double ref)
+{   /* compute_bending_dtheta_ref (model_fold_offset.py:280-282) */
+    return 2.0 * c->Kb * (theta - ref) * c->dx * c->dx * 1.0 / 3.0;
+}
+
+/* Cloth.prepare_bending (model_fold_offset.py:415-448) */
+void orc_cloth_prepare_bending(orc_cloth *c)
+{
+#pragma omp parallel for
+    for (int i = 0; i < c->NF; i++) {
+        for (int l = 0; l < 3; l++) {
+            const double *p = c->pos + 3 * c->f2v[3 * i + l];
+            const double *a = c->pos + 3 * c->f2v[3 * i + (l + 1) % 3];
+            const double *b = c->pos + 3 * c->f2v[3 * i + (l + 2) % 3];
+            double edge[3], nd[3], en[3], edge1[3], t[3];
+            v_sub(b, a, edge);
+            for (int k = 0; k < 3; k++) nd[k] = c->norm_dir[3 * i + k];
+            if (cloth_judge(c, i, c->cf[3 * i + l], l)) for (int k = 0; k < 3; k++) nd[k] = -nd[k];
+            v_cross(nd, edge, en);
+            v_sub(a, p, edge1);
+            if (v_dot(en, edge1) > 0) for (int k = 0; k < 3; k++) en[k] = -en[k];
+            double el = v_norm(edge);
+            double *Mm = c->mat_M + (size_t)(i * 3 + l) * 9, *Nm = c->mat_N + (size_t)(i * 3 + l) * 9;
+            for (int r = 0; r < 3; r++) for (int s = 0; s < 3; s++) { Mm[r * 3 + s] = nd[r] * en[s]; Nm[r * 3 + s] = Mm[r * 3 + s] / el; }
+            double ap[3], bp[3];
+            v_sub(a, p, ap); v_sub(b, p, bp);
+            double la = v_norm(ap), lb = v_norm(bp);
+            c->angle[3 * i + l] = (ap[0] / la) * (bp[0] / lb) + (ap[1] / la) * (bp[1] / lb) + (ap[2] / la) * (bp[2] / lb);
+            v_sub(p, a, t);
+            c->heights[3 * i + l] = fabs(v_dot(t, en)) / v_norm(en);
+            if (c->cf[3 * i + l] != -1) {
+                double theta = cloth_angle(c, i, c->cf[3 * i + l], l);
+                c->c_i[3 * i + l] = bend_dtheta_ref(c, theta, c->ref_angle[3 * i + l]);
+            } else c->c_i[3 * i + l] = 0;
+        }
+        for (int l = 0; l < 3; l++)
+            c->d_i[3 * i + l] = c->c_i[3 * i + (l + 1) % 3] * c->angle[3 * i + (l + 2) % 3]
+                              + c->c_i[3 * i + (l + 2) % 3] * c->angle[3 * i + (l + 1) % 3] - c->c_i[3 * i + l];
+    }
+}
+
+/* Cloth.compute_bending_grad (model_fold_offset.py:379-402) */
+static void cloth_bending_grad(const orc_cloth *c, int i1, int l, double *a, double *b, double *cc, double *d)
+{
+    int i2 = c->cf[3 * i1 + l];
+    int p11 = (l + 1) % 3, p12 = (l + 2) % 3;
+    int p4 = c->cp[3 * i1 + l];
+    int p21 = (p4 + 1) % 3;
+    if (c->f2v[3 * i1 + p11] != c->f2v[3 * i2 + p21]) p21 = (p4 + 2) % 3;
+    int p22 = 3 - p21 - p4;
+    const double *n1 = c->norm_dir + 3 * i1, *n2 = c->norm_dir + 3 * i2;
+    const double *h1 = c->heights + 3 * i1, *h2 = c->heights + 3 * i2;
+    const double *g1 = c->angle + 3 * i1, *g2 = c->angle + 3 * i2;
+    for (int k = 0; k < 3; k++) {
+        a[k] = -1.0 / h1[l] * n1[k];
+        d[k] = -1.0 / h2[p4] * n2[k];
+        b[k] = g1[p12] / h1[p11] * n1[k] + g2[p22] / h2[p21] * n2[k];
+        cc[k] = g1[p11] / h1[p12] * n1[k] + g2[p21] / h2[p22] * n2[k];
+    }
+}
+
+/* the five closed forms of model_fold_offset.py:296-377 (restated; Q14 lives in area_dxy_p12) */
+static double area_dx(double area, const double *p1, const double *p2, const double *p3, int dim)
+{   /* compute_area_dx :312-325 */
+    area = area * 2.0;
+    int d1 = (dim == 0) ? 1 : 0, d2 = 3 - d1 - dim;
+    double deri = 0.5 * (p1[dim] * ((p2[d1] - p3[d1]) * (p2[d1] - p3[d1]) + (p2[d2] - p3[d2]) * (p2[d2] - p3[d2]))
+        - p2[dim] * (p1[d1] * (p2[d1] - p3[d1]) - p2[d1] * p3[d1] + p3[d1] * p3[d1] + p1[d2] * p2[d2] - p1[d2] * p3[d2] - p2[d2] * p3[d2] + p3[d2] * p3[d2])
+        + p3[dim] * (p1[d1] * (p2[d1] - p3[d1]) - p2[d1] * p2[d1] + p2[d1] * p3[d1] + (p1[d2] - p2[d2]) * (p2[d2] - p3[d2]))) / area;
+    return deri;
+}
+#define MNR(x, y) ((p2[x] - p1[x]) * (p3[y] - p1[y]) - (p3[x] - p1[x]) * (p2[y] - p1[y]))
+static double area_dx2(double area, const double *p1, const double *p2, const double *p3, int dim)
+{   /* compute_area_dx2 :296-310 */
+    area = area * 2.0;
+    int d1 = (dim == 0) ? 1 : 0, d2 = 3 - d1 - dim;
+    double q = (p2[d1] - p3[d1]) * MNR(dim, d1) + (p2[d2] - p3[d2]) * MNR(dim, d2);
+    double deri = ((p2[d1] - p3[d1]) * (p2[d1] - p3[d1]) + (p2[d2] - p3[d2]) * (p2[d2] - p3[d2])) / area - q * q / (area * area * area);
+    return deri * 0.5;
+}
+static double area_dxy_p1(double area, const double *p1, const double *p2, const double *p3, int dim, int d1)
+{   /* compute_area_dxy_p1 :327-341 */
+    area = area * 2.0;
+    int d2 = 3 - d1 - dim;
+    double deri = ((p3[dim] - p2[dim]) * (p2[d1] - p3[d1])) / area
+        - (((p3[dim] - p2[dim]) * MNR(dim, d1) + (p2[d2] - p3[d2]) * MNR(d1, d2))
+           * ((p2[d1] - p3[d1]) * MNR(dim, d1) + (p2[d2] - p3[d2]) * MNR(dim, d2))) / (area * area * area);
+    return deri * 0.5;
+}
+static double area_dx2_p12(double area, const double *p1, const double *p2, const double *p3, int dim)
+{   /* compute_area_dx2_p12 :343-361 */
+    area = area * 2.0;
+    int d1 = (dim == 0) ? 1 : 0, d2 = 3 - d1 - dim;
+    double deri = ((p3[d1] - p1[d1]) * (p2[d1] - p3[d1]) + (p3[d2] - p1[d2]) * (p2[d2] - p3[d2])) / area
+        - (((p2[d1] - p3[d1]) * MNR(dim, d1) + (p2[d2] - p3[d2]) * MNR(dim, d2))
+           * ((p3[d1] - p1[d1]) * MNR(dim, d1) + (p3[d2] - p1[d2]) * MNR(dim, d2))) / (area * area * area);
+    return deri * 0.5;
+}
+static double area_dxy_p12(double area, const double *p1, const double *p2, const double *p3, int dim, int d1)
+{   /* compute_area_dxy_p12 :363-377 (not the true mixed derivative, Q14) */
+    area = area * 2.0;
+    int d2 = 3 - d1 - dim;
+    double deri = (MNR(dim, d1) + (p1[dim] - p3[dim]) * (p2[d1] - p3[d1])) / area
+        - ((2 * (p1[dim] - p3[dim]) * MNR(dim, d1) + (p3[d2] - p1[d2]) * MNR(d1, d2))
+           * ((p2[d1] - p3[d1]) * MNR(dim, d1) + (p2[d2] - p3[d2]) * MNR(dim, d2))) / (area * area * area);
+    return deri * 0.5;
+}
+#undef MNR
+
+static inline double rest_len(const orc_cloth *c, int l) { return l == 2 ? c->dx * sqrt(2.0) : c->dx; } /* l_i :783-785 */
+static inline double rest_area(const orc_cloth *c) { return c->dx * c->dx * 0.5; }                         /* V  :782 */
+
+/* Cloth.compute_energy (model_fold_offset.py:190-218).  parts[0..3] = vertex, edge, area, bending.
+ * The per-quad edge list of :202-213 equals "three edges of every triangle" (Q4: the diagonal twice). */
+double orc_cloth_energy(orc_cloth *c, double *parts)
+{
+    double Uv = 0, Ue = 0, Ua = 0, Ub = 0;
+    double dt = c->dt;
+#pragma omp parallel for reduction(+ : Uv)
+    for (int i = 0; i < c->NV; i++) {
+        const double *x = c->pos + 3 * i, *xp = c->prev_pos + 3 * i, *v = c->vel + 3 * i;
+        Uv += -v_dot(x, c->gravity) * c->mass;
+        double X[3] = { x[0] - xp[0] - v[0] * dt, x[1] - xp[1] - v[1] * dt, x[2] - xp[2] - v[2] * dt };
+        Uv += 0.5 * c->mass * v_dot(X, X) / (dt * dt);
+    }
+#pragma omp parallel for reduction(+ : Ue, Ua, Ub)
+    for (int i = 0; i < c->NF; i++) {
+        const int *f = c->f2v + 3 * i;
+        const double *a = c->pos + 3 * f[0], *b = c->pos + 3 * f[1], *cc = c->pos + 3 * f[2];
+        double l0[3], l1[3], n[3];
+        v_sub(b, a, l0); v_sub(cc, a, l1); v_cross(l0, l1, n);
+        double area = v_norm(n) * 0.5, V = rest_area(c);
+        Ua += c->Ka * (1 - area / V) * (1 - area / V) * V;
+        for (int l = 0; l < 3; l++) {
+            double e[3];
+            v_sub(c->pos + 3 * f[(l + 1) % 3], c->pos + 3 * f[l], e);
+            double len = v_norm(e), base = rest_len(c, l);
+            Ue += c->Kl * (1 - len / base) * (1 - len / base) * base;
+        }
+        for (int l = 0; l < 3; l++)
+            if (c->cf[3 * i + l] > i) {   /* compute_bending_energy :108-120 */
+                double theta = cloth_angle(c, i, c->cf[3 * i + l], l);
+                double dth = theta - c->ref_angle[3 * i + l];
+                Ub += c->Kb * dth * dth * c->dx * c->dx * 1.0 / 3.0;
+            }
+    }
+    if (parts) { parts[0] = Uv; parts[1] = Ue; parts[2] = Ua; parts[3] = Ub; }
+    return Uv + Ue + Ua + Ub;
+}
+
+/* Cloth.compute_residual (model_fold_offset.py:639-687); mask bit0 vertex terms, bit1 edge, bit2 area, bit3 bending.
+ * F_b is cloth-local [NV][3], overwritten. */
+void orc_cloth_residual(orc_cloth *c, double *F_b, int mask)
+{
+    double dt = c->dt;
+    for (int i = 0; i < c->NV; i++)
+        for (int k = 0; k < 3; k++) {
+            double f = 0;
+            if (mask & 1) {
+                f = -c->mass * c->gravity[k];
+                f += c->mass * (c->pos[3 * i + k] - c->prev_pos[3 * i + k] - c->vel[3 * i + k] * dt) / (dt * dt);
+            }
+            F_b[3 * i + k] = f;
+        }
+#pragma omp parallel for
+    for (int i = 0; i < c->NF; i++) {
+        const int *f = c->f2v + 3 * i;
+        if (mask & 2)
+            for (int l = 0; l < 3; l++) {
+                int xx = f[l], yy = f[(l + 1) % 3];
+                double delta[3];
+                v_sub(c->pos + 3 * xx, c->pos + 3 * yy, delta);
+                double lt = v_norm(delta), base = rest_len(c, l);
+                double dl = -c->Kl * 2.0 * (1.0 - lt / base);     /* compute_membrane_dl :260-262 */
+                for (int k = 0; k < 3; k++) {
+                    double g = delta[k] * dl / lt;
+                    ATOMIC
+                    F_b[3 * xx + k] += g;
+                    ATOMIC
+                    F_b[3 * yy + k] += -g;
+                }
+            }
+        if (mask & 4) {
+            const double *a = c->pos + 3 * f[0], *b = c->pos + 3 * f[1], *cc = c->pos + 3 * f[2];
+            double v1[3], v2[3], n[3];
+            v_sub(b, a, v1); v_sub(cc, a, v2); v_cross(v1, v2, n);
+            double area = 0.5 * v_norm(n), V = rest_area(c);
+            double da = -c->Ka * 2.0 * (1.0 - area / V);          /* compute_membrane_darea :268-270 */
+            for (int l = 0; l < 3; l++)
+                for (int j = 0; j < 3; j++) {
+                    double g = da * area_dx(area, c->pos + 3 * f[l], c->pos + 3 * f[(l + 1) % 3], c->pos + 3 * f[(l + 2) % 3], j);
+                    ATOMIC
+                    F_b[3 * f[l] + j] += g;
+                }
+        }
+        if (mask & 8)
+            for (int l = 0; l < 3; l++)
+                if (c->cf[3 * i + l] > i) {
+                    double a[3], b[3], cc[3], d[3];
+                    cloth_bending_grad(c, i, l, a, b, cc, d);
+                    double theta = cloth_angle(c, i, c->cf[3 * i + l], l);
+                    double dth = bend_dtheta_ref(c, theta, c->ref_angle[3 * i + l]);
+                    int v0 = f[l], v1 = f[(l + 1) % 3], v2 = f[(l + 2) % 3];
+                    int v3 = c->f2v[3 * c->cf[3 * i + l] + c->cp[3 * i + l]];
+                    for (int k = 0; k < 3; k++) {
+                        ATOMIC
+                        F_b[3 * v0 + k] += dth * a[k];
+                        ATOMIC
+                        F_b[3 * v1 + k] += dth * b[k];
+                        ATOMIC
+                        F_b[3 * v2 + k] += dth * cc[k];
+                        ATOMIC
+                        F_b[3 * v3 + k] += dth * d[k];
+                    }
+                }
+    }
+}
+
+/* Cloth.compute_Hessian_me (model_fold_offset.py:466-524), without the mass diagonal
+ * (see orc_add_mass_diag).  Q15: off-diagonal of "d2l" has a + sign. */
+void orc_cloth_hessian_me(orc_cloth *c, orc_mat *A, int spd)
+{
+#pragma omp parallel for
+    for (int i = 0; i < c->NF; i++) {
+        const int *f = c->f2v + 3 * i;
+        for (int l = 0; l < 3; l++) {
+            int xx = f[l], yy = f[(l + 1) % 3];
+            const double *a = c->pos + 3 * xx, *b = c->pos + 3 * yy;
+            double delta[3], H[9];
+            v_sub(a, b, delta);
+            double lt = v_norm(delta), base = rest_len(c, l);
+            double dl = -c->Kl * 2.0 * (1.0 - lt / base);
+            double dl2 = c->Kl * 2.0 / base;                      /* compute_membrane_dl2 :264-266 */
+            for (int j = 0; j < 3; j++)
+                for (int k = 0; k < 3; k++) {
+                    double second;
+                    if (j == k) second = (lt * lt - (a[j] - b[j]) * (a[j] - b[j])) / (lt * lt * lt);  /* compute_l_dx2 :288-290 */
+                    else second = (a[j] - b[j]) * (a[k] - b[k]) / (lt * lt * lt);                     /* compute_l_dxy :292-294 */
+                    H[j * 3 + k] = dl * second + dl2 * (delta[j] / lt) * (delta[k] / lt);
+                }
+            if (spd) orc_spd_project(H, 3, 10);
+            int X = xx + c->offset, Y = yy + c->offset;
+            for (int j = 0; j < 3; j++)
+                for (int k = 0; k < 3; k++) {
+                    add_H(A, X * 3 + j, X * 3 + k, H[j * 3 + k]);
+                    add_H(A, X * 3 + j, Y * 3 + k, -H[j * 3 + k]);
+                    add_H(A, Y * 3 + j, X * 3 + k, -H[j * 3 + k]);
+                    add_H(A, Y * 3 + j, Y * 3 + k, H[j * 3 + k]);
+                }
+        }
+    }
+}
+
+/* Cloth.compute_Hessian_ma (model_fold_offset.py:526-580) */
+void orc_cloth_hessian_ma(orc_cloth *c, orc_mat *A)
+{
+#pragma omp parallel for
+    for (int i = 0; i < c->NF; i++) {
+        const int *f = c->f2v + 3 * i;
+        const double *P[3] = { c->pos + 3 * f[0], c->pos + 3 * f[1], c->pos + 3 * f[2] };
+        double v1[3], v2[3], n[3], fd[3][3];
+        double V = rest_area(c);
+        double darea2 = c->Ka * 2.0 / V;                           /* compute_membrane_darea2 :272-274 */
+        v_sub(P[1], P[0], v1); v_sub(P[2], P[0], v2); v_cross(v1, v2, n);
+        double area = 0.5 * v_norm(n);
+        double da = -c->Ka * 2.0 * (1.0 - area / V);
+        for (int l = 0; l < 3; l++)
+            for (int j = 0; j < 3; j++) fd[l][j] = area_dx(area, P[l], P[(l + 1) % 3], P[(l + 2) % 3], j);
+        for (int j = 0; j < 3; j++)
+            for (int k = 0; k < 3; k++)
+                for (int l = 0; l < 3; l++)
+                    for (int m = 0; m < 3; m++) {
+                        int xx = f[l] + c->offset, yy = f[m] + c->offset;
+                        double h = fd[l][j] * fd[m][k] * darea2;
+                        if (j == k) {
+                            if (l == m) h += da * area_dx2(area, P[l], P[(l + 1) % 3], P[(l + 2) % 3], j);
+                            else h += da * area_dx2_p12(area, P[l], P[m], P[3 - l - m], j);
+                        } else {
+                            if (l == m) h += da * area_dxy_p1(area, P[l], P[(l + 1) % 3], P[(l + 2) % 3], j, k);
+                            else h += da * area_dxy_p12(area, P[l], P[m], P[3 - l - m], j, k);
+                        }
+                        add_H(A, xx * 3 + j, yy * 3 + k, h);
+                    }
+    }
+}
+
+/* Cloth.compute_Hessian_bending (model_fold_offset.py:582-637).  Loop 1 indexes c_i / mat_N with
+ * the LOCAL index l where the face index was meant (Q1): rows l=0..2 of c_i, mat_N[l*3+..]. */
+void orc_cloth_hessian_bending(orc_cloth *c, orc_mat *A)
+{
+#pragma omp parallel for
+    for (int i = 0; i < c->NF; i++) {
+        const int *f = c->f2v + 3 * i;
+        for (int l = 0; l < 3; l++)
+            for (int lm = l; lm < l + 2; lm++) {
+                int m = lm % 3;
+                double H[9];
+                double s = 1.0 / (c->heights[3 * i + l] * c->heights[3 * i + m]);
+                const double *Mm = c->mat_M + (size_t)(i * 3 + m) * 9, *Ml = c->mat_M + (size_t)(i * 3 + l) * 9;
+                double dl = c->d_i[3 * i + l], dm = c->d_i[3 * i + m];
+                for (int r = 0; r < 3; r++)
+                    for (int q = 0; q < 3; q++) H[r * 3 + q] = s * (dl * Mm[q * 3 + r] + dm * Ml[r * 3 + q]);
+                if (l == m) {
+                    int i1 = (l + 1) % 3, i2 = (l + 2) % 3;
+                    const double *N1 = c->mat_N + (size_t)(l * 3 + i1) * 9, *N2 = c->mat_N + (size_t)(l * 3 + i2) * 9;
+                    double c1 = c->c_i[3 * l + i1], c2 = c->c_i[3 * l + i2];
+                    for (int r = 0; r < 9; r++) H[r] += -c1 * N1[r] - c2 * N2[r];
+                } else {
+                    int i3 = 3 - l - m;
+                    const double *N3 = c->mat_N + (size_t)(l * 3 + i3) * 9;
+                    double c3 = c->c_i[3 * l + i3];
+                    for (int r = 0; r < 9; r++) H[r] += c3 * N3[r];
+                }
+                int xx = f[l] + c->offset, yy = f[m] + c->offset;
+                for (int j = 0; j < 3; j++)
+                    for (int k = 0; k < 3; k++) {
+                        add_H(A, xx * 3 + j, yy * 3 + k, H[j * 3 + k]);
+                        if (l != m) add_H(A, yy * 3 + j, xx * 3 + k, H[k * 3 + j]);
+                    }
+            }
+        for (int l = 0; l < 3; l++)
+            if (c->cf[3 * i + l] > i) {
+                double g[4][3];
+                cloth_bending_grad(c, i, l, g[0], g[1], g[2], g[3]);
+                int pt[4] = { f[l], f[(l + 1) % 3], f[(l + 2) % 3], c->f2v[3 * c->cf[3 * i + l] + c->cp[3 * i + l]] };
+                double d2 = 2.0 * c->Kb * c->dx * c->dx * 1.0 / 3.0;   /* compute_bending_dtheta2 :284-286 */
+                for (int j = 0; j < 4; j++)
+                    for (int k = 0; k < 4; k++)
+                        for (int jj = 0; jj < 3; jj++)
+                            for (int kk = 0; kk < 3; kk++)
+                                add_H(A, (pt[j] + c->offset) * 3 + jj, (pt[k] + c->offset) * 3 + kk, d2 * g[j][jj] * g[k][kk]);
+            }
+    }
+}
+
+/* Cloth.update_ref_angle (model_fold_offset.py:176-185); ref_angle updated in place */
+void orc_cloth_update_ref_angle(orc_cloth *c, double *ref_angle, double k_angle)
+{
+    for (int i = 0; i < c->NF; i++)
+        for (int l = 0; l < 3; l++)
+            if (c->cf[3 * i + l] > i) {
+                double theta = cloth_angle(c, i, c->cf[3 * i + l], l);
+                double dis = theta - ref_angle[3 * i + l];
+                double ad = fabs(dis);
+                if (ad > k_angle) ref_angle[3 * i + l] += (ad - k_angle) * dis / ad;
+            }
+}
+
+/* Cloth.compute_deri_Kb / compute_deri (model_fold_offset.py:1082-1148): dF/dK per vertex (cloth-local).
+ * Any of d_kl/d_ka/d_kb may be NULL. */
+void orc_cloth_compute_deri(orc_cloth *c, double *d_kl, double *d_ka, double *d_kb)
+{
+    size_t n = (size_t)c->NV * 3;
+    double *tmp = (double *)malloc(n * 8);
+    if (d_kl) { orc_cloth_residual(c, tmp, 2); for (size_t i = 0; i < n; i++) d_kl[i] = -tmp[i] / c->Kl; }
+    if (d_ka) { orc_cloth_residual(c, tmp, 4); for (size_t i = 0; i < n; i++) d_ka[i] = -tmp[i] / c->Ka; }
+    if (d_kb) { orc_cloth_residual(c, tmp, 8); for (size_t i = 0; i < n; i++) d_kb[i] = -tmp[i] / c->Kb; }
+    free(tmp);
+}
+
+/* Cloth.ref_angle_backprop_x2a (model_fold_offset.py:1154-1168): angleref_grad_prev [NF][3] += ... ; p global [3 tot_NV] */
+void orc_cloth_refangle_x2a(orc_cloth *c, double *angleref_grad_prev, const double *p)
+{
+    double d_ref = -2.0 * c->Kb * c->dx * c->dx * 1.0 / 3.0;     /* dtheta_ref :1150-1152 */
+    for (int i = 0; i < c->NF; i++)
+        for (int l = 0; l < 3; l++)
+            if (c->cf[3 * i + l] > i) {
+                double g[4][3];
+                cloth_bending_grad(c, i, l, g[0], g[1], g[2], g[3]);
+                const int *f = c->f2v + 3 * i;
+                int pt[4] = { f[l], f[(l + 1) % 3], f[(l + 2) % 3], c->f2v[3 * c->cf[3 * i + l] + c->cp[3 * i + l]] };
+                for (int j = 0; j < 3; j++)
+                    for (int q = 0; q < 4; q++)
+                        angleref_grad_prev[3 * i + l] += -p[(pt[q] + c->offset) * 3 + j] * d_ref * g[q][j];
+            }
+}
+
+/* Cloth.ref_angle_backprop_a2ax (model_fold_offset.py:1179-1206): note the 0.1 leak on the non-yielding branch */
+void orc_cloth_refangle_a2ax(orc_cloth *c, const double *angleref_grad_step, double *angleref_grad_prev,
+                             double *pos_grad_step /* global [tot_NV][3] */, double k_angle)
+{
+    for (int i = 0; i < c->NF; i++)
+        for (int l = 0; l < 3; l++)
+            if (c->cf[3 * i + l] > i) {
+                double g[4][3];
+                cloth_bending_grad(c, i, l, g[0], g[1], g[2], g[3]);
+                double theta = cloth_angle(c, i, c->cf[3 * i + l], l);
+                angleref_grad_prev[3 * i + l] += angleref_grad_step[3 * i + l];
+                double dis = theta - c->ref_angle[3 * i + l];
+                double sign = angleref_grad_step[3 * i + l];
+                if (!(fabs(dis) > k_angle)) sign *= 0.1;
+                const int *f = c->f2v + 3 * i;
+                int pt[4] = { f[l], f[(l + 1) % 3], f[(l + 2) % 3], c->f2v[3 * c->cf[3 * i + l] + c->cp[3 * i + l]] };
+                for (int q = 0; q < 4; q++)
+                    for (int j = 0; j < 3; j++) pos_grad_step[(pt[q] + c->offset) * 3 + j] += sign * g[q][j];
+            }
+}
+
+/* ------------------------------------------------------------------ surface normals
+ * BaseScene.calc_vn (engine/BaseScene.py:837-850) */
+void orc_calc_vn(int nv, int nf, const int *faces, const double *pos, double *vn)
+{
+    memset(vn, 0, (size_t)nv * 24);
+    for (int i = 0; i < nf; i++) {
+        const double *v1 = pos + 3 * faces[3 * i], *v2 = pos + 3 * faces[3 * i + 1], *v3 = pos + 3 * faces[3 * i + 2];
+        double a[3], b[3], n[3];
+        v_sub(v2, v1, a); v_sub(v3, v1, b); v_cross(a, b, n);
+        for (int q = 0; q < 3; q++) for (int k = 0; k < 3; k++) vn[3 * faces[3 * i + q] + k] += n[k];
+    }
+    for (int i = 0; i < nv; i++) {
+        double l = v_norm(vn + 3 * i);
+        for (int k = 0; k < 3; k++) vn[3 * i + k] /= l;    /* 0/0 = NaN for interior tet vertices, as in Taichi */
+    }
+}
+
+/* ------------------------------------------------------------------ contact candidate search
+ * geometry.pt2tri (engine/geometry.py:23-87) */
+static int pt2tri(const double *x, const double *p1, const double *p2, const double *p3, double *d_out, double *w)
+{
+    double e1[3], e2[3], e3[3], n[3], t[3], x1[3], u[3], cr[3];
+    v_sub(p2, p1, e1); v_sub(p3, p2, e2); v_sub(p1, p3, e3);
+    double l;
+    l = v_norm(e1); for (int k = 0; k < 3; k++) e1[k] /= l;
+    l = v_norm(e2); for (int k = 0; k < 3; k++) e2[k] /= l;
+    l = v_norm(e3); for (int k = 0; k < 3; k++) e3[k] /= l;
+    v_cross(e1, e3, t); l = v_norm(t);
+    for (int k = 0; k < 3; k++) n[k] = -(t[k] / l);
+    v_sub(x, p1, u);
+    double h = v_dot(u, n);
+    for (int k = 0; k < 3; k++) x1[k] = x[k] - h * n[k];
+    int c = 0; double d = 0.0;
+    w[0] = w[1] = w[2] = 0;
+    double a1[3], a2[3], a3[3];
+    v_sub(x1, p1, a1); v_sub(x1, p2, a2); v_sub(x1, p3, a3);
+    v_cross(a1, e1, cr);
+    if (v_dot(cr, n) > 0) {
+        if (v_dot(a1, e1) < 0) { c = 1; v_sub(x, p1, u); d = v_norm(u); w[0] = 1; }
+        else if (v_dot(a2, e1) > 0) { c = 2; v_sub(x, p2, u); d = v_norm(u); w[1] = 1; }
+        else {
+            c = -3;
+            double ee[3]; v_sub(p2, p1, ee);
+            double alpha = v_dot(a1, e1) / v_dot(ee, e1);
+            double x2[3]; for (int k = 0; k < 3; k++) x2[k] = p1[k] + alpha * ee[k];
+            v_sub(x, x2, u); d = v_norm(u); w[0] = 1 - alpha; w[1] = alpha; w[2] = 0;
+        }
+    } else {
+        v_cross(a2, e2, cr);
+        if (v_dot(cr, n) > 0) {
+            if (v_dot(a2, e2) < 0) { c = 2; v_sub(x, p2, u); d = v_norm(u); w[1] = 1; }
+            else if (v_dot(a3, e2) > 0) { c = 3; v_sub(x, p3, u); d = v_norm(u); w[2] = 1; }
+            else {
+                c = -1;
+                double ee[3]; v_sub(p3, p2, ee);
+                double alpha = v_dot(a2, e2) / v_dot(ee, e2);
+                double x2[3]; for (int k = 0; k < 3; k++) x2[k] = p2[k] + alpha * ee[k];
+                v_sub(x, x2, u); d = v_norm(u); w[0] = 0; w[1] = 1 - alpha; w[2] = alpha;
+            }
+        } else {
+            v_cross(a3, e3, cr);
+            if (v_dot(cr, n) > 0) {
+                if (v_dot(a3, e3) < 0) { c = 3; v_sub(x, p3, u); d = v_norm(u); w[2] = 1; }
+                else if (v_dot(a1, e3) > 0) { c = 1; v_sub(x, p1, u); d = v_norm(u); w[0] = 1; }
+                else {
+                    c = -2;
+                    double ee[3]; v_sub(p1, p3, ee);
+                    double alpha = v_dot(a3, e3) / v_dot(ee, e3);
+                    double x2[3]; for (int k = 0; k < 3; k++) x2[k] = p3[k] + alpha * ee[k];
+                    v_sub(x, x2, u); d = v_norm(u); w[0] = alpha; w[1] = 0; w[2] = 1 - alpha;
+                }
+            } else {
+                v_sub(x, x1, u); d = v_norm(u);
+                double s1[3], s2[3], sc[3];
+                v_sub(p3, p1, s1); v_sub(p2, p1, s2); v_cross(s1, s2, sc);
+                double S = v_norm(sc);
+                double b1[3], b2[3];
+                v_sub(p3, p2, b1); v_sub(x1, p2, b2); v_cross(b1, b2, sc); w[0] = v_dot(sc, n) / S;
+                v_sub(p1, p3, b1); v_sub(x1, p3, b2); v_cross(b1, b2, sc); w[1] = v_dot(sc, n) / S;
+                v_sub(p2, p1, b1); v_sub(x1, p1, b2); v_cross(b1, b2, sc); w[2] = v_dot(sc, n) / S;
+            }
+        }
+    }
+    *d_out = d;
+    return c;
+}
+
+/* geometry.grid_idx (engine/geometry.py:89-94) with the module constants of :8-10 */
+#define GRID_H 0.003
+static int grid_n_(void) { return (int)floor(0.2 / GRID_H) * 2; }
+static void grid_idx(const double *x, int *o)
+{
+    int gn = grid_n_();
+    double bound = GRID_H * (gn - 1) / 2;
+    for (int k = 0; k < 3; k++) {
+        double v = x[k] < -bound ? -bound : (x[k] > bound ? bound : x[k]);
+        o[k] = (int)floor(v / GRID_H) + gn / 2;
+    }
+}
+int orc_grid_n(void) { return grid_n_(); }
+
+/* geometry.p2g + geometry.project_pair (engine/geometry.py:96-221) for ONE surface body against ONE
+ * query vertex range.  Candidate order = cells in (i,j,k) lexicographic order, faces in ascending
+ * index inside a cell (the serial order of the reference's scatter loop :145-157).
+ * proj_* are the [tot_NV]-sized rows of this surface body. */
+void orc_project_pair(int nv, const double *pos, const double *vn, const int *faces, int f_start, int f_end,
+                      int v_start, int v_end, const int *border_flag,
+                      int *proj_flag, int *proj_dir, int *proj_idx, double *proj_w)
+{
+    (void)nv;
+    int gn = grid_n_();
+    size_t ncell = (size_t)gn * gn * gn;
+    int *cnt = (int *)calloc(ncell + 1, sizeof(int));
+    int nf = f_end - f_start;
+    int *cell_of = (int *)malloc(sizeof(int) * (size_t)(nf > 0 ? nf : 1));
+    int lo[3] = { gn, gn, gn }, hi[3] = { 0, 0, 0 };
+    for (int i = f_start; i < f_end; i++) {
+        const double *a = pos + 3 * faces[3 * i], *b = pos + 3 * faces[3 * i + 1], *c = pos + 3 * faces[3 * i + 2];
+        double mid[3] = { (a[0] + b[0] + c[0]) / 3, (a[1] + b[1] + c[1]) / 3, (a[2] + b[2] + c[2]) / 3 };
+        int g[3]; grid_idx(mid, g);
+        for (int k = 0; k < 3; k++) { if (g[k] < lo[k]) lo[k] = g[k]; if (g[k] > hi[k]) hi[k] = g[k]; }
+        int cid = (g[0] * gn + g[1]) * gn + g[2];
+        cell_of[i - f_start] = cid;
+        cnt[cid + 1]++;
+    }
+    for (size_t q = 0; q < ncell; q++) cnt[q + 1] += cnt[q];     /* cnt[c] = base index of cell c */
+    int *order = (int *)malloc(sizeof(int) * (size_t)(nf > 0 ? nf : 1));
+    int *fill = (int *)calloc(ncell, sizeof(int));
+    for (int i = 0; i < nf; i++) { int cid = cell_of[i]; order[cnt[cid] + fill[cid]++] = f_start + i; }
+    free(fill);
+
+#pragma omp parallel for
+    for (int i = v_start; i < v_end; i++) {
+        const double *xq = pos + 3 * i;
+        int q[3]; grid_idx(xq, q);
+        int r0[3], r1[3];
+        for (int k = 0; k < 3; k++) {
+            r0[k] = q[k] - 1 > lo[k] ? q[k] - 1 : lo[k];
+            r1[k] = (q[k] + 1 < hi[k] ? q[k] + 1 : hi[k]) + 1;
+        }
+        double d_min = 1e6, cos_max = -1e6;
+        int pflag = 0, pidx[3] = { 0, 0, 0 };
+        double pw[3] = { 0, 0, 0 };
+        for (int gi = r0[0]; gi < r1[0]; gi++)
+            for (int gj = r0[1]; gj < r1[1]; gj++)
+                for (int gk = r0[2]; gk < r1[2]; gk++) {
+                    int cid = (gi * gn + gj) * gn + gk;
+                    for (int s = cnt[cid]; s < cnt[cid + 1]; s++) {
+                        int fi = order[s];
+                        const int *fv = faces + 3 * fi;
+                        const double *v1 = pos + 3 * fv[0], *v2 = pos + 3 * fv[1], *v3 = pos + 3 * fv[2];
+                        double d, w[3];
+                        int c = pt2tri(xq, v1, v2, v3, &d, w);
+                        double vt[3], e1[3], e2[3], nt[3], dd[3];
+                        for (int k = 0; k < 3; k++) vt[k] = v1[k] * w[0] + v2[k] * w[1] + v3[k] * w[2];
+                        v_sub(v2, v1, e1); v_sub(v3, v1, e2); v_cross(e1, e2, nt);
+                        double nl = v_norm(nt);
+                        v_sub(xq, vt, dd);
+                        double cs = (dd[0] * (nt[0] / nl) + dd[1] * (nt[1] / nl) + dd[2] * (nt[2] / nl));
+                        if (d < d_min - 1e-5 || (d < d_min + 1e-5 && cs > cos_max)) {
+                            d_min = d; cos_max = cs;
+                            pidx[0] = fv[0]; pidx[1] = fv[1]; pidx[2] = fv[2];
+                            pw[0] = w[0]; pw[1] = w[1]; pw[2] = w[2];
+                            if (c == 0) pflag = 1;
+                            else if (c > 0) pflag = !border_flag[fv[c - 1]];
+                            else {
+                                int p1 = (c != -3) ? fv[2] : fv[0];
+                                int p2 = (c != -3) ? fv[2 + c] : fv[1];
+                                pflag = !(border_flag[p1] && border_flag[p2]);
+                            }
+                        }
+                    }
+                }
+        const double *v1 = pos + 3 * pidx[0], *v2 = pos + 3 * pidx[1], *v3 = pos + 3 * pidx[2];
+        const double *n1 = vn + 3 * pidx[0], *n2 = vn + 3 * pidx[1], *n3 = vn + 3 * pidx[2];
+        double v[3], n[3], dd[3];
+        for (int k = 0; k < 3; k++) {
+            v[k] = pw[0] * v1[k] + pw[1] * v2[k] + pw[2] * v3[k];
+            n[k] = pw[0] * n1[k] + pw[1] * n2[k] + pw[2] * n3[k];
+        }
+        v_sub(xq, v, dd);
+        if (proj_flag[i] == 0 && pflag == 1) proj_dir[i] = v_dot(dd, n) > 0;
+        proj_flag[i] = pflag;
+        proj_idx[3 * i] = pidx[0]; proj_idx[3 * i + 1] = pidx[1]; proj_idx[3 * i + 2] = pidx[2];
+        proj_w[3 * i] = pw[0]; proj_w[3 * i + 1] = pw[1]; proj_w[3 * i + 2] = pw[2];
+    }
+    free(cnt); free(cell_of); free(order);
+}
+
+/* ------------------------------------------------------------------ contact constraints
+ * BaseScene.contact_pair_analysis (engine/BaseScene.py:778-816).  Appends in ascending vertex order
+ * (the reference's atomic append order is nondeterministic; the SET is what is compared).
+ * Returns the new constraint count. */
+int orc_contact_pair_analysis(const double *pos, const double *prev_pos, int v_start, int v_end, double mu,
+                              double k_contact, double eps_contact,
+                              const int *proj_flag, const int *proj_dir, const int *proj_idx, const double *proj_w,
+                              int nc, int max_nc, int *c_idx, double *c_w, double *c_k, double *c_mu, double *c_dx0,
+                              double *c_T, double *c_n)
+{
+    for (int i = v_start; i < v_end; i++) {
+        if (!proj_flag[i]) continue;
+        int idx[3] = { proj_idx[3 * i], proj_idx[3 * i + 1], proj_idx[3 * i + 2] };
+        double w[3] = { proj_w[3 * i], proj_w[3 * i + 1], proj_w[3 * i + 2] };
+        double xc[3], x0c[3], e1[3], e2[3], n[3], dd[3];
+        for (int k = 0; k < 3; k++) {
+            xc[k] = pos[3 * idx[0] + k] * w[0] + pos[3 * idx[1] + k] * w[1] + pos[3 * idx[2] + k] * w[2];
+            x0c[k] = prev_pos[3 * idx[0] + k] * w[0] + prev_pos[3 * idx[1] + k] * w[1] + prev_pos[3 * idx[2] + k] * w[2];
+        }
+        v_sub(pos + 3 * idx[1], pos + 3 * idx[0], e1); v_sub(pos + 3 * idx[2], pos + 3 * idx[0], e2); v_cross(e1, e2, n);
+        double nl = v_norm(n);
+        for (int k = 0; k < 3; k++) n[k] /= nl;
+        if (proj_dir[i] == 0) {
+            for (int k = 0; k < 3; k++) n[k] = -n[k];
+            int t = idx[1]; idx[1] = idx[2]; idx[2] = t;
+            double tw = w[1]; w[1] = w[2]; w[2] = tw;
+        }
+        v_sub(pos + 3 * i, xc, dd);
+        double dist = v_dot(dd, n);
+        if (dist < eps_contact) {
+            if (nc >= max_nc) return -1;
+            double cforce = k_contact * (dist - eps_contact);
+            c_idx[4 * nc] = idx[0]; c_idx[4 * nc + 1] = idx[1]; c_idx[4 * nc + 2] = idx[2]; c_idx[4 * nc + 3] = i;
+            for (int k = 0; k < 3; k++) { c_w[3 * nc + k] = w[k]; c_dx0[3 * nc + k] = prev_pos[3 * i + k] - x0c[k]; c_n[3 * nc + k] = n[k]; }
+            c_k[nc] = -mu * cforce; c_mu[nc] = mu;
+            double t1[3], t2[3];
+            if (fabs(n[0]) < 0.5) { t1[0] = n[0]; t1[1] = n[2]; t1[2] = -n[1]; }
+            else { t1[0] = n[1]; t1[1] = -n[0]; t1[2] = n[2]; }
+            v_cross(n, t1, t2); v_cross(n, t2, t1);                 /* Q13: not normalised */
+            for (int k = 0; k < 3; k++) { c_T[6 * nc + k] = t1[k]; c_T[6 * nc + 3 + k] = t2[k]; }
+            nc++;
+        }
+    }
+    return nc;
+}
+
+/* contact_diff.det (engine/contact_diff.py:4-25): value, gradient G[9], Hessian H[9][9] (H zero-filled by caller) */
+static double cd_det(const double *a, const double *b, const double *c, double *G, double H[9][9])
+{
+    double d = a[0] * b[1] * c[2] + a[1] * b[2] * c[0] + a[2] * b[0] * c[1] - a[2] * b[1] * c[0] - a[1] * b[0] * c[2] - a[0] * b[2] * c[1];
+    if (G) {
+        double t[3];
+        v_cross(b, c, t); G[0] = t[0]; G[1] = t[1]; G[2] = t[2];
+        v_cross(c, a, t); G[3] = t[0]; G[4] = t[1]; G[5] = t[2];
+        v_cross(a, b, t); G[6] = t[0]; G[7] = t[1]; G[8] = t[2];
+        for (int i = 0; i < 3; i++) {
+            int j = i < 2 ? i + 1 : 0, k = i > 0 ? i - 1 : 2;
+            H[0 + i][3 + j] = H[3 + j][0 + i] = c[k];
+            H[3 + i][6 + j] = H[6 + j][3 + i] = a[k];
+            H[6 + i][0 + j] = H[0 + j][6 + i] = b[k];
+            H[3 + i][0 + j] = H[0 + j][3 + i] = -c[k];
+            H[6 + i][3 + j] = H[3 + j][6 + i] = -a[k];
+            H[0 + i][6 + j] = H[6 + j][0 + i] = -b[k];
+        }
+    }
+    return d;
+}
+
+/* contact_diff.cross (engine/contact_diff.py:27-129): |a x b|, gradient (6 entries), Hessian (6x6 block).
+ * The SymPy-generated Hessian of the reference is exact (Q16); restated as the algebraically
+ * equivalent closed form  H = (K_i . K_j)/c - (K_i . n)(K_j . n)/c,  plus the first-order term in n,
+ * with K_i = d(a x b)/dq_i and n = (a x b)/c. */
+static double cd_cross(const double *a, const double *b, double *G, double H[9][9])
+{
+    double cr[3];
+    v_cross(a, b, cr);
+    double c = v_norm(cr);
+    if (G) {
+        double n[3] = { cr[0] / c, cr[1] / c, cr[2] / c };
+        /* J[i][:] = d(a x b)/dq_i, q = (a0,a1,a2,b0,b1,b2) */
+        double J[6][3];
+        for (int i = 0; i < 3; i++) {
+            double e[3] = { 0, 0, 0 }; e[i] = 1;
+            v_cross(e, b, J[i]);
+            v_cross(a, e, J[3 + i]);
+        }
+        for (int i = 0; i < 6; i++) G[i] = v_dot(J[i], n);
+        G[6] = G[7] = G[8] = 0;
+        for (int i = 0; i < 6; i++)
+            for (int j = 0; j < 6; j++) {
+                double h = (v_dot(J[i], J[j]) - G[i] * G[j]) / c;
+                /* second derivative of (a x b) is non-zero only for mixed (a_i, b_j): e_i x e_j */
+                if (i < 3 && j >= 3) { double e1[3] = { 0, 0, 0 }, e2[3] = { 0, 0, 0 }, t[3]; e1[i] = 1; e2[j - 3] = 1; v_cross(e1, e2, t); h += v_dot(t, n); }
+                if (i >= 3 && j < 3) { double e1[3] = { 0, 0, 0 }, e2[3] = { 0, 0, 0 }, t[3]; e1[j] = 1; e2[i - 3] = 1; v_cross(e1, e2, t); h += v_dot(t, n); }
+                H[i][j] = h;
+            }
+    }
+    return c;
+}
+
+typedef struct {
+    int nc;
+    const int *idx; const double *w, *k, *mu, *dx0, *T, *n;
+    double k_contact, eps_contact, eps_v, h;
+} orc_contacts;
+
+/* friction kernels f0, f1, f2 (engine/BaseScene.py:453-478) */
+static double fr_f0(const orc_contacts *C, double x)
+{
+    double e = C->eps_v * C->h;
+    if (x > e) return x;
+    return -x / (3.0 * C->eps_v * C->eps_v) * x / (C->h * C->h) * x + x / e * x + e / 3.0;
+}
+static double fr_f1(const orc_contacts *C, double x)
+{
+    double e = C->eps_v * C->h;
+    if (x > e) return 1.0 / x;
+    return -x / (e * e) + 2.0 / e;
+}
+static double fr_f2(const orc_contacts *C, double x)
+{
+    double e = C->eps_v * C->h;
+    if (x > e) return -1.0 / (x * x);
+    return -1.0 / (e * e);
+}
+
+/* normal part of BaseScene.contact_energy (engine/BaseScene.py:490-543): returns 1 if active;
+ * e = energy, G[9] scaled gradient, H[9][9] Hessian (before projection) */
+static int contact_normal(const orc_contacts *C, const double *pos, int i, int diff, double *e, double *G, double H[9][9])
+{
+    const int *idx = C->idx + 4 * i;
+    double p1[3], p2[3], p[3];
+    v_sub(pos + 3 * idx[1], pos + 3 * idx[0], p1);
+    v_sub(pos + 3 * idx[2], pos + 3 * idx[0], p2);
+    v_sub(pos + 3 * idx[3], pos + 3 * idx[0], p);
+    double dG[9], cG[9], dH[9][9], cH[9][9];
+    memset(dH, 0, sizeof(dH)); memset(cH, 0, sizeof(cH));
+    double d = cd_det(p1, p2, p, diff ? dG : NULL, dH);
+    double c = cd_cross(p1, p2, diff ? cG : NULL, cH);
+    if (!(d / c < C->eps_contact)) return 0;
+    if (diff) {
+        for (int j = 0; j < 9; j++) G[j] = dG[j] / c - d * cG[j] / (c * c);
+        for (int j = 0; j < 9; j++)
+            for (int k = 0; k < 9; k++)
+                H[j][k] = dH[j][k] / c - dG[j] * cG[k] / (c * c) - dG[k] * cG[j] / (c * c) - d * cH[j][k] / (c * c)
+                        + 2 * d * cG[j] * cG[k] / (c * c * c);
+    }
+    d /= c;
+    *e = 0.5 * C->k_contact * (d - C->eps_contact) * (d - C->eps_contact);
+    double pe_pd = C->k_contact * (d - C->eps_contact);
+    if (diff) {
+        for (int j = 0; j < 9; j++)
+            for (int k = 0; k < 9; k++) H[j][k] = C->k_contact * G[j] * G[k] + pe_pd * H[j][k];
+        for (int j = 0; j < 9; j++) G[j] *= pe_pd;
+    }
+    return 1;
+}
+
+orc_contacts *orc_contacts_create(int nc, const int *idx, const double *w, const double *k, const double *mu,
+                                  const double *dx0, const double *T, const double *n,
+                                  double k_contact, double eps_contact, double eps_v, double h)
+{
+    orc_contacts *C = (orc_contacts *)calloc(1, sizeof(orc_contacts));
+    C->nc = nc; C->idx = idx; C->w = w; C->k = k; C->mu = mu; C->dx0 = dx0; C->T = T; C->n = n;
+    C->k_contact = k_contact; C->eps_contact = eps_contact; C->eps_v = eps_v; C->h = h;
+    return C;
+}
+void orc_contacts_destroy(orc_contacts *C) { free(C); }
+
+static void friction_u(const orc_contacts *C, const double *pos, int i, double *u, double *r)
+{
+    const int *idx = C->idx + 4 * i; const double *w = C->w + 3 * i, *T = C->T + 6 * i;
+    double dx[3];
+    for (int k = 0; k < 3; k++)
+        dx[k] = pos[3 * idx[3] + k] - (pos[3 * idx[0] + k] * w[0] + pos[3 * idx[1] + k] * w[1] + pos[3 * idx[2] + k] * w[2]) - C->dx0[3 * i + k];
+    u[0] = v_dot(T, dx); u[1] = v_dot(T + 3, dx);
+    *r = sqrt(u[0] * u[0] + u[1] * u[1]);
+}
+
+/* BaseScene.contact_energy(diff=False) (engine/BaseScene.py:487-598): returns the contact+friction energy */
+double orc_contact_energy(const orc_contacts *C, const double *pos)
+{
+    double E = 0;
+    for (int i = 0; i < C->nc; i++) {
+        double e;
+        if (contact_normal(C, pos, i, 0, &e, NULL, NULL)) E += e;
+    }
+    for (int i = 0; i < C->nc; i++) {
+        double u[2], r;
+        friction_u(C, pos, i, u, &r);
+        E += C->k[i] * fr_f0(C, r);
+    }
+    return E;
+}
+
+/* BaseScene.contact_energy(diff=True, spd) (engine/BaseScene.py:487-598): adds into F (masked by frozen,
+ * BaseScene.add_F :392-397) and into the matrix via add_H. */
+void orc_contact_grad_hess(const orc_contacts *C, const double *pos, const int *frozen, double *F, orc_mat *A, int spd)
+{
+    for (int i = 0; i < C->nc; i++) {
+        const int *idx = C->idx + 4 * i;
+        double e, G[9], H[9][9];
+        if (contact_normal(C, pos, i, 1, &e, G, H)) {
+            if (spd) orc_spd_project(&H[0][0], 9, 20);
+            for (int j = 0; j < 3; j++)
+                for (int k = 0; k < 3; k++) {
+                    double g = G[k * 3 + j];
+                    int r1 = idx[k + 1] * 3 + j, r0 = idx[0] * 3 + j;
+                    if (F) { if (!frozen[r1]) F[r1] += g; if (!frozen[r0]) F[r0] += -g; }
+                    if (A)
+                        for (int j2 = 0; j2 < 3; j2++)
+                            for (int k2 = 0; k2 < 3; k2++) {
+                                double h = H[k * 3 + j][k2 * 3 + j2];
+                                add_H(A, idx[k + 1] * 3 + j, idx[k2 + 1] * 3 + j2, h);
+                                add_H(A, idx[k + 1] * 3 + j, idx[0] * 3 + j2, -h);
+                                add_H(A, idx[0] * 3 + j, idx[k2 + 1] * 3 + j2, -h);
+                                add_H(A, idx[0] * 3 + j, idx[0] * 3 + j2, h);
+                            }
+                }
+        }
+    }
+    for (int i = 0; i < C->nc; i++) {
+        const int *idx = C->idx + 4 * i; const double *w = C->w + 3 * i, *T = C->T + 6 * i;
+        double k = C->k[i], u[2], r;
+        friction_u(C, pos, i, u, &r);
+        double f1 = fr_f1(C, r);
+        double g[2] = { u[0] * k * f1, u[1] * k * f1 };
+        double g1[3];
+        for (int q = 0; q < 3; q++) g1[q] = g[0] * T[q] + g[1] * T[3 + q];
+        double h[4] = { f1, 0, 0, f1 };
+        if (r > 1e-9) {
+            double f2 = fr_f2(C, r);
+            h[0] += f2 * (u[0] / r) * u[0]; h[1] += f2 * (u[0] / r) * u[1];
+            h[2] += f2 * (u[1] / r) * u[0]; h[3] += f2 * (u[1] / r) * u[1];
+        }
+        if (spd) orc_spd_project_2d(h);
+        double h1[3][3];
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++)
+                h1[a][b] = k * (T[a] * (h[0] * T[b] + h[1] * T[3 + b]) + T[3 + a] * (h[2] * T[b] + h[3] * T[3 + b]));
+        double w1[4] = { -w[0], -w[1], -w[2], 1 };
+        for (int i1 = 0; i1 < 4; i1++)
+            for (int j1 = 0; j1 < 3; j1++) {
+                int r_ = idx[i1] * 3 + j1;
+                if (F && !frozen[r_]) F[r_] += w1[i1] * g1[j1];
+            }
+        if (A)
+            for (int i1 = 0; i1 < 4; i1++)
+                for (int i2 = 0; i2 < 4; i2++)
+                    for (int j1 = 0; j1 < 3; j1++)
+                        for (int j2 = 0; j2 < 3; j2++)
+                            add_H(A, idx[i1] * 3 + j1, idx[i2] * 3 + j2, w1[i1] * w1[i2] * h1[j1][j2]);
+    }
+}
+
+/* BaseScene.contact_energy_backprop (engine/BaseScene.py:682-730): pos_grad_prev is pos_grad[step-1] [tot_NV][3] */
+void orc_contact_backprop(const orc_contacts *C, const double *pos, const double *p, double *pos_grad_prev)
+{
+    for (int i = 0; i < C->nc; i++) {
+        const int *idx = C->idx + 4 * i; const double *w = C->w + 3 * i, *T = C->T + 6 * i, *n_c = C->n + 3 * i;
+        double k = C->k[i], u[2], r;
+        friction_u(C, pos, i, u, &r);
+        double pressure = k / C->mu[i];
+        double f1 = fr_f1(C, r);
+        double g[2] = { u[0] * k * f1, u[1] * k * f1 };
+        double g1[3];
+        for (int q = 0; q < 3; q++) g1[q] = g[0] * T[q] + g[1] * T[3 + q];
+        double wa[4] = { w[0], w[1], w[2], -1 };
+        for (int i1 = 0; i1 < 4; i1++)
+            for (int j1 = 0; j1 < 3; j1++) {
+                double dfdp = wa[i1] * g1[j1] / pressure;
+                double zT = p[idx[i1] * 3 + j1];
+                for (int i2 = 0; i2 < 4; i2++)
+                    for (int j2 = 0; j2 < 3; j2++)
+                        pos_grad_prev[idx[i2] * 3 + j2] += zT * dfdp * wa[i2] * n_c[j2] * C->k_contact;
+            }
+        double h[4] = { f1, 0, 0, f1 };
+        if (r > 1e-9) {
+            double f2 = fr_f2(C, r);
+            h[0] += f2 * (u[0] / r) * u[0]; h[1] += f2 * (u[0] / r) * u[1];
+            h[2] += f2 * (u[1] / r) * u[0]; h[3] += f2 * (u[1] / r) * u[1];
+        }
+        double h1[3][3];
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++)
+                h1[a][b] = k * (T[a] * (h[0] * T[b] + h[1] * T[3 + b]) + T[3 + a] * (h[2] * T[b] + h[3] * T[3 + b]));
+        double w1[4] = { -w[0], -w[1], -w[2], 1 };
+        for (int i1 = 0; i1 < 4; i1++)
+            for (int i2 = 0; i2 < 4; i2++)
+                for (int j1 = 0; j1 < 3; j1++)
+                    for (int j2 = 0; j2 < 3; j2++) {
+                        double zT = p[idx[i1] * 3 + j1];
+                        pos_grad_prev[idx[i2] * 3 + j2] += zT * w1[i1] * w1[i2] * h1[j1][j2];
+                    }
+    }
+}
+
+/* per-vertex inertia + gravity energy for non-cloth (tet) bodies: Elastic.compute_energy vertex loops
+ * (engine/model_elastic_offset.py:316-323) with ext_force = 0 */
+double orc_vertex_energy(int v_start, int v_end, const double *pos, const double *prev_pos, const double *vel,
+                         const double *mass, const double *gravity, double dt)
+{
+    double U = 0;
+    for (int i = v_start; i < v_end; i++) {
+        const double *x = pos + 3 * i, *xp = prev_pos + 3 * i, *v = vel + 3 * i;
+        U += -mass[i] * v_dot(gravity, x);
+        double X[3] = { x[0] - xp[0] - v[0] * dt, x[1] - xp[1] - v[1] * dt, x[2] - xp[2] - v[2] * dt };
+        U += 0.5 * mass[i] * v_dot(X, X) / (dt * dt);
+    }
+    return U;
+}
+
+int orc_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
