@@ -124,3 +124,124 @@ def test_cloth_terms_match_reference(golden_dir, name):
     assert _rel(ref2, g["ref_angle_after_k0p02"]) < 1e-12
     assert np.abs(ref2 - ref).max() > 1e-3          # the plastic branch was exercised
     L.orc_cloth_destroy(c)
+
+
+# ----------------------------------------------------------------------------- scene level
+def _scene_from_golden(g):
+    N, M = int(g["cloth_N"]), int(g["cloth_M"])
+    off = int(g["table_offset"])
+    NFc = 2 * N * M
+    s = orc.OracleScene(N, M, float(g["cloth_dx"]), float(g["dt"]), g["pos0"][off:], g["faces"][NFc:] - off, g["mass"][off:],
+                        Kb=float(g["Kb"]), k_angle=float(g["k_angle"]), k_contact=float(g["k_contact"]),
+                        eps_contact=float(g["eps_contact"]), eps_v=float(g["eps_v"]), mu=float(g["mu"]))
+    s.pos[:] = g["pos0"]; s.prev_pos[:] = g["pos0"]; s.vel[:] = g["vel0"]; s.ref_angle[:] = g["ref_angle0"]
+    return s
+
+
+def _scene_override(s, pos):
+    """noise-sign override for the current cloth state (see noise_sign_override)"""
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(orc.__file__), "ti_emu"))
+    import taichi as ti_emu
+    p = pos[:s.NVc]
+    nd = np.zeros((s.NFc, 3))
+    for i in range(s.NFc):
+        a, b, c = (p[s.f2v[i, k]].view(ti_emu._Arr) for k in range(3))
+        nd[i] = (b - a).cross(c - b).normalized()      # Cloth.compute_normal_dir as the stand-in evaluates it
+    return noise_sign_override(s.f2v, s.cf, p, nd)
+
+
+def test_box_mesher_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "bouncing.npz"))
+    off = int(g["table_offset"]); NFc = 2 * int(g["cloth_N"]) * int(g["cloth_M"])
+    pos, tets, faces, mass = orc.box_mesh(0.07, 9, 9, 2, (-0.035, -0.035, -0.00875))
+    assert np.abs(pos - g["pos0"][off:]).max() < 1e-15
+    assert np.array_equal(tets, g["tet_vertices"])
+    assert np.array_equal(faces + off, g["faces"][NFc:])
+    assert _rel(mass, g["mass"][off:]) < 1e-12
+
+
+def test_scene_contact_query_and_first_newton_iterations(golden_dir):
+    g = np.load(os.path.join(golden_dir, "bouncing.npz"))
+    s = _scene_from_golden(g)
+    L = orc.lib()
+    frame = 1
+    s.prev_pos[:] = s.pos
+    s.calc_vn(); s.projection_query(); s.contact_analysis()
+    tv = slice(int(g["table_offset"]), None)
+    # vertex normals of surface vertices (interior tet vertices are 0/0 = NaN in both)
+    assert np.allclose(s.vn, g[f"f{frame}_vn"], rtol=0, atol=1e-12, equal_nan=True)
+    assert np.array_equal(s.proj_flag, g[f"f{frame}_proj_flag"])
+    assert np.array_equal(s.proj_dir, g[f"f{frame}_proj_dir"])
+    assert np.array_equal(s.proj_idx, g[f"f{frame}_proj_idx"])
+    assert np.abs(s.proj_w - g[f"f{frame}_proj_w"]).max() < 1e-12
+    nc = int(g[f"f{frame}_nc"])
+    assert s.nc == nc and nc > 0
+    # constraint SET is bit-exact; the reference's append order is nondeterministic, ours is by vertex
+    key = lambda a: sorted(map(tuple, a))
+    assert key(s.c_idx[:nc]) == key(g[f"f{frame}_const_idx"])
+    o1 = np.argsort(s.c_idx[:nc, 3]); o2 = np.argsort(g[f"f{frame}_const_idx"][:, 3])
+    for mine, k in ((s.c_w, "const_w"), (s.c_k, "const_k"), (s.c_mu, "const_mu"), (s.c_dx0, "const_dx0"), (s.c_T, "const_T"), (s.c_n, "const_n")):
+        assert _rel(mine[:nc][o1], g[f"f{frame}_{k}"][o2]) < 1e-10, k
+    s._build_pattern()
+    for it in (1, 2):
+        s.pos[:] = g[f"f{frame}_it{it}_pos"]
+        ov = _scene_override(s, s.pos)
+        L.orc_cloth_set_neg_override(s.cloth, ov.ctypes.data_as(C.c_char_p))
+        E0 = s.compute_energy()
+        assert abs(E0 - g[f"f{frame}_newton_log"][it - 1, 0]) <= 1e-12 * abs(E0)
+        s.compute_residual_and_hessian(spd=True)
+        assert _rel(s.F, g[f"f{frame}_it{it}_F"]) < 1e-10
+        import scipy.sparse as sp
+        Hg = sp.csr_matrix((g[f"f{frame}_it{it}_H_data"], g[f"f{frame}_it{it}_H_indices"], g[f"f{frame}_it{it}_H_indptr"]),
+                           shape=(3 * s.NV, 3 * s.NV))
+        D = (s.matrix() - Hg).tocoo()
+        assert np.abs(D.data).max() <= 1e-9 * np.abs(Hg.data).max()
+        p = s.solve(s.F)
+        assert _rel(p, g[f"f{frame}_it{it}_p"]) < 1e-7
+    L.orc_cloth_set_neg_override(s.cloth, None)
+
+
+def test_scene_rollout_positions_match_reference(golden_dir):
+    """Forward rollout with the oracle's own Newton path (canonical side-test rule, SuperLU): the converged
+    positions must agree with the reference's to the Newton tolerance (1e-7 * dt on the last step size)."""
+    g = np.load(os.path.join(golden_dir, "bouncing.npz"))
+    s = _scene_from_golden(g)
+    T = int(g["T"])
+    for frame in range(1, T):
+        log = []
+        s.time_step(log=log)
+        assert s.nc == int(g[f"f{frame}_nc"])
+        assert sorted(map(tuple, s.c_idx[:s.nc])) == sorted(map(tuple, g[f"f{frame}_const_idx"]))
+        err = np.abs(s.pos - g[f"f{frame}_pos"]).max()
+        assert err < 2e-9, (frame, err)           # both stop at |p|_inf < 5e-10 m with a linear rate < 0.5
+        assert np.abs(s.vel - g[f"f{frame}_vel"]).max() < 2e-9 / float(g["dt"]) * 1.01
+        assert np.abs(s.ref_angle - g[f"f{frame}_ref_angle"]).max() < 1e-6
+    assert abs(s.reward() - float(g["reward"])) < 1e-7
+
+
+def test_scene_adjoint_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "bouncing.npz"))
+    s = _scene_from_golden(g)
+    T = int(g["T"])
+    L = orc.lib()
+    gr = orc.OracleGrad(s, T)
+    gr.pos_buffer[:] = g["pos_buffer"]                       # reference trajectory: isolates the backward pass
+    gr.ref_angle_buffer[0] = g["ref_angle0"]
+    for f in range(1, T):
+        gr.ref_angle_buffer[f] = g[f"f{f}_ref_angle"]
+    gr.get_loss_table()
+    assert np.array_equal(gr.pos_grad, g["pos_grad_seed"])
+    for j in range(T - 1, 0, -1):
+        ov = _scene_override(s, gr.pos_buffer[j])
+        L.orc_cloth_set_neg_override(s.cloth, ov.ctypes.data_as(C.c_char_p))
+        gr.transfer_grad(j)
+        assert s.nc == int(g[f"b{j}_nc"])
+        assert sorted(map(tuple, s.c_idx[:s.nc])) == sorted(map(tuple, g[f"b{j}_const_idx"]))
+        assert _rel(gr.d_kb, g[f"b{j}_d_kb"]) < 1e-10
+        assert _rel(gr.z, g[f"b{j}_z"]) < 1e-8, j
+        assert _rel(gr.pos_grad, g[f"b{j}_pos_grad"]) < 1e-8, j
+        assert _rel(s.tmp_z_frozen, g[f"b{j}_tmp_z_frozen"]) < 1e-8
+        assert abs(gr.grad_kb - float(g[f"b{j}_grad_kb"])) <= 1e-8 * abs(float(g[f"b{j}_grad_kb"]))
+    L.orc_cloth_set_neg_override(s.cloth, None)
+    assert abs(gr.grad_kb - float(g["grad_kb"])) <= 1e-8 * abs(float(g["grad_kb"]))
