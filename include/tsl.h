@@ -1,0 +1,164 @@
+/*
+ * tsl.h -- C ABI of libtsl.so, the B200 (sm_100a) thin-shell implicit-step engine.
+ *
+ * The reference (Genesis-Embodied-AI/ThinShellLab) has no FFI: its boundary is the Python object API
+ * of code/engine/BaseScene.py + code/engine/analytic_grad_system.py as driven by
+ * code/training/trajopt_*.py.  Each entry point below names the reference method(s) it replaces.
+ * All functions return 0 on success and a negative tsl_status otherwise; tsl_last_error() gives text.
+ * Pointers named *_dev are CUDA device pointers owned by the caller (torch tensors); *_host are host
+ * pointers.  All work is enqueued on the stream given to tsl_set_stream (default: legacy stream 0).
+ * One context per GPU / rank; a context is not re-entrant.
+ */
+#ifndef TSL_H
+#define TSL_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct tsl_ctx tsl_ctx;
+
+enum tsl_status {
+    TSL_OK = 0,
+    TSL_ERR_INVALID = -1,       /* bad argument / call order */
+    TSL_ERR_CUDA = -2,          /* a CUDA call failed */
+    TSL_ERR_CAPACITY = -3,      /* max_n_constraints or grid capacity exceeded */
+    TSL_ERR_UNSUPPORTED = -4,   /* configuration outside what this build implements (never silently wrong) */
+    TSL_ERR_NUMERIC = -5        /* NaN / breakdown */
+};
+
+/* scene constants: BaseScene.__init__ / Scene_*.init_scene_parameters
+ * (code/engine/BaseScene.py:31-53, code/task_scene/Scene_bouncing.py:37-53) */
+typedef struct tsl_config {
+    int struct_size;            /* = sizeof(tsl_config), ABI check */
+    int n_verts;                /* tot_NV */
+    double dt;                  /* self.dt == self.h */
+    double k_contact, eps_contact, eps_v;
+    double damping;             /* BaseScene.damping (velocity update) */
+    double gravity[3];
+    int max_n_constraints;      /* BaseScene.max_n_constraints */
+    double grid_h;              /* geometry.grid_h   (code/engine/geometry.py:8), reference value 0.003 */
+    int grid_n;                 /* geometry.grid_n   (:9), reference value 132 */
+} tsl_config;
+
+typedef struct tsl_step_stats {
+    int newton_iters;           /* Newton iterations taken                      */
+    int linear_iters;           /* total Krylov iterations                      */
+    int linesearch_evals;       /* energy evaluations inside the line searches  */
+    int n_contacts;             /* nc after contact_analysis                    */
+    int converged;              /* 1 if delta < tol                             */
+    int flags;                  /* bit0: negative curvature met in PCG; bit1: Krylov hit its cap */
+    double delta;               /* last |p|_inf / h  (BaseScene.newton_step return value) */
+    double energy;              /* E at the accepted point                      */
+    double ms_contact, ms_assembly, ms_solve, ms_linesearch; /* host wall clock per phase (diagnostic) */
+} tsl_step_stats;
+
+typedef struct tsl_solve_stats {
+    int iters;
+    int flags;                  /* as tsl_step_stats.flags */
+    double rel_residual;        /* |b - A x|_2 / |b|_2 as tracked by the recurrence */
+} tsl_solve_stats;
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int tsl_create(const tsl_config *cfg, tsl_ctx **out);
+int tsl_destroy(tsl_ctx *ctx);
+const char *tsl_last_error(tsl_ctx *ctx);
+const char *tsl_version(void);
+int tsl_set_stream(tsl_ctx *ctx, void *cuda_stream);
+
+/* ---- scene description (cold path) --------------------------------------------------------- */
+/* Cloth(N, dt, Len, tot_NV, rho, offset, is_square, M) + Cloth.init_mesh
+ * (code/engine/model_fold_offset.py:11-106, 929-1018).  Returns the cloth id (>= 0).
+ * ref_angle_dev: [2*N*M][3] f64 plastic rest angles, owned by the caller (Cloth.ref_angle). */
+int tsl_add_cloth(tsl_ctx *ctx, int N, int M, int v_offset, double dx, double rho,
+                  double Kl, double Ka, double Kb, double k_angle, double *ref_angle_dev);
+/* Cloth.Kl/Ka/Kb/k_angle[None] = ...  (scripts set sys.cloths[0].Kb[None], trajopt_bouncing.py:46) */
+int tsl_set_cloth_params(tsl_ctx *ctx, int cloth, double Kl, double Ka, double Kb, double k_angle);
+/* topology read-back for tests / renderers: Cloth.f2v, counter_face, counter_point ([2NM][3] i32, host) */
+int tsl_get_cloth_topology(tsl_ctx *ctx, int cloth, int *f2v_host, int *counter_face_host, int *counter_point_host);
+
+/* BaseScene.faces + body_list (code/engine/BaseScene.py:81,91-99, init_faces :355-359):
+ * faces_host [tot_nf][3] global vertex ids, bodies_host [n_bodies][4] = v_start, v_end, f_start, f_end. */
+int tsl_set_surfaces(tsl_ctx *ctx, const int *faces_host, int tot_nf, const int *bodies_host, int n_bodies);
+/* one contact_pair_analysis(b_idx, v_start, v_end, mu) line of a scene's contact_analysis()
+ * (code/task_scene/Scene_bouncing.py:91-96, code/engine/BaseScene.py:778-816) */
+int tsl_add_contact_pair(tsl_ctx *ctx, int surface_body, int v_start, int v_end, double mu);
+int tsl_set_contact_mu(tsl_ctx *ctx, int pair, double mu);   /* sys.mu_cloth_elastic[None] = ... */
+
+/* BaseScene.pos / prev_pos / vel ([n_verts][3] f64), mass [n_verts] f64, frozen [3 n_verts] i32,
+ * border_flag [n_verts] i32 (may be NULL = all zero): borrowed device pointers */
+int tsl_bind_state(tsl_ctx *ctx, double *pos_dev, double *prev_pos_dev, double *vel_dev,
+                   const double *mass_dev, const int *frozen_dev, const int *border_flag_dev);
+/* builds the block-sparse pattern and scratch; call once after the scene is described */
+int tsl_finalize(tsl_ctx *ctx);
+/* BaseScene.reset(): proj_flag.fill(0) (code/engine/BaseScene.py:268) -- sticky contact sides */
+int tsl_reset_contact_state(tsl_ctx *ctx);
+
+/* ---- hot path -------------------------------------------------------------------------------- */
+/* BaseScene.calc_vn + geometry.projection_query + Scene.contact_analysis
+ * (code/engine/BaseScene.py:837-850, code/engine/geometry.py:223-229, Scene_bouncing.py:91-96).
+ * Uses the bound pos / prev_pos.  n_contacts_out may be NULL. */
+int tsl_contact_detect(tsl_ctx *ctx, int *n_contacts_out);
+/* BaseScene.compute_energy (code/engine/BaseScene.py:427-451) at the bound pos */
+int tsl_energy(tsl_ctx *ctx, double *energy_out);
+/* BaseScene.compute_residual_and_Hessian(spd) / compute_Hessian(spd) (code/engine/BaseScene.py:976-1052).
+ * flags: bit0 residual into F, bit1 Hessian, bit2 spd projection (forward), bit3 symmetrise element
+ * blocks (forward PCG matrix), bit4 store Hessian in fp64 (adjoint) instead of fp32. */
+#define TSL_ASM_RESIDUAL 1
+#define TSL_ASM_HESSIAN 2
+#define TSL_ASM_SPD 4
+#define TSL_ASM_SYM 8
+#define TSL_ASM_F64 16
+int tsl_assemble(tsl_ctx *ctx, int flags);
+/* SparseMatrix.solve (code/engine/sparse_solver.py:85-105): x = H^-1 b with the last assembled Hessian.
+ * fp32 Hessian: block-Jacobi PCG (fp32 vectors, fp64 reductions); fp64 Hessian: block-Jacobi BiCGStab (fp64).
+ * rhs_dev / x_dev: [3 n_verts] f64 device. */
+int tsl_solve(tsl_ctx *ctx, const double *rhs_dev, double *x_dev, double rel_tol, int max_iters, tsl_solve_stats *stats);
+/* BaseScene.time_step(f_contact, frame) with Scene_bouncing.timestep_finish
+ * (code/engine/BaseScene.py:1327-1370, code/task_scene/Scene_bouncing.py:115-119) */
+int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *stats);
+/* same, end to end from HOST buffers: copies pos/vel host->device into the bound tensors, steps,
+ * copies pos/vel back (the reference's Field.from_numpy / to_numpy around time_step) */
+int tsl_step_forward_host(tsl_ctx *ctx, double *pos_host, double *vel_host, int max_newton, double tol, tsl_step_stats *stats);
+
+/* analytic_grad_system.Grad.transfer_grad(step, sys, f_contact) (code/engine/analytic_grad_system.py:115-160)
+ * for one step t.  Device pointers, f64:
+ *   x_t, x_tm1            [n_verts][3]  pos_buffer[t], pos_buffer[t-1]
+ *   ref_angle_tm1         [NF][3]       ref_angle_buffer[t-1] (cloth 0)
+ *   pos_grad_t/tm1/tm2    [n_verts][3]  pos_grad[t] (clamped + updated in place), pos_grad[t-1], pos_grad[t-2] (NULL if t < 2)
+ *   angleref_grad_t/tm1   [NF][3]
+ *   grad_kb_accum_dev     [1]           += sum_free z * d_kb   (Grad.get_parameters_grad :69-79)
+ *   z_out_dev             [3 n_verts]   adjoint solution (may be NULL)
+ * clamp: +-1 (system-ID Grad, :104-108) or +-1000 (trajectory Grad). */
+int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, const double *ref_angle_tm1,
+                      double *pos_grad_t, double *pos_grad_tm1, double *pos_grad_tm2,
+                      const double *angleref_grad_t, double *angleref_grad_tm1,
+                      double *grad_kb_accum_dev, double *z_out_dev, double clamp, double rel_tol, int max_iters,
+                      tsl_solve_stats *stats);
+
+/* ---- introspection used by the parity tests and the benchmark ---------------------------------- */
+int tsl_get_residual(tsl_ctx *ctx, double *F_host);                     /* BaseScene.F [3 n_verts] */
+int tsl_get_matrix_nnzb(tsl_ctx *ctx, int *nnzb_out);                   /* number of 3x3 blocks (unpadded) */
+/* last assembled Hessian as block-CSR on the host: rowptr [n_verts+1], colidx [nnzb], val [nnzb][3][3] f64 */
+int tsl_get_matrix(tsl_ctx *ctx, int *rowptr_host, int *colidx_host, double *val_host);
+/* contact candidates / constraints: proj_* rows of one surface body; const_* of the current set */
+int tsl_get_projection(tsl_ctx *ctx, int surface_body, int *flag_host, int *dir_host, int *idx_host, double *w_host);
+int tsl_get_constraints(tsl_ctx *ctx, int *n_out, int *idx_host, double *w_host, double *k_host, double *dx0_host,
+                        double *T_host, double *n_host);
+/* dimensions of the solver, for roofline arithmetic */
+typedef struct tsl_sizes {
+    int n_verts, n_tris, n_hinges, nnzb, nnzb_padded, n_contacts;
+    long long bytes_matrix_f32, bytes_matrix_f64;
+} tsl_sizes;
+int tsl_get_sizes(tsl_ctx *ctx, tsl_sizes *out);
+/* benchmark hooks: run `iters` PCG iterations (no convergence test) on the last fp32 Hessian, and time
+ * one kernel class with CUDA events on the context's stream; ms_out = average per launch.
+ * what: 0 = PCG iteration (SpMV + 2 vector kernels), 1 = SpMV only, 2 = energy, 3 = residual, 4 = Hessian */
+int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out);
+/* number of kernels this library has launched since creation (bench.py's gpu_launches) */
+long long tsl_launch_count(tsl_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSL_H */

@@ -846,8 +846,11 @@ static int pt2tri(const double *x, const double *p1, const double *p2, const dou
 }
 
 /* geometry.grid_idx (engine/geometry.py:89-94) with the module constants of :8-10 */
-#define GRID_H 0.003
-static int grid_n_(void) { return (int)floor(0.2 / GRID_H) * 2; }
+static double GRID_H = 0.003;
+static int GRID_N = 0;   /* 0: the reference's int(0.2 // grid_h) * 2 = 132 */
+/* capacity override for sheets larger than the reference's hard-coded +-0.1965 m grid (same cell size) */
+void orc_set_grid(double h, int n) { GRID_H = h; GRID_N = n; }
+static int grid_n_(void) { return GRID_N > 0 ? GRID_N : (int)floor(0.2 / GRID_H) * 2; }
 static void grid_idx(const double *x, int *o)
 {
     int gn = grid_n_();

@@ -148,8 +148,9 @@ class OracleScene:
 
     def __init__(self, N, M, dx, dt, table_pos, table_faces, table_mass, *, rho=40.0, Kl=1000.0, Ka=1000.0,
                  Kb=100.0, k_angle=3.14, k_contact=40000.0, eps_contact=4e-4, eps_v=0.01, mu=0.5,
-                 damping=1.0, gravity=(0.0, 0.0, -9.8), max_n_constraints=10000, extra_frozen_vertices=()):
+                 damping=1.0, gravity=(0.0, 0.0, -9.8), max_n_constraints=10000, extra_frozen_vertices=(), grid_h=0.003, grid_n=0):
         L = lib()
+        self.grid = (grid_h, grid_n)
         self.N, self.M, self.dx, self.dt = N, M, dx, dt
         self.NVc = (N + 1) * (M + 1)
         self.NFc = 2 * N * M
@@ -238,6 +239,7 @@ class OracleScene:
 
     def projection_query(self):
         L = lib()
+        L.orc_set_grid(_f(self.grid[0]), int(self.grid[1]))
         for b, (fs, fe) in enumerate(self.body_f):
             for b2, (vs, ve) in enumerate(self.body_v):
                 if b2 != b:

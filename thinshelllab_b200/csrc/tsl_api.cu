@@ -1,0 +1,630 @@
+// tsl_api.cu -- the C ABI of libtsl.so (see include/tsl.h): scene description, pattern construction and the
+// Newton / adjoint drivers that sequence the kernels of tsl_physics.cu, tsl_contact.cu and tsl_linalg.cu.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+
+#include "tsl_internal.cuh"
+#include "tsl_kernels.cuh"
+
+using namespace tsl;
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return TSL_ERR_CUDA; } } while (0)
+#define REQUIRE(c, msg) do { if (!(c)) { ctx->err = (msg); return TSL_ERR_INVALID; } } while (0)
+#define TRY(x) do { int r_ = (x); if (r_ != TSL_OK) return r_; } while (0)
+
+static double now_ms()
+{
+    using namespace std::chrono;
+    return duration<double, std::milli>(steady_clock::now().time_since_epoch()).count();
+}
+
+template <typename T>
+static int upload(tsl_ctx *ctx, T **dst, const std::vector<T> &src)
+{
+    CK(cudaMalloc(dst, sizeof(T) * std::max<size_t>(src.size(), 1)));
+    if (!src.empty()) CK(cudaMemcpy(*dst, src.data(), sizeof(T) * src.size(), cudaMemcpyHostToDevice));
+    return TSL_OK;
+}
+
+extern "C" {
+
+const char *tsl_version(void) { return "thinshelllab_b200 libtsl 0.1 (sm_100a)"; }
+
+int tsl_create(const tsl_config *cfg, tsl_ctx **out)
+{
+    if (!cfg || !out || cfg->struct_size != (int)sizeof(tsl_config)) return TSL_ERR_INVALID;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return TSL_ERR_CUDA;   // no CPU fallback: fail loudly
+    tsl_ctx *ctx = new tsl_ctx();
+    ctx->cfg = *cfg;
+    if (ctx->cfg.grid_h <= 0) ctx->cfg.grid_h = 0.003;
+    if (ctx->cfg.grid_n <= 0) ctx->cfg.grid_n = 132;
+    *out = ctx;
+    return TSL_OK;
+}
+
+int tsl_destroy(tsl_ctx *ctx)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    // device memory is released with the process / context; explicit frees for the large arrays
+    cudaFree(ctx->A.val32); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
+    cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q);
+    for (int i = 0; i < 8; i++) cudaFree(ctx->bi[i]);
+    cudaFree(ctx->minv32); cudaFree(ctx->minv64); cudaFree(ctx->F); cudaFree(ctx->sol); cudaFree(ctx->x1);
+    for (auto &c : ctx->cloths) {
+        cudaFree(c.f2v); cudaFree(c.cf); cudaFree(c.cp); cudaFree(c.side_deg); cudaFree(c.hinge_face); cudaFree(c.hinge_l);
+        cudaFree(c.tri_slot); cudaFree(c.hinge_slot); cudaFree(c.norm_dir); cudaFree(c.q1);
+    }
+    cudaFree(ctx->faces); cudaFree(ctx->vn); cudaFree(ctx->proj_flag); cudaFree(ctx->proj_dir); cudaFree(ctx->proj_idx); cudaFree(ctx->proj_w);
+    cudaFree(ctx->cell_key); cudaFree(ctx->cell_key_sorted); cudaFree(ctx->face_id); cudaFree(ctx->face_id_sorted); cudaFree(ctx->cub_tmp);
+    cudaFree(ctx->cflag); cudaFree(ctx->cscan);
+    cudaFree(ctx->con.idx); cudaFree(ctx->con.w); cudaFree(ctx->con.k); cudaFree(ctx->con.mu); cudaFree(ctx->con.dx0); cudaFree(ctx->con.T); cudaFree(ctx->con.n);
+    cudaFree(ctx->ks); cudaFreeHost(ctx->ks_host); cudaFree(ctx->red_partial); cudaFree(ctx->red_ticket); cudaFree(ctx->red_out); cudaFreeHost(ctx->red_host);
+    cudaFree(ctx->d_kb); cudaFree(ctx->adj_rhs); cudaFree(ctx->adj_z); cudaFree(ctx->error_flag); cudaFree(ctx->zero_border);
+    delete ctx;
+    return TSL_OK;
+}
+
+const char *tsl_last_error(tsl_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+int tsl_set_stream(tsl_ctx *ctx, void *s) { if (!ctx) return TSL_ERR_INVALID; ctx->stream = (cudaStream_t)s; return TSL_OK; }
+long long tsl_launch_count(tsl_ctx *ctx) { return ctx ? ctx->launches : -1; }
+
+// ---------------------------------------------------------------------------------------------- scene description
+// Cloth.init_mesh (code/engine/model_fold_offset.py:929-1018): alternating-diagonal grid, neighbour tables with the
+// reference's wiring (including the entries it never writes, which stay 0 -- quirk Q2).
+static void build_cloth_mesh(int N, int M, std::vector<int> &f2v, std::vector<int> &cf, std::vector<int> &cp)
+{
+    int NF = 2 * N * M;
+    f2v.assign(3 * NF, 0); cf.assign(3 * NF, 0); cp.assign(3 * NF, 0);
+    auto F = [&](int f, int l) -> int & { return f2v[3 * f + l]; };
+    auto CF = [&](int f, int l) -> int & { return cf[3 * f + l]; };
+    auto CP = [&](int f, int l) -> int & { return cp[3 * f + l]; };
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < M; j++) {
+            int k = (i * M + j) * 2;
+            int a = i * (M + 1) + j, b = a + 1, c = a + M + 2, d = a + M + 1;
+            int up = ((i - 1) * M + j) * 2 + 1, down = ((i + 1) * M + j) * 2;
+            bool even = ((i + j) % 2 == 0);
+            if (even) { F(k, 0) = c; F(k, 1) = b; F(k, 2) = a; F(k + 1, 0) = a; F(k + 1, 1) = d; F(k + 1, 2) = c; }
+            else { F(k, 0) = b; F(k, 1) = a; F(k, 2) = d; F(k + 1, 0) = d; F(k + 1, 1) = c; F(k + 1, 2) = b; }
+            // (face, slot) <- (neighbour, opposite slot) in the reference's assignment order
+            struct W { int f, l, nb, op; bool ok; };
+            W even_w[4] = { { k, 0, up, 2, i > 0 }, { k, 2, k + 2, 0, j < M - 1 }, { k + 1, 0, down, 2, i < N - 1 }, { k + 1, 2, k - 2, 0, j > 0 } };
+            W odd_w[4] = { { k, 2, up, 0, i > 0 }, { k + 1, 0, k + 3, 2, j < M - 1 }, { k + 1, 2, down, 0, i < N - 1 }, { k, 2, k - 2, 2, j > 0 } };
+            const W *ws = even ? even_w : odd_w;
+            for (int q = 0; q < 4; q++) {
+                const W &w = ws[q];
+                if (w.ok) { CF(w.f, w.l) = w.nb; CP(w.f, w.l) = w.op; }
+                else CF(w.f, w.l) = -1;
+            }
+            CF(k, 1) = k + 1; CP(k, 1) = 1; CF(k + 1, 1) = k; CP(k + 1, 1) = 1;
+        }
+}
+
+int tsl_add_cloth(tsl_ctx *ctx, int N, int M, int v_offset, double dx, double rho, double Kl, double Ka, double Kb, double k_angle,
+                  double *ref_angle_dev)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(!ctx->finalized, "tsl_add_cloth after tsl_finalize");
+    REQUIRE(N >= 1 && M >= 1 && 2 * N * M >= 3 && ref_angle_dev, "tsl_add_cloth: bad arguments");
+    REQUIRE(ctx->cloths.empty(), "this build supports one cloth body per context");
+    ClothDev c;
+    memset(&c, 0, sizeof(c));
+    c.N = N; c.M = M; c.NV = (N + 1) * (M + 1); c.NF = 2 * N * M; c.offset = v_offset;
+    REQUIRE(v_offset >= 0 && v_offset + c.NV <= ctx->cfg.n_verts, "tsl_add_cloth: vertex range outside n_verts");
+    c.P.dx = dx; c.P.dt = ctx->cfg.dt; c.P.mass = rho * dx * dx; c.P.Kl = Kl; c.P.Ka = Ka; c.P.Kb = Kb; c.P.k_angle = k_angle;
+    c.ref_angle = ref_angle_dev;
+    std::vector<int> f2v, cf, cp;
+    build_cloth_mesh(N, M, f2v, cf, cp);
+    // hinges: (face, slot) whose neighbour has the larger index (model_fold_offset.py:217 and everywhere else)
+    std::vector<int> hf, hl;
+    std::vector<unsigned char> deg(c.NF, 0);
+    for (int i = 0; i < c.NF; i++)
+        for (int l = 0; l < 3; l++) {
+            int i2 = cf[3 * i + l];
+            if (i2 > i) { hf.push_back(i); hl.push_back(l); }
+            if (i2 != -1) {
+                // side test of compute_angle / judge_angle uses vertices f2v[i][(l+1)%2], f2v[i][l]; if both lie in face i2
+                // the test is exactly 0 in exact arithmetic
+                int va = f2v[3 * i + (l + 1) % 2], vb = f2v[3 * i + l];
+                bool ina = false, inb = false;
+                for (int q = 0; q < 3; q++) { ina |= f2v[3 * i2 + q] == va; inb |= f2v[3 * i2 + q] == vb; }
+                if (ina && inb) deg[i] |= (unsigned char)(1u << l);
+            }
+        }
+    c.NH = (int)hf.size();
+    TRY(upload(ctx, &c.f2v, f2v)); TRY(upload(ctx, &c.cf, cf)); TRY(upload(ctx, &c.cp, cp));
+    TRY(upload(ctx, &c.side_deg, deg)); TRY(upload(ctx, &c.hinge_face, hf)); TRY(upload(ctx, &c.hinge_l, hl));
+    CK(cudaMalloc(&c.norm_dir, sizeof(double) * 3 * c.NF));
+    CK(cudaMalloc(&c.q1, sizeof(double) * 90));
+    CK(cudaMemset(c.q1, 0, sizeof(double) * 90));
+    ctx->cloths.push_back(c);
+    ctx->h_f2v.push_back(f2v); ctx->h_cf.push_back(cf); ctx->h_cp.push_back(cp);
+    return (int)ctx->cloths.size() - 1;
+}
+
+int tsl_set_cloth_params(tsl_ctx *ctx, int cloth, double Kl, double Ka, double Kb, double k_angle)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(cloth >= 0 && cloth < (int)ctx->cloths.size(), "bad cloth id");
+    ClothDev &c = ctx->cloths[cloth];
+    c.P.Kl = Kl; c.P.Ka = Ka; c.P.Kb = Kb; c.P.k_angle = k_angle;
+    return TSL_OK;
+}
+
+int tsl_get_cloth_topology(tsl_ctx *ctx, int cloth, int *f2v, int *cf, int *cp)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(cloth >= 0 && cloth < (int)ctx->cloths.size(), "bad cloth id");
+    size_t n = ctx->h_f2v[cloth].size() * sizeof(int);
+    if (f2v) memcpy(f2v, ctx->h_f2v[cloth].data(), n);
+    if (cf) memcpy(cf, ctx->h_cf[cloth].data(), n);
+    if (cp) memcpy(cp, ctx->h_cp[cloth].data(), n);
+    return TSL_OK;
+}
+
+int tsl_set_surfaces(tsl_ctx *ctx, const int *faces_host, int tot_nf, const int *bodies_host, int n_bodies)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(!ctx->finalized, "tsl_set_surfaces after tsl_finalize");
+    REQUIRE(faces_host && bodies_host && tot_nf > 0 && n_bodies > 0, "tsl_set_surfaces: bad arguments");
+    ctx->tot_nf = tot_nf;
+    CK(cudaMalloc(&ctx->faces, sizeof(int) * 3 * tot_nf));
+    CK(cudaMemcpy(ctx->faces, faces_host, sizeof(int) * 3 * tot_nf, cudaMemcpyHostToDevice));
+    ctx->bodies.clear();
+    for (int b = 0; b < n_bodies; b++) {
+        SurfaceBody sb = { bodies_host[4 * b], bodies_host[4 * b + 1], bodies_host[4 * b + 2], bodies_host[4 * b + 3] };
+        REQUIRE(sb.f_start >= 0 && sb.f_end <= tot_nf && sb.v_start >= 0 && sb.v_end <= ctx->cfg.n_verts, "tsl_set_surfaces: body range");
+        ctx->bodies.push_back(sb);
+    }
+    return TSL_OK;
+}
+
+int tsl_add_contact_pair(tsl_ctx *ctx, int surface_body, int v_start, int v_end, double mu)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(surface_body >= 0 && surface_body < (int)ctx->bodies.size(), "tsl_add_contact_pair: bad body");
+    REQUIRE(v_start >= 0 && v_end <= ctx->cfg.n_verts && v_start <= v_end, "tsl_add_contact_pair: bad range");
+    ContactPair p = { surface_body, v_start, v_end, mu };
+    ctx->pairs.push_back(p);
+    return (int)ctx->pairs.size() - 1;
+}
+int tsl_set_contact_mu(tsl_ctx *ctx, int pair, double mu)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(pair >= 0 && pair < (int)ctx->pairs.size(), "bad pair id");
+    ctx->pairs[pair].mu = mu;
+    return TSL_OK;
+}
+
+int tsl_bind_state(tsl_ctx *ctx, double *pos, double *prev_pos, double *vel, const double *mass, const int *frozen, const int *border_flag)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(pos && prev_pos && vel && mass && frozen, "tsl_bind_state: null pointer");
+    ctx->pos = pos; ctx->prev_pos = prev_pos; ctx->vel = vel; ctx->mass = mass; ctx->frozen = frozen;
+    if (border_flag) ctx->border_flag = border_flag;
+    else {
+        if (!ctx->zero_border) {
+            CK(cudaMalloc(&ctx->zero_border, sizeof(int) * ctx->cfg.n_verts));
+            CK(cudaMemset(ctx->zero_border, 0, sizeof(int) * ctx->cfg.n_verts));
+        }
+        ctx->border_flag = ctx->zero_border;
+    }
+    return TSL_OK;
+}
+
+// Block pattern = vertex adjacency through triangles and hinges + the diagonal (contacts against frozen bodies only
+// touch the diagonal).  Built once on the host, laid out as sliced ELL (see SellMatrix).
+int tsl_finalize(tsl_ctx *ctx)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(!ctx->finalized, "tsl_finalize called twice");
+    REQUIRE(ctx->pos, "tsl_finalize before tsl_bind_state");
+    int nv = ctx->cfg.n_verts;
+    SellMatrix &A = ctx->A;
+    // ---- adjacency lists
+    std::vector<int> cnt(nv + 1, 0);
+    auto for_each_pair = [&](auto &&fn) {
+        for (size_t ci = 0; ci < ctx->cloths.size(); ci++) {
+            const ClothDev &c = ctx->cloths[ci];
+            const std::vector<int> &f2v = ctx->h_f2v[ci], &cf = ctx->h_cf[ci], &cp = ctx->h_cp[ci];
+            for (int i = 0; i < c.NF; i++) {
+                int v[3] = { f2v[3 * i] + c.offset, f2v[3 * i + 1] + c.offset, f2v[3 * i + 2] + c.offset };
+                for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) fn(v[a], v[b]);
+                for (int l = 0; l < 3; l++) {
+                    int i2 = cf[3 * i + l];
+                    if (i2 > i) {
+                        int h[4] = { v[l], v[(l + 1) % 3], v[(l + 2) % 3], f2v[3 * i2 + cp[3 * i + l]] + c.offset };
+                        for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) fn(h[a], h[b]);
+                    }
+                }
+            }
+        }
+        for (int v = 0; v < nv; v++) fn(v, v);
+    };
+    for_each_pair([&](int r, int) { cnt[r + 1]++; });
+    std::vector<long long> start(nv + 1, 0);
+    for (int v = 0; v < nv; v++) start[v + 1] = start[v] + cnt[v + 1];
+    std::vector<int> cols((size_t)start[nv]);
+    std::vector<long long> fill(start.begin(), start.end() - 1);
+    for_each_pair([&](int r, int c) { cols[(size_t)fill[r]++] = c; });
+    A.h_rowptr.assign(nv + 1, 0);
+    A.h_colidx.clear();
+    A.h_colidx.reserve((size_t)nv * 12);
+    for (int v = 0; v < nv; v++) {
+        auto b = cols.begin() + start[v], e = cols.begin() + start[v + 1];
+        std::sort(b, e);
+        e = std::unique(b, e);
+        A.h_colidx.insert(A.h_colidx.end(), b, e);
+        A.h_rowptr[v + 1] = (int)A.h_colidx.size();
+    }
+    std::vector<int>().swap(cols);
+    A.n_rows = nv;
+    A.nnzb = (int)A.h_colidx.size();
+    A.n_slices = (nv + 31) / 32;
+    // ---- sliced ELL
+    A.h_slice_base.assign(A.n_slices + 1, 0);
+    for (int S = 0; S < A.n_slices; S++) {
+        int w = 0;
+        for (int r = 32 * S; r < std::min(nv, 32 * S + 32); r++) w = std::max(w, A.h_rowptr[r + 1] - A.h_rowptr[r]);
+        long long nb = (long long)A.h_slice_base[S] + 32LL * w;
+        REQUIRE(nb < (1LL << 31) - 64, "matrix too large for 32-bit block ids");
+        A.h_slice_base[S + 1] = (int)nb;
+    }
+    A.nnzb_pad = A.h_slice_base[A.n_slices];
+    A.h_colidx_pad.assign((size_t)A.nnzb_pad, 0);
+    std::vector<int> diag(nv, -1);
+    for (int S = 0; S < A.n_slices; S++) {
+        int w = (A.h_slice_base[S + 1] - A.h_slice_base[S]) / 32;
+        for (int lane = 0; lane < 32; lane++) {
+            int r = 32 * S + lane;
+            for (int k = 0; k < w; k++) {
+                int pb = A.h_slice_base[S] + k * 32 + lane;
+                int col = (r < nv) ? r : 0;                       // padding: valid column, zero value
+                if (r < nv && k < A.h_rowptr[r + 1] - A.h_rowptr[r]) col = A.h_colidx[A.h_rowptr[r] + k];
+                A.h_colidx_pad[pb] = col;
+                if (r < nv && col == r && diag[r] < 0 && k < A.h_rowptr[r + 1] - A.h_rowptr[r]) diag[r] = pb;
+            }
+        }
+    }
+    auto slot_of = [&](int r, int c) -> int {
+        const int *b = A.h_colidx.data() + A.h_rowptr[r], *e = A.h_colidx.data() + A.h_rowptr[r + 1];
+        const int *it = std::lower_bound(b, e, c);
+        int k = (int)(it - b);
+        return A.h_slice_base[r >> 5] + k * 32 + (r & 31);
+    };
+    for (size_t ci = 0; ci < ctx->cloths.size(); ci++) {
+        ClothDev &c = ctx->cloths[ci];
+        const std::vector<int> &f2v = ctx->h_f2v[ci], &cf = ctx->h_cf[ci], &cp = ctx->h_cp[ci];
+        std::vector<int> ts((size_t)c.NF * 9), hs((size_t)c.NH * 16);
+        int h = 0;
+        for (int i = 0; i < c.NF; i++) {
+            int v[3] = { f2v[3 * i] + c.offset, f2v[3 * i + 1] + c.offset, f2v[3 * i + 2] + c.offset };
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) ts[(size_t)i * 9 + a * 3 + b] = slot_of(v[a], v[b]);
+            for (int l = 0; l < 3; l++) {
+                int i2 = cf[3 * i + l];
+                if (i2 > i) {
+                    int hv[4] = { v[l], v[(l + 1) % 3], v[(l + 2) % 3], f2v[3 * i2 + cp[3 * i + l]] + c.offset };
+                    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) hs[(size_t)h * 16 + a * 4 + b] = slot_of(hv[a], hv[b]);
+                    h++;
+                }
+            }
+        }
+        TRY(upload(ctx, &c.tri_slot, ts)); TRY(upload(ctx, &c.hinge_slot, hs));
+    }
+    TRY(upload(ctx, &A.slice_base, A.h_slice_base));
+    TRY(upload(ctx, &A.colidx, A.h_colidx_pad));
+    TRY(upload(ctx, &A.diag_pb, diag));
+    CK(cudaMalloc(&A.val32, sizeof(float) * 9 * (size_t)A.nnzb_pad));
+    CK(cudaMemset(A.val32, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
+    // ---- scratch
+    CK(cudaMalloc(&ctx->F, sizeof(double) * 3 * nv));
+    CK(cudaMalloc(&ctx->x1, sizeof(double) * 3 * nv));
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    ctx->red_blocks = sms * 4;                                  // persistent grid-stride reductions: 4 CTAs of 256 per SM
+    CK(cudaMalloc(&ctx->red_partial, sizeof(double) * ctx->red_blocks));
+    CK(cudaMalloc(&ctx->red_ticket, sizeof(unsigned int)));
+    CK(cudaMemset(ctx->red_ticket, 0, sizeof(unsigned int)));
+    CK(cudaMalloc(&ctx->red_out, sizeof(double) * 8));
+    CK(cudaMallocHost(&ctx->red_host, sizeof(double) * 8));
+    CK(cudaMalloc(&ctx->error_flag, sizeof(int)));
+    CK(cudaMemset(ctx->error_flag, 0, sizeof(int)));
+    TRY(contact_alloc(ctx));
+    TRY(linalg_alloc(ctx));
+    ctx->finalized = true;
+    return TSL_OK;
+}
+
+int tsl_reset_contact_state(tsl_ctx *ctx)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    size_t pb = (size_t)std::max<size_t>(ctx->bodies.size(), 1) * ctx->cfg.n_verts;
+    CK(cudaMemsetAsync(ctx->proj_flag, 0, sizeof(int) * pb, ctx->stream));
+    return TSL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- hot path
+static int check_device_flags(tsl_ctx *ctx)
+{
+    int f = 0;
+    CK(cudaMemcpyAsync(&f, ctx->error_flag, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (f & 1) { ctx->err = "contact against a non-frozen triangle is not implemented in this build"; return TSL_ERR_UNSUPPORTED; }
+    return TSL_OK;
+}
+
+int tsl_contact_detect(tsl_ctx *ctx, int *n_out)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    TRY(contact_detect(ctx, ctx->pos, ctx->prev_pos));
+    if (n_out) *n_out = ctx->nc;
+    return TSL_OK;
+}
+
+static int energy_sync(tsl_ctx *ctx, double *out)
+{
+    launch_energy(ctx, ctx->pos, ctx->red_out);
+    CK(cudaMemcpyAsync(ctx->red_host, ctx->red_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = ctx->red_host[0];
+    return TSL_OK;
+}
+int tsl_energy(tsl_ctx *ctx, double *out)
+{
+    if (!ctx || !ctx->finalized || !out) return TSL_ERR_INVALID;
+    return energy_sync(ctx, out);
+}
+
+static int ensure_f64(tsl_ctx *ctx)
+{
+    if (ctx->A.val64) return TSL_OK;
+    size_t nr = (size_t)ctx->A.n_slices * 32;
+    CK(cudaMalloc(&ctx->A.val64, sizeof(double) * 9 * (size_t)ctx->A.nnzb_pad));
+    CK(cudaMalloc(&ctx->minv64, sizeof(double) * 9 * nr));
+    for (int i = 0; i < 8; i++) { CK(cudaMalloc(&ctx->bi[i], sizeof(double) * 3 * nr)); CK(cudaMemset(ctx->bi[i], 0, sizeof(double) * 3 * nr)); }
+    CK(cudaMalloc(&ctx->d_kb, sizeof(double) * 3 * nr));
+    CK(cudaMalloc(&ctx->adj_rhs, sizeof(double) * 3 * nr));
+    CK(cudaMalloc(&ctx->adj_z, sizeof(double) * 3 * nr));
+    return TSL_OK;
+}
+
+int tsl_assemble(tsl_ctx *ctx, int flags)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    if (flags & TSL_ASM_RESIDUAL) launch_residual(ctx, ctx->pos);
+    if (flags & TSL_ASM_HESSIAN) {
+        bool f64 = (flags & TSL_ASM_F64) != 0;
+        if (f64) TRY(ensure_f64(ctx));
+        launch_hessian(ctx, ctx->pos, f64, (flags & TSL_ASM_SPD) ? 1 : 0, (flags & TSL_ASM_SYM) ? 1 : 0);
+        launch_block_jacobi(ctx, f64);
+        ctx->last_f64 = f64;
+    }
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+
+int tsl_solve(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
+{
+    if (!ctx || !ctx->finalized || !rhs || !x) return TSL_ERR_INVALID;
+    if (ctx->last_f64) return solve_bicgstab64(ctx, rhs, x, rel_tol, max_iters, st);
+    return solve_pcg32(ctx, rhs, x, rel_tol, max_iters, st);
+}
+
+// BaseScene.time_step (code/engine/BaseScene.py:1327-1370) + newton_step (:1159-1230)
+int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *stats)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    int n3 = 3 * ctx->cfg.n_verts;
+    cudaStream_t s = ctx->stream;
+    tsl_step_stats st;
+    memset(&st, 0, sizeof(st));
+    double t0 = now_ms();
+    // timestep_init: prev_pos <- pos
+    CK(cudaMemcpyAsync(ctx->prev_pos, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
+    TRY(contact_detect(ctx, ctx->pos, ctx->prev_pos));
+    st.n_contacts = ctx->nc;
+    st.ms_contact = now_ms() - t0;
+    double E0 = 0;
+    TRY(energy_sync(ctx, &E0));
+    double dt = ctx->cfg.dt;
+    int it = 0;
+    while (it < max_newton) {
+        it++;
+        t0 = now_ms();
+        launch_residual(ctx, ctx->pos);
+        launch_hessian(ctx, ctx->pos, false, 1, 1);
+        launch_block_jacobi(ctx, false);
+        ctx->last_f64 = false;
+        if (it == 1) TRY(check_device_flags(ctx));
+        double t1 = now_ms();
+        st.ms_assembly += t1 - t0;
+        tsl_solve_stats ss;
+        // inexact Newton: the residual is exact (fp64), so a loose linear tolerance only changes the path
+        TRY(solve_pcg32(ctx, ctx->F, ctx->sol, 1e-4, 4000, &ss));
+        st.linear_iters += ss.iters;
+        st.flags |= ss.flags;
+        launch_absmax(ctx, ctx->sol, n3, ctx->red_out + 1);
+        CK(cudaMemcpyAsync(ctx->x1, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(ctx->red_host + 1, ctx->red_out + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        double p_norm = ctx->red_host[1];
+        double t2 = now_ms();
+        st.ms_solve += t2 - t1;
+        if (!(p_norm == p_norm)) { ctx->err = "NaN in Newton direction"; return TSL_ERR_NUMERIC; }
+        // backtracking on E < E0, floor 1e-8, x stays at the last trial (quirk Q9)
+        double alpha = 1.0, E = E0;
+        while (alpha > 1e-8) {
+            launch_axpy_pos(ctx, ctx->x1, ctx->sol, alpha, ctx->pos);
+            TRY(energy_sync(ctx, &E));
+            st.linesearch_evals++;
+            if (E < E0) break;
+            alpha /= 2;
+        }
+        st.ms_linesearch += now_ms() - t2;
+        E0 = E;                               // the reference re-evaluates the same point at the top of the loop
+        st.delta = p_norm / dt;
+        if (st.delta < tol) { st.converged = 1; break; }
+    }
+    st.newton_iters = it;
+    st.energy = E0;
+    // Scene_bouncing.timestep_finish: update_vel, update_ref_angle
+    launch_update_vel(ctx);
+    for (auto &c : ctx->cloths) launch_update_ref_angle(ctx, c);
+    CK(cudaGetLastError());
+    if (stats) *stats = st;
+    return TSL_OK;
+}
+
+int tsl_step_forward_host(tsl_ctx *ctx, double *pos_host, double *vel_host, int max_newton, double tol, tsl_step_stats *stats)
+{
+    if (!ctx || !ctx->finalized || !pos_host || !vel_host) return TSL_ERR_INVALID;
+    size_t nb = sizeof(double) * 3 * (size_t)ctx->cfg.n_verts;
+    CK(cudaMemcpyAsync(ctx->pos, pos_host, nb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->vel, vel_host, nb, cudaMemcpyHostToDevice, ctx->stream));
+    TRY(tsl_step_forward(ctx, max_newton, tol, stats));
+    CK(cudaMemcpyAsync(pos_host, ctx->pos, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(vel_host, ctx->vel, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return TSL_OK;
+}
+
+// analytic_grad_system.Grad.transfer_grad (code/engine/analytic_grad_system.py:115-160)
+int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, const double *ref_angle_tm1,
+                      double *pg_t, double *pg_tm1, double *pg_tm2, const double *ag_t, double *ag_tm1,
+                      double *grad_kb_accum, double *z_out, double clamp, double rel_tol, int max_iters, tsl_solve_stats *stats)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    REQUIRE(x_t && x_tm1 && ref_angle_tm1 && pg_t && pg_tm1 && ag_t && ag_tm1 && grad_kb_accum, "tsl_step_backward: null pointer");
+    REQUIRE(ctx->cloths.size() == 1, "tsl_step_backward needs one cloth");
+    TRY(ensure_f64(ctx));
+    int nv = ctx->cfg.n_verts, n3 = 3 * nv;
+    cudaStream_t s = ctx->stream;
+    ClothDev &c = ctx->cloths[0];
+    size_t nb = sizeof(double) * n3, nfb = sizeof(double) * 3 * (size_t)c.NF;
+    // clamp_grad(step)
+    launch_clamp(ctx, pg_t, n3, clamp);
+    // copy_pos_only(step-1): pos = prev_pos = x_{t-1}; contact re-detection there (quirk Q7)
+    CK(cudaMemcpyAsync(ctx->pos, x_tm1, nb, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(ctx->prev_pos, x_tm1, nb, cudaMemcpyDeviceToDevice, s));
+    TRY(contact_detect(ctx, ctx->pos, ctx->prev_pos));
+    // copy_pos_and_refangle(step): pos = x_t, prev_pos = x_{t-1}, ref_angle = ref_angle[t-1]
+    CK(cudaMemcpyAsync(ctx->pos, x_t, nb, cudaMemcpyDeviceToDevice, s));
+    CK(cudaMemcpyAsync(c.ref_angle, ref_angle_tm1, nfb, cudaMemcpyDeviceToDevice, s));
+    // ref_angle_backprop_a2ax: plastic rest-angle adjoint feeds pos_grad[t] before the solve
+    launch_refangle_a2ax(ctx, c, ctx->pos, ag_t, ag_tm1, pg_t);
+    // get_paramters_grad: d_kb = dF/dKb
+    launch_cloth_param_deri(ctx, c, ctx->pos, ctx->d_kb);
+    // H = reference Hessian without projection, fp64
+    launch_hessian(ctx, ctx->pos, true, 0, 0);
+    launch_block_jacobi(ctx, true);
+    ctx->last_f64 = true;
+    TRY(check_device_flags(ctx));
+    double *z = z_out ? z_out : ctx->adj_z;
+    TRY(solve_bicgstab64(ctx, pg_t, z, rel_tol, max_iters, stats));
+    // friction lag terms and rest-angle terms into step t-1, then the time recurrence and dL/dKb
+    launch_contact_backprop(ctx, ctx->pos, z, pg_tm1);
+    launch_refangle_x2a(ctx, c, ctx->pos, z, ag_tm1);
+    launch_adjoint_tail(ctx, z, ctx->d_kb, pg_tm1, pg_tm2, grad_kb_accum);
+    CK(cudaStreamSynchronize(s));
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- introspection
+int tsl_get_residual(tsl_ctx *ctx, double *F_host)
+{
+    if (!ctx || !ctx->finalized || !F_host) return TSL_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(F_host, ctx->F, sizeof(double) * 3 * ctx->cfg.n_verts, cudaMemcpyDeviceToHost));
+    return TSL_OK;
+}
+int tsl_get_matrix_nnzb(tsl_ctx *ctx, int *n) { if (!ctx || !ctx->finalized || !n) return TSL_ERR_INVALID; *n = ctx->A.nnzb; return TSL_OK; }
+int tsl_get_matrix(tsl_ctx *ctx, int *rowptr, int *colidx, double *val)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    const SellMatrix &A = ctx->A;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (rowptr) memcpy(rowptr, A.h_rowptr.data(), sizeof(int) * (A.n_rows + 1));
+    if (colidx) memcpy(colidx, A.h_colidx.data(), sizeof(int) * A.nnzb);
+    if (val) {
+        size_t n = 9 * (size_t)A.nnzb_pad;
+        std::vector<double> pad(n);
+        if (ctx->last_f64) CK(cudaMemcpy(pad.data(), A.val64, sizeof(double) * n, cudaMemcpyDeviceToHost));
+        else {
+            std::vector<float> t(n);
+            CK(cudaMemcpy(t.data(), A.val32, sizeof(float) * n, cudaMemcpyDeviceToHost));
+            for (size_t i = 0; i < n; i++) pad[i] = t[i];
+        }
+        for (int r = 0; r < A.n_rows; r++)
+            for (int k = 0; k < A.h_rowptr[r + 1] - A.h_rowptr[r]; k++) {
+                long long pb = (long long)A.h_slice_base[r >> 5] + k * 32 + (r & 31);
+                for (int cc = 0; cc < 9; cc++) val[9 * (size_t)(A.h_rowptr[r] + k) + cc] = pad[(size_t)sell_addr(pb, r & 31, cc)];
+            }
+    }
+    return TSL_OK;
+}
+int tsl_get_projection(tsl_ctx *ctx, int body, int *flag, int *dir, int *idx, double *w)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    REQUIRE(body >= 0 && body < (int)ctx->bodies.size(), "bad body");
+    size_t nv = ctx->cfg.n_verts, off = (size_t)body * nv;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (flag) CK(cudaMemcpy(flag, ctx->proj_flag + off, sizeof(int) * nv, cudaMemcpyDeviceToHost));
+    if (dir) CK(cudaMemcpy(dir, ctx->proj_dir + off, sizeof(int) * nv, cudaMemcpyDeviceToHost));
+    if (idx) CK(cudaMemcpy(idx, ctx->proj_idx + 3 * off, sizeof(int) * 3 * nv, cudaMemcpyDeviceToHost));
+    if (w) CK(cudaMemcpy(w, ctx->proj_w + 3 * off, sizeof(double) * 3 * nv, cudaMemcpyDeviceToHost));
+    return TSL_OK;
+}
+int tsl_get_constraints(tsl_ctx *ctx, int *n_out, int *idx, double *w, double *k, double *dx0, double *T, double *n)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    int nc = ctx->nc;
+    if (n_out) *n_out = nc;
+    if (nc == 0) return TSL_OK;
+    if (idx) CK(cudaMemcpy(idx, ctx->con.idx, sizeof(int) * 4 * nc, cudaMemcpyDeviceToHost));
+    if (w) CK(cudaMemcpy(w, ctx->con.w, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost));
+    if (k) CK(cudaMemcpy(k, ctx->con.k, sizeof(double) * nc, cudaMemcpyDeviceToHost));
+    if (dx0) CK(cudaMemcpy(dx0, ctx->con.dx0, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost));
+    if (T) CK(cudaMemcpy(T, ctx->con.T, sizeof(double) * 6 * nc, cudaMemcpyDeviceToHost));
+    if (n) CK(cudaMemcpy(n, ctx->con.n, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost));
+    return TSL_OK;
+}
+int tsl_get_sizes(tsl_ctx *ctx, tsl_sizes *out)
+{
+    if (!ctx || !ctx->finalized || !out) return TSL_ERR_INVALID;
+    memset(out, 0, sizeof(*out));
+    out->n_verts = ctx->cfg.n_verts;
+    for (auto &c : ctx->cloths) { out->n_tris += c.NF; out->n_hinges += c.NH; }
+    out->nnzb = ctx->A.nnzb; out->nnzb_padded = (int)ctx->A.nnzb_pad; out->n_contacts = ctx->nc;
+    out->bytes_matrix_f32 = (long long)ctx->A.nnzb_pad * 40; out->bytes_matrix_f64 = (long long)ctx->A.nnzb_pad * 76;
+    return TSL_OK;
+}
+
+int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out)
+{
+    if (!ctx || !ctx->finalized || !ms_out || iters <= 0) return TSL_ERR_INVALID;
+    if (what == 0 || what == 1) return bench_pcg_iterations(ctx, iters, what == 1, ms_out);
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+    for (int i = 0; i < iters; i++) {
+        if (what == 2) launch_energy(ctx, ctx->pos, ctx->red_out);
+        else if (what == 3) launch_residual(ctx, ctx->pos);
+        else if (what == 4) launch_hessian(ctx, ctx->pos, false, 1, 1);
+        else { ctx->err = "tsl_bench_kernel: unknown kernel class"; return TSL_ERR_INVALID; }
+    }
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_out = ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return TSL_OK;
+}
+
+}  // extern "C"

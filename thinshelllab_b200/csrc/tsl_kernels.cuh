@@ -1,0 +1,34 @@
+// tsl_kernels.cuh -- host-side launchers shared between the translation units of libtsl.
+#pragma once
+#include "tsl_internal.cuh"
+
+namespace tsl {
+
+// tsl_physics.cu
+void launch_face_normals(tsl_ctx *ctx, const ClothDev &c, const double *pos);
+void launch_energy(tsl_ctx *ctx, const double *pos, double *out_dev);
+void launch_residual(tsl_ctx *ctx, const double *pos);
+void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kb);
+void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym);
+void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alpha, double *pos);
+void launch_update_vel(tsl_ctx *ctx);
+void launch_update_ref_angle(tsl_ctx *ctx, const ClothDev &c);
+void launch_absmax(tsl_ctx *ctx, const double *a, int n, double *out_dev);
+void launch_refangle_a2ax(tsl_ctx *ctx, const ClothDev &c, const double *pos, const double *ag_step, double *ag_prev, double *pg_step);
+void launch_refangle_x2a(tsl_ctx *ctx, const ClothDev &c, const double *pos, const double *z, double *ag_prev);
+void launch_contact_backprop(tsl_ctx *ctx, const double *pos, const double *z, double *pg_prev);
+void launch_clamp(tsl_ctx *ctx, double *a, int n, double lim);
+void launch_adjoint_tail(tsl_ctx *ctx, const double *z, const double *d_kb, double *pg_tm1, double *pg_tm2, double *grad_kb_accum);
+
+// tsl_contact.cu
+int contact_alloc(tsl_ctx *ctx);
+int contact_detect(tsl_ctx *ctx, const double *pos, const double *prev_pos);
+
+// tsl_linalg.cu
+int linalg_alloc(tsl_ctx *ctx);
+void launch_block_jacobi(tsl_ctx *ctx, bool f64);
+int solve_pcg32(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st);
+int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st);
+int bench_pcg_iterations(tsl_ctx *ctx, int iters, int spmv_only, float *ms_out);
+
+}  // namespace tsl
