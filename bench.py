@@ -1,0 +1,262 @@
+#!/usr/bin/env python
+"""bench.py -- BASELINE.json metric: element-updates/sec per implicit fwd+bwd step; HBM GB/s vs peak.
+
+One "step" = one implicit forward time step of the sheet (contact query, Newton with block-Jacobi PCG, line search) plus
+one adjoint step for it (contact re-detection, un-projected fp64 Hessian, BiCGStab solve, parameter gradient dL/dKb).
+`value` = triangles x steps / device time with state resident in HBM; `e2e` = the same through the host-buffer C-ABI entry
+point (tsl_step_forward_host) + host-side loss seed / gradient read-back, copies inside the timed region.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--sheet-n 707] [--impl reference]
+
+N > 1 (torchrun): round 1 runs one independent sheet per rank (replicas, weak scaling) -- the strip-partitioned solver of
+SURVEY.md section 8e is not implemented yet; the JSON line says so in config.parallelism.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)"""
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop_ev = gpu_index, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self._stop_ev.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop_ev.wait(0.2)
+
+    def stop(self):
+        self._stop_ev.set()
+        self.join(timeout=5)
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(int(r[0]) for r in self.rows if r[0].isdigit())
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(len(r) > 2 + k and r[2 + k].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arm (oracle)
+def oracle_fwd_bwd(sample_n, steps, threads=None):
+    """times `steps` fwd+bwd steps of the CPU oracle on a sample_n x sample_n sheet (each from the same initial state)."""
+    from oracle import tsl_oracle as orc
+    from thinshelllab_b200.synthetic import sheet_spec
+    if threads:
+        orc.lib().orc_set_num_threads(int(threads))
+    sp = sheet_spec(sample_n)
+    times = []
+    for _ in range(steps):
+        o = orc.OracleScene(sample_n, sample_n, sp["dx"], sp["dt"], sp["table_pos"], sp["table_faces"], sp["table_mass"], k_contact=sp["k_contact"],
+                            mu=sp["mu"], max_n_constraints=sp["max_n_constraints"], grid_n=sp["grid_n"])
+        o.pos[:o.NVc] = sp["cloth_pos"]; o.prev_pos[:] = o.pos
+        g = orc.OracleGrad(o, 2)
+        t0 = time.perf_counter()
+        g.copy_pos(0)
+        o.time_step()
+        g.copy_pos(1)
+        g.pos_grad[1, :o.NVc, 2] = 1.0
+        g.transfer_grad(1)
+        times.append(time.perf_counter() - t0)
+    return sp["n_tris"], times, orc.lib().orc_num_threads()
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n = args.cpu_sample_n
+    for _ in range(args.warmup):
+        pass                                    # the CPU arm has no warm-up state worth paying ~25 s per step for
+    tris, times, threads = oracle_fwd_bwd(n, max(1, args.steps))
+    T = float(np.sum(times))
+    val = tris * len(times) / T
+    sample = f"{n}x{n} sheet ({tris} tris) over the table, {len(times)} fwd+bwd step(s) from the bench's initial-state generator; SuperLU direct solves"
+    print(json.dumps({
+        "impl": "reference", "metric": "tri_steps_per_s (implicit fwd+bwd step)", "value": val, "unit": "tri-steps/s", "n_gpus": args.gpus,
+        "steps": len(times), "warmup": 0, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"sheet {args.sheet_n}x{args.sheet_n} fwd+bwd (CPU arm runs the bounded sample below)", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "tri-steps/s", "cores": threads, "kind": "port", "sample": sample,
+                         "note": "CPU oracle (restatement of the reference sources, pinned to goldens); Taichi/CuPy cannot be installed here"},
+        "e2e": {"value": val, "unit": "tri-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from thinshelllab_b200.engine.analytic_grad_system import Grad
+    from thinshelllab_b200.synthetic import sheet_scene
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = f"cuda:{local}"
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    N = args.sheet_n
+    s = sheet_scene(N, device=dev, seed=rank)
+    e = s.engine
+    NVc = s.cloths[0].NV
+    n_tris = 2 * N * N
+    g = Grad(s, 2, 0)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    stats = []
+
+    def fwd_bwd_device():
+        g.copy_pos(s, 0)
+        st = s.time_step()
+        g.copy_pos(s, 1)
+        g._pos_grad.zero_(); g._angleref_grad.zero_()
+        g._pos_grad[1, :NVc, 2] = 1.0                      # loss seed: Grad.get_loss_slide-style dL/dz = 1 on the cloth
+        its, flags, rr = g.transfer_grad(1, s, rel_tol=args.adjoint_tol)
+        stats.append((st.newton_iters, st.linear_iters, st.linesearch_evals, st.n_contacts, its, st.flags, flags))
+
+    # host buffers of the e2e path
+    pos_h = torch.empty((e.n_verts, 3), dtype=torch.float64).pin_memory()
+    vel_h = torch.empty((e.n_verts, 3), dtype=torch.float64).pin_memory()
+    seed_h = torch.zeros((e.n_verts, 3), dtype=torch.float64).pin_memory(); seed_h[:NVc, 2] = 1.0
+    pg_h = torch.empty((e.n_verts, 3), dtype=torch.float64).pin_memory()
+
+    def fwd_bwd_host():
+        g._pos_buffer[0].copy_(pos_h, non_blocking=True)    # x_{t-1} travels with the step's inputs
+        g._ref_angle_buffer[0, 0].copy_(e.cloth_ref_angle[0])
+        st = e.step_forward_host(pos_h, vel_h)             # H2D pos, vel -> step -> D2H pos, vel
+        g.copy_pos(s, 1)
+        g._pos_grad.zero_(); g._angleref_grad.zero_()
+        g._pos_grad[1].copy_(seed_h, non_blocking=True)     # H2D loss seed
+        g.transfer_grad(1, s, rel_tol=args.adjoint_tol)
+        pg_h.copy_(g._pos_grad[0], non_blocking=True)       # D2H dL/dx_{t-1}
+        kb = g.grad_kb[None]                                # D2H dL/dKb (8 bytes, syncs)
+        return kb
+
+    for _ in range(args.warmup):
+        fwd_bwd_device()
+    stats.clear()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    l0 = e.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        fwd_bwd_device()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = e.launch_count() - l0
+    clocks = sampler.stop() if rank == 0 else None
+    # e2e
+    pos_h.copy_(e.pos); vel_h.copy_(e.vel)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        fwd_bwd_host()
+    barrier()
+    ms_e2e = 1e3 * (time.perf_counter() - t0)
+    if world > 1:
+        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    # ---- roofline of the dominant kernel (PCG SpMV), timed live with CUDA events on the launching stream inside libtsl
+    from thinshelllab_b200 import _lib
+    e.assemble(_lib.ASM_RESIDUAL | _lib.ASM_HESSIAN | _lib.ASM_NEWTON | _lib.ASM_SPD)
+    sz = e.sizes()
+    e.bench_kernel(1, 20)
+    ms_spmv = e.bench_kernel(1, 200)
+    e.bench_kernel(0, 20)
+    ms_pcg = e.bench_kernel(0, 200)
+    V = sz["n_verts"]
+    spmv_bytes = 40.0 * sz["nnzb"] + 28.0 * V                      # 36 B + 4 B per block, row ptr 4V, x 12V, y 12V
+    pcg_bytes = 40.0 * sz["nnzb"] + (4 + 24 + 108 + 36) * V       # one PCG iteration, ~608 B / vertex
+    peak, peak_src = _peaks()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    st = np.array(stats, dtype=np.float64)
+    value = world * n_tris * args.steps / (ms * 1e-3)
+    e2e = world * n_tris * args.steps / (ms_e2e * 1e-3)
+    nb = e.n_verts * 24
+    out = {
+        "metric": "tri_steps_per_s (implicit fwd+bwd step)", "value": value, "unit": "tri-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64 residual/energy/adjoint, f32 forward Hessian + PCG vectors", "data": "synthetic",
+        "config": {"workload": f"sheet {N}x{N} ({n_tris} tris, dx 2 mm) landing on a frozen table, Scene_bouncing physics, fwd + adjoint (dL/dKb) per step",
+                   "sheet_n": N, "n_tris": n_tris, "n_verts": V, "nnzb": sz["nnzb"], "nnzb_padded": sz["nnzb_padded"],
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (element partition not implemented in round 1)",
+                   "l2": "matrix %.0f MB > 126 MB L2" % (sz["bytes_matrix_f32"] / 1e6) if sz["bytes_matrix_f32"] > 126e6 else
+                         "working set %.0f MB fits the 126 MB L2: roofline fraction can exceed 1" % (sz["bytes_matrix_f32"] / 1e6),
+                   "per_step_mean": {"newton_iters": st[:, 0].mean(), "pcg_iters": st[:, 1].mean(), "linesearch_evals": st[:, 2].mean(),
+                                     "contacts": st[:, 3].mean(), "bicgstab_iters": st[:, 4].mean()},
+                   "flags": {"pcg_negative_curvature_steps": int((st[:, 5].astype(int) & 1).sum()), "krylov_cap_hit": int(((st[:, 5].astype(int) | st[:, 6].astype(int)) & 2).sum() // 2)}},
+        "clocks": clocks,
+        "e2e": {"value": e2e, "unit": "tri-steps/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 4 * nb, "d2h_bytes_per_step": 3 * nb + 8},
+        "gpu_launches": int(launches),
+        "roofline": {"bound": "hbm", "kernel": "k_spmv_dots<float> (PCG SpMV + fused dot)", "achieved": spmv_bytes / (ms_spmv * 1e-3) / 1e9, "peak": peak,
+                     "peak_source": peak_src, "unit": "GB/s", "frac": spmv_bytes / (ms_spmv * 1e-3) / 1e9 / peak, "traffic": None,
+                     "us_per_launch": 1e3 * ms_spmv, "algorithmic_bytes_per_launch": spmv_bytes,
+                     "pcg_iteration": {"us": 1e3 * ms_pcg, "algorithmic_bytes": pcg_bytes, "achieved": pcg_bytes / (ms_pcg * 1e-3) / 1e9,
+                                       "frac": pcg_bytes / (ms_pcg * 1e-3) / 1e9 / peak}},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        tris, times, threads = oracle_fwd_bwd(args.cpu_sample_n, 1)
+        out["cpu_baseline"] = {"value": tris / times[0], "unit": "tri-steps/s", "cores": threads, "kind": "port",
+                               "sample": f"{args.cpu_sample_n}x{args.cpu_sample_n} sheet ({tris} tris), 1 fwd+bwd step, CPU oracle (fp64, SuperLU direct solves; not Taichi)"}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--sheet-n", type=int, default=707, help="sheet is N x N quads: 158 -> 50k tris, 316 -> 200k, 707 -> 1M")
+    ap.add_argument("--cpu-sample-n", type=int, default=32)
+    ap.add_argument("--adjoint-tol", type=float, default=1e-8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+    else:
+        run_ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

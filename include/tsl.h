@@ -103,12 +103,15 @@ int tsl_contact_detect(tsl_ctx *ctx, int *n_contacts_out);
 int tsl_energy(tsl_ctx *ctx, double *energy_out);
 /* BaseScene.compute_residual_and_Hessian(spd) / compute_Hessian(spd) (code/engine/BaseScene.py:976-1052).
  * flags: bit0 residual into F, bit1 Hessian, bit2 spd projection (forward), bit3 symmetrise element
- * blocks (forward PCG matrix), bit4 store Hessian in fp64 (adjoint) instead of fp32. */
+ * blocks, bit4 store Hessian in fp64 (adjoint) instead of fp32. */
 #define TSL_ASM_RESIDUAL 1
 #define TSL_ASM_HESSIAN 2
 #define TSL_ASM_SPD 4
 #define TSL_ASM_SYM 8
 #define TSL_ASM_F64 16
+/* bit5: assemble the engine's own forward Newton matrix (exact membrane Hessian + Gauss-Newton bending, DESIGN.md
+ * section 4) instead of the reference's formulas; with it, TSL_ASM_SPD means "clamp the indefinite pieces". */
+#define TSL_ASM_NEWTON 32
 int tsl_assemble(tsl_ctx *ctx, int flags);
 /* SparseMatrix.solve (code/engine/sparse_solver.py:85-105): x = H^-1 b with the last assembled Hessian.
  * fp32 Hessian: block-Jacobi PCG (fp32 vectors, fp64 reductions); fp64 Hessian: block-Jacobi BiCGStab (fp64).

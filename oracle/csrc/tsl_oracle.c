@@ -1247,6 +1247,106 @@ void orc_contact_backprop(const orc_contacts *C, const double *pos, const double
     }
 }
 
+
+/* ------------------------------------------------------------------ NOT a reference restatement:
+ * CPU twin of the product's forward Newton matrix ("PSD mode").  The reference's own
+ * Hessian is inexact (Q14, Q15) and makes Newton crawl on stiff sheets; only the fixed point has to match the
+ * reference, so the CUDA forward path uses this symmetric positive definite model instead:
+ *   edge   : max(dE/dl, 0)/l (I - d d^T) + d2E/dl2 d d^T        (exact, compression clamped)
+ *   area   : d2E/dA2 g g^T + max(dE/dA, 0) * J^T (I - n n^T) J / (2|n|)   (PSD part of the exact Hessian)
+ *   bending: d2E/dtheta2 grad(theta) grad(theta)^T               (Gauss-Newton)
+ * Used by tests to check the CUDA forward matrix and to study Newton iteration counts on the CPU. */
+static int PSD_FLAGS = 3;   /* bit0: clamp compressed edges, bit1: clamp the area term (experiment switches) */
+void orc_set_psd_flags(int f) { PSD_FLAGS = f; }
+void orc_cloth_hessian_psd(orc_cloth *c, orc_mat *A)
+{
+#pragma omp parallel for
+    for (int i = 0; i < c->NF; i++) {
+        const int *f = c->f2v + 3 * i;
+        for (int l = 0; l < 3; l++) {
+            int xx = f[l], yy = f[(l + 1) % 3];
+            double d[3];
+            v_sub(c->pos + 3 * xx, c->pos + 3 * yy, d);
+            double lt = v_norm(d), base = rest_len(c, l);
+            double dl = -c->Kl * 2.0 * (1.0 - lt / base), dl2 = c->Kl * 2.0 / base;
+            double g = (dl > 0 || !(PSD_FLAGS & 1)) ? dl / lt : 0.0;
+            int X = xx + c->offset, Y = yy + c->offset;
+            for (int j = 0; j < 3; j++)
+                for (int k = 0; k < 3; k++) {
+                    double dd = (d[j] / lt) * (d[k] / lt);
+                    double h = g * ((j == k) - dd) + dl2 * dd;
+                    add_H(A, X * 3 + j, X * 3 + k, h); add_H(A, X * 3 + j, Y * 3 + k, -h);
+                    add_H(A, Y * 3 + j, X * 3 + k, -h); add_H(A, Y * 3 + j, Y * 3 + k, h);
+                }
+        }
+        {
+            const double *P[3] = { c->pos + 3 * f[0], c->pos + 3 * f[1], c->pos + 3 * f[2] };
+            double e1[3], e2[3], n[3];
+            v_sub(P[1], P[0], e1); v_sub(P[2], P[0], e2); v_cross(e1, e2, n);
+            double nl = v_norm(n), area = 0.5 * nl, V = rest_area(c);
+            double da = -c->Ka * 2.0 * (1.0 - area / V), da2 = c->Ka * 2.0 / V;
+            double nh[3] = { n[0] / nl, n[1] / nl, n[2] / nl };
+            /* J[q][:] = d n / d q, q = 9 vertex coordinates: dn/dp1 = -(dn/de1 + dn/de2), dn/de1_j = e_j x e2, dn/de2_j = e1 x e_j */
+            double J[9][3];
+            for (int j = 0; j < 3; j++) {
+                double ej[3] = { 0, 0, 0 }; ej[j] = 1;
+                v_cross(ej, e2, J[3 + j]); v_cross(e1, ej, J[6 + j]);
+                for (int k = 0; k < 3; k++) J[j][k] = -(J[3 + j][k] + J[6 + j][k]);
+            }
+            double g[9];
+            for (int q = 0; q < 9; q++) g[q] = 0.5 * v_dot(J[q], nh);
+            double s = (da > 0 || !(PSD_FLAGS & 2)) ? da / (2.0 * nl) : 0.0;
+            for (int a = 0; a < 9; a++)
+                for (int b = 0; b < 9; b++) {
+                    double h = da2 * g[a] * g[b] + s * (v_dot(J[a], J[b]) - 4.0 * g[a] * g[b]);
+                    add_H(A, (f[a / 3] + c->offset) * 3 + a % 3, (f[b / 3] + c->offset) * 3 + b % 3, h);
+                }
+        }
+        for (int l = 0; l < 3; l++)
+            if (c->cf[3 * i + l] > i) {
+                double g[4][3];
+                cloth_bending_grad(c, i, l, g[0], g[1], g[2], g[3]);
+                int pt[4] = { f[l], f[(l + 1) % 3], f[(l + 2) % 3], c->f2v[3 * c->cf[3 * i + l] + c->cp[3 * i + l]] };
+                double d2 = 2.0 * c->Kb * c->dx * c->dx * 1.0 / 3.0;
+                for (int j = 0; j < 4; j++)
+                    for (int k = 0; k < 4; k++)
+                        for (int jj = 0; jj < 3; jj++)
+                            for (int kk = 0; kk < 3; kk++)
+                                add_H(A, (pt[j] + c->offset) * 3 + jj, (pt[k] + c->offset) * 3 + kk, d2 * g[j][jj] * g[k][kk]);
+            }
+    }
+}
+/* contact part of the PSD mode: k_contact n n^T on the query vertex (exact when the triangle is frozen) plus the
+ * PSD-projected friction block; only the vertex-vertex block (all that survives a frozen triangle). */
+void orc_contact_hessian_psd_vertex(const orc_contacts *C, const double *pos, orc_mat *A)
+{
+    for (int i = 0; i < C->nc; i++) {
+        const int *idx = C->idx + 4 * i; const double *T = C->T + 6 * i;
+        double p1[3], p2[3], p[3], cr[3];
+        v_sub(pos + 3 * idx[1], pos + 3 * idx[0], p1); v_sub(pos + 3 * idx[2], pos + 3 * idx[0], p2); v_sub(pos + 3 * idx[3], pos + 3 * idx[0], p);
+        v_cross(p1, p2, cr);
+        double c = v_norm(cr), d = v_dot(cr, p) / c;
+        double B[3][3] = { { 0 } };
+        if (d < C->eps_contact)
+            for (int a = 0; a < 3; a++) for (int b = 0; b < 3; b++) B[a][b] = C->k_contact * (cr[a] / c) * (cr[b] / c);
+        double k = C->k[i], u[2], r;
+        friction_u(C, pos, i, u, &r);
+        double f1 = fr_f1(C, r);
+        double h[4] = { f1, 0, 0, f1 };
+        if (r > 1e-9) {
+            double f2 = fr_f2(C, r);
+            h[0] += f2 * (u[0] / r) * u[0]; h[1] += f2 * (u[0] / r) * u[1];
+            h[2] += f2 * (u[1] / r) * u[0]; h[3] += f2 * (u[1] / r) * u[1];
+        }
+        orc_spd_project_2d(h);
+        for (int a = 0; a < 3; a++)
+            for (int b = 0; b < 3; b++) {
+                B[a][b] += k * (T[a] * (h[0] * T[b] + h[1] * T[3 + b]) + T[3 + a] * (h[2] * T[b] + h[3] * T[3 + b]));
+                add_H(A, idx[3] * 3 + a, idx[3] * 3 + b, B[a][b]);
+            }
+    }
+}
+
 /* per-vertex inertia + gravity energy for non-cloth (tet) bodies: Elastic.compute_energy vertex loops
  * (engine/model_elastic_offset.py:316-323) with ext_force = 0 */
 double orc_vertex_energy(int v_start, int v_end, const double *pos, const double *prev_pos, const double *vel,

@@ -151,6 +151,7 @@ class OracleScene:
                  damping=1.0, gravity=(0.0, 0.0, -9.8), max_n_constraints=10000, extra_frozen_vertices=(), grid_h=0.003, grid_n=0):
         L = lib()
         self.grid = (grid_h, grid_n)
+        self.hessian_mode = "reference"
         self.N, self.M, self.dx, self.dt = N, M, dx, dt
         self.NVc = (N + 1) * (M + 1)
         self.NFc = 2 * N * M
@@ -286,6 +287,15 @@ class OracleScene:
         t0 = time.perf_counter()
         self.val[:] = 0
         cs = self._contacts()
+        if self.hessian_mode == "psd":      # CPU twin of the product's forward Newton matrix (not a reference restatement)
+            L.orc_contact_grad_hess(cs, _d(self.pos), _i(self.frozen), _d(self.F), None, 0)
+            L.orc_contact_hessian_psd_vertex(cs, _d(self.pos), self.mat)
+            L.orc_contacts_destroy(cs)
+            L.orc_add_mass_diag(self.mat, _d(self.mass), _f(self.dt))
+            L.orc_cloth_hessian_psd(self.cloth, self.mat)
+            assert L.orc_mat_missing(self.mat) == 0
+            self._tick("hessian", t0)
+            return
         L.orc_contact_grad_hess(cs, _d(self.pos), _i(self.frozen), _d(self.F), self.mat, int(spd))
         L.orc_contacts_destroy(cs)
         L.orc_add_mass_diag(self.mat, _d(self.mass), _f(self.dt))

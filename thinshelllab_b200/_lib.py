@@ -73,7 +73,7 @@ SIGNATURES = {
     "tsl_launch_count": (C.c_longlong, [_vp]),
 }
 
-ASM_RESIDUAL, ASM_HESSIAN, ASM_SPD, ASM_SYM, ASM_F64 = 1, 2, 4, 8, 16
+ASM_RESIDUAL, ASM_HESSIAN, ASM_SPD, ASM_SYM, ASM_F64, ASM_NEWTON = 1, 2, 4, 8, 16, 32
 
 _LIB = None
 

@@ -399,7 +399,7 @@ int tsl_assemble(tsl_ctx *ctx, int flags)
     if (flags & TSL_ASM_HESSIAN) {
         bool f64 = (flags & TSL_ASM_F64) != 0;
         if (f64) TRY(ensure_f64(ctx));
-        launch_hessian(ctx, ctx->pos, f64, (flags & TSL_ASM_SPD) ? 1 : 0, (flags & TSL_ASM_SYM) ? 1 : 0);
+        launch_hessian(ctx, ctx->pos, f64, (flags & TSL_ASM_SPD) ? 1 : 0, (flags & TSL_ASM_SYM) ? 1 : 0, (flags & TSL_ASM_NEWTON) ? 1 : 0);
         launch_block_jacobi(ctx, f64);
         ctx->last_f64 = f64;
     }
@@ -432,21 +432,42 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     TRY(energy_sync(ctx, &E0));
     double dt = ctx->cfg.dt;
     int it = 0;
+    // Inexact Newton on the engine's own Newton matrix (k_hessian_tri_newton): the exact membrane Hessian first; if PCG
+    // meets negative curvature the iteration is redone with the indefinite pieces clamped (positive definite).  The
+    // residual is exact fp64, so matrix model, fp32 storage and Krylov tolerance only shape the path to the same fixed
+    // point the reference's Newton iteration converges to.  Forcing term: Eisenstat-Walker choice 2.
+    double eta = 0.1, fnorm_prev = -1;
     while (it < max_newton) {
         it++;
         t0 = now_ms();
         launch_residual(ctx, ctx->pos);
-        launch_hessian(ctx, ctx->pos, false, 1, 1);
+        launch_hessian(ctx, ctx->pos, false, 0, 0, 1);
         launch_block_jacobi(ctx, false);
         ctx->last_f64 = false;
         if (it == 1) TRY(check_device_flags(ctx));
         double t1 = now_ms();
         st.ms_assembly += t1 - t0;
         tsl_solve_stats ss;
-        // inexact Newton: the residual is exact (fp64), so a loose linear tolerance only changes the path
-        TRY(solve_pcg32(ctx, ctx->F, ctx->sol, 1e-4, 4000, &ss));
+        TRY(solve_pcg32(ctx, ctx->F, ctx->sol, eta, 4000, &ss));
         st.linear_iters += ss.iters;
-        st.flags |= ss.flags;
+        if (ss.flags & 1) {
+            st.flags |= 1;
+            double t1b = now_ms();
+            launch_hessian(ctx, ctx->pos, false, 1, 0, 1);
+            launch_block_jacobi(ctx, false);
+            st.ms_assembly += now_ms() - t1b;
+            TRY(solve_pcg32(ctx, ctx->F, ctx->sol, eta, 4000, &ss));
+            st.linear_iters += ss.iters;
+        }
+        st.flags |= (ss.flags & 2);
+        double fnorm = ctx->ks_host->rr0;
+        if (fnorm_prev > 0 && fnorm > 0) {
+            double e2 = 0.9 * (fnorm / fnorm_prev) * (fnorm / fnorm_prev);
+            double safe = 0.9 * eta * eta;
+            if (safe > 0.1) e2 = std::max(e2, safe);
+            eta = std::min(0.1, std::max(1e-4, e2));
+        }
+        fnorm_prev = fnorm;
         launch_absmax(ctx, ctx->sol, n3, ctx->red_out + 1);
         CK(cudaMemcpyAsync(ctx->x1, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(ctx->red_host + 1, ctx->red_out + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -519,7 +540,7 @@ int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, cons
     // get_paramters_grad: d_kb = dF/dKb
     launch_cloth_param_deri(ctx, c, ctx->pos, ctx->d_kb);
     // H = reference Hessian without projection, fp64
-    launch_hessian(ctx, ctx->pos, true, 0, 0);
+    launch_hessian(ctx, ctx->pos, true, 0, 0, 0);
     launch_block_jacobi(ctx, true);
     ctx->last_f64 = true;
     TRY(check_device_flags(ctx));
@@ -615,7 +636,7 @@ int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out)
     for (int i = 0; i < iters; i++) {
         if (what == 2) launch_energy(ctx, ctx->pos, ctx->red_out);
         else if (what == 3) launch_residual(ctx, ctx->pos);
-        else if (what == 4) launch_hessian(ctx, ctx->pos, false, 1, 1);
+        else if (what == 4) launch_hessian(ctx, ctx->pos, false, 0, 0, 1);
         else { ctx->err = "tsl_bench_kernel: unknown kernel class"; return TSL_ERR_INVALID; }
     }
     CK(cudaEventRecord(e1, ctx->stream));

@@ -9,7 +9,7 @@ void launch_face_normals(tsl_ctx *ctx, const ClothDev &c, const double *pos);
 void launch_energy(tsl_ctx *ctx, const double *pos, double *out_dev);
 void launch_residual(tsl_ctx *ctx, const double *pos);
 void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kb);
-void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym);
+void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model);
 void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alpha, double *pos);
 void launch_update_vel(tsl_ctx *ctx);
 void launch_update_ref_angle(tsl_ctx *ctx, const ClothDev &c);

@@ -239,6 +239,7 @@ int solve_pcg32(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int 
     }
     k_f32_to_f64<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, ctx->cg_x, x);
     ctx->launches++;
+    ctx->ks_host->rr0 = sqrt(rr0);      // |b|_2 for the caller's forcing term
     if (st) { st->iters = it; st->flags = flags; st->rel_residual = rr0 > 0 ? sqrt(rr / rr0) : 0.0; }
     CK(cudaGetLastError());
     return TSL_OK;

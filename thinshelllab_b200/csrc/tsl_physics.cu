@@ -426,6 +426,77 @@ __global__ void __launch_bounds__(128) k_hessian_tri(ClothDev c, const double *_
     }
 }
 
+
+// Forward Newton matrix ("Newton model") -- NOT the reference's Hessian.  Only the fixed point of
+// the forward step has to match the reference, and the reference's own matrix (Q14/Q15 + per-edge projection) makes
+// Newton crawl whenever the sheet carries compression; this model is the exact membrane Hessian with its indefinite
+// pieces optionally clamped:
+//   edge : dE/dl / l (I - d d^T) + d2E/dl2 d d^T          clamp: drop dE/dl < 0 (compressed edge)
+//   area : d2E/dA2 g g^T + dE/dA * J^T (I - n n^T) J / (2|n|)      clamp: drop dE/dA < 0
+//   (bending: Gauss-Newton term only = k_hessian_hinge)
+// Symmetric by construction; positive definite when clamped.
+template <typename T>
+__global__ void __launch_bounds__(128) k_hessian_tri_newton(ClothDev c, const double *__restrict__ pos, const int *__restrict__ frozen,
+                                                            T *val, int clamp)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c.NF) return;
+    FaceV f = load_face(c, pos, i);
+    double He[3][9];
+#pragma unroll
+    for (int l = 0; l < 3; l++) {
+        d3 dv = f.p[l] - f.p[(l + 1) % 3];
+        double lt = norm(dv), base = rest_len(c.P, l);
+        double dl = -c.P.Kl * 2.0 * (1.0 - lt / base), dl2 = c.P.Kl * 2.0 / base;
+        double g = (dl > 0 || !clamp) ? dl / lt : 0.0;
+        double d[3] = { dv.x / lt, dv.y / lt, dv.z / lt };
+#pragma unroll
+        for (int j = 0; j < 3; j++)
+#pragma unroll
+            for (int k = 0; k < 3; k++) He[l][j * 3 + k] = g * ((j == k ? 1.0 : 0.0) - d[j] * d[k]) + dl2 * d[j] * d[k];
+    }
+    d3 e1 = f.p[1] - f.p[0], e2 = f.p[2] - f.p[0];
+    d3 n = cross(e1, e2);
+    double nl = norm(n), area = 0.5 * nl, V = rest_area(c.P);
+    double da = -c.P.Ka * 2.0 * (1.0 - area / V), da2 = c.P.Ka * 2.0 / V;
+    double sa = (da > 0 || !clamp) ? da / (2.0 * nl) : 0.0;
+    d3 nh = mk(n.x / nl, n.y / nl, n.z / nl);
+    // J[a][j] = d n / d p_a,j : vertex 1: e_j x e2, vertex 2: e1 x e_j, vertex 0: minus both
+    d3 J[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {
+        d3 ej = mk(j == 0 ? 1.0 : 0.0, j == 1 ? 1.0 : 0.0, j == 2 ? 1.0 : 0.0);
+        J[1][j] = cross(ej, e2); J[2][j] = cross(e1, ej);
+        J[0][j] = -(J[1][j] + J[2][j]);
+    }
+    double g[3][3];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) g[a][j] = 0.5 * dot(J[a][j], nh);
+    const int *slot = c.tri_slot + 9 * i;
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++) {
+            double B[9];
+#pragma unroll
+            for (int j = 0; j < 3; j++)
+#pragma unroll
+                for (int k = 0; k < 3; k++) B[j * 3 + k] = da2 * g[a][j] * g[b][k] + sa * (dot(J[a][j], J[b][k]) - 4.0 * g[a][j] * g[b][k]);
+            if (a == b) {
+                const int lp = (a + 2) % 3;
+#pragma unroll
+                for (int r = 0; r < 9; r++) B[r] += He[a][r] + He[lp][r];
+            } else {
+                const int l = ((a + 1) % 3 == b) ? a : b;       // edge l joins (l, l+1)
+#pragma unroll
+                for (int r = 0; r < 9; r++) B[r] -= He[l][r];
+            }
+            add_block(val, slot[a * 3 + b], c.offset + f.v[a], c.offset + f.v[b], frozen, B);
+        }
+}
+
 // hinge Hessian, loop 2 of Cloth.compute_Hessian_bending (:616-637): d2E/dtheta2 * grad(theta) grad(theta)^T
 template <typename T>
 __global__ void __launch_bounds__(128) k_hessian_hinge(ClothDev c, const double *__restrict__ pos, const int *__restrict__ frozen, T *val)
@@ -718,7 +789,7 @@ void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos,
     ctx->launches += 2;
 }
 template <typename T>
-static void launch_hessian_t(tsl_ctx *ctx, const double *pos, T *val, int spd, int sym)
+static void launch_hessian_t(tsl_ctx *ctx, const double *pos, T *val, int spd, int sym, int newton_model)
 {
     int n = ctx->cfg.n_verts;
     ContactParams cp = { ctx->cfg.k_contact, ctx->cfg.eps_contact, ctx->cfg.eps_v, ctx->cfg.dt };
@@ -726,21 +797,27 @@ static void launch_hessian_t(tsl_ctx *ctx, const double *pos, T *val, int spd, i
     k_hessian_mass<T><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, ctx->mass, ctx->cfg.dt, ctx->A.diag_pb, val);
     ctx->launches++;
     for (auto &c : ctx->cloths) {
-        launch_face_normals(ctx, c, pos);
-        k_q1_prepare<<<1, 32, 0, ctx->stream>>>(c, pos);
-        k_hessian_tri<T><<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, ctx->frozen, val, spd, sym);
+        if (newton_model) {
+            k_hessian_tri_newton<T><<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, ctx->frozen, val, spd);
+            ctx->launches += 1;
+        } else {
+            launch_face_normals(ctx, c, pos);
+            k_q1_prepare<<<1, 32, 0, ctx->stream>>>(c, pos);
+            k_hessian_tri<T><<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, ctx->frozen, val, spd, sym);
+            ctx->launches += 3;
+        }
         k_hessian_hinge<T><<<GRID(c.NH, 128), 128, 0, ctx->stream>>>(c, pos, ctx->frozen, val);
-        ctx->launches += 3;
+        ctx->launches += 1;
     }
     if (ctx->nc > 0) {
-        k_hessian_contact<T><<<GRID(ctx->nc, 128), 128, 0, ctx->stream>>>(ctx->con, ctx->nc, cp, pos, ctx->frozen, ctx->A.diag_pb, val, spd, ctx->error_flag);
+        k_hessian_contact<T><<<GRID(ctx->nc, 128), 128, 0, ctx->stream>>>(ctx->con, ctx->nc, cp, pos, ctx->frozen, ctx->A.diag_pb, val, spd | newton_model, ctx->error_flag);
         ctx->launches++;
     }
 }
-void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym)
+void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model)
 {
-    if (f64) launch_hessian_t<double>(ctx, pos, ctx->A.val64, spd, sym);
-    else launch_hessian_t<float>(ctx, pos, ctx->A.val32, spd, sym);
+    if (f64) launch_hessian_t<double>(ctx, pos, ctx->A.val64, spd, sym, newton_model);
+    else launch_hessian_t<float>(ctx, pos, ctx->A.val32, spd, sym, newton_model);
 }
 void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alpha, double *pos)
 {
