@@ -156,8 +156,20 @@ typedef struct tsl_sizes {
 int tsl_get_sizes(tsl_ctx *ctx, tsl_sizes *out);
 /* benchmark hooks: run `iters` PCG iterations (no convergence test) on the last fp32 Hessian, and time
  * one kernel class with CUDA events on the context's stream; ms_out = average per launch.
- * what: 0 = PCG iteration (SpMV + 2 vector kernels), 1 = SpMV only, 2 = energy, 3 = residual, 4 = Hessian */
+ * what: 0 = PCG iteration (SpMV + vector kernels + preconditioner), 1 = SpMV only, 2 = energy, 3 = residual, 4 = Hessian,
+ * 5 = preconditioner application (one V-cycle) */
 int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out);
+/* solver options (the reference has none: its solve is a direct factorisation, code/engine/sparse_solver.py:85-105).
+ * TSL_OPT_PRECOND: 0 = block-Jacobi, 1 = geometric multigrid V-cycle over the cloth grid (default);
+ * TSL_OPT_MG_*: Chebyshev smoother degree (default 2), coarsest-grid sweep degree (8), eigenvalue interval ratio (8),
+ * safety factor on the power-iteration estimate of lambda_max (1.2). */
+enum tsl_option { TSL_OPT_PRECOND = 0, TSL_OPT_MG_DEGREE = 1, TSL_OPT_MG_COARSE_DEGREE = 2, TSL_OPT_MG_RATIO = 3, TSL_OPT_MG_SAFETY = 4 };
+int tsl_set_option(tsl_ctx *ctx, int key, double value);
+/* multigrid level read-back for tests: dims_host[3] = n0, n1, number of levels; lmax_host[1]; val_host [25][9][n0*n1] f32
+ * (5x5 stencil of 3x3 blocks, slot-major; level 0 returns the stencil copy of the cloth block).  Any pointer may be NULL. */
+int tsl_mg_get_level(tsl_ctx *ctx, int level, int *dims_host, float *lmax_host, float *val_host);
+/* z = M^-1 b with the preconditioner built by the last tsl_assemble / step (b, z: [3 n_verts] f64 device) */
+int tsl_precond_apply(tsl_ctx *ctx, const double *b_dev, double *z_dev);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */
 long long tsl_launch_count(tsl_ctx *ctx);
 

@@ -134,15 +134,15 @@ def test_linear_solvers(golden):
     F = e.residual()
     import scipy.sparse.linalg as spla
     ref = spla.spsolve(H, F)
-    x, (iters, flags, rr) = e.solve(torch.from_numpy(F).to(e.device), rel_tol=1e-6, max_iters=5000)
-    assert flags == 0 and iters > 0
+    x, (iters, flags, rr) = e.solve(torch.from_numpy(F).to(e.device), rel_tol=1e-6, max_iters=500)
+    assert flags == 0 and 0 < iters < 100
     assert _rel(x.cpu().numpy(), ref) < 1e-3            # fp32 Krylov on a kappa ~ 1e5 system
     e.assemble(_lib.ASM_HESSIAN | _lib.ASM_F64)
     H = e.matrix().tocsc()
     rhs = np.random.default_rng(0).standard_normal(F.shape)
     ref = spla.spsolve(H, rhs)
-    x, (iters, flags, rr) = e.solve(torch.from_numpy(rhs).to(e.device), rel_tol=1e-10, max_iters=20000)
-    assert (flags & 2) == 0 and rr < 1e-9, (iters, flags, rr)
+    x, (iters, flags, rr) = e.solve(torch.from_numpy(rhs).to(e.device), rel_tol=1e-10, max_iters=2000)
+    assert flags == 0 and rr < 1e-9 and iters < 300, (iters, flags, rr)
     assert _rel(x.cpu().numpy(), ref) < 1e-7
 
 

@@ -70,9 +70,13 @@ SIGNATURES = {
     "tsl_get_constraints": (_i, [_vp, _ip, _vp, _vp, _vp, _vp, _vp, _vp]),
     "tsl_get_sizes": (_i, [_vp, C.POINTER(SizesC)]),
     "tsl_bench_kernel": (_i, [_vp, _i, _i, C.POINTER(C.c_float)]),
+    "tsl_set_option": (_i, [_vp, _i, _d]),
+    "tsl_mg_get_level": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "tsl_precond_apply": (_i, [_vp, _vp, _vp]),
     "tsl_launch_count": (C.c_longlong, [_vp]),
 }
 
+OPT_PRECOND, OPT_MG_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_RATIO, OPT_MG_SAFETY = 0, 1, 2, 3, 4
 ASM_RESIDUAL, ASM_HESSIAN, ASM_SPD, ASM_SYM, ASM_F64, ASM_NEWTON = 1, 2, 4, 8, 16, 32
 
 _LIB = None

@@ -220,5 +220,26 @@ class ShellEngine:
         self._ck(self.L.tsl_bench_kernel(self.ctx, what, iters, C.byref(ms)))
         return ms.value
 
+    def set_option(self, key, value):
+        self._ck(self.L.tsl_set_option(self.ctx, int(key), float(value)))
+
+    def mg_level(self, level, values=True):
+        """multigrid level read-back: (n0, n1, n_levels, lmax, val[25, 3, 3, n0*n1] or None)"""
+        dims = (C.c_int * 3)()
+        lmax = C.c_float()
+        self._ck(self.L.tsl_mg_get_level(self.ctx, level, dims, C.byref(lmax), C.c_void_p(0)))
+        val = None
+        if values:
+            val = np.zeros((25, 3, 3, dims[0] * dims[1]), np.float32)
+            self._ck(self.L.tsl_mg_get_level(self.ctx, level, dims, C.byref(lmax), _np_ptr(val)))
+        return dims[0], dims[1], dims[2], lmax.value, val
+
+    def precond_apply(self, b):
+        """z = M^-1 b with the current preconditioner (b: [3 n_verts] float64 CUDA tensor)"""
+        self._sync_stream()
+        z = torch.zeros_like(b)
+        self._ck(self.L.tsl_precond_apply(self.ctx, _ptr(b), _ptr(z)))
+        return z
+
     def launch_count(self):
         return int(self.L.tsl_launch_count(self.ctx))

@@ -3,6 +3,8 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "tsl_internal.cuh"
@@ -49,7 +51,8 @@ int tsl_destroy(tsl_ctx *ctx)
 {
     if (!ctx) return TSL_ERR_INVALID;
     // device memory is released with the process / context; explicit frees for the large arrays
-    cudaFree(ctx->A.val32); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
+    tsl::mg_free(ctx);
+    cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
     cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q);
     for (int i = 0; i < 8; i++) cudaFree(ctx->bi[i]);
     cudaFree(ctx->minv32); cudaFree(ctx->minv64); cudaFree(ctx->F); cudaFree(ctx->sol); cudaFree(ctx->x1);
@@ -319,6 +322,8 @@ int tsl_finalize(tsl_ctx *ctx)
     TRY(upload(ctx, &A.diag_pb, diag));
     CK(cudaMalloc(&A.val32, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     CK(cudaMemset(A.val32, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
+    CK(cudaMalloc(&A.val32c, sizeof(float) * 9 * (size_t)A.nnzb_pad));
+    CK(cudaMemset(A.val32c, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     // ---- scratch
     CK(cudaMalloc(&ctx->F, sizeof(double) * 3 * nv));
     CK(cudaMalloc(&ctx->x1, sizeof(double) * 3 * nv));
@@ -335,6 +340,8 @@ int tsl_finalize(tsl_ctx *ctx)
     CK(cudaMemset(ctx->error_flag, 0, sizeof(int)));
     TRY(contact_alloc(ctx));
     TRY(linalg_alloc(ctx));
+    TRY(mg_alloc(ctx));
+    if (const char *e = getenv("TSL_PRECOND")) ctx->precond = atoi(e);
     ctx->finalized = true;
     return TSL_OK;
 }
@@ -400,7 +407,10 @@ int tsl_assemble(tsl_ctx *ctx, int flags)
         bool f64 = (flags & TSL_ASM_F64) != 0;
         if (f64) TRY(ensure_f64(ctx));
         launch_hessian(ctx, ctx->pos, f64, (flags & TSL_ASM_SPD) ? 1 : 0, (flags & TSL_ASM_SYM) ? 1 : 0, (flags & TSL_ASM_NEWTON) ? 1 : 0);
-        launch_block_jacobi(ctx, f64);
+        // the preconditioner hierarchy always comes from the clamped (positive definite) Newton matrix at the same state
+        launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);
+        TRY(mg_setup(ctx));
+        if (f64) launch_block_jacobi64(ctx);
         ctx->last_f64 = f64;
     }
     CK(cudaGetLastError());
@@ -411,10 +421,20 @@ int tsl_solve(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int ma
 {
     if (!ctx || !ctx->finalized || !rhs || !x) return TSL_ERR_INVALID;
     if (ctx->last_f64) return solve_bicgstab64(ctx, rhs, x, rel_tol, max_iters, st);
-    return solve_pcg32(ctx, rhs, x, rel_tol, max_iters, st);
+    return solve_pcg32(ctx, ctx->A.val32, rhs, x, rel_tol, max_iters, st);
 }
 
 // BaseScene.time_step (code/engine/BaseScene.py:1327-1370) + newton_step (:1159-1230)
+//
+// Newton iteration of the B200 path.  The residual is the reference's exact fp64 gradient, so the
+// fixed point is the reference's; matrix model, fp32 storage and Krylov tolerance only shape the path:
+//   * A_c = clamped (positive definite) Newton matrix -> multigrid hierarchy, and the operator of fallback solves;
+//   * A_e = exact membrane Hessian + Gauss-Newton bending -> operator of the regular solves (quadratic convergence
+//     near the minimiser).  If PCG meets negative curvature the step is redone with A_c, and the exact attempt is
+//     skipped for the next 1, 3, 7, 8, ... iterations (back-off);
+//   * forcing term: Eisenstat-Walker choice 2 clipped to [1e-3, 0.1];
+//   * line search: the reference's halving on E < E0 (floor 1e-8, x left at the last trial, quirk Q9), plus doubling
+//     while the energy keeps falling when alpha = 1 was accepted (clamped steps are too short along buckling modes).
 int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *stats)
 {
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
@@ -422,6 +442,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     cudaStream_t s = ctx->stream;
     tsl_step_stats st;
     memset(&st, 0, sizeof(st));
+    const bool trace = getenv("TSL_TRACE") != nullptr;
     double t0 = now_ms();
     // timestep_init: prev_pos <- pos
     CK(cudaMemcpyAsync(ctx->prev_pos, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
@@ -432,41 +453,46 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     TRY(energy_sync(ctx, &E0));
     double dt = ctx->cfg.dt;
     int it = 0;
-    // Inexact Newton on the engine's own Newton matrix (k_hessian_tri_newton): the exact membrane Hessian first; if PCG
-    // meets negative curvature the iteration is redone with the indefinite pieces clamped (positive definite).  The
-    // residual is exact fp64, so matrix model, fp32 storage and Krylov tolerance only shape the path to the same fixed
-    // point the reference's Newton iteration converges to.  Forcing term: Eisenstat-Walker choice 2.
+    const bool mgp = ctx->precond != 0 && ctx->mg.n_levels > 0;
+    const int max_pcg = mgp ? 200 : 4000;
     double eta = 0.1, fnorm_prev = -1;
+    int skip = 0, back = 0;
     while (it < max_newton) {
         it++;
         t0 = now_ms();
         launch_residual(ctx, ctx->pos);
-        launch_hessian(ctx, ctx->pos, false, 0, 0, 1);
-        launch_block_jacobi(ctx, false);
+        const bool try_exact = (skip == 0);
+        launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                    // A_c -> val32c
+        if (try_exact) launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);    // A_e -> val32
+        TRY(mg_setup(ctx));
         ctx->last_f64 = false;
         if (it == 1) TRY(check_device_flags(ctx));
         double t1 = now_ms();
         st.ms_assembly += t1 - t0;
         tsl_solve_stats ss;
-        TRY(solve_pcg32(ctx, ctx->F, ctx->sol, eta, 4000, &ss));
-        st.linear_iters += ss.iters;
-        if (ss.flags & 1) {
-            st.flags |= 1;
-            double t1b = now_ms();
-            launch_hessian(ctx, ctx->pos, false, 1, 0, 1);
-            launch_block_jacobi(ctx, false);
-            st.ms_assembly += now_ms() - t1b;
-            TRY(solve_pcg32(ctx, ctx->F, ctx->sol, eta, 4000, &ss));
+        int used = 0, it_exact = 0;
+        if (try_exact) {
+            TRY(solve_pcg32(ctx, ctx->A.val32, ctx->F, ctx->sol, eta, max_pcg, &ss));
             st.linear_iters += ss.iters;
+            it_exact = ss.iters;
+            if (ss.flags & 1) {
+                st.flags |= 1;
+                back = std::min(8, 2 * back + 1);
+                skip = back;
+                TRY(solve_pcg32(ctx, ctx->A.val32c, ctx->F, ctx->sol, eta, max_pcg, &ss));
+                st.linear_iters += ss.iters;
+                used = 1;
+            } else back = 0;
+        } else {
+            skip--;
+            TRY(solve_pcg32(ctx, ctx->A.val32c, ctx->F, ctx->sol, eta, max_pcg, &ss));
+            st.linear_iters += ss.iters;
+            used = 2;
         }
         st.flags |= (ss.flags & 2);
         double fnorm = ctx->ks_host->rr0;
-        if (fnorm_prev > 0 && fnorm > 0) {
-            double e2 = 0.9 * (fnorm / fnorm_prev) * (fnorm / fnorm_prev);
-            double safe = 0.9 * eta * eta;
-            if (safe > 0.1) e2 = std::max(e2, safe);
-            eta = std::min(0.1, std::max(1e-4, e2));
-        }
+        double eta_used = eta;
+        if (fnorm_prev > 0 && fnorm > 0) eta = std::min(0.1, std::max(1e-3, 0.9 * (fnorm / fnorm_prev) * (fnorm / fnorm_prev)));
         fnorm_prev = fnorm;
         launch_absmax(ctx, ctx->sol, n3, ctx->red_out + 1);
         CK(cudaMemcpyAsync(ctx->x1, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
@@ -485,9 +511,24 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
             if (E < E0) break;
             alpha /= 2;
         }
+        if (alpha == 1.0 && E < E0) {
+            // extrapolation: keep doubling while the energy falls
+            while (alpha < 64.0) {
+                double E2 = 0;
+                launch_axpy_pos(ctx, ctx->x1, ctx->sol, 2 * alpha, ctx->pos);
+                TRY(energy_sync(ctx, &E2));
+                st.linesearch_evals++;
+                if (E2 < E) { alpha *= 2; E = E2; }
+                else { launch_axpy_pos(ctx, ctx->x1, ctx->sol, alpha, ctx->pos); break; }
+            }
+        }
         st.ms_linesearch += now_ms() - t2;
-        E0 = E;                               // the reference re-evaluates the same point at the top of the loop
         st.delta = p_norm / dt;
+        if (trace)
+            fprintf(stderr, "[tsl] newton %3d: %s pcg=%d%s |F|=%.3e eta=%.1e delta=%.3e alpha=%.3g E=%.12e nc=%d\n", it,
+                    used == 0 ? "exact" : (used == 1 ? "negcurv->clamped" : "clamped(skip)"), ss.iters,
+                    used == 1 ? (std::string(" (exact try ") + std::to_string(it_exact) + ")").c_str() : "", fnorm, eta_used, st.delta, alpha, E, ctx->nc);
+        E0 = E;                               // the reference re-evaluates the same point at the top of the loop
         if (st.delta < tol) { st.converged = 1; break; }
     }
     st.newton_iters = it;
@@ -541,7 +582,10 @@ int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, cons
     launch_cloth_param_deri(ctx, c, ctx->pos, ctx->d_kb);
     // H = reference Hessian without projection, fp64
     launch_hessian(ctx, ctx->pos, true, 0, 0, 0);
-    launch_block_jacobi(ctx, true);
+    // preconditioner: multigrid hierarchy of the clamped Newton matrix at x_t
+    launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);
+    TRY(mg_setup(ctx));
+    launch_block_jacobi64(ctx);
     ctx->last_f64 = true;
     TRY(check_device_flags(ctx));
     double *z = z_out ? z_out : ctx->adj_z;
@@ -629,7 +673,7 @@ int tsl_get_sizes(tsl_ctx *ctx, tsl_sizes *out)
 int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out)
 {
     if (!ctx || !ctx->finalized || !ms_out || iters <= 0) return TSL_ERR_INVALID;
-    if (what == 0 || what == 1) return bench_pcg_iterations(ctx, iters, what == 1, ms_out);
+    if (what == 0 || what == 1 || what == 5) return bench_pcg_iterations(ctx, iters, what, ms_out);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, ctx->stream));
@@ -646,6 +690,31 @@ int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out)
     *ms_out = ms / iters;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     return TSL_OK;
+}
+
+int tsl_set_option(tsl_ctx *ctx, int key, double value)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    switch (key) {
+    case TSL_OPT_PRECOND: ctx->precond = (int)value; break;
+    case TSL_OPT_MG_DEGREE: REQUIRE(value >= 1 && value <= TSL_MG_MAX_DEGREE, "mg degree out of range"); ctx->mg.degree = (int)value; break;
+    case TSL_OPT_MG_COARSE_DEGREE: REQUIRE(value >= 1 && value <= TSL_MG_MAX_DEGREE, "mg coarse degree out of range"); ctx->mg.coarse_degree = (int)value; break;
+    case TSL_OPT_MG_RATIO: REQUIRE(value > 1, "mg ratio must exceed 1"); ctx->mg.ratio = (float)value; break;
+    case TSL_OPT_MG_SAFETY: REQUIRE(value >= 1, "mg safety must be >= 1"); ctx->mg.safety = (float)value; break;
+    default: ctx->err = "tsl_set_option: unknown key"; return TSL_ERR_INVALID;
+    }
+    return TSL_OK;
+}
+int tsl_mg_get_level(tsl_ctx *ctx, int level, int *dims, float *lmax, float *val_host)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    return mg_get_level(ctx, level, dims, lmax, val_host);
+}
+int tsl_precond_apply(tsl_ctx *ctx, const double *b_dev, double *z_dev)
+{
+    if (!ctx || !ctx->finalized || !b_dev || !z_dev) return TSL_ERR_INVALID;
+    // fp64 boundary, fp32 cycle: staged through the solver's own vectors
+    return precond_apply_f64io(ctx, b_dev, z_dev);
 }
 
 }  // extern "C"

@@ -25,7 +25,8 @@ struct SellMatrix {
     int *slice_base = nullptr;  // [n_slices+1] device, in blocks
     int *colidx = nullptr;      // [nnzb_pad] device
     int *diag_pb = nullptr;     // [n_rows] device: padded block id of the diagonal block
-    float *val32 = nullptr;     // [nnzb_pad*9]
+    float *val32 = nullptr;     // [nnzb_pad*9]  operator of the forward solve (exact or clamped Newton matrix)
+    float *val32c = nullptr;    // [nnzb_pad*9]  clamped (positive definite) Newton matrix: multigrid hierarchy + fallback operator
     double *val64 = nullptr;    // [nnzb_pad*9], allocated on first fp64 assembly
     // host copies (pattern export, slot lookup at setup)
     std::vector<int> h_rowptr, h_colidx, h_slice_base, h_colidx_pad;
@@ -56,6 +57,36 @@ struct ContactDev {
     double *dx0;       // [max_nc][3]
     double *T;         // [max_nc][6]
     double *n;         // [max_nc][3]
+};
+
+// ------------------------------------------------------------------------------------------------
+// Geometric multigrid over the cloth's structured vertex grid (tsl_mg.cu): the preconditioner of the forward PCG and
+// of the adjoint BiCGStab.  Level 0 is the sliced-ELL matrix itself (all vertices); level l >= 1 is an n0 x n1 vertex
+// grid whose operator is the Galerkin product P^T A P (bilinear P) stored as a 5x5 stencil of 3x3 blocks, SoA:
+//   val[(slot*9 + comp) * nvp + v],  slot = (dI+2)*5 + (dJ+2),  v = I*n1 + J
+// so that one thread per vertex reads consecutive addresses for every (slot, comp).
+#define TSL_MG_MAX_LEVELS 12
+#define TSL_MG_MAX_DEGREE 8
+struct MgLevel {
+    int n0 = 0, n1 = 0, nv = 0, nvp = 0;   // grid, vertices, vertices padded to 32
+    int nrows = 0;                         // rows of the level's vectors (level 0: all matrix rows; else nv)
+    float *val = nullptr;                  // stencil operator [225][nvp]  (level 0: stencil copy of the cloth block, Galerkin input only)
+    float *dinv = nullptr;                 // [nrows][9] inverse diagonal blocks
+    float *x[2] = { nullptr, nullptr };    // iterate ping-pong [3 nrows]
+    float *b = nullptr, *r = nullptr, *d = nullptr;   // right-hand side, residual, Chebyshev direction
+    float *pv[2] = { nullptr, nullptr };   // power-iteration vectors (kept across setups: warm start)
+};
+struct MgDev {
+    int n_levels = 0;                      // 0 = multigrid unavailable (no cloth)
+    int cloth_offset = 0;
+    MgLevel lev[TSL_MG_MAX_LEVELS];
+    float *coef = nullptr;                 // device [levels][TSL_MG_MAX_DEGREE][2]: Chebyshev (a, c) per step
+    float *powc = nullptr;                 // device [levels][2][2]: (a, c) of the first / later power-iteration steps
+    double *pow_acc = nullptr;             // device [levels][16]: |v_k|^2 of the power iteration
+    float *lmax = nullptr;                 // device [levels]: estimate (diagnostic read-back)
+    int setups = 0;
+    int degree = 2, coarse_degree = 8;
+    float ratio = 8.f, coarse_ratio = 200.f, safety = 1.2f;
 };
 
 // Krylov scalars kept on the device so a solve never needs the host inside the loop
@@ -115,6 +146,9 @@ struct tsl_ctx {
     double *bi[8] = { nullptr };                 // BiCGStab vectors: r, rhat, p, v, y, s, z, t
     double *sol = nullptr;                       // [3 n_verts] Newton direction (f64)
     double *x1 = nullptr;                        // [n_verts][3] line-search base
+    tsl::MgDev mg;
+    int precond = 1;                             // 0 block-Jacobi, 1 multigrid V-cycle
+    float *cg_r64tmp = nullptr;                  // [3 n_rows_pad] fp32 staging of fp64 vectors for the V-cycle
     tsl::KrylovScalars *ks = nullptr;            // device
     tsl::KrylovScalars *ks_host = nullptr;       // pinned
     // reductions

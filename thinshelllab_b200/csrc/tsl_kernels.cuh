@@ -9,7 +9,8 @@ void launch_face_normals(tsl_ctx *ctx, const ClothDev &c, const double *pos);
 void launch_energy(tsl_ctx *ctx, const double *pos, double *out_dev);
 void launch_residual(tsl_ctx *ctx, const double *pos);
 void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kb);
-void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model);
+// into_clamped: the fp32 result goes to A.val32c (multigrid hierarchy / fallback operator) instead of A.val32
+void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model, bool into_clamped = false);
 void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alpha, double *pos);
 void launch_update_vel(tsl_ctx *ctx);
 void launch_update_ref_angle(tsl_ctx *ctx, const ClothDev &c);
@@ -26,9 +27,20 @@ int contact_detect(tsl_ctx *ctx, const double *pos, const double *prev_pos);
 
 // tsl_linalg.cu
 int linalg_alloc(tsl_ctx *ctx);
-void launch_block_jacobi(tsl_ctx *ctx, bool f64);
-int solve_pcg32(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st);
+void launch_block_jacobi64(tsl_ctx *ctx);
+// forward solve: PCG (fp32 vectors, fp64 reductions) on `opval` (A.val32 or A.val32c), preconditioned by the hierarchy of the
+// last mg_setup; st->flags bit0 = negative curvature met (x = last iterate before it, or the preconditioned gradient)
+int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st);
+// adjoint solve: right-preconditioned BiCGStab in fp64 on A.val64, restarted on breakdown
 int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st);
-int bench_pcg_iterations(tsl_ctx *ctx, int iters, int spmv_only, float *ms_out);
+int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out);
+int precond_apply_f64io(tsl_ctx *ctx, const double *in, double *out);
+
+// tsl_mg.cu
+int mg_alloc(tsl_ctx *ctx);
+void mg_free(tsl_ctx *ctx);
+int mg_setup(tsl_ctx *ctx);
+int mg_apply(tsl_ctx *ctx, const float *b, float *z, double *acc_bz);
+int mg_get_level(tsl_ctx *ctx, int level, int *dims, float *lmax, float *val_host);
 
 }  // namespace tsl

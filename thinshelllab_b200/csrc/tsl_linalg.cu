@@ -105,28 +105,27 @@ __device__ __forceinline__ void apply_minv(const T *__restrict__ minv, int r, T 
 }
 
 // ------------------------------------------------------------------------------------------------ PCG (fp32)
-// init: x = 0, r = b, z = M^-1 r, p = z, rz[0] = r.z, rr[0] = r.r
-__global__ void __launch_bounds__(256) k_pcg_init(int n_rows, const double *__restrict__ b, const float *__restrict__ minv,
-                                                  float *x, float *r, float *z, float *p, KrylovScalars *ks)
+// Preconditioned CG with the preconditioner applied between kernels (mg_apply: V-cycle or block-Jacobi):
+//   init      : x = 0, r = b, rr[0] = r.r                         z = M r, rz[0] = r.z (fused in the preconditioner)   p = z
+//   iteration : q = A p, pq[c] = p.q | x += a p, r -= a q, rr[n] | z = M r, rz[n] = r.z                                | p = z + (rz[n]/rz[c]) p
+// c = it & 1, n = c ^ 1.  Step lengths are formed on the device; the host reads the scalars once per iteration
+// (an iteration is a whole V-cycle, so the read-back is noise) to test convergence / negative curvature.
+__global__ void __launch_bounds__(256) k_pcg_init(int n_rows, int n_alloc, const double *__restrict__ b, float *x, float *r, KrylovScalars *ks)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
-    double rz = 0, rr = 0;
-    if (row < n_rows) {
-        float r0 = (float)b[3 * row], r1 = (float)b[3 * row + 1], r2 = (float)b[3 * row + 2];
-        float z0, z1, z2;
-        apply_minv<float>(minv, row, r0, r1, r2, z0, z1, z2);
+    double rr = 0;
+    if (row < n_alloc) {
+        float r0 = 0, r1 = 0, r2 = 0;
+        if (row < n_rows) { r0 = (float)b[3 * row]; r1 = (float)b[3 * row + 1]; r2 = (float)b[3 * row + 2]; }
         x[3 * row] = x[3 * row + 1] = x[3 * row + 2] = 0.f;
         r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
-        z[3 * row] = z0; z[3 * row + 1] = z1; z[3 * row + 2] = z2;
-        p[3 * row] = z0; p[3 * row + 1] = z1; p[3 * row + 2] = z2;
-        rz = (double)r0 * z0 + (double)r1 * z1 + (double)r2 * z2;
         rr = (double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2;
     }
-    block_atomic_sum2(rz, rr, &ks->acc_rz[0], &ks->acc_rr[0]);
+    block_atomic_sum2(rr, 0.0, &ks->acc_rr[0], nullptr);
 }
-// iteration `it`:  alpha = rz[it&1] / pq[it&1];  x += alpha p;  r -= alpha q;  z = M^-1 r;  rz[(it+1)&1] += r.z;  rr[(it+1)&1] += r.r
-__global__ void __launch_bounds__(256) k_pcg_update(int n_rows, int it, const float *__restrict__ minv, const float *__restrict__ p,
-                                                    const float *__restrict__ q, float *x, float *r, float *z, KrylovScalars *ks)
+// alpha = rz[c] / pq[c];  x += alpha p;  r -= alpha q;  rr[n] += r.r
+__global__ void __launch_bounds__(256) k_pcg_update(int n_rows, int it, const float *__restrict__ p, const float *__restrict__ q,
+                                                    float *x, float *r, KrylovScalars *ks)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     int cur = it & 1, nxt = cur ^ 1;
@@ -138,33 +137,33 @@ __global__ void __launch_bounds__(256) k_pcg_update(int n_rows, int it, const fl
     if (bad && it == 0 && row < n_rows) {   // no progress yet: fall back to the preconditioned gradient direction
         x[3 * row] = p[3 * row]; x[3 * row + 1] = p[3 * row + 1]; x[3 * row + 2] = p[3 * row + 2];
     }
-    if (row == 0) ks->acc_pq[nxt] = 0;  // consumed by iteration it-1, next written by iteration it+1
-    double rz = 0, rr = 0;
-    if (row < n_rows && !frozen) {
+    if (row == 0) ks->acc_pq[nxt] = 0;      // consumed by iteration it-1, next written by iteration it+1
+    if (frozen) {                           // keep the scalars of the frozen state so later iterations are no-ops
+        if (row == 0) { ks->acc_rr[nxt] = ks->acc_rr[cur]; }
+        return;
+    }
+    double rr = 0;
+    if (row < n_rows) {
         float alpha = (float)(rzc / pq);
         float r0 = r[3 * row] - alpha * q[3 * row], r1 = r[3 * row + 1] - alpha * q[3 * row + 1], r2 = r[3 * row + 2] - alpha * q[3 * row + 2];
         x[3 * row] += alpha * p[3 * row]; x[3 * row + 1] += alpha * p[3 * row + 1]; x[3 * row + 2] += alpha * p[3 * row + 2];
-        float z0, z1, z2;
-        apply_minv<float>(minv, row, r0, r1, r2, z0, z1, z2);
         r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
-        z[3 * row] = z0; z[3 * row + 1] = z1; z[3 * row + 2] = z2;
-        rz = (double)r0 * z0 + (double)r1 * z1 + (double)r2 * z2;
         rr = (double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2;
     }
-    if (frozen) {                       // keep the scalars of the frozen state so later iterations are no-ops
-        if (row == 0) { ks->acc_rz[nxt] = rzc; ks->acc_rr[nxt] = ks->acc_rr[cur]; }
-        return;
-    }
-    block_atomic_sum2(rz, rr, &ks->acc_rz[nxt], &ks->acc_rr[nxt]);
+    block_atomic_sum2(rr, 0.0, &ks->acc_rr[nxt], nullptr);
 }
-// p = z + beta p with beta = rz[(it+1)&1] / rz[it&1]
+// p = z + beta p with beta = rz[n] / rz[c]   (it < 0: p = z)
 __global__ void __launch_bounds__(256) k_pcg_direction(int n, int it, const float *__restrict__ z, float *p, KrylovScalars *ks)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (it < 0) { if (i < n) p[i] = z[i]; return; }
     int cur = it & 1, nxt = cur ^ 1;
     const bool bad = !(ks->acc_pq[cur] > 0.0);     // same test as k_pcg_update (acc_pq[cur] is still intact)
     if (bad && i == 0) atomicOr(&ks->flags, 1);
-    if ((ks->flags & 1) || bad) return;
+    if ((ks->flags & 1) || bad) {
+        if (i == 0) ks->acc_rz[nxt] = ks->acc_rz[cur];
+        return;
+    }
     float beta = (float)(ks->acc_rz[nxt] / ks->acc_rz[cur]);
     if (i < n) p[i] = z[i] + beta * p[i];
 }
@@ -173,14 +172,20 @@ __global__ void k_f32_to_f64(int n, const float *__restrict__ a, double *b)
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) b[i] = (double)a[i];
 }
+__global__ void k_f64_to_f32(int n, int n_alloc, const double *__restrict__ a, float *b)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_alloc) b[i] = i < n ? (float)a[i] : 0.f;
+}
 
 int linalg_alloc(tsl_ctx *ctx)
 {
     int nr = ctx->A.n_slices * 32;
     size_t nb = sizeof(float) * 3 * (size_t)nr;
     CK(cudaMalloc(&ctx->cg_x, nb)); CK(cudaMalloc(&ctx->cg_r, nb)); CK(cudaMalloc(&ctx->cg_z, nb));
-    CK(cudaMalloc(&ctx->cg_p, nb)); CK(cudaMalloc(&ctx->cg_q, nb));
-    CK(cudaMemset(ctx->cg_p, 0, nb)); CK(cudaMemset(ctx->cg_x, 0, nb));
+    CK(cudaMalloc(&ctx->cg_p, nb)); CK(cudaMalloc(&ctx->cg_q, nb)); CK(cudaMalloc(&ctx->cg_r64tmp, nb));
+    CK(cudaMemset(ctx->cg_p, 0, nb)); CK(cudaMemset(ctx->cg_x, 0, nb)); CK(cudaMemset(ctx->cg_r, 0, nb));
+    CK(cudaMemset(ctx->cg_z, 0, nb)); CK(cudaMemset(ctx->cg_q, 0, nb)); CK(cudaMemset(ctx->cg_r64tmp, 0, nb));
     CK(cudaMalloc(&ctx->minv32, sizeof(float) * 9 * (size_t)nr));
     CK(cudaMalloc(&ctx->ks, sizeof(KrylovScalars)));
     CK(cudaMallocHost(&ctx->ks_host, sizeof(KrylovScalars)));
@@ -188,45 +193,62 @@ int linalg_alloc(tsl_ctx *ctx)
     return TSL_OK;
 }
 
-void launch_block_jacobi(tsl_ctx *ctx, bool f64)
+void launch_block_jacobi64(tsl_ctx *ctx)
 {
     int n = ctx->cfg.n_verts;
-    if (f64) k_block_jacobi<double><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, ctx->A.diag_pb, ctx->A.val64, ctx->minv64);
-    else k_block_jacobi<float><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, ctx->A.diag_pb, ctx->A.val32, ctx->minv32);
+    k_block_jacobi<double><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, ctx->A.diag_pb, ctx->A.val64, ctx->minv64);
     ctx->launches++;
 }
 
-static void pcg_iteration(tsl_ctx *ctx, int it)
+static int pcg_iteration(tsl_ctx *ctx, const float *opval, int it)
 {
     int n = ctx->cfg.n_verts;
     const SellMatrix &A = ctx->A;
     KrylovScalars *ks = ctx->ks;
-    int cur = it & 1;
+    int cur = it & 1, nxt = cur ^ 1;
     // q = A p, pq[cur] += p.q ; also clears rz/rr of the next parity (they were read by iteration it-1's direction update)
-    k_spmv_dots<float><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, A.slice_base, A.colidx, A.val32, ctx->cg_p, ctx->cg_q, ctx->cg_p,
-                                                              &ks->acc_pq[cur], nullptr, &ks->acc_rz[cur ^ 1], &ks->acc_rr[cur ^ 1]);
-    k_pcg_update<<<GRID(n, 256), 256, 0, ctx->stream>>>(n, it, ctx->minv32, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ctx->cg_z, ks);
+    k_spmv_dots<float><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, ctx->cg_p,
+                                                              &ks->acc_pq[cur], nullptr, &ks->acc_rz[nxt], &ks->acc_rr[nxt]);
+    k_pcg_update<<<GRID(n, 256), 256, 0, ctx->stream>>>(n, it, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ks);
+    ctx->launches += 2;
+    int rc = mg_apply(ctx, ctx->cg_r, ctx->cg_z, &ks->acc_rz[nxt]);
+    if (rc != TSL_OK) return rc;
     k_pcg_direction<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(3 * n, it, ctx->cg_z, ctx->cg_p, ks);
-    ctx->launches += 3;
+    ctx->launches++;
+    return TSL_OK;
 }
 
-int solve_pcg32(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
+static int pcg_start(tsl_ctx *ctx, const double *rhs)
+{
+    int n = ctx->cfg.n_verts, nr = ctx->A.n_slices * 32;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(ctx->ks, 0, sizeof(KrylovScalars), s));
+    k_pcg_init<<<GRID(nr, 256), 256, 0, s>>>(n, nr, rhs, ctx->cg_x, ctx->cg_r, ctx->ks);
+    ctx->launches++;
+    int rc = mg_apply(ctx, ctx->cg_r, ctx->cg_z, &ctx->ks->acc_rz[0]);
+    if (rc != TSL_OK) return rc;
+    k_pcg_direction<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, -1, ctx->cg_z, ctx->cg_p, ctx->ks);
+    ctx->launches++;
+    return TSL_OK;
+}
+
+int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
 {
     int n = ctx->cfg.n_verts;
     cudaStream_t s = ctx->stream;
-    CK(cudaMemsetAsync(ctx->ks, 0, sizeof(KrylovScalars), s));
-    k_pcg_init<<<GRID(n, 256), 256, 0, s>>>(n, rhs, ctx->minv32, ctx->cg_x, ctx->cg_r, ctx->cg_z, ctx->cg_p, ctx->ks);
-    ctx->launches++;
+    int rc = pcg_start(ctx, rhs);
+    if (rc != TSL_OK) return rc;
     CK(cudaMemcpyAsync(ctx->ks_host, ctx->ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     double rr0 = ctx->ks_host->acc_rr[0];
     int it = 0, flags = 0;
     double rr = rr0;
-    const int check_every = 10;
+    // the block-Jacobi iteration is three short kernels: poll less often there
+    const int check_every = (ctx->precond == 0 || ctx->mg.n_levels == 0) ? 10 : 1;
     if (rr0 > 0) {
         while (it < max_iters) {
             int chunk = std::min(check_every, max_iters - it);
-            for (int k = 0; k < chunk; k++, it++) pcg_iteration(ctx, it);
+            for (int k = 0; k < chunk; k++, it++) { rc = pcg_iteration(ctx, opval, it); if (rc != TSL_OK) return rc; }
             CK(cudaMemcpyAsync(ctx->ks_host, ctx->ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
             rr = ctx->ks_host->acc_rr[it & 1];
@@ -245,23 +267,29 @@ int solve_pcg32(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int 
     return TSL_OK;
 }
 
-int bench_pcg_iterations(tsl_ctx *ctx, int iters, int spmv_only, float *ms_out)
+// what: 0 = full PCG iterations, 1 = SpMV only, 5 = V-cycle only
+int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out)
 {
     int n = ctx->cfg.n_verts;
     cudaStream_t s = ctx->stream;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     // a well-defined state: r = F, p = z = M^-1 F
-    CK(cudaMemsetAsync(ctx->ks, 0, sizeof(KrylovScalars), s));
-    k_pcg_init<<<GRID(n, 256), 256, 0, s>>>(n, ctx->F, ctx->minv32, ctx->cg_x, ctx->cg_r, ctx->cg_z, ctx->cg_p, ctx->ks);
-    ctx->launches++;
+    int rc = pcg_start(ctx, ctx->F);
+    if (rc != TSL_OK) return rc;
     CK(cudaEventRecord(e0, s));
     for (int it = 0; it < iters; it++) {
-        if (spmv_only) {
+        if (what == 1) {
             k_spmv_dots<float><<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32, ctx->cg_p, ctx->cg_q, ctx->cg_p,
                                                             &ctx->ks->acc_pq[it & 1], nullptr, nullptr, nullptr);
             ctx->launches++;
-        } else pcg_iteration(ctx, it);
+        } else if (what == 5) {
+            rc = mg_apply(ctx, ctx->cg_r, ctx->cg_z, nullptr);
+            if (rc != TSL_OK) return rc;
+        } else {
+            rc = pcg_iteration(ctx, ctx->A.val32, it);
+            if (rc != TSL_OK) return rc;
+        }
     }
     CK(cudaEventRecord(e1, s));
     CK(cudaEventSynchronize(e1));
@@ -273,7 +301,12 @@ int bench_pcg_iterations(tsl_ctx *ctx, int iters, int spmv_only, float *ms_out)
 }
 
 // ------------------------------------------------------------------------------------------------ BiCGStab (fp64)
-// vectors: bi[0]=r, [1]=rhat, [2]=p, [3]=v, [4]=y, [5]=s, [6]=z, [7]=t ; x accumulated in the caller's buffer
+// Right-preconditioned BiCGStab on the fp64 matrix (the reference's un-projected, non-symmetric Hessian):
+//   p = r + beta (p - omega v);  y = M p;  v = A y;  alpha = rho / (rhat.v);  s = r - alpha v;  z = M s;  t = A z;
+//   omega = (t.s)/(t.t);  dx += alpha y + omega z;  r = s - omega t
+// M = the fp32 V-cycle of the clamped Newton matrix at the same state (or fp64 block-Jacobi, precond == 0).
+// vectors: bi[0]=r, [1]=rhat, [2]=p, [3]=v, [4]=y, [5]=s, [6]=z, [7]=t ; the correction dx accumulates in ctx->sol,
+// the outer loop adds it to x and restarts from the true residual (breakdown recovery + iterative refinement).
 __global__ void __launch_bounds__(256) k_bi_init(int n, const double *__restrict__ b, double *x, double *r, double *rhat, double *p, double *v,
                                                  KrylovScalars *ks)
 {
@@ -286,11 +319,10 @@ __global__ void __launch_bounds__(256) k_bi_init(int n, const double *__restrict
     }
     block_atomic_sum2(rr, rr, &ks->acc_rho[0], &ks->acc_rr[0]);
 }
-// K_a (iteration it): beta = (rho_new/rho_old)(alpha/omega); p = r + beta (p - omega v); y = M^-1 p
-__global__ void __launch_bounds__(256) k_bi_a(int n_rows, int it, const double *__restrict__ minv, const double *__restrict__ r,
-                                              const double *__restrict__ v, double *p, double *y, KrylovScalars *ks)
+// K_a (iteration it): beta = (rho_new/rho_old)(alpha/omega); p = r + beta (p - omega v)
+__global__ void __launch_bounds__(256) k_bi_a(int n, int it, const double *__restrict__ r, const double *__restrict__ v, double *p, KrylovScalars *ks)
 {
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cur = it & 1;
     if (ks->flags & 1) return;
     double beta = 0, omega = 0;
@@ -299,35 +331,18 @@ __global__ void __launch_bounds__(256) k_bi_a(int n_rows, int it, const double *
         omega = ks->acc_ts / ks->acc_tt;
         beta = (rho_new / rho_old) * (ks->alpha / omega);
     }
-    if (row >= n_rows) return;
-    double pp[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        int i = 3 * row + k;
-        pp[k] = r[i] + beta * (p[i] - omega * v[i]);
-        p[i] = pp[k];
-    }
-    double y0, y1, y2;
-    apply_minv<double>(minv, row, pp[0], pp[1], pp[2], y0, y1, y2);
-    y[3 * row] = y0; y[3 * row + 1] = y1; y[3 * row + 2] = y2;
+    if (i < n) p[i] = r[i] + beta * (p[i] - omega * v[i]);
 }
-// K_c: alpha = rho_new / (rhat.v); s = r - alpha v; z = M^-1 s
-__global__ void __launch_bounds__(256) k_bi_c(int n_rows, int it, const double *__restrict__ minv, const double *__restrict__ r,
-                                              const double *__restrict__ v, double *s, double *z, KrylovScalars *ks)
+// K_c: alpha = rho_new / (rhat.v); s = r - alpha v
+__global__ void __launch_bounds__(256) k_bi_c(int n, int it, const double *__restrict__ r, const double *__restrict__ v, double *s, KrylovScalars *ks)
 {
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
     int cur = it & 1;
     if (ks->flags & 1) return;
     double rhv = ks->acc_rhv;
-    if (!(rhv != 0.0) || !(rhv == rhv)) { if (row == 0) atomicOr(&ks->flags, 1); return; }
+    if (!(rhv != 0.0) || !(rhv == rhv)) { if (i == 0) atomicOr(&ks->flags, 1); return; }
     double alpha = ks->acc_rho[cur] / rhv;
-    if (row >= n_rows) return;
-    double ss[3];
-#pragma unroll
-    for (int k = 0; k < 3; k++) { int i = 3 * row + k; ss[k] = r[i] - alpha * v[i]; s[i] = ss[k]; }
-    double z0, z1, z2;
-    apply_minv<double>(minv, row, ss[0], ss[1], ss[2], z0, z1, z2);
-    z[3 * row] = z0; z[3 * row + 1] = z1; z[3 * row + 2] = z2;
+    if (i < n) s[i] = r[i] - alpha * v[i];
 }
 // K_e: omega = ts/tt; x += alpha y + omega z; r = s - omega t; rho[(it+1)&1] += rhat.r; rr[(it+1)&1] += r.r
 __global__ void __launch_bounds__(256) k_bi_e(int n, int it, const double *__restrict__ y, const double *__restrict__ z,
@@ -358,6 +373,61 @@ __global__ void k_bi_store_alpha(int it, KrylovScalars *ks)
     if (ks->flags & 1) return;
     ks->alpha = ks->acc_rho[it & 1] / ks->acc_rhv;
 }
+// out = M in for fp64 vectors
+template <typename T>
+__global__ void __launch_bounds__(256) k_apply_minv64(int n_rows, const T *__restrict__ minv, const double *__restrict__ in, double *out)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= n_rows) return;
+    double z0, z1, z2;
+    apply_minv<double>(minv, row, in[3 * row], in[3 * row + 1], in[3 * row + 2], z0, z1, z2);
+    out[3 * row] = z0; out[3 * row + 1] = z1; out[3 * row + 2] = z2;
+}
+int precond_apply_f64io(tsl_ctx *ctx, const double *in, double *out);
+static int precond64(tsl_ctx *ctx, const double *in, double *out)
+{
+    int n = ctx->cfg.n_verts;
+    cudaStream_t s = ctx->stream;
+    if (ctx->precond == 0 || ctx->mg.n_levels == 0) {
+        k_apply_minv64<double><<<GRID(n, 256), 256, 0, s>>>(n, ctx->minv64, in, out);
+        ctx->launches++;
+        return TSL_OK;
+    }
+    return precond_apply_f64io(ctx, in, out);
+}
+// out = M in through the fp32 preconditioner of the last mg_setup (V-cycle, or fp32 block-Jacobi when precond == 0)
+int precond_apply_f64io(tsl_ctx *ctx, const double *in, double *out)
+{
+    int n = ctx->cfg.n_verts, nr = ctx->A.n_slices * 32;
+    cudaStream_t s = ctx->stream;
+    k_f64_to_f32<<<GRID(3 * nr, 256), 256, 0, s>>>(3 * n, 3 * nr, in, ctx->cg_r64tmp);
+    int rc = mg_apply(ctx, ctx->cg_r64tmp, ctx->cg_z, nullptr);
+    if (rc != TSL_OK) return rc;
+    k_f32_to_f64<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, ctx->cg_z, out);
+    ctx->launches += 2;
+    return TSL_OK;
+}
+// r = b - A x (fp64), rr = |r|^2 into acc
+__global__ void __launch_bounds__(256) k_residual64(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
+                                                    const double *__restrict__ val, const double *__restrict__ b, const double *__restrict__ x,
+                                                    double *r, double *acc_rr)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double rr = 0;
+    if (row < n_rows) {
+        double y0, y1, y2;
+        spmv_row<double>(slice_base, colidx, val, x, row, y0, y1, y2);
+        double r0 = b[3 * row] - y0, r1 = b[3 * row + 1] - y1, r2 = b[3 * row + 2] - y2;
+        r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
+        rr = r0 * r0 + r1 * r1 + r2 * r2;
+    }
+    block_atomic_sum2(rr, 0.0, acc_rr, nullptr);
+}
+__global__ void k_axpy64(int n, const double *__restrict__ dx, double *x)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] += dx[i];
+}
 
 int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
 {
@@ -366,42 +436,71 @@ int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol,
     const SellMatrix &A = ctx->A;
     KrylovScalars *ks = ctx->ks;
     double *r = ctx->bi[0], *rhat = ctx->bi[1], *p = ctx->bi[2], *v = ctx->bi[3], *y = ctx->bi[4], *sv = ctx->bi[5], *z = ctx->bi[6], *t = ctx->bi[7];
-    CK(cudaMemsetAsync(ks, 0, sizeof(KrylovScalars), s));
-    k_bi_init<<<GRID(n3, 256), 256, 0, s>>>(n3, rhs, x, r, rhat, p, v, ks);
-    ctx->launches++;
-    CK(cudaMemcpyAsync(ctx->ks_host, ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    double rr0 = ctx->ks_host->acc_rr[0], rr = rr0;
-    int it = 0, flags = 0;
-    const int check_every = 10;
-    if (rr0 > 0) {
+    double *dx = ctx->sol;                 // correction of the current restart cycle
+    double *res = ctx->adj_rhs;            // true residual b - A x
+    CK(cudaMemsetAsync(x, 0, sizeof(double) * n3, s));
+    CK(cudaMemcpyAsync(res, rhs, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
+    double rr00 = -1, rr = 0;
+    int it = 0, flags = 0, restarts = 0;
+    const int check_every = (ctx->precond == 0 || ctx->mg.n_levels == 0) ? 10 : 1;
+    const int max_restarts = 8;
+    while (true) {
+        CK(cudaMemsetAsync(ks, 0, sizeof(KrylovScalars), s));
+        k_bi_init<<<GRID(n3, 256), 256, 0, s>>>(n3, res, dx, r, rhat, p, v, ks);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(ctx->ks_host, ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        double rr0 = ctx->ks_host->acc_rr[0];
+        if (rr00 < 0) rr00 = rr0;
+        rr = rr0;
+        if (!(rr0 == rr0)) { ctx->err = "BiCGStab: NaN residual"; return TSL_ERR_NUMERIC; }
+        if (rr0 <= rel_tol * rel_tol * rr00 || rr00 == 0) break;
+        int it_cycle = 0;
+        bool broke = false;
         while (it < max_iters) {
             int chunk = std::min(check_every, max_iters - it);
-            for (int k = 0; k < chunk; k++, it++) {
-                int cur = it & 1;
-                k_bi_a<<<GRID(n, 256), 256, 0, s>>>(n, it, ctx->minv64, r, v, p, y, ks);
+            for (int k = 0; k < chunk; k++, it++, it_cycle++) {
+                int cur = it_cycle & 1;
+                k_bi_a<<<GRID(n3, 256), 256, 0, s>>>(n3, it_cycle, r, v, p, ks);
+                int rc = precond64(ctx, p, y);
+                if (rc != TSL_OK) return rc;
                 // v = A y, rhv += rhat.v ; clears rho/rr of the next parity (K_a has read rho_old) and ts/tt (K_a has read omega)
                 k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, y, v, rhat, &ks->acc_rhv, nullptr,
                                                                  &ks->acc_rho[cur ^ 1], &ks->acc_rr[cur ^ 1]);
-                k_bi_c<<<GRID(n, 256), 256, 0, s>>>(n, it, ctx->minv64, r, v, sv, z, ks);
-                k_bi_store_alpha<<<1, 1, 0, s>>>(it, ks);
+                k_bi_c<<<GRID(n3, 256), 256, 0, s>>>(n3, it_cycle, r, v, sv, ks);
+                k_bi_store_alpha<<<1, 1, 0, s>>>(it_cycle, ks);
                 CK(cudaMemsetAsync(&ks->acc_ts, 0, 2 * sizeof(double), s));
+                rc = precond64(ctx, sv, z);
+                if (rc != TSL_OK) return rc;
                 // t = A z, ts += s.t, tt += t.t
                 k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, z, t, sv, &ks->acc_ts, &ks->acc_tt, nullptr, nullptr);
-                k_bi_e<<<GRID(n3, 256), 256, 0, s>>>(n3, it, y, z, sv, t, rhat, x, r, ks);
+                k_bi_e<<<GRID(n3, 256), 256, 0, s>>>(n3, it_cycle, y, z, sv, t, rhat, dx, r, ks);
                 ctx->launches += 6;
             }
             CK(cudaMemcpyAsync(ctx->ks_host, ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            rr = ctx->ks_host->acc_rr[it & 1];
-            flags = ctx->ks_host->flags;
-            if (!(rr == rr)) { ctx->err = "BiCGStab produced NaN"; return TSL_ERR_NUMERIC; }
-            if (flags & 1) break;
-            if (rr <= rel_tol * rel_tol * rr0) break;
+            rr = ctx->ks_host->acc_rr[it_cycle & 1];
+            if (!(rr == rr)) { broke = true; break; }          // dx is poisoned: drop this cycle's correction
+            if (ctx->ks_host->flags & 1) break;                // breakdown: dx holds the last good iterate
+            if (rr <= rel_tol * rel_tol * rr00) break;
         }
-        if (it >= max_iters && rr > rel_tol * rel_tol * rr0) flags |= 2;
+        // x += dx, true residual for the next cycle / the final report
+        if (!broke) {
+            k_axpy64<<<GRID(n3, 256), 256, 0, s>>>(n3, dx, x);
+            ctx->launches++;
+        }
+        CK(cudaMemsetAsync(&ks->acc_rr[0], 0, sizeof(double), s));
+        k_residual64<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, rhs, x, res, &ks->acc_rr[0]);
+        ctx->launches++;
+        CK(cudaMemcpyAsync(ctx->ks_host, ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        rr = ctx->ks_host->acc_rr[0];
+        if (!(rr == rr)) { ctx->err = "BiCGStab produced NaN"; return TSL_ERR_NUMERIC; }
+        if (rr <= rel_tol * rel_tol * rr00) break;
+        if (it >= max_iters) { flags |= 2; break; }
+        if (++restarts > max_restarts) { flags |= 1; break; }
     }
-    if (st) { st->iters = it; st->flags = flags; st->rel_residual = rr0 > 0 ? sqrt(rr / rr0) : 0.0; }
+    if (st) { st->iters = it; st->flags = flags; st->rel_residual = rr00 > 0 ? sqrt(rr / rr00) : 0.0; }
     CK(cudaGetLastError());
     return TSL_OK;
 }

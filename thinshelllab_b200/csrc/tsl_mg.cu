@@ -1,0 +1,577 @@
+// tsl_mg.cu -- geometric multigrid preconditioner over the cloth's structured vertex grid (sm_100a).
+//
+// The reference solves every Newton / adjoint system with a sparse direct solver (cuSOLVER QR through CuPy,
+// code/engine/sparse_solver.py:85-105).  The B200 path keeps the matrix block-sparse and iterates; what makes
+// that competitive is this preconditioner: Cloth is always an (N+1) x (M+1) vertex grid
+// (code/engine/model_fold_offset.py:929-1018), so the hierarchy is geometric --
+//   * prolongation P: bilinear per coordinate (vertices with even (i, j) survive), applied per x/y/z component,
+//   * coarse operators: Galerkin products P^T A P, recomputed on the device for every new matrix; a fine stencil of
+//     radius 2 (triangle + hinge neighbours) gives coarse stencils of radius 2 on every level -> 5x5 blocks of 3x3,
+//   * smoother: Chebyshev polynomial in D^-1 A (D = 3x3 diagonal blocks) on [lmax/ratio, lmax]; lmax(D^-1 A) comes
+//     from a few warm-started power iterations per level with a safety factor (the iteration is sensitive to an
+//     under-estimate, not to an over-estimate),
+//   * coarsest grid (<= 6 vertices in one direction): a longer Chebyshev sweep, no direct solve.
+// The V-cycle is symmetric (same polynomial before and after the coarse correction), so it is a valid PCG
+// preconditioner.  Everything is fp32; all coefficients live in device memory, so setup and application never
+// synchronise with the host.  Bound: every kernel streams its level's matrix once (HBM / L2), the small levels are
+// launch-latency bound.
+#include "tsl_internal.cuh"
+#include "tsl_kernels.cuh"
+
+namespace tsl {
+
+#define GRID(n, b) (unsigned)(((n) + (b) - 1) / (b))
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return TSL_ERR_CUDA; } } while (0)
+
+// ------------------------------------------------------------------------------------------------ row operators
+struct SellOp {
+    const int *slice_base, *colidx;
+    const float *val;
+    __device__ __forceinline__ void mul(int row, const float *__restrict__ x, float &y0, float &y1, float &y2) const
+    {
+        int S = row >> 5, lane = row & 31;
+        int b0 = slice_base[S], b1 = slice_base[S + 1];
+        float a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 2
+        for (int b = b0; b < b1; b += 32) {
+            int col = __ldg(colidx + b + lane);
+            const float *v = val + (long long)b * 9 + lane;
+            float x0 = x[3 * col], x1 = x[3 * col + 1], x2 = x[3 * col + 2];
+            a0 += __ldg(v) * x0 + __ldg(v + 32) * x1 + __ldg(v + 64) * x2;
+            a1 += __ldg(v + 96) * x0 + __ldg(v + 128) * x1 + __ldg(v + 160) * x2;
+            a2 += __ldg(v + 192) * x0 + __ldg(v + 224) * x1 + __ldg(v + 256) * x2;
+        }
+        y0 = a0; y1 = a1; y2 = a2;
+    }
+};
+struct StencilOp {
+    const float *val;
+    int n0, n1, nvp;
+    __device__ __forceinline__ void mul(int v, const float *__restrict__ x, float &y0, float &y1, float &y2) const
+    {
+        int I = v / n1, J = v - I * n1;
+        float a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+        for (int dI = -2; dI <= 2; dI++) {
+            int ii = I + dI;
+            if ((unsigned)ii >= (unsigned)n0) continue;
+#pragma unroll
+            for (int dJ = -2; dJ <= 2; dJ++) {
+                int jj = J + dJ;
+                if ((unsigned)jj >= (unsigned)n1) continue;
+                const int slot = (dI + 2) * 5 + (dJ + 2);
+                const float *a = val + (size_t)(slot * 9) * nvp + v;
+                int u = ii * n1 + jj;
+                float x0 = x[3 * u], x1 = x[3 * u + 1], x2 = x[3 * u + 2];
+                a0 += __ldg(a) * x0 + __ldg(a + nvp) * x1 + __ldg(a + 2 * (size_t)nvp) * x2;
+                a1 += __ldg(a + 3 * (size_t)nvp) * x0 + __ldg(a + 4 * (size_t)nvp) * x1 + __ldg(a + 5 * (size_t)nvp) * x2;
+                a2 += __ldg(a + 6 * (size_t)nvp) * x0 + __ldg(a + 7 * (size_t)nvp) * x1 + __ldg(a + 8 * (size_t)nvp) * x2;
+            }
+        }
+        y0 = a0; y1 = a1; y2 = a2;
+    }
+};
+
+__device__ __forceinline__ void block_atomic_sum(double a, double *acc)
+{
+    __shared__ double sa[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) sa[w] = a;
+    __syncthreads();
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        a = lane < nw ? sa[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) atomicAdd(acc, a);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ smoother kernels
+// d = c D^-1 b ; x_out = d                     (first Chebyshev step from a zero guess: no matrix pass)
+// acc (optional) += b . x_out
+__global__ void __launch_bounds__(256) k_cheb_first(int nrows, const float *__restrict__ dinv, const float *__restrict__ b, float *d,
+                                                    float *x_out, const float *__restrict__ coef, double *acc)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0;
+    if (row < nrows) {
+        float c = coef[1];
+        float r0 = b[3 * row], r1 = b[3 * row + 1], r2 = b[3 * row + 2];
+        const float *m = dinv + 9 * (size_t)row;
+        float d0 = c * (m[0] * r0 + m[1] * r1 + m[2] * r2), d1 = c * (m[3] * r0 + m[4] * r1 + m[5] * r2), d2 = c * (m[6] * r0 + m[7] * r1 + m[8] * r2);
+        if (d) { d[3 * row] = d0; d[3 * row + 1] = d1; d[3 * row + 2] = d2; }
+        x_out[3 * row] = d0; x_out[3 * row + 1] = d1; x_out[3 * row + 2] = d2;
+        s = (double)r0 * d0 + (double)r1 * d1 + (double)r2 * d2;
+    }
+    if (acc) block_atomic_sum(s, acc);
+}
+// d = a d + c D^-1 (b - A x_in) ; x_out = x_in + d     (b == nullptr: b = 0; x_out == nullptr: not stored)
+// acc_mode 1: acc += b . x_out      acc_mode 2: acc += d . d
+template <class Op>
+__global__ void __launch_bounds__(256) k_cheb_step(Op A, int nrows, const float *__restrict__ dinv, const float *__restrict__ b,
+                                                   const float *__restrict__ x_in, float *d, float *x_out,
+                                                   const float *__restrict__ coef, double *acc, int acc_mode)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0;
+    if (row < nrows) {
+        float a = coef[0], c = coef[1];
+        float y0, y1, y2;
+        A.mul(row, x_in, y0, y1, y2);
+        float b0 = 0, b1 = 0, b2 = 0;
+        if (b) { b0 = b[3 * row]; b1 = b[3 * row + 1]; b2 = b[3 * row + 2]; }
+        float r0 = b0 - y0, r1 = b1 - y1, r2 = b2 - y2;
+        const float *m = dinv + 9 * (size_t)row;
+        float d0 = c * (m[0] * r0 + m[1] * r1 + m[2] * r2), d1 = c * (m[3] * r0 + m[4] * r1 + m[5] * r2), d2 = c * (m[6] * r0 + m[7] * r1 + m[8] * r2);
+        if (a != 0.f) { d0 += a * d[3 * row]; d1 += a * d[3 * row + 1]; d2 += a * d[3 * row + 2]; }
+        d[3 * row] = d0; d[3 * row + 1] = d1; d[3 * row + 2] = d2;
+        if (x_out) {
+            float o0 = x_in[3 * row] + d0, o1 = x_in[3 * row + 1] + d1, o2 = x_in[3 * row + 2] + d2;
+            x_out[3 * row] = o0; x_out[3 * row + 1] = o1; x_out[3 * row + 2] = o2;
+            if (acc_mode == 1) s = (double)b0 * o0 + (double)b1 * o1 + (double)b2 * o2;
+        }
+        if (acc_mode == 2) s = (double)d0 * d0 + (double)d1 * d1 + (double)d2 * d2;
+    }
+    if (acc) block_atomic_sum(s, acc);
+}
+template <class Op>
+__global__ void __launch_bounds__(256) k_mg_residual(Op A, int nrows, const float *__restrict__ b, const float *__restrict__ x, float *r)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
+    float y0, y1, y2;
+    A.mul(row, x, y0, y1, y2);
+    r[3 * row] = b[3 * row] - y0; r[3 * row + 1] = b[3 * row + 1] - y1; r[3 * row + 2] = b[3 * row + 2] - y2;
+}
+// z = D^-1 b, acc += b . z  (block-Jacobi preconditioner, precond == 0)
+__global__ void __launch_bounds__(256) k_apply_dinv(int nrows, const float *__restrict__ dinv, const float *__restrict__ b, float *z, double *acc)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0;
+    if (row < nrows) {
+        float r0 = b[3 * row], r1 = b[3 * row + 1], r2 = b[3 * row + 2];
+        const float *m = dinv + 9 * (size_t)row;
+        float z0 = m[0] * r0 + m[1] * r1 + m[2] * r2, z1 = m[3] * r0 + m[4] * r1 + m[5] * r2, z2 = m[6] * r0 + m[7] * r1 + m[8] * r2;
+        z[3 * row] = z0; z[3 * row + 1] = z1; z[3 * row + 2] = z2;
+        s = (double)r0 * z0 + (double)r1 * z1 + (double)r2 * z2;
+    }
+    if (acc) block_atomic_sum(s, acc);
+}
+
+// ------------------------------------------------------------------------------------------------ transfer operators
+// 1-D bilinear weight of fine index 2I + a (a in -1..1) towards coarse parent I of nc coarse points
+__device__ __forceinline__ float pw1(int a, int I, int nc) { return a == 0 ? 1.f : (a < 0 ? 0.5f : (I + 1 < nc ? 0.5f : 1.f)); }
+
+// b_c = P^T r_f.  off: first row of the grid inside the fine vectors (level 0: cloth vertex offset); mask: frozen
+// flags [3 * rows] of the fine vectors or nullptr (frozen DOFs do not take part in the coarse correction)
+__global__ void k_restrict(int n0f, int n1f, int off, const float *__restrict__ r_f, const int *__restrict__ mask,
+                           int n0c, int n1c, float *b_c)
+{
+    int cv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (cv >= n0c * n1c) return;
+    int I = cv / n1c, J = cv - I * n1c;
+    float s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+    for (int a = -1; a <= 1; a++) {
+        int i = 2 * I + a;
+        if ((unsigned)i >= (unsigned)n0f) continue;
+        float wi = pw1(a, I, n0c);
+#pragma unroll
+        for (int b = -1; b <= 1; b++) {
+            int j = 2 * J + b;
+            if ((unsigned)j >= (unsigned)n1f) continue;
+            float w = wi * pw1(b, J, n1c);
+            size_t fr = 3 * (size_t)(off + i * n1f + j);
+            float m0 = 1, m1 = 1, m2 = 1;
+            if (mask) { m0 = mask[fr] ? 0.f : 1.f; m1 = mask[fr + 1] ? 0.f : 1.f; m2 = mask[fr + 2] ? 0.f : 1.f; }
+            s0 += w * m0 * r_f[fr]; s1 += w * m1 * r_f[fr + 1]; s2 += w * m2 * r_f[fr + 2];
+        }
+    }
+    b_c[3 * cv] = s0; b_c[3 * cv + 1] = s1; b_c[3 * cv + 2] = s2;
+}
+// x_f += P x_c
+__global__ void k_prolong_add(int n0f, int n1f, int off, float *x_f, const int *__restrict__ mask, int n0c, int n1c,
+                              const float *__restrict__ x_c)
+{
+    int fv = blockIdx.x * blockDim.x + threadIdx.x;
+    if (fv >= n0f * n1f) return;
+    int i = fv / n1f, j = fv - i * n1f;
+    int I0 = i >> 1, J0 = j >> 1;
+    int nI = 1, nJ = 1;
+    float wI[2] = { 1.f, 0.f }, wJ[2] = { 1.f, 0.f };
+    if (i & 1) { if (I0 + 1 < n0c) { nI = 2; wI[0] = wI[1] = 0.5f; } }
+    if (j & 1) { if (J0 + 1 < n1c) { nJ = 2; wJ[0] = wJ[1] = 0.5f; } }
+    float s0 = 0, s1 = 0, s2 = 0;
+    for (int a = 0; a < nI; a++)
+        for (int b = 0; b < nJ; b++) {
+            int cv = (I0 + a) * n1c + (J0 + b);
+            float w = wI[a] * wJ[b];
+            s0 += w * x_c[3 * cv]; s1 += w * x_c[3 * cv + 1]; s2 += w * x_c[3 * cv + 2];
+        }
+    size_t fr = 3 * (size_t)(off + fv);
+    if (mask) { if (mask[fr]) s0 = 0; if (mask[fr + 1]) s1 = 0; if (mask[fr + 2]) s2 = 0; }
+    x_f[fr] += s0; x_f[fr + 1] += s1; x_f[fr + 2] += s2;
+}
+
+// ------------------------------------------------------------------------------------------------ setup kernels
+// stencil copy of the cloth block of the sliced-ELL matrix (input of the first Galerkin product)
+__global__ void k_sell_to_stencil(int off, int nvc, int n1, const int *__restrict__ slice_base, const int *__restrict__ colidx,
+                                  const float *__restrict__ val, const int *__restrict__ diag_pb, float *out, int nvp)
+{
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nvc) return;
+    int row = off + v;
+    int S = row >> 5, lane = row & 31;
+    int i = v / n1, j = v - i * n1;
+    int b0 = slice_base[S], b1 = slice_base[S + 1];
+    int dpb = diag_pb[row];
+    for (int b = b0; b < b1; b += 32) {
+        int pb = b + lane;
+        int col = colidx[pb];
+        int cv = col - off;
+        if (cv < 0 || cv >= nvc) continue;
+        if (col == row && pb != dpb) continue;          // ELL padding (zero block pointing at the diagonal)
+        int ip = cv / n1, jp = cv - ip * n1;
+        int di = ip - i, dj = jp - j;
+        if (di < -2 || di > 2 || dj < -2 || dj > 2) continue;
+        int slot = (di + 2) * 5 + (dj + 2);
+        const float *src = val + (long long)b * 9 + lane;
+        float *dst = out + (size_t)(slot * 9) * nvp + v;
+#pragma unroll
+        for (int c = 0; c < 9; c++) dst[(size_t)c * nvp] = src[c * 32];
+    }
+}
+// A_c = P^T A_f P, one thread per (coarse vertex, coarse stencil slot).  mask: frozen flags of the fine grid's
+// DOFs ([3 * nvf], level 0 only) -- frozen DOFs are left out of the coarse spaces.
+template <bool MASK>
+__global__ void __launch_bounds__(128) k_galerkin(const float *__restrict__ val_f, int n0f, int n1f, int nvpf, const int *__restrict__ mask,
+                                                  float *val_c, int n0c, int n1c, int nvpc)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int nvc = n0c * n1c;
+    if (t >= nvc * 25) return;
+    int slot = t / nvc, cv = t - slot * nvc;
+    int I = cv / n1c, J = cv - I * n1c;
+    int Ip = I + slot / 5 - 2, Jp = J + slot % 5 - 2;
+    float acc[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) acc[c] = 0.f;
+    if ((unsigned)Ip < (unsigned)n0c && (unsigned)Jp < (unsigned)n1c) {
+        for (int a = -1; a <= 1; a++) {
+            int i = 2 * I + a;
+            if ((unsigned)i >= (unsigned)n0f) continue;
+            float wi = pw1(a, I, n0c);
+            for (int b = -1; b <= 1; b++) {
+                int j = 2 * J + b;
+                if ((unsigned)j >= (unsigned)n1f) continue;
+                float wr = wi * pw1(b, J, n1c);
+                int fv = i * n1f + j;
+                for (int ap = -1; ap <= 1; ap++) {
+                    int ip = 2 * Ip + ap;
+                    int di = ip - i;
+                    if ((unsigned)ip >= (unsigned)n0f || di < -2 || di > 2) continue;
+                    float wip = wr * pw1(ap, Ip, n0c);
+                    for (int bp = -1; bp <= 1; bp++) {
+                        int jp = 2 * Jp + bp;
+                        int dj = jp - j;
+                        if ((unsigned)jp >= (unsigned)n1f || dj < -2 || dj > 2) continue;
+                        float w = wip * pw1(bp, Jp, n1c);
+                        const float *src = val_f + (size_t)(((di + 2) * 5 + (dj + 2)) * 9) * nvpf + fv;
+                        if (MASK) {
+                            int fc = ip * n1f + jp;
+                            float mr[3], mc[3];
+#pragma unroll
+                            for (int q = 0; q < 3; q++) { mr[q] = mask[3 * fv + q] ? 0.f : w; mc[q] = mask[3 * fc + q] ? 0.f : 1.f; }
+#pragma unroll
+                            for (int c = 0; c < 9; c++) acc[c] += mr[c / 3] * mc[c % 3] * __ldg(src + (size_t)c * nvpf);
+                        } else {
+#pragma unroll
+                            for (int c = 0; c < 9; c++) acc[c] += w * __ldg(src + (size_t)c * nvpf);
+                        }
+                    }
+                }
+            }
+        }
+    }
+    float *dst = val_c + (size_t)(slot * 9) * nvpc + cv;
+#pragma unroll
+    for (int c = 0; c < 9; c++) dst[(size_t)c * nvpc] = acc[c];
+}
+__device__ __forceinline__ void inv3_guarded(const float *a, float *inv)
+{
+    double c00 = (double)a[4] * a[8] - (double)a[5] * a[7], c01 = (double)a[5] * a[6] - (double)a[3] * a[8], c02 = (double)a[3] * a[7] - (double)a[4] * a[6];
+    double det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+    double sc = fabs((double)a[0] * a[4] * a[8]);
+    if (!(fabs(det) > 1e-12 * sc) || !(det == det)) {
+        // singular block (all DOFs of the vertex masked out): the vertex takes no part in this level
+#pragma unroll
+        for (int c = 0; c < 9; c++) inv[c] = 0.f;
+        return;
+    }
+    double id = 1.0 / det;
+    inv[0] = (float)(c00 * id); inv[1] = (float)(((double)a[2] * a[7] - (double)a[1] * a[8]) * id); inv[2] = (float)(((double)a[1] * a[5] - (double)a[2] * a[4]) * id);
+    inv[3] = (float)(c01 * id); inv[4] = (float)(((double)a[0] * a[8] - (double)a[2] * a[6]) * id); inv[5] = (float)(((double)a[2] * a[3] - (double)a[0] * a[5]) * id);
+    inv[6] = (float)(c02 * id); inv[7] = (float)(((double)a[1] * a[6] - (double)a[0] * a[7]) * id); inv[8] = (float)(((double)a[0] * a[4] - (double)a[1] * a[3]) * id);
+}
+__global__ void k_dinv_stencil(int nv, int nvp, const float *__restrict__ val, float *dinv)
+{
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= nv) return;
+    float a[9], inv[9];
+#pragma unroll
+    for (int c = 0; c < 9; c++) a[c] = val[(size_t)(12 * 9 + c) * nvp + v];
+    inv3_guarded(a, inv);
+#pragma unroll
+    for (int c = 0; c < 9; c++) dinv[9 * (size_t)v + c] = inv[c];
+}
+__global__ void k_dinv_sell(int n_rows, int n_alloc, const int *__restrict__ diag_pb, const float *__restrict__ val, float *dinv)
+{
+    int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_alloc) return;
+    float a[9], inv[9];
+    if (r < n_rows) {
+        long long base = sell_addr(diag_pb[r], r & 31, 0);
+#pragma unroll
+        for (int c = 0; c < 9; c++) a[c] = val[base + c * 32];
+        inv3_guarded(a, inv);
+    } else {
+#pragma unroll
+        for (int c = 0; c < 9; c++) inv[c] = 0.f;
+    }
+#pragma unroll
+    for (int c = 0; c < 9; c++) dinv[9 * (size_t)r + c] = inv[c];
+}
+__global__ void k_fill_hash(int n, float *v, unsigned seed)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned h = (unsigned)i * 2654435761u ^ seed;
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    v[i] = (float)(h & 0xffffff) / 8388608.f - 1.f;
+}
+// Chebyshev coefficients of every level from the power-iteration norms; also the scale of the next warm start
+__global__ void k_mg_coeffs(int n_levels, const double *__restrict__ pow_acc, int k_last, float safety, float ratio, float coarse_ratio,
+                            int degree, int coarse_degree, float *coef, float *powc, float *lmax_out)
+{
+    int l = threadIdx.x;
+    if (l >= n_levels) return;
+    double n1 = pow_acc[l * 16 + k_last], n0 = pow_acc[l * 16 + k_last - 1];
+    double lam = sqrt(n1 / n0);
+    if (!(lam > 1e-6) || !(lam < 1e6)) lam = 4.0;             // degenerate level (e.g. everything masked): any finite value
+    double lmax = safety * lam;
+    bool coarsest = (l == n_levels - 1);
+    double lmin = lmax / (coarsest ? coarse_ratio : ratio);
+    int deg = coarsest ? coarse_degree : degree;
+    double theta = 0.5 * (lmax + lmin), delta = 0.5 * (lmax - lmin), sigma = theta / delta, rho = 1.0 / sigma;
+    float *c = coef + (size_t)l * TSL_MG_MAX_DEGREE * 2;
+    c[0] = 0.f; c[1] = (float)(1.0 / theta);
+    for (int k = 1; k < deg; k++) {
+        double rho_new = 1.0 / (2.0 * sigma - rho);
+        c[2 * k] = (float)(rho_new * rho); c[2 * k + 1] = (float)(2.0 * rho_new / delta);
+        rho = rho_new;
+    }
+    powc[l * 4 + 0] = 0.f; powc[l * 4 + 1] = (n1 > 0 && n1 < 1e300) ? (float)(-1.0 / sqrt(n1)) : -1.f;
+    powc[l * 4 + 2] = 0.f; powc[l * 4 + 3] = -1.f;
+    lmax_out[l] = (float)lmax;
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+static int pad32(int n) { return (n + 31) / 32 * 32; }
+
+int mg_alloc(tsl_ctx *ctx)
+{
+    MgDev &mg = ctx->mg;
+    mg.n_levels = 0;
+    if (ctx->cloths.empty()) return TSL_OK;
+    const ClothDev &c = ctx->cloths[0];
+    mg.cloth_offset = c.offset;
+    int n0 = c.N + 1, n1 = c.M + 1;
+    int nrows0 = ctx->A.n_slices * 32;
+    for (int l = 0; l < TSL_MG_MAX_LEVELS; l++) {
+        MgLevel &L = mg.lev[l];
+        L.n0 = n0; L.n1 = n1; L.nv = n0 * n1; L.nvp = pad32(L.nv);
+        L.nrows = (l == 0) ? nrows0 : L.nv;
+        size_t vb = sizeof(float) * 3 * (size_t)std::max(L.nrows, 32);
+        CK(cudaMalloc(&L.val, sizeof(float) * 225 * (size_t)L.nvp));
+        CK(cudaMemset(L.val, 0, sizeof(float) * 225 * (size_t)L.nvp));
+        CK(cudaMalloc(&L.dinv, sizeof(float) * 9 * (size_t)std::max(L.nrows, 32)));
+        for (int q = 0; q < 2; q++) {
+            CK(cudaMalloc(&L.x[q], vb)); CK(cudaMemset(L.x[q], 0, vb));
+            CK(cudaMalloc(&L.pv[q], vb)); CK(cudaMemset(L.pv[q], 0, vb));
+        }
+        CK(cudaMalloc(&L.b, vb)); CK(cudaMalloc(&L.r, vb)); CK(cudaMalloc(&L.d, vb));
+        CK(cudaMemset(L.b, 0, vb)); CK(cudaMemset(L.r, 0, vb)); CK(cudaMemset(L.d, 0, vb));
+        mg.n_levels = l + 1;
+        if (std::min(n0, n1) <= 6) break;
+        n0 = (n0 - 1) / 2 + 1; n1 = (n1 - 1) / 2 + 1;
+    }
+    CK(cudaMalloc(&mg.coef, sizeof(float) * TSL_MG_MAX_LEVELS * TSL_MG_MAX_DEGREE * 2));
+    CK(cudaMalloc(&mg.powc, sizeof(float) * TSL_MG_MAX_LEVELS * 4));
+    CK(cudaMalloc(&mg.pow_acc, sizeof(double) * TSL_MG_MAX_LEVELS * 16));
+    CK(cudaMalloc(&mg.lmax, sizeof(float) * TSL_MG_MAX_LEVELS));
+    std::vector<float> pc(TSL_MG_MAX_LEVELS * 4);
+    for (int l = 0; l < TSL_MG_MAX_LEVELS; l++) { pc[4 * l] = 0; pc[4 * l + 1] = -1; pc[4 * l + 2] = 0; pc[4 * l + 3] = -1; }
+    CK(cudaMemcpy(mg.powc, pc.data(), sizeof(float) * pc.size(), cudaMemcpyHostToDevice));
+    mg.setups = 0;
+    return TSL_OK;
+}
+
+void mg_free(tsl_ctx *ctx)
+{
+    MgDev &mg = ctx->mg;
+    for (int l = 0; l < mg.n_levels; l++) {
+        MgLevel &L = mg.lev[l];
+        cudaFree(L.val); cudaFree(L.dinv); cudaFree(L.b); cudaFree(L.r); cudaFree(L.d);
+        for (int q = 0; q < 2; q++) { cudaFree(L.x[q]); cudaFree(L.pv[q]); }
+    }
+    cudaFree(mg.coef); cudaFree(mg.powc); cudaFree(mg.pow_acc); cudaFree(mg.lmax);
+    mg.n_levels = 0;
+}
+
+static SellOp sell_op(tsl_ctx *ctx, const float *val) { SellOp o; o.slice_base = ctx->A.slice_base; o.colidx = ctx->A.colidx; o.val = val; return o; }
+static StencilOp stencil_op(const MgLevel &L) { StencilOp o; o.val = L.val; o.n0 = L.n0; o.n1 = L.n1; o.nvp = L.nvp; return o; }
+
+// d = a d + c D^-1 (b - A x_in), x_out = x_in + d on level l (level 0 smooths with the clamped matrix)
+static void launch_step(tsl_ctx *ctx, int l, const float *b, const float *x_in, float *d, float *x_out, const float *coef, double *acc, int mode)
+{
+    MgLevel &L = ctx->mg.lev[l];
+    if (l == 0)
+        k_cheb_step<SellOp><<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32c), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    else
+        k_cheb_step<StencilOp><<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(stencil_op(L), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    ctx->launches++;
+}
+
+// Builds the hierarchy for the matrix currently in A.val32c.  No host synchronisation.
+int mg_setup(tsl_ctx *ctx)
+{
+    MgDev &mg = ctx->mg;
+    cudaStream_t s = ctx->stream;
+    const SellMatrix &A = ctx->A;
+    int nrows0 = A.n_slices * 32;
+    if (mg.n_levels == 0) {          // no cloth: block-Jacobi only
+        k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32c, ctx->minv32);
+        ctx->launches++;
+        return TSL_OK;
+    }
+    const ClothDev &c = ctx->cloths[0];
+    MgLevel &L0 = mg.lev[0];
+    k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32c, L0.dinv);
+    ctx->launches++;
+    if (mg.n_levels > 1) {
+        // the pattern is static: every slot this kernel writes is rewritten on each setup, the others stay zero
+        k_sell_to_stencil<<<GRID(L0.nv, 128), 128, 0, s>>>(c.offset, L0.nv, L0.n1, A.slice_base, A.colidx, A.val32c, A.diag_pb, L0.val, L0.nvp);
+        ctx->launches++;
+    }
+    for (int l = 0; l + 1 < mg.n_levels; l++) {
+        MgLevel &F = mg.lev[l], &C = mg.lev[l + 1];
+        long long nt = 25LL * C.nv;
+        if (l == 0)
+            k_galerkin<true><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.nvp, ctx->frozen + 3 * (size_t)c.offset, C.val, C.n0, C.n1, C.nvp);
+        else
+            k_galerkin<false><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.nvp, nullptr, C.val, C.n0, C.n1, C.nvp);
+        k_dinv_stencil<<<GRID(C.nv, 256), 256, 0, s>>>(C.nv, C.nvp, C.val, C.dinv);
+        ctx->launches += 2;
+    }
+    // lambda_max(D^-1 A) per level: power iteration, warm-started from the previous setup
+    CK(cudaMemsetAsync(mg.pow_acc, 0, sizeof(double) * TSL_MG_MAX_LEVELS * 16, s));
+    int its = (mg.setups == 0) ? 10 : 4;
+    for (int l = 0; l < mg.n_levels; l++) {
+        MgLevel &L = mg.lev[l];
+        if (mg.setups == 0) {
+            k_fill_hash<<<GRID(3 * L.nrows, 256), 256, 0, s>>>(3 * L.nrows, L.pv[0], 0x9e3779b9u * (l + 1));
+            ctx->launches++;
+        }
+        for (int k = 0; k < its; k++) {
+            launch_step(ctx, l, nullptr, L.pv[k & 1], L.pv[(k & 1) ^ 1], nullptr, mg.powc + 4 * l + (k == 0 ? 0 : 2), mg.pow_acc + 16 * l + k, 2);
+        }
+        // its is even: the final vector is back in pv[0]
+    }
+    k_mg_coeffs<<<1, 32, 0, s>>>(mg.n_levels, mg.pow_acc, its - 1, mg.safety, mg.ratio, mg.coarse_ratio, mg.degree, mg.coarse_degree,
+                                 mg.coef, mg.powc, mg.lmax);
+    ctx->launches++;
+    mg.setups++;
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+
+// z = M^-1 b : one V-cycle (or block-Jacobi when precond == 0); acc_bz (optional, device) += b . z
+static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, double *acc)
+{
+    MgDev &mg = ctx->mg;
+    MgLevel &L = mg.lev[l];
+    cudaStream_t s = ctx->stream;
+    const float *coef = mg.coef + (size_t)l * TSL_MG_MAX_DEGREE * 2;
+    const bool last = (l == mg.n_levels - 1);
+    const int deg = last ? mg.coarse_degree : mg.degree;
+    // pre-smoothing (or the coarsest-grid sweep) from a zero guess
+    float *cur = nullptr;
+    for (int k = 0; k < deg; k++) {
+        bool final_k = last && (k == deg - 1);
+        float *out = (final_k && z_out) ? z_out : L.x[k & 1];
+        double *a = final_k ? acc : nullptr;
+        if (k == 0) {
+            k_cheb_first<<<GRID(L.nrows, 256), 256, 0, s>>>(L.nrows, L.dinv, b, L.d, out, coef, a);
+            ctx->launches++;
+        } else launch_step(ctx, l, b, cur, L.d, out, coef + 2 * k, a, a ? 1 : 0);
+        cur = out;
+    }
+    if (last) return cur;
+    MgLevel &C = mg.lev[l + 1];
+    int off = (l == 0) ? mg.cloth_offset : 0;
+    const int *mask = (l == 0) ? ctx->frozen : nullptr;
+    if (l == 0) k_mg_residual<SellOp><<<GRID(L.nrows, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32c), L.nrows, b, cur, L.r);
+    else k_mg_residual<StencilOp><<<GRID(L.nrows, 256), 256, 0, s>>>(stencil_op(L), L.nrows, b, cur, L.r);
+    k_restrict<<<GRID(C.nv, 128), 128, 0, s>>>(L.n0, L.n1, off, L.r, mask, C.n0, C.n1, C.b);
+    ctx->launches += 2;
+    float *xc = vcycle_level(ctx, l + 1, C.b, nullptr, nullptr);
+    k_prolong_add<<<GRID(L.nv, 256), 256, 0, s>>>(L.n0, L.n1, off, cur, mask, C.n0, C.n1, xc);
+    ctx->launches++;
+    // post-smoothing with the same polynomial (symmetric cycle)
+    for (int k = 0; k < deg; k++) {
+        bool final_k = (k == deg - 1);
+        float *out = (final_k && z_out) ? z_out : (cur == L.x[0] ? L.x[1] : L.x[0]);
+        double *a = (final_k && l == 0) ? acc : nullptr;
+        launch_step(ctx, l, b, cur, L.d, out, coef + 2 * k, a, a ? 1 : 0);
+        cur = out;
+    }
+    return cur;
+}
+
+int mg_apply(tsl_ctx *ctx, const float *b, float *z, double *acc_bz)
+{
+    MgDev &mg = ctx->mg;
+    if (mg.n_levels == 0 || ctx->precond == 0) {
+        int nrows0 = ctx->A.n_slices * 32;
+        const float *dinv = (mg.n_levels == 0) ? ctx->minv32 : mg.lev[0].dinv;
+        k_apply_dinv<<<GRID(nrows0, 256), 256, 0, ctx->stream>>>(nrows0, dinv, b, z, acc_bz);
+        ctx->launches++;
+        return TSL_OK;
+    }
+    vcycle_level(ctx, 0, b, z, acc_bz);
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+
+// test / diagnostic read-back of one level: grid, lambda_max estimate, stencil operator [25][9][nv] (slot-major)
+int mg_get_level(tsl_ctx *ctx, int level, int *dims, float *lmax, float *val_host)
+{
+    MgDev &mg = ctx->mg;
+    if (level < 0 || level >= mg.n_levels) { ctx->err = "mg_get_level: no such level"; return TSL_ERR_INVALID; }
+    MgLevel &L = mg.lev[level];
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (dims) { dims[0] = L.n0; dims[1] = L.n1; dims[2] = mg.n_levels; }
+    if (lmax) CK(cudaMemcpy(lmax, mg.lmax + level, sizeof(float), cudaMemcpyDeviceToHost));
+    if (val_host) {
+        std::vector<float> tmp((size_t)225 * L.nvp);
+        CK(cudaMemcpy(tmp.data(), L.val, sizeof(float) * tmp.size(), cudaMemcpyDeviceToHost));
+        for (int sc = 0; sc < 225; sc++)
+            for (int v = 0; v < L.nv; v++) val_host[(size_t)sc * L.nv + v] = tmp[(size_t)sc * L.nvp + v];
+    }
+    return TSL_OK;
+}
+
+}  // namespace tsl

@@ -814,10 +814,10 @@ static void launch_hessian_t(tsl_ctx *ctx, const double *pos, T *val, int spd, i
         ctx->launches++;
     }
 }
-void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model)
+void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model, bool into_clamped)
 {
     if (f64) launch_hessian_t<double>(ctx, pos, ctx->A.val64, spd, sym, newton_model);
-    else launch_hessian_t<float>(ctx, pos, ctx->A.val32, spd, sym, newton_model);
+    else launch_hessian_t<float>(ctx, pos, into_clamped ? ctx->A.val32c : ctx->A.val32, spd, sym, newton_model);
 }
 void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alpha, double *pos)
 {

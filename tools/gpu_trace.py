@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Diagnostic run on a GPU box: Newton traces (TSL_TRACE=1) of the synthetic sheet, position error against the CPU oracle at
+small sizes, per-kernel-class timings.  Usage: python tools/gpu_trace.py N STEPS [--oracle]"""
+import os
+import sys
+import time
+
+os.environ.setdefault("TSL_TRACE", "1")
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import torch
+
+from thinshelllab_b200 import _lib
+from thinshelllab_b200.synthetic import sheet_scene
+
+N = int(sys.argv[1]); steps = int(sys.argv[2]); use_oracle = "--oracle" in sys.argv
+s = sheet_scene(N)
+e = s.engine
+o = None
+if use_oracle:
+    from oracle import tsl_oracle as orc
+    c = s.cloths[0]
+    tpos, tfaces, tmass = s._table
+    o = orc.OracleScene(c.N, c.M, c.dx, s.dt, tpos, tfaces, tmass, Kb=100.0, k_angle=3.14, k_contact=s.k_contact, eps_contact=s.eps_contact,
+                        eps_v=s.eps_v, mu=0.5, max_n_constraints=s.max_n_constraints, grid_n=e.cfg.grid_n)
+    o.pos[:] = e.pos.cpu().numpy(); o.prev_pos[:] = o.pos; o.vel[:] = 0
+for k in range(steps):
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    st = s.time_step()
+    torch.cuda.synchronize(); dt = time.perf_counter() - t0
+    msg = f"step {k}: {1e3 * dt:.1f} ms newton={st.newton_iters} pcg={st.linear_iters} ls={st.linesearch_evals} nc={st.n_contacts} conv={st.converged} flags={st.flags} " \
+          f"ms(contact/asm/solve/ls)={st.ms_contact:.1f}/{st.ms_assembly:.1f}/{st.ms_solve:.1f}/{st.ms_linesearch:.1f}"
+    if o is not None:
+        it = o.time_step()
+        msg += f" | oracle newton={it} nc={o.nc} max|dx|={np.abs(e.pos.cpu().numpy() - o.pos).max():.3e}"
+    print(msg, flush=True)
+e.contact_detect()
+e.assemble(_lib.ASM_RESIDUAL | _lib.ASM_HESSIAN | _lib.ASM_NEWTON | _lib.ASM_SPD)
+sz = e.sizes()
+print("sizes", sz)
+for name, what in (("pcg_iter", 0), ("spmv", 1), ("energy", 2), ("residual", 3), ("hessian", 4), ("vcycle", 5)):
+    e.bench_kernel(what, 5)
+    print(f"  {name}: {1e3 * e.bench_kernel(what, 50):.1f} us")
+for lev in range(e.mg_level(0, values=False)[2]):
+    n0, n1, nl, lmax, _ = e.mg_level(lev, values=False)
+    print(f"  level {lev}: {n0}x{n1} lmax {lmax:.3f}")
