@@ -6,7 +6,8 @@
  * code/training/trajopt_*.py.  Each entry point below names the reference method(s) it replaces.
  * All functions return 0 on success and a negative tsl_status otherwise; tsl_last_error() gives text.
  * Pointers named *_dev are CUDA device pointers owned by the caller (torch tensors); *_host are host
- * pointers.  All work is enqueued on the stream given to tsl_set_stream (default: legacy stream 0).
+ * pointers.  Work runs on a stream the library owns, ordered after everything already enqueued on the stream given to
+ * tsl_set_stream (default: legacy stream 0) at entry, and that stream is made to wait for the library's work at exit.
  * One context per GPU / rank; a context is not re-entrant.
  */
 #ifndef TSL_H
@@ -157,13 +158,14 @@ int tsl_get_sizes(tsl_ctx *ctx, tsl_sizes *out);
 /* benchmark hooks: run `iters` PCG iterations (no convergence test) on the last fp32 Hessian, and time
  * one kernel class with CUDA events on the context's stream; ms_out = average per launch.
  * what: 0 = PCG iteration (SpMV + vector kernels + preconditioner), 1 = SpMV only, 2 = energy, 3 = residual, 4 = Hessian,
- * 5 = preconditioner application (one V-cycle) */
+ * 5 = preconditioner application (one V-cycle), 6 = multigrid setup (Galerkin products + eigenvalue estimates) */
 int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out);
 /* solver options (the reference has none: its solve is a direct factorisation, code/engine/sparse_solver.py:85-105).
  * TSL_OPT_PRECOND: 0 = block-Jacobi, 1 = geometric multigrid V-cycle over the cloth grid (default);
  * TSL_OPT_MG_*: Chebyshev smoother degree (default 2), coarsest-grid sweep degree (8), eigenvalue interval ratio (8),
- * safety factor on the power-iteration estimate of lambda_max (1.2). */
-enum tsl_option { TSL_OPT_PRECOND = 0, TSL_OPT_MG_DEGREE = 1, TSL_OPT_MG_COARSE_DEGREE = 2, TSL_OPT_MG_RATIO = 3, TSL_OPT_MG_SAFETY = 4 };
+ * safety factor on the power-iteration estimate of lambda_max (1.2);
+ * TSL_OPT_GRAPHS: 1 = replay the solver iterations as captured CUDA graphs (default), 0 = eager launches. */
+enum tsl_option { TSL_OPT_PRECOND = 0, TSL_OPT_MG_DEGREE = 1, TSL_OPT_MG_COARSE_DEGREE = 2, TSL_OPT_MG_RATIO = 3, TSL_OPT_MG_SAFETY = 4, TSL_OPT_GRAPHS = 5 };
 int tsl_set_option(tsl_ctx *ctx, int key, double value);
 /* multigrid level read-back for tests: dims_host[3] = n0, n1, number of levels; lmax_host[1]; val_host [25][9][n0*n1] f32
  * (5x5 stencil of 3x3 blocks, slot-major; level 0 returns the stencil copy of the cloth block).  Any pointer may be NULL. */

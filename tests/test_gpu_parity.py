@@ -137,9 +137,13 @@ def test_linear_solvers(golden):
     x, (iters, flags, rr) = e.solve(torch.from_numpy(F).to(e.device), rel_tol=1e-6, max_iters=500)
     assert flags == 0 and 0 < iters < 100
     assert _rel(x.cpu().numpy(), ref) < 1e-3            # fp32 Krylov on a kappa ~ 1e5 system
+    # the adjoint system lives at a converged state (analytic_grad_system.py:131-140): un-projected reference Hessian, fp64
+    st = s.time_step()
+    assert st.converged
     e.assemble(_lib.ASM_HESSIAN | _lib.ASM_F64)
     H = e.matrix().tocsc()
     rhs = np.random.default_rng(0).standard_normal(F.shape)
+    rhs[e.frozen.cpu().numpy() != 0] = 0
     ref = spla.spsolve(H, rhs)
     x, (iters, flags, rr) = e.solve(torch.from_numpy(rhs).to(e.device), rel_tol=1e-10, max_iters=2000)
     assert flags == 0 and rr < 1e-9 and iters < 300, (iters, flags, rr)
@@ -199,6 +203,7 @@ def _oracle_for(s, **kw):
     o = orc.OracleScene(c.N, c.M, c.dx, s.dt, tpos, tfaces, tmass, Kb=100.0, k_angle=3.14, k_contact=s.k_contact, eps_contact=s.eps_contact,
                         eps_v=s.eps_v, mu=0.5, max_n_constraints=s.max_n_constraints, grid_n=s.engine.cfg.grid_n, **kw)
     o.pos[:] = s.engine.pos.cpu().numpy(); o.prev_pos[:] = s.engine.prev_pos.cpu().numpy(); o.vel[:] = s.engine.vel.cpu().numpy()
+    o.ref_angle[:] = s.engine.cloth_ref_angle[0].cpu().numpy()
     return o
 
 

@@ -16,6 +16,23 @@ using namespace tsl;
 #define REQUIRE(c, msg) do { if (!(c)) { ctx->err = (msg); return TSL_ERR_INVALID; } } while (0)
 #define TRY(x) do { int r_ = (x); if (r_ != TSL_OK) return r_; } while (0)
 
+// Orders the library's stream after the caller's stream on entry and the caller's stream after the library's on exit.
+struct StreamScope {
+    tsl_ctx *c;
+    explicit StreamScope(tsl_ctx *ctx) : c(ctx)
+    {
+        if (!c) return;
+        cudaEventRecord(c->ev_in, c->user_stream);
+        cudaStreamWaitEvent(c->stream, c->ev_in, 0);
+    }
+    ~StreamScope()
+    {
+        if (!c) return;
+        cudaEventRecord(c->ev_out, c->stream);
+        cudaStreamWaitEvent(c->user_stream, c->ev_out, 0);
+    }
+};
+
 static double now_ms()
 {
     using namespace std::chrono;
@@ -41,6 +58,10 @@ int tsl_create(const tsl_config *cfg, tsl_ctx **out)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return TSL_ERR_CUDA;   // no CPU fallback: fail loudly
     tsl_ctx *ctx = new tsl_ctx();
     ctx->cfg = *cfg;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return TSL_ERR_CUDA; }
+    if (const char *e = getenv("TSL_GRAPHS")) ctx->use_graphs = atoi(e);
     if (ctx->cfg.grid_h <= 0) ctx->cfg.grid_h = 0.003;
     if (ctx->cfg.grid_n <= 0) ctx->cfg.grid_n = 132;
     *out = ctx;
@@ -51,6 +72,8 @@ int tsl_destroy(tsl_ctx *ctx)
 {
     if (!ctx) return TSL_ERR_INVALID;
     // device memory is released with the process / context; explicit frees for the large arrays
+    cudaStreamSynchronize(ctx->stream);
+    tsl::graphs_invalidate(ctx);
     tsl::mg_free(ctx);
     cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
     cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q);
@@ -66,12 +89,13 @@ int tsl_destroy(tsl_ctx *ctx)
     cudaFree(ctx->con.idx); cudaFree(ctx->con.w); cudaFree(ctx->con.k); cudaFree(ctx->con.mu); cudaFree(ctx->con.dx0); cudaFree(ctx->con.T); cudaFree(ctx->con.n);
     cudaFree(ctx->ks); cudaFreeHost(ctx->ks_host); cudaFree(ctx->red_partial); cudaFree(ctx->red_ticket); cudaFree(ctx->red_out); cudaFreeHost(ctx->red_host);
     cudaFree(ctx->d_kb); cudaFree(ctx->adj_rhs); cudaFree(ctx->adj_z); cudaFree(ctx->error_flag); cudaFree(ctx->zero_border);
+    cudaEventDestroy(ctx->ev_in); cudaEventDestroy(ctx->ev_out); cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TSL_OK;
 }
 
 const char *tsl_last_error(tsl_ctx *ctx) { return ctx ? ctx->err.c_str() : "null context"; }
-int tsl_set_stream(tsl_ctx *ctx, void *s) { if (!ctx) return TSL_ERR_INVALID; ctx->stream = (cudaStream_t)s; return TSL_OK; }
+int tsl_set_stream(tsl_ctx *ctx, void *s) { if (!ctx) return TSL_ERR_INVALID; ctx->user_stream = (cudaStream_t)s; return TSL_OK; }
 long long tsl_launch_count(tsl_ctx *ctx) { return ctx ? ctx->launches : -1; }
 
 // ---------------------------------------------------------------------------------------------- scene description
@@ -207,6 +231,7 @@ int tsl_bind_state(tsl_ctx *ctx, double *pos, double *prev_pos, double *vel, con
     if (!ctx) return TSL_ERR_INVALID;
     REQUIRE(pos && prev_pos && vel && mass && frozen, "tsl_bind_state: null pointer");
     ctx->pos = pos; ctx->prev_pos = prev_pos; ctx->vel = vel; ctx->mass = mass; ctx->frozen = frozen;
+    graphs_invalidate(ctx);                      // captured graphs hold the old pointers
     if (border_flag) ctx->border_flag = border_flag;
     else {
         if (!ctx->zero_border) {
@@ -349,6 +374,7 @@ int tsl_finalize(tsl_ctx *ctx)
 int tsl_reset_contact_state(tsl_ctx *ctx)
 {
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    StreamScope scope_(ctx);
     size_t pb = (size_t)std::max<size_t>(ctx->bodies.size(), 1) * ctx->cfg.n_verts;
     CK(cudaMemsetAsync(ctx->proj_flag, 0, sizeof(int) * pb, ctx->stream));
     return TSL_OK;
@@ -367,6 +393,7 @@ static int check_device_flags(tsl_ctx *ctx)
 int tsl_contact_detect(tsl_ctx *ctx, int *n_out)
 {
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    StreamScope scope_(ctx);
     TRY(contact_detect(ctx, ctx->pos, ctx->prev_pos));
     if (n_out) *n_out = ctx->nc;
     return TSL_OK;
@@ -383,6 +410,7 @@ static int energy_sync(tsl_ctx *ctx, double *out)
 int tsl_energy(tsl_ctx *ctx, double *out)
 {
     if (!ctx || !ctx->finalized || !out) return TSL_ERR_INVALID;
+    StreamScope scope_(ctx);
     return energy_sync(ctx, out);
 }
 
@@ -402,6 +430,7 @@ static int ensure_f64(tsl_ctx *ctx)
 int tsl_assemble(tsl_ctx *ctx, int flags)
 {
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    StreamScope scope_(ctx);
     if (flags & TSL_ASM_RESIDUAL) launch_residual(ctx, ctx->pos);
     if (flags & TSL_ASM_HESSIAN) {
         bool f64 = (flags & TSL_ASM_F64) != 0;
@@ -409,7 +438,7 @@ int tsl_assemble(tsl_ctx *ctx, int flags)
         launch_hessian(ctx, ctx->pos, f64, (flags & TSL_ASM_SPD) ? 1 : 0, (flags & TSL_ASM_SYM) ? 1 : 0, (flags & TSL_ASM_NEWTON) ? 1 : 0);
         // the preconditioner hierarchy always comes from the clamped (positive definite) Newton matrix at the same state
         launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);
-        TRY(mg_setup(ctx));
+        TRY(mg_setup_replay(ctx));
         if (f64) launch_block_jacobi64(ctx);
         ctx->last_f64 = f64;
     }
@@ -420,6 +449,7 @@ int tsl_assemble(tsl_ctx *ctx, int flags)
 int tsl_solve(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
 {
     if (!ctx || !ctx->finalized || !rhs || !x) return TSL_ERR_INVALID;
+    StreamScope scope_(ctx);
     if (ctx->last_f64) return solve_bicgstab64(ctx, rhs, x, rel_tol, max_iters, st);
     return solve_pcg32(ctx, ctx->A.val32, rhs, x, rel_tol, max_iters, st);
 }
@@ -438,6 +468,7 @@ int tsl_solve(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int ma
 int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *stats)
 {
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    StreamScope scope_(ctx);
     int n3 = 3 * ctx->cfg.n_verts;
     cudaStream_t s = ctx->stream;
     tsl_step_stats st;
@@ -464,7 +495,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         const bool try_exact = (skip == 0);
         launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                    // A_c -> val32c
         if (try_exact) launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);    // A_e -> val32
-        TRY(mg_setup(ctx));
+        TRY(mg_setup_replay(ctx));
         ctx->last_f64 = false;
         if (it == 1) TRY(check_device_flags(ctx));
         double t1 = now_ms();
@@ -544,6 +575,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
 int tsl_step_forward_host(tsl_ctx *ctx, double *pos_host, double *vel_host, int max_newton, double tol, tsl_step_stats *stats)
 {
     if (!ctx || !ctx->finalized || !pos_host || !vel_host) return TSL_ERR_INVALID;
+    StreamScope scope_(ctx);
     size_t nb = sizeof(double) * 3 * (size_t)ctx->cfg.n_verts;
     CK(cudaMemcpyAsync(ctx->pos, pos_host, nb, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(ctx->vel, vel_host, nb, cudaMemcpyHostToDevice, ctx->stream));
@@ -560,6 +592,7 @@ int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, cons
                       double *grad_kb_accum, double *z_out, double clamp, double rel_tol, int max_iters, tsl_solve_stats *stats)
 {
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    StreamScope scope_(ctx);
     REQUIRE(x_t && x_tm1 && ref_angle_tm1 && pg_t && pg_tm1 && ag_t && ag_tm1 && grad_kb_accum, "tsl_step_backward: null pointer");
     REQUIRE(ctx->cloths.size() == 1, "tsl_step_backward needs one cloth");
     TRY(ensure_f64(ctx));
@@ -584,7 +617,7 @@ int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, cons
     launch_hessian(ctx, ctx->pos, true, 0, 0, 0);
     // preconditioner: multigrid hierarchy of the clamped Newton matrix at x_t
     launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);
-    TRY(mg_setup(ctx));
+    TRY(mg_setup_replay(ctx));
     launch_block_jacobi64(ctx);
     ctx->last_f64 = true;
     TRY(check_device_flags(ctx));
@@ -673,7 +706,8 @@ int tsl_get_sizes(tsl_ctx *ctx, tsl_sizes *out)
 int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out)
 {
     if (!ctx || !ctx->finalized || !ms_out || iters <= 0) return TSL_ERR_INVALID;
-    if (what == 0 || what == 1 || what == 5) return bench_pcg_iterations(ctx, iters, what, ms_out);
+    StreamScope scope_(ctx);
+    if (what == 0 || what == 1 || what == 5 || what == 6) return bench_pcg_iterations(ctx, iters, what, ms_out);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, ctx->stream));
@@ -701,8 +735,11 @@ int tsl_set_option(tsl_ctx *ctx, int key, double value)
     case TSL_OPT_MG_COARSE_DEGREE: REQUIRE(value >= 1 && value <= TSL_MG_MAX_DEGREE, "mg coarse degree out of range"); ctx->mg.coarse_degree = (int)value; break;
     case TSL_OPT_MG_RATIO: REQUIRE(value > 1, "mg ratio must exceed 1"); ctx->mg.ratio = (float)value; break;
     case TSL_OPT_MG_SAFETY: REQUIRE(value >= 1, "mg safety must be >= 1"); ctx->mg.safety = (float)value; break;
+    case TSL_OPT_GRAPHS: ctx->use_graphs = (int)value; break;
     default: ctx->err = "tsl_set_option: unknown key"; return TSL_ERR_INVALID;
     }
+    cudaStreamSynchronize(ctx->stream);
+    graphs_invalidate(ctx);
     return TSL_OK;
 }
 int tsl_mg_get_level(tsl_ctx *ctx, int level, int *dims, float *lmax, float *val_host)
@@ -713,6 +750,7 @@ int tsl_mg_get_level(tsl_ctx *ctx, int level, int *dims, float *lmax, float *val
 int tsl_precond_apply(tsl_ctx *ctx, const double *b_dev, double *z_dev)
 {
     if (!ctx || !ctx->finalized || !b_dev || !z_dev) return TSL_ERR_INVALID;
+    StreamScope scope_(ctx);
     // fp64 boundary, fp32 cycle: staged through the solver's own vectors
     return precond_apply_f64io(ctx, b_dev, z_dev);
 }

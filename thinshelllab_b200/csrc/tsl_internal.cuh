@@ -89,26 +89,35 @@ struct MgDev {
     float ratio = 8.f, coarse_ratio = 200.f, safety = 1.2f;
 };
 
-// Krylov scalars kept on the device so a solve never needs the host inside the loop
+// Krylov scalars kept on the device so a solve never needs the host inside an iteration.  There is no parity /
+// iteration index in any kernel argument: a one-thread "rotate" kernel at the end of every iteration moves the
+// freshly accumulated sums into place, so one captured CUDA graph serves every iteration.
 struct KrylovScalars {
-    double acc_pq[2];     // PCG: p.Ap   (parity buffers)
-    double acc_rz[2];     // PCG: r.z
-    double acc_rr[2];     // |r|^2
-    double acc_rho[2];    // BiCGStab: rhat.r
-    double acc_rhv;       // rhat.v
-    double acc_ts, acc_tt;
-    double alpha;
-    double rr0;           // |b|^2
+    // PCG
+    double pq;            // p.Ap of the current iteration
+    double rz, rz_new;    // r.z before / after the update
+    double rr, rr_new;    // |r|^2 before / after the update
+    // BiCGStab
+    double rho, rho_old, rho_next;   // rhat.r of this / the previous / the next iteration
+    double rhv, ts, tt;              // rhat.v, t.s, t.t
+    double alpha, omega;             // step lengths of the previous iteration
+    double rr0;           // |b|^2 (host side only)
     int flags;            // bit0 negative curvature / breakdown (iteration frozen)
-    int pad;
+    int iter;             // iterations completed
 };
+
+struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; const void *key = nullptr; };
 
 }  // namespace tsl
 
 struct tsl_ctx {
     tsl_config cfg;
     std::string err;
-    cudaStream_t stream = 0;
+    cudaStream_t stream = 0;                     // the library's own stream: all work runs here (graph capture needs a real stream)
+    cudaStream_t user_stream = 0;                // the caller's stream (tsl_set_stream); ordered against `stream` with events
+    cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+    int use_graphs = 1;                          // TSL_GRAPHS=0 disables CUDA-graph replay of the solver iterations
+    tsl::GraphSlot g_pcg[2], g_bicg, g_mgsetup;  // captured iteration bodies (PCG per operator array)
     long long launches = 0;
     bool finalized = false;
 

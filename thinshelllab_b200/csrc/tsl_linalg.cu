@@ -1,10 +1,13 @@
 // tsl_linalg.cu -- block-sparse linear algebra of the implicit step (sm_100a).
 //
 // Replaces SparseMatrix.solve (code/engine/sparse_solver.py:85-105; cuSOLVER sparse QR through CuPy) with
-//   * forward Newton:  block-Jacobi PCG on the fp32 sliced-ELL matrix (fp32 vectors, fp64 reductions),
-//   * adjoint:         block-Jacobi BiCGStab in fp64 on the un-projected, non-symmetric reference Hessian.
-// The whole iteration runs without the host: step lengths are formed on the device from reduction results
-// kept in a KrylovScalars struct; the host only polls |r|^2 every `check_every` iterations.
+//   * forward Newton:  PCG on the fp32 sliced-ELL matrix (fp32 vectors, fp64 reductions),
+//   * adjoint:         right-preconditioned BiCGStab in fp64 on the un-projected, non-symmetric reference Hessian,
+// both preconditioned by the multigrid V-cycle of tsl_mg.cu (or block-Jacobi, TSL_OPT_PRECOND = 0).
+// A whole iteration runs without the host: step lengths are formed on the device from reduction results kept in a
+// KrylovScalars struct and a one-thread "rotate" kernel advances them, so the iteration body has no host-dependent
+// argument and is replayed as ONE captured CUDA graph (~60 kernel nodes with the V-cycle; the per-launch CPU cost
+// would otherwise dominate every mesh that fits the L2).  The host reads the scalars once per iteration.
 // HBM-bound: the SpMV streams 40 B (fp32) / 76 B (fp64) per 3x3 block in full-line transactions
 // (see SellMatrix), gathers the direction vector through L1/L2, and fuses the dot products it feeds.
 #include "tsl_internal.cuh"
@@ -14,6 +17,7 @@ namespace tsl {
 
 #define GRID(n, b) (unsigned)(((n) + (b) - 1) / (b))
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return TSL_ERR_CUDA; } } while (0)
+#define TRYR(x) do { int r_ = (x); if (r_ != TSL_OK) return r_; } while (0)
 
 __device__ __forceinline__ double warp_sum_d(double v)
 {
@@ -61,10 +65,9 @@ __device__ __forceinline__ void spmv_row(const int *__restrict__ slice_base, con
 template <typename T>
 __global__ void __launch_bounds__(256) k_spmv_dots(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
                                                    const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y,
-                                                   const T *__restrict__ u, double *acc_uy, double *acc_yy, double *zero_a, double *zero_b)
+                                                   const T *__restrict__ u, double *acc_uy, double *acc_yy)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row == 0) { if (zero_a) *zero_a = 0; if (zero_b) *zero_b = 0; }
     double uy = 0, yy = 0;
     if (row < n_rows) {
         T y0, y1, y2;
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(256) k_spmv_dots(int n_rows, const int *__rest
     block_atomic_sum2(uy, yy, acc_uy, acc_yy);
 }
 
-// block-Jacobi: inverse of the diagonal 3x3 blocks
+// block-Jacobi: inverse of the diagonal 3x3 blocks (fp64 adjoint matrix, TSL_OPT_PRECOND = 0 only)
 template <typename T>
 __global__ void k_block_jacobi(int n_rows, const int *__restrict__ diag_pb, const T *__restrict__ val, T *minv)
 {
@@ -95,21 +98,52 @@ __global__ void k_block_jacobi(int n_rows, const int *__restrict__ diag_pb, cons
 #pragma unroll
     for (int c = 0; c < 9; c++) minv[9 * r + c] = (T)inv[c];
 }
-template <typename T>
-__device__ __forceinline__ void apply_minv(const T *__restrict__ minv, int r, T r0, T r1, T r2, T &z0, T &z1, T &z2)
+
+// ------------------------------------------------------------------------------------------------ graph replay
+// Runs `body` (a fixed sequence of launches on ctx->stream) through a cached CUDA graph; `key` identifies what the
+// captured pointers refer to (a different key re-captures).  Falls back to eager launches when graphs are disabled.
+template <class Body>
+static int replay(tsl_ctx *ctx, GraphSlot &slot, const void *key, Body body)
 {
-    const T *m = minv + 9 * r;
-    z0 = m[0] * r0 + m[1] * r1 + m[2] * r2;
-    z1 = m[3] * r0 + m[4] * r1 + m[5] * r2;
-    z2 = m[6] * r0 + m[7] * r1 + m[8] * r2;
+    if (!ctx->use_graphs) return body();
+    if (slot.exec && slot.key != key) { cudaGraphExecDestroy(slot.exec); slot.exec = nullptr; }
+    if (!slot.exec) {
+        cudaGraph_t g = nullptr;
+        long long l0 = ctx->launches;
+        CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = body();
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+        if (rc != TSL_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (e != cudaSuccess) { ctx->err = std::string("cudaStreamEndCapture: ") + cudaGetErrorString(e); return TSL_ERR_CUDA; }
+        slot.launches = ctx->launches - l0;
+        ctx->launches = l0;
+        e = cudaGraphInstantiate(&slot.exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { slot.exec = nullptr; ctx->err = std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e); return TSL_ERR_CUDA; }
+        slot.key = key;
+    }
+    CK(cudaGraphLaunch(slot.exec, ctx->stream));
+    ctx->launches += slot.launches;
+    return TSL_OK;
+}
+void graphs_invalidate(tsl_ctx *ctx)
+{
+    GraphSlot *all[4] = { &ctx->g_pcg[0], &ctx->g_pcg[1], &ctx->g_bicg, &ctx->g_mgsetup };
+    for (GraphSlot *g : all) if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; g->key = nullptr; }
+}
+int mg_setup_replay(tsl_ctx *ctx)
+{
+    // the first setup runs the cold power iteration eagerly; later ones replay one graph
+    if (ctx->mg.setups == 0 || ctx->mg.n_levels == 0) return mg_setup(ctx);
+    return replay(ctx, ctx->g_mgsetup, ctx->A.val32c, [&]() { return mg_setup(ctx); });
 }
 
 // ------------------------------------------------------------------------------------------------ PCG (fp32)
-// Preconditioned CG with the preconditioner applied between kernels (mg_apply: V-cycle or block-Jacobi):
-//   init      : x = 0, r = b, rr[0] = r.r                         z = M r, rz[0] = r.z (fused in the preconditioner)   p = z
-//   iteration : q = A p, pq[c] = p.q | x += a p, r -= a q, rr[n] | z = M r, rz[n] = r.z                                | p = z + (rz[n]/rz[c]) p
-// c = it & 1, n = c ^ 1.  Step lengths are formed on the device; the host reads the scalars once per iteration
-// (an iteration is a whole V-cycle, so the read-back is noise) to test convergence / negative curvature.
+//   start     : x = 0, r = b, rr_new = r.r | z = M r, rz_new = r.z (fused in the preconditioner) | p = z | rotate
+//   iteration : q = A p, pq = p.q | alpha = rz/pq, x += alpha p, r -= alpha q, rr_new = r.r | z = M r, rz_new = r.z
+//               | p = z + (rz_new/rz) p | rotate: rz <- rz_new, rr <- rr_new, sums cleared, iter++
+// Negative curvature (pq <= 0) freezes the iterate: x keeps the last value (or becomes the preconditioned gradient
+// if nothing was accepted yet) and flags bit0 is raised by the rotate kernel -- truncated Newton.
 __global__ void __launch_bounds__(256) k_pcg_init(int n_rows, int n_alloc, const double *__restrict__ b, float *x, float *r, KrylovScalars *ks)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
@@ -121,51 +155,47 @@ __global__ void __launch_bounds__(256) k_pcg_init(int n_rows, int n_alloc, const
         r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
         rr = (double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2;
     }
-    block_atomic_sum2(rr, 0.0, &ks->acc_rr[0], nullptr);
+    block_atomic_sum2(rr, 0.0, &ks->rr_new, nullptr);
 }
-// alpha = rz[c] / pq[c];  x += alpha p;  r -= alpha q;  rr[n] += r.r
-__global__ void __launch_bounds__(256) k_pcg_update(int n_rows, int it, const float *__restrict__ p, const float *__restrict__ q,
+__global__ void __launch_bounds__(256) k_pcg_update(int n_rows, const float *__restrict__ p, const float *__restrict__ q,
                                                     float *x, float *r, KrylovScalars *ks)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
-    int cur = it & 1, nxt = cur ^ 1;
-    double pq = ks->acc_pq[cur], rzc = ks->acc_rz[cur];
-    // negative curvature or breakdown freezes the iterate (truncated Newton).  This kernel only READS the flag
-    // (k_pcg_direction publishes it), so every thread takes the same branch.
+    double pq = ks->pq, rz = ks->rz;
     const bool bad = !(pq > 0.0);
-    const bool frozen = ((ks->flags & 1) != 0) || bad;
-    if (bad && it == 0 && row < n_rows) {   // no progress yet: fall back to the preconditioned gradient direction
+    const bool frozen = ((ks->flags & 1) != 0) || bad;      // flags is only written by the rotate kernel: uniform branch
+    if (bad && !(ks->flags & 1) && ks->iter == 0 && row < n_rows) {   // nothing accepted yet: preconditioned gradient
         x[3 * row] = p[3 * row]; x[3 * row + 1] = p[3 * row + 1]; x[3 * row + 2] = p[3 * row + 2];
     }
-    if (row == 0) ks->acc_pq[nxt] = 0;      // consumed by iteration it-1, next written by iteration it+1
-    if (frozen) {                           // keep the scalars of the frozen state so later iterations are no-ops
-        if (row == 0) { ks->acc_rr[nxt] = ks->acc_rr[cur]; }
-        return;
-    }
+    if (frozen) return;
     double rr = 0;
     if (row < n_rows) {
-        float alpha = (float)(rzc / pq);
+        float alpha = (float)(rz / pq);
         float r0 = r[3 * row] - alpha * q[3 * row], r1 = r[3 * row + 1] - alpha * q[3 * row + 1], r2 = r[3 * row + 2] - alpha * q[3 * row + 2];
         x[3 * row] += alpha * p[3 * row]; x[3 * row + 1] += alpha * p[3 * row + 1]; x[3 * row + 2] += alpha * p[3 * row + 2];
         r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
         rr = (double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2;
     }
-    block_atomic_sum2(rr, 0.0, &ks->acc_rr[nxt], nullptr);
+    block_atomic_sum2(rr, 0.0, &ks->rr_new, nullptr);
 }
-// p = z + beta p with beta = rz[n] / rz[c]   (it < 0: p = z)
-__global__ void __launch_bounds__(256) k_pcg_direction(int n, int it, const float *__restrict__ z, float *p, KrylovScalars *ks)
+// p = z + beta p with beta = rz_new / rz   (first != 0: p = z)
+__global__ void __launch_bounds__(256) k_pcg_direction(int n, int first, const float *__restrict__ z, float *p, const KrylovScalars *ks)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (it < 0) { if (i < n) p[i] = z[i]; return; }
-    int cur = it & 1, nxt = cur ^ 1;
-    const bool bad = !(ks->acc_pq[cur] > 0.0);     // same test as k_pcg_update (acc_pq[cur] is still intact)
-    if (bad && i == 0) atomicOr(&ks->flags, 1);
-    if ((ks->flags & 1) || bad) {
-        if (i == 0) ks->acc_rz[nxt] = ks->acc_rz[cur];
-        return;
-    }
-    float beta = (float)(ks->acc_rz[nxt] / ks->acc_rz[cur]);
+    if (first) { if (i < n) p[i] = z[i]; return; }
+    if ((ks->flags & 1) || !(ks->pq > 0.0)) return;
+    float beta = (float)(ks->rz_new / ks->rz);
     if (i < n) p[i] = z[i] + beta * p[i];
+}
+__global__ void k_pcg_rotate(int first, KrylovScalars *ks)
+{
+    if (first) { ks->rz = ks->rz_new; ks->rr = ks->rr_new; ks->rz_new = 0; ks->rr_new = 0; ks->pq = 0; return; }
+    if (!(ks->flags & 1)) {
+        if (!(ks->pq > 0.0)) ks->flags |= 1;
+        else { ks->rz = ks->rz_new; ks->rr = ks->rr_new; }
+    }
+    ks->rz_new = 0; ks->rr_new = 0; ks->pq = 0;
+    ks->iter++;
 }
 __global__ void k_f32_to_f64(int n, const float *__restrict__ a, double *b)
 {
@@ -200,22 +230,27 @@ void launch_block_jacobi64(tsl_ctx *ctx)
     ctx->launches++;
 }
 
-static int pcg_iteration(tsl_ctx *ctx, const float *opval, int it)
+static int pcg_iteration_body(tsl_ctx *ctx, const float *opval)
 {
     int n = ctx->cfg.n_verts;
     const SellMatrix &A = ctx->A;
     KrylovScalars *ks = ctx->ks;
-    int cur = it & 1, nxt = cur ^ 1;
-    // q = A p, pq[cur] += p.q ; also clears rz/rr of the next parity (they were read by iteration it-1's direction update)
-    k_spmv_dots<float><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, ctx->cg_p,
-                                                              &ks->acc_pq[cur], nullptr, &ks->acc_rz[nxt], &ks->acc_rr[nxt]);
-    k_pcg_update<<<GRID(n, 256), 256, 0, ctx->stream>>>(n, it, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ks);
+    cudaStream_t s = ctx->stream;
+    k_spmv_dots<float><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, ctx->cg_p, &ks->pq, nullptr);
+    k_pcg_update<<<GRID(n, 256), 256, 0, s>>>(n, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ks);
     ctx->launches += 2;
-    int rc = mg_apply(ctx, ctx->cg_r, ctx->cg_z, &ks->acc_rz[nxt]);
-    if (rc != TSL_OK) return rc;
-    k_pcg_direction<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(3 * n, it, ctx->cg_z, ctx->cg_p, ks);
-    ctx->launches++;
+    TRYR(mg_apply(ctx, ctx->cg_r, ctx->cg_z, &ks->rz_new));
+    k_pcg_direction<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, 0, ctx->cg_z, ctx->cg_p, ks);
+    k_pcg_rotate<<<1, 1, 0, s>>>(0, ks);
+    ctx->launches += 2;
     return TSL_OK;
+}
+static int pcg_iteration(tsl_ctx *ctx, const float *opval)
+{
+    GraphSlot &slot = ctx->g_pcg[opval == ctx->A.val32c ? 1 : 0];
+    // the key folds in the preconditioner choice so that an option change re-captures
+    const void *key = (const char *)opval + (ctx->precond ? 1 : 0);
+    return replay(ctx, slot, key, [&]() { return pcg_iteration_body(ctx, opval); });
 }
 
 static int pcg_start(tsl_ctx *ctx, const double *rhs)
@@ -225,10 +260,10 @@ static int pcg_start(tsl_ctx *ctx, const double *rhs)
     CK(cudaMemsetAsync(ctx->ks, 0, sizeof(KrylovScalars), s));
     k_pcg_init<<<GRID(nr, 256), 256, 0, s>>>(n, nr, rhs, ctx->cg_x, ctx->cg_r, ctx->ks);
     ctx->launches++;
-    int rc = mg_apply(ctx, ctx->cg_r, ctx->cg_z, &ctx->ks->acc_rz[0]);
-    if (rc != TSL_OK) return rc;
-    k_pcg_direction<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, -1, ctx->cg_z, ctx->cg_p, ctx->ks);
-    ctx->launches++;
+    TRYR(mg_apply(ctx, ctx->cg_r, ctx->cg_z, &ctx->ks->rz_new));
+    k_pcg_direction<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, 1, ctx->cg_z, ctx->cg_p, ctx->ks);
+    k_pcg_rotate<<<1, 1, 0, s>>>(1, ctx->ks);
+    ctx->launches += 2;
     return TSL_OK;
 }
 
@@ -236,22 +271,21 @@ int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, 
 {
     int n = ctx->cfg.n_verts;
     cudaStream_t s = ctx->stream;
-    int rc = pcg_start(ctx, rhs);
-    if (rc != TSL_OK) return rc;
+    TRYR(pcg_start(ctx, rhs));
     CK(cudaMemcpyAsync(ctx->ks_host, ctx->ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
-    double rr0 = ctx->ks_host->acc_rr[0];
+    double rr0 = ctx->ks_host->rr;
     int it = 0, flags = 0;
     double rr = rr0;
-    // the block-Jacobi iteration is three short kernels: poll less often there
-    const int check_every = (ctx->precond == 0 || ctx->mg.n_levels == 0) ? 10 : 1;
+    // the block-Jacobi iteration is a handful of short kernels: poll less often there
+    const int check_every = (ctx->precond == 0 || ctx->mg.n_levels == 0) ? 8 : 1;
     if (rr0 > 0) {
         while (it < max_iters) {
             int chunk = std::min(check_every, max_iters - it);
-            for (int k = 0; k < chunk; k++, it++) { rc = pcg_iteration(ctx, opval, it); if (rc != TSL_OK) return rc; }
+            for (int k = 0; k < chunk; k++, it++) TRYR(pcg_iteration(ctx, opval));
             CK(cudaMemcpyAsync(ctx->ks_host, ctx->ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            rr = ctx->ks_host->acc_rr[it & 1];
+            rr = ctx->ks_host->rr;
             flags = ctx->ks_host->flags;
             if (!(rr == rr)) { ctx->err = "PCG produced NaN"; return TSL_ERR_NUMERIC; }
             if (flags & 1) break;
@@ -267,7 +301,7 @@ int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, 
     return TSL_OK;
 }
 
-// what: 0 = full PCG iterations, 1 = SpMV only, 5 = V-cycle only
+// what: 0 = full PCG iterations, 1 = SpMV only, 5 = V-cycle only, 6 = multigrid setup
 int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out)
 {
     int n = ctx->cfg.n_verts;
@@ -275,21 +309,18 @@ int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out)
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     // a well-defined state: r = F, p = z = M^-1 F
-    int rc = pcg_start(ctx, ctx->F);
-    if (rc != TSL_OK) return rc;
+    TRYR(pcg_start(ctx, ctx->F));
+    if (what == 0) TRYR(pcg_iteration(ctx, ctx->A.val32));      // capture outside the timed region
+    if (what == 6) TRYR(mg_setup_replay(ctx));
     CK(cudaEventRecord(e0, s));
     for (int it = 0; it < iters; it++) {
         if (what == 1) {
             k_spmv_dots<float><<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32, ctx->cg_p, ctx->cg_q, ctx->cg_p,
-                                                            &ctx->ks->acc_pq[it & 1], nullptr, nullptr, nullptr);
+                                                            &ctx->ks->pq, nullptr);
             ctx->launches++;
-        } else if (what == 5) {
-            rc = mg_apply(ctx, ctx->cg_r, ctx->cg_z, nullptr);
-            if (rc != TSL_OK) return rc;
-        } else {
-            rc = pcg_iteration(ctx, ctx->A.val32, it);
-            if (rc != TSL_OK) return rc;
-        }
+        } else if (what == 5) TRYR(mg_apply(ctx, ctx->cg_r, ctx->cg_z, nullptr));
+        else if (what == 6) TRYR(mg_setup_replay(ctx));
+        else TRYR(pcg_iteration(ctx, ctx->A.val32));
     }
     CK(cudaEventRecord(e1, s));
     CK(cudaEventSynchronize(e1));
@@ -317,48 +348,37 @@ __global__ void __launch_bounds__(256) k_bi_init(int n, const double *__restrict
         x[i] = 0; r[i] = bi; rhat[i] = bi; p[i] = 0; v[i] = 0;
         rr = bi * bi;
     }
-    block_atomic_sum2(rr, rr, &ks->acc_rho[0], &ks->acc_rr[0]);
+    block_atomic_sum2(rr, rr, &ks->rho, &ks->rr);
 }
-// K_a (iteration it): beta = (rho_new/rho_old)(alpha/omega); p = r + beta (p - omega v)
-__global__ void __launch_bounds__(256) k_bi_a(int n, int it, const double *__restrict__ r, const double *__restrict__ v, double *p, KrylovScalars *ks)
+// beta = (rho/rho_old)(alpha/omega); p = r + beta (p - omega v)
+__global__ void __launch_bounds__(256) k_bi_a(int n, const double *__restrict__ r, const double *__restrict__ v, double *p, const KrylovScalars *ks)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int cur = it & 1;
     if (ks->flags & 1) return;
     double beta = 0, omega = 0;
-    if (it > 0) {
-        double rho_new = ks->acc_rho[cur], rho_old = ks->acc_rho[cur ^ 1];
-        omega = ks->acc_ts / ks->acc_tt;
-        beta = (rho_new / rho_old) * (ks->alpha / omega);
-    }
+    if (ks->iter > 0) { omega = ks->omega; beta = (ks->rho / ks->rho_old) * (ks->alpha / omega); }
     if (i < n) p[i] = r[i] + beta * (p[i] - omega * v[i]);
 }
-// K_c: alpha = rho_new / (rhat.v); s = r - alpha v
-__global__ void __launch_bounds__(256) k_bi_c(int n, int it, const double *__restrict__ r, const double *__restrict__ v, double *s, KrylovScalars *ks)
+// alpha = rho / (rhat.v); s = r - alpha v
+__global__ void __launch_bounds__(256) k_bi_c(int n, const double *__restrict__ r, const double *__restrict__ v, double *s, const KrylovScalars *ks)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int cur = it & 1;
     if (ks->flags & 1) return;
-    double rhv = ks->acc_rhv;
-    if (!(rhv != 0.0) || !(rhv == rhv)) { if (i == 0) atomicOr(&ks->flags, 1); return; }
-    double alpha = ks->acc_rho[cur] / rhv;
+    double rhv = ks->rhv;
+    if (!(rhv != 0.0) || !(rhv == rhv)) return;           // breakdown: the rotate kernel raises the flag
+    double alpha = ks->rho / rhv;
     if (i < n) s[i] = r[i] - alpha * v[i];
 }
-// K_e: omega = ts/tt; x += alpha y + omega z; r = s - omega t; rho[(it+1)&1] += rhat.r; rr[(it+1)&1] += r.r
-__global__ void __launch_bounds__(256) k_bi_e(int n, int it, const double *__restrict__ y, const double *__restrict__ z,
+// omega = ts/tt; dx += alpha y + omega z; r = s - omega t; rho_next += rhat.r; rr_new += r.r
+__global__ void __launch_bounds__(256) k_bi_e(int n, const double *__restrict__ y, const double *__restrict__ z,
                                               const double *__restrict__ s, const double *__restrict__ t, const double *__restrict__ rhat,
                                               double *x, double *r, KrylovScalars *ks)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    int nxt = (it & 1) ^ 1;
-    if (ks->flags & 1) {
-        if (i == 0) { ks->acc_rr[nxt] = ks->acc_rr[nxt ^ 1]; ks->acc_rho[nxt] = ks->acc_rho[nxt ^ 1]; }
-        return;
-    }
-    double tt = ks->acc_tt;
-    double omega = tt > 0 ? ks->acc_ts / tt : 0.0;
-    double alpha = ks->alpha;
-    if (i == 0) ks->acc_rhv = 0;
+    double rhv = ks->rhv, tt = ks->tt;
+    if ((ks->flags & 1) || !(rhv != 0.0) || !(rhv == rhv)) return;
+    double omega = tt > 0 ? ks->ts / tt : 0.0;
+    double alpha = ks->rho / rhv;
     double rho = 0, rr = 0;
     if (i < n) {
         x[i] += alpha * y[i] + omega * z[i];
@@ -366,34 +386,32 @@ __global__ void __launch_bounds__(256) k_bi_e(int n, int it, const double *__res
         r[i] = ri;
         rho = rhat[i] * ri; rr = ri * ri;
     }
-    block_atomic_sum2(rho, rr, &ks->acc_rho[nxt], &ks->acc_rr[nxt]);
+    block_atomic_sum2(rho, rr, &ks->rho_next, &ks->rr_new);
 }
-__global__ void k_bi_store_alpha(int it, KrylovScalars *ks)
-{   // runs between K_c and the second SpMV: publishes alpha while rho/rhv are still intact
-    if (ks->flags & 1) return;
-    ks->alpha = ks->acc_rho[it & 1] / ks->acc_rhv;
+__global__ void k_bi_rotate(KrylovScalars *ks)
+{
+    if (!(ks->flags & 1)) {
+        double rhv = ks->rhv, tt = ks->tt;
+        double omega = tt > 0 ? ks->ts / tt : 0.0;
+        if (!(rhv != 0.0) || !(rhv == rhv) || !(omega != 0.0) || !(ks->rho_next != 0.0)) ks->flags |= 1;
+        if ((rhv != 0.0) && (rhv == rhv)) {
+            ks->alpha = ks->rho / rhv; ks->omega = omega;
+            ks->rho_old = ks->rho; ks->rho = ks->rho_next; ks->rr = ks->rr_new;
+        }
+    }
+    ks->rho_next = 0; ks->rr_new = 0; ks->rhv = 0; ks->ts = 0; ks->tt = 0;
+    ks->iter++;
 }
-// out = M in for fp64 vectors
-template <typename T>
-__global__ void __launch_bounds__(256) k_apply_minv64(int n_rows, const T *__restrict__ minv, const double *__restrict__ in, double *out)
+// out = M in for fp64 vectors (block-Jacobi)
+__global__ void __launch_bounds__(256) k_apply_minv64(int n_rows, const double *__restrict__ minv, const double *__restrict__ in, double *out)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= n_rows) return;
-    double z0, z1, z2;
-    apply_minv<double>(minv, row, in[3 * row], in[3 * row + 1], in[3 * row + 2], z0, z1, z2);
-    out[3 * row] = z0; out[3 * row + 1] = z1; out[3 * row + 2] = z2;
-}
-int precond_apply_f64io(tsl_ctx *ctx, const double *in, double *out);
-static int precond64(tsl_ctx *ctx, const double *in, double *out)
-{
-    int n = ctx->cfg.n_verts;
-    cudaStream_t s = ctx->stream;
-    if (ctx->precond == 0 || ctx->mg.n_levels == 0) {
-        k_apply_minv64<double><<<GRID(n, 256), 256, 0, s>>>(n, ctx->minv64, in, out);
-        ctx->launches++;
-        return TSL_OK;
-    }
-    return precond_apply_f64io(ctx, in, out);
+    const double *m = minv + 9 * (size_t)row;
+    double r0 = in[3 * row], r1 = in[3 * row + 1], r2 = in[3 * row + 2];
+    out[3 * row] = m[0] * r0 + m[1] * r1 + m[2] * r2;
+    out[3 * row + 1] = m[3] * r0 + m[4] * r1 + m[5] * r2;
+    out[3 * row + 2] = m[6] * r0 + m[7] * r1 + m[8] * r2;
 }
 // out = M in through the fp32 preconditioner of the last mg_setup (V-cycle, or fp32 block-Jacobi when precond == 0)
 int precond_apply_f64io(tsl_ctx *ctx, const double *in, double *out)
@@ -401,11 +419,20 @@ int precond_apply_f64io(tsl_ctx *ctx, const double *in, double *out)
     int n = ctx->cfg.n_verts, nr = ctx->A.n_slices * 32;
     cudaStream_t s = ctx->stream;
     k_f64_to_f32<<<GRID(3 * nr, 256), 256, 0, s>>>(3 * n, 3 * nr, in, ctx->cg_r64tmp);
-    int rc = mg_apply(ctx, ctx->cg_r64tmp, ctx->cg_z, nullptr);
-    if (rc != TSL_OK) return rc;
+    TRYR(mg_apply(ctx, ctx->cg_r64tmp, ctx->cg_z, nullptr));
     k_f32_to_f64<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, ctx->cg_z, out);
     ctx->launches += 2;
     return TSL_OK;
+}
+static int precond64(tsl_ctx *ctx, const double *in, double *out)
+{
+    int n = ctx->cfg.n_verts;
+    if (ctx->precond == 0 || ctx->mg.n_levels == 0) {
+        k_apply_minv64<<<GRID(n, 256), 256, 0, ctx->stream>>>(n, ctx->minv64, in, out);
+        ctx->launches++;
+        return TSL_OK;
+    }
+    return precond_apply_f64io(ctx, in, out);
 }
 // r = b - A x (fp64), rr = |r|^2 into acc
 __global__ void __launch_bounds__(256) k_residual64(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
@@ -429,72 +456,75 @@ __global__ void k_axpy64(int n, const double *__restrict__ dx, double *x)
     if (i < n) x[i] += dx[i];
 }
 
-int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
+static int bicg_iteration_body(tsl_ctx *ctx)
 {
     int n = ctx->cfg.n_verts, n3 = 3 * n;
     cudaStream_t s = ctx->stream;
     const SellMatrix &A = ctx->A;
     KrylovScalars *ks = ctx->ks;
     double *r = ctx->bi[0], *rhat = ctx->bi[1], *p = ctx->bi[2], *v = ctx->bi[3], *y = ctx->bi[4], *sv = ctx->bi[5], *z = ctx->bi[6], *t = ctx->bi[7];
+    double *dx = ctx->sol;
+    k_bi_a<<<GRID(n3, 256), 256, 0, s>>>(n3, r, v, p, ks);
+    TRYR(precond64(ctx, p, y));
+    k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, y, v, rhat, &ks->rhv, nullptr);
+    k_bi_c<<<GRID(n3, 256), 256, 0, s>>>(n3, r, v, sv, ks);
+    TRYR(precond64(ctx, sv, z));
+    k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, z, t, sv, &ks->ts, &ks->tt);
+    k_bi_e<<<GRID(n3, 256), 256, 0, s>>>(n3, y, z, sv, t, rhat, dx, r, ks);
+    k_bi_rotate<<<1, 1, 0, s>>>(ks);
+    ctx->launches += 6;
+    return TSL_OK;
+}
+
+int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
+{
+    int n = ctx->cfg.n_verts, n3 = 3 * n;
+    cudaStream_t s = ctx->stream;
+    const SellMatrix &A = ctx->A;
+    KrylovScalars *ks = ctx->ks;
+    double *r = ctx->bi[0], *rhat = ctx->bi[1], *p = ctx->bi[2], *v = ctx->bi[3];
     double *dx = ctx->sol;                 // correction of the current restart cycle
     double *res = ctx->adj_rhs;            // true residual b - A x
     CK(cudaMemsetAsync(x, 0, sizeof(double) * n3, s));
     CK(cudaMemcpyAsync(res, rhs, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
     double rr00 = -1, rr = 0;
     int it = 0, flags = 0, restarts = 0;
-    const int check_every = (ctx->precond == 0 || ctx->mg.n_levels == 0) ? 10 : 1;
+    const int check_every = (ctx->precond == 0 || ctx->mg.n_levels == 0) ? 8 : 1;
     const int max_restarts = 8;
+    const void *key = (const char *)ctx->A.val64 + (ctx->precond ? 1 : 0);
     while (true) {
         CK(cudaMemsetAsync(ks, 0, sizeof(KrylovScalars), s));
         k_bi_init<<<GRID(n3, 256), 256, 0, s>>>(n3, res, dx, r, rhat, p, v, ks);
         ctx->launches++;
         CK(cudaMemcpyAsync(ctx->ks_host, ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        double rr0 = ctx->ks_host->acc_rr[0];
+        double rr0 = ctx->ks_host->rr;
         if (rr00 < 0) rr00 = rr0;
         rr = rr0;
         if (!(rr0 == rr0)) { ctx->err = "BiCGStab: NaN residual"; return TSL_ERR_NUMERIC; }
         if (rr0 <= rel_tol * rel_tol * rr00 || rr00 == 0) break;
-        int it_cycle = 0;
-        bool broke = false;
+        bool poisoned = false;
         while (it < max_iters) {
             int chunk = std::min(check_every, max_iters - it);
-            for (int k = 0; k < chunk; k++, it++, it_cycle++) {
-                int cur = it_cycle & 1;
-                k_bi_a<<<GRID(n3, 256), 256, 0, s>>>(n3, it_cycle, r, v, p, ks);
-                int rc = precond64(ctx, p, y);
-                if (rc != TSL_OK) return rc;
-                // v = A y, rhv += rhat.v ; clears rho/rr of the next parity (K_a has read rho_old) and ts/tt (K_a has read omega)
-                k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, y, v, rhat, &ks->acc_rhv, nullptr,
-                                                                 &ks->acc_rho[cur ^ 1], &ks->acc_rr[cur ^ 1]);
-                k_bi_c<<<GRID(n3, 256), 256, 0, s>>>(n3, it_cycle, r, v, sv, ks);
-                k_bi_store_alpha<<<1, 1, 0, s>>>(it_cycle, ks);
-                CK(cudaMemsetAsync(&ks->acc_ts, 0, 2 * sizeof(double), s));
-                rc = precond64(ctx, sv, z);
-                if (rc != TSL_OK) return rc;
-                // t = A z, ts += s.t, tt += t.t
-                k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, z, t, sv, &ks->acc_ts, &ks->acc_tt, nullptr, nullptr);
-                k_bi_e<<<GRID(n3, 256), 256, 0, s>>>(n3, it_cycle, y, z, sv, t, rhat, dx, r, ks);
-                ctx->launches += 6;
-            }
+            for (int k = 0; k < chunk; k++, it++) TRYR(replay(ctx, ctx->g_bicg, key, [&]() { return bicg_iteration_body(ctx); }));
             CK(cudaMemcpyAsync(ctx->ks_host, ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
             CK(cudaStreamSynchronize(s));
-            rr = ctx->ks_host->acc_rr[it_cycle & 1];
-            if (!(rr == rr)) { broke = true; break; }          // dx is poisoned: drop this cycle's correction
+            rr = ctx->ks_host->rr;
+            if (!(rr == rr)) { poisoned = true; break; }       // dx is poisoned: drop this cycle's correction
             if (ctx->ks_host->flags & 1) break;                // breakdown: dx holds the last good iterate
             if (rr <= rel_tol * rel_tol * rr00) break;
         }
         // x += dx, true residual for the next cycle / the final report
-        if (!broke) {
+        if (!poisoned) {
             k_axpy64<<<GRID(n3, 256), 256, 0, s>>>(n3, dx, x);
             ctx->launches++;
         }
-        CK(cudaMemsetAsync(&ks->acc_rr[0], 0, sizeof(double), s));
-        k_residual64<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, rhs, x, res, &ks->acc_rr[0]);
+        CK(cudaMemsetAsync(&ks->rr, 0, sizeof(double), s));
+        k_residual64<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, rhs, x, res, &ks->rr);
         ctx->launches++;
         CK(cudaMemcpyAsync(ctx->ks_host, ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
-        rr = ctx->ks_host->acc_rr[0];
+        rr = ctx->ks_host->rr;
         if (!(rr == rr)) { ctx->err = "BiCGStab produced NaN"; return TSL_ERR_NUMERIC; }
         if (rr <= rel_tol * rel_tol * rr00) break;
         if (it >= max_iters) { flags |= 2; break; }

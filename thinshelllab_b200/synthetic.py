@@ -44,5 +44,6 @@ def sheet_scene(N, device="cuda:0", **kw):
     NV = (N + 1) ** 2
     s.engine.pos[:NV] = torch.from_numpy(sp["cloth_pos"]).to(s.engine.device)
     s.engine.prev_pos.copy_(s.engine.pos)
+    s.engine.cloth_ref_angle[0].zero_()     # a flat sheet: no pre-creased rows (Scene_bouncing's init_ref_angle_bridge is scene specific)
     s.spec = sp
     return s

@@ -24,6 +24,7 @@ if use_oracle:
     o = orc.OracleScene(c.N, c.M, c.dx, s.dt, tpos, tfaces, tmass, Kb=100.0, k_angle=3.14, k_contact=s.k_contact, eps_contact=s.eps_contact,
                         eps_v=s.eps_v, mu=0.5, max_n_constraints=s.max_n_constraints, grid_n=e.cfg.grid_n)
     o.pos[:] = e.pos.cpu().numpy(); o.prev_pos[:] = o.pos; o.vel[:] = 0
+    o.ref_angle[:] = e.cloth_ref_angle[0].cpu().numpy()
 for k in range(steps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
     st = s.time_step()
@@ -38,7 +39,7 @@ e.contact_detect()
 e.assemble(_lib.ASM_RESIDUAL | _lib.ASM_HESSIAN | _lib.ASM_NEWTON | _lib.ASM_SPD)
 sz = e.sizes()
 print("sizes", sz)
-for name, what in (("pcg_iter", 0), ("spmv", 1), ("energy", 2), ("residual", 3), ("hessian", 4), ("vcycle", 5)):
+for name, what in (("pcg_iter", 0), ("spmv", 1), ("energy", 2), ("residual", 3), ("hessian", 4), ("vcycle", 5), ("mg_setup", 6)):
     e.bench_kernel(what, 5)
     print(f"  {name}: {1e3 * e.bench_kernel(what, 50):.1f} us")
 for lev in range(e.mg_level(0, values=False)[2]):
