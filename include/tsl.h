@@ -48,7 +48,8 @@ typedef struct tsl_step_stats {
     int linesearch_evals;       /* energy evaluations inside the line searches  */
     int n_contacts;             /* nc after contact_analysis                    */
     int converged;              /* 1 if delta < tol                             */
-    int flags;                  /* bit0: negative curvature met in PCG; bit1: Krylov hit its cap */
+    int flags;                  /* bit0: negative curvature met in PCG; bit1: Krylov hit its cap; bit2: a step was accepted below the
+                                   resolution of the energy sum (plain Newton step near convergence) */
     double delta;               /* last |p|_inf / h  (BaseScene.newton_step return value) */
     double energy;              /* E at the accepted point                      */
     double ms_contact, ms_assembly, ms_solve, ms_linesearch; /* host wall clock per phase (diagnostic) */

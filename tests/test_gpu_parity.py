@@ -207,18 +207,48 @@ def _oracle_for(s, **kw):
     return o
 
 
+def _accept_fixed_point(s, o, pos0, vel0):
+    """Parity of one converged step.  Where the incremental potential has a unique minimiser the positions agree to 3e-7 m.
+    A buckling sheet has several (the reference's own answer then depends on its Newton path, quirk Q9); there the CUDA
+    result must be a fixed point of the REFERENCE's iteration -- its Newton step from x_gpu, with its own projected
+    Hessian and a direct solve, is below 10x its stopping threshold -- and must not lie above the reference's energy.
+    Returns the position difference; the oracle is then moved to the CUDA state so that later steps stay comparable."""
+    e = s.engine
+    x_gpu = e.pos.cpu().numpy()
+    err = np.abs(x_gpu - o.pos).max()
+    if err >= 3e-7:
+        x_o, vel_o = o.pos.copy(), o.vel.copy()
+        o.vel[:] = vel0                      # the step's potential uses the velocity at the start of the step
+        E_o = o.compute_energy()
+        o.pos[:] = x_gpu
+        E_g = o.compute_energy()
+        o.compute_residual_and_hessian(spd=True)
+        p = o.solve(o.F)
+        assert np.abs(p).max() / o.dt < 1e-6, ("not a fixed point of the reference iteration", np.abs(p).max() / o.dt)
+        assert E_g <= E_o + 1e-9 * abs(E_o), (E_g, E_o)
+        o.pos[:] = x_o; o.vel[:] = vel_o
+    # continue both from the CUDA state (positions, velocities, plastic angles, sticky contact sides)
+    o.pos[:] = x_gpu; o.vel[:] = e.vel.cpu().numpy(); o.ref_angle[:] = e.cloth_ref_angle[0].cpu().numpy()
+    flag, d, idx, w = e.projection(1)
+    o.proj_flag[1][:] = flag; o.proj_dir[1][:] = d
+    return err
+
+
 def test_sheet_steps_vs_oracle_small():
-    """32 x 32 synthetic sheet landing on the table: two full implicit steps, CUDA (own Newton matrix, PCG) against the
-    oracle (reference Hessian, direct solve): same contact sets, same fixed points"""
+    """32 x 32 synthetic sheet landing on the table: three full implicit steps, CUDA (own Newton matrix, multigrid PCG) against
+    the oracle (reference Hessian, direct solve): same contact sets, same fixed points"""
     s = sheet_scene(32)
     o = _oracle_for(s)
-    for step in range(2):
+    errs = []
+    for step in range(3):
+        pos0, vel0 = o.pos.copy(), o.vel.copy()
         st = s.time_step()
         o.time_step()
         assert st.converged
         assert st.n_contacts == o.nc and o.nc > 50
         assert sorted(map(tuple, s.engine.constraints()["idx"])) == sorted(map(tuple, o.c_idx[:o.nc]))
-        assert np.abs(s.engine.pos.cpu().numpy() - o.pos).max() < 3e-7, step
+        errs.append(_accept_fixed_point(s, o, pos0, vel0))
+    assert errs[0] < 3e-7, errs           # the first step (sheet settling on the table) has a unique minimiser
 
 
 def test_sheet_50k_first_iteration_and_properties():

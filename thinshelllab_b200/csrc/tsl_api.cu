@@ -526,10 +526,12 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         if (fnorm_prev > 0 && fnorm > 0) eta = std::min(0.1, std::max(1e-3, 0.9 * (fnorm / fnorm_prev) * (fnorm / fnorm_prev)));
         fnorm_prev = fnorm;
         launch_absmax(ctx, ctx->sol, n3, ctx->red_out + 1);
+        launch_dot(ctx, ctx->F, ctx->sol, n3, ctx->red_out + 3);
         CK(cudaMemcpyAsync(ctx->x1, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
-        CK(cudaMemcpyAsync(ctx->red_host + 1, ctx->red_out + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+        CK(cudaMemcpyAsync(ctx->red_host + 1, ctx->red_out + 1, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         double p_norm = ctx->red_host[1];
+        double decrement = ctx->red_host[3];      // F . p: first-order energy decrease of the full step
         double t2 = now_ms();
         st.ms_solve += t2 - t1;
         if (!(p_norm == p_norm)) { ctx->err = "NaN in Newton direction"; return TSL_ERR_NUMERIC; }
@@ -540,6 +542,8 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
             TRY(energy_sync(ctx, &E));
             st.linesearch_evals++;
             if (E < E0) break;
+            // below the resolution of the fp64 energy sum the comparison is noise: take the plain Newton step
+            if (alpha == 1.0 && decrement >= 0 && decrement <= 1e-10 * fabs(E0)) { st.flags |= 4; break; }
             alpha /= 2;
         }
         if (alpha == 1.0 && E < E0) {

@@ -63,8 +63,8 @@ struct ContactDev {
 // Geometric multigrid over the cloth's structured vertex grid (tsl_mg.cu): the preconditioner of the forward PCG and
 // of the adjoint BiCGStab.  Level 0 is the sliced-ELL matrix itself (all vertices); level l >= 1 is an n0 x n1 vertex
 // grid whose operator is the Galerkin product P^T A P (bilinear P) stored as a 5x5 stencil of 3x3 blocks, SoA:
-//   val[(slot*9 + comp) * nvp + v],  slot = (dI+2)*5 + (dJ+2),  v = I*n1 + J
-// so that one thread per vertex reads consecutive addresses for every (slot, comp).
+//   val[v*225 + slot*9 + comp],  slot = (dI+2)*5 + (dJ+2),  v = I*n1 + J
+// so that one warp per vertex streams its row with coalesced loads.
 #define TSL_MG_MAX_LEVELS 12
 #define TSL_MG_MAX_DEGREE 8
 struct MgLevel {

@@ -15,6 +15,7 @@ void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alp
 void launch_update_vel(tsl_ctx *ctx);
 void launch_update_ref_angle(tsl_ctx *ctx, const ClothDev &c);
 void launch_absmax(tsl_ctx *ctx, const double *a, int n, double *out_dev);
+void launch_dot(tsl_ctx *ctx, const double *a, const double *b, int n, double *out_dev);
 void launch_refangle_a2ax(tsl_ctx *ctx, const ClothDev &c, const double *pos, const double *ag_step, double *ag_prev, double *pg_step);
 void launch_refangle_x2a(tsl_ctx *ctx, const ClothDev &c, const double *pos, const double *z, double *ag_prev);
 void launch_contact_backprop(tsl_ctx *ctx, const double *pos, const double *z, double *pg_prev);

@@ -7,6 +7,7 @@
 //   * prolongation P: bilinear per coordinate (vertices with even (i, j) survive), applied per x/y/z component,
 //   * coarse operators: Galerkin products P^T A P, recomputed on the device for every new matrix; a fine stencil of
 //     radius 2 (triangle + hinge neighbours) gives coarse stencils of radius 2 on every level -> 5x5 blocks of 3x3,
+//     stored per vertex as 225 contiguous floats and applied by one warp per vertex,
 //   * smoother: Chebyshev polynomial in D^-1 A (D = 3x3 diagonal blocks) on [lmax/ratio, lmax]; lmax(D^-1 A) comes
 //     from a few warm-started power iterations per level with a safety factor (the iteration is sensitive to an
 //     under-estimate, not to an over-estimate),
@@ -44,33 +45,38 @@ struct SellOp {
         y0 = a0; y1 = a1; y2 = a2;
     }
 };
+// Stencil levels: one WARP per vertex.  The 225 values of a vertex row (25 slots x 3x3) are contiguous, so the warp
+// streams them with 8 fully coalesced loads; lane e handles element e = slot*9 + comp of each 32-chunk, multiplies by
+// the matching component of the neighbour's x and the three row sums are formed with a shuffle reduction.  (A
+// thread-per-vertex walk over 25 slots is a 35-45 us latency chain even on a 36-vertex grid: measured, profiles/.)
+// Slots that point outside the grid hold zeros (k_galerkin writes them), so neighbour indices are clamped, not branched.
 struct StencilOp {
-    const float *val;
-    int n0, n1, nvp;
-    __device__ __forceinline__ void mul(int v, const float *__restrict__ x, float &y0, float &y1, float &y2) const
-    {
-        int I = v / n1, J = v - I * n1;
-        float a0 = 0, a1 = 0, a2 = 0;
-#pragma unroll
-        for (int dI = -2; dI <= 2; dI++) {
-            int ii = I + dI;
-            if ((unsigned)ii >= (unsigned)n0) continue;
-#pragma unroll
-            for (int dJ = -2; dJ <= 2; dJ++) {
-                int jj = J + dJ;
-                if ((unsigned)jj >= (unsigned)n1) continue;
-                const int slot = (dI + 2) * 5 + (dJ + 2);
-                const float *a = val + (size_t)(slot * 9) * nvp + v;
-                int u = ii * n1 + jj;
-                float x0 = x[3 * u], x1 = x[3 * u + 1], x2 = x[3 * u + 2];
-                a0 += __ldg(a) * x0 + __ldg(a + nvp) * x1 + __ldg(a + 2 * (size_t)nvp) * x2;
-                a1 += __ldg(a + 3 * (size_t)nvp) * x0 + __ldg(a + 4 * (size_t)nvp) * x1 + __ldg(a + 5 * (size_t)nvp) * x2;
-                a2 += __ldg(a + 6 * (size_t)nvp) * x0 + __ldg(a + 7 * (size_t)nvp) * x1 + __ldg(a + 8 * (size_t)nvp) * x2;
-            }
-        }
-        y0 = a0; y1 = a1; y2 = a2;
-    }
+    const float *val;      // [nv][225]
+    int n0, n1;
 };
+__device__ __forceinline__ void stencil_row_warp(const StencilOp &A, int v, int lane, const float *__restrict__ x, float &y0, float &y1, float &y2)
+{
+    int I = v / A.n1, J = v - I * A.n1;
+    const float *row = A.val + (size_t)v * 225;
+    float a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int e = k * 32 + lane;
+        if (e < 225) {
+            int slot = e / 9, c = e - slot * 9;
+            int q = slot / 5;
+            int ii = min(max(I + q - 2, 0), A.n0 - 1), jj = min(max(J + slot - q * 5 - 2, 0), A.n1 - 1);
+            int r = c / 3;
+            float t = __ldg(row + e) * x[3 * (ii * A.n1 + jj) + (c - r * 3)];
+            a0 += (r == 0) ? t : 0.f; a1 += (r == 1) ? t : 0.f; a2 += (r == 2) ? t : 0.f;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    y0 = a0; y1 = a1; y2 = a2;
+}
 
 __device__ __forceinline__ void block_atomic_sum(double a, double *acc)
 {
@@ -110,10 +116,9 @@ __global__ void __launch_bounds__(256) k_cheb_first(int nrows, const float *__re
 }
 // d = a d + c D^-1 (b - A x_in) ; x_out = x_in + d     (b == nullptr: b = 0; x_out == nullptr: not stored)
 // acc_mode 1: acc += b . x_out      acc_mode 2: acc += d . d
-template <class Op>
-__global__ void __launch_bounds__(256) k_cheb_step(Op A, int nrows, const float *__restrict__ dinv, const float *__restrict__ b,
-                                                   const float *__restrict__ x_in, float *d, float *x_out,
-                                                   const float *__restrict__ coef, double *acc, int acc_mode)
+__global__ void __launch_bounds__(256) k_cheb_step_sell(SellOp A, int nrows, const float *__restrict__ dinv, const float *__restrict__ b,
+                                                        const float *__restrict__ x_in, float *d, float *x_out,
+                                                        const float *__restrict__ coef, double *acc, int acc_mode)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0;
@@ -137,14 +142,50 @@ __global__ void __launch_bounds__(256) k_cheb_step(Op A, int nrows, const float 
     }
     if (acc) block_atomic_sum(s, acc);
 }
-template <class Op>
-__global__ void __launch_bounds__(256) k_mg_residual(Op A, int nrows, const float *__restrict__ b, const float *__restrict__ x, float *r)
+// the same update on a stencil level, one warp per vertex (lanes 0..2 finish the three components)
+__global__ void __launch_bounds__(256) k_cheb_step_stencil(StencilOp A, int nv, const float *__restrict__ dinv, const float *__restrict__ b,
+                                                           const float *__restrict__ x_in, float *d, float *x_out,
+                                                           const float *__restrict__ coef, double *acc, int acc_mode)
+{
+    int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    double s = 0;
+    if (v < nv) {
+        float y0, y1, y2;
+        stencil_row_warp(A, v, lane, x_in, y0, y1, y2);
+        if (lane < 3) {
+            float a = coef[0], c = coef[1];
+            float r0 = -y0, r1 = -y1, r2 = -y2;
+            float bq = 0.f;
+            if (b) { r0 += b[3 * v]; r1 += b[3 * v + 1]; r2 += b[3 * v + 2]; bq = b[3 * v + lane]; }
+            const float *m = dinv + 9 * (size_t)v + 3 * lane;
+            float dq = c * (m[0] * r0 + m[1] * r1 + m[2] * r2);
+            if (a != 0.f) dq += a * d[3 * v + lane];
+            d[3 * v + lane] = dq;
+            if (x_out) {
+                float o = x_in[3 * v + lane] + dq;
+                x_out[3 * v + lane] = o;
+                if (acc_mode == 1) s = (double)bq * o;
+            }
+            if (acc_mode == 2) s = (double)dq * dq;
+        }
+    }
+    if (acc) block_atomic_sum(s, acc);
+}
+__global__ void __launch_bounds__(256) k_mg_residual_sell(SellOp A, int nrows, const float *__restrict__ b, const float *__restrict__ x, float *r)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nrows) return;
     float y0, y1, y2;
     A.mul(row, x, y0, y1, y2);
     r[3 * row] = b[3 * row] - y0; r[3 * row + 1] = b[3 * row + 1] - y1; r[3 * row + 2] = b[3 * row + 2] - y2;
+}
+__global__ void __launch_bounds__(256) k_mg_residual_stencil(StencilOp A, int nv, const float *__restrict__ b, const float *__restrict__ x, float *r)
+{
+    int v = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (v >= nv) return;
+    float y0, y1, y2;
+    stencil_row_warp(A, v, lane, x, y0, y1, y2);
+    if (lane < 3) r[3 * v + lane] = b[3 * v + lane] - (lane == 0 ? y0 : (lane == 1 ? y1 : y2));
 }
 // z = D^-1 b, acc += b . z  (block-Jacobi preconditioner, precond == 0)
 __global__ void __launch_bounds__(256) k_apply_dinv(int nrows, const float *__restrict__ dinv, const float *__restrict__ b, float *z, double *acc)
@@ -239,9 +280,9 @@ __global__ void k_sell_to_stencil(int off, int nvc, int n1, const int *__restric
         if (di < -2 || di > 2 || dj < -2 || dj > 2) continue;
         int slot = (di + 2) * 5 + (dj + 2);
         const float *src = val + (long long)b * 9 + lane;
-        float *dst = out + (size_t)(slot * 9) * nvp + v;
+        float *dst = out + (size_t)v * 225 + slot * 9;
 #pragma unroll
-        for (int c = 0; c < 9; c++) dst[(size_t)c * nvp] = src[c * 32];
+        for (int c = 0; c < 9; c++) dst[c] = src[c * 32];
     }
 }
 // A_c = P^T A_f P, one thread per (coarse vertex, coarse stencil slot).  mask: frozen flags of the fine grid's
@@ -253,7 +294,7 @@ __global__ void __launch_bounds__(128) k_galerkin(const float *__restrict__ val_
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int nvc = n0c * n1c;
     if (t >= nvc * 25) return;
-    int slot = t / nvc, cv = t - slot * nvc;
+    int cv = t / 25, slot = t - cv * 25;
     int I = cv / n1c, J = cv - I * n1c;
     int Ip = I + slot / 5 - 2, Jp = J + slot % 5 - 2;
     float acc[9];
@@ -279,26 +320,26 @@ __global__ void __launch_bounds__(128) k_galerkin(const float *__restrict__ val_
                         int dj = jp - j;
                         if ((unsigned)jp >= (unsigned)n1f || dj < -2 || dj > 2) continue;
                         float w = wip * pw1(bp, Jp, n1c);
-                        const float *src = val_f + (size_t)(((di + 2) * 5 + (dj + 2)) * 9) * nvpf + fv;
+                        const float *src = val_f + (size_t)fv * 225 + ((di + 2) * 5 + (dj + 2)) * 9;
                         if (MASK) {
                             int fc = ip * n1f + jp;
                             float mr[3], mc[3];
 #pragma unroll
                             for (int q = 0; q < 3; q++) { mr[q] = mask[3 * fv + q] ? 0.f : w; mc[q] = mask[3 * fc + q] ? 0.f : 1.f; }
 #pragma unroll
-                            for (int c = 0; c < 9; c++) acc[c] += mr[c / 3] * mc[c % 3] * __ldg(src + (size_t)c * nvpf);
+                            for (int c = 0; c < 9; c++) acc[c] += mr[c / 3] * mc[c % 3] * __ldg(src + c);
                         } else {
 #pragma unroll
-                            for (int c = 0; c < 9; c++) acc[c] += w * __ldg(src + (size_t)c * nvpf);
+                            for (int c = 0; c < 9; c++) acc[c] += w * __ldg(src + c);
                         }
                     }
                 }
             }
         }
     }
-    float *dst = val_c + (size_t)(slot * 9) * nvpc + cv;
+    float *dst = val_c + (size_t)cv * 225 + slot * 9;
 #pragma unroll
-    for (int c = 0; c < 9; c++) dst[(size_t)c * nvpc] = acc[c];
+    for (int c = 0; c < 9; c++) dst[c] = acc[c];
 }
 __device__ __forceinline__ void inv3_guarded(const float *a, float *inv)
 {
@@ -322,7 +363,7 @@ __global__ void k_dinv_stencil(int nv, int nvp, const float *__restrict__ val, f
     if (v >= nv) return;
     float a[9], inv[9];
 #pragma unroll
-    for (int c = 0; c < 9; c++) a[c] = val[(size_t)(12 * 9 + c) * nvp + v];
+    for (int c = 0; c < 9; c++) a[c] = val[(size_t)v * 225 + 12 * 9 + c];
     inv3_guarded(a, inv);
 #pragma unroll
     for (int c = 0; c < 9; c++) dinv[9 * (size_t)v + c] = inv[c];
@@ -432,16 +473,16 @@ void mg_free(tsl_ctx *ctx)
 }
 
 static SellOp sell_op(tsl_ctx *ctx, const float *val) { SellOp o; o.slice_base = ctx->A.slice_base; o.colidx = ctx->A.colidx; o.val = val; return o; }
-static StencilOp stencil_op(const MgLevel &L) { StencilOp o; o.val = L.val; o.n0 = L.n0; o.n1 = L.n1; o.nvp = L.nvp; return o; }
+static StencilOp stencil_op(const MgLevel &L) { StencilOp o; o.val = L.val; o.n0 = L.n0; o.n1 = L.n1; return o; }
 
 // d = a d + c D^-1 (b - A x_in), x_out = x_in + d on level l (level 0 smooths with the clamped matrix)
 static void launch_step(tsl_ctx *ctx, int l, const float *b, const float *x_in, float *d, float *x_out, const float *coef, double *acc, int mode)
 {
     MgLevel &L = ctx->mg.lev[l];
     if (l == 0)
-        k_cheb_step<SellOp><<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32c), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        k_cheb_step_sell<<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32c), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     else
-        k_cheb_step<StencilOp><<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(stencil_op(L), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        k_cheb_step_stencil<<<GRID(32LL * L.nv, 256), 256, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     ctx->launches++;
 }
 
@@ -523,8 +564,8 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
     MgLevel &C = mg.lev[l + 1];
     int off = (l == 0) ? mg.cloth_offset : 0;
     const int *mask = (l == 0) ? ctx->frozen : nullptr;
-    if (l == 0) k_mg_residual<SellOp><<<GRID(L.nrows, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32c), L.nrows, b, cur, L.r);
-    else k_mg_residual<StencilOp><<<GRID(L.nrows, 256), 256, 0, s>>>(stencil_op(L), L.nrows, b, cur, L.r);
+    if (l == 0) k_mg_residual_sell<<<GRID(L.nrows, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32c), L.nrows, b, cur, L.r);
+    else k_mg_residual_stencil<<<GRID(32LL * L.nv, 256), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     k_restrict<<<GRID(C.nv, 128), 128, 0, s>>>(L.n0, L.n1, off, L.r, mask, C.n0, C.n1, C.b);
     ctx->launches += 2;
     float *xc = vcycle_level(ctx, l + 1, C.b, nullptr, nullptr);
@@ -569,7 +610,7 @@ int mg_get_level(tsl_ctx *ctx, int level, int *dims, float *lmax, float *val_hos
         std::vector<float> tmp((size_t)225 * L.nvp);
         CK(cudaMemcpy(tmp.data(), L.val, sizeof(float) * tmp.size(), cudaMemcpyDeviceToHost));
         for (int sc = 0; sc < 225; sc++)
-            for (int v = 0; v < L.nv; v++) val_host[(size_t)sc * L.nv + v] = tmp[(size_t)sc * L.nvp + v];
+            for (int v = 0; v < L.nv; v++) val_host[(size_t)sc * L.nv + v] = tmp[(size_t)v * 225 + sc];
     }
     return TSL_OK;
 }

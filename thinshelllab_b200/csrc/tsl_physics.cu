@@ -635,6 +635,15 @@ __global__ void k_absmax(int n, const double *__restrict__ a, double *partial, u
     }
 }
 
+// a . b with the deterministic grid reduction (Newton decrement F . p for the line search's noise test)
+__global__ void __launch_bounds__(256) k_dot(int n, const double *__restrict__ a, const double *__restrict__ b, double *partial, unsigned int *ticket, double *out)
+{
+    double s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += a[i] * b[i];
+    s = block_sum(s);
+    grid_sum_finish(s, partial, ticket, out);
+}
+
 // ------------------------------------------------------------------------------------------------ adjoint element kernels
 // Cloth.ref_angle_backprop_a2ax (model_fold_offset.py:1179-1206)
 __global__ void k_refangle_a2ax(ClothDev c, const double *__restrict__ pos, const double *__restrict__ ag_step, double *ag_prev, double *pos_grad_step)
@@ -839,6 +848,11 @@ void launch_update_ref_angle(tsl_ctx *ctx, const ClothDev &c)
 void launch_absmax(tsl_ctx *ctx, const double *a, int n, double *out_dev)
 {
     k_absmax<<<ctx->red_blocks, 256, 0, ctx->stream>>>(n, a, ctx->red_partial, ctx->red_ticket, out_dev);
+    ctx->launches++;
+}
+void launch_dot(tsl_ctx *ctx, const double *a, const double *b, int n, double *out_dev)
+{
+    k_dot<<<ctx->red_blocks, 256, 0, ctx->stream>>>(n, a, b, ctx->red_partial, ctx->red_ticket, out_dev);
     ctx->launches++;
 }
 void launch_refangle_a2ax(tsl_ctx *ctx, const ClothDev &c, const double *pos, const double *ag_step, double *ag_prev, double *pg_step)

@@ -14,6 +14,7 @@ from thinshelllab_b200 import _lib
 from thinshelllab_b200.synthetic import sheet_scene
 
 N = int(sys.argv[1]); steps = int(sys.argv[2]); use_oracle = "--oracle" in sys.argv
+max_newton = int(sys.argv[sys.argv.index("--max-newton") + 1]) if "--max-newton" in sys.argv else 1000
 s = sheet_scene(N)
 e = s.engine
 o = None
@@ -27,7 +28,7 @@ if use_oracle:
     o.ref_angle[:] = e.cloth_ref_angle[0].cpu().numpy()
 for k in range(steps):
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    st = s.time_step()
+    st = s.time_step(max_newton=max_newton)
     torch.cuda.synchronize(); dt = time.perf_counter() - t0
     msg = f"step {k}: {1e3 * dt:.1f} ms newton={st.newton_iters} pcg={st.linear_iters} ls={st.linesearch_evals} nc={st.n_contacts} conv={st.converged} flags={st.flags} " \
           f"ms(contact/asm/solve/ls)={st.ms_contact:.1f}/{st.ms_assembly:.1f}/{st.ms_solve:.1f}/{st.ms_linesearch:.1f}"
