@@ -8,8 +8,8 @@ point (tsl_step_forward_host) + host-side loss seed / gradient read-back, copies
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--sheet-n 707] [--impl reference]
 
-N > 1 (torchrun): round 1 runs one independent sheet per rank (replicas, weak scaling) -- the strip-partitioned solver of
-SURVEY.md section 8e is not implemented yet; the JSON line says so in config.parallelism.
+N > 1 (torchrun): one independent sheet per rank (replicas, weak scaling, no data-path collective) -- the strip-partitioned
+solver of SURVEY.md section 8e is not implemented yet; the JSON line says so in config.parallelism.
 """
 import argparse
 import json
@@ -23,6 +23,11 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+
+
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed ncu --set full capture
+# (profiles/), keyed by sheet size; None where no capture exists
+TRAFFIC = {}
 
 
 def _peaks():
@@ -189,17 +194,30 @@ def run_ours(args, rank, world):
         t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
-    # ---- roofline of the dominant kernel (PCG SpMV), timed live with CUDA events on the launching stream inside libtsl
+    # ---- roofline of the dominant kernel class (fine-level block-sparse matrix pass: PCG SpMV and the V-cycle's fine
+    # smoother / residual kernels stream the same bytes), timed live with CUDA events on the launching stream inside libtsl
     from thinshelllab_b200 import _lib
     e.assemble(_lib.ASM_RESIDUAL | _lib.ASM_HESSIAN | _lib.ASM_NEWTON | _lib.ASM_SPD)
     sz = e.sizes()
     e.bench_kernel(1, 20)
     ms_spmv = e.bench_kernel(1, 200)
-    e.bench_kernel(0, 20)
-    ms_pcg = e.bench_kernel(0, 200)
+    e.bench_kernel(0, 10)
+    ms_pcg = e.bench_kernel(0, 100)
+    e.bench_kernel(5, 10)
+    ms_vcycle = e.bench_kernel(5, 100)
+    ms_setup = e.bench_kernel(6, 20)
+    ms_hess = e.bench_kernel(4, 20)
+    ms_resid = e.bench_kernel(3, 20)
+    ms_energy = e.bench_kernel(2, 20)
     V = sz["n_verts"]
     spmv_bytes = 40.0 * sz["nnzb"] + 28.0 * V                      # 36 B + 4 B per block, row ptr 4V, x 12V, y 12V
-    pcg_bytes = 40.0 * sz["nnzb"] + (4 + 24 + 108 + 36) * V       # one PCG iteration, ~608 B / vertex
+    # one multigrid-PCG iteration: 5 fine-level matrix passes (SpMV, 3 smoother steps, 1 residual) + 4 passes over every
+    # coarse level (900 B per coarse vertex, ~1/3 V in total) + ~25 fine vector passes
+    n_coarse, ng = 0, N + 1
+    while ng > 6:
+        ng = (ng - 1) // 2 + 1
+        n_coarse += ng * ng
+    pcg_bytes = 5 * 40.0 * sz["nnzb"] + 4 * 900.0 * n_coarse + 25 * 12.0 * V
     peak, peak_src = _peaks()
     if rank != 0:
         if world > 1:
@@ -212,23 +230,27 @@ def run_ours(args, rank, world):
     out = {
         "metric": "tri_steps_per_s (implicit fwd+bwd step)", "value": value, "unit": "tri-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 residual/energy/adjoint, f32 forward Hessian + PCG vectors", "data": "synthetic",
+        "dtype": "f64 (state, energy, residual, contact, adjoint matrix and solve) + f32 (forward Newton matrix, PCG vectors, multigrid)", "data": "synthetic",
         "config": {"workload": f"sheet {N}x{N} ({n_tris} tris, dx 2 mm) landing on a frozen table, Scene_bouncing physics, fwd + adjoint (dL/dKb) per step",
                    "sheet_n": N, "n_tris": n_tris, "n_verts": V, "nnzb": sz["nnzb"], "nnzb_padded": sz["nnzb_padded"],
                    "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (element partition not implemented in round 1)",
                    "l2": "matrix %.0f MB > 126 MB L2" % (sz["bytes_matrix_f32"] / 1e6) if sz["bytes_matrix_f32"] > 126e6 else
                          "working set %.0f MB fits the 126 MB L2: roofline fraction can exceed 1" % (sz["bytes_matrix_f32"] / 1e6),
+                   "solver": "Newton (exact / clamped matrix, line search) + multigrid-preconditioned PCG; adjoint: multigrid-preconditioned BiCGStab fp64",
                    "per_step_mean": {"newton_iters": st[:, 0].mean(), "pcg_iters": st[:, 1].mean(), "linesearch_evals": st[:, 2].mean(),
                                      "contacts": st[:, 3].mean(), "bicgstab_iters": st[:, 4].mean()},
+                   "per_step": [{"newton": int(r[0]), "pcg": int(r[1]), "bicgstab": int(r[4]), "contacts": int(r[3])} for r in st],
                    "flags": {"pcg_negative_curvature_steps": int((st[:, 5].astype(int) & 1).sum()), "krylov_cap_hit": int(((st[:, 5].astype(int) | st[:, 6].astype(int)) & 2).sum() // 2)}},
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "tri-steps/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 4 * nb, "d2h_bytes_per_step": 3 * nb + 8},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_spmv_dots<float> (PCG SpMV + fused dot)", "achieved": spmv_bytes / (ms_spmv * 1e-3) / 1e9, "peak": peak,
-                     "peak_source": peak_src, "unit": "GB/s", "frac": spmv_bytes / (ms_spmv * 1e-3) / 1e9 / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": "k_spmv_dots<float> (fine-level sliced-ELL matrix pass + fused dot; same traffic as k_cheb_step_sell / k_mg_residual_sell)",
+                     "achieved": spmv_bytes / (ms_spmv * 1e-3) / 1e9, "peak": peak,
+                     "peak_source": peak_src, "unit": "GB/s", "frac": spmv_bytes / (ms_spmv * 1e-3) / 1e9 / peak, "traffic": TRAFFIC.get(N),
                      "us_per_launch": 1e3 * ms_spmv, "algorithmic_bytes_per_launch": spmv_bytes,
                      "pcg_iteration": {"us": 1e3 * ms_pcg, "algorithmic_bytes": pcg_bytes, "achieved": pcg_bytes / (ms_pcg * 1e-3) / 1e9,
-                                       "frac": pcg_bytes / (ms_pcg * 1e-3) / 1e9 / peak}},
+                                       "frac": pcg_bytes / (ms_pcg * 1e-3) / 1e9 / peak, "note": "one captured CUDA graph: SpMV + update + V-cycle + direction"},
+                     "other_us": {"vcycle": 1e3 * ms_vcycle, "mg_setup": 1e3 * ms_setup, "hessian": 1e3 * ms_hess, "residual": 1e3 * ms_resid, "energy": 1e3 * ms_energy}},
     }
     if world == 1 and not args.no_cpu_baseline:
         tris, times, threads = oracle_fwd_bwd(args.cpu_sample_n, 1)

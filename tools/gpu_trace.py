@@ -38,6 +38,14 @@ for k in range(steps):
     print(msg, flush=True)
 e.contact_detect()
 e.assemble(_lib.ASM_RESIDUAL | _lib.ASM_HESSIAN | _lib.ASM_NEWTON | _lib.ASM_SPD)
+if "--solves" in sys.argv:
+    F = torch.from_numpy(e.residual()).to(e.device)
+    g = torch.Generator(device="cpu").manual_seed(0)
+    R = torch.randn(F.shape[0], generator=g, dtype=torch.float64).to(e.device) * (e.frozen == 0)
+    for name, rhs in (("F(converged)", F), ("random", R)):
+        for tol in (1e-2, 1e-4, 1e-6):
+            x, (it, fl, rr) = e.solve(rhs, rel_tol=tol, max_iters=300)
+            print(f"  solve {name} |rhs|={float(rhs.norm()):.3e} tol={tol:g}: its={it} flags={fl} rr={rr:.3e}")
 sz = e.sizes()
 print("sizes", sz)
 for name, what in (("pcg_iter", 0), ("spmv", 1), ("energy", 2), ("residual", 3), ("hessian", 4), ("vcycle", 5), ("mg_setup", 6)):
