@@ -76,7 +76,7 @@ int tsl_destroy(tsl_ctx *ctx)
     tsl::graphs_invalidate(ctx);
     tsl::mg_free(ctx);
     cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
-    cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q);
+    cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q); cudaFree(ctx->cg_r32);
     for (int i = 0; i < 8; i++) cudaFree(ctx->bi[i]);
     cudaFree(ctx->minv32); cudaFree(ctx->minv64); cudaFree(ctx->F); cudaFree(ctx->sol); cudaFree(ctx->x1);
     for (auto &c : ctx->cloths) {
@@ -456,15 +456,22 @@ int tsl_solve(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int ma
 
 // BaseScene.time_step (code/engine/BaseScene.py:1327-1370) + newton_step (:1159-1230)
 //
-// Newton iteration of the B200 path.  The residual is the reference's exact fp64 gradient, so the
-// fixed point is the reference's; matrix model, fp32 storage and Krylov tolerance only shape the path:
-//   * A_c = clamped (positive definite) Newton matrix -> multigrid hierarchy, and the operator of fallback solves;
-//   * A_e = exact membrane Hessian + Gauss-Newton bending -> operator of the regular solves (quadratic convergence
-//     near the minimiser).  If PCG meets negative curvature the step is redone with A_c, and the exact attempt is
-//     skipped for the next 1, 3, 7, 8, ... iterations (back-off);
+// Newton iteration of the B200 path.  The residual is the reference's exact fp64 gradient, so a
+// converged state is a fixed point of the reference's iteration; matrix model, fp32 storage and Krylov tolerance only
+// shape the path:
+//   * A_e = exact membrane Hessian + Gauss-Newton bending (fp32): the operator of every regular solve (quadratic
+//     convergence near the minimiser);
+//   * A_c = the same with the indefinite pieces clamped (positive definite): source of the multigrid hierarchy, which is
+//     rebuilt only every few iterations (a stale preconditioner costs Krylov iterations, never accuracy), and operator
+//     of the last-resort solve;
+//   * PCG meets negative curvature (buckling sheet): the step is x_k, the last iterate before it, if that lowers the
+//     energy, plus a move along the direction of negative curvature p_k whose length is found by doubling on the energy;
+//     the next iteration is usually positive definite again (measured: 4x fewer Newton iterations than falling back to
+//     A_c, same minimiser);
 //   * forcing term: Eisenstat-Walker choice 2 clipped to [1e-3, 0.1];
 //   * line search: the reference's halving on E < E0 (floor 1e-8, x left at the last trial, quirk Q9), plus doubling
-//     while the energy keeps falling when alpha = 1 was accepted (clamped steps are too short along buckling modes).
+//     while the energy keeps falling when alpha = 1 was accepted, plus acceptance of the plain Newton step when the
+//     predicted decrease is below the resolution of the fp64 energy sum.
 int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *stats)
 {
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
@@ -473,7 +480,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     cudaStream_t s = ctx->stream;
     tsl_step_stats st;
     memset(&st, 0, sizeof(st));
-    const bool trace = getenv("TSL_TRACE") != nullptr;
+    const bool trace = getenv("TSL_TRACE") != nullptr && atoi(getenv("TSL_TRACE")) != 0;
     double t0 = now_ms();
     // timestep_init: prev_pos <- pos
     CK(cudaMemcpyAsync(ctx->prev_pos, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
@@ -486,48 +493,93 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     int it = 0;
     const bool mgp = ctx->precond != 0 && ctx->mg.n_levels > 0;
     const int max_pcg = mgp ? 200 : 4000;
+    const int refresh_every = 8;
+    const double len_scale = ctx->cloths.empty() ? 1e-3 : ctx->cloths[0].P.dx;
     double eta = 0.1, fnorm_prev = -1;
-    int skip = 0, back = 0;
+    int age = refresh_every;                  // iterations since the hierarchy was built (forces a build at it == 1)
+    int last_pcg = 0, fresh_pcg = 0;
     while (it < max_newton) {
         it++;
         t0 = now_ms();
         launch_residual(ctx, ctx->pos);
-        const bool try_exact = (skip == 0);
-        launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                    // A_c -> val32c
-        if (try_exact) launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);    // A_e -> val32
-        TRY(mg_setup_replay(ctx));
+        launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);                    // A_e -> val32
+        // hierarchy: rebuilt every few iterations, or as soon as the Krylov count drifts away from what a fresh one gave
+        if (age >= refresh_every || last_pcg > 2 * fresh_pcg + 8) {
+            launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                 // A_c -> val32c
+            TRY(mg_setup_replay(ctx));
+            age = 0;
+        }
         ctx->last_f64 = false;
         if (it == 1) TRY(check_device_flags(ctx));
         double t1 = now_ms();
         st.ms_assembly += t1 - t0;
         tsl_solve_stats ss;
-        int used = 0, it_exact = 0;
-        if (try_exact) {
-            TRY(solve_pcg32(ctx, ctx->A.val32, ctx->F, ctx->sol, eta, max_pcg, &ss));
-            st.linear_iters += ss.iters;
-            it_exact = ss.iters;
-            if (ss.flags & 1) {
-                st.flags |= 1;
-                back = std::min(8, 2 * back + 1);
-                skip = back;
-                TRY(solve_pcg32(ctx, ctx->A.val32c, ctx->F, ctx->sol, eta, max_pcg, &ss));
-                st.linear_iters += ss.iters;
-                used = 1;
-            } else back = 0;
-        } else {
-            skip--;
-            TRY(solve_pcg32(ctx, ctx->A.val32c, ctx->F, ctx->sol, eta, max_pcg, &ss));
-            st.linear_iters += ss.iters;
-            used = 2;
-        }
-        st.flags |= (ss.flags & 2);
+        TRY(solve_pcg32(ctx, ctx->A.val32, ctx->F, ctx->sol, eta, max_pcg, &ss));
+        st.linear_iters += ss.iters;
+        last_pcg = ss.iters;
+        if (age == 0) fresh_pcg = ss.iters;
+        age++;
         double fnorm = ctx->ks_host->rr0;
         double eta_used = eta;
         if (fnorm_prev > 0 && fnorm > 0) eta = std::min(0.1, std::max(1e-3, 0.9 * (fnorm / fnorm_prev) * (fnorm / fnorm_prev)));
         fnorm_prev = fnorm;
+        CK(cudaMemcpyAsync(ctx->x1, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
+        bool fallback = false;
+        if (ss.flags & 1) {
+            // ---- negative curvature at PCG iteration ss.iters: x_k is in sol, p_k in cg_p
+            st.flags |= 1;
+            double t2 = now_ms();
+            st.ms_solve += t2 - t1;
+            const bool have_base = ss.iters > 1;
+            double Eb = E0, base = 0.0;
+            if (have_base) {
+                launch_axpy_pos(ctx, ctx->x1, ctx->sol, 1.0, ctx->pos);
+                TRY(energy_sync(ctx, &Eb));
+                st.linesearch_evals++;
+                if (Eb < E0) base = 1.0; else Eb = E0;
+            }
+            // orientation and scale of p_k: descent means F . p > 0
+            launch_absmax(ctx, ctx->cg_p, n3, ctx->red_out + 1);
+            launch_dot(ctx, ctx->F, ctx->cg_p, n3, ctx->red_out + 3);
+            CK(cudaMemcpyAsync(ctx->red_host + 1, ctx->red_out + 1, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            double pmax = ctx->red_host[1], sgn = ctx->red_host[3] >= 0 ? 1.0 : -1.0;
+            double tbest = 0.0, Ebest = Eb;
+            if (pmax > 0 && pmax == pmax) {
+                double tau = 1e-4 * len_scale / pmax;
+                for (int k = 0; k < 40; k++) {
+                    double E = 0;
+                    launch_axpy2_pos(ctx, ctx->x1, ctx->sol, base, ctx->cg_p, sgn * tau, ctx->pos);
+                    TRY(energy_sync(ctx, &E));
+                    st.linesearch_evals++;
+                    if (E < Ebest) { Ebest = E; tbest = tau; tau *= 2; } else break;
+                }
+            }
+            st.ms_linesearch += now_ms() - t2;
+            if (tbest > 0 || base > 0) {
+                launch_axpy2_pos(ctx, ctx->x1, ctx->sol, base, ctx->cg_p, sgn * tbest, ctx->pos);
+                if (trace)
+                    fprintf(stderr, "[tsl] newton %3d: negcurv@pcg=%d base=%g move=%.2e dE=%.3e |F|=%.3e E=%.12e nc=%d\n", it, ss.iters, base,
+                            tbest * pmax, E0 - Ebest, fnorm, Ebest, ctx->nc);
+                E0 = Ebest;
+                st.delta = 1.0;               // not a Newton step: no convergence test on it
+                continue;
+            }
+            // neither the partial solve nor the curvature direction lowers the energy: positive definite fallback
+            fallback = true;
+            t1 = now_ms();
+            if (age > 1) {                    // the stored A_c is stale as an OPERATOR: rebuild it (and the hierarchy) for this state
+                launch_hessian(ctx, ctx->x1, false, 1, 0, 1, true);
+                TRY(mg_setup_replay(ctx));
+                age = 1;
+            }
+            launch_axpy_pos(ctx, ctx->x1, ctx->sol, 0.0, ctx->pos);
+            TRY(solve_pcg32(ctx, ctx->A.val32c, ctx->F, ctx->sol, eta_used, max_pcg, &ss));
+            st.linear_iters += ss.iters;
+        }
+        st.flags |= (ss.flags & 2);
         launch_absmax(ctx, ctx->sol, n3, ctx->red_out + 1);
         launch_dot(ctx, ctx->F, ctx->sol, n3, ctx->red_out + 3);
-        CK(cudaMemcpyAsync(ctx->x1, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
         CK(cudaMemcpyAsync(ctx->red_host + 1, ctx->red_out + 1, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         double p_norm = ctx->red_host[1];
@@ -560,9 +612,8 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         st.ms_linesearch += now_ms() - t2;
         st.delta = p_norm / dt;
         if (trace)
-            fprintf(stderr, "[tsl] newton %3d: %s pcg=%d%s |F|=%.3e eta=%.1e delta=%.3e alpha=%.3g E=%.12e nc=%d\n", it,
-                    used == 0 ? "exact" : (used == 1 ? "negcurv->clamped" : "clamped(skip)"), ss.iters,
-                    used == 1 ? (std::string(" (exact try ") + std::to_string(it_exact) + ")").c_str() : "", fnorm, eta_used, st.delta, alpha, E, ctx->nc);
+            fprintf(stderr, "[tsl] newton %3d: %s pcg=%d age=%d |F|=%.3e eta=%.1e delta=%.3e alpha=%.3g E=%.12e nc=%d\n", it,
+                    fallback ? "clamped-fallback" : "exact", ss.iters, age, fnorm, eta_used, st.delta, alpha, E, ctx->nc);
         E0 = E;                               // the reference re-evaluates the same point at the top of the loop
         if (st.delta < tol) { st.converged = 1; break; }
     }

@@ -151,7 +151,8 @@ struct tsl_ctx {
     bool last_f64 = false;
     double *F = nullptr;                         // [3 n_verts] residual
     float *minv32 = nullptr; double *minv64 = nullptr;   // [n_verts][9] block-Jacobi inverse
-    float *cg_x = nullptr, *cg_r = nullptr, *cg_z = nullptr, *cg_p = nullptr, *cg_q = nullptr;  // [3 n_rows_pad]
+    double *cg_x = nullptr, *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr;   // PCG vectors [3 n_rows_pad] (fp64)
+    float *cg_r32 = nullptr, *cg_z = nullptr;     // fp32 copy of r (preconditioner input) and z = M r
     double *bi[8] = { nullptr };                 // BiCGStab vectors: r, rhat, p, v, y, s, z, t
     double *sol = nullptr;                       // [3 n_verts] Newton direction (f64)
     double *x1 = nullptr;                        // [n_verts][3] line-search base

@@ -12,6 +12,7 @@ void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos,
 // into_clamped: the fp32 result goes to A.val32c (multigrid hierarchy / fallback operator) instead of A.val32
 void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model, bool into_clamped = false);
 void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alpha, double *pos);
+void launch_axpy2_pos(tsl_ctx *ctx, const double *x1, const double *u, double a, const double *w, double b, double *pos);
 void launch_update_vel(tsl_ctx *ctx);
 void launch_update_ref_angle(tsl_ctx *ctx, const ClothDev &c);
 void launch_absmax(tsl_ctx *ctx, const double *a, int n, double *out_dev);

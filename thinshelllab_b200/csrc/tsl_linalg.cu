@@ -1,7 +1,7 @@
 // tsl_linalg.cu -- block-sparse linear algebra of the implicit step (sm_100a).
 //
 // Replaces SparseMatrix.solve (code/engine/sparse_solver.py:85-105; cuSOLVER sparse QR through CuPy) with
-//   * forward Newton:  PCG on the fp32 sliced-ELL matrix (fp32 vectors, fp64 reductions),
+//   * forward Newton:  PCG on the fp32 sliced-ELL matrix with fp64 vectors and accumulation,
 //   * adjoint:         right-preconditioned BiCGStab in fp64 on the un-projected, non-symmetric reference Hessian,
 // both preconditioned by the multigrid V-cycle of tsl_mg.cu (or block-Jacobi, TSL_OPT_PRECOND = 0).
 // A whole iteration runs without the host: step lengths are formed on the device from reduction results kept in a
@@ -79,6 +79,34 @@ __global__ void __launch_bounds__(256) k_spmv_dots(int n_rows, const int *__rest
     block_atomic_sum2(uy, yy, acc_uy, acc_yy);
 }
 
+// q = A p with the fp32 matrix and fp64 vectors / accumulation; acc_pq += p . q.  The forward PCG keeps x, r, p, q in fp64:
+// with fp32 vectors the residual recurrence stalls near eps32 * cond(A) ~ 1e-2 (measured), while rounding the MATRIX to
+// fp32 only perturbs the system consistently.
+__global__ void __launch_bounds__(256) k_spmv_mixed(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
+                                                    const float *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
+                                                    double *acc_xy)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double xy = 0;
+    if (row < n_rows) {
+        int S = row >> 5, lane = row & 31;
+        int b0 = slice_base[S], b1 = slice_base[S + 1];
+        double a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 2
+        for (int b = b0; b < b1; b += 32) {
+            int col = __ldg(colidx + b + lane);
+            const float *v = val + (long long)b * 9 + lane;
+            double x0 = x[3 * col], x1 = x[3 * col + 1], x2 = x[3 * col + 2];
+            a0 += __ldg(v) * x0 + __ldg(v + 32) * x1 + __ldg(v + 64) * x2;
+            a1 += __ldg(v + 96) * x0 + __ldg(v + 128) * x1 + __ldg(v + 160) * x2;
+            a2 += __ldg(v + 192) * x0 + __ldg(v + 224) * x1 + __ldg(v + 256) * x2;
+        }
+        y[3 * row] = a0; y[3 * row + 1] = a1; y[3 * row + 2] = a2;
+        xy = x[3 * row] * a0 + x[3 * row + 1] * a1 + x[3 * row + 2] * a2;
+    }
+    block_atomic_sum2(xy, 0.0, acc_xy, nullptr);
+}
+
 // block-Jacobi: inverse of the diagonal 3x3 blocks (fp64 adjoint matrix, TSL_OPT_PRECOND = 0 only)
 template <typename T>
 __global__ void k_block_jacobi(int n_rows, const int *__restrict__ diag_pb, const T *__restrict__ val, T *minv)
@@ -142,50 +170,49 @@ int mg_setup_replay(tsl_ctx *ctx)
 //   start     : x = 0, r = b, rr_new = r.r | z = M r, rz_new = r.z (fused in the preconditioner) | p = z | rotate
 //   iteration : q = A p, pq = p.q | alpha = rz/pq, x += alpha p, r -= alpha q, rr_new = r.r | z = M r, rz_new = r.z
 //               | p = z + (rz_new/rz) p | rotate: rz <- rz_new, rr <- rr_new, sums cleared, iter++
-// Negative curvature (pq <= 0) freezes the iterate: x keeps the last value (or becomes the preconditioned gradient
-// if nothing was accepted yet) and flags bit0 is raised by the rotate kernel -- truncated Newton.
-__global__ void __launch_bounds__(256) k_pcg_init(int n_rows, int n_alloc, const double *__restrict__ b, float *x, float *r, KrylovScalars *ks)
+// Negative curvature (pq <= 0) freezes the iterate: x keeps the last accepted value, p keeps the direction of negative
+// curvature and flags bit0 is raised by the rotate kernel; the Newton driver decides what to do with both.
+__global__ void __launch_bounds__(256) k_pcg_init(int n_rows, int n_alloc, const double *__restrict__ b, double *x, double *r, float *r32, KrylovScalars *ks)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     double rr = 0;
     if (row < n_alloc) {
-        float r0 = 0, r1 = 0, r2 = 0;
-        if (row < n_rows) { r0 = (float)b[3 * row]; r1 = (float)b[3 * row + 1]; r2 = (float)b[3 * row + 2]; }
-        x[3 * row] = x[3 * row + 1] = x[3 * row + 2] = 0.f;
+        double r0 = 0, r1 = 0, r2 = 0;
+        if (row < n_rows) { r0 = b[3 * row]; r1 = b[3 * row + 1]; r2 = b[3 * row + 2]; }
+        x[3 * row] = x[3 * row + 1] = x[3 * row + 2] = 0.0;
         r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
-        rr = (double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2;
+        r32[3 * row] = (float)r0; r32[3 * row + 1] = (float)r1; r32[3 * row + 2] = (float)r2;
+        rr = r0 * r0 + r1 * r1 + r2 * r2;
     }
     block_atomic_sum2(rr, 0.0, &ks->rr_new, nullptr);
 }
-__global__ void __launch_bounds__(256) k_pcg_update(int n_rows, const float *__restrict__ p, const float *__restrict__ q,
-                                                    float *x, float *r, KrylovScalars *ks)
+// alpha = rz / pq;  x += alpha p;  r -= alpha q (fp64), r32 = (float) r for the preconditioner;  rr_new += r.r
+__global__ void __launch_bounds__(256) k_pcg_update(int n_rows, const double *__restrict__ p, const double *__restrict__ q,
+                                                    double *x, double *r, float *r32, KrylovScalars *ks)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     double pq = ks->pq, rz = ks->rz;
-    const bool bad = !(pq > 0.0);
-    const bool frozen = ((ks->flags & 1) != 0) || bad;      // flags is only written by the rotate kernel: uniform branch
-    if (bad && !(ks->flags & 1) && ks->iter == 0 && row < n_rows) {   // nothing accepted yet: preconditioned gradient
-        x[3 * row] = p[3 * row]; x[3 * row + 1] = p[3 * row + 1]; x[3 * row + 2] = p[3 * row + 2];
-    }
-    if (frozen) return;
+    // negative curvature or breakdown freezes the iterate; flags is only written by the rotate kernel: uniform branch
+    if ((ks->flags & 1) || !(pq > 0.0)) return;
     double rr = 0;
     if (row < n_rows) {
-        float alpha = (float)(rz / pq);
-        float r0 = r[3 * row] - alpha * q[3 * row], r1 = r[3 * row + 1] - alpha * q[3 * row + 1], r2 = r[3 * row + 2] - alpha * q[3 * row + 2];
+        double alpha = rz / pq;
+        double r0 = r[3 * row] - alpha * q[3 * row], r1 = r[3 * row + 1] - alpha * q[3 * row + 1], r2 = r[3 * row + 2] - alpha * q[3 * row + 2];
         x[3 * row] += alpha * p[3 * row]; x[3 * row + 1] += alpha * p[3 * row + 1]; x[3 * row + 2] += alpha * p[3 * row + 2];
         r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
-        rr = (double)r0 * r0 + (double)r1 * r1 + (double)r2 * r2;
+        r32[3 * row] = (float)r0; r32[3 * row + 1] = (float)r1; r32[3 * row + 2] = (float)r2;
+        rr = r0 * r0 + r1 * r1 + r2 * r2;
     }
     block_atomic_sum2(rr, 0.0, &ks->rr_new, nullptr);
 }
 // p = z + beta p with beta = rz_new / rz   (first != 0: p = z)
-__global__ void __launch_bounds__(256) k_pcg_direction(int n, int first, const float *__restrict__ z, float *p, const KrylovScalars *ks)
+__global__ void __launch_bounds__(256) k_pcg_direction(int n, int first, const float *__restrict__ z, double *p, const KrylovScalars *ks)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (first) { if (i < n) p[i] = z[i]; return; }
+    if (first) { if (i < n) p[i] = (double)z[i]; return; }
     if ((ks->flags & 1) || !(ks->pq > 0.0)) return;
-    float beta = (float)(ks->rz_new / ks->rz);
-    if (i < n) p[i] = z[i] + beta * p[i];
+    double beta = ks->rz_new / ks->rz;
+    if (i < n) p[i] = (double)z[i] + beta * p[i];
 }
 __global__ void k_pcg_rotate(int first, KrylovScalars *ks)
 {
@@ -212,10 +239,11 @@ int linalg_alloc(tsl_ctx *ctx)
 {
     int nr = ctx->A.n_slices * 32;
     size_t nb = sizeof(float) * 3 * (size_t)nr;
-    CK(cudaMalloc(&ctx->cg_x, nb)); CK(cudaMalloc(&ctx->cg_r, nb)); CK(cudaMalloc(&ctx->cg_z, nb));
-    CK(cudaMalloc(&ctx->cg_p, nb)); CK(cudaMalloc(&ctx->cg_q, nb)); CK(cudaMalloc(&ctx->cg_r64tmp, nb));
-    CK(cudaMemset(ctx->cg_p, 0, nb)); CK(cudaMemset(ctx->cg_x, 0, nb)); CK(cudaMemset(ctx->cg_r, 0, nb));
-    CK(cudaMemset(ctx->cg_z, 0, nb)); CK(cudaMemset(ctx->cg_q, 0, nb)); CK(cudaMemset(ctx->cg_r64tmp, 0, nb));
+    size_t nbd = sizeof(double) * 3 * (size_t)nr;
+    CK(cudaMalloc(&ctx->cg_x, nbd)); CK(cudaMalloc(&ctx->cg_r, nbd)); CK(cudaMalloc(&ctx->cg_p, nbd)); CK(cudaMalloc(&ctx->cg_q, nbd));
+    CK(cudaMalloc(&ctx->cg_r32, nb)); CK(cudaMalloc(&ctx->cg_z, nb)); CK(cudaMalloc(&ctx->cg_r64tmp, nb));
+    CK(cudaMemset(ctx->cg_p, 0, nbd)); CK(cudaMemset(ctx->cg_x, 0, nbd)); CK(cudaMemset(ctx->cg_r, 0, nbd)); CK(cudaMemset(ctx->cg_q, 0, nbd));
+    CK(cudaMemset(ctx->cg_z, 0, nb)); CK(cudaMemset(ctx->cg_r32, 0, nb)); CK(cudaMemset(ctx->cg_r64tmp, 0, nb));
     CK(cudaMalloc(&ctx->minv32, sizeof(float) * 9 * (size_t)nr));
     CK(cudaMalloc(&ctx->ks, sizeof(KrylovScalars)));
     CK(cudaMallocHost(&ctx->ks_host, sizeof(KrylovScalars)));
@@ -236,10 +264,10 @@ static int pcg_iteration_body(tsl_ctx *ctx, const float *opval)
     const SellMatrix &A = ctx->A;
     KrylovScalars *ks = ctx->ks;
     cudaStream_t s = ctx->stream;
-    k_spmv_dots<float><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, ctx->cg_p, &ks->pq, nullptr);
-    k_pcg_update<<<GRID(n, 256), 256, 0, s>>>(n, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ks);
+    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, &ks->pq);
+    k_pcg_update<<<GRID(n, 256), 256, 0, s>>>(n, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ctx->cg_r32, ks);
     ctx->launches += 2;
-    TRYR(mg_apply(ctx, ctx->cg_r, ctx->cg_z, &ks->rz_new));
+    TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, &ks->rz_new));
     k_pcg_direction<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, 0, ctx->cg_z, ctx->cg_p, ks);
     k_pcg_rotate<<<1, 1, 0, s>>>(0, ks);
     ctx->launches += 2;
@@ -258,9 +286,9 @@ static int pcg_start(tsl_ctx *ctx, const double *rhs)
     int n = ctx->cfg.n_verts, nr = ctx->A.n_slices * 32;
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(ctx->ks, 0, sizeof(KrylovScalars), s));
-    k_pcg_init<<<GRID(nr, 256), 256, 0, s>>>(n, nr, rhs, ctx->cg_x, ctx->cg_r, ctx->ks);
+    k_pcg_init<<<GRID(nr, 256), 256, 0, s>>>(n, nr, rhs, ctx->cg_x, ctx->cg_r, ctx->cg_r32, ctx->ks);
     ctx->launches++;
-    TRYR(mg_apply(ctx, ctx->cg_r, ctx->cg_z, &ctx->ks->rz_new));
+    TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, &ctx->ks->rz_new));
     k_pcg_direction<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, 1, ctx->cg_z, ctx->cg_p, ctx->ks);
     k_pcg_rotate<<<1, 1, 0, s>>>(1, ctx->ks);
     ctx->launches += 2;
@@ -293,8 +321,7 @@ int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, 
         }
         if (it >= max_iters && rr > rel_tol * rel_tol * rr0) flags |= 2;
     }
-    k_f32_to_f64<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, ctx->cg_x, x);
-    ctx->launches++;
+    CK(cudaMemcpyAsync(x, ctx->cg_x, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, s));
     ctx->ks_host->rr0 = sqrt(rr0);      // |b|_2 for the caller's forcing term
     if (st) { st->iters = it; st->flags = flags; st->rel_residual = rr0 > 0 ? sqrt(rr / rr0) : 0.0; }
     CK(cudaGetLastError());
@@ -315,10 +342,9 @@ int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out)
     CK(cudaEventRecord(e0, s));
     for (int it = 0; it < iters; it++) {
         if (what == 1) {
-            k_spmv_dots<float><<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32, ctx->cg_p, ctx->cg_q, ctx->cg_p,
-                                                            &ctx->ks->pq, nullptr);
+            k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32, ctx->cg_p, ctx->cg_q, &ctx->ks->pq);
             ctx->launches++;
-        } else if (what == 5) TRYR(mg_apply(ctx, ctx->cg_r, ctx->cg_z, nullptr));
+        } else if (what == 5) TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, nullptr));
         else if (what == 6) TRYR(mg_setup_replay(ctx));
         else TRYR(pcg_iteration(ctx, ctx->A.val32));
     }

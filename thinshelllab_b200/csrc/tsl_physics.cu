@@ -592,6 +592,11 @@ __global__ void k_axpy_pos(int n, const double *__restrict__ x1, const double *_
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) pos[i] = x1[i] - p[i] * alpha;
 }
+__global__ void k_axpy2_pos(int n, const double *__restrict__ x1, const double *__restrict__ u, double a, const double *__restrict__ w, double b, double *pos)
+{   // pos = x1 - a u - b w  (negative-curvature move of the Newton driver)
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) pos[i] = x1[i] - a * u[i] - b * w[i];
+}
 __global__ void k_update_vel(int n, const double *__restrict__ pos, const double *__restrict__ prev_pos, double s, double *vel)
 {   // BaseScene.update_vel (BaseScene.py:868-872): s = damping / dt
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -832,6 +837,12 @@ void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alp
 {
     int n = 3 * ctx->cfg.n_verts;
     k_axpy_pos<<<GRID(n, 256), 256, 0, ctx->stream>>>(n, x1, p, alpha, pos);
+    ctx->launches++;
+}
+void launch_axpy2_pos(tsl_ctx *ctx, const double *x1, const double *u, double a, const double *w, double b, double *pos)
+{
+    int n = 3 * ctx->cfg.n_verts;
+    k_axpy2_pos<<<GRID(n, 256), 256, 0, ctx->stream>>>(n, x1, u, a, w, b, pos);
     ctx->launches++;
 }
 void launch_update_vel(tsl_ctx *ctx)
