@@ -165,8 +165,13 @@ int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out);
  * TSL_OPT_PRECOND: 0 = block-Jacobi, 1 = geometric multigrid V-cycle over the cloth grid (default);
  * TSL_OPT_MG_*: Chebyshev smoother degree (default 2), coarsest-grid sweep degree (8), eigenvalue interval ratio (8),
  * safety factor on the power-iteration estimate of lambda_max (1.2);
+ * TSL_OPT_NEWTON_MODE: what the forward Newton iteration does when PCG meets negative curvature in the exact matrix --
+ *   0 = redo the step with the clamped (projected) matrix and skip the exact attempt for a few iterations (default: the
+ *       path closest to the reference's projected Newton), 1 = move along the direction of negative curvature and keep
+ *       the multigrid hierarchy for several iterations (fewer iterations on buckling sheets; may settle in another
+ *       local minimum than the reference's path);
  * TSL_OPT_GRAPHS: 1 = replay the solver iterations as captured CUDA graphs (default), 0 = eager launches. */
-enum tsl_option { TSL_OPT_PRECOND = 0, TSL_OPT_MG_DEGREE = 1, TSL_OPT_MG_COARSE_DEGREE = 2, TSL_OPT_MG_RATIO = 3, TSL_OPT_MG_SAFETY = 4, TSL_OPT_GRAPHS = 5 };
+enum tsl_option { TSL_OPT_PRECOND = 0, TSL_OPT_MG_DEGREE = 1, TSL_OPT_MG_COARSE_DEGREE = 2, TSL_OPT_MG_RATIO = 3, TSL_OPT_MG_SAFETY = 4, TSL_OPT_GRAPHS = 5, TSL_OPT_NEWTON_MODE = 6 };
 int tsl_set_option(tsl_ctx *ctx, int key, double value);
 /* multigrid level read-back for tests: dims_host[3] = n0, n1, number of levels; lmax_host[1]; val_host [25][9][n0*n1] f32
  * (5x5 stencil of 3x3 blocks, slot-major; level 0 returns the stencil copy of the cloth block).  Any pointer may be NULL. */

@@ -251,6 +251,21 @@ def test_sheet_steps_vs_oracle_small():
     assert errs[0] < 3e-7, errs           # the first step (sheet settling on the table) has a unique minimiser
 
 
+def test_sheet_steps_negative_curvature_mode():
+    """TSL_OPT_NEWTON_MODE = 1 (moves along directions of negative curvature, lagged hierarchy): every step converges to a
+    fixed point of the reference iteration; positions agree where the minimiser is unique"""
+    s = sheet_scene(32)
+    s.engine.set_option(_lib.OPT_NEWTON_MODE, 1)
+    o = _oracle_for(s)
+    for step in range(3):
+        pos0, vel0 = o.pos.copy(), o.vel.copy()
+        st = s.time_step()
+        o.time_step()
+        assert st.converged
+        assert st.n_contacts == o.nc
+        _accept_fixed_point(s, o, pos0, vel0)
+
+
 def test_sheet_50k_first_iteration_and_properties():
     """config 1 size (158 x 158, 49 928 triangles): contact sets, energy and residual against the oracle at full size, then
     size-independent properties of the CUDA step: the accepted step lowers the energy, frozen vertices do not move,

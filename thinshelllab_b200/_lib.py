@@ -76,7 +76,7 @@ SIGNATURES = {
     "tsl_launch_count": (C.c_longlong, [_vp]),
 }
 
-OPT_PRECOND, OPT_MG_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_RATIO, OPT_MG_SAFETY, OPT_GRAPHS = 0, 1, 2, 3, 4, 5
+OPT_PRECOND, OPT_MG_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_RATIO, OPT_MG_SAFETY, OPT_GRAPHS, OPT_NEWTON_MODE = 0, 1, 2, 3, 4, 5, 6
 ASM_RESIDUAL, ASM_HESSIAN, ASM_SPD, ASM_SYM, ASM_F64, ASM_NEWTON = 1, 2, 4, 8, 16, 32
 
 _LIB = None

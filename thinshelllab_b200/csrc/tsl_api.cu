@@ -367,6 +367,7 @@ int tsl_finalize(tsl_ctx *ctx)
     TRY(linalg_alloc(ctx));
     TRY(mg_alloc(ctx));
     if (const char *e = getenv("TSL_PRECOND")) ctx->precond = atoi(e);
+    if (const char *e = getenv("TSL_NEWTON_MODE")) ctx->newton_mode = atoi(e);
     ctx->finalized = true;
     return TSL_OK;
 }
@@ -496,12 +497,44 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     const int refresh_every = 8;
     const double len_scale = ctx->cloths.empty() ? 1e-3 : ctx->cloths[0].P.dx;
     double eta = 0.1, fnorm_prev = -1;
+    int skip = 0, back = 0;                   // newton_mode 0: exact attempts skipped after a failure (1, 3, 7, 8, ...)
     int age = refresh_every;                  // iterations since the hierarchy was built (forces a build at it == 1)
     int last_pcg = 0, fresh_pcg = 0;
     while (it < max_newton) {
         it++;
         t0 = now_ms();
         launch_residual(ctx, ctx->pos);
+        tsl_solve_stats ss;
+        double t1;
+        bool fallback = false;
+        if (ctx->newton_mode == 0) {
+            // ---- projected-Newton fallback with back-off (the path closest to the reference's own iteration)
+            const bool try_exact = (skip == 0);
+            launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                     // A_c -> val32c
+            if (try_exact) launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);     // A_e -> val32
+            TRY(mg_setup_replay(ctx));
+            ctx->last_f64 = false;
+            if (it == 1) TRY(check_device_flags(ctx));
+            t1 = now_ms();
+            st.ms_assembly += t1 - t0;
+            if (try_exact) {
+                TRY(solve_pcg32(ctx, ctx->A.val32, ctx->F, ctx->sol, eta, max_pcg, &ss));
+                st.linear_iters += ss.iters;
+                if (ss.flags & 1) {
+                    st.flags |= 1;
+                    back = std::min(8, 2 * back + 1);
+                    skip = back;
+                    fallback = true;
+                    TRY(solve_pcg32(ctx, ctx->A.val32c, ctx->F, ctx->sol, eta, max_pcg, &ss));
+                    st.linear_iters += ss.iters;
+                } else back = 0;
+            } else {
+                skip--;
+                fallback = true;
+                TRY(solve_pcg32(ctx, ctx->A.val32c, ctx->F, ctx->sol, eta, max_pcg, &ss));
+                st.linear_iters += ss.iters;
+            }
+        } else {
         launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);                    // A_e -> val32
         // hierarchy: rebuilt every few iterations, or as soon as the Krylov count drifts away from what a fresh one gave
         if (age >= refresh_every || last_pcg > 2 * fresh_pcg + 8) {
@@ -511,21 +544,20 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         }
         ctx->last_f64 = false;
         if (it == 1) TRY(check_device_flags(ctx));
-        double t1 = now_ms();
+        t1 = now_ms();
         st.ms_assembly += t1 - t0;
-        tsl_solve_stats ss;
         TRY(solve_pcg32(ctx, ctx->A.val32, ctx->F, ctx->sol, eta, max_pcg, &ss));
         st.linear_iters += ss.iters;
         last_pcg = ss.iters;
         if (age == 0) fresh_pcg = ss.iters;
         age++;
+        }
         double fnorm = ctx->ks_host->rr0;
         double eta_used = eta;
         if (fnorm_prev > 0 && fnorm > 0) eta = std::min(0.1, std::max(1e-3, 0.9 * (fnorm / fnorm_prev) * (fnorm / fnorm_prev)));
         fnorm_prev = fnorm;
         CK(cudaMemcpyAsync(ctx->x1, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
-        bool fallback = false;
-        if (ss.flags & 1) {
+        if (ctx->newton_mode != 0 && (ss.flags & 1)) {
             // ---- negative curvature at PCG iteration ss.iters: x_k is in sol, p_k in cg_p
             st.flags |= 1;
             double t2 = now_ms();
@@ -791,6 +823,7 @@ int tsl_set_option(tsl_ctx *ctx, int key, double value)
     case TSL_OPT_MG_RATIO: REQUIRE(value > 1, "mg ratio must exceed 1"); ctx->mg.ratio = (float)value; break;
     case TSL_OPT_MG_SAFETY: REQUIRE(value >= 1, "mg safety must be >= 1"); ctx->mg.safety = (float)value; break;
     case TSL_OPT_GRAPHS: ctx->use_graphs = (int)value; break;
+    case TSL_OPT_NEWTON_MODE: ctx->newton_mode = (int)value; break;
     default: ctx->err = "tsl_set_option: unknown key"; return TSL_ERR_INVALID;
     }
     cudaStreamSynchronize(ctx->stream);

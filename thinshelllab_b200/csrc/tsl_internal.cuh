@@ -158,6 +158,7 @@ struct tsl_ctx {
     double *x1 = nullptr;                        // [n_verts][3] line-search base
     tsl::MgDev mg;
     int precond = 1;                             // 0 block-Jacobi, 1 multigrid V-cycle
+    int newton_mode = 0;                         // 0 projected-Newton fallback, 1 negative-curvature moves + lagged hierarchy
     float *cg_r64tmp = nullptr;                  // [3 n_rows_pad] fp32 staging of fp64 vectors for the V-cycle
     tsl::KrylovScalars *ks = nullptr;            // device
     tsl::KrylovScalars *ks_host = nullptr;       // pinned

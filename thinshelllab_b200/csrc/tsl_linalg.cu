@@ -161,8 +161,7 @@ void graphs_invalidate(tsl_ctx *ctx)
 }
 int mg_setup_replay(tsl_ctx *ctx)
 {
-    // the first setup runs the cold power iteration eagerly; later ones replay one graph
-    if (ctx->mg.setups == 0 || ctx->mg.n_levels == 0) return mg_setup(ctx);
+    if (ctx->mg.n_levels == 0) return mg_setup(ctx);
     return replay(ctx, ctx->g_mgsetup, ctx->A.val32c, [&]() { return mg_setup(ctx); });
 }
 

@@ -9,8 +9,8 @@
 //     radius 2 (triangle + hinge neighbours) gives coarse stencils of radius 2 on every level -> 5x5 blocks of 3x3,
 //     stored per vertex as 225 contiguous floats and applied by one warp per vertex,
 //   * smoother: Chebyshev polynomial in D^-1 A (D = 3x3 diagonal blocks) on [lmax/ratio, lmax]; lmax(D^-1 A) comes
-//     from a few warm-started power iterations per level with a safety factor (the iteration is sensitive to an
-//     under-estimate, not to an over-estimate),
+//     from 10 power iterations per level with a safety factor (the iteration is sensitive to an under-estimate,
+//     not to an over-estimate),
 //   * coarsest grid (<= 6 vertices in one direction): a longer Chebyshev sweep, no direct solve.
 // The V-cycle is symmetric (same polynomial before and after the coarse correction), so it is a valid PCG
 // preconditioner.  Everything is fp32; all coefficients live in device memory, so setup and application never
@@ -517,19 +517,17 @@ int mg_setup(tsl_ctx *ctx)
         k_dinv_stencil<<<GRID(C.nv, 256), 256, 0, s>>>(C.nv, C.nvp, C.val, C.dinv);
         ctx->launches += 2;
     }
-    // lambda_max(D^-1 A) per level: power iteration, warm-started from the previous setup
+    // lambda_max(D^-1 A) per level: 10 power iterations from a fixed pseudo-random vector.  (Warm-starting from the
+    // previous setup's vector was measured to UNDER-estimate after the contact set changes -- the old dominant mode
+    // has almost no overlap with the new one -- and an under-estimate is what the Chebyshev smoother cannot tolerate.)
     CK(cudaMemsetAsync(mg.pow_acc, 0, sizeof(double) * TSL_MG_MAX_LEVELS * 16, s));
-    int its = (mg.setups == 0) ? 10 : 4;
+    const int its = 10;
     for (int l = 0; l < mg.n_levels; l++) {
         MgLevel &L = mg.lev[l];
-        if (mg.setups == 0) {
-            k_fill_hash<<<GRID(3 * L.nrows, 256), 256, 0, s>>>(3 * L.nrows, L.pv[0], 0x9e3779b9u * (l + 1));
-            ctx->launches++;
-        }
-        for (int k = 0; k < its; k++) {
-            launch_step(ctx, l, nullptr, L.pv[k & 1], L.pv[(k & 1) ^ 1], nullptr, mg.powc + 4 * l + (k == 0 ? 0 : 2), mg.pow_acc + 16 * l + k, 2);
-        }
-        // its is even: the final vector is back in pv[0]
+        k_fill_hash<<<GRID(3 * L.nrows, 256), 256, 0, s>>>(3 * L.nrows, L.pv[0], 0x9e3779b9u * (l + 1));
+        ctx->launches++;
+        for (int k = 0; k < its; k++)
+            launch_step(ctx, l, nullptr, L.pv[k & 1], L.pv[(k & 1) ^ 1], nullptr, mg.powc + 4 * l + 2, mg.pow_acc + 16 * l + k, 2);
     }
     k_mg_coeffs<<<1, 32, 0, s>>>(mg.n_levels, mg.pow_acc, its - 1, mg.safety, mg.ratio, mg.coarse_ratio, mg.degree, mg.coarse_degree,
                                  mg.coef, mg.powc, mg.lmax);

@@ -17,6 +17,8 @@ N = int(sys.argv[1]); steps = int(sys.argv[2]); use_oracle = "--oracle" in sys.a
 max_newton = int(sys.argv[sys.argv.index("--max-newton") + 1]) if "--max-newton" in sys.argv else 1000
 s = sheet_scene(N)
 e = s.engine
+if "--mode" in sys.argv:
+    e.set_option(_lib.OPT_NEWTON_MODE, int(sys.argv[sys.argv.index("--mode") + 1]))
 o = None
 if use_oracle:
     from oracle import tsl_oracle as orc
