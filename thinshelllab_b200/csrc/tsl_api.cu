@@ -75,7 +75,7 @@ int tsl_destroy(tsl_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     tsl::graphs_invalidate(ctx);
     tsl::mg_free(ctx);
-    cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
+    cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->A.val32m); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
     cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q); cudaFree(ctx->cg_r32);
     for (int i = 0; i < 8; i++) cudaFree(ctx->bi[i]);
     cudaFree(ctx->minv32); cudaFree(ctx->minv64); cudaFree(ctx->F); cudaFree(ctx->sol); cudaFree(ctx->x1);
@@ -349,6 +349,8 @@ int tsl_finalize(tsl_ctx *ctx)
     CK(cudaMemset(A.val32, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     CK(cudaMalloc(&A.val32c, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     CK(cudaMemset(A.val32c, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
+    CK(cudaMalloc(&A.val32m, sizeof(float) * 9 * (size_t)A.nnzb_pad));
+    CK(cudaMemset(A.val32m, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     // ---- scratch
     CK(cudaMalloc(&ctx->F, sizeof(double) * 3 * nv));
     CK(cudaMalloc(&ctx->x1, sizeof(double) * 3 * nv));
@@ -512,7 +514,11 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
             const bool try_exact = (skip == 0);
             launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                     // A_c -> val32c
             if (try_exact) launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);     // A_e -> val32
-            TRY(mg_setup_replay(ctx));
+            // hierarchy: rebuilt every few iterations, or as soon as the Krylov count drifts away from what a fresh one gave
+            if (age >= refresh_every || last_pcg > 2 * fresh_pcg + 8) {
+                TRY(mg_setup_replay(ctx));
+                age = 0;
+            }
             ctx->last_f64 = false;
             if (it == 1) TRY(check_device_flags(ctx));
             t1 = now_ms();
@@ -534,6 +540,9 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
                 TRY(solve_pcg32(ctx, ctx->A.val32c, ctx->F, ctx->sol, eta, max_pcg, &ss));
                 st.linear_iters += ss.iters;
             }
+            last_pcg = ss.iters;
+            if (age == 0) fresh_pcg = ss.iters;
+            age++;
         } else {
         launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);                    // A_e -> val32
         // hierarchy: rebuilt every few iterations, or as soon as the Krylov count drifts away from what a fresh one gave

@@ -26,7 +26,8 @@ struct SellMatrix {
     int *colidx = nullptr;      // [nnzb_pad] device
     int *diag_pb = nullptr;     // [n_rows] device: padded block id of the diagonal block
     float *val32 = nullptr;     // [nnzb_pad*9]  operator of the forward solve (exact or clamped Newton matrix)
-    float *val32c = nullptr;    // [nnzb_pad*9]  clamped (positive definite) Newton matrix: multigrid hierarchy + fallback operator
+    float *val32c = nullptr;    // [nnzb_pad*9]  clamped (positive definite) Newton matrix: fallback operator, source of the hierarchy
+    float *val32m = nullptr;    // [nnzb_pad*9]  snapshot of val32c the current multigrid hierarchy was built from (level-0 smoother matrix)
     double *val64 = nullptr;    // [nnzb_pad*9], allocated on first fp64 assembly
     // host copies (pattern export, slot lookup at setup)
     std::vector<int> h_rowptr, h_colidx, h_slice_base, h_colidx_pad;

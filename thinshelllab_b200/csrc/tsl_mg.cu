@@ -480,31 +480,34 @@ static void launch_step(tsl_ctx *ctx, int l, const float *b, const float *x_in, 
 {
     MgLevel &L = ctx->mg.lev[l];
     if (l == 0)
-        k_cheb_step_sell<<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32c), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        k_cheb_step_sell<<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32m), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     else
         k_cheb_step_stencil<<<GRID(32LL * L.nv, 256), 256, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     ctx->launches++;
 }
 
-// Builds the hierarchy for the matrix currently in A.val32c.  No host synchronisation.
+// Builds the hierarchy for the matrix currently in A.val32c (snapshotted into A.val32m).  No host synchronisation.
 int mg_setup(tsl_ctx *ctx)
 {
     MgDev &mg = ctx->mg;
     cudaStream_t s = ctx->stream;
     const SellMatrix &A = ctx->A;
     int nrows0 = A.n_slices * 32;
+    // the hierarchy is built from (and its level-0 smoother keeps using) a snapshot, so that the caller may refresh
+    // A.val32c every Newton iteration while the preconditioner stays self-consistent until the next build
+    CK(cudaMemcpyAsync(A.val32m, A.val32c, sizeof(float) * 9 * (size_t)A.nnzb_pad, cudaMemcpyDeviceToDevice, s));
     if (mg.n_levels == 0) {          // no cloth: block-Jacobi only
-        k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32c, ctx->minv32);
+        k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32m, ctx->minv32);
         ctx->launches++;
         return TSL_OK;
     }
     const ClothDev &c = ctx->cloths[0];
     MgLevel &L0 = mg.lev[0];
-    k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32c, L0.dinv);
+    k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32m, L0.dinv);
     ctx->launches++;
     if (mg.n_levels > 1) {
         // the pattern is static: every slot this kernel writes is rewritten on each setup, the others stay zero
-        k_sell_to_stencil<<<GRID(L0.nv, 128), 128, 0, s>>>(c.offset, L0.nv, L0.n1, A.slice_base, A.colidx, A.val32c, A.diag_pb, L0.val, L0.nvp);
+        k_sell_to_stencil<<<GRID(L0.nv, 128), 128, 0, s>>>(c.offset, L0.nv, L0.n1, A.slice_base, A.colidx, A.val32m, A.diag_pb, L0.val, L0.nvp);
         ctx->launches++;
     }
     for (int l = 0; l + 1 < mg.n_levels; l++) {
@@ -562,7 +565,7 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
     MgLevel &C = mg.lev[l + 1];
     int off = (l == 0) ? mg.cloth_offset : 0;
     const int *mask = (l == 0) ? ctx->frozen : nullptr;
-    if (l == 0) k_mg_residual_sell<<<GRID(L.nrows, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32c), L.nrows, b, cur, L.r);
+    if (l == 0) k_mg_residual_sell<<<GRID(L.nrows, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32m), L.nrows, b, cur, L.r);
     else k_mg_residual_stencil<<<GRID(32LL * L.nv, 256), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     k_restrict<<<GRID(C.nv, 128), 128, 0, s>>>(L.n0, L.n1, off, L.r, mask, C.n0, C.n1, C.b);
     ctx->launches += 2;
