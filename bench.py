@@ -198,10 +198,8 @@ def run_ours(args, rank, world):
         fwd_bwd_host()
     barrier()
     ms_e2e = 1e3 * (time.perf_counter() - t0)
-    if world > 1:
-        t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, ms_e2e = float(t[0]), float(t[1])
+    from thinshelllab_b200 import dist as tdist
+    units, (ms, ms_e2e) = tdist.aggregate(n_tris * args.steps, [ms, ms_e2e], device=dev)   # SUM of units, MAX of times
     # ---- roofline of the dominant kernel class (fine-level block-sparse matrix pass: PCG SpMV and the V-cycle's fine
     # smoother / residual kernels stream the same bytes), timed live with CUDA events on the launching stream inside libtsl
     from thinshelllab_b200 import _lib
@@ -232,8 +230,8 @@ def run_ours(args, rank, world):
             dist.destroy_process_group()
         return
     st = np.array(stats, dtype=np.float64)
-    value = world * n_tris * args.steps / (ms * 1e-3)
-    e2e = world * n_tris * args.steps / (ms_e2e * 1e-3)
+    value = units / (ms * 1e-3)
+    e2e = units / (ms_e2e * 1e-3)
     nb = e.n_verts * 24
     out = {
         "metric": "tri_steps_per_s (implicit fwd+bwd step)", "value": value, "unit": "tri-steps/s", "n_gpus": world, "steps": args.steps,

@@ -55,7 +55,7 @@ def _stencil_to_csr(n0, n1, val):
     return A
 
 
-@pytest.mark.parametrize("N,pinned", [(40, False), (37, False), (24, True)])
+@pytest.mark.parametrize("N,pinned", [(40, False), (37, False), (24, True), (200, False)])   # 200: element-major (large-level) layout
 def test_galerkin_hierarchy_matches_scipy(N, pinned):
     kw = {}
     s = sheet_scene(N)
@@ -82,6 +82,8 @@ def test_galerkin_hierarchy_matches_scipy(N, pinned):
         G = _stencil_to_csr(n0, n1, val)
         assert abs(G - Al).max() <= 2e-5 * abs(Al).max(), lev
         assert abs(G - G.T).max() <= 2e-5 * abs(Al).max()
+        if n0 * n1 > 3000:
+            continue
         # power-iteration estimate (times the safety factor) must not be below the true lambda_max(D^-1 A)
         Gb = G.tobsr((3, 3))
         D = np.zeros((n0 * n1, 3, 3))

@@ -365,6 +365,14 @@ int tsl_finalize(tsl_ctx *ctx)
     CK(cudaMallocHost(&ctx->red_host, sizeof(double) * 8));
     CK(cudaMalloc(&ctx->error_flag, sizeof(int)));
     CK(cudaMemset(ctx->error_flag, 0, sizeof(int)));
+    // trailing rows whose three DOFs are frozen (the table of every bouncing-type scene) never enter the forward solve
+    {
+        std::vector<int> fz(3 * (size_t)nv);
+        CK(cudaMemcpy(fz.data(), ctx->frozen, sizeof(int) * fz.size(), cudaMemcpyDeviceToHost));
+        int last = -1;
+        for (int v = 0; v < nv; v++) if (!(fz[3 * v] && fz[3 * v + 1] && fz[3 * v + 2])) last = v;
+        ctx->n_solve = std::max(last + 1, 1);
+    }
     TRY(contact_alloc(ctx));
     TRY(linalg_alloc(ctx));
     TRY(mg_alloc(ctx));
@@ -496,7 +504,14 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     int it = 0;
     const bool mgp = ctx->precond != 0 && ctx->mg.n_levels > 0;
     const int max_pcg = mgp ? 200 : 4000;
+    // The hierarchy may be kept only while it is demonstrably as good as a fresh one: small Newton steps (the matrix barely
+    // moves: the long tail of a buckling step), Krylov count within 3 of what the fresh hierarchy needed, at most 8
+    // iterations old.  (Measured: a setup costs ~4.5 PCG iterations at 1M triangles; keeping a hierarchy through the
+    // first iterations of a step, while contacts and strains still change, costs 15.)
     const int refresh_every = 8;
+    auto keep_hierarchy = [&](int age_, int last_, int fresh_, double delta_) {
+        return age_ < refresh_every && it > 1 && delta_ < 2e-3 && last_ <= fresh_ + 3;
+    };
     const double len_scale = ctx->cloths.empty() ? 1e-3 : ctx->cloths[0].P.dx;
     double eta = 0.1, fnorm_prev = -1;
     int skip = 0, back = 0;                   // newton_mode 0: exact attempts skipped after a failure (1, 3, 7, 8, ...)
@@ -515,7 +530,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
             launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                     // A_c -> val32c
             if (try_exact) launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);     // A_e -> val32
             // hierarchy: rebuilt every few iterations, or as soon as the Krylov count drifts away from what a fresh one gave
-            if (age >= refresh_every || last_pcg > 2 * fresh_pcg + 8) {
+            if (!keep_hierarchy(age, last_pcg, fresh_pcg, st.delta)) {
                 TRY(mg_setup_replay(ctx));
                 age = 0;
             }
@@ -546,7 +561,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         } else {
         launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);                    // A_e -> val32
         // hierarchy: rebuilt every few iterations, or as soon as the Krylov count drifts away from what a fresh one gave
-        if (age >= refresh_every || last_pcg > 2 * fresh_pcg + 8) {
+        if (!keep_hierarchy(age, last_pcg, fresh_pcg, st.delta)) {
             launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                 // A_c -> val32c
             TRY(mg_setup_replay(ctx));
             age = 0;

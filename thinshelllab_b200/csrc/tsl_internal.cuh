@@ -64,12 +64,13 @@ struct ContactDev {
 // Geometric multigrid over the cloth's structured vertex grid (tsl_mg.cu): the preconditioner of the forward PCG and
 // of the adjoint BiCGStab.  Level 0 is the sliced-ELL matrix itself (all vertices); level l >= 1 is an n0 x n1 vertex
 // grid whose operator is the Galerkin product P^T A P (bilinear P) stored as a 5x5 stencil of 3x3 blocks, SoA:
-//   val[v*225 + slot*9 + comp],  slot = (dI+2)*5 + (dJ+2),  v = I*n1 + J
-// so that one warp per vertex streams its row with coalesced loads.
+//   element e = slot*9 + comp of vertex v,  slot = (dI+2)*5 + (dJ+2),  v = I*n1 + J,  at val[v*sv + e*se]
+// (row-major + one warp per vertex on small levels, element-major + one thread per vertex on large ones).
 #define TSL_MG_MAX_LEVELS 12
 #define TSL_MG_MAX_DEGREE 8
 struct MgLevel {
     int n0 = 0, n1 = 0, nv = 0, nvp = 0;   // grid, vertices, vertices padded to 32
+    long long sv = 225, se = 1;            // layout of val: element (v, e) at val[v*sv + e*se] (row-major small levels, element-major large)
     int nrows = 0;                         // rows of the level's vectors (level 0: all matrix rows; else nv)
     float *val = nullptr;                  // stencil operator [225][nvp]  (level 0: stencil copy of the cloth block, Galerkin input only)
     float *dinv = nullptr;                 // [nrows][9] inverse diagonal blocks
@@ -157,6 +158,8 @@ struct tsl_ctx {
     double *bi[8] = { nullptr };                 // BiCGStab vectors: r, rhat, p, v, y, s, z, t
     double *sol = nullptr;                       // [3 n_verts] Newton direction (f64)
     double *x1 = nullptr;                        // [n_verts][3] line-search base
+    int n_solve = 0;                             // rows [n_solve, n_verts) are fully frozen (decoupled, zero residual): the forward
+                                                 // solve and the multigrid cycle skip them (tsl_finalize)
     tsl::MgDev mg;
     int precond = 1;                             // 0 block-Jacobi, 1 multigrid V-cycle
     int newton_mode = 0;                         // 0 projected-Newton fallback, 1 negative-curvature moves + lagged hierarchy

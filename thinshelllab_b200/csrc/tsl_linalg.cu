@@ -234,6 +234,17 @@ __global__ void k_f64_to_f32(int n, int n_alloc, const double *__restrict__ a, f
     if (i < n_alloc) b[i] = i < n ? (float)a[i] : 0.f;
 }
 
+__global__ void k_apply_dinv_tail(int r0, int r1, const float *__restrict__ dinv, const double *__restrict__ in, double *out)
+{
+    int row = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= r1) return;
+    const float *m = dinv + 9 * (size_t)row;
+    double a = in[3 * row], b = in[3 * row + 1], c = in[3 * row + 2];
+    out[3 * row] = m[0] * a + m[1] * b + m[2] * c;
+    out[3 * row + 1] = m[3] * a + m[4] * b + m[5] * c;
+    out[3 * row + 2] = m[6] * a + m[7] * b + m[8] * c;
+}
+
 int linalg_alloc(tsl_ctx *ctx)
 {
     int nr = ctx->A.n_slices * 32;
@@ -259,7 +270,7 @@ void launch_block_jacobi64(tsl_ctx *ctx)
 
 static int pcg_iteration_body(tsl_ctx *ctx, const float *opval)
 {
-    int n = ctx->cfg.n_verts;
+    int n = ctx->n_solve;
     const SellMatrix &A = ctx->A;
     KrylovScalars *ks = ctx->ks;
     cudaStream_t s = ctx->stream;
@@ -282,7 +293,7 @@ static int pcg_iteration(tsl_ctx *ctx, const float *opval)
 
 static int pcg_start(tsl_ctx *ctx, const double *rhs)
 {
-    int n = ctx->cfg.n_verts, nr = ctx->A.n_slices * 32;
+    int n = ctx->n_solve, nr = ctx->A.n_slices * 32;
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(ctx->ks, 0, sizeof(KrylovScalars), s));
     k_pcg_init<<<GRID(nr, 256), 256, 0, s>>>(n, nr, rhs, ctx->cg_x, ctx->cg_r, ctx->cg_r32, ctx->ks);
@@ -321,6 +332,11 @@ int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, 
         if (it >= max_iters && rr > rel_tol * rel_tol * rr0) flags |= 2;
     }
     CK(cudaMemcpyAsync(x, ctx->cg_x, sizeof(double) * 3 * (size_t)n, cudaMemcpyDeviceToDevice, s));
+    if (ctx->n_solve < n) {      // decoupled frozen rows: x = D^-1 b exactly (zero for the masked Newton residual)
+        const float *dinv = (ctx->mg.n_levels == 0) ? ctx->minv32 : ctx->mg.lev[0].dinv;
+        k_apply_dinv_tail<<<GRID(n - ctx->n_solve, 256), 256, 0, s>>>(ctx->n_solve, n, dinv, rhs, x);
+        ctx->launches++;
+    }
     ctx->ks_host->rr0 = sqrt(rr0);      // |b|_2 for the caller's forcing term
     if (st) { st->iters = it; st->flags = flags; st->rel_residual = rr0 > 0 ? sqrt(rr / rr0) : 0.0; }
     CK(cudaGetLastError());
@@ -330,7 +346,7 @@ int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, 
 // what: 0 = full PCG iterations, 1 = SpMV only, 5 = V-cycle only, 6 = multigrid setup
 int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out)
 {
-    int n = ctx->cfg.n_verts;
+    int n = ctx->n_solve;
     cudaStream_t s = ctx->stream;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -447,6 +463,12 @@ int precond_apply_f64io(tsl_ctx *ctx, const double *in, double *out)
     TRYR(mg_apply(ctx, ctx->cg_r64tmp, ctx->cg_z, nullptr));
     k_f32_to_f64<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, ctx->cg_z, out);
     ctx->launches += 2;
+    if (ctx->n_solve < n && ctx->mg.n_levels > 0 && ctx->precond != 0) {
+        // fully frozen trailing rows are decoupled: their exact inverse is the diagonal block's (the cycle skips them)
+        int m = n - ctx->n_solve;
+        k_apply_dinv_tail<<<GRID(m, 256), 256, 0, s>>>(ctx->n_solve, n, ctx->mg.lev[0].dinv, in, out);
+        ctx->launches++;
+    }
     return TSL_OK;
 }
 static int precond64(tsl_ctx *ctx, const double *in, double *out)

@@ -50,14 +50,19 @@ struct SellOp {
 // the matching component of the neighbour's x and the three row sums are formed with a shuffle reduction.  (A
 // thread-per-vertex walk over 25 slots is a 35-45 us latency chain even on a 36-vertex grid: measured, profiles/.)
 // Slots that point outside the grid hold zeros (k_galerkin writes them), so neighbour indices are clamped, not branched.
+// Two layouts, chosen per level by size (MgLevel::sv / se: element (v, e) lives at val[v*sv + e*se]):
+//   small levels  (sv, se) = (225, 1): row-contiguous, one warp per vertex -- latency bound, wants few loads per thread;
+//   large levels  (sv, se) = (1, nvp): element-major, one THREAD per vertex with the 25 slots fully unrolled and
+//                 clamped neighbour indices -- 225 independent coalesced loads per thread, bandwidth bound.
 struct StencilOp {
-    const float *val;      // [nv][225]
+    const float *val;
     int n0, n1;
+    long long sv, se;
 };
 __device__ __forceinline__ void stencil_row_warp(const StencilOp &A, int v, int lane, const float *__restrict__ x, float &y0, float &y1, float &y2)
 {
     int I = v / A.n1, J = v - I * A.n1;
-    const float *row = A.val + (size_t)v * 225;
+    const float *row = A.val + (size_t)v * 225;      // warp kernels run on row-contiguous levels only
     float a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -116,6 +121,60 @@ __global__ void __launch_bounds__(256) k_cheb_first(int nrows, const float *__re
 }
 // d = a d + c D^-1 (b - A x_in) ; x_out = x_in + d     (b == nullptr: b = 0; x_out == nullptr: not stored)
 // acc_mode 1: acc += b . x_out      acc_mode 2: acc += d . d
+// thread-per-vertex product for element-major levels
+__device__ __forceinline__ void stencil_row_thread(const StencilOp &A, int v, const float *__restrict__ x, float &y0, float &y1, float &y2)
+{
+    int I = v / A.n1, J = v - I * A.n1;
+    const float *a = A.val + (size_t)v * A.sv;
+    const long long se = A.se;
+    float a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int slot = 0; slot < 25; slot++) {
+        const int dI = slot / 5 - 2, dJ = slot % 5 - 2;
+        int ii = min(max(I + dI, 0), A.n0 - 1), jj = min(max(J + dJ, 0), A.n1 - 1);     // out-of-grid slots hold zeros
+        int u = ii * A.n1 + jj;
+        float x0 = x[3 * u], x1 = x[3 * u + 1], x2 = x[3 * u + 2];
+        const float *q = a + (size_t)(slot * 9) * se;
+        a0 += __ldg(q) * x0 + __ldg(q + se) * x1 + __ldg(q + 2 * se) * x2;
+        a1 += __ldg(q + 3 * se) * x0 + __ldg(q + 4 * se) * x1 + __ldg(q + 5 * se) * x2;
+        a2 += __ldg(q + 6 * se) * x0 + __ldg(q + 7 * se) * x1 + __ldg(q + 8 * se) * x2;
+    }
+    y0 = a0; y1 = a1; y2 = a2;
+}
+__global__ void __launch_bounds__(128) k_cheb_step_stencil_t(StencilOp A, int nv, const float *__restrict__ dinv, const float *__restrict__ b,
+                                                             const float *__restrict__ x_in, float *d, float *x_out,
+                                                             const float *__restrict__ coef, double *acc, int acc_mode)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    double s = 0;
+    if (row < nv) {
+        float a = coef[0], c = coef[1];
+        float y0, y1, y2;
+        stencil_row_thread(A, row, x_in, y0, y1, y2);
+        float b0 = 0, b1 = 0, b2 = 0;
+        if (b) { b0 = b[3 * row]; b1 = b[3 * row + 1]; b2 = b[3 * row + 2]; }
+        float r0 = b0 - y0, r1 = b1 - y1, r2 = b2 - y2;
+        const float *m = dinv + 9 * (size_t)row;
+        float d0 = c * (m[0] * r0 + m[1] * r1 + m[2] * r2), d1 = c * (m[3] * r0 + m[4] * r1 + m[5] * r2), d2 = c * (m[6] * r0 + m[7] * r1 + m[8] * r2);
+        if (a != 0.f) { d0 += a * d[3 * row]; d1 += a * d[3 * row + 1]; d2 += a * d[3 * row + 2]; }
+        d[3 * row] = d0; d[3 * row + 1] = d1; d[3 * row + 2] = d2;
+        if (x_out) {
+            float o0 = x_in[3 * row] + d0, o1 = x_in[3 * row + 1] + d1, o2 = x_in[3 * row + 2] + d2;
+            x_out[3 * row] = o0; x_out[3 * row + 1] = o1; x_out[3 * row + 2] = o2;
+            if (acc_mode == 1) s = (double)b0 * o0 + (double)b1 * o1 + (double)b2 * o2;
+        }
+        if (acc_mode == 2) s = (double)d0 * d0 + (double)d1 * d1 + (double)d2 * d2;
+    }
+    if (acc) block_atomic_sum(s, acc);
+}
+__global__ void __launch_bounds__(128) k_mg_residual_stencil_t(StencilOp A, int nv, const float *__restrict__ b, const float *__restrict__ x, float *r)
+{
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nv) return;
+    float y0, y1, y2;
+    stencil_row_thread(A, row, x, y0, y1, y2);
+    r[3 * row] = b[3 * row] - y0; r[3 * row + 1] = b[3 * row + 1] - y1; r[3 * row + 2] = b[3 * row + 2] - y2;
+}
 __global__ void __launch_bounds__(256) k_cheb_step_sell(SellOp A, int nrows, const float *__restrict__ dinv, const float *__restrict__ b,
                                                         const float *__restrict__ x_in, float *d, float *x_out,
                                                         const float *__restrict__ coef, double *acc, int acc_mode)
@@ -260,7 +319,7 @@ __global__ void k_prolong_add(int n0f, int n1f, int off, float *x_f, const int *
 // ------------------------------------------------------------------------------------------------ setup kernels
 // stencil copy of the cloth block of the sliced-ELL matrix (input of the first Galerkin product)
 __global__ void k_sell_to_stencil(int off, int nvc, int n1, const int *__restrict__ slice_base, const int *__restrict__ colidx,
-                                  const float *__restrict__ val, const int *__restrict__ diag_pb, float *out, int nvp)
+                                  const float *__restrict__ val, const int *__restrict__ diag_pb, float *out, long long sv, long long se)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nvc) return;
@@ -280,21 +339,23 @@ __global__ void k_sell_to_stencil(int off, int nvc, int n1, const int *__restric
         if (di < -2 || di > 2 || dj < -2 || dj > 2) continue;
         int slot = (di + 2) * 5 + (dj + 2);
         const float *src = val + (long long)b * 9 + lane;
-        float *dst = out + (size_t)v * 225 + slot * 9;
+        float *dst = out + (size_t)v * sv + (size_t)(slot * 9) * se;
 #pragma unroll
-        for (int c = 0; c < 9; c++) dst[c] = src[c * 32];
+        for (int c = 0; c < 9; c++) dst[(size_t)c * se] = src[c * 32];
     }
 }
 // A_c = P^T A_f P, one thread per (coarse vertex, coarse stencil slot).  mask: frozen flags of the fine grid's
 // DOFs ([3 * nvf], level 0 only) -- frozen DOFs are left out of the coarse spaces.
 template <bool MASK>
-__global__ void __launch_bounds__(128) k_galerkin(const float *__restrict__ val_f, int n0f, int n1f, int nvpf, const int *__restrict__ mask,
-                                                  float *val_c, int n0c, int n1c, int nvpc)
+__global__ void __launch_bounds__(128) k_galerkin(const float *__restrict__ val_f, int n0f, int n1f, long long svf, long long sef, const int *__restrict__ mask,
+                                                  float *val_c, int n0c, int n1c, long long svc, long long sec)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
     int nvc = n0c * n1c;
     if (t >= nvc * 25) return;
-    int cv = t / 25, slot = t - cv * 25;
+    // element-major coarse level: consecutive threads = consecutive vertices of one slot; row-major: consecutive slots
+    int cv, slot;
+    if (svc == 1) { slot = t / nvc; cv = t - slot * nvc; } else { cv = t / 25; slot = t - cv * 25; }
     int I = cv / n1c, J = cv - I * n1c;
     int Ip = I + slot / 5 - 2, Jp = J + slot % 5 - 2;
     float acc[9];
@@ -320,26 +381,26 @@ __global__ void __launch_bounds__(128) k_galerkin(const float *__restrict__ val_
                         int dj = jp - j;
                         if ((unsigned)jp >= (unsigned)n1f || dj < -2 || dj > 2) continue;
                         float w = wip * pw1(bp, Jp, n1c);
-                        const float *src = val_f + (size_t)fv * 225 + ((di + 2) * 5 + (dj + 2)) * 9;
+                        const float *src = val_f + (size_t)fv * svf + (size_t)(((di + 2) * 5 + (dj + 2)) * 9) * sef;
                         if (MASK) {
                             int fc = ip * n1f + jp;
                             float mr[3], mc[3];
 #pragma unroll
                             for (int q = 0; q < 3; q++) { mr[q] = mask[3 * fv + q] ? 0.f : w; mc[q] = mask[3 * fc + q] ? 0.f : 1.f; }
 #pragma unroll
-                            for (int c = 0; c < 9; c++) acc[c] += mr[c / 3] * mc[c % 3] * __ldg(src + c);
+                            for (int c = 0; c < 9; c++) acc[c] += mr[c / 3] * mc[c % 3] * __ldg(src + (size_t)c * sef);
                         } else {
 #pragma unroll
-                            for (int c = 0; c < 9; c++) acc[c] += w * __ldg(src + c);
+                            for (int c = 0; c < 9; c++) acc[c] += w * __ldg(src + (size_t)c * sef);
                         }
                     }
                 }
             }
         }
     }
-    float *dst = val_c + (size_t)cv * 225 + slot * 9;
+    float *dst = val_c + (size_t)cv * svc + (size_t)(slot * 9) * sec;
 #pragma unroll
-    for (int c = 0; c < 9; c++) dst[c] = acc[c];
+    for (int c = 0; c < 9; c++) dst[(size_t)c * sec] = acc[c];
 }
 __device__ __forceinline__ void inv3_guarded(const float *a, float *inv)
 {
@@ -357,13 +418,13 @@ __device__ __forceinline__ void inv3_guarded(const float *a, float *inv)
     inv[3] = (float)(c01 * id); inv[4] = (float)(((double)a[0] * a[8] - (double)a[2] * a[6]) * id); inv[5] = (float)(((double)a[2] * a[3] - (double)a[0] * a[5]) * id);
     inv[6] = (float)(c02 * id); inv[7] = (float)(((double)a[1] * a[6] - (double)a[0] * a[7]) * id); inv[8] = (float)(((double)a[0] * a[4] - (double)a[1] * a[3]) * id);
 }
-__global__ void k_dinv_stencil(int nv, int nvp, const float *__restrict__ val, float *dinv)
+__global__ void k_dinv_stencil(int nv, long long sv, long long se, const float *__restrict__ val, float *dinv)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
     float a[9], inv[9];
 #pragma unroll
-    for (int c = 0; c < 9; c++) a[c] = val[(size_t)v * 225 + 12 * 9 + c];
+    for (int c = 0; c < 9; c++) a[c] = val[(size_t)v * sv + (size_t)(12 * 9 + c) * se];
     inv3_guarded(a, inv);
 #pragma unroll
     for (int c = 0; c < 9; c++) dinv[9 * (size_t)v + c] = inv[c];
@@ -434,11 +495,12 @@ int mg_alloc(tsl_ctx *ctx)
     for (int l = 0; l < TSL_MG_MAX_LEVELS; l++) {
         MgLevel &L = mg.lev[l];
         L.n0 = n0; L.n1 = n1; L.nv = n0 * n1; L.nvp = pad32(L.nv);
-        L.nrows = (l == 0) ? nrows0 : L.nv;
-        size_t vb = sizeof(float) * 3 * (size_t)std::max(L.nrows, 32);
+        if (L.nv >= 8192) { L.sv = 1; L.se = L.nvp; } else { L.sv = 225; L.se = 1; }
+        L.nrows = (l == 0) ? ctx->n_solve : L.nv;       // level 0 works on the rows of the forward solve
+        size_t vb = sizeof(float) * 3 * (size_t)std::max(l == 0 ? nrows0 : L.nrows, 32);
         CK(cudaMalloc(&L.val, sizeof(float) * 225 * (size_t)L.nvp));
         CK(cudaMemset(L.val, 0, sizeof(float) * 225 * (size_t)L.nvp));
-        CK(cudaMalloc(&L.dinv, sizeof(float) * 9 * (size_t)std::max(L.nrows, 32)));
+        CK(cudaMalloc(&L.dinv, sizeof(float) * 9 * (size_t)std::max(l == 0 ? nrows0 : L.nrows, 32)));
         for (int q = 0; q < 2; q++) {
             CK(cudaMalloc(&L.x[q], vb)); CK(cudaMemset(L.x[q], 0, vb));
             CK(cudaMalloc(&L.pv[q], vb)); CK(cudaMemset(L.pv[q], 0, vb));
@@ -473,7 +535,7 @@ void mg_free(tsl_ctx *ctx)
 }
 
 static SellOp sell_op(tsl_ctx *ctx, const float *val) { SellOp o; o.slice_base = ctx->A.slice_base; o.colidx = ctx->A.colidx; o.val = val; return o; }
-static StencilOp stencil_op(const MgLevel &L) { StencilOp o; o.val = L.val; o.n0 = L.n0; o.n1 = L.n1; return o; }
+static StencilOp stencil_op(const MgLevel &L) { StencilOp o; o.val = L.val; o.n0 = L.n0; o.n1 = L.n1; o.sv = L.sv; o.se = L.se; return o; }
 
 // d = a d + c D^-1 (b - A x_in), x_out = x_in + d on level l (level 0 smooths with the clamped matrix)
 static void launch_step(tsl_ctx *ctx, int l, const float *b, const float *x_in, float *d, float *x_out, const float *coef, double *acc, int mode)
@@ -481,6 +543,8 @@ static void launch_step(tsl_ctx *ctx, int l, const float *b, const float *x_in, 
     MgLevel &L = ctx->mg.lev[l];
     if (l == 0)
         k_cheb_step_sell<<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32m), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    else if (L.sv == 1)
+        k_cheb_step_stencil_t<<<GRID(L.nv, 128), 128, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     else
         k_cheb_step_stencil<<<GRID(32LL * L.nv, 256), 256, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     ctx->launches++;
@@ -507,17 +571,17 @@ int mg_setup(tsl_ctx *ctx)
     ctx->launches++;
     if (mg.n_levels > 1) {
         // the pattern is static: every slot this kernel writes is rewritten on each setup, the others stay zero
-        k_sell_to_stencil<<<GRID(L0.nv, 128), 128, 0, s>>>(c.offset, L0.nv, L0.n1, A.slice_base, A.colidx, A.val32m, A.diag_pb, L0.val, L0.nvp);
+        k_sell_to_stencil<<<GRID(L0.nv, 128), 128, 0, s>>>(c.offset, L0.nv, L0.n1, A.slice_base, A.colidx, A.val32m, A.diag_pb, L0.val, L0.sv, L0.se);
         ctx->launches++;
     }
     for (int l = 0; l + 1 < mg.n_levels; l++) {
         MgLevel &F = mg.lev[l], &C = mg.lev[l + 1];
         long long nt = 25LL * C.nv;
         if (l == 0)
-            k_galerkin<true><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.nvp, ctx->frozen + 3 * (size_t)c.offset, C.val, C.n0, C.n1, C.nvp);
+            k_galerkin<true><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.sv, F.se, ctx->frozen + 3 * (size_t)c.offset, C.val, C.n0, C.n1, C.sv, C.se);
         else
-            k_galerkin<false><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.nvp, nullptr, C.val, C.n0, C.n1, C.nvp);
-        k_dinv_stencil<<<GRID(C.nv, 256), 256, 0, s>>>(C.nv, C.nvp, C.val, C.dinv);
+            k_galerkin<false><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.sv, F.se, nullptr, C.val, C.n0, C.n1, C.sv, C.se);
+        k_dinv_stencil<<<GRID(C.nv, 256), 256, 0, s>>>(C.nv, C.sv, C.se, C.val, C.dinv);
         ctx->launches += 2;
     }
     // lambda_max(D^-1 A) per level: 10 power iterations from a fixed pseudo-random vector.  (Warm-starting from the
@@ -566,6 +630,7 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
     int off = (l == 0) ? mg.cloth_offset : 0;
     const int *mask = (l == 0) ? ctx->frozen : nullptr;
     if (l == 0) k_mg_residual_sell<<<GRID(L.nrows, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32m), L.nrows, b, cur, L.r);
+    else if (L.sv == 1) k_mg_residual_stencil_t<<<GRID(L.nv, 128), 128, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     else k_mg_residual_stencil<<<GRID(32LL * L.nv, 256), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     k_restrict<<<GRID(C.nv, 128), 128, 0, s>>>(L.n0, L.n1, off, L.r, mask, C.n0, C.n1, C.b);
     ctx->launches += 2;
@@ -589,7 +654,7 @@ int mg_apply(tsl_ctx *ctx, const float *b, float *z, double *acc_bz)
     if (mg.n_levels == 0 || ctx->precond == 0) {
         int nrows0 = ctx->A.n_slices * 32;
         const float *dinv = (mg.n_levels == 0) ? ctx->minv32 : mg.lev[0].dinv;
-        k_apply_dinv<<<GRID(nrows0, 256), 256, 0, ctx->stream>>>(nrows0, dinv, b, z, acc_bz);
+        k_apply_dinv<<<GRID(nrows0, 256), 256, 0, ctx->stream>>>(nrows0, dinv, b, z, acc_bz);   // block-Jacobi: every row
         ctx->launches++;
         return TSL_OK;
     }
@@ -611,7 +676,7 @@ int mg_get_level(tsl_ctx *ctx, int level, int *dims, float *lmax, float *val_hos
         std::vector<float> tmp((size_t)225 * L.nvp);
         CK(cudaMemcpy(tmp.data(), L.val, sizeof(float) * tmp.size(), cudaMemcpyDeviceToHost));
         for (int sc = 0; sc < 225; sc++)
-            for (int v = 0; v < L.nv; v++) val_host[(size_t)sc * L.nv + v] = tmp[(size_t)v * 225 + sc];
+            for (int v = 0; v < L.nv; v++) val_host[(size_t)sc * L.nv + v] = tmp[(size_t)v * L.sv + (size_t)sc * L.se];
     }
     return TSL_OK;
 }
