@@ -27,7 +27,7 @@ sys.path.insert(0, ROOT)
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed ncu --set full capture
 # (profiles/), keyed by sheet size; None where no capture exists
-TRAFFIC = {}
+TRAFFIC = {707: 283.47e6}     # profiles/r1_ncu_full_k_spmv_mixed.csv: 273.57 MB read + 9.90 MB written
 
 
 def _peaks():
@@ -216,14 +216,15 @@ def run_ours(args, rank, world):
     ms_resid = e.bench_kernel(3, 20)
     ms_energy = e.bench_kernel(2, 20)
     V = sz["n_verts"]
-    spmv_bytes = 40.0 * sz["nnzb"] + 28.0 * V                      # 36 B + 4 B per block, row ptr 4V, x 12V, y 12V
+    Vs, Bs = sz["n_solve"], sz["nnzb_solve"]                         # rows / blocks the forward solve touches (the frozen table is skipped)
+    spmv_bytes = 40.0 * Bs + (4 + 24 + 24) * Vs                    # 36 B + 4 B per block, row ptr 4V, fp64 x 24V, fp64 y 24V
     # one multigrid-PCG iteration: 5 fine-level matrix passes (SpMV, 3 smoother steps, 1 residual) + 4 passes over every
     # coarse level (900 B per coarse vertex, ~1/3 V in total) + ~25 fine vector passes
     n_coarse, ng = 0, N + 1
     while ng > 6:
         ng = (ng - 1) // 2 + 1
         n_coarse += ng * ng
-    pcg_bytes = 5 * 40.0 * sz["nnzb"] + 4 * 900.0 * n_coarse + 25 * 12.0 * V
+    pcg_bytes = 5 * 40.0 * Bs + 4 * 900.0 * n_coarse + 25 * 12.0 * Vs
     peak, peak_src = _peaks()
     if rank != 0:
         if world > 1:
@@ -238,7 +239,7 @@ def run_ours(args, rank, world):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 (state, energy, residual, contact, adjoint matrix and solve) + f32 (forward Newton matrix, PCG vectors, multigrid)", "data": "synthetic",
         "config": {"workload": f"sheet {N}x{N} ({n_tris} tris, dx 2 mm) landing on a frozen table, Scene_bouncing physics, fwd + adjoint (dL/dKb) per step",
-                   "sheet_n": N, "n_tris": n_tris, "n_verts": V, "nnzb": sz["nnzb"], "nnzb_padded": sz["nnzb_padded"],
+                   "sheet_n": N, "n_tris": n_tris, "n_verts": V, "nnzb": sz["nnzb"], "nnzb_padded": sz["nnzb_padded"], "n_solve": Vs, "nnzb_solve": Bs,
                    "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (element partition not implemented in round 1)",
                    "l2": "matrix %.0f MB > 126 MB L2" % (sz["bytes_matrix_f32"] / 1e6) if sz["bytes_matrix_f32"] > 126e6 else
                          "working set %.0f MB fits the 126 MB L2: roofline fraction can exceed 1" % (sz["bytes_matrix_f32"] / 1e6),
@@ -250,7 +251,7 @@ def run_ours(args, rank, world):
         "clocks": clocks,
         "e2e": {"value": e2e, "unit": "tri-steps/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 4 * nb, "d2h_bytes_per_step": 3 * nb + 8},
         "gpu_launches": int(launches),
-        "roofline": {"bound": "hbm", "kernel": "k_spmv_dots<float> (fine-level sliced-ELL matrix pass + fused dot; same traffic as k_cheb_step_sell / k_mg_residual_sell)",
+        "roofline": {"bound": "hbm", "kernel": "k_spmv_mixed (fine-level sliced-ELL matrix pass of PCG, fp32 matrix x fp64 vector + fused dot; k_cheb_step_sell / k_mg_residual_sell stream the same matrix)",
                      "achieved": spmv_bytes / (ms_spmv * 1e-3) / 1e9, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": spmv_bytes / (ms_spmv * 1e-3) / 1e9 / peak, "traffic": TRAFFIC.get(N),
                      "us_per_launch": 1e3 * ms_spmv, "algorithmic_bytes_per_launch": spmv_bytes,

@@ -154,6 +154,7 @@ int tsl_get_constraints(tsl_ctx *ctx, int *n_out, int *idx_host, double *w_host,
 typedef struct tsl_sizes {
     int n_verts, n_tris, n_hinges, nnzb, nnzb_padded, n_contacts;
     long long bytes_matrix_f32, bytes_matrix_f64;
+    int n_solve, nnzb_solve;    /* rows / blocks of the forward solve (trailing fully frozen bodies are skipped) */
 } tsl_sizes;
 int tsl_get_sizes(tsl_ctx *ctx, tsl_sizes *out);
 /* benchmark hooks: run `iters` PCG iterations (no convergence test) on the last fp32 Hessian, and time

@@ -34,7 +34,7 @@ class SolveStatsC(C.Structure):
 
 class SizesC(C.Structure):
     _fields_ = [("n_verts", C.c_int), ("n_tris", C.c_int), ("n_hinges", C.c_int), ("nnzb", C.c_int), ("nnzb_padded", C.c_int),
-                ("n_contacts", C.c_int), ("bytes_matrix_f32", C.c_longlong), ("bytes_matrix_f64", C.c_longlong)]
+                ("n_contacts", C.c_int), ("bytes_matrix_f32", C.c_longlong), ("bytes_matrix_f64", C.c_longlong), ("n_solve", C.c_int), ("nnzb_solve", C.c_int)]
 
 
 _vp, _i, _d = C.c_void_p, C.c_int, C.c_double

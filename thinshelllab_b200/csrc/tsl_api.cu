@@ -811,6 +811,7 @@ int tsl_get_sizes(tsl_ctx *ctx, tsl_sizes *out)
     for (auto &c : ctx->cloths) { out->n_tris += c.NF; out->n_hinges += c.NH; }
     out->nnzb = ctx->A.nnzb; out->nnzb_padded = (int)ctx->A.nnzb_pad; out->n_contacts = ctx->nc;
     out->bytes_matrix_f32 = (long long)ctx->A.nnzb_pad * 40; out->bytes_matrix_f64 = (long long)ctx->A.nnzb_pad * 76;
+    out->n_solve = ctx->n_solve; out->nnzb_solve = ctx->A.h_rowptr[ctx->n_solve];
     return TSL_OK;
 }
 
