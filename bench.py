@@ -97,9 +97,10 @@ def run_reference(args, rank):
     if rank != 0:
         return
     n = args.cpu_sample_n
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())       # torchrun pins it to 1: the CPU arm uses every host core
     for _ in range(args.warmup):
         pass                                    # the CPU arm has no warm-up state worth paying ~25 s per step for
-    tris, times, threads = oracle_fwd_bwd(n, max(1, args.steps))
+    tris, times, threads = oracle_fwd_bwd(n, max(1, args.steps), threads=os.cpu_count())
     T = float(np.sum(times))
     val = tris * len(times) / T
     sample = f"{n}x{n} sheet ({tris} tris) over the table, {len(times)} fwd+bwd step(s) from the bench's initial-state generator; SuperLU direct solves"
@@ -260,7 +261,7 @@ def run_ours(args, rank, world):
                      "other_us": {"vcycle": 1e3 * ms_vcycle, "mg_setup": 1e3 * ms_setup, "hessian": 1e3 * ms_hess, "residual": 1e3 * ms_resid, "energy": 1e3 * ms_energy}},
     }
     if world == 1 and not args.no_cpu_baseline:
-        tris, times, threads = oracle_fwd_bwd(args.cpu_sample_n, 1)
+        tris, times, threads = oracle_fwd_bwd(args.cpu_sample_n, 1, threads=os.cpu_count())
         out["cpu_baseline"] = {"value": tris / times[0], "unit": "tri-steps/s", "cores": threads, "kind": "port",
                                "sample": f"{args.cpu_sample_n}x{args.cpu_sample_n} sheet ({tris} tris), 1 fwd+bwd step, CPU oracle (fp64, SuperLU direct solves; not Taichi)"}
     print(json.dumps(out))

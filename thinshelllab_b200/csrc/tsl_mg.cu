@@ -261,6 +261,132 @@ __global__ void __launch_bounds__(256) k_apply_dinv(int nrows, const float *__re
     if (acc) block_atomic_sum(s, acc);
 }
 
+// ------------------------------------------------------------------------------------------------ fused coarse tail
+// The levels with at most 1024 vertices (<= 32 x 32) are ~7 kernels of 3-5 us each in a graph -- pure launch latency.
+// k_vcycle_tail runs the whole sub-cycle of those levels in ONE thread block (32 warps, one warp per vertex,
+// __syncthreads() between phases; the vectors live in L1/L2).  No __restrict__ / __ldg on vectors here: they are
+// rewritten between phases of the same kernel.
+#define TSL_MG_TAIL_MAX 4
+struct TailLevel { const float *val, *dinv; float *x0, *x1, *b, *r, *d; int n0, n1, nv; };
+struct TailArgs { TailLevel lev[TSL_MG_TAIL_MAX]; int n; int degree, coarse_degree; const float *coef; int first_level; };
+
+__device__ __forceinline__ void tail_row(const TailLevel &L, int v, int lane, const float *x, float &y0, float &y1, float &y2)
+{
+    int I = v / L.n1, J = v - I * L.n1;
+    const float *row = L.val + (size_t)v * 225;
+    float a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+        int e = k * 32 + lane;
+        if (e < 225) {
+            int slot = e / 9, c = e - slot * 9;
+            int q = slot / 5;
+            int ii = min(max(I + q - 2, 0), L.n0 - 1), jj = min(max(J + slot - q * 5 - 2, 0), L.n1 - 1);
+            int r = c / 3;
+            float t = __ldg(row + e) * x[3 * (ii * L.n1 + jj) + (c - r * 3)];
+            a0 += (r == 0) ? t : 0.f; a1 += (r == 1) ? t : 0.f; a2 += (r == 2) ? t : 0.f;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a0 += __shfl_xor_sync(0xffffffffu, a0, o); a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    y0 = a0; y1 = a1; y2 = a2;
+}
+// d = a d + c D^-1 (b - A x_in), x_out = x_in + d   (first: x_in = 0, no matrix pass)
+__device__ __forceinline__ void tail_step(const TailLevel &L, const float *b, const float *x_in, float *x_out, float a, float c, bool first)
+{
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    for (int v = warp; v < L.nv; v += nw) {
+        float y0 = 0, y1 = 0, y2 = 0;
+        if (!first) tail_row(L, v, lane, x_in, y0, y1, y2);
+        if (lane < 3) {
+            float r0 = b[3 * v] - y0, r1 = b[3 * v + 1] - y1, r2 = b[3 * v + 2] - y2;
+            const float *m = L.dinv + 9 * (size_t)v + 3 * lane;
+            float dq = c * (m[0] * r0 + m[1] * r1 + m[2] * r2);
+            if (a != 0.f) dq += a * L.d[3 * v + lane];
+            L.d[3 * v + lane] = dq;
+            x_out[3 * v + lane] = (first ? 0.f : x_in[3 * v + lane]) + dq;
+        }
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(1024) k_vcycle_tail(TailArgs A)
+{
+    const int last = A.n - 1;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    // ---- downward: pre-smooth, residual, restrict (the coarsest level is solved by the long sweep)
+    for (int l = 0; l <= last; l++) {
+        const TailLevel &L = A.lev[l];
+        const float *coef = A.coef + (size_t)(A.first_level + l) * TSL_MG_MAX_DEGREE * 2;
+        const int deg = (l == last) ? A.coarse_degree : A.degree;
+        for (int k = 0; k < deg; k++) {
+            float *out = (k & 1) ? L.x1 : L.x0;
+            const float *in = (k & 1) ? L.x0 : L.x1;
+            tail_step(L, L.b, in, out, coef[2 * k], coef[2 * k + 1], k == 0);
+        }
+        if (l == last) break;
+        const float *cur = ((deg - 1) & 1) ? L.x1 : L.x0;
+        for (int v = warp; v < L.nv; v += nw) {
+            float y0, y1, y2;
+            tail_row(L, v, lane, cur, y0, y1, y2);
+            if (lane < 3) L.r[3 * v + lane] = L.b[3 * v + lane] - (lane == 0 ? y0 : (lane == 1 ? y1 : y2));
+        }
+        __syncthreads();
+        const TailLevel &C = A.lev[l + 1];
+        for (int cv = threadIdx.x; cv < C.nv; cv += blockDim.x) {
+            int I = cv / C.n1, J = cv - I * C.n1;
+            float s0 = 0, s1 = 0, s2 = 0;
+            for (int a = -1; a <= 1; a++) {
+                int i = 2 * I + a;
+                if ((unsigned)i >= (unsigned)L.n0) continue;
+                float wi = a == 0 ? 1.f : (a < 0 ? 0.5f : (I + 1 < C.n0 ? 0.5f : 1.f));
+                for (int b = -1; b <= 1; b++) {
+                    int j = 2 * J + b;
+                    if ((unsigned)j >= (unsigned)L.n1) continue;
+                    float w = wi * (b == 0 ? 1.f : (b < 0 ? 0.5f : (J + 1 < C.n1 ? 0.5f : 1.f)));
+                    int fr = 3 * (i * L.n1 + j);
+                    s0 += w * L.r[fr]; s1 += w * L.r[fr + 1]; s2 += w * L.r[fr + 2];
+                }
+            }
+            C.b[3 * cv] = s0; C.b[3 * cv + 1] = s1; C.b[3 * cv + 2] = s2;
+        }
+        __syncthreads();
+    }
+    // ---- upward: prolong, post-smooth
+    for (int l = last - 1; l >= 0; l--) {
+        const TailLevel &L = A.lev[l], &C = A.lev[l + 1];
+        const float *coef = A.coef + (size_t)(A.first_level + l) * TSL_MG_MAX_DEGREE * 2;
+        const int cdeg = (l + 1 == last) ? A.coarse_degree : A.degree;
+        // result of the coarser level: after `cdeg` pre steps (+ `cdeg` post steps unless it is the coarsest)
+        int steps_c = (l + 1 == last) ? cdeg : 2 * cdeg;
+        const float *xc = ((steps_c - 1) & 1) ? C.x1 : C.x0;
+        float *cur = ((A.degree - 1) & 1) ? L.x1 : L.x0;
+        for (int fv = threadIdx.x; fv < L.nv; fv += blockDim.x) {
+            int i = fv / L.n1, j = fv - i * L.n1;
+            int I0 = i >> 1, J0 = j >> 1, nI = 1, nJ = 1;
+            float wI = 1.f, wJ = 1.f;
+            if ((i & 1) && I0 + 1 < C.n0) { nI = 2; wI = 0.5f; }
+            if ((j & 1) && J0 + 1 < C.n1) { nJ = 2; wJ = 0.5f; }
+            float s0 = 0, s1 = 0, s2 = 0;
+            for (int a = 0; a < nI; a++)
+                for (int b = 0; b < nJ; b++) {
+                    int cv = 3 * ((I0 + a) * C.n1 + (J0 + b));
+                    s0 += xc[cv]; s1 += xc[cv + 1]; s2 += xc[cv + 2];
+                }
+            float w = wI * wJ;
+            cur[3 * fv] += w * s0; cur[3 * fv + 1] += w * s1; cur[3 * fv + 2] += w * s2;
+        }
+        __syncthreads();
+        for (int k = 0; k < A.degree; k++) {
+            int kk = A.degree + k;                 // continues the ping-pong of the pre-smoothing steps
+            float *out = (kk & 1) ? L.x1 : L.x0;
+            const float *in = (kk & 1) ? L.x0 : L.x1;
+            tail_step(L, L.b, in, out, coef[2 * k], coef[2 * k + 1], false);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------ transfer operators
 // 1-D bilinear weight of fine index 2I + a (a in -1..1) towards coarse parent I of nc coarse points
 __device__ __forceinline__ float pw1(int a, int I, int nc) { return a == 0 ? 1.f : (a < 0 ? 0.5f : (I + 1 < nc ? 0.5f : 1.f)); }
@@ -511,6 +637,11 @@ int mg_alloc(tsl_ctx *ctx)
         if (std::min(n0, n1) <= 6) break;
         n0 = (n0 - 1) / 2 + 1; n1 = (n1 - 1) / 2 + 1;
     }
+    // levels from tail_level on (<= 1024 vertices each, row-major, at most TSL_MG_TAIL_MAX of them) run in one fused kernel
+    mg.tail_level = -1;
+    for (int l = 1; l < mg.n_levels; l++)
+        if (mg.lev[l].nv <= 1024 && mg.n_levels - l <= TSL_MG_TAIL_MAX) { mg.tail_level = l; break; }
+    if (const char *e = getenv("TSL_MG_TAIL")) if (atoi(e) == 0) mg.tail_level = -1;
     CK(cudaMalloc(&mg.coef, sizeof(float) * TSL_MG_MAX_LEVELS * TSL_MG_MAX_DEGREE * 2));
     CK(cudaMalloc(&mg.powc, sizeof(float) * TSL_MG_MAX_LEVELS * 4));
     CK(cudaMalloc(&mg.pow_acc, sizeof(double) * TSL_MG_MAX_LEVELS * 16));
@@ -610,6 +741,20 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
     MgDev &mg = ctx->mg;
     MgLevel &L = mg.lev[l];
     cudaStream_t s = ctx->stream;
+    if (l > 0 && l == mg.tail_level && b == L.b) {
+        // the remaining levels fit one thread block: one kernel for the whole sub-cycle
+        TailArgs T;
+        T.n = mg.n_levels - l; T.degree = mg.degree; T.coarse_degree = mg.coarse_degree; T.coef = mg.coef; T.first_level = l;
+        for (int q = 0; q < T.n; q++) {
+            MgLevel &Q = mg.lev[l + q];
+            T.lev[q].val = Q.val; T.lev[q].dinv = Q.dinv; T.lev[q].x0 = Q.x[0]; T.lev[q].x1 = Q.x[1];
+            T.lev[q].b = Q.b; T.lev[q].r = Q.r; T.lev[q].d = Q.d; T.lev[q].n0 = Q.n0; T.lev[q].n1 = Q.n1; T.lev[q].nv = Q.nv;
+        }
+        k_vcycle_tail<<<1, 1024, 0, s>>>(T);
+        ctx->launches++;
+        int steps = (T.n == 1) ? mg.coarse_degree : 2 * mg.degree;
+        return ((steps - 1) & 1) ? L.x[1] : L.x[0];
+    }
     const float *coef = mg.coef + (size_t)l * TSL_MG_MAX_DEGREE * 2;
     const bool last = (l == mg.n_levels - 1);
     const int deg = last ? mg.coarse_degree : mg.degree;
