@@ -641,7 +641,9 @@ int mg_alloc(tsl_ctx *ctx)
     mg.tail_level = -1;
     for (int l = 1; l < mg.n_levels; l++)
         if (mg.lev[l].nv <= 1024 && mg.n_levels - l <= TSL_MG_TAIL_MAX) { mg.tail_level = l; break; }
-    if (const char *e = getenv("TSL_MG_TAIL")) if (atoi(e) == 0) mg.tail_level = -1;
+    // Measured (profiles/README.md): one SM walking 529 + 144 + 36 vertices through 16 dependent phases is SLOWER than the
+    // ~20 tiny graph nodes it replaces (PCG iteration 784 vs 645 us at 1 M triangles), so the fused tail is opt-in only.
+    { const char *e = getenv("TSL_MG_TAIL"); if (!e || atoi(e) == 0) mg.tail_level = -1; }
     CK(cudaMalloc(&mg.coef, sizeof(float) * TSL_MG_MAX_LEVELS * TSL_MG_MAX_DEGREE * 2));
     CK(cudaMalloc(&mg.powc, sizeof(float) * TSL_MG_MAX_LEVELS * 4));
     CK(cudaMalloc(&mg.pow_acc, sizeof(double) * TSL_MG_MAX_LEVELS * 16));
