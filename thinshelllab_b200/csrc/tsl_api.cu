@@ -75,7 +75,7 @@ int tsl_destroy(tsl_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     tsl::graphs_invalidate(ctx);
     tsl::mg_free(ctx);
-    cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->A.val32m); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
+    cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->A.val32m); cudaFree(ctx->A.val32t); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
     cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q); cudaFree(ctx->cg_r32);
     for (int i = 0; i < 8; i++) cudaFree(ctx->bi[i]);
     cudaFree(ctx->minv32); cudaFree(ctx->minv64); cudaFree(ctx->F); cudaFree(ctx->sol); cudaFree(ctx->x1);
@@ -349,6 +349,8 @@ int tsl_finalize(tsl_ctx *ctx)
     CK(cudaMemset(A.val32, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     CK(cudaMalloc(&A.val32c, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     CK(cudaMemset(A.val32c, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
+    CK(cudaMalloc(&A.val32t, sizeof(float) * 9 * (size_t)A.nnzb_pad));
+    CK(cudaMemset(A.val32t, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     CK(cudaMalloc(&A.val32m, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     CK(cudaMemset(A.val32m, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     // ---- scratch
@@ -514,6 +516,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     };
     const double len_scale = ctx->cloths.empty() ? 1e-3 : ctx->cloths[0].P.dx;
     double eta = 0.1, fnorm_prev = -1;
+    double theta = 0.0, theta_used = 0.0;     // newton_mode 2: blend factor of the next / the last solve
     int skip = 0, back = 0;                   // newton_mode 0: exact attempts skipped after a failure (1, 3, 7, 8, ...)
     int age = refresh_every;                  // iterations since the hierarchy was built (forces a build at it == 1)
     int last_pcg = 0, fresh_pcg = 0;
@@ -555,6 +558,36 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
                 TRY(solve_pcg32(ctx, ctx->A.val32c, ctx->F, ctx->sol, eta, max_pcg, &ss));
                 st.linear_iters += ss.iters;
             }
+            last_pcg = ss.iters;
+            if (age == 0) fresh_pcg = ss.iters;
+            age++;
+        } else if (ctx->newton_mode == 2) {
+            // ---- blended operator A_theta = A_e + theta (A_c - A_e): the smallest theta in {0, 1/16, 1/8, ..., 1} for which PCG
+            // meets no negative curvature (the clamped matrix over-stiffens every compressed element, the blend only as
+            // much as definiteness needs)
+            launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                     // A_c -> val32c
+            launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);                    // A_e -> val32
+            if (!keep_hierarchy(age, last_pcg, fresh_pcg, st.delta)) {
+                TRY(mg_setup_replay(ctx));
+                age = 0;
+            }
+            ctx->last_f64 = false;
+            if (it == 1) TRY(check_device_flags(ctx));
+            t1 = now_ms();
+            st.ms_assembly += t1 - t0;
+            while (true) {
+                const float *op = ctx->A.val32;
+                if (theta >= 1.0) op = ctx->A.val32c;
+                else if (theta > 0.0) { launch_blend(ctx, ctx->A.val32, ctx->A.val32c, (float)theta, ctx->A.val32t); op = ctx->A.val32t; }
+                TRY(solve_pcg32(ctx, op, ctx->F, ctx->sol, eta, max_pcg, &ss));
+                st.linear_iters += ss.iters;
+                if (!(ss.flags & 1) || theta >= 1.0) break;
+                st.flags |= 1;
+                theta = std::min(1.0, std::max(2.0 * theta, 1.0 / 16));
+            }
+            fallback = theta > 0.0;
+            theta_used = theta;
+            theta = theta > 1.0 / 16 ? 0.5 * theta : 0.0;
             last_pcg = ss.iters;
             if (age == 0) fresh_pcg = ss.iters;
             age++;
@@ -669,7 +702,8 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         st.delta = p_norm / dt;
         if (trace)
             fprintf(stderr, "[tsl] newton %3d: %s pcg=%d age=%d |F|=%.3e eta=%.1e delta=%.3e alpha=%.3g E=%.12e nc=%d\n", it,
-                    fallback ? "clamped-fallback" : "exact", ss.iters, age, fnorm, eta_used, st.delta, alpha, E, ctx->nc);
+                    fallback ? (ctx->newton_mode == 2 ? (std::string("theta=") + std::to_string(theta_used)).c_str() : "clamped-fallback") : "exact", ss.iters, age,
+                    fnorm, eta_used, st.delta, alpha, E, ctx->nc);
         E0 = E;                               // the reference re-evaluates the same point at the top of the loop
         if (st.delta < tol) { st.converged = 1; break; }
     }

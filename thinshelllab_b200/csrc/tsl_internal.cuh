@@ -27,6 +27,7 @@ struct SellMatrix {
     int *diag_pb = nullptr;     // [n_rows] device: padded block id of the diagonal block
     float *val32 = nullptr;     // [nnzb_pad*9]  operator of the forward solve (exact or clamped Newton matrix)
     float *val32c = nullptr;    // [nnzb_pad*9]  clamped (positive definite) Newton matrix: fallback operator, source of the hierarchy
+    float *val32t = nullptr;    // [nnzb_pad*9]  blended operator val32 + theta (val32c - val32) (Newton mode 2)
     float *val32m = nullptr;    // [nnzb_pad*9]  snapshot of val32c the current multigrid hierarchy was built from (level-0 smoother matrix)
     double *val64 = nullptr;    // [nnzb_pad*9], allocated on first fp64 assembly
     // host copies (pattern export, slot lookup at setup)
@@ -120,7 +121,7 @@ struct tsl_ctx {
     cudaStream_t user_stream = 0;                // the caller's stream (tsl_set_stream); ordered against `stream` with events
     cudaEvent_t ev_in = nullptr, ev_out = nullptr;
     int use_graphs = 1;                          // TSL_GRAPHS=0 disables CUDA-graph replay of the solver iterations
-    tsl::GraphSlot g_pcg[2], g_bicg, g_mgsetup;  // captured iteration bodies (PCG per operator array)
+    tsl::GraphSlot g_pcg[3], g_bicg, g_mgsetup, g_pcg_start;  // captured iteration bodies (PCG per operator array)
     long long launches = 0;
     bool finalized = false;
 
@@ -163,7 +164,7 @@ struct tsl_ctx {
                                                  // solve and the multigrid cycle skip them (tsl_finalize)
     tsl::MgDev mg;
     int precond = 1;                             // 0 block-Jacobi, 1 multigrid V-cycle
-    int newton_mode = 0;                         // 0 projected-Newton fallback, 1 negative-curvature moves + lagged hierarchy
+    int newton_mode = 0;                         // 0 projected-Newton fallback, 1 negative-curvature moves, 2 blended operator
     float *cg_r64tmp = nullptr;                  // [3 n_rows_pad] fp32 staging of fp64 vectors for the V-cycle
     tsl::KrylovScalars *ks = nullptr;            // device
     tsl::KrylovScalars *ks_host = nullptr;       // pinned

@@ -30,6 +30,7 @@ int contact_detect(tsl_ctx *ctx, const double *pos, const double *prev_pos);
 // tsl_linalg.cu
 int linalg_alloc(tsl_ctx *ctx);
 void launch_block_jacobi64(tsl_ctx *ctx);
+void launch_blend(tsl_ctx *ctx, const float *a, const float *b, float t, float *out);   // out = a + t (b - a) over the matrix values
 // forward solve: PCG (fp32 vectors, fp64 reductions) on `opval` (A.val32 or A.val32c), preconditioned by the hierarchy of the
 // last mg_setup; st->flags bit0 = negative curvature met (x = last iterate before it, or the preconditioned gradient)
 int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st);

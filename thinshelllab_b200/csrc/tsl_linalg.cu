@@ -156,7 +156,7 @@ static int replay(tsl_ctx *ctx, GraphSlot &slot, const void *key, Body body)
 }
 void graphs_invalidate(tsl_ctx *ctx)
 {
-    GraphSlot *all[4] = { &ctx->g_pcg[0], &ctx->g_pcg[1], &ctx->g_bicg, &ctx->g_mgsetup };
+    GraphSlot *all[6] = { &ctx->g_pcg[0], &ctx->g_pcg[1], &ctx->g_pcg[2], &ctx->g_bicg, &ctx->g_mgsetup, &ctx->g_pcg_start };
     for (GraphSlot *g : all) if (g->exec) { cudaGraphExecDestroy(g->exec); g->exec = nullptr; g->key = nullptr; }
 }
 int mg_setup_replay(tsl_ctx *ctx)
@@ -245,6 +245,18 @@ __global__ void k_apply_dinv_tail(int r0, int r1, const float *__restrict__ dinv
     out[3 * row + 2] = m[6] * a + m[7] * b + m[8] * c;
 }
 
+__global__ void k_blend(long long n, const float *__restrict__ a, const float *__restrict__ b, float t, float *out)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] + t * (b[i] - a[i]);
+}
+void launch_blend(tsl_ctx *ctx, const float *a, const float *b, float t, float *out)
+{
+    long long n = 9LL * ctx->A.nnzb_pad;
+    k_blend<<<GRID(n, 256), 256, 0, ctx->stream>>>(n, a, b, t, out);
+    ctx->launches++;
+}
+
 int linalg_alloc(tsl_ctx *ctx)
 {
     int nr = ctx->A.n_slices * 32;
@@ -285,13 +297,20 @@ static int pcg_iteration_body(tsl_ctx *ctx, const float *opval)
 }
 static int pcg_iteration(tsl_ctx *ctx, const float *opval)
 {
-    GraphSlot &slot = ctx->g_pcg[opval == ctx->A.val32c ? 1 : 0];
+    GraphSlot &slot = ctx->g_pcg[opval == ctx->A.val32c ? 1 : (opval == ctx->A.val32t ? 2 : 0)];
     // the key folds in the preconditioner choice so that an option change re-captures
     const void *key = (const char *)opval + (ctx->precond ? 1 : 0);
     return replay(ctx, slot, key, [&]() { return pcg_iteration_body(ctx, opval); });
 }
 
+static int pcg_start_body(tsl_ctx *ctx, const double *rhs);
+// the start of a solve (initial residual + first preconditioner application) is ~60 launches: replayed as a graph too
 static int pcg_start(tsl_ctx *ctx, const double *rhs)
+{
+    const void *key = (const char *)rhs + (ctx->precond ? 1 : 0);
+    return replay(ctx, ctx->g_pcg_start, key, [&]() { return pcg_start_body(ctx, rhs); });
+}
+static int pcg_start_body(tsl_ctx *ctx, const double *rhs)
 {
     int n = ctx->n_solve, nr = ctx->A.n_slices * 32;
     cudaStream_t s = ctx->stream;
