@@ -128,6 +128,9 @@ def run_ours(args, rank, world):
     N = args.sheet_n
     s = sheet_scene(N, device=dev, seed=rank)
     e = s.engine
+    if args.newton_mode >= 0:
+        from thinshelllab_b200 import _lib as _l
+        e.set_option(_l.OPT_NEWTON_MODE, args.newton_mode)
     NVc = s.cloths[0].NV
     n_tris = 2 * N * N
     g = Grad(s, 2, 0)
@@ -244,7 +247,8 @@ def run_ours(args, rank, world):
                    "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (element partition not implemented in round 1)",
                    "l2": "matrix %.0f MB > 126 MB L2" % (sz["bytes_matrix_f32"] / 1e6) if sz["bytes_matrix_f32"] > 126e6 else
                          "working set %.0f MB fits the 126 MB L2: roofline fraction can exceed 1" % (sz["bytes_matrix_f32"] / 1e6),
-                   "solver": "Newton (exact / clamped matrix, line search) + multigrid-preconditioned PCG; adjoint: multigrid-preconditioned BiCGStab fp64",
+                   "solver": "Newton (exact / clamped / blended matrix, line search) + multigrid-preconditioned PCG; adjoint: multigrid-preconditioned BiCGStab fp64",
+                   "newton_mode": ("library default" if args.newton_mode < 0 else args.newton_mode),
                    "per_step_mean": {"newton_iters": st[:, 0].mean(), "pcg_iters": st[:, 1].mean(), "linesearch_evals": st[:, 2].mean(),
                                      "contacts": st[:, 3].mean(), "bicgstab_iters": st[:, 4].mean()},
                    "per_step": [{"newton": int(r[0]), "pcg": int(r[1]), "bicgstab": int(r[4]), "contacts": int(r[3])} for r in st],
@@ -279,6 +283,7 @@ def main():
     ap.add_argument("--cpu-sample-n", type=int, default=32)
     ap.add_argument("--adjoint-tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--newton-mode", type=int, default=-1, help="TSL_OPT_NEWTON_MODE of the forward solve (-1: library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

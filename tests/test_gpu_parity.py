@@ -150,10 +150,13 @@ def test_linear_solvers(golden):
     assert _rel(x.cpu().numpy(), ref) < 1e-7
 
 
-def test_forward_rollout_matches_reference(golden):
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_forward_rollout_matches_reference(golden, mode):
+    """every Newton mode reproduces the reference's own Scene_bouncing rollout (positions of all frames to 3e-7 m)"""
     g = golden
     s = _gpu_scene_from_golden(g)
     e = s.engine
+    e.set_option(_lib.OPT_NEWTON_MODE, mode)
     T = int(g["T"])
     for frame in range(1, T):
         st = s.time_step()
@@ -251,11 +254,12 @@ def test_sheet_steps_vs_oracle_small():
     assert errs[0] < 3e-7, errs           # the first step (sheet settling on the table) has a unique minimiser
 
 
-def test_sheet_steps_negative_curvature_mode():
-    """TSL_OPT_NEWTON_MODE = 1 (moves along directions of negative curvature, lagged hierarchy): every step converges to a
-    fixed point of the reference iteration; positions agree where the minimiser is unique"""
+@pytest.mark.parametrize("mode", [1, 2])
+def test_sheet_steps_other_newton_modes(mode):
+    """TSL_OPT_NEWTON_MODE = 1 (moves along directions of negative curvature) and 2 (blended operator): every step converges
+    to a fixed point of the reference iteration; positions agree where the minimiser is unique"""
     s = sheet_scene(32)
-    s.engine.set_option(_lib.OPT_NEWTON_MODE, 1)
+    s.engine.set_option(_lib.OPT_NEWTON_MODE, mode)
     o = _oracle_for(s)
     for step in range(3):
         pos0, vel0 = o.pos.copy(), o.vel.copy()
