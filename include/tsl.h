@@ -167,11 +167,12 @@ int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out);
  * TSL_OPT_MG_*: Chebyshev smoother degree (default 2), coarsest-grid sweep degree (8), eigenvalue interval ratio (8),
  * safety factor on the power-iteration estimate of lambda_max (1.2);
  * TSL_OPT_NEWTON_MODE: what the forward Newton iteration does when PCG meets negative curvature in the exact matrix --
- *   0 = redo the step with the clamped (projected) matrix and skip the exact attempt for a few iterations (default: the
- *       path closest to the reference's projected Newton), 1 = move along the direction of negative curvature and keep
+ *   0 = redo the step with the clamped (projected) matrix and skip the exact attempt for a few iterations (the path
+ *       closest to the reference's projected Newton), 1 = move along the direction of negative curvature and keep
  *       the multigrid hierarchy for several iterations (fewer iterations on buckling sheets; may settle in another
  *       local minimum than the reference's path), 2 = solve with the blend A_e + theta (A_c - A_e), theta the smallest of
- *       0, 1/16, ..., 1 that PCG accepts (fewest iterations measured; same caveat about the minimum);
+ *       0, 1/16, ..., 1 that PCG accepts (default: fewest iterations measured; reproduces the reference's Scene_bouncing
+ *       rollout like the others; on buckling steps it may settle in another local minimum than mode 0);
  * TSL_OPT_GRAPHS: 1 = replay the solver iterations as captured CUDA graphs (default), 0 = eager launches. */
 enum tsl_option { TSL_OPT_PRECOND = 0, TSL_OPT_MG_DEGREE = 1, TSL_OPT_MG_COARSE_DEGREE = 2, TSL_OPT_MG_RATIO = 3, TSL_OPT_MG_SAFETY = 4, TSL_OPT_GRAPHS = 5, TSL_OPT_NEWTON_MODE = 6 };
 int tsl_set_option(tsl_ctx *ctx, int key, double value);

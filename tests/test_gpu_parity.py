@@ -237,10 +237,12 @@ def _accept_fixed_point(s, o, pos0, vel0):
     return err
 
 
-def test_sheet_steps_vs_oracle_small():
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_sheet_steps_vs_oracle_small(mode):
     """32 x 32 synthetic sheet landing on the table: three full implicit steps, CUDA (own Newton matrix, multigrid PCG) against
-    the oracle (reference Hessian, direct solve): same contact sets, same fixed points"""
+    the oracle (reference Hessian, direct solve): same contact sets, same fixed points, for every Newton mode"""
     s = sheet_scene(32)
+    s.engine.set_option(_lib.OPT_NEWTON_MODE, mode)
     o = _oracle_for(s)
     errs = []
     for step in range(3):
@@ -251,23 +253,10 @@ def test_sheet_steps_vs_oracle_small():
         assert st.n_contacts == o.nc and o.nc > 50
         assert sorted(map(tuple, s.engine.constraints()["idx"])) == sorted(map(tuple, o.c_idx[:o.nc]))
         errs.append(_accept_fixed_point(s, o, pos0, vel0))
-    assert errs[0] < 3e-7, errs           # the first step (sheet settling on the table) has a unique minimiser
-
-
-@pytest.mark.parametrize("mode", [1, 2])
-def test_sheet_steps_other_newton_modes(mode):
-    """TSL_OPT_NEWTON_MODE = 1 (moves along directions of negative curvature) and 2 (blended operator): every step converges
-    to a fixed point of the reference iteration; positions agree where the minimiser is unique"""
-    s = sheet_scene(32)
-    s.engine.set_option(_lib.OPT_NEWTON_MODE, mode)
-    o = _oracle_for(s)
-    for step in range(3):
-        pos0, vel0 = o.pos.copy(), o.vel.copy()
-        st = s.time_step()
-        o.time_step()
-        assert st.converged
-        assert st.n_contacts == o.nc
-        _accept_fixed_point(s, o, pos0, vel0)
+    if mode != 1:
+        # the first step (sheet settling on the table) has a unique minimiser; mode 1 (negative-curvature moves) is known
+        # to leave the reference's basin even there and is covered by the fixed-point criterion only
+        assert errs[0] < 3e-7, errs
 
 
 def test_sheet_50k_first_iteration_and_properties():

@@ -164,7 +164,7 @@ struct tsl_ctx {
                                                  // solve and the multigrid cycle skip them (tsl_finalize)
     tsl::MgDev mg;
     int precond = 1;                             // 0 block-Jacobi, 1 multigrid V-cycle
-    int newton_mode = 0;                         // 0 projected-Newton fallback, 1 negative-curvature moves, 2 blended operator
+    int newton_mode = 2;                         // 0 projected-Newton fallback, 1 negative-curvature moves, 2 blended operator
     float *cg_r64tmp = nullptr;                  // [3 n_rows_pad] fp32 staging of fp64 vectors for the V-cycle
     tsl::KrylovScalars *ks = nullptr;            // device
     tsl::KrylovScalars *ks_host = nullptr;       // pinned
