@@ -75,7 +75,7 @@ int tsl_destroy(tsl_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     tsl::graphs_invalidate(ctx);
     tsl::mg_free(ctx);
-    cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->A.val32m); cudaFree(ctx->A.val32t); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb); cudaFree(ctx->A.srow2v); cudaFree(ctx->A.v2srow);
+    cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->A.val32m); cudaFree(ctx->A.val32t); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
     cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q); cudaFree(ctx->cg_r32);
     for (int i = 0; i < 8; i++) cudaFree(ctx->bi[i]);
     cudaFree(ctx->minv32); cudaFree(ctx->minv64); cudaFree(ctx->F); cudaFree(ctx->sol); cudaFree(ctx->x1);
@@ -291,23 +291,12 @@ int tsl_finalize(tsl_ctx *ctx)
     std::vector<int>().swap(cols);
     A.n_rows = nv;
     A.nnzb = (int)A.h_colidx.size();
-    A.n_slices = 2 * ((nv + 63) / 64);                       // whole windows of 64 sliced rows
-    // ---- row order: stable sort by length (descending) inside windows of 64 rows
-    const int nsr = A.n_slices * 32;
-    A.h_srow2v.assign(nsr, -1);
-    A.h_v2srow.assign(nv, -1);
-    for (int w0 = 0; w0 < nsr; w0 += 64) {
-        std::vector<int> rows;
-        for (int r = w0; r < std::min(nv, w0 + 64); r++) rows.push_back(r);
-        std::stable_sort(rows.begin(), rows.end(), [&](int x, int y) { return A.h_rowptr[x + 1] - A.h_rowptr[x] > A.h_rowptr[y + 1] - A.h_rowptr[y]; });
-        for (size_t q = 0; q < rows.size(); q++) { A.h_srow2v[w0 + q] = rows[q]; A.h_v2srow[rows[q]] = w0 + (int)q; }
-    }
-    auto len_of_srow = [&](int sr) { int r = A.h_srow2v[sr]; return r < 0 ? 0 : A.h_rowptr[r + 1] - A.h_rowptr[r]; };
+    A.n_slices = (nv + 31) / 32;
     // ---- sliced ELL
     A.h_slice_base.assign(A.n_slices + 1, 0);
     for (int S = 0; S < A.n_slices; S++) {
         int w = 0;
-        for (int sr = 32 * S; sr < 32 * S + 32; sr++) w = std::max(w, len_of_srow(sr));
+        for (int r = 32 * S; r < std::min(nv, 32 * S + 32); r++) w = std::max(w, A.h_rowptr[r + 1] - A.h_rowptr[r]);
         long long nb = (long long)A.h_slice_base[S] + 32LL * w;
         REQUIRE(nb < (1LL << 31) - 64, "matrix too large for 32-bit block ids");
         A.h_slice_base[S + 1] = (int)nb;
@@ -318,14 +307,13 @@ int tsl_finalize(tsl_ctx *ctx)
     for (int S = 0; S < A.n_slices; S++) {
         int w = (A.h_slice_base[S + 1] - A.h_slice_base[S]) / 32;
         for (int lane = 0; lane < 32; lane++) {
-            int r = A.h_srow2v[32 * S + lane];
+            int r = 32 * S + lane;
             for (int k = 0; k < w; k++) {
                 int pb = A.h_slice_base[S] + k * 32 + lane;
-                int col = (r >= 0) ? r : 0;                       // padding: valid column, zero value
-                bool real = r >= 0 && k < A.h_rowptr[r + 1] - A.h_rowptr[r];
-                if (real) col = A.h_colidx[A.h_rowptr[r] + k];
+                int col = (r < nv) ? r : 0;                       // padding: valid column, zero value
+                if (r < nv && k < A.h_rowptr[r + 1] - A.h_rowptr[r]) col = A.h_colidx[A.h_rowptr[r] + k];
                 A.h_colidx_pad[pb] = col;
-                if (real && col == r && diag[r] < 0) diag[r] = pb;
+                if (r < nv && col == r && diag[r] < 0 && k < A.h_rowptr[r + 1] - A.h_rowptr[r]) diag[r] = pb;
             }
         }
     }
@@ -333,8 +321,7 @@ int tsl_finalize(tsl_ctx *ctx)
         const int *b = A.h_colidx.data() + A.h_rowptr[r], *e = A.h_colidx.data() + A.h_rowptr[r + 1];
         const int *it = std::lower_bound(b, e, c);
         int k = (int)(it - b);
-        int sr = A.h_v2srow[r];
-        return A.h_slice_base[sr >> 5] + k * 32 + (sr & 31);
+        return A.h_slice_base[r >> 5] + k * 32 + (r & 31);
     };
     for (size_t ci = 0; ci < ctx->cloths.size(); ci++) {
         ClothDev &c = ctx->cloths[ci];
@@ -358,8 +345,6 @@ int tsl_finalize(tsl_ctx *ctx)
     TRY(upload(ctx, &A.slice_base, A.h_slice_base));
     TRY(upload(ctx, &A.colidx, A.h_colidx_pad));
     TRY(upload(ctx, &A.diag_pb, diag));
-    TRY(upload(ctx, &A.srow2v, A.h_srow2v));
-    TRY(upload(ctx, &A.v2srow, A.h_v2srow));
     CK(cudaMalloc(&A.val32, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     CK(cudaMemset(A.val32, 0, sizeof(float) * 9 * (size_t)A.nnzb_pad));
     CK(cudaMalloc(&A.val32c, sizeof(float) * 9 * (size_t)A.nnzb_pad));
@@ -819,9 +804,8 @@ int tsl_get_matrix(tsl_ctx *ctx, int *rowptr, int *colidx, double *val)
         }
         for (int r = 0; r < A.n_rows; r++)
             for (int k = 0; k < A.h_rowptr[r + 1] - A.h_rowptr[r]; k++) {
-                int sr = A.h_v2srow[r];
-                long long pb = (long long)A.h_slice_base[sr >> 5] + k * 32 + (sr & 31);
-                for (int cc = 0; cc < 9; cc++) val[9 * (size_t)(A.h_rowptr[r] + k) + cc] = pad[(size_t)sell_addr(pb, sr & 31, cc)];
+                long long pb = (long long)A.h_slice_base[r >> 5] + k * 32 + (r & 31);
+                for (int cc = 0; cc < 9; cc++) val[9 * (size_t)(A.h_rowptr[r] + k) + cc] = pad[(size_t)sell_addr(pb, r & 31, cc)];
             }
     }
     return TSL_OK;

@@ -13,11 +13,7 @@ namespace tsl {
 // ------------------------------------------------------------------------------------------------
 // Block-sparse matrix in a sliced-ELL layout tuned for one-thread-per-block-row SpMV:
 //   rows are grouped in slices of 32 (one warp); slice S has width W_S = max blocks per row in it;
-//   rows are PERMUTED inside windows of 64 (sorted by length, SELL-C-sigma with C = 32, sigma = 64): cloth rows have 9 or
-//   13 blocks by vertex parity, so a window splits into one slice of long and one of short rows and the padding drops
-//   from 17 % to ~2 %.  srow = position of a row in that order, srow2v / v2srow map to vertex ids; vectors stay in
-//   vertex order (a warp touches every second vertex of its window; the sibling slice picks up the rest from L1/L2).
-//   padded block id  pb = base[S] + k*32 + lane           (k-th block of sliced row srow = 32*S + lane; lane = pb & 31)
+//   padded block id  pb = base[S] + k*32 + lane           (k-th block of row 32*S + lane)
 //   value address    (pb - lane)*9 + c*32 + lane           (component c = 3*r + col of the 3x3 block)
 // so for a fixed (S, k, c) the 32 lanes of a warp read 32 consecutive values: every load of the SpMV
 // is a full 128-byte (fp32) / 256-byte (fp64) line.  Padding blocks carry value 0 and a valid column.
@@ -28,16 +24,14 @@ struct SellMatrix {
     long long nnzb_pad = 0; // padded blocks
     int *slice_base = nullptr;  // [n_slices+1] device, in blocks
     int *colidx = nullptr;      // [nnzb_pad] device
-    int *diag_pb = nullptr;     // [n_rows] device: padded block id of the diagonal block (by vertex)
-    int *srow2v = nullptr;      // [n_slices*32] device: vertex of a sliced row (-1: padding row)
-    int *v2srow = nullptr;      // [n_rows] device: sliced row of a vertex
+    int *diag_pb = nullptr;     // [n_rows] device: padded block id of the diagonal block
     float *val32 = nullptr;     // [nnzb_pad*9]  operator of the forward solve (exact or clamped Newton matrix)
     float *val32c = nullptr;    // [nnzb_pad*9]  clamped (positive definite) Newton matrix: fallback operator, source of the hierarchy
     float *val32t = nullptr;    // [nnzb_pad*9]  blended operator val32 + theta (val32c - val32) (Newton mode 2)
     float *val32m = nullptr;    // [nnzb_pad*9]  snapshot of val32c the current multigrid hierarchy was built from (level-0 smoother matrix)
     double *val64 = nullptr;    // [nnzb_pad*9], allocated on first fp64 assembly
     // host copies (pattern export, slot lookup at setup)
-    std::vector<int> h_rowptr, h_colidx, h_slice_base, h_colidx_pad, h_srow2v, h_v2srow;
+    std::vector<int> h_rowptr, h_colidx, h_slice_base, h_colidx_pad;
 };
 __host__ __device__ __forceinline__ long long sell_addr(long long pb, int lane, int c) { return (pb - lane) * 9 + (long long)c * 32 + lane; }
 

@@ -41,15 +41,7 @@ __device__ __forceinline__ void block_atomic_sum2(double a, double b, double *ac
     }
 }
 
-// sliced row -> vertex for the kernels that walk the matrix: thread = sliced row srow; returns -1 for padding rows and for
-// vertices outside [0, n_rows)
-__device__ __forceinline__ int vertex_of_srow(const int *__restrict__ srow2v, int srow, int n_rows)
-{
-    if (srow >= ((n_rows + 63) & ~63)) return -1;
-    int v = __ldg(srow2v + srow);
-    return (v >= 0 && v < n_rows) ? v : -1;
-}
-// y = A x for one block row per thread (row = SLICED row index); returns the 3 results in registers
+// y = A x for one block row per thread; returns the 3 results in registers
 template <typename T>
 __device__ __forceinline__ void spmv_row(const int *__restrict__ slice_base, const int *__restrict__ colidx, const T *__restrict__ val,
                                          const T *__restrict__ x, int row, T &y0, T &y1, T &y2)
@@ -71,17 +63,15 @@ __device__ __forceinline__ void spmv_row(const int *__restrict__ slice_base, con
 
 // y = A x;  acc_uy += u . y;  acc_yy += y . y   (u may alias x)
 template <typename T>
-__global__ void __launch_bounds__(256) k_spmv_dots(int n_rows, const int *__restrict__ srow2v, const int *__restrict__ slice_base,
-                                                   const int *__restrict__ colidx,
+__global__ void __launch_bounds__(256) k_spmv_dots(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
                                                    const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y,
                                                    const T *__restrict__ u, double *acc_uy, double *acc_yy)
 {
-    int srow = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = vertex_of_srow(srow2v, srow, n_rows);
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
     double uy = 0, yy = 0;
-    if (row >= 0) {
+    if (row < n_rows) {
         T y0, y1, y2;
-        spmv_row<T>(slice_base, colidx, val, x, srow, y0, y1, y2);
+        spmv_row<T>(slice_base, colidx, val, x, row, y0, y1, y2);
         y[3 * row] = y0; y[3 * row + 1] = y1; y[3 * row + 2] = y2;
         if (u) uy = (double)u[3 * row] * y0 + (double)u[3 * row + 1] * y1 + (double)u[3 * row + 2] * y2;
         yy = (double)y0 * y0 + (double)y1 * y1 + (double)y2 * y2;
@@ -92,16 +82,14 @@ __global__ void __launch_bounds__(256) k_spmv_dots(int n_rows, const int *__rest
 // q = A p with the fp32 matrix and fp64 vectors / accumulation; acc_pq += p . q.  The forward PCG keeps x, r, p, q in fp64:
 // with fp32 vectors the residual recurrence stalls near eps32 * cond(A) ~ 1e-2 (measured), while rounding the MATRIX to
 // fp32 only perturbs the system consistently.
-__global__ void __launch_bounds__(256) k_spmv_mixed(int n_rows, const int *__restrict__ srow2v, const int *__restrict__ slice_base,
-                                                    const int *__restrict__ colidx,
+__global__ void __launch_bounds__(256) k_spmv_mixed(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
                                                     const float *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
                                                     double *acc_xy)
 {
-    int srow = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = vertex_of_srow(srow2v, srow, n_rows);
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
     double xy = 0;
-    if (row >= 0) {
-        int S = srow >> 5, lane = srow & 31;
+    if (row < n_rows) {
+        int S = row >> 5, lane = row & 31;
         int b0 = slice_base[S], b1 = slice_base[S + 1];
         double a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll 2
@@ -125,7 +113,7 @@ __global__ void k_block_jacobi(int n_rows, const int *__restrict__ diag_pb, cons
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_rows) return;
-    long long base = sell_addr(diag_pb[r], diag_pb[r] & 31, 0);
+    long long base = sell_addr(diag_pb[r], r & 31, 0);
     double a[9];
 #pragma unroll
     for (int c = 0; c < 9; c++) a[c] = (double)val[base + c * 32];
@@ -298,7 +286,7 @@ static int pcg_iteration_body(tsl_ctx *ctx, const float *opval)
     const SellMatrix &A = ctx->A;
     KrylovScalars *ks = ctx->ks;
     cudaStream_t s = ctx->stream;
-    k_spmv_mixed<<<GRID((n + 63) & ~63, 256), 256, 0, s>>>(n, A.srow2v, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, &ks->pq);
+    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, &ks->pq);
     k_pcg_update<<<GRID(n, 256), 256, 0, s>>>(n, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ctx->cg_r32, ks);
     ctx->launches += 2;
     TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, &ks->rz_new));
@@ -388,7 +376,7 @@ int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out)
     CK(cudaEventRecord(e0, s));
     for (int it = 0; it < iters; it++) {
         if (what == 1) {
-            k_spmv_mixed<<<GRID((n + 63) & ~63, 256), 256, 0, s>>>(n, ctx->A.srow2v, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32, ctx->cg_p, ctx->cg_q, &ctx->ks->pq);
+            k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32, ctx->cg_p, ctx->cg_q, &ctx->ks->pq);
             ctx->launches++;
         } else if (what == 5) TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, nullptr));
         else if (what == 6) TRYR(mg_setup_replay(ctx));
@@ -513,17 +501,15 @@ static int precond64(tsl_ctx *ctx, const double *in, double *out)
     return precond_apply_f64io(ctx, in, out);
 }
 // r = b - A x (fp64), rr = |r|^2 into acc
-__global__ void __launch_bounds__(256) k_residual64(int n_rows, const int *__restrict__ srow2v, const int *__restrict__ slice_base,
-                                                    const int *__restrict__ colidx,
+__global__ void __launch_bounds__(256) k_residual64(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
                                                     const double *__restrict__ val, const double *__restrict__ b, const double *__restrict__ x,
                                                     double *r, double *acc_rr)
 {
-    int srow = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = vertex_of_srow(srow2v, srow, n_rows);
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
     double rr = 0;
-    if (row >= 0) {
+    if (row < n_rows) {
         double y0, y1, y2;
-        spmv_row<double>(slice_base, colidx, val, x, srow, y0, y1, y2);
+        spmv_row<double>(slice_base, colidx, val, x, row, y0, y1, y2);
         double r0 = b[3 * row] - y0, r1 = b[3 * row + 1] - y1, r2 = b[3 * row + 2] - y2;
         r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
         rr = r0 * r0 + r1 * r1 + r2 * r2;
@@ -546,10 +532,10 @@ static int bicg_iteration_body(tsl_ctx *ctx)
     double *dx = ctx->sol;
     k_bi_a<<<GRID(n3, 256), 256, 0, s>>>(n3, r, v, p, ks);
     TRYR(precond64(ctx, p, y));
-    k_spmv_dots<double><<<GRID((n + 63) & ~63, 256), 256, 0, s>>>(n, A.srow2v, A.slice_base, A.colidx, A.val64, y, v, rhat, &ks->rhv, nullptr);
+    k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, y, v, rhat, &ks->rhv, nullptr);
     k_bi_c<<<GRID(n3, 256), 256, 0, s>>>(n3, r, v, sv, ks);
     TRYR(precond64(ctx, sv, z));
-    k_spmv_dots<double><<<GRID((n + 63) & ~63, 256), 256, 0, s>>>(n, A.srow2v, A.slice_base, A.colidx, A.val64, z, t, sv, &ks->ts, &ks->tt);
+    k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, z, t, sv, &ks->ts, &ks->tt);
     k_bi_e<<<GRID(n3, 256), 256, 0, s>>>(n3, y, z, sv, t, rhat, dx, r, ks);
     k_bi_rotate<<<1, 1, 0, s>>>(ks);
     ctx->launches += 6;
@@ -600,7 +586,7 @@ int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol,
             ctx->launches++;
         }
         CK(cudaMemsetAsync(&ks->rr, 0, sizeof(double), s));
-        k_residual64<<<GRID((n + 63) & ~63, 256), 256, 0, s>>>(n, A.srow2v, A.slice_base, A.colidx, A.val64, rhs, x, res, &ks->rr);
+        k_residual64<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, rhs, x, res, &ks->rr);
         ctx->launches++;
         CK(cudaMemcpyAsync(ctx->ks_host, ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));

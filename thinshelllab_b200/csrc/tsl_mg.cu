@@ -26,18 +26,11 @@ namespace tsl {
 
 // ------------------------------------------------------------------------------------------------ row operators
 struct SellOp {
-    const int *slice_base, *colidx, *srow2v;
+    const int *slice_base, *colidx;
     const float *val;
-    // thread = sliced row; returns its vertex or -1 (padding row / vertex outside the solve)
-    __device__ __forceinline__ int vertex(int srow, int n_rows) const
+    __device__ __forceinline__ void mul(int row, const float *__restrict__ x, float &y0, float &y1, float &y2) const
     {
-        if (srow >= ((n_rows + 63) & ~63)) return -1;
-        int v = __ldg(srow2v + srow);
-        return (v >= 0 && v < n_rows) ? v : -1;
-    }
-    __device__ __forceinline__ void mul(int srow, const float *__restrict__ x, float &y0, float &y1, float &y2) const
-    {
-        int S = srow >> 5, lane = srow & 31;
+        int S = row >> 5, lane = row & 31;
         int b0 = slice_base[S], b1 = slice_base[S + 1];
         float a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll 2
@@ -186,13 +179,12 @@ __global__ void __launch_bounds__(256) k_cheb_step_sell(SellOp A, int nrows, con
                                                         const float *__restrict__ x_in, float *d, float *x_out,
                                                         const float *__restrict__ coef, double *acc, int acc_mode)
 {
-    int srow = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = A.vertex(srow, nrows);
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
     double s = 0;
-    if (row >= 0) {
+    if (row < nrows) {
         float a = coef[0], c = coef[1];
         float y0, y1, y2;
-        A.mul(srow, x_in, y0, y1, y2);
+        A.mul(row, x_in, y0, y1, y2);
         float b0 = 0, b1 = 0, b2 = 0;
         if (b) { b0 = b[3 * row]; b1 = b[3 * row + 1]; b2 = b[3 * row + 2]; }
         float r0 = b0 - y0, r1 = b1 - y1, r2 = b2 - y2;
@@ -240,11 +232,10 @@ __global__ void __launch_bounds__(256) k_cheb_step_stencil(StencilOp A, int nv, 
 }
 __global__ void __launch_bounds__(256) k_mg_residual_sell(SellOp A, int nrows, const float *__restrict__ b, const float *__restrict__ x, float *r)
 {
-    int srow = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = A.vertex(srow, nrows);
-    if (row < 0) return;
+    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= nrows) return;
     float y0, y1, y2;
-    A.mul(srow, x, y0, y1, y2);
+    A.mul(row, x, y0, y1, y2);
     r[3 * row] = b[3 * row] - y0; r[3 * row + 1] = b[3 * row + 1] - y1; r[3 * row + 2] = b[3 * row + 2] - y2;
 }
 __global__ void __launch_bounds__(256) k_mg_residual_stencil(StencilOp A, int nv, const float *__restrict__ b, const float *__restrict__ x, float *r)
@@ -453,14 +444,13 @@ __global__ void k_prolong_add(int n0f, int n1f, int off, float *x_f, const int *
 
 // ------------------------------------------------------------------------------------------------ setup kernels
 // stencil copy of the cloth block of the sliced-ELL matrix (input of the first Galerkin product)
-__global__ void k_sell_to_stencil(int off, int nvc, int n1, const int *__restrict__ v2srow, const int *__restrict__ slice_base, const int *__restrict__ colidx,
+__global__ void k_sell_to_stencil(int off, int nvc, int n1, const int *__restrict__ slice_base, const int *__restrict__ colidx,
                                   const float *__restrict__ val, const int *__restrict__ diag_pb, float *out, long long sv, long long se)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nvc) return;
     int row = off + v;
-    int srow = v2srow[row];
-    int S = srow >> 5, lane = srow & 31;
+    int S = row >> 5, lane = row & 31;
     int i = v / n1, j = v - i * n1;
     int b0 = slice_base[S], b1 = slice_base[S + 1];
     int dpb = diag_pb[row];
@@ -571,7 +561,7 @@ __global__ void k_dinv_sell(int n_rows, int n_alloc, const int *__restrict__ dia
     if (r >= n_alloc) return;
     float a[9], inv[9];
     if (r < n_rows) {
-        long long base = sell_addr(diag_pb[r], diag_pb[r] & 31, 0);
+        long long base = sell_addr(diag_pb[r], r & 31, 0);
 #pragma unroll
         for (int c = 0; c < 9; c++) a[c] = val[base + c * 32];
         inv3_guarded(a, inv);
@@ -677,7 +667,7 @@ void mg_free(tsl_ctx *ctx)
     mg.n_levels = 0;
 }
 
-static SellOp sell_op(tsl_ctx *ctx, const float *val) { SellOp o; o.slice_base = ctx->A.slice_base; o.colidx = ctx->A.colidx; o.srow2v = ctx->A.srow2v; o.val = val; return o; }
+static SellOp sell_op(tsl_ctx *ctx, const float *val) { SellOp o; o.slice_base = ctx->A.slice_base; o.colidx = ctx->A.colidx; o.val = val; return o; }
 static StencilOp stencil_op(const MgLevel &L) { StencilOp o; o.val = L.val; o.n0 = L.n0; o.n1 = L.n1; o.sv = L.sv; o.se = L.se; return o; }
 
 // d = a d + c D^-1 (b - A x_in), x_out = x_in + d on level l (level 0 smooths with the clamped matrix)
@@ -685,7 +675,7 @@ static void launch_step(tsl_ctx *ctx, int l, const float *b, const float *x_in, 
 {
     MgLevel &L = ctx->mg.lev[l];
     if (l == 0)
-        k_cheb_step_sell<<<GRID((L.nrows + 63) & ~63, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32m), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        k_cheb_step_sell<<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32m), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     else if (L.sv == 1)
         k_cheb_step_stencil_t<<<GRID(L.nv, 128), 128, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     else
@@ -714,7 +704,7 @@ int mg_setup(tsl_ctx *ctx)
     ctx->launches++;
     if (mg.n_levels > 1) {
         // the pattern is static: every slot this kernel writes is rewritten on each setup, the others stay zero
-        k_sell_to_stencil<<<GRID(L0.nv, 128), 128, 0, s>>>(c.offset, L0.nv, L0.n1, A.v2srow, A.slice_base, A.colidx, A.val32m, A.diag_pb, L0.val, L0.sv, L0.se);
+        k_sell_to_stencil<<<GRID(L0.nv, 128), 128, 0, s>>>(c.offset, L0.nv, L0.n1, A.slice_base, A.colidx, A.val32m, A.diag_pb, L0.val, L0.sv, L0.se);
         ctx->launches++;
     }
     for (int l = 0; l + 1 < mg.n_levels; l++) {
@@ -786,7 +776,7 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
     MgLevel &C = mg.lev[l + 1];
     int off = (l == 0) ? mg.cloth_offset : 0;
     const int *mask = (l == 0) ? ctx->frozen : nullptr;
-    if (l == 0) k_mg_residual_sell<<<GRID((L.nrows + 63) & ~63, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32m), L.nrows, b, cur, L.r);
+    if (l == 0) k_mg_residual_sell<<<GRID(L.nrows, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32m), L.nrows, b, cur, L.r);
     else if (L.sv == 1) k_mg_residual_stencil_t<<<GRID(L.nv, 128), 128, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     else k_mg_residual_stencil<<<GRID(32LL * L.nv, 256), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     k_restrict<<<GRID(C.nv, 128), 128, 0, s>>>(L.n0, L.n1, off, L.r, mask, C.n0, C.n1, C.b);

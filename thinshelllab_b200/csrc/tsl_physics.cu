@@ -266,7 +266,7 @@ __global__ void k_mask_frozen(int n, const int *__restrict__ frozen, double *F)
 template <typename T>
 __device__ __forceinline__ void add_block(T *val, int pb, int row, int col, const int *__restrict__ frozen, const double *B)
 {
-    int lane = pb & 31;                      // slice bases are multiples of 32
+    int lane = row & 31;
     long long base = sell_addr(pb, lane, 0);
 #pragma unroll
     for (int a = 0; a < 3; a++) {
@@ -532,7 +532,7 @@ __global__ void k_hessian_mass(int n_verts, const double *__restrict__ mass, dou
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= n_verts) return;
-    long long base = sell_addr(diag_pb[v], diag_pb[v] & 31, 0);
+    long long base = sell_addr(diag_pb[v], v & 31, 0);
     T m = (T)(mass[v] / (dt * dt));
     atomicAdd(val + base + 0 * 32, m); atomicAdd(val + base + 4 * 32, m); atomicAdd(val + base + 8 * 32, m);
 }
