@@ -115,6 +115,51 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def secondary_50k(args, dev):
+    """BASELINE.json configs[1] / configs[2] (50 k-triangle sheet, forward only and forward + adjoint) on one GPU, state resident in
+    HBM: reported inside config, next to the 1 M-triangle headline"""
+    import torch
+    from thinshelllab_b200.engine.analytic_grad_system import Grad
+    from thinshelllab_b200.synthetic import sheet_scene
+    N = 158
+    s = sheet_scene(N, device=dev)
+    if args.newton_mode >= 0:
+        from thinshelllab_b200 import _lib as _l
+        s.engine.set_option(_l.OPT_NEWTON_MODE, args.newton_mode)
+    e, NVc, g = s.engine, s.cloths[0].NV, Grad(s, 2, 0)
+
+    def fwd():
+        g.copy_pos(s, 0)
+        s.time_step()
+        g.copy_pos(s, 1)
+
+    def bwd():
+        g._pos_grad.zero_(); g._angleref_grad.zero_()
+        g._pos_grad[1, :NVc, 2] = 1.0
+        g.transfer_grad(1, s, rel_tol=args.adjoint_tol)
+
+    for _ in range(3):
+        fwd(); bwd()
+    snap = (e.pos.clone(), e.vel.clone(), e.cloth_ref_angle[0].clone())
+    out = {}
+    for name, with_bwd in (("configs[1] forward only", False), ("configs[2] forward + adjoint", True)):
+        e.pos.copy_(snap[0]); e.prev_pos.copy_(snap[0]); e.vel.copy_(snap[1]); e.cloth_ref_angle[0].copy_(snap[2]); e.reset_contact_state()
+        torch.cuda.synchronize()
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        for _ in range(3):
+            fwd()
+            if with_bwd:
+                bwd()
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1)
+        out[name] = {"sheet": "158x158 (49928 tris)", "steps": 3, "ms_per_step": ms / 3, "tri_steps_per_s": 2 * N * N * 3 / (ms * 1e-3)}
+    del s, g
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -242,7 +287,8 @@ def run_ours(args, rank, world):
         "metric": "tri_steps_per_s (implicit fwd+bwd step)", "value": value, "unit": "tri-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64 (state, energy, residual, contact, adjoint matrix and solve) + f32 (forward Newton matrix, PCG vectors, multigrid)", "data": "synthetic",
-        "config": {"workload": f"sheet {N}x{N} ({n_tris} tris, dx 2 mm) landing on a frozen table, Scene_bouncing physics, fwd + adjoint (dL/dKb) per step",
+        "config": {"workload": f"sheet {N}x{N} ({n_tris} tris, dx 2 mm) landing on a frozen table, Scene_bouncing physics, fwd + adjoint (dL/dKb) per step"
+                               + (" -- the 1 M-triangle sheet of BASELINE configs[4] / north_star on ONE GPU (largest single-GPU configuration; configs[1] and [2] are in baseline_configs_50k)" if N == 707 else ""),
                    "sheet_n": N, "n_tris": n_tris, "n_verts": V, "nnzb": sz["nnzb"], "nnzb_padded": sz["nnzb_padded"], "n_solve": Vs, "nnzb_solve": Bs,
                    "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (element partition not implemented in round 1)",
                    "l2": "matrix %.0f MB > 126 MB L2" % (sz["bytes_matrix_f32"] / 1e6) if sz["bytes_matrix_f32"] > 126e6 else
@@ -264,6 +310,8 @@ def run_ours(args, rank, world):
                                        "frac": pcg_bytes / (ms_pcg * 1e-3) / 1e9 / peak, "note": "one captured CUDA graph: SpMV + update + V-cycle + direction"},
                      "other_us": {"vcycle": 1e3 * ms_vcycle, "mg_setup": 1e3 * ms_setup, "hessian": 1e3 * ms_hess, "residual": 1e3 * ms_resid, "energy": 1e3 * ms_energy}},
     }
+    if world == 1 and N != 158 and not args.no_secondary:
+        out["config"]["baseline_configs_50k"] = secondary_50k(args, dev)
     if world == 1 and not args.no_cpu_baseline:
         tris, times, threads = oracle_fwd_bwd(args.cpu_sample_n, 1, threads=os.cpu_count())
         out["cpu_baseline"] = {"value": tris / times[0], "unit": "tri-steps/s", "cores": threads, "kind": "port",
@@ -283,6 +331,7 @@ def main():
     ap.add_argument("--cpu-sample-n", type=int, default=32)
     ap.add_argument("--adjoint-tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the 50 k-triangle configs[1] / configs[2] measurement")
     ap.add_argument("--newton-mode", type=int, default=-1, help="TSL_OPT_NEWTON_MODE of the forward solve (-1: library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

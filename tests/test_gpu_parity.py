@@ -259,6 +259,25 @@ def test_sheet_steps_vs_oracle_small(mode):
         assert errs[0] < 3e-7, errs
 
 
+def test_pinned_row_sheet_vs_oracle():
+    """frozen cloth DOFs (the pinned row of Scene_folding, code/task_scene/Scene_folding.py:123-127): they are masked in
+    assembly, left out of the multigrid coarse spaces, and must not move; positions against the oracle on the first steps"""
+    N = 24
+    pinned = tuple(N * (N + 1) + j for j in range(N + 1))
+    s = sheet_scene(N, pinned_vertices=pinned)
+    o = _oracle_for(s, extra_frozen_vertices=pinned)
+    x_pin = s.engine.pos[list(pinned)].clone()
+    errs = []
+    for step in range(2):
+        pos0, vel0 = o.pos.copy(), o.vel.copy()
+        st = s.time_step()
+        o.time_step()
+        assert st.converged and st.n_contacts == o.nc
+        assert torch.equal(s.engine.pos[list(pinned)], x_pin)
+        errs.append(_accept_fixed_point(s, o, pos0, vel0))
+    assert errs[0] < 3e-7, errs
+
+
 def test_sheet_50k_first_iteration_and_properties():
     """config 1 size (158 x 158, 49 928 triangles): contact sets, energy and residual against the oracle at full size, then
     size-independent properties of the CUDA step: the accepted step lowers the energy, frozen vertices do not move,

@@ -30,7 +30,7 @@ def sheet_spec(N, dx=0.002, dt=5e-3, seed=0, z0=0.0003, bump=0.25, noise=0.01, k
                 eps_contact=0.0004, eps_v=0.01, max_n_constraints=NV + 16, n_tris=2 * N * N, n_verts=NV + tpos.shape[0])
 
 
-def sheet_scene(N, device="cuda:0", **kw):
+def sheet_scene(N, device="cuda:0", pinned_vertices=(), **kw):
     import torch
 
     from .task_scene.Scene_bouncing import Scene
@@ -38,7 +38,7 @@ def sheet_scene(N, device="cuda:0", **kw):
     size = sp["size"]
     s = Scene(cloth_size=size, cloth_N=N, dt=sp["dt"], table_size=sp["table_size"], table_N=sp["table_N"], table_offset=sp["table_offset"],
               cloth_offset=(-0.5 * size, -0.5 * size, 0.0), reset_offset=(-0.5 * size, -0.5 * size, 0.0),
-              k_contact=sp["k_contact"], max_n_constraints=sp["max_n_constraints"], grid_n=sp["grid_n"], device=device)
+              k_contact=sp["k_contact"], max_n_constraints=sp["max_n_constraints"], grid_n=sp["grid_n"], pinned_vertices=pinned_vertices, device=device)
     s.mu_cloth_elastic[None] = sp["mu"]
     s.init_all()
     NV = (N + 1) ** 2
