@@ -1,0 +1,44 @@
+"""The module tree the reference's driver scripts import resolves against this package (no GPU needed to import), and the
+host-side agent / optimiser mirrors keep the reference's semantics (code/agent/traj_opt_single.py:15-48,
+code/optimizer/optim.py:37-81)."""
+import numpy as np
+import torch
+
+
+def test_reference_import_names_resolve():
+    from thinshelllab_b200 import compat
+    compat.install()
+    import taichi as ti
+    ti.init(ti.cpu, default_fp=ti.f64, default_ip=ti.i32, fast_math=False)
+    from thinshelllab.agent.traj_opt_single import agent_trajopt  # noqa: F401
+    from thinshelllab.engine import linalg  # noqa: F401
+    from thinshelllab.engine.analytic_grad_system import Grad  # noqa: F401
+    from thinshelllab.engine.geometry import projection_query  # noqa: F401
+    from thinshelllab.engine.render_engine import Renderer
+    from thinshelllab.optimizer.optim import Adam_single  # noqa: F401
+    from thinshelllab.task_scene.Scene_bouncing import Body, Scene  # noqa: F401
+    import imageio  # noqa: F401
+    import matplotlib.pyplot as plt
+    plt.plot([0], [0])
+    assert hasattr(Renderer, "set_save_dir") and hasattr(Renderer, "render") and hasattr(Renderer, "end_rendering")
+
+
+def test_agent_and_adam_semantics():
+    from thinshelllab_b200.agent.traj_opt_single import agent_trajopt
+    from thinshelllab_b200.optimizer.optim import Adam_single
+    a = agent_trajopt(4, 2, max_moving_dist=0.0005)
+    a.traj[1, 0, 0] = 0.002                      # 4x too far: rescaled to 0.0005
+    a.traj[2, 0, 0] = 0.0021                     # then measured from the rescaled frame 1
+    a.fix_action(0.015)
+    t = a.traj.to_numpy()
+    assert abs(t[1, 0, 0] - 0.0005) < 1e-8 and abs(t[2, 0, 0] - 0.001) < 1e-8
+    a.get_action(2)
+    assert np.allclose(a.delta_pos.to_numpy()[0], [0.0005, 0, 0], atol=1e-8)
+    # Adam: epsilon inside the square root, lr decays by `discount` every 10 steps
+    p = torch.zeros((1, 1, 1), dtype=torch.float64)
+    opt = Adam_single((1, 1, 1), 1e-2, 0.9, 0.999, 1e-8, discount=0.5)
+    opt.step(p, torch.ones((1, 1, 1)))
+    assert abs(float(p) + 1e-2 / np.sqrt(1 + 1e-8)) < 1e-12
+    for _ in range(9):
+        opt.step(p, torch.ones((1, 1, 1)))
+    assert abs(opt.lr - 5e-3) < 1e-15

@@ -1,0 +1,38 @@
+"""agent_trajopt on torch tensors: the open-loop trajectory container of the reference's drivers
+(code/agent/traj_opt_single.py:4-48).  O(T x parts) host-side bookkeeping, not a kernel target:
+same attribute names and semantics so that driver scripts run unchanged."""
+import torch
+
+from ..fields import TensorField
+
+
+class agent_trajopt:
+    def __init__(self, tot_timestep, cnt, max_moving_dist=0.0005):
+        self._traj = torch.zeros((tot_timestep, cnt, 6), dtype=torch.float64)
+        self._delta_pos = torch.zeros((cnt, 3), dtype=torch.float64)
+        self._delta_rot = torch.zeros((cnt, 3), dtype=torch.float64)
+        self.tmp_action = TensorField(torch.zeros((cnt, 6), dtype=torch.float64))
+        self.action_dim = 6 * cnt
+        self.tot_timestep, self.max_moving_dist, self.n_part = tot_timestep, max_moving_dist, cnt
+
+    traj = property(lambda self: TensorField(self._traj))
+    delta_pos = property(lambda self: TensorField(self._delta_pos))
+    delta_rot = property(lambda self: TensorField(self._delta_rot))
+
+    def calculate_dist(self, frame, max_dist, j):
+        d = self._traj[frame, j] - self._traj[frame - 1, j]
+        return float(d[:3].norm() + d[3:].norm() * max_dist)
+
+    def fix_action(self, max_dist):
+        """rescales every per-frame increment so that |dpos| + max_dist |drot| <= max_moving_dist (sequentially in time, :15-27)"""
+        for i in range(1, self.tot_timestep):
+            for j in range(self.n_part):
+                d = self._traj[i, j] - self._traj[i - 1, j]
+                w = self.max_moving_dist / (float(d[:3].norm() + d[3:].norm() * max_dist) + 1e-8)
+                if w < 1.0:
+                    self._traj[i, j] = self._traj[i - 1, j] + d * w
+
+    def get_action(self, step):
+        d = self._traj[step] - self._traj[step - 1]
+        self._delta_pos.copy_(d[:, :3])
+        self._delta_rot.copy_(d[:, 3:])

@@ -10,6 +10,13 @@ from ..fields import Scalar, TensorField
 from ..meshes import box_body
 
 
+class Body:
+    """BaseScene.Body (code/engine/BaseScene.py:23-27): vertex / face range of one body in the scene-global arrays"""
+
+    def __init__(self, v_start=0, v_end=0, f_start=0, f_end=0):
+        self.v_start, self.v_end, self.f_start, self.f_end = v_start, v_end, f_start, f_end
+
+
 class _ClothView:
     """the attributes of engine.model_fold_offset.Cloth that drivers touch"""
 
