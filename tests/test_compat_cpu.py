@@ -1,11 +1,24 @@
 """The module tree the reference's driver scripts import resolves against this package (no GPU needed to import), and the
 host-side agent / optimiser mirrors keep the reference's semantics (code/agent/traj_opt_single.py:15-48,
 code/optimizer/optim.py:37-81)."""
+import sys
+
 import numpy as np
+import pytest
 import torch
 
 
-def test_reference_import_names_resolve():
+@pytest.fixture
+def clean_modules():
+    """compat.install() registers stand-ins in sys.modules: remove whatever it added, other tests import the real things"""
+    before = set(sys.modules)
+    yield
+    for k in set(sys.modules) - before:
+        if k.split(".")[0] in ("taichi", "imageio", "matplotlib", "thinshelllab"):
+            del sys.modules[k]
+
+
+def test_reference_import_names_resolve(clean_modules):
     from thinshelllab_b200 import compat
     compat.install()
     import taichi as ti

@@ -38,9 +38,16 @@ def noise_sign_override(f2v, cf, pos, norm_dir):
     """Signs that the emulated reference produced for the topologically degenerate side tests
     (see cloth_neg() in oracle/csrc/tsl_oracle.c): recomputed with the same numpy expression the
     taichi stand-in evaluates, so they are bit-identical to the golden run."""
+    import importlib.util
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(orc.__file__), "ti_emu"))
-    import taichi as ti_emu
+    # the emulation module by PATH (another test may have registered an inert `taichi` stand-in under that name)
+    ti_emu = sys.modules.get("_tsl_ti_emu")
+    if ti_emu is None:
+        path = os.path.join(os.path.dirname(orc.__file__), "ti_emu", "taichi", "__init__.py")
+        spec = importlib.util.spec_from_file_location("_tsl_ti_emu", path, submodule_search_locations=[os.path.dirname(path)])
+        ti_emu = importlib.util.module_from_spec(spec)
+        sys.modules["_tsl_ti_emu"] = ti_emu
+        spec.loader.exec_module(ti_emu)
     NF = f2v.shape[0]
     ov = -np.ones((NF, 3), np.int8)
     for i in range(NF):
@@ -140,9 +147,16 @@ def _scene_from_golden(g):
 
 def _scene_override(s, pos):
     """noise-sign override for the current cloth state (see noise_sign_override)"""
+    import importlib.util
     import sys
-    sys.path.insert(0, os.path.join(os.path.dirname(orc.__file__), "ti_emu"))
-    import taichi as ti_emu
+    # the emulation module by PATH (another test may have registered an inert `taichi` stand-in under that name)
+    ti_emu = sys.modules.get("_tsl_ti_emu")
+    if ti_emu is None:
+        path = os.path.join(os.path.dirname(orc.__file__), "ti_emu", "taichi", "__init__.py")
+        spec = importlib.util.spec_from_file_location("_tsl_ti_emu", path, submodule_search_locations=[os.path.dirname(path)])
+        ti_emu = importlib.util.module_from_spec(spec)
+        sys.modules["_tsl_ti_emu"] = ti_emu
+        spec.loader.exec_module(ti_emu)
     p = pos[:s.NVc]
     nd = np.zeros((s.NFc, 3))
     for i in range(s.NFc):
