@@ -141,6 +141,68 @@ __device__ __forceinline__ void stencil_row_thread(const StencilOp &A, int v, co
     }
     y0 = a0; y1 = a1; y2 = a2;
 }
+// two threads per vertex (even / odd slots): a 354 x 354 level has only 125 k vertices = 41 % of the resident thread slots
+// of 148 SMs, so halving the work per thread doubles the loads in flight; partial sums are combined with one shuffle
+__device__ __forceinline__ void stencil_row_pair(const StencilOp &A, int v, int half, const float *__restrict__ x, float &y0, float &y1, float &y2)
+{
+    int I = v / A.n1, J = v - I * A.n1;
+    const float *a = A.val + (size_t)v * A.sv;
+    const long long se = A.se;
+    float a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll
+    for (int q = 0; q < 13; q++) {
+        int slot = 2 * q + half;
+        if (slot < 25) {
+            int dI = slot / 5 - 2, dJ = slot - (slot / 5) * 5 - 2;
+            int ii = min(max(I + dI, 0), A.n0 - 1), jj = min(max(J + dJ, 0), A.n1 - 1);
+            int u = ii * A.n1 + jj;
+            float x0 = x[3 * u], x1 = x[3 * u + 1], x2 = x[3 * u + 2];
+            const float *p = a + (size_t)(slot * 9) * se;
+            a0 += __ldg(p) * x0 + __ldg(p + se) * x1 + __ldg(p + 2 * se) * x2;
+            a1 += __ldg(p + 3 * se) * x0 + __ldg(p + 4 * se) * x1 + __ldg(p + 5 * se) * x2;
+            a2 += __ldg(p + 6 * se) * x0 + __ldg(p + 7 * se) * x1 + __ldg(p + 8 * se) * x2;
+        }
+    }
+    a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
+    y0 = a0; y1 = a1; y2 = a2;
+}
+__global__ void __launch_bounds__(256) k_cheb_step_stencil_t2(StencilOp A, int nv, const float *__restrict__ dinv, const float *__restrict__ b,
+                                                              const float *__restrict__ x_in, float *d, float *x_out,
+                                                              const float *__restrict__ coef, double *acc, int acc_mode)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int row = t >> 1, half = t & 1;
+    double s = 0;
+    float y0 = 0, y1 = 0, y2 = 0;
+    bool live = row < nv;
+    stencil_row_pair(A, live ? row : nv - 1, half, x_in, y0, y1, y2);      // all lanes take part in the shuffle
+    if (live && half == 0) {
+        float a = coef[0], c = coef[1];
+        float b0 = 0, b1 = 0, b2 = 0;
+        if (b) { b0 = b[3 * row]; b1 = b[3 * row + 1]; b2 = b[3 * row + 2]; }
+        float r0 = b0 - y0, r1 = b1 - y1, r2 = b2 - y2;
+        const float *m = dinv + 9 * (size_t)row;
+        float d0 = c * (m[0] * r0 + m[1] * r1 + m[2] * r2), d1 = c * (m[3] * r0 + m[4] * r1 + m[5] * r2), d2 = c * (m[6] * r0 + m[7] * r1 + m[8] * r2);
+        if (a != 0.f) { d0 += a * d[3 * row]; d1 += a * d[3 * row + 1]; d2 += a * d[3 * row + 2]; }
+        d[3 * row] = d0; d[3 * row + 1] = d1; d[3 * row + 2] = d2;
+        if (x_out) {
+            float o0 = x_in[3 * row] + d0, o1 = x_in[3 * row + 1] + d1, o2 = x_in[3 * row + 2] + d2;
+            x_out[3 * row] = o0; x_out[3 * row + 1] = o1; x_out[3 * row + 2] = o2;
+            if (acc_mode == 1) s = (double)b0 * o0 + (double)b1 * o1 + (double)b2 * o2;
+        }
+        if (acc_mode == 2) s = (double)d0 * d0 + (double)d1 * d1 + (double)d2 * d2;
+    }
+    if (acc) block_atomic_sum(s, acc);
+}
+__global__ void __launch_bounds__(256) k_mg_residual_stencil_t2(StencilOp A, int nv, const float *__restrict__ b, const float *__restrict__ x, float *r)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int row = t >> 1, half = t & 1;
+    float y0, y1, y2;
+    bool live = row < nv;
+    stencil_row_pair(A, live ? row : nv - 1, half, x, y0, y1, y2);
+    if (live && half == 0) { r[3 * row] = b[3 * row] - y0; r[3 * row + 1] = b[3 * row + 1] - y1; r[3 * row + 2] = b[3 * row + 2] - y2; }
+}
 __global__ void __launch_bounds__(128) k_cheb_step_stencil_t(StencilOp A, int nv, const float *__restrict__ dinv, const float *__restrict__ b,
                                                              const float *__restrict__ x_in, float *d, float *x_out,
                                                              const float *__restrict__ coef, double *acc, int acc_mode)
@@ -638,6 +700,7 @@ int mg_alloc(tsl_ctx *ctx)
         n0 = (n0 - 1) / 2 + 1; n1 = (n1 - 1) / 2 + 1;
     }
     // levels from tail_level on (<= 1024 vertices each, row-major, at most TSL_MG_TAIL_MAX of them) run in one fused kernel
+    { const char *e = getenv("TSL_MG_PAIR"); mg.pair_threads = e ? atoi(e) : 1; }
     mg.tail_level = -1;
     for (int l = 1; l < mg.n_levels; l++)
         if (mg.lev[l].nv <= 1024 && mg.n_levels - l <= TSL_MG_TAIL_MAX) { mg.tail_level = l; break; }
@@ -676,6 +739,8 @@ static void launch_step(tsl_ctx *ctx, int l, const float *b, const float *x_in, 
     MgLevel &L = ctx->mg.lev[l];
     if (l == 0)
         k_cheb_step_sell<<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32m), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    else if (L.sv == 1 && ctx->mg.pair_threads)
+        k_cheb_step_stencil_t2<<<GRID(2LL * L.nv, 256), 256, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     else if (L.sv == 1)
         k_cheb_step_stencil_t<<<GRID(L.nv, 128), 128, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     else
@@ -777,6 +842,7 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
     int off = (l == 0) ? mg.cloth_offset : 0;
     const int *mask = (l == 0) ? ctx->frozen : nullptr;
     if (l == 0) k_mg_residual_sell<<<GRID(L.nrows, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32m), L.nrows, b, cur, L.r);
+    else if (L.sv == 1 && mg.pair_threads) k_mg_residual_stencil_t2<<<GRID(2LL * L.nv, 256), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     else if (L.sv == 1) k_mg_residual_stencil_t<<<GRID(L.nv, 128), 128, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     else k_mg_residual_stencil<<<GRID(32LL * L.nv, 256), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     k_restrict<<<GRID(C.nv, 128), 128, 0, s>>>(L.n0, L.n1, off, L.r, mask, C.n0, C.n1, C.b);
