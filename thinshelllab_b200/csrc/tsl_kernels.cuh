@@ -45,7 +45,9 @@ int mg_setup_replay(tsl_ctx *ctx);   // mg_setup through a captured graph after 
 int mg_alloc(tsl_ctx *ctx);
 void mg_free(tsl_ctx *ctx);
 int mg_setup(tsl_ctx *ctx);
-int mg_apply(tsl_ctx *ctx, const float *b, float *z, double *acc_bz);
+// first_done: the caller already applied the first Chebyshev step of level 0 (d = c D^-1 b, x[0] = d) while producing b
+int mg_apply(tsl_ctx *ctx, const float *b, float *z, double *acc_bz, bool first_done = false);
+void mg_first_step_targets(tsl_ctx *ctx, const float **dinv, float **d, float **x0, const float **coef);
 int mg_get_level(tsl_ctx *ctx, int level, int *dims, float *lmax, float *val_host);
 
 }  // namespace tsl

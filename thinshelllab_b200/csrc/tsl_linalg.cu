@@ -186,8 +186,10 @@ __global__ void __launch_bounds__(256) k_pcg_init(int n_rows, int n_alloc, const
     block_atomic_sum2(rr, 0.0, &ks->rr_new, nullptr);
 }
 // alpha = rz / pq;  x += alpha p;  r -= alpha q (fp64), r32 = (float) r for the preconditioner;  rr_new += r.r
+// Optionally also the first Chebyshev step of the V-cycle's level 0 on the new residual (mg_d = c D^-1 r, mg_x0 = mg_d).
 __global__ void __launch_bounds__(256) k_pcg_update(int n_rows, const double *__restrict__ p, const double *__restrict__ q,
-                                                    double *x, double *r, float *r32, KrylovScalars *ks)
+                                                    double *x, double *r, float *r32, KrylovScalars *ks,
+                                                    const float *__restrict__ mg_dinv, float *mg_d, float *mg_x0, const float *__restrict__ mg_coef)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     double pq = ks->pq, rz = ks->rz;
@@ -199,8 +201,16 @@ __global__ void __launch_bounds__(256) k_pcg_update(int n_rows, const double *__
         double r0 = r[3 * row] - alpha * q[3 * row], r1 = r[3 * row + 1] - alpha * q[3 * row + 1], r2 = r[3 * row + 2] - alpha * q[3 * row + 2];
         x[3 * row] += alpha * p[3 * row]; x[3 * row + 1] += alpha * p[3 * row + 1]; x[3 * row + 2] += alpha * p[3 * row + 2];
         r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
-        r32[3 * row] = (float)r0; r32[3 * row + 1] = (float)r1; r32[3 * row + 2] = (float)r2;
+        float f0 = (float)r0, f1 = (float)r1, f2 = (float)r2;
+        r32[3 * row] = f0; r32[3 * row + 1] = f1; r32[3 * row + 2] = f2;
         rr = r0 * r0 + r1 * r1 + r2 * r2;
+        if (mg_dinv) {
+            float c = mg_coef[1];
+            const float *m = mg_dinv + 9 * (size_t)row;
+            float d0 = c * (m[0] * f0 + m[1] * f1 + m[2] * f2), d1 = c * (m[3] * f0 + m[4] * f1 + m[5] * f2), d2 = c * (m[6] * f0 + m[7] * f1 + m[8] * f2);
+            mg_d[3 * row] = d0; mg_d[3 * row + 1] = d1; mg_d[3 * row + 2] = d2;
+            mg_x0[3 * row] = d0; mg_x0[3 * row + 1] = d1; mg_x0[3 * row + 2] = d2;
+        }
     }
     block_atomic_sum2(rr, 0.0, &ks->rr_new, nullptr);
 }
@@ -287,9 +297,11 @@ static int pcg_iteration_body(tsl_ctx *ctx, const float *opval)
     KrylovScalars *ks = ctx->ks;
     cudaStream_t s = ctx->stream;
     k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, &ks->pq);
-    k_pcg_update<<<GRID(n, 256), 256, 0, s>>>(n, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ctx->cg_r32, ks);
+    const float *mg_dinv, *mg_coef; float *mg_d, *mg_x0;
+    mg_first_step_targets(ctx, &mg_dinv, &mg_d, &mg_x0, &mg_coef);
+    k_pcg_update<<<GRID(n, 256), 256, 0, s>>>(n, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ctx->cg_r32, ks, mg_dinv, mg_d, mg_x0, mg_coef);
     ctx->launches += 2;
-    TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, &ks->rz_new));
+    TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, &ks->rz_new, mg_dinv != nullptr));
     k_pcg_direction<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, 0, ctx->cg_z, ctx->cg_p, ks);
     k_pcg_rotate<<<1, 1, 0, s>>>(0, ks);
     ctx->launches += 2;

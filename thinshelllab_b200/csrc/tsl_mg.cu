@@ -455,8 +455,10 @@ __device__ __forceinline__ float pw1(int a, int I, int nc) { return a == 0 ? 1.f
 
 // b_c = P^T r_f.  off: first row of the grid inside the fine vectors (level 0: cloth vertex offset); mask: frozen
 // flags [3 * rows] of the fine vectors or nullptr (frozen DOFs do not take part in the coarse correction)
+// Optionally fused with the first Chebyshev step of the coarse level (zero guess: d = c D^-1 b, x = d), which only needs the
+// vertex's own right-hand side: one graph node less per level.
 __global__ void k_restrict(int n0f, int n1f, int off, const float *__restrict__ r_f, const int *__restrict__ mask,
-                           int n0c, int n1c, float *b_c)
+                           int n0c, int n1c, float *b_c, const float *__restrict__ dinv_c, float *d_c, float *x0_c, const float *__restrict__ coef_c)
 {
     int cv = blockIdx.x * blockDim.x + threadIdx.x;
     if (cv >= n0c * n1c) return;
@@ -479,6 +481,13 @@ __global__ void k_restrict(int n0f, int n1f, int off, const float *__restrict__ 
         }
     }
     b_c[3 * cv] = s0; b_c[3 * cv + 1] = s1; b_c[3 * cv + 2] = s2;
+    if (dinv_c) {
+        float c = coef_c[1];
+        const float *m = dinv_c + 9 * (size_t)cv;
+        float d0 = c * (m[0] * s0 + m[1] * s1 + m[2] * s2), d1 = c * (m[3] * s0 + m[4] * s1 + m[5] * s2), d2 = c * (m[6] * s0 + m[7] * s1 + m[8] * s2);
+        d_c[3 * cv] = d0; d_c[3 * cv + 1] = d1; d_c[3 * cv + 2] = d2;
+        x0_c[3 * cv] = d0; x0_c[3 * cv + 1] = d1; x0_c[3 * cv + 2] = d2;
+    }
 }
 // x_f += P x_c
 __global__ void k_prolong_add(int n0f, int n1f, int off, float *x_f, const int *__restrict__ mask, int n0c, int n1c,
@@ -803,7 +812,7 @@ int mg_setup(tsl_ctx *ctx)
 }
 
 // z = M^-1 b : one V-cycle (or block-Jacobi when precond == 0); acc_bz (optional, device) += b . z
-static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, double *acc)
+static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, double *acc, bool first_done = false)
 {
     MgDev &mg = ctx->mg;
     MgLevel &L = mg.lev[l];
@@ -832,8 +841,10 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
         float *out = (final_k && z_out) ? z_out : L.x[k & 1];
         double *a = final_k ? acc : nullptr;
         if (k == 0) {
-            k_cheb_first<<<GRID(L.nrows, 256), 256, 0, s>>>(L.nrows, L.dinv, b, L.d, out, coef, a);
-            ctx->launches++;
+            if (!first_done) {         // otherwise the producer of b (k_restrict / k_pcg_update) already wrote d and x[0]
+                k_cheb_first<<<GRID(L.nrows, 256), 256, 0, s>>>(L.nrows, L.dinv, b, L.d, out, coef, a);
+                ctx->launches++;
+            }
         } else launch_step(ctx, l, b, cur, L.d, out, coef + 2 * k, a, a ? 1 : 0);
         cur = out;
     }
@@ -845,9 +856,12 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
     else if (L.sv == 1 && mg.pair_threads) k_mg_residual_stencil_t2<<<GRID(2LL * L.nv, 256), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     else if (L.sv == 1) k_mg_residual_stencil_t<<<GRID(L.nv, 128), 128, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     else k_mg_residual_stencil<<<GRID(32LL * L.nv, 256), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
-    k_restrict<<<GRID(C.nv, 128), 128, 0, s>>>(L.n0, L.n1, off, L.r, mask, C.n0, C.n1, C.b);
+    const bool c_last = (l + 1 == mg.n_levels - 1);
+    const bool fuse_first = (l + 1 != mg.tail_level) && ((c_last ? mg.coarse_degree : mg.degree) >= 2);
+    const float *coef_c = mg.coef + (size_t)(l + 1) * TSL_MG_MAX_DEGREE * 2;
+    k_restrict<<<GRID(C.nv, 128), 128, 0, s>>>(L.n0, L.n1, off, L.r, mask, C.n0, C.n1, C.b, fuse_first ? C.dinv : nullptr, C.d, C.x[0], coef_c);
     ctx->launches += 2;
-    float *xc = vcycle_level(ctx, l + 1, C.b, nullptr, nullptr);
+    float *xc = vcycle_level(ctx, l + 1, C.b, nullptr, nullptr, fuse_first);
     k_prolong_add<<<GRID(L.nv, 256), 256, 0, s>>>(L.n0, L.n1, off, cur, mask, C.n0, C.n1, xc);
     ctx->launches++;
     // post-smoothing with the same polynomial (symmetric cycle)
@@ -861,7 +875,15 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
     return cur;
 }
 
-int mg_apply(tsl_ctx *ctx, const float *b, float *z, double *acc_bz)
+// level-0 buffers a producer of the right-hand side may fill with the first Chebyshev step itself (see k_pcg_update)
+void mg_first_step_targets(tsl_ctx *ctx, const float **dinv, float **d, float **x0, const float **coef)
+{
+    MgDev &mg = ctx->mg;
+    bool ok = mg.n_levels > 0 && ctx->precond != 0 && ((mg.n_levels == 1 ? mg.coarse_degree : mg.degree) >= 2);
+    *dinv = ok ? mg.lev[0].dinv : nullptr; *d = ok ? mg.lev[0].d : nullptr; *x0 = ok ? mg.lev[0].x[0] : nullptr; *coef = ok ? mg.coef : nullptr;
+}
+
+int mg_apply(tsl_ctx *ctx, const float *b, float *z, double *acc_bz, bool first_done)
 {
     MgDev &mg = ctx->mg;
     if (mg.n_levels == 0 || ctx->precond == 0) {
@@ -871,7 +893,7 @@ int mg_apply(tsl_ctx *ctx, const float *b, float *z, double *acc_bz)
         ctx->launches++;
         return TSL_OK;
     }
-    vcycle_level(ctx, 0, b, z, acc_bz);
+    vcycle_level(ctx, 0, b, z, acc_bz, first_done);
     CK(cudaGetLastError());
     return TSL_OK;
 }
