@@ -76,7 +76,7 @@ int tsl_destroy(tsl_ctx *ctx)
     tsl::graphs_invalidate(ctx);
     tsl::mg_free(ctx);
     cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->A.val32m); cudaFree(ctx->A.val32t); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
-    cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q); cudaFree(ctx->cg_r32);
+    cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q); cudaFree(ctx->cg_r32); cudaFree(ctx->ncdir);
     for (int i = 0; i < 8; i++) cudaFree(ctx->bi[i]);
     cudaFree(ctx->minv32); cudaFree(ctx->minv64); cudaFree(ctx->F); cudaFree(ctx->sol); cudaFree(ctx->x1);
     for (auto &c : ctx->cloths) {
@@ -380,6 +380,7 @@ int tsl_finalize(tsl_ctx *ctx)
     TRY(mg_alloc(ctx));
     if (const char *e = getenv("TSL_PRECOND")) ctx->precond = atoi(e);
     if (const char *e = getenv("TSL_NEWTON_MODE")) ctx->newton_mode = atoi(e);
+    if (const char *e = getenv("TSL_PROBE")) ctx->probe = atoi(e);
     ctx->finalized = true;
     return TSL_OK;
 }
@@ -517,6 +518,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     const double len_scale = ctx->cloths.empty() ? 1e-3 : ctx->cloths[0].P.dx;
     double eta = 0.1, fnorm_prev = -1;
     double theta = 0.0, theta_used = 0.0;     // newton_mode 2: blend factor of the next / the last solve
+    bool have_ncdir = false;                  // ctx->ncdir holds a direction of negative curvature met in this step
     int skip = 0, back = 0;                   // newton_mode 0: exact attempts skipped after a failure (1, 3, 7, 8, ...)
     int age = refresh_every;                  // iterations since the hierarchy was built (forces a build at it == 1)
     int last_pcg = 0, fresh_pcg = 0;
@@ -575,6 +577,14 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
             if (it == 1) TRY(check_device_flags(ctx));
             t1 = now_ms();
             st.ms_assembly += t1 - t0;
+            if (have_ncdir && ctx->probe) {
+                // curvature probe: the direction of negative curvature met last usually still is one; two matrix passes tell,
+                // for every theta, whether the blend is indefinite along it -- those solves are not attempted
+                double pAe = 0, pAc = 0;
+                TRY(probe_curvature(ctx, ctx->A.val32, ctx->ncdir, &pAe));
+                TRY(probe_curvature(ctx, ctx->A.val32c, ctx->ncdir, &pAc));
+                while (theta < 1.0 && (1.0 - theta) * pAe + theta * pAc <= 0.0) theta = std::min(1.0, std::max(2.0 * theta, 1.0 / 16));
+            }
             while (true) {
                 const float *op = ctx->A.val32;
                 if (theta >= 1.0) op = ctx->A.val32c;
@@ -583,6 +593,8 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
                 st.linear_iters += ss.iters;
                 if (!(ss.flags & 1) || theta >= 1.0) break;
                 st.flags |= 1;
+                CK(cudaMemcpyAsync(ctx->ncdir, ctx->cg_p, sizeof(double) * 3 * (size_t)ctx->n_solve, cudaMemcpyDeviceToDevice, s));
+                have_ncdir = true;
                 theta = std::min(1.0, std::max(2.0 * theta, 1.0 / 16));
             }
             fallback = theta > 0.0;

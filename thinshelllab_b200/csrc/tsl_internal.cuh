@@ -157,6 +157,7 @@ struct tsl_ctx {
     double *F = nullptr;                         // [3 n_verts] residual
     float *minv32 = nullptr; double *minv64 = nullptr;   // [n_verts][9] block-Jacobi inverse
     double *cg_x = nullptr, *cg_r = nullptr, *cg_p = nullptr, *cg_q = nullptr;   // PCG vectors [3 n_rows_pad] (fp64)
+    double *ncdir = nullptr;                     // last direction of negative curvature PCG met (curvature probe, Newton mode 2)
     float *cg_r32 = nullptr, *cg_z = nullptr;     // fp32 copy of r (preconditioner input) and z = M r
     double *bi[8] = { nullptr };                 // BiCGStab vectors: r, rhat, p, v, y, s, z, t
     double *sol = nullptr;                       // [3 n_verts] Newton direction (f64)
@@ -165,6 +166,7 @@ struct tsl_ctx {
                                                  // solve and the multigrid cycle skip them (tsl_finalize)
     tsl::MgDev mg;
     int precond = 1;                             // 0 block-Jacobi, 1 multigrid V-cycle
+    int probe = 1;                               // Newton mode 2: curvature probe before the solves (TSL_PROBE=0 disables)
     int newton_mode = 2;                         // 0 projected-Newton fallback, 1 negative-curvature moves, 2 blended operator
     float *cg_r64tmp = nullptr;                  // [3 n_rows_pad] fp32 staging of fp64 vectors for the V-cycle
     tsl::KrylovScalars *ks = nullptr;            // device

@@ -38,6 +38,7 @@ int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, 
 int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st);
 int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out);
 int precond_apply_f64io(tsl_ctx *ctx, const double *in, double *out);
+int probe_curvature(tsl_ctx *ctx, const float *opval, const double *dir, double *out);
 void graphs_invalidate(tsl_ctx *ctx);
 int mg_setup_replay(tsl_ctx *ctx);   // mg_setup through a captured graph after the first (cold) call
 

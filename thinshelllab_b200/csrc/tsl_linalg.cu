@@ -280,6 +280,7 @@ int linalg_alloc(tsl_ctx *ctx)
     CK(cudaMalloc(&ctx->ks, sizeof(KrylovScalars)));
     CK(cudaMallocHost(&ctx->ks_host, sizeof(KrylovScalars)));
     CK(cudaMalloc(&ctx->sol, sizeof(double) * 3 * (size_t)nr));
+    CK(cudaMalloc(&ctx->ncdir, nbd)); CK(cudaMemset(ctx->ncdir, 0, nbd));
     return TSL_OK;
 }
 
@@ -371,6 +372,20 @@ int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, 
     ctx->ks_host->rr0 = sqrt(rr0);      // |b|_2 for the caller's forcing term
     if (st) { st->iters = it; st->flags = flags; st->rel_residual = rr0 > 0 ? sqrt(rr / rr0) : 0.0; }
     CK(cudaGetLastError());
+    return TSL_OK;
+}
+
+// dir . A dir with the fp32 matrix `opval` (curvature probe of the Newton driver); synchronises
+int probe_curvature(tsl_ctx *ctx, const float *opval, const double *dir, double *out)
+{
+    int n = ctx->n_solve;
+    cudaStream_t s = ctx->stream;
+    CK(cudaMemsetAsync(&ctx->ks->pq, 0, sizeof(double), s));
+    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, opval, dir, ctx->cg_q, &ctx->ks->pq);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(&ctx->ks_host->pq, &ctx->ks->pq, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *out = ctx->ks_host->pq;
     return TSL_OK;
 }
 
