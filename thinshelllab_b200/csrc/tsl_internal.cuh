@@ -166,7 +166,7 @@ struct tsl_ctx {
                                                  // solve and the multigrid cycle skip them (tsl_finalize)
     tsl::MgDev mg;
     int precond = 1;                             // 0 block-Jacobi, 1 multigrid V-cycle
-    int probe = 1;                               // Newton mode 2: curvature probe before the solves (TSL_PROBE=0 disables)
+    int probe = 0;                               // Newton mode 2: curvature probe before the solves (TSL_PROBE=1; measured: no gain)
     int newton_mode = 2;                         // 0 projected-Newton fallback, 1 negative-curvature moves, 2 blended operator
     float *cg_r64tmp = nullptr;                  // [3 n_rows_pad] fp32 staging of fp64 vectors for the V-cycle
     tsl::KrylovScalars *ks = nullptr;            // device
