@@ -169,6 +169,8 @@ def run_ours(args, rank, world):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
     N = args.sheet_n
     s = sheet_scene(N, device=dev, seed=rank)
