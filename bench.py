@@ -23,10 +23,10 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-# NCCL prints its version banner on STDOUT when NCCL_DEBUG=VERSION (set in this image) and caches the variable on first use:
-# override it before torch is imported, so that stdout carries the one JSON line only
-if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-    os.environ["NCCL_DEBUG"] = "WARN"
+# NCCL prints its version banner on STDOUT at NCCL_DEBUG=VERSION (set in this image) and at every higher level: drop the
+# variable (level NONE) before torch is imported, so that stdout carries the one JSON line only
+if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+    del os.environ["NCCL_DEBUG"]
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed ncu --set full capture
@@ -173,8 +173,6 @@ def run_ours(args, rank, world):
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout: keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=torch.device(dev))
     N = args.sheet_n
     s = sheet_scene(N, device=dev, seed=rank)
