@@ -529,6 +529,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         tsl_solve_stats ss;
         double t1;
         bool fallback = false;
+        std::string attempts;                 // trace only: theta:iterations of every solve attempt (x = negative curvature)
         if (ctx->newton_mode == 0) {
             // ---- projected-Newton fallback with back-off (the path closest to the reference's own iteration)
             const bool try_exact = (skip == 0);
@@ -591,6 +592,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
                 else if (theta > 0.0) { launch_blend(ctx, ctx->A.val32, ctx->A.val32c, (float)theta, ctx->A.val32t); op = ctx->A.val32t; }
                 TRY(solve_pcg32(ctx, op, ctx->F, ctx->sol, eta, max_pcg, &ss));
                 st.linear_iters += ss.iters;
+                if (trace) attempts += " " + std::to_string(theta).substr(0, 6) + ":" + std::to_string(ss.iters) + ((ss.flags & 1) ? "x" : "");
                 if (!(ss.flags & 1) || theta >= 1.0) break;
                 st.flags |= 1;
                 CK(cudaMemcpyAsync(ctx->ncdir, ctx->cg_p, sizeof(double) * 3 * (size_t)ctx->n_solve, cudaMemcpyDeviceToDevice, s));
@@ -713,9 +715,9 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         st.ms_linesearch += now_ms() - t2;
         st.delta = p_norm / dt;
         if (trace)
-            fprintf(stderr, "[tsl] newton %3d: %s pcg=%d age=%d |F|=%.3e eta=%.1e delta=%.3e alpha=%.3g E=%.12e nc=%d\n", it,
+            fprintf(stderr, "[tsl] newton %3d: %s pcg=%d age=%d |F|=%.3e eta=%.1e delta=%.3e alpha=%.3g E=%.12e nc=%d%s\n", it,
                     fallback ? (ctx->newton_mode == 2 ? (std::string("theta=") + std::to_string(theta_used)).c_str() : "clamped-fallback") : "exact", ss.iters, age,
-                    fnorm, eta_used, st.delta, alpha, E, ctx->nc);
+                    fnorm, eta_used, st.delta, alpha, E, ctx->nc, attempts.c_str());
         E0 = E;                               // the reference re-evaluates the same point at the top of the loop
         if (st.delta < tol) { st.converged = 1; break; }
     }
