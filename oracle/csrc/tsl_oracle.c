@@ -1362,6 +1362,236 @@ double orc_vertex_energy(int v_start, int v_end, const double *pos, const double
     return U;
 }
 
+/* ------------------------------------------------------------------ tetrahedral bodies
+ * kind 0: Elastic "box" model (engine/model_elastic_offset.py): neo-Hookean, P = mu (F - F^-T) + lam log(J) F^-T, J = max(det F, 0.01)
+ * kind 1: Elastic "tactile" model (engine/model_elastic_tactile.py): P = mu F + lam (J - alpha) J F^-T
+ * All arrays body-local: pos [nv][3], tets [nc][4], B [nc][3][3] = inverse rest Ds, W [nc] rest volume, m [nv] lumped mass. */
+typedef struct {
+    int kind, nv, nc;
+    const int *tets;
+    const double *B, *W, *m;
+    double mu, lam, alpha, dt;
+    const double *gravity;   /* [3] */
+    const double *ext;       /* [nv][3] or NULL */
+} orc_tets;
+
+orc_tets *orc_tets_create(int kind, int nv, int nc, const int *tets, const double *B, const double *W, const double *m,
+                          double mu, double lam, double alpha, double dt, const double *gravity, const double *ext)
+{
+    orc_tets *t = (orc_tets *)calloc(1, sizeof(orc_tets));
+    t->kind = kind; t->nv = nv; t->nc = nc; t->tets = tets; t->B = B; t->W = W; t->m = m;
+    t->mu = mu; t->lam = lam; t->alpha = alpha; t->dt = dt; t->gravity = gravity; t->ext = ext;
+    return t;
+}
+void orc_tets_destroy(orc_tets *t) { free(t); }
+
+static void m3_mul(const double *a, const double *b, double *o)          /* o = a b */
+{
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+static void m3_mul_bt(const double *a, const double *b, double *o)       /* o = a b^T */
+{
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) o[3 * i + j] = a[3 * i] * b[3 * j] + a[3 * i + 1] * b[3 * j + 1] + a[3 * i + 2] * b[3 * j + 2];
+}
+static double m3_det(const double *a)
+{
+    return a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+}
+static void m3_inv(const double *a, double *o)
+{
+    double id = 1.0 / m3_det(a);
+    o[0] = (a[4] * a[8] - a[5] * a[7]) * id; o[1] = (a[2] * a[7] - a[1] * a[8]) * id; o[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    o[3] = (a[5] * a[6] - a[3] * a[8]) * id; o[4] = (a[0] * a[8] - a[2] * a[6]) * id; o[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    o[6] = (a[3] * a[7] - a[4] * a[6]) * id; o[7] = (a[1] * a[6] - a[0] * a[7]) * id; o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+/* Elastic.Ds (model_elastic_offset.py:169-171): columns x_i - x_3 */
+static void tet_Ds(const double *pos, const int *v, double *D)
+{
+    for (int i = 0; i < 3; i++) for (int r = 0; r < 3; r++) D[3 * r + i] = pos[3 * v[i] + r] - pos[3 * v[3] + r];
+}
+/* Elastic.init_pos (model_elastic_offset.py:240-253, model_elastic_tactile.py:215-229): B = Ds^-1, W = |det Ds| / 6, lumped mass */
+void orc_tets_rest(int nv, int nc, const int *tets, const double *rest, double density, double *B, double *W, double *m)
+{
+    for (int i = 0; i < nv; i++) m[i] = 0;
+    for (int c = 0; c < nc; c++) {
+        double D[9];
+        tet_Ds(rest, tets + 4 * c, D);
+        m3_inv(D, B + 9 * c);
+        W[c] = fabs(m3_det(D)) / 6;
+        for (int i = 0; i < 4; i++) m[tets[4 * c + i]] += W[c] / 4 * density;
+    }
+}
+/* first Piola stress of one cell; returns J as used by the model */
+static void tet_P(const orc_tets *t, const double *F, double *P)
+{
+    double Fi[9], FiT[9];
+    m3_inv(F, Fi);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) FiT[3 * i + j] = Fi[3 * j + i];
+    double J = m3_det(F);
+    if (t->kind == 0) {
+        if (J < 0.01) J = 0.01;
+        double lj = log(J);
+        for (int q = 0; q < 9; q++) P[q] = t->mu * (F[q] - FiT[q]) + t->lam * lj * FiT[q];
+    } else {
+        for (int q = 0; q < 9; q++) P[q] = t->mu * F[q] + t->lam * (J - t->alpha) * J * FiT[q];
+    }
+}
+/* Elastic.compute_energy (model_elastic_offset.py:315-332, model_elastic_tactile.py:184-201) */
+double orc_tets_energy(const orc_tets *t, const double *pos, const double *prev, const double *vel)
+{
+    double U = 0;
+    for (int c = 0; c < t->nv; c++) {
+        U += -t->m[c] * v_dot(t->gravity, pos + 3 * c);
+        if (t->ext) U += -v_dot(t->ext + 3 * c, pos + 3 * c);
+    }
+    for (int c = 0; c < t->nv; c++) {
+        double X[3];
+        for (int j = 0; j < 3; j++) X[j] = pos[3 * c + j] - prev[3 * c + j] - vel[3 * c + j] * t->dt;
+        U += 0.5 * t->m[c] * v_dot(X, X) / (t->dt * t->dt);
+    }
+    for (int c = 0; c < t->nc; c++) {
+        double D[9], F[9];
+        tet_Ds(pos, t->tets + 4 * c, D);
+        m3_mul(D, t->B + 9 * c, F);
+        double J = m3_det(F), I = 0, phi;
+        for (int q = 0; q < 9; q++) I += F[q] * F[q];
+        if (t->kind == 0) {
+            double lj = log(J > 0.01 ? J : 0.01);
+            phi = t->mu / 2 * (I - 3) - t->mu * lj + t->lam / 2 * lj * lj;
+        } else {
+            phi = t->mu / 2 * (I - 3) + t->lam / 2 * (J - t->alpha) * (J - t->alpha);
+        }
+        U += t->W[c] * phi;
+    }
+    return U;
+}
+/* Elastic.get_force (model_elastic_offset.py:187-208, model_elastic_tactile.py:158-174): F_f [nv][3] */
+void orc_tets_force(const orc_tets *t, const double *pos, double *F_f)
+{
+    for (int i = 0; i < 3 * t->nv; i++) F_f[i] = 0;
+    for (int c = 0; c < t->nc; c++) {
+        const int *v = t->tets + 4 * c;
+        double D[9], F[9], P[9], H[9];
+        tet_Ds(pos, v, D);
+        m3_mul(D, t->B + 9 * c, F);
+        tet_P(t, F, P);
+        m3_mul_bt(P, t->B + 9 * c, H);
+        for (int q = 0; q < 9; q++) H[q] *= -t->W[c];
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) { F_f[3 * v[i] + j] += H[3 * j + i]; F_f[3 * v[3] + j] -= H[3 * j + i]; }
+    }
+    for (int u = 0; u < t->nv; u++)
+        for (int j = 0; j < 3; j++) {
+            F_f[3 * u + j] += t->gravity[j] * t->m[u];
+            if (t->ext) F_f[3 * u + j] += t->ext[3 * u + j];
+        }
+}
+/* Elastic.compute_residual (model_elastic_offset.py:210-213): F_b = m (x - x_prev - v dt) / dt^2 - F_f */
+void orc_tets_residual(const orc_tets *t, const double *pos, const double *prev, const double *vel, double *F_b)
+{
+    orc_tets_force(t, pos, F_b);
+    for (int i = 0; i < t->nv; i++)
+        for (int j = 0; j < 3; j++)
+            F_b[3 * i + j] = t->m[i] * (pos[3 * i + j] - prev[3 * i + j] - vel[3 * i + j] * t->dt) / (t->dt * t->dt) - F_b[3 * i + j];
+}
+/* reduced 9x9 energy Hessian of one cell over (vertex n < 3, dim): H9[(n,dim)][(i,j)] = d f_{i,j} / d x_{n,dim} sign-flipped
+ * (model_elastic_tactile.py:96-113; the box model's dP_dFij sum, model_elastic_offset.py:118-147, contracted the same way) */
+static void tet_H9(const orc_tets *t, int c, const double *pos, double H9[9][9])
+{
+    const double *B = t->B + 9 * c;
+    double D[9], F[9], Fi[9], FiT[9];
+    tet_Ds(pos, t->tets + 4 * c, D);
+    m3_mul(D, B, F);
+    m3_inv(F, Fi);
+    for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) FiT[3 * i + j] = Fi[3 * j + i];
+    double J = m3_det(F);
+    if (t->kind == 0 && J < 0.01) J = 0.01;
+    for (int n = 0; n < 3; n++)
+        for (int dim = 0; dim < 3; dim++) {
+            double dD[9] = { 0 }, dF[9], dFT[9], dP[9], tmp[9], tmp2[9], dH[9];
+            dD[3 * dim + n] = 1;
+            m3_mul(dD, B, dF);
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) dFT[3 * i + j] = dF[3 * j + i];
+            m3_mul(Fi, dF, tmp);
+            double dTr = tmp[0] + tmp[4] + tmp[8];
+            m3_mul(FiT, dFT, tmp); m3_mul(tmp, FiT, tmp2);      /* F^-T dF^T F^-T */
+            if (t->kind == 0) {
+                double lj = log(J);
+                for (int q = 0; q < 9; q++) dP[q] = t->mu * dF[q] + (t->mu - t->lam * lj) * tmp2[q] + t->lam * dTr * FiT[q];
+            } else {
+                for (int q = 0; q < 9; q++)
+                    dP[q] = t->mu * dF[q] + t->lam * 2 * J * J * dTr * FiT[q] - t->lam * t->alpha * J * dTr * FiT[q]
+                            - t->lam * (J - t->alpha) * J * tmp2[q];
+            }
+            m3_mul_bt(dP, B, dH);
+            for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) H9[n * 3 + dim][i * 3 + j] = t->W[c] * dH[3 * j + i];
+        }
+}
+/* Elastic.compute_Hessian (model_elastic_offset.py:95-167 / model_elastic_tactile.py:82-124): mass diagonal (unmasked) +
+ * element blocks through add_H.  The box model ignores spd (no projection in the reference); its 12x12 scatter
+ * (rows = force on vertex j, cols = perturbed (n, dim), 4th vertex by minus sums) equals the 9x9 expansion below because
+ * dD of vertex 3 is minus the sum of the others. */
+void orc_tets_hessian(const orc_tets *t, const double *pos, int offset, orc_mat *A, int spd)
+{
+    for (int i = 0; i < t->nv; i++)
+        for (int j = 0; j < 3; j++) mat_add_raw(A, 3 * (i + offset) + j, 3 * (i + offset) + j, t->m[i] / (t->dt * t->dt));
+    for (int c = 0; c < t->nc; c++) {
+        double H9[9][9];
+        tet_H9(t, c, pos, H9);
+        if (spd && t->kind == 1) orc_spd_project(&H9[0][0], 9, 20);
+        int idx[4];
+        for (int q = 0; q < 4; q++) idx[q] = t->tets[4 * c + q] + offset;
+        if (t->kind == 1) {
+            for (int j = 0; j < 3; j++) for (int k = 0; k < 3; k++)
+                for (int j2 = 0; j2 < 3; j2++) for (int k2 = 0; k2 < 3; k2++) {
+                    double h = H9[k * 3 + j][k2 * 3 + j2];
+                    add_H(A, idx[k] * 3 + j, idx[k2] * 3 + j2, h);
+                    add_H(A, idx[k] * 3 + j, idx[3] * 3 + j2, -h);
+                    add_H(A, idx[3] * 3 + j, idx[k2] * 3 + j2, -h);
+                    add_H(A, idx[3] * 3 + j, idx[3] * 3 + j2, h);
+                }
+        } else {
+            /* row (force on vertex j, comp r), column (perturbed vertex n, dim): -dH[n,dim][r][j] = H9[(n,dim)][(j,r)] */
+            for (int n = 0; n < 4; n++) for (int dim = 0; dim < 3; dim++) {
+                int ind = idx[n] * 3 + dim;
+                double col[9];   /* col[(j,r)] for j < 3 */
+                for (int q = 0; q < 9; q++) {
+                    if (n < 3) col[q] = H9[n * 3 + dim][q];
+                    else col[q] = -(H9[0 * 3 + dim][q] + H9[1 * 3 + dim][q] + H9[2 * 3 + dim][q]);
+                }
+                for (int j = 0; j < 3; j++) for (int r = 0; r < 3; r++) add_H(A, idx[j] * 3 + r, ind, col[j * 3 + r]);
+                for (int r = 0; r < 3; r++) add_H(A, idx[3] * 3 + r, ind, -(col[0 * 3 + r] + col[1 * 3 + r] + col[2 * 3 + r]));
+            }
+        }
+    }
+}
+/* Elastic.compute_deri (model_elastic_offset.py:423-438 / model_elastic_tactile.py:329-347): d_mu, d_lam [nv][3], accumulated */
+void orc_tets_deri(const orc_tets *t, const double *pos, double *d_mu, double *d_lam)
+{
+    for (int c = 0; c < t->nc; c++) {
+        const int *v = t->tets + 4 * c;
+        double D[9], F[9], Fi[9], FiT[9], P1[9], P2[9], H1[9], H2[9];
+        tet_Ds(pos, v, D);
+        m3_mul(D, t->B + 9 * c, F);
+        m3_inv(F, Fi);
+        for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) FiT[3 * i + j] = Fi[3 * j + i];
+        double J = m3_det(F);
+        if (t->kind == 0) {
+            if (J < 0.01) J = 0.01;
+            for (int q = 0; q < 9; q++) { P1[q] = t->mu * (F[q] - FiT[q]); P2[q] = t->lam * log(J) * FiT[q]; }
+        } else {
+            for (int q = 0; q < 9; q++) { P1[q] = t->mu * (F[q] - J * FiT[q]); P2[q] = t->lam * (J - 1) * J * FiT[q]; }
+        }
+        m3_mul_bt(P1, t->B + 9 * c, H1); m3_mul_bt(P2, t->B + 9 * c, H2);
+        for (int i = 0; i < 3; i++)
+            for (int j = 0; j < 3; j++) {
+                double f1 = -t->W[c] * H1[3 * j + i] / t->mu, f2 = -t->W[c] * H2[3 * j + i] / t->lam;
+                d_mu[3 * v[i] + j] += f1; d_mu[3 * v[3] + j] -= f1;
+                d_lam[3 * v[i] + j] += f2; d_lam[3 * v[3] + j] -= f2;
+            }
+    }
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

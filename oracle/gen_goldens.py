@@ -147,6 +147,57 @@ def gen_spd():
     print("wrote spd_projector")
 
 
+def tet_case(name, kind, seed):
+    """term-by-term goldens of a tet body: model_elastic_tactile.Elastic (kind 'tactile') or
+    model_elastic_offset.Elastic (kind 'box')"""
+    rng = np.random.default_rng(seed)
+    dt = 5e-3
+    if kind == "tactile":
+        from thinshelllab.engine.model_elastic_tactile import Elastic
+        e = Elastic(dt, 0, 0.5)
+        e.init(0.01, -0.002, 0.03, True)
+        par = dict(mu=e.mu[None], lam=e.lam[None], alpha=e.alpha[None])
+        amp = 0.03
+    else:
+        from thinshelllab.engine.model_elastic_offset import Elastic
+        e = Elastic(dt, 0.03, 0, 4, 3, 3)
+        e.init(-0.01, 0.0, 0.002)
+        par = dict(mu=e.mu[None], lam=e.lam[None], alpha=0.0)
+        e.lam[None] = 1.5e5    # the reference default nu = 0 gives lam = 0: exercise the lam terms too
+        par["lam"] = 1.5e5
+        amp = 0.06
+    e.gravity[None] = ti.Vector([0.3, -0.2, -9.8])
+    rest = e.F_x.to_numpy()
+    tets = e.F_vertices.to_numpy()
+    edge = np.linalg.norm(rest[tets[:, 0]] - rest[tets[:, 1]], axis=1).mean()
+    pos = rest + rng.uniform(-amp * edge, amp * edge, rest.shape)
+    prev = pos + rng.uniform(-0.01 * edge, 0.01 * edge, rest.shape)
+    vel = rng.uniform(-0.05, 0.05, rest.shape)
+    ext = rng.uniform(-1e-3, 1e-3, rest.shape)
+    e.F_x.from_numpy(pos); e.F_x_prev.from_numpy(prev); e.F_v.from_numpy(vel); e.ext_force.from_numpy(ext)
+    out = dict(kind=kind, dt=dt, rest=rest, tets=tets, f2v=e.f2v.to_numpy(), F_B=e.F_B.to_numpy(), F_W=e.F_W.to_numpy(),
+               F_m=e.F_m.to_numpy(), pos=pos, prev_pos=prev, vel=vel, ext_force=ext, gravity=e.gravity.to_numpy(),
+               density=e.density, **par)
+    if kind == "tactile":
+        out["F_ox"] = e.F_ox.to_numpy(); out["ratio"] = e.ratio; out["is_surface"] = e.is_surface.to_numpy()
+    e.compute_energy(); out["U"] = e.U[None]
+    e.get_force(); out["F_f"] = e.F_f.to_numpy()
+    e.compute_residual(); out["F_b"] = e.F_b.to_numpy()
+    n = 3 * e.n_verts
+    for spd in (0, 1):
+        r = _Rec(n); e.compute_Hessian(r, spd); out[f"H_spd{spd}"] = r.M
+    e.d_mu.fill(0); e.d_lam.fill(0)
+    e.compute_deri()
+    out["d_mu"] = e.d_mu.to_numpy(); out["d_lam"] = e.d_lam.to_numpy()
+    np.savez_compressed(os.path.join(OUT, f"tet_{name}.npz"), **out)
+    print("wrote tet", name, "U", out["U"], "nverts", e.n_verts, "ncells", e.n_cells, flush=True)
+
+
+def gen_tets():
+    tet_case("box_4x3x3", "box", 21)
+    tet_case("tactile", "tactile", 22)
+
+
 def _csr_of(sysm):
     """dense-backed SparseMatrix -> scipy CSR (code/engine/sparse_solver.py:13-17)"""
     import scipy.sparse as sp
@@ -268,11 +319,136 @@ def gen_bouncing(T=4, use_reset=False, tag="bouncing"):
     print("wrote", tag)
 
 
+def gen_folding(T=3, tag="folding"):
+    """config 0: Scene_folding forward rollout + trajectory adjoint, following training/trajopt_folding.py:50-133
+    (cloth 15x3 + frozen table + tactile pad on a kinematic gripper)"""
+    import scipy.sparse as sp
+    from thinshelllab.task_scene.Scene_folding import Scene
+    from thinshelllab.engine.geometry import projection_query
+    from thinshelllab.engine.analytic_grad_single import Grad
+    from thinshelllab.agent.traj_opt_single import agent_trajopt
+    from cupyx.scipy.sparse import linalg as fake_linalg
+    s = Scene(cloth_size=0.1)
+    s.device = "cpu"; s.H.device = "cpu"
+    s.cloths[0].Kb[None] = 400.0
+    g = Grad(s, T, s.elastic_cnt - 1)
+    agent = agent_trajopt(T, s.elastic_cnt - 1, max_moving_dist=0.001)
+    s.init_all()
+    g.init_mass(s)
+    s.reset()
+    s.mu_cloth_elastic[None] = 5.0
+    traj = np.zeros((T, s.elastic_cnt - 1, 6))
+    for i in range(1, T):
+        traj[i, 0] = [2e-4 * i, -1e-4 * i, -4e-4 * i, 2e-3 * i, 1e-2 * i, -3e-3 * i]
+    agent.traj.from_numpy(traj)
+    pad = s.elastics[1]
+    out = dict(T=T, dt=s.dt, k_contact=s.k_contact, eps_contact=s.eps_contact, eps_v=s.eps_v, mu=5.0, Kb=400.0,
+               k_angle=s.cloths[0].k_angle[None], cloth_N=s.cloths[0].N, cloth_M=s.cloths[0].M, cloth_dx=s.cloths[0].dx,
+               cloth_mass=s.cloths[0].mass, cloth_size=0.1, traj=traj,
+               pos0=s.pos.to_numpy(), vel0=s.vel.to_numpy(), mass=s.mass.to_numpy(), frozen=s.frozen.to_numpy(),
+               faces=s.faces.to_numpy(), ref_angle0=s.cloths[0].ref_angle.to_numpy(), border_flag=s.border_flag.to_numpy(),
+               gravity=s.gravity.to_numpy(),
+               table_tets=s.elastics[0].F_vertices.to_numpy(), table_offset=s.elastics[0].offset, table_nverts=s.elastics[0].n_verts,
+               pad_tets=pad.F_vertices.to_numpy(), pad_offset=pad.offset, pad_nverts=pad.n_verts, pad_F_ox=pad.F_ox.to_numpy(),
+               pad_ratio=pad.ratio, pad_f2v=pad.f2v.to_numpy(), pad_is_surface=pad.is_surface.to_numpy(),
+               pad_F_B=pad.F_B.to_numpy(), pad_F_W=pad.F_W.to_numpy(), pad_mu=pad.mu[None], pad_lam=pad.lam[None],
+               pad_alpha=pad.alpha[None], pad_gravity=pad.gravity.to_numpy(), table_gravity=s.elastics[0].gravity.to_numpy(),
+               table_mu=s.elastics[0].mu[None], table_lam=s.elastics[0].lam[None],
+               gripper_pos0=s.gripper.pos.to_numpy(), gripper_rot0=s.gripper.rot.to_numpy(), gripper_F_x=s.gripper.F_x.to_numpy(),
+               gripper_bound_idx=s.gripper.bound_idx.to_numpy(),
+               body_v=np.array([[b.v_start, b.v_end] for b in s.body_list]),
+               body_f=np.array([[b.f_start, b.f_end] for b in s.body_list]))
+    g.copy_pos(s, 0)
+    t0 = time.time()
+    for frame in range(1, T):
+        agent.get_action(frame)
+        s.action(frame, agent.delta_pos, agent.delta_rot)
+        out[f"f{frame}_pos_after_action"] = s.pos.to_numpy()
+        out[f"f{frame}_gripper_pos"] = s.gripper.pos.to_numpy()
+        out[f"f{frame}_gripper_rot"] = s.gripper.rot.to_numpy()
+        out[f"f{frame}_gripper_rotmat"] = s.gripper.rotmat.to_numpy()
+        # instrumented copy of Scene_folding.time_step (code/task_scene/Scene_folding.py:275-321): same calls, same order
+        s.timestep_init()
+        s.calc_vn()
+        projection_query(s)
+        s.contact_analysis()
+        nc = s.nc[None]
+        out[f"f{frame}_nc"] = nc
+        out[f"f{frame}_proj_flag"] = s.proj_flag.to_numpy()
+        out[f"f{frame}_proj_dir"] = s.proj_dir.to_numpy()
+        out[f"f{frame}_proj_idx"] = s.proj_idx.to_numpy()
+        out[f"f{frame}_proj_w"] = s.proj_w.to_numpy()
+        for k in ("const_idx", "const_w", "const_k", "const_mu", "const_dx0", "const_T", "const_n"):
+            out[f"f{frame}_{k}"] = getattr(s, k).to_numpy()[:nc]
+        it = 0
+        log = []
+        while it < 50:
+            it += 1
+            s.newton_step_init()
+            s.compute_energy()
+            E0 = s.E[None]
+            s.compute_residual_and_Hessian(False, it, spd=True)
+            if it <= 1:
+                H = _csr_of(s.H)
+                out[f"f{frame}_it{it}_H_data"] = H.data
+                out[f"f{frame}_it{it}_H_indices"] = H.indices
+                out[f"f{frame}_it{it}_H_indptr"] = H.indptr
+                out[f"f{frame}_it{it}_F"] = s.F.to_numpy()
+                out[f"f{frame}_it{it}_pos"] = s.pos.to_numpy()
+                out[f"f{frame}_it{it}_E0"] = E0
+            delta, alpha = s.newton_step(it)
+            log.append((E0, delta, alpha, s.E[None]))
+            print(f"frame {frame} it {it} E0 {E0:.10e} delta {delta:.3e} alpha {alpha} nc {nc} t {time.time()-t0:.0f}s", flush=True)
+            if delta < 1e-7:
+                break
+        s.timestep_finish()
+        out[f"f{frame}_newton_log"] = np.array(log)
+        out[f"f{frame}_pos"] = s.pos.to_numpy()
+        out[f"f{frame}_vel"] = s.vel.to_numpy()
+        out[f"f{frame}_ref_angle"] = s.cloths[0].ref_angle.to_numpy()
+        g.copy_pos(s, frame)
+        np.savez_compressed(os.path.join(OUT, f"{tag}_partial.npz"), **out)
+    out["reward"] = s.compute_reward(1.0, -1.0)
+    g.get_loss_fold(s, 1.0, -1.0)
+    # a position loss on the last frame as well, so that the adjoint right-hand side is not almost empty
+    pg = g.pos_grad.to_numpy()
+    NVc = s.cloths[0].NV
+    pg[T - 1, :NVc, 2] = 1.0
+    g.pos_grad.from_numpy(pg)
+    out["pos_grad_seed"] = g.pos_grad.to_numpy()
+    out["angleref_grad_seed"] = g.angleref_grad.to_numpy()
+    for j in range(T - 1, 0, -1):
+        g.transfer_grad(j, s, projection_query)
+        out[f"b{j}_z"] = fake_linalg.LAST_SOLVE["x"].copy()
+        out[f"b{j}_rhs"] = fake_linalg.LAST_SOLVE["b"].copy()
+        Hb = sp.csr_matrix(fake_linalg.LAST_SOLVE["H"])
+        out[f"b{j}_H_data"], out[f"b{j}_H_indices"], out[f"b{j}_H_indptr"] = Hb.data, Hb.indices, Hb.indptr
+        out[f"b{j}_nc"] = s.nc[None]
+        out[f"b{j}_const_idx"] = s.const_idx.to_numpy()[:s.nc[None]]
+        out[f"b{j}_pos_grad"] = g.pos_grad.to_numpy()
+        out[f"b{j}_angleref_grad"] = g.angleref_grad.to_numpy()
+        out[f"b{j}_tmp_z_frozen"] = s.tmp_z_frozen.to_numpy()
+        out[f"b{j}_gripper_grad"] = g.gripper_grad.to_numpy()
+        print(f"backward {j} gripper_grad {g.gripper_grad.to_numpy()[j]} t {time.time()-t0:.0f}s", flush=True)
+    out["gripper_grad"] = g.gripper_grad.to_numpy()
+    out["pos_buffer"] = g.pos_buffer.to_numpy()
+    out["ref_angle_buffer"] = g.ref_angle_buffer.to_numpy()
+    out["gripper_pos_buffer"] = g.gripper_pos_buffer.to_numpy()
+    out["gripper_rot_buffer"] = g.gripper_rot_buffer.to_numpy()
+    np.savez_compressed(os.path.join(OUT, f"{tag}.npz"), **out)
+    os.remove(os.path.join(OUT, f"{tag}_partial.npz"))
+    print("wrote", tag)
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["cloth", "spd"]
     if "cloth" in what:
         gen_cloth()
     if "spd" in what:
         gen_spd()
+    if "tets" in what:
+        gen_tets()
     if "bouncing" in what:
         gen_bouncing()
+    if "folding" in what:
+        gen_folding()

@@ -46,6 +46,8 @@ def lib():
         L.orc_cloth_energy.restype = C.c_double
         L.orc_contact_energy.restype = C.c_double
         L.orc_vertex_energy.restype = C.c_double
+        L.orc_tets_create.restype = C.c_void_p
+        L.orc_tets_energy.restype = C.c_double
         _LIB = L
     return _LIB
 
@@ -62,6 +64,54 @@ def _i(a):
 
 def _f(x):
     return C.c_double(float(x))
+
+
+# ----------------------------------------------------------------------------- tetrahedral bodies
+TET_BOX, TET_TACTILE = 0, 1
+
+
+class Tets:
+    """one Elastic body of the reference: kind TET_BOX (engine/model_elastic_offset.py) or TET_TACTILE
+    (engine/model_elastic_tactile.py); arrays are body-local"""
+
+    def __init__(self, kind, rest, tets, density, mu, lam, alpha, dt, gravity, ext=None):
+        L = lib()
+        self.kind = kind
+        self.rest = np.ascontiguousarray(rest, np.float64)
+        self.tets = np.ascontiguousarray(tets, np.int32)
+        self.nv, self.nc = self.rest.shape[0], self.tets.shape[0]
+        self.B = np.zeros((self.nc, 3, 3)); self.W = np.zeros(self.nc); self.m = np.zeros(self.nv)
+        L.orc_tets_rest(self.nv, self.nc, _i(self.tets), _d(self.rest), _f(density), _d(self.B), _d(self.W), _d(self.m))
+        self.gravity = np.ascontiguousarray(gravity, np.float64)
+        self.ext = None if ext is None else np.ascontiguousarray(ext, np.float64)
+        self.mu, self.lam, self.alpha, self.dt = float(mu), float(lam), float(alpha), float(dt)
+        self._make()
+
+    def _make(self):
+        L = lib()
+        self.h = C.c_void_p(L.orc_tets_create(self.kind, self.nv, self.nc, _i(self.tets), _d(self.B), _d(self.W), _d(self.m),
+                                              _f(self.mu), _f(self.lam), _f(self.alpha), _f(self.dt), _d(self.gravity),
+                                              _d(self.ext) if self.ext is not None else None))
+
+    def set_params(self, mu, lam):
+        lib().orc_tets_destroy(self.h)
+        self.mu, self.lam = float(mu), float(lam)
+        self._make()
+
+    def energy(self, pos, prev, vel):
+        return lib().orc_tets_energy(self.h, _d(pos), _d(prev), _d(vel))
+
+    def force(self, pos):
+        F = np.zeros((self.nv, 3)); lib().orc_tets_force(self.h, _d(pos), _d(F)); return F
+
+    def residual(self, pos, prev, vel):
+        F = np.zeros((self.nv, 3)); lib().orc_tets_residual(self.h, _d(pos), _d(prev), _d(vel), _d(F)); return F
+
+    def hessian(self, pos, offset, mat, spd):
+        lib().orc_tets_hessian(self.h, _d(pos), int(offset), mat, int(spd))
+
+    def deri(self, pos):
+        a = np.zeros((self.nv, 3)); b = np.zeros((self.nv, 3)); lib().orc_tets_deri(self.h, _d(pos), _d(a), _d(b)); return a, b
 
 
 # ----------------------------------------------------------------------------- meshers

@@ -259,3 +259,29 @@ def test_scene_adjoint_matches_reference(golden_dir):
         assert abs(gr.grad_kb - float(g[f"b{j}_grad_kb"])) <= 1e-8 * abs(float(g[f"b{j}_grad_kb"]))
     L.orc_cloth_set_neg_override(s.cloth, None)
     assert abs(gr.grad_kb - float(g["grad_kb"])) <= 1e-8 * abs(float(g["grad_kb"]))
+
+
+@pytest.mark.parametrize("name", ["box_4x3x3", "tactile"])
+def test_tet_terms_match_reference(golden_dir, name):
+    """Elastic.compute_energy / get_force / compute_residual / compute_Hessian / compute_deri of both tet models
+    (engine/model_elastic_offset.py, engine/model_elastic_tactile.py) against the emulated reference run"""
+    g = np.load(os.path.join(golden_dir, f"tet_{name}.npz"))
+    kind = orc.TET_TACTILE if str(g["kind"]) == "tactile" else orc.TET_BOX
+    t = orc.Tets(kind, g["rest"], g["tets"], float(g["density"]), g["mu"], g["lam"], g["alpha"], g["dt"], g["gravity"], g["ext_force"])
+    assert _rel(t.B, g["F_B"]) < 1e-12 and _rel(t.W, g["F_W"]) < 1e-12 and _rel(t.m, g["F_m"]) < 1e-12
+    pos = np.ascontiguousarray(g["pos"]); prev = np.ascontiguousarray(g["prev_pos"]); vel = np.ascontiguousarray(g["vel"])
+    U = t.energy(pos, prev, vel)
+    assert abs(U - g["U"]) <= 1e-12 * abs(g["U"])
+    assert _rel(t.force(pos), g["F_f"]) < 1e-12
+    assert _rel(t.residual(pos, prev, vel), g["F_b"]) < 1e-12
+    for spd in (0, 1):
+        mat, val, dense, keep = _dense_mat(t.nv)
+        t.hessian(pos, 0, mat, spd)
+        assert orc.lib().orc_mat_missing(mat) == 0
+        ref = g[f"H_spd{spd}"]
+        assert np.abs(dense() - ref).max() <= 1e-9 * np.abs(ref).max(), spd
+    if kind == orc.TET_BOX:
+        # the reference's box model has no projection: spd is ignored
+        assert np.array_equal(g["H_spd0"], g["H_spd1"])
+    d_mu, d_lam = t.deri(pos)
+    assert _rel(d_mu, g["d_mu"]) < 1e-12 and _rel(d_lam, g["d_lam"]) < 1e-12
