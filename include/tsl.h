@@ -79,6 +79,16 @@ int tsl_set_cloth_params(tsl_ctx *ctx, int cloth, double Kl, double Ka, double K
 /* topology read-back for tests / renderers: Cloth.f2v, counter_face, counter_point ([2NM][3] i32, host) */
 int tsl_get_cloth_topology(tsl_ctx *ctx, int cloth, int *f2v_host, int *counter_face_host, int *counter_point_host);
 
+/* Elastic bodies: the neo-Hookean box (kind 0; code/engine/model_elastic_offset.py:11-93, init_pos :240-253) and the tactile pad / ball
+ * (kind 1; code/engine/model_elastic_tactile.py:13-80, init_pos :215-229).  tets_host [n_cells][4] body-local vertex ids
+ * (Elastic.F_vertices), B_host [n_cells][3][3] = F_B (inverse rest Ds), W_host [n_cells] = F_W (rest volume); mu, lam, alpha as the
+ * reference's fields; gravity_host [3] = Elastic.gravity (NULL: the scene's; effector pads carry none, BaseScene.py:371-374).
+ * Vertex masses come from the bound mass array.  Returns the body id (>= 0). */
+int tsl_add_tets(tsl_ctx *ctx, int kind, int v_offset, int n_verts, int n_cells, const int *tets_host, const double *B_host,
+                 const double *W_host, double mu, double lam, double alpha, const double *gravity_host);
+/* Elastic.mu / lam [None] = ... */
+int tsl_set_tet_params(tsl_ctx *ctx, int body, double mu, double lam);
+
 /* BaseScene.faces + body_list (code/engine/BaseScene.py:81,91-99, init_faces :355-359):
  * faces_host [tot_nf][3] global vertex ids, bodies_host [n_bodies][4] = v_start, v_end, f_start, f_end. */
 int tsl_set_surfaces(tsl_ctx *ctx, const int *faces_host, int tot_nf, const int *bodies_host, int n_bodies);
@@ -141,11 +151,37 @@ int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, cons
                       double *grad_kb_accum_dev, double *z_out_dev, double clamp, double rel_tol, int max_iters,
                       tsl_solve_stats *stats);
 
+/* Grad.transfer_grad of the trajectory optimiser (code/engine/analytic_grad_single.py:217-255): tsl_step_backward plus
+ *   z_frozen_out_dev [3 n_verts]  BaseScene.tmp_z_frozen of the second, "counting" assembly (code/engine/BaseScene.py:399-405;
+ *                                 analytic_grad_single.py:240-243); may be NULL
+ * and grad_kb_accum_dev may be NULL (no system-ID gradient). */
+int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, const double *ref_angle_tm1,
+                         double *pos_grad_t, double *pos_grad_tm1, double *pos_grad_tm2,
+                         const double *angleref_grad_t, double *angleref_grad_tm1,
+                         double *grad_kb_accum_dev, double *z_out_dev, double *z_frozen_out_dev, double clamp, double rel_tol,
+                         int max_iters, tsl_solve_stats *stats);
+
+/* Kinematic boundary of a pad (code/engine/gripper_single.py): gripper.get_vert_pos + update_bound + the scene's pushup
+ * (:79-83, 157-161; Scene_folding.action, code/task_scene/Scene_folding.py:213-224) for the n_bound driven vertices of the body at
+ * v_offset: pos[v_offset + bound_idx[i]] = p + R F_x[bound_idx[i]].  bound_idx_dev [n_bound] i32, Fx_dev [body verts][3] f64 (device),
+ * pos3_host [3], rotmat9_host [9] fp32 row-major (the reference keeps rotmat in an f32 field). */
+int tsl_gripper_apply(tsl_ctx *ctx, int v_offset, int n_bound, const int *bound_idx_dev, const double *Fx_dev,
+                      const double *pos3_host, const float *rotmat9_host);
+/* gripper.gather_grad (code/engine/gripper_single.py:133-150): out6_host = (d_pos, d_angle) = mean over the bound vertices of
+ * tmp_z_frozen and of (R F_x) x tmp_z_frozen, clamped to +-clamp_pos / +-clamp_angle (10 / 100 in the reference). */
+int tsl_gripper_gather(tsl_ctx *ctx, const double *z_frozen_dev, int v_offset, int n_bound, const int *bound_idx_dev,
+                       const double *Fx_dev, const float *rotmat9_host, double clamp_pos, double clamp_angle, double *out6_host);
+
 /* ---- introspection used by the parity tests and the benchmark ---------------------------------- */
 int tsl_get_residual(tsl_ctx *ctx, double *F_host);                     /* BaseScene.F [3 n_verts] */
 int tsl_get_matrix_nnzb(tsl_ctx *ctx, int *nnzb_out);                   /* number of 3x3 blocks (unpadded) */
 /* last assembled Hessian as block-CSR on the host: rowptr [n_verts+1], colidx [nnzb], val [nnzb][3][3] f64 */
 int tsl_get_matrix(tsl_ctx *ctx, int *rowptr_host, int *colidx_host, double *val_host);
+/* blocks of the last assembled Hessian that are not in the static pattern: the 12 off-diagonal 3x3 blocks of every constraint
+ * against a triangle with free vertices (kept in a side buffer, applied after the sliced-ELL pass).  n_out = 12 * constraints
+ * (0 when every contact surface is frozen); rows_host, cols_host [n_out] vertex ids, val_host [n_out][3][3] f64; may be NULL to
+ * query n_out only. */
+int tsl_get_contact_blocks(tsl_ctx *ctx, int *n_out, int *rows_host, int *cols_host, double *val_host);
 /* contact candidates / constraints: proj_* rows of one surface body; const_* of the current set */
 int tsl_get_projection(tsl_ctx *ctx, int surface_body, int *flag_host, int *dir_host, int *idx_host, double *w_host);
 int tsl_get_constraints(tsl_ctx *ctx, int *n_out, int *idx_host, double *w_host, double *k_host, double *dx0_host,

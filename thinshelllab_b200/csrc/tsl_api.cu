@@ -89,6 +89,8 @@ int tsl_destroy(tsl_ctx *ctx)
     cudaFree(ctx->con.idx); cudaFree(ctx->con.w); cudaFree(ctx->con.k); cudaFree(ctx->con.mu); cudaFree(ctx->con.dx0); cudaFree(ctx->con.T); cudaFree(ctx->con.n);
     cudaFree(ctx->ks); cudaFreeHost(ctx->ks_host); cudaFree(ctx->red_partial); cudaFree(ctx->red_ticket); cudaFree(ctx->red_out); cudaFreeHost(ctx->red_host);
     cudaFree(ctx->d_kb); cudaFree(ctx->adj_rhs); cudaFree(ctx->adj_z); cudaFree(ctx->error_flag); cudaFree(ctx->zero_border);
+    for (auto &t : ctx->tets) { cudaFree(t.tets); cudaFree(t.B); cudaFree(t.W); cudaFree(t.slot); }
+    cudaFree(ctx->nc_dev); cudaFree(ctx->cside32); cudaFree(ctx->cside64); cudaFree(ctx->yc); cudaFree(ctx->vgrav);
     cudaEventDestroy(ctx->ev_in); cudaEventDestroy(ctx->ev_out); cudaStreamDestroy(ctx->stream);
     delete ctx;
     return TSL_OK;
@@ -192,6 +194,37 @@ int tsl_get_cloth_topology(tsl_ctx *ctx, int cloth, int *f2v, int *cf, int *cp)
     return TSL_OK;
 }
 
+// Elastic(...) of model_elastic_offset.py (kind 0) / model_elastic_tactile.py (kind 1): cells, inverse rest Ds, rest volumes
+int tsl_add_tets(tsl_ctx *ctx, int kind, int v_offset, int n_verts, int n_cells, const int *tets_host, const double *B_host,
+                 const double *W_host, double mu, double lam, double alpha, const double *gravity_host)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(!ctx->finalized, "tsl_add_tets after tsl_finalize");
+    REQUIRE((kind == 0 || kind == 1) && n_verts > 0 && n_cells > 0 && tets_host && B_host && W_host, "tsl_add_tets: bad arguments");
+    REQUIRE(v_offset >= 0 && v_offset + n_verts <= ctx->cfg.n_verts, "tsl_add_tets: vertex range outside n_verts");
+    REQUIRE((int)ctx->tets.size() < TSL_MAX_TETS, "tsl_add_tets: too many tetrahedral bodies");
+    std::vector<int> tv(tets_host, tets_host + 4 * (size_t)n_cells);
+    for (int q : tv) REQUIRE(q >= 0 && q < n_verts, "tsl_add_tets: cell vertex out of range");
+    TetDev t;
+    memset(&t, 0, sizeof(t));
+    t.nv = n_verts; t.nc = n_cells; t.offset = v_offset;
+    t.P.kind = kind; t.P.mu = mu; t.P.lam = lam; t.P.alpha = alpha;
+    TRY(upload(ctx, &t.tets, tv));
+    TRY(upload(ctx, &t.B, std::vector<double>(B_host, B_host + 9 * (size_t)n_cells)));
+    TRY(upload(ctx, &t.W, std::vector<double>(W_host, W_host + (size_t)n_cells)));
+    ctx->tets.push_back(t);
+    ctx->h_tets.push_back(tv);
+    for (int k = 0; k < 3; k++) ctx->h_tet_gravity.push_back(gravity_host ? gravity_host[k] : ctx->cfg.gravity[k]);
+    return (int)ctx->tets.size() - 1;
+}
+int tsl_set_tet_params(tsl_ctx *ctx, int body, double mu, double lam)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(body >= 0 && body < (int)ctx->tets.size(), "bad tet body id");
+    ctx->tets[body].P.mu = mu; ctx->tets[body].P.lam = lam;
+    return TSL_OK;
+}
+
 int tsl_set_surfaces(tsl_ctx *ctx, const int *faces_host, int tot_nf, const int *bodies_host, int n_bodies)
 {
     if (!ctx) return TSL_ERR_INVALID;
@@ -270,6 +303,12 @@ int tsl_finalize(tsl_ctx *ctx)
                 }
             }
         }
+        for (size_t ti = 0; ti < ctx->tets.size(); ti++) {
+            const TetDev &t = ctx->tets[ti];
+            const std::vector<int> &tv = ctx->h_tets[ti];
+            for (int c = 0; c < t.nc; c++)
+                for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) fn(tv[4 * c + a] + t.offset, tv[4 * c + b] + t.offset);
+        }
         for (int v = 0; v < nv; v++) fn(v, v);
     };
     for_each_pair([&](int r, int) { cnt[r + 1]++; });
@@ -342,6 +381,14 @@ int tsl_finalize(tsl_ctx *ctx)
         }
         TRY(upload(ctx, &c.tri_slot, ts)); TRY(upload(ctx, &c.hinge_slot, hs));
     }
+    for (size_t ti = 0; ti < ctx->tets.size(); ti++) {
+        TetDev &t = ctx->tets[ti];
+        const std::vector<int> &tv = ctx->h_tets[ti];
+        std::vector<int> sl((size_t)t.nc * 16);
+        for (int c = 0; c < t.nc; c++)
+            for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) sl[(size_t)c * 16 + a * 4 + b] = slot_of(tv[4 * c + a] + t.offset, tv[4 * c + b] + t.offset);
+        TRY(upload(ctx, &t.slot, sl));
+    }
     TRY(upload(ctx, &A.slice_base, A.h_slice_base));
     TRY(upload(ctx, &A.colidx, A.h_colidx_pad));
     TRY(upload(ctx, &A.diag_pb, diag));
@@ -374,6 +421,36 @@ int tsl_finalize(tsl_ctx *ctx)
         int last = -1;
         for (int v = 0; v < nv; v++) if (!(fz[3 * v] && fz[3 * v + 1] && fz[3 * v + 2])) last = v;
         ctx->n_solve = std::max(last + 1, 1);
+        // a contact pair whose surface body has a free DOF needs all 16 blocks of its constraints (side buffer)
+        ctx->general_contact = false;
+        for (auto &p : ctx->pairs) {
+            const SurfaceBody &sb = ctx->bodies[p.body];
+            for (int v = sb.v_start; v < sb.v_end; v++)
+                if (!(fz[3 * v] && fz[3 * v + 1] && fz[3 * v + 2])) ctx->general_contact = true;
+        }
+    }
+    if (ctx->general_contact) {
+        size_t m = (size_t)std::max(ctx->cfg.max_n_constraints, 1);
+        CK(cudaMalloc(&ctx->nc_dev, sizeof(int)));
+        CK(cudaMemset(ctx->nc_dev, 0, sizeof(int)));
+        CK(cudaMalloc(&ctx->cside32, sizeof(float) * 108 * m));
+        CK(cudaMemset(ctx->cside32, 0, sizeof(float) * 108 * m));
+        CK(cudaMalloc(&ctx->yc, sizeof(double) * 3 * 32 * (size_t)A.n_slices));
+        CK(cudaMemset(ctx->yc, 0, sizeof(double) * 3 * 32 * (size_t)A.n_slices));
+    }
+    {
+        // bodies whose gravity differs from the scene's (effector pads carry none, BaseScene.init_property :371-374)
+        bool differs = false;
+        for (size_t ti = 0; ti < ctx->tets.size(); ti++)
+            for (int k = 0; k < 3; k++) differs = differs || ctx->h_tet_gravity[3 * ti + k] != ctx->cfg.gravity[k];
+        if (differs) {
+            std::vector<double> vg(3 * (size_t)nv);
+            for (int v = 0; v < nv; v++) for (int k = 0; k < 3; k++) vg[3 * (size_t)v + k] = ctx->cfg.gravity[k];
+            for (size_t ti = 0; ti < ctx->tets.size(); ti++)
+                for (int v = 0; v < ctx->tets[ti].nv; v++)
+                    for (int k = 0; k < 3; k++) vg[3 * (size_t)(v + ctx->tets[ti].offset) + k] = ctx->h_tet_gravity[3 * ti + k];
+            TRY(upload(ctx, &ctx->vgrav, vg));
+        }
     }
     TRY(contact_alloc(ctx));
     TRY(linalg_alloc(ctx));
@@ -438,6 +515,11 @@ static int ensure_f64(tsl_ctx *ctx)
     CK(cudaMalloc(&ctx->d_kb, sizeof(double) * 3 * nr));
     CK(cudaMalloc(&ctx->adj_rhs, sizeof(double) * 3 * nr));
     CK(cudaMalloc(&ctx->adj_z, sizeof(double) * 3 * nr));
+    if (ctx->general_contact) {
+        size_t m = (size_t)std::max(ctx->cfg.max_n_constraints, 1);
+        CK(cudaMalloc(&ctx->cside64, sizeof(double) * 108 * m));
+        CK(cudaMemset(ctx->cside64, 0, sizeof(double) * 108 * m));
+    }
     return TSL_OK;
 }
 
@@ -506,7 +588,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     double dt = ctx->cfg.dt;
     int it = 0;
     const bool mgp = ctx->precond != 0 && ctx->mg.n_levels > 0;
-    const int max_pcg = mgp ? 200 : 4000;
+    const int max_pcg = (mgp && ctx->tets.empty()) ? 200 : 4000;   // tetrahedral rows only see the level-0 smoother
     // The hierarchy may be kept only while it is demonstrably as good as a fresh one: small Newton steps (the matrix barely
     // moves: the long tail of a buckling step), Krylov count within 3 of what the fresh hierarchy needed, at most 8
     // iterations old.  (Measured: a setup costs ~4.5 PCG iterations at 1M triangles; keeping a hierarchy through the
@@ -745,14 +827,16 @@ int tsl_step_forward_host(tsl_ctx *ctx, double *pos_host, double *vel_host, int 
     return TSL_OK;
 }
 
-// analytic_grad_system.Grad.transfer_grad (code/engine/analytic_grad_system.py:115-160)
-int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, const double *ref_angle_tm1,
-                      double *pg_t, double *pg_tm1, double *pg_tm2, const double *ag_t, double *ag_tm1,
-                      double *grad_kb_accum, double *z_out, double clamp, double rel_tol, int max_iters, tsl_solve_stats *stats)
+// Grad.transfer_grad: analytic_grad_system.py:115-160 (system identification, grad_kb) and analytic_grad_single.py:217-255
+// (trajectory optimisation: the same recurrence plus tmp_z_frozen, the sensitivity to the kinematically driven vertices)
+int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, const double *ref_angle_tm1,
+                         double *pg_t, double *pg_tm1, double *pg_tm2, const double *ag_t, double *ag_tm1,
+                         double *grad_kb_accum, double *z_out, double *z_frozen_out, double clamp, double rel_tol, int max_iters,
+                         tsl_solve_stats *stats)
 {
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
     StreamScope scope_(ctx);
-    REQUIRE(x_t && x_tm1 && ref_angle_tm1 && pg_t && pg_tm1 && ag_t && ag_tm1 && grad_kb_accum, "tsl_step_backward: null pointer");
+    REQUIRE(x_t && x_tm1 && ref_angle_tm1 && pg_t && pg_tm1 && ag_t && ag_tm1, "tsl_step_backward: null pointer");
     REQUIRE(ctx->cloths.size() == 1, "tsl_step_backward needs one cloth");
     TRY(ensure_f64(ctx));
     int nv = ctx->cfg.n_verts, n3 = 3 * nv;
@@ -771,7 +855,7 @@ int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, cons
     // ref_angle_backprop_a2ax: plastic rest-angle adjoint feeds pos_grad[t] before the solve
     launch_refangle_a2ax(ctx, c, ctx->pos, ag_t, ag_tm1, pg_t);
     // get_paramters_grad: d_kb = dF/dKb
-    launch_cloth_param_deri(ctx, c, ctx->pos, ctx->d_kb);
+    if (grad_kb_accum) launch_cloth_param_deri(ctx, c, ctx->pos, ctx->d_kb);
     // H = reference Hessian without projection, fp64
     launch_hessian(ctx, ctx->pos, true, 0, 0, 0);
     // preconditioner: multigrid hierarchy of the clamped Newton matrix at x_t
@@ -782,12 +866,97 @@ int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, cons
     TRY(check_device_flags(ctx));
     double *z = z_out ? z_out : ctx->adj_z;
     TRY(solve_bicgstab64(ctx, pg_t, z, rel_tol, max_iters, stats));
+    if (z_frozen_out) {
+        // second assembly with counting_z_frozen: tmp_z_frozen[j] = -sum_{i free} H[i][j] z[i] for frozen j
+        CK(cudaMemsetAsync(z_frozen_out, 0, nb, s));
+        launch_hessian_counting(ctx, ctx->pos, z, z_frozen_out);
+    }
     // friction lag terms and rest-angle terms into step t-1, then the time recurrence and dL/dKb
     launch_contact_backprop(ctx, ctx->pos, z, pg_tm1);
     launch_refangle_x2a(ctx, c, ctx->pos, z, ag_tm1);
-    launch_adjoint_tail(ctx, z, ctx->d_kb, pg_tm1, pg_tm2, grad_kb_accum);
+    launch_adjoint_tail(ctx, z, grad_kb_accum ? ctx->d_kb : nullptr, pg_tm1, pg_tm2, grad_kb_accum);
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());
+    return TSL_OK;
+}
+int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, const double *ref_angle_tm1,
+                      double *pg_t, double *pg_tm1, double *pg_tm2, const double *ag_t, double *ag_tm1,
+                      double *grad_kb_accum, double *z_out, double clamp, double rel_tol, int max_iters, tsl_solve_stats *stats)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(grad_kb_accum, "tsl_step_backward: null pointer");
+    return tsl_step_backward_ex(ctx, x_t, x_tm1, ref_angle_tm1, pg_t, pg_tm1, pg_tm2, ag_t, ag_tm1, grad_kb_accum, z_out, nullptr, clamp,
+                                rel_tol, max_iters, stats);
+}
+
+// ---------------------------------------------------------------------------------------------- kinematic boundary (gripper)
+// gripper.get_vert_pos + update_bound + pushup (code/engine/gripper_single.py:79-83, 157-161; Scene_folding.action :213-224):
+// pos[v_offset + bound_idx[i]] = p + R F_x[bound_idx[i]], R in fp32 as the reference stores it (rotmat is an f32 field)
+__global__ void k_gripper_apply(int n_bound, const int *__restrict__ bound_idx, const double *__restrict__ Fx, int v_offset,
+                                double px, double py, double pz, float r0, float r1, float r2, float r3, float r4, float r5, float r6, float r7, float r8,
+                                double *pos)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_bound) return;
+    int b = bound_idx[i];
+    double x = Fx[3 * b], y = Fx[3 * b + 1], z = Fx[3 * b + 2];
+    double *o = pos + 3 * (size_t)(v_offset + b);
+    o[0] = px + ((double)r0 * x + (double)r1 * y + (double)r2 * z);
+    o[1] = py + ((double)r3 * x + (double)r4 * y + (double)r5 * z);
+    o[2] = pz + ((double)r6 * x + (double)r7 * y + (double)r8 * z);
+}
+// gripper.gather_grad (code/engine/gripper_single.py:133-150): one block, deterministic tree sum over the bound vertices
+__global__ void __launch_bounds__(256) k_gripper_gather(int n_bound, const int *__restrict__ bound_idx, const double *__restrict__ Fx, int v_offset,
+                                                        const double *__restrict__ zf, float r0, float r1, float r2, float r3, float r4, float r5,
+                                                        float r6, float r7, float r8, double clamp_pos, double clamp_angle, double *out6)
+{
+    __shared__ double sh[6][256];
+    double acc[6] = { 0, 0, 0, 0, 0, 0 };
+    for (int i = threadIdx.x; i < n_bound; i += blockDim.x) {
+        int b = bound_idx[i];
+        const double *g = zf + 3 * (size_t)(v_offset + b);
+        double x = Fx[3 * b], y = Fx[3 * b + 1], z = Fx[3 * b + 2];
+        double rx = (double)r0 * x + (double)r1 * y + (double)r2 * z, ry = (double)r3 * x + (double)r4 * y + (double)r5 * z,
+               rz = (double)r6 * x + (double)r7 * y + (double)r8 * z;
+        acc[0] += g[0]; acc[1] += g[1]; acc[2] += g[2];
+        acc[3] += ry * g[2] - rz * g[1]; acc[4] += rz * g[0] - rx * g[2]; acc[5] += rx * g[1] - ry * g[0];
+    }
+    for (int k = 0; k < 6; k++) sh[k][threadIdx.x] = acc[k];
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) for (int k = 0; k < 6; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x < 6) {
+        double v = sh[threadIdx.x][0] / (1.0 * n_bound);
+        double lim = threadIdx.x < 3 ? clamp_pos : clamp_angle;
+        out6[threadIdx.x] = fmin(fmax(v, -lim), lim);
+    }
+}
+int tsl_gripper_apply(tsl_ctx *ctx, int v_offset, int n_bound, const int *bound_idx_dev, const double *Fx_dev, const double *pos3_host,
+                      const float *R)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    REQUIRE(n_bound > 0 && bound_idx_dev && Fx_dev && pos3_host && R, "tsl_gripper_apply: bad arguments");
+    StreamScope scope_(ctx);
+    k_gripper_apply<<<(n_bound + 127) / 128, 128, 0, ctx->stream>>>(n_bound, bound_idx_dev, Fx_dev, v_offset, pos3_host[0], pos3_host[1], pos3_host[2],
+                                                                   R[0], R[1], R[2], R[3], R[4], R[5], R[6], R[7], R[8], ctx->pos);
+    ctx->launches++;
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+int tsl_gripper_gather(tsl_ctx *ctx, const double *z_frozen_dev, int v_offset, int n_bound, const int *bound_idx_dev, const double *Fx_dev,
+                       const float *R, double clamp_pos, double clamp_angle, double *out6_host)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    REQUIRE(n_bound > 0 && z_frozen_dev && bound_idx_dev && Fx_dev && R && out6_host, "tsl_gripper_gather: bad arguments");
+    StreamScope scope_(ctx);
+    k_gripper_gather<<<1, 256, 0, ctx->stream>>>(n_bound, bound_idx_dev, Fx_dev, v_offset, z_frozen_dev, R[0], R[1], R[2], R[3], R[4], R[5], R[6],
+                                                 R[7], R[8], clamp_pos, clamp_angle, ctx->red_out + 2);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(ctx->red_host + 2, ctx->red_out + 2, 6 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int k = 0; k < 6; k++) out6_host[k] = ctx->red_host[2 + k];
     return TSL_OK;
 }
 
@@ -849,6 +1018,31 @@ int tsl_get_constraints(tsl_ctx *ctx, int *n_out, int *idx, double *w, double *k
     if (dx0) CK(cudaMemcpy(dx0, ctx->con.dx0, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost));
     if (T) CK(cudaMemcpy(T, ctx->con.T, sizeof(double) * 6 * nc, cudaMemcpyDeviceToHost));
     if (n) CK(cudaMemcpy(n, ctx->con.n, sizeof(double) * 3 * nc, cudaMemcpyDeviceToHost));
+    return TSL_OK;
+}
+int tsl_get_contact_blocks(tsl_ctx *ctx, int *n_out, int *rows, int *cols, double *val)
+{
+    if (!ctx || !ctx->finalized || !n_out) return TSL_ERR_INVALID;
+    CK(cudaStreamSynchronize(ctx->stream));
+    int nc = ctx->general_contact ? ctx->nc : 0;
+    *n_out = 12 * nc;
+    if (nc == 0 || !rows || !cols || !val) return TSL_OK;
+    std::vector<int> idx(4 * (size_t)nc);
+    CK(cudaMemcpy(idx.data(), ctx->con.idx, sizeof(int) * idx.size(), cudaMemcpyDeviceToHost));
+    size_t n = 108 * (size_t)nc;
+    if (ctx->last_f64) CK(cudaMemcpy(val, ctx->cside64, sizeof(double) * n, cudaMemcpyDeviceToHost));
+    else {
+        std::vector<float> t(n);
+        CK(cudaMemcpy(t.data(), ctx->cside32, sizeof(float) * n, cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < n; i++) val[i] = t[i];
+    }
+    for (int i = 0; i < nc; i++)
+        for (int a = 0; a < 4; a++)
+            for (int k = 0; k < 3; k++) {
+                int b = k < a ? k : k + 1;
+                rows[12 * (size_t)i + a * 3 + k] = idx[4 * i + a];
+                cols[12 * (size_t)i + a * 3 + k] = idx[4 * i + b];
+            }
     return TSL_OK;
 }
 int tsl_get_sizes(tsl_ctx *ctx, tsl_sizes *out)

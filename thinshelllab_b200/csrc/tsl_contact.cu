@@ -266,6 +266,7 @@ int contact_detect(tsl_ctx *ctx, const double *pos, const double *prev_pos)
     int nv = ctx->cfg.n_verts;
     cudaStream_t st = ctx->stream;
     ctx->nc = 0;
+    if (ctx->nc_dev) CK(cudaMemsetAsync(ctx->nc_dev, 0, sizeof(int), st));
     if (ctx->pairs.empty() || ctx->tot_nf == 0) return TSL_OK;
     GridP g = { ctx->cfg.grid_h, ctx->cfg.grid_n };
     CK(cudaMemsetAsync(ctx->vn, 0, sizeof(double) * 3 * nv, st));
@@ -325,6 +326,7 @@ int contact_detect(tsl_ctx *ctx, const double *pos, const double *prev_pos)
         }
         ctx->nc += count;
     }
+    if (ctx->nc_dev) CK(cudaMemcpyAsync(ctx->nc_dev, &ctx->nc, sizeof(int), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
     CK(cudaGetLastError());
     return TSL_OK;
 }

@@ -7,6 +7,7 @@
 
 #include "../../include/tsl.h"
 #include "tsl_elements.cuh"
+#include "tsl_solids.cuh"
 
 namespace tsl {
 
@@ -47,6 +48,22 @@ struct ClothDev {
     double *norm_dir;            // [NF][3] scratch: unit normals
     double *q1;                  // [9 + 81] c_i rows and mat_N of faces 0..2 (quirk Q1)
 };
+
+// tetrahedral body (Elastic of model_elastic_offset.py / model_elastic_tactile.py): vertex range [offset, offset + nv)
+#define TSL_MAX_TETS 8
+struct TetDev {
+    int nv, nc, offset;
+    TetParams P;
+    int *tets;                   // [nc][4] body-local vertex ids
+    double *B, *W;               // [nc][9] inverse rest Ds, [nc] rest volume
+    int *slot;                   // [nc][16] padded block ids of the (a, b) blocks of a cell
+};
+struct TetSet { int n; TetDev b[TSL_MAX_TETS]; };
+
+// where Hessian blocks go: the matrix values, or -- in the "counting" pass of the adjoint (BaseScene.add_H with
+// counting_z_frozen, BaseScene.py:399-405) -- tmp_z_frozen[j] -= H[i][j] z[i] for free i, frozen j
+template <typename T>
+struct Sink { T *val; const double *z; double *zf; };
 
 struct SurfaceBody { int v_start, v_end, f_start, f_end; };
 struct ContactPair { int body, v_start, v_end; double mu; };
@@ -150,6 +167,17 @@ struct tsl_ctx {
     int *cflag = nullptr, *cscan = nullptr;     // [n_verts] compaction scratch
     tsl::ContactDev con;
     int nc = 0;
+    // contact against triangles that move (cloth faces, pads, ball): the 12 off-diagonal blocks of every constraint live in a
+    // side buffer applied after the sliced-ELL pass (the pattern of the ELL matrix is static); diagonal blocks go into the ELL
+    bool general_contact = false;                // some contact pair's surface body has a free vertex (tsl_finalize)
+    int *nc_dev = nullptr;                       // [1] current constraint count for the graph-replayed side pass
+    float *cside32 = nullptr; double *cside64 = nullptr;   // [max_nc][12][9]
+    double *yc = nullptr;                        // [3 n_rows_pad] side-pass accumulator, consumed and cleared by the next matrix pass
+
+    std::vector<tsl::TetDev> tets;
+    std::vector<std::vector<int>> h_tets;
+    double *vgrav = nullptr;                     // [n_verts][3] per-vertex gravity when a body's differs from cfg.gravity, else null
+    std::vector<double> h_tet_gravity;           // [n_tets][3]
 
     // linear system
     tsl::SellMatrix A;

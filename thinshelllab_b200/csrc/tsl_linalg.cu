@@ -10,6 +10,8 @@
 // would otherwise dominate every mesh that fits the L2).  The host reads the scalars once per iteration.
 // HBM-bound: the SpMV streams 40 B (fp32) / 76 B (fp64) per 3x3 block in full-line transactions
 // (see SellMatrix), gathers the direction vector through L1/L2, and fuses the dot products it feeds.
+#include <algorithm>
+
 #include "tsl_internal.cuh"
 #include "tsl_kernels.cuh"
 
@@ -65,13 +67,17 @@ __device__ __forceinline__ void spmv_row(const int *__restrict__ slice_base, con
 template <typename T>
 __global__ void __launch_bounds__(256) k_spmv_dots(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
                                                    const T *__restrict__ val, const T *__restrict__ x, T *__restrict__ y,
-                                                   const T *__restrict__ u, double *acc_uy, double *acc_yy)
+                                                   const T *__restrict__ u, double *acc_uy, double *acc_yy, double *yc)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     double uy = 0, yy = 0;
     if (row < n_rows) {
         T y0, y1, y2;
         spmv_row<T>(slice_base, colidx, val, x, row, y0, y1, y2);
+        if (yc) {   // contributions of the contact side pass, consumed and cleared
+            y0 += (T)yc[3 * row]; y1 += (T)yc[3 * row + 1]; y2 += (T)yc[3 * row + 2];
+            yc[3 * row] = 0; yc[3 * row + 1] = 0; yc[3 * row + 2] = 0;
+        }
         y[3 * row] = y0; y[3 * row + 1] = y1; y[3 * row + 2] = y2;
         if (u) uy = (double)u[3 * row] * y0 + (double)u[3 * row + 1] * y1 + (double)u[3 * row + 2] * y2;
         yy = (double)y0 * y0 + (double)y1 * y1 + (double)y2 * y2;
@@ -84,7 +90,7 @@ __global__ void __launch_bounds__(256) k_spmv_dots(int n_rows, const int *__rest
 // fp32 only perturbs the system consistently.
 __global__ void __launch_bounds__(256) k_spmv_mixed(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
                                                     const float *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
-                                                    double *acc_xy)
+                                                    double *acc_xy, double *yc)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     double xy = 0;
@@ -101,10 +107,48 @@ __global__ void __launch_bounds__(256) k_spmv_mixed(int n_rows, const int *__res
             a1 += __ldg(v + 96) * x0 + __ldg(v + 128) * x1 + __ldg(v + 160) * x2;
             a2 += __ldg(v + 192) * x0 + __ldg(v + 224) * x1 + __ldg(v + 256) * x2;
         }
+        if (yc) {   // contributions of the contact side pass, consumed and cleared
+            a0 += yc[3 * row]; a1 += yc[3 * row + 1]; a2 += yc[3 * row + 2];
+            yc[3 * row] = 0; yc[3 * row + 1] = 0; yc[3 * row + 2] = 0;
+        }
         y[3 * row] = a0; y[3 * row + 1] = a1; y[3 * row + 2] = a2;
         xy = x[3 * row] * a0 + x[3 * row + 1] * a1 + x[3 * row + 2] * a2;
     }
     block_atomic_sum2(xy, 0.0, acc_xy, nullptr);
+}
+
+// Contact side pass: yc += sum over constraints of the 12 off-diagonal 3x3 blocks between (f0, f1, f2, v) times x.
+// The constraint count is read from the device so that the launch can sit inside a captured iteration graph; one thread per
+// (constraint, row vertex), grid-stride.  Runs BEFORE the sliced-ELL pass, which adds yc to its rows and clears it.
+template <typename TV>
+__global__ void __launch_bounds__(128) k_side_apply(const int *__restrict__ nc_dev, const int *__restrict__ cidx, const TV *__restrict__ side,
+                                                    const double *__restrict__ x, double *yc)
+{
+    int n = 4 * (*nc_dev);
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        int i = t >> 2, a = t & 3;
+        const int *idx = cidx + 4 * i;
+        double y0 = 0, y1 = 0, y2 = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            int b = k < a ? k : k + 1;
+            const TV *B = side + ((size_t)i * 12 + a * 3 + k) * 9;
+            double x0 = x[3 * idx[b]], x1 = x[3 * idx[b] + 1], x2 = x[3 * idx[b] + 2];
+            y0 += (double)B[0] * x0 + (double)B[1] * x1 + (double)B[2] * x2;
+            y1 += (double)B[3] * x0 + (double)B[4] * x1 + (double)B[5] * x2;
+            y2 += (double)B[6] * x0 + (double)B[7] * x1 + (double)B[8] * x2;
+        }
+        atomicAdd(yc + 3 * idx[a], y0); atomicAdd(yc + 3 * idx[a] + 1, y1); atomicAdd(yc + 3 * idx[a] + 2, y2);
+    }
+}
+template <typename TV>
+static double *side_pass(tsl_ctx *ctx, const TV *side, const double *x)
+{
+    if (!ctx->general_contact) return nullptr;
+    int blocks = std::max(1, std::min((4 * ctx->con.max_nc + 127) / 128, 592));
+    k_side_apply<TV><<<blocks, 128, 0, ctx->stream>>>(ctx->nc_dev, ctx->con.idx, side, x, ctx->yc);
+    ctx->launches++;
+    return ctx->yc;
 }
 
 // block-Jacobi: inverse of the diagonal 3x3 blocks (fp64 adjoint matrix, TSL_OPT_PRECOND = 0 only)
@@ -297,7 +341,8 @@ static int pcg_iteration_body(tsl_ctx *ctx, const float *opval)
     const SellMatrix &A = ctx->A;
     KrylovScalars *ks = ctx->ks;
     cudaStream_t s = ctx->stream;
-    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, &ks->pq);
+    double *yc = side_pass<float>(ctx, ctx->cside32, ctx->cg_p);
+    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, &ks->pq, yc);
     const float *mg_dinv, *mg_coef; float *mg_d, *mg_x0;
     mg_first_step_targets(ctx, &mg_dinv, &mg_d, &mg_x0, &mg_coef);
     k_pcg_update<<<GRID(n, 256), 256, 0, s>>>(n, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ctx->cg_r32, ks, mg_dinv, mg_d, mg_x0, mg_coef);
@@ -381,7 +426,7 @@ int probe_curvature(tsl_ctx *ctx, const float *opval, const double *dir, double 
     int n = ctx->n_solve;
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(&ctx->ks->pq, 0, sizeof(double), s));
-    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, opval, dir, ctx->cg_q, &ctx->ks->pq);
+    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, opval, dir, ctx->cg_q, &ctx->ks->pq, nullptr);
     ctx->launches++;
     CK(cudaMemcpyAsync(&ctx->ks_host->pq, &ctx->ks->pq, sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -403,7 +448,7 @@ int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out)
     CK(cudaEventRecord(e0, s));
     for (int it = 0; it < iters; it++) {
         if (what == 1) {
-            k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32, ctx->cg_p, ctx->cg_q, &ctx->ks->pq);
+            k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32, ctx->cg_p, ctx->cg_q, &ctx->ks->pq, nullptr);
             ctx->launches++;
         } else if (what == 5) TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, nullptr));
         else if (what == 6) TRYR(mg_setup_replay(ctx));
@@ -530,13 +575,17 @@ static int precond64(tsl_ctx *ctx, const double *in, double *out)
 // r = b - A x (fp64), rr = |r|^2 into acc
 __global__ void __launch_bounds__(256) k_residual64(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
                                                     const double *__restrict__ val, const double *__restrict__ b, const double *__restrict__ x,
-                                                    double *r, double *acc_rr)
+                                                    double *r, double *acc_rr, double *yc)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     double rr = 0;
     if (row < n_rows) {
         double y0, y1, y2;
         spmv_row<double>(slice_base, colidx, val, x, row, y0, y1, y2);
+        if (yc) {
+            y0 += yc[3 * row]; y1 += yc[3 * row + 1]; y2 += yc[3 * row + 2];
+            yc[3 * row] = 0; yc[3 * row + 1] = 0; yc[3 * row + 2] = 0;
+        }
         double r0 = b[3 * row] - y0, r1 = b[3 * row + 1] - y1, r2 = b[3 * row + 2] - y2;
         r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
         rr = r0 * r0 + r1 * r1 + r2 * r2;
@@ -559,10 +608,12 @@ static int bicg_iteration_body(tsl_ctx *ctx)
     double *dx = ctx->sol;
     k_bi_a<<<GRID(n3, 256), 256, 0, s>>>(n3, r, v, p, ks);
     TRYR(precond64(ctx, p, y));
-    k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, y, v, rhat, &ks->rhv, nullptr);
+    double *yc = side_pass<double>(ctx, ctx->cside64, y);
+    k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, y, v, rhat, &ks->rhv, nullptr, yc);
     k_bi_c<<<GRID(n3, 256), 256, 0, s>>>(n3, r, v, sv, ks);
     TRYR(precond64(ctx, sv, z));
-    k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, z, t, sv, &ks->ts, &ks->tt);
+    yc = side_pass<double>(ctx, ctx->cside64, z);
+    k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, z, t, sv, &ks->ts, &ks->tt, yc);
     k_bi_e<<<GRID(n3, 256), 256, 0, s>>>(n3, y, z, sv, t, rhat, dx, r, ks);
     k_bi_rotate<<<1, 1, 0, s>>>(ks);
     ctx->launches += 6;
@@ -613,7 +664,8 @@ int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol,
             ctx->launches++;
         }
         CK(cudaMemsetAsync(&ks->rr, 0, sizeof(double), s));
-        k_residual64<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, rhs, x, res, &ks->rr);
+        double *yc = side_pass<double>(ctx, ctx->cside64, x);
+        k_residual64<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, rhs, x, res, &ks->rr, yc);
         ctx->launches++;
         CK(cudaMemcpyAsync(ctx->ks_host, ks, sizeof(KrylovScalars), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));

@@ -103,7 +103,7 @@ __global__ void k_face_normals(ClothDev c, const double *__restrict__ pos)
 __global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_verts, const double *__restrict__ pos,
                                                 const double *__restrict__ prev_pos, const double *__restrict__ vel,
                                                 const double *__restrict__ mass, d3 g, double dt,
-                                                ContactDev con, int nc, ContactParams cp,
+                                                ContactDev con, int nc, ContactParams cp, TetSet ts, const double *__restrict__ vgrav,
                                                 double *partial, unsigned int *ticket, double *out)
 {
     double E = 0;
@@ -112,7 +112,20 @@ __global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_v
         d3 x = ld3(pos, i), xp = ld3(prev_pos, i), v = ld3(vel, i);
         double m = mass[i];
         d3 X = x - xp - dt * v;
-        E += -m * dot(x, g) + 0.5 * m * dot(X, X) / (dt * dt);
+        d3 gi = vgrav ? ld3(vgrav, i) : g;
+        E += -m * dot(x, gi) + 0.5 * m * dot(X, X) / (dt * dt);
+    }
+    // Elastic.compute_energy (model_elastic_offset.py:315-332, model_elastic_tactile.py:184-201): strain energy of the cells
+    for (int b = 0; b < ts.n; b++) {
+        const TetDev &t = ts.b[b];
+        for (int c = tid; c < t.nc; c += nth) {
+            d3 x[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) x[q] = ld3(pos, t.offset + t.tets[4 * c + q]);
+            double F[9];
+            tet_F(x, t.B + 9 * c, F);
+            E += tet_energy(t.P, F, t.W[c]);
+        }
     }
     if (n_cloth > 0)
         for (int i = tid; i < c.NF; i += nth) {
@@ -157,13 +170,30 @@ __device__ __forceinline__ void red_add3(double *F, int v, d3 g)
 // vertex part of the residual for every body: m (x - x_prev - v dt)/dt^2 - m g  (model_fold_offset.py:641-648,
 // model_elastic_offset.py:212-214 with zero internal force for the frozen box).  Overwrites F.
 __global__ void k_residual_vertex(int n_verts, const double *__restrict__ pos, const double *__restrict__ prev_pos,
-                                  const double *__restrict__ vel, const double *__restrict__ mass, d3 g, double dt, double *F)
+                                  const double *__restrict__ vel, const double *__restrict__ mass, d3 g, const double *__restrict__ vgrav,
+                                  double dt, double *F)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * n_verts) return;
     int v = i / 3, k = i - 3 * v;
     double m = mass[v];
-    F[i] = m * (pos[i] - prev_pos[i] - vel[i] * dt) / (dt * dt) - m * comp(g, k);
+    F[i] = m * (pos[i] - prev_pos[i] - vel[i] * dt) / (dt * dt) - m * (vgrav ? vgrav[i] : comp(g, k));
+}
+// elastic force of the cells of one tetrahedral body (Elastic.get_force / compute_residual,
+// model_elastic_offset.py:187-213, model_elastic_tactile.py:158-182); scale as in k_residual_cloth
+__global__ void __launch_bounds__(128) k_residual_tets(TetDev t, const double *__restrict__ pos, double *F, double scale)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= t.nc) return;
+    d3 x[4], g[4];
+    int v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { v[q] = t.offset + t.tets[4 * c + q]; x[q] = ld3(pos, v[q]); }
+    double Fm[9];
+    tet_F(x, t.B + 9 * c, Fm);
+    tet_grad(t.P, Fm, t.B + 9 * c, t.W[c], g);
+#pragma unroll
+    for (int q = 0; q < 4; q++) red_add3(F, v[q], scale * g[q]);
 }
 __global__ void k_fill_zero(double *a, long long n)
 {
@@ -264,8 +294,20 @@ __global__ void k_mask_frozen(int n, const int *__restrict__ frozen, double *F)
 
 // ------------------------------------------------------------------------------------------------ Hessian
 template <typename T>
-__device__ __forceinline__ void add_block(T *val, int pb, int row, int col, const int *__restrict__ frozen, const double *B)
+__device__ __forceinline__ void add_block(const Sink<T> &S, int pb, int row, int col, const int *__restrict__ frozen, const double *B)
 {
+    if (S.zf) {
+        // counting pass of the adjoint (BaseScene.add_H :399-405): free row, frozen column
+#pragma unroll
+        for (int a = 0; a < 3; a++) {
+            if (frozen[3 * row + a]) continue;
+            double za = S.z[3 * row + a];
+#pragma unroll
+            for (int b = 0; b < 3; b++)
+                if (frozen[3 * col + b]) atomicAdd(S.zf + 3 * col + b, -B[a * 3 + b] * za);
+        }
+        return;
+    }
     int lane = row & 31;
     long long base = sell_addr(pb, lane, 0);
 #pragma unroll
@@ -273,7 +315,7 @@ __device__ __forceinline__ void add_block(T *val, int pb, int row, int col, cons
         bool fr = frozen[3 * row + a] != 0;
 #pragma unroll
         for (int b = 0; b < 3; b++)
-            if (!fr && !frozen[3 * col + b]) atomicAdd(val + base + (a * 3 + b) * 32, (T)B[a * 3 + b]);
+            if (!fr && !frozen[3 * col + b]) atomicAdd(S.val + base + (a * 3 + b) * 32, (T)B[a * 3 + b]);
     }
 }
 
@@ -338,7 +380,7 @@ __global__ void k_q1_prepare(ClothDev c, const double *__restrict__ pos)
 // (Cloth.compute_Hessian_me :466-524, _ma :526-580, _bending loop 1 :585-614).
 template <typename T>
 __global__ void __launch_bounds__(128) k_hessian_tri(ClothDev c, const double *__restrict__ pos, const int *__restrict__ frozen,
-                                                     T *val, int spd, int sym)
+                                                     Sink<T> S, int spd, int sym)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.NF) return;
@@ -389,7 +431,7 @@ __global__ void __launch_bounds__(128) k_hessian_tri(ClothDev c, const double *_
 #pragma unroll
                     for (int q = r + 1; q < 3; q++) { double m_ = 0.5 * (B[r * 3 + q] + B[q * 3 + r]); B[r * 3 + q] = B[q * 3 + r] = m_; }
             }
-            add_block(val, slot[l * 3 + l], c.offset + f.v[l], c.offset + f.v[l], frozen, B);
+            add_block(S, slot[l * 3 + l], c.offset + f.v[l], c.offset + f.v[l], frozen, B);
         }
         // ---- off-diagonal pair (l, m) and (m, l), m = l+1
         {
@@ -420,8 +462,8 @@ __global__ void __launch_bounds__(128) k_hessian_tri(ClothDev c, const double *_
 #pragma unroll
                     for (int q = 0; q < 3; q++) { double m_ = 0.5 * (B[r * 3 + q] + Bt[q * 3 + r]); B[r * 3 + q] = m_; Bt[q * 3 + r] = m_; }
             }
-            add_block(val, slot[l * 3 + m], c.offset + f.v[l], c.offset + f.v[m], frozen, B);
-            add_block(val, slot[m * 3 + l], c.offset + f.v[m], c.offset + f.v[l], frozen, Bt);
+            add_block(S, slot[l * 3 + m], c.offset + f.v[l], c.offset + f.v[m], frozen, B);
+            add_block(S, slot[m * 3 + l], c.offset + f.v[m], c.offset + f.v[l], frozen, Bt);
         }
     }
 }
@@ -437,7 +479,7 @@ __global__ void __launch_bounds__(128) k_hessian_tri(ClothDev c, const double *_
 // Symmetric by construction; positive definite when clamped.
 template <typename T>
 __global__ void __launch_bounds__(128) k_hessian_tri_newton(ClothDev c, const double *__restrict__ pos, const int *__restrict__ frozen,
-                                                            T *val, int clamp)
+                                                            Sink<T> S, int clamp)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c.NF) return;
@@ -493,13 +535,13 @@ __global__ void __launch_bounds__(128) k_hessian_tri_newton(ClothDev c, const do
 #pragma unroll
                 for (int r = 0; r < 9; r++) B[r] -= He[l][r];
             }
-            add_block(val, slot[a * 3 + b], c.offset + f.v[a], c.offset + f.v[b], frozen, B);
+            add_block(S, slot[a * 3 + b], c.offset + f.v[a], c.offset + f.v[b], frozen, B);
         }
 }
 
 // hinge Hessian, loop 2 of Cloth.compute_Hessian_bending (:616-637): d2E/dtheta2 * grad(theta) grad(theta)^T
 template <typename T>
-__global__ void __launch_bounds__(128) k_hessian_hinge(ClothDev c, const double *__restrict__ pos, const int *__restrict__ frozen, T *val)
+__global__ void __launch_bounds__(128) k_hessian_hinge(ClothDev c, const double *__restrict__ pos, const int *__restrict__ frozen, Sink<T> S)
 {
     int h = blockIdx.x * blockDim.x + threadIdx.x;
     if (h >= c.NH) return;
@@ -522,7 +564,7 @@ __global__ void __launch_bounds__(128) k_hessian_hinge(ClothDev c, const double 
             for (int r = 0; r < 3; r++)
 #pragma unroll
                 for (int s = 0; s < 3; s++) B[r * 3 + s] = d2 * gj[r] * gk[s];
-            add_block(val, slot[j * 4 + k], c.offset + pt[j], c.offset + pt[k], frozen, B);
+            add_block(S, slot[j * 4 + k], c.offset + pt[j], c.offset + pt[k], frozen, B);
         }
 }
 
@@ -543,7 +585,7 @@ __global__ void k_hessian_mass(int n_verts, const double *__restrict__ mass, dou
 // block k T^T h T.  A non-frozen triangle DOF raises error bit 0 (TSL_ERR_UNSUPPORTED) instead of being wrong.
 template <typename T>
 __global__ void k_hessian_contact(ContactDev con, int nc, ContactParams cp, const double *__restrict__ pos,
-                                  const int *__restrict__ frozen, const int *__restrict__ diag_pb, T *val, int spd, int *error_flag)
+                                  const int *__restrict__ frozen, const int *__restrict__ diag_pb, Sink<T> S, int spd, int *error_flag)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nc) return;
@@ -583,7 +625,88 @@ __global__ void k_hessian_contact(ContactDev con, int nc, ContactParams cp, cons
 #pragma unroll
         for (int b = 0; b < 3; b++)
             B[a * 3 + b] += k * (Tm[a] * (h[0] * Tm[b] + h[1] * Tm[3 + b]) + Tm[3 + a] * (h[2] * Tm[b] + h[3] * Tm[3 + b]));
-    add_block(val, diag_pb[idx[3]], idx[3], idx[3], frozen, B);
+    add_block(S, diag_pb[idx[3]], idx[3], idx[3], frozen, B);
+}
+
+// cell Hessian of a tetrahedral body: reduced 9x9 by the reference's nine unit perturbations, optionally through
+// SPD_Projector(9, K=20), expanded to the 16 blocks of the cell (Elastic.compute_Hessian, model_elastic_offset.py:95-167,
+// model_elastic_tactile.py:82-124).  One thread per cell; the 9x9 lives in local memory (bodies are a few thousand cells).
+template <typename T>
+__global__ void __launch_bounds__(64) k_hessian_tets(TetDev t, const double *__restrict__ pos, const int *__restrict__ frozen, Sink<T> S, int project)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= t.nc) return;
+    d3 x[4];
+    int v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { v[q] = t.offset + t.tets[4 * c + q]; x[q] = ld3(pos, v[q]); }
+    double Fm[9], H9[81];
+    tet_F(x, t.B + 9 * c, Fm);
+    tet_H9(t.P, Fm, t.B + 9 * c, t.W[c], H9);
+    if (project) spd_project<9>(H9, 20);
+    const int *slot = t.slot + 16 * c;
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) {
+            double Bk[9];
+            tet_block(H9, t.P.kind, a, b, Bk);
+            add_block(S, slot[a * 4 + b], v[a], v[b], frozen, Bk);
+        }
+}
+
+// contact + friction Hessian of one constraint against a triangle that may move: all 16 blocks over (f0, f1, f2, v)
+// (BaseScene.contact_energy(diff=True), BaseScene.py:503-593).  Diagonal blocks go to the sliced-ELL matrix, the 12
+// off-diagonal ones to the side buffer side[i][a*3 + (b < a ? b : b - 1)][9] (masked by frozen, plain stores).
+template <typename T>
+__global__ void __launch_bounds__(64) k_hessian_contact_general(ContactDev con, int nc, ContactParams cp, const double *__restrict__ pos,
+                                                                const int *__restrict__ frozen, const int *__restrict__ diag_pb,
+                                                                Sink<T> S, T *side, int spd)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nc) return;
+    const int *idx = con.idx + 4 * i;
+    d3 x0 = ld3(pos, idx[0]), x1 = ld3(pos, idx[1]), x2 = ld3(pos, idx[2]), xv = ld3(pos, idx[3]);
+    double G[9], H[81];
+    bool active = contact_normal_full(x1 - x0, x2 - x0, xv - x0, cp.k_contact, cp.eps_contact, G, H);
+    if (active && spd) spd_project<9>(H, 20);
+    const double *w = con.w + 3 * i, *Tm = con.T + 6 * i, *dx0 = con.dx0 + 3 * i;
+    d3 dx = xv - (w[0] * x0 + w[1] * x1 + w[2] * x2) - mk(dx0[0], dx0[1], dx0[2]);
+    double u[2] = { Tm[0] * dx.x + Tm[1] * dx.y + Tm[2] * dx.z, Tm[3] * dx.x + Tm[4] * dx.y + Tm[5] * dx.z };
+    double r_ = sqrt(u[0] * u[0] + u[1] * u[1]);
+    double f1 = fr_f1(cp, r_);
+    double h[4] = { f1, 0, 0, f1 };
+    if (r_ > 1e-9) {
+        double f2 = fr_f2(cp, r_);
+        h[0] += f2 * (u[0] / r_) * u[0]; h[1] += f2 * (u[0] / r_) * u[1];
+        h[2] += f2 * (u[1] / r_) * u[0]; h[3] += f2 * (u[1] / r_) * u[1];
+    }
+    if (spd) psd_project_2x2(h);
+    double k = con.k[i], h1[9];
+#pragma unroll
+    for (int a = 0; a < 3; a++)
+#pragma unroll
+        for (int b = 0; b < 3; b++)
+            h1[a * 3 + b] = k * (Tm[a] * (h[0] * Tm[b] + h[1] * Tm[3 + b]) + Tm[3 + a] * (h[2] * Tm[b] + h[3] * Tm[3 + b]));
+    double w1[4] = { -w[0], -w[1], -w[2], 1.0 };
+    for (int a = 0; a < 4; a++)
+        for (int b = 0; b < 4; b++) {
+            double Bk[9];
+            if (active) contact_block(H, a, b, Bk);
+            else {
+#pragma unroll
+                for (int q = 0; q < 9; q++) Bk[q] = 0;
+            }
+#pragma unroll
+            for (int q = 0; q < 9; q++) Bk[q] += w1[a] * w1[b] * h1[q];
+            if (a == b || S.zf) add_block(S, diag_pb[idx[a]], idx[a], idx[b], frozen, Bk);
+            else {
+                T *dst = side + ((size_t)i * 12 + a * 3 + (b < a ? b : b - 1)) * 9;
+#pragma unroll
+                for (int r = 0; r < 3; r++)
+#pragma unroll
+                    for (int q = 0; q < 3; q++)
+                        dst[r * 3 + q] = (frozen[3 * idx[a] + r] || frozen[3 * idx[b] + q]) ? (T)0 : (T)Bk[r * 3 + q];
+            }
+        }
 }
 
 // ------------------------------------------------------------------------------------------------ misc state kernels
@@ -751,7 +874,7 @@ __global__ void k_adjoint_tail(int n_verts, const double *__restrict__ z, const 
             double xh = zi * mass[i / 3] / (dt * dt);
             pg_tm1[i] += xh * (1 + damping);
             if (pg_tm2) pg_tm2[i] -= xh * damping;
-            s += zi * d_kb[i];
+            if (d_kb) s += zi * d_kb[i];
         }
     }
     s = block_sum(s);
@@ -767,14 +890,21 @@ void launch_face_normals(tsl_ctx *ctx, const ClothDev &c, const double *pos)
     k_face_normals<<<GRID(c.NF, 256), 256, 0, ctx->stream>>>(c, pos);
     ctx->launches++;
 }
+static TetSet tet_set(tsl_ctx *ctx)
+{
+    TetSet ts;
+    ts.n = (int)ctx->tets.size();
+    for (int b = 0; b < ts.n; b++) ts.b[b] = ctx->tets[b];
+    return ts;
+}
 void launch_energy(tsl_ctx *ctx, const double *pos, double *out_dev)
 {
     ClothDev c = ctx->cloths.empty() ? ClothDev() : ctx->cloths[0];
     ContactParams cp = { ctx->cfg.k_contact, ctx->cfg.eps_contact, ctx->cfg.eps_v, ctx->cfg.dt };
     d3 g = mk(ctx->cfg.gravity[0], ctx->cfg.gravity[1], ctx->cfg.gravity[2]);
     k_energy<<<ctx->red_blocks, 256, 0, ctx->stream>>>(c, (int)ctx->cloths.size(), ctx->cfg.n_verts, pos, ctx->prev_pos, ctx->vel,
-                                                        ctx->mass, g, ctx->cfg.dt, ctx->con, ctx->nc, cp, ctx->red_partial,
-                                                        ctx->red_ticket, out_dev);
+                                                        ctx->mass, g, ctx->cfg.dt, ctx->con, ctx->nc, cp, tet_set(ctx), ctx->vgrav,
+                                                        ctx->red_partial, ctx->red_ticket, out_dev);
     ctx->launches++;
 }
 void launch_residual(tsl_ctx *ctx, const double *pos)
@@ -782,10 +912,14 @@ void launch_residual(tsl_ctx *ctx, const double *pos)
     int n = ctx->cfg.n_verts;
     d3 g = mk(ctx->cfg.gravity[0], ctx->cfg.gravity[1], ctx->cfg.gravity[2]);
     ContactParams cp = { ctx->cfg.k_contact, ctx->cfg.eps_contact, ctx->cfg.eps_v, ctx->cfg.dt };
-    k_residual_vertex<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(n, pos, ctx->prev_pos, ctx->vel, ctx->mass, g, ctx->cfg.dt, ctx->F);
+    k_residual_vertex<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(n, pos, ctx->prev_pos, ctx->vel, ctx->mass, g, ctx->vgrav, ctx->cfg.dt, ctx->F);
     ctx->launches++;
     for (auto &c : ctx->cloths) {
         k_residual_cloth<<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, ctx->F, 14, 1.0);
+        ctx->launches++;
+    }
+    for (auto &t : ctx->tets) {
+        k_residual_tets<<<GRID(t.nc, 128), 128, 0, ctx->stream>>>(t, pos, ctx->F, 1.0);
         ctx->launches++;
     }
     if (ctx->nc > 0) {
@@ -802,37 +936,63 @@ void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos,
     k_residual_cloth<<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, d_kb, 8, -1.0 / c.P.Kb);
     ctx->launches += 2;
 }
+// elements of the Hessian into the sink S (matrix values, or the counting pass of the adjoint)
 template <typename T>
-static void launch_hessian_t(tsl_ctx *ctx, const double *pos, T *val, int spd, int sym, int newton_model)
+static void launch_hessian_elements(tsl_ctx *ctx, const double *pos, Sink<T> S, T *side, int spd, int sym, int newton_model)
 {
-    int n = ctx->cfg.n_verts;
     ContactParams cp = { ctx->cfg.k_contact, ctx->cfg.eps_contact, ctx->cfg.eps_v, ctx->cfg.dt };
-    cudaMemsetAsync(val, 0, sizeof(T) * 9 * (size_t)ctx->A.nnzb_pad, ctx->stream);
-    k_hessian_mass<T><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, ctx->mass, ctx->cfg.dt, ctx->A.diag_pb, val);
-    ctx->launches++;
     for (auto &c : ctx->cloths) {
         if (newton_model) {
-            k_hessian_tri_newton<T><<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, ctx->frozen, val, spd);
+            k_hessian_tri_newton<T><<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, ctx->frozen, S, spd);
             ctx->launches += 1;
         } else {
             launch_face_normals(ctx, c, pos);
             k_q1_prepare<<<1, 32, 0, ctx->stream>>>(c, pos);
-            k_hessian_tri<T><<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, ctx->frozen, val, spd, sym);
+            k_hessian_tri<T><<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, ctx->frozen, S, spd, sym);
             ctx->launches += 3;
         }
-        k_hessian_hinge<T><<<GRID(c.NH, 128), 128, 0, ctx->stream>>>(c, pos, ctx->frozen, val);
+        k_hessian_hinge<T><<<GRID(c.NH, 128), 128, 0, ctx->stream>>>(c, pos, ctx->frozen, S);
         ctx->launches += 1;
     }
+    for (auto &t : ctx->tets) {
+        // reference matrices: only the tactile model is projected, and only when spd (forward); Newton model: the exact cell
+        // Hessian, projected in the clamped variant for either model
+        int project = newton_model ? spd : (spd && t.P.kind == 1);
+        k_hessian_tets<T><<<GRID(t.nc, 64), 64, 0, ctx->stream>>>(t, pos, ctx->frozen, S, project);
+        ctx->launches++;
+    }
     if (ctx->nc > 0) {
-        k_hessian_contact<T><<<GRID(ctx->nc, 128), 128, 0, ctx->stream>>>(ctx->con, ctx->nc, cp, pos, ctx->frozen, ctx->A.diag_pb, val, spd | newton_model, ctx->error_flag);
+        if (ctx->general_contact)
+            k_hessian_contact_general<T><<<GRID(ctx->nc, 64), 64, 0, ctx->stream>>>(ctx->con, ctx->nc, cp, pos, ctx->frozen, ctx->A.diag_pb, S, side, spd | newton_model);
+        else
+            k_hessian_contact<T><<<GRID(ctx->nc, 128), 128, 0, ctx->stream>>>(ctx->con, ctx->nc, cp, pos, ctx->frozen, ctx->A.diag_pb, S, spd | newton_model, ctx->error_flag);
         ctx->launches++;
     }
 }
+template <typename T>
+static void launch_hessian_t(tsl_ctx *ctx, const double *pos, T *val, T *side, int spd, int sym, int newton_model)
+{
+    int n = ctx->cfg.n_verts;
+    cudaMemsetAsync(val, 0, sizeof(T) * 9 * (size_t)ctx->A.nnzb_pad, ctx->stream);
+    k_hessian_mass<T><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, ctx->mass, ctx->cfg.dt, ctx->A.diag_pb, val);
+    ctx->launches++;
+    Sink<T> S = { val, nullptr, nullptr };
+    launch_hessian_elements<T>(ctx, pos, S, side, spd, sym, newton_model);
+}
 void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model, bool into_clamped)
 {
-    if (f64) launch_hessian_t<double>(ctx, pos, ctx->A.val64, spd, sym, newton_model);
-    else launch_hessian_t<float>(ctx, pos, into_clamped ? ctx->A.val32c : ctx->A.val32, spd, sym, newton_model);
+    if (f64) launch_hessian_t<double>(ctx, pos, ctx->A.val64, ctx->cside64, spd, sym, newton_model);
+    else launch_hessian_t<float>(ctx, pos, into_clamped ? ctx->A.val32c : ctx->A.val32, ctx->cside32, spd, sym, newton_model);
 }
+// second assembly of Grad.transfer_grad with counting_z_frozen (analytic_grad_single.py:240-243): zf[j] -= H[i][j] z[i]
+// over free rows i and frozen columns j of the reference's un-projected Hessian.  zf must be zeroed by the caller.
+void launch_hessian_counting(tsl_ctx *ctx, const double *pos, const double *z, double *zf)
+{
+    Sink<double> S = { nullptr, z, zf };
+    launch_hessian_elements<double>(ctx, pos, S, nullptr, 0, 0, 0);
+}
+// Elastic.compute_deri (model_elastic_offset.py:423-438, model_elastic_tactile.py:329-347) is not on the system-ID path
+// built here (grad_kb only).
 void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alpha, double *pos)
 {
     int n = 3 * ctx->cfg.n_verts;
@@ -892,8 +1052,11 @@ void launch_adjoint_tail(tsl_ctx *ctx, const double *z, const double *d_kb, doub
 {
     k_adjoint_tail<<<ctx->red_blocks, 256, 0, ctx->stream>>>(ctx->cfg.n_verts, z, ctx->mass, ctx->frozen, d_kb, ctx->cfg.dt, 1.0, pg_tm1, pg_tm2,
                                                              ctx->red_partial, ctx->red_ticket, ctx->red_out + 2);
-    k_accumulate<<<1, 1, 0, ctx->stream>>>(grad_kb_accum, ctx->red_out + 2);
-    ctx->launches += 2;
+    ctx->launches++;
+    if (grad_kb_accum) {
+        k_accumulate<<<1, 1, 0, ctx->stream>>>(grad_kb_accum, ctx->red_out + 2);
+        ctx->launches++;
+    }
 }
 
 }  // namespace tsl

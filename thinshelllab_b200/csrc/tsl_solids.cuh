@@ -1,0 +1,324 @@
+// tsl_solids.cuh -- per-element physics of tetrahedral bodies and of vertex-triangle contact against a moving
+// triangle, as __host__ __device__ functions (element-local fp64 data, no memory traffic).
+//
+// Reference formulas (ThinShellLab, paths relative to code/engine):
+//   box model      model_elastic_offset.py   get_force :187-208, compute_energy :315-332, compute_Hessian :95-167
+//                  neo-Hookean, P = mu (F - F^-T) + lam log(J) F^-T, J clamped at 0.01
+//   tactile model  model_elastic_tactile.py  get_force :158-174, compute_energy :184-201, compute_Hessian :82-124
+//                  P = mu F + lam (J - alpha) J F^-T, reduced 9x9 Hessian (vertex 3 eliminated) -> SPD_Projector(9, K=20)
+//   projector      linalg.py SPD_Projector :15-148 (Householder tridiagonalisation + K shifted QR sweeps, thresholds Q8)
+//   contact        BaseScene.contact_energy :488-543 with contact_diff.det / cross (contact_diff.py:4-129)
+// The host build of this header is what tests/test_solids_host.py checks against the oracle.
+#pragma once
+#include "tsl_elements.cuh"
+
+namespace tsl {
+
+// ------------------------------------------------------------------------------------------------ 3x3 helpers (row-major [9])
+TSL_HD void m3mul(const double *a, const double *b, double *o)
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o[3 * i + j] = a[3 * i] * b[j] + a[3 * i + 1] * b[3 + j] + a[3 * i + 2] * b[6 + j];
+}
+TSL_HD void m3mul_bt(const double *a, const double *b, double *o)   // a b^T
+{
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) o[3 * i + j] = a[3 * i] * b[3 * j] + a[3 * i + 1] * b[3 * j + 1] + a[3 * i + 2] * b[3 * j + 2];
+}
+TSL_HD double m3det(const double *a)
+{
+    return a[0] * (a[4] * a[8] - a[5] * a[7]) - a[1] * (a[3] * a[8] - a[5] * a[6]) + a[2] * (a[3] * a[7] - a[4] * a[6]);
+}
+TSL_HD void m3inv(const double *a, double *o)
+{
+    double id = 1.0 / m3det(a);
+    o[0] = (a[4] * a[8] - a[5] * a[7]) * id; o[1] = (a[2] * a[7] - a[1] * a[8]) * id; o[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+    o[3] = (a[5] * a[6] - a[3] * a[8]) * id; o[4] = (a[0] * a[8] - a[2] * a[6]) * id; o[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+    o[6] = (a[3] * a[7] - a[4] * a[6]) * id; o[7] = (a[1] * a[6] - a[0] * a[7]) * id; o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+}
+
+// ------------------------------------------------------------------------------------------------ SPD projector
+// SPD_Projector.project for an N x N matrix held row-major in M (in place): the reference's own algorithm, thresholds
+// included, because the projected matrices enter the parity tests entry by entry.
+template <int N>
+TSL_HD void spd_project(double *M, int K)
+{
+    double A[N][N], T[N][N], Q[N][N];
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) { A[i][j] = M[i * N + j]; T[i][j] = 0; Q[i][j] = (i == j) ? 1.0 : 0.0; }
+    // ---- Householder reduction to tridiagonal form, reflectors accumulated in Q
+    for (int i = 0; i < N - 2; i++) {
+        double b = 0.0;
+        for (int j = i + 1; j < N; j++) b += A[j][i] * A[j][i];
+        b = sqrt(b);
+        if (b < 1e-6) {
+            T[i][i] = -1;
+            for (int j = i + 1; j < N; j++) A[i][j] = 0;
+            continue;
+        }
+        T[i][i] = 1;
+        if (A[i + 1][i] < 0) b = -b;
+        T[i + 1][i] = A[i + 1][i] + b;
+        double c = T[i + 1][i] * T[i + 1][i];
+        for (int j = i + 2; j < N; j++) { T[j][i] = A[j][i]; c += A[j][i] * A[j][i]; }
+        c = sqrt(2 / c);
+        for (int j = i + 1; j < N; j++) { T[j][i] *= c; T[i][j] = 0; }
+        for (int j = i + 1; j < N; j++) {
+            for (int k = i + 1; k <= j; k++) T[i][j] += A[j][k] * T[k][i];
+            for (int k = j + 1; k < N; k++) T[i][j] += A[k][j] * T[k][i];
+        }
+        double d = 0.0;
+        for (int j = i + 1; j < N; j++) d += T[i][j] * T[j][i];
+        d *= 0.5;
+        for (int j = i + 1; j < N; j++) { T[i][j] -= T[j][i] * d; A[i][j] = A[j][i] = 0; }
+        A[i + 1][i] = A[i][i + 1] = -b;
+        for (int j = i + 1; j < N; j++)
+            for (int k = i + 1; k <= j; k++) A[j][k] -= T[i][j] * T[k][i] + T[i][k] * T[j][i];
+        for (int k = 0; k < N; k++) {
+            double s = 0.0;
+            for (int j = i + 1; j < N; j++) s += Q[k][j] * T[j][i];
+            for (int j = i + 1; j < N; j++) Q[k][j] -= s * T[j][i];
+        }
+    }
+    A[N - 2][N - 1] = A[N - 1][N - 2];
+    // ---- K implicit-shift QR sweeps on the tridiagonal matrix (Wilkinson shift of the active trailing 2x2)
+    for (int sweep = 0; sweep < K; sweep++) {
+        int m = 0;
+        for (int i = 0; i < N - 1; i++) if (fabs(A[i + 1][i]) > 1e-5) m = i + 2;
+        if (m == 0) break;
+        double a = A[m - 2][m - 2], b = A[m - 2][m - 1], c = A[m - 1][m - 1];
+        double d = (a - c) / 2;
+        double sd = d > 0 ? 1.0 : -1.0;
+        double mu = c;
+        if (fabs(b) > 1e-6) mu -= (sd * b * b) / (fabs(d) + sqrt(d * d + b * b));
+        for (int i = 0; i < N; i++) A[i][i] -= mu;
+        for (int i = 0; i < m - 1; i++) {
+            double a1 = A[i][i], b1 = A[i][i + 1], e1 = A[i + 1][i], d1 = A[i + 1][i + 1];
+            double s = fabs(e1) > 1e-5 ? fabs(e1 / sqrt(a1 * a1 + e1 * e1)) : 0.0;
+            if (a1 * e1 < 0) s = -s;
+            double cc = sqrt(fmax(1 - s * s, 0.0));
+            T[0][i] = s;
+            A[i][i] = a1 * cc + e1 * s;
+            A[i][i + 1] = b1 * cc + d1 * s;
+            A[i + 1][i + 1] = d1 * cc - b1 * s;
+            if (i < N - 2) A[i + 1][i + 2] *= cc;
+        }
+        for (int i = 0; i < m - 1; i++) {
+            double a1 = A[i][i], b1 = A[i][i + 1], d1 = A[i + 1][i + 1];
+            double s = T[0][i];
+            double cc = sqrt(fmax(1 - s * s, 0.0));
+            A[i][i] = a1 * cc + b1 * s;
+            A[i + 1][i] = s * d1;
+            A[i + 1][i + 1] = cc * d1;
+            for (int r = 0; r < N; r++) {
+                double qa = Q[r][i], qb = Q[r][i + 1];
+                Q[r][i] = qa * cc + qb * s; Q[r][i + 1] = -qa * s + qb * cc;
+            }
+        }
+        for (int i = 0; i < N - 1; i++) A[i][i + 1] = A[i + 1][i];
+        for (int i = 0; i < N; i++) A[i][i] += mu;
+    }
+    // ---- rebuild from the positive eigenpairs
+    for (int i = 0; i < N; i++) T[0][i] = A[i][i];
+    for (int i = 0; i < N * N; i++) M[i] = 0;
+    for (int i = 0; i < N; i++) {
+        double v = T[0][i];
+        if (v > 0)
+            for (int j = 0; j < N; j++) {
+                double v2 = v * Q[j][i];
+                for (int k = 0; k < N; k++) M[j * N + k] += v2 * Q[k][i];
+            }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ tetrahedra
+struct TetParams { int kind; double mu, lam, alpha; };   // kind 0 box (neo-Hookean), 1 tactile
+
+// deformation gradient F = Ds B with Ds columns x_i - x_3 (Elastic.Ds, model_elastic_offset.py:169-171)
+TSL_HD void tet_F(const d3 *x, const double *B, double *F)
+{
+    double D[9];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        d3 e = x[i] - x[3];
+        D[i] = e.x; D[3 + i] = e.y; D[6 + i] = e.z;
+    }
+    m3mul(D, B, F);
+}
+// strain energy density times rest volume
+TSL_HD double tet_energy(const TetParams &t, const double *F, double W)
+{
+    double J = m3det(F), I = 0;
+#pragma unroll
+    for (int q = 0; q < 9; q++) I += F[q] * F[q];
+    if (t.kind == 0) {
+        double lj = log(J > 0.01 ? J : 0.01);
+        return W * (t.mu / 2 * (I - 3) - t.mu * lj + t.lam / 2 * lj * lj);
+    }
+    return W * (t.mu / 2 * (I - 3) + t.lam / 2 * (J - t.alpha) * (J - t.alpha));
+}
+// gradient of the element energy w.r.t. its 4 vertices: g[i] = dE/dx_i  (= minus the reference's F_f contribution)
+TSL_HD void tet_grad(const TetParams &t, const double *F, const double *B, double W, d3 *g)
+{
+    double Fi[9], P[9], H[9];
+    m3inv(F, Fi);
+    double J = m3det(F);
+    if (t.kind == 0) {
+        if (J < 0.01) J = 0.01;
+        double lj = log(J);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) P[3 * i + j] = t.mu * (F[3 * i + j] - Fi[3 * j + i]) + t.lam * lj * Fi[3 * j + i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) P[3 * i + j] = t.mu * F[3 * i + j] + t.lam * (J - t.alpha) * J * Fi[3 * j + i];
+    }
+    m3mul_bt(P, B, H);                  // column i of W P B^T = dE/dx_i
+    g[3] = mk(0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        g[i] = mk(W * H[i], W * H[3 + i], W * H[6 + i]);
+        g[3] = g[3] - g[i];
+    }
+}
+// reduced 9x9 Hessian over (vertex n < 3, dim): H9[(n,dim)][(i,j)] = d2E / dx_{n,dim} dx_{i,j}, built from the 9 unit
+// perturbations of Ds exactly as the reference does (dP for dF = e_dim e_n^T B)
+TSL_HD void tet_H9(const TetParams &t, const double *F, const double *B, double W, double *H9)
+{
+    double Fi[9], FiT[9];
+    m3inv(F, Fi);
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+        for (int j = 0; j < 3; j++) FiT[3 * i + j] = Fi[3 * j + i];
+    double J = m3det(F);
+    if (t.kind == 0 && J < 0.01) J = 0.01;
+    double lj = t.kind == 0 ? log(J) : 0.0;
+    for (int n = 0; n < 3; n++)
+        for (int dim = 0; dim < 3; dim++) {
+            double dF[9], dFT[9], tmp[9], tmp2[9], dP[9], dH[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) dF[q] = 0;
+#pragma unroll
+            for (int j = 0; j < 3; j++) dF[3 * dim + j] = B[3 * n + j];
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) dFT[3 * i + j] = dF[3 * j + i];
+            m3mul(Fi, dF, tmp);
+            double dTr = tmp[0] + tmp[4] + tmp[8];
+            m3mul(FiT, dFT, tmp); m3mul(tmp, FiT, tmp2);            // F^-T dF^T F^-T
+            if (t.kind == 0) {
+#pragma unroll
+                for (int q = 0; q < 9; q++) dP[q] = t.mu * dF[q] + (t.mu - t.lam * lj) * tmp2[q] + t.lam * dTr * FiT[q];
+            } else {
+#pragma unroll
+                for (int q = 0; q < 9; q++)
+                    dP[q] = t.mu * dF[q] + t.lam * 2 * J * J * dTr * FiT[q] - t.lam * t.alpha * J * dTr * FiT[q]
+                            - t.lam * (J - t.alpha) * J * tmp2[q];
+            }
+            m3mul_bt(dP, B, dH);
+#pragma unroll
+            for (int i = 0; i < 3; i++)
+#pragma unroll
+                for (int j = 0; j < 3; j++) H9[(n * 3 + dim) * 9 + i * 3 + j] = W * dH[3 * j + i];
+        }
+}
+// 3x3 block (row vertex a, column vertex b) of the 12x12 element matrix expanded from H9 (vertex 3 = minus the sum).
+//   tactile (model_elastic_tactile.py:114-124): rows are the first index of H9, M[a,j][b,j2] = H9[(a,j)][(b,j2)]
+//   box     (model_elastic_offset.py:148-167): rows are the force index, M[a,r][b,dim] = H9[(b,dim)][(a,r)]
+// (identical for a symmetric H9; the un-projected reference matrices are symmetric only up to rounding)
+TSL_HD void tet_block(const double *H9, int kind, int a, int b, double *Bk)
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            double v = 0;
+            for (int p = (a < 3 ? a : 0); p < (a < 3 ? a + 1 : 3); p++)
+                for (int q = (b < 3 ? b : 0); q < (b < 3 ? b + 1 : 3); q++)
+                    v += kind == 1 ? H9[(p * 3 + r) * 9 + q * 3 + s] : H9[(q * 3 + s) * 9 + p * 3 + r];
+            Bk[3 * r + s] = ((a < 3) == (b < 3)) ? v : -v;
+        }
+}
+
+// ------------------------------------------------------------------------------------------------ contact, normal part
+// d = det(p1, p2, p) / |p1 x p2| over q = (p1, p2, p) (9 unknowns); E = k/2 (d - eps)^2 when d < eps.
+// Returns false when inactive.  G[9] = dE/dq, H[81] = d2E/dq2 before projection (quotient rule, BaseScene.py:503-521).
+TSL_HD bool contact_normal_full(d3 p1, d3 p2, d3 p, double k_contact, double eps, double *G, double *H)
+{
+    d3 cr = cross(p1, p2);
+    double c = norm(cr);
+    double det = dot(cr, p);
+    if (!(det / c < eps)) return false;
+    d3 n = (1.0 / c) * cr;
+    // gradient of det and of c
+    d3 gd[3] = { cross(p2, p), cross(p, p1), cr };
+    double dG[9] = { gd[0].x, gd[0].y, gd[0].z, gd[1].x, gd[1].y, gd[1].z, gd[2].x, gd[2].y, gd[2].z };
+    d3 Jc[6];                                   // d(p1 x p2)/dq_i, i < 6
+    for (int i = 0; i < 3; i++) {
+        d3 e = mk(i == 0 ? 1.0 : 0.0, i == 1 ? 1.0 : 0.0, i == 2 ? 1.0 : 0.0);
+        Jc[i] = cross(e, p2); Jc[3 + i] = cross(p1, e);
+    }
+    double cG[9];
+    for (int i = 0; i < 6; i++) cG[i] = dot(Jc[i], n);
+    cG[6] = cG[7] = cG[8] = 0;
+    double a[3] = { p1.x, p1.y, p1.z }, b[3] = { p2.x, p2.y, p2.z }, cc[3] = { p.x, p.y, p.z };
+    double nn[3] = { n.x, n.y, n.z };
+    double d = det / c, pe = k_contact * (d - eps);
+    double Gd[9];
+    for (int j = 0; j < 9; j++) Gd[j] = dG[j] / c - det * cG[j] / (c * c);
+    for (int j = 0; j < 9; j++)
+        for (int k = 0; k < 9; k++) {
+            // Hessian of det: entries (block I, comp i) x (block J, comp j) = eps_{ijk} * third vector's comp k, signed
+            double dH = 0;
+            int bj = j / 3, ij = j % 3, bk = k / 3, ik = k % 3;
+            if (bj != bk && ij != ik) {
+                int kk = 3 - ij - ik;                                // remaining component
+                const double *third = (bj + bk == 1) ? cc : ((bj + bk == 3) ? a : b);
+                // sign: +1 if (block bj -> bk, comp ij -> ik) follow the same cyclic sense, else -1
+                int sb = ((bk - bj + 3) % 3 == 1) ? 1 : -1;
+                int sc = ((ik - ij + 3) % 3 == 1) ? 1 : -1;
+                dH = (sb * sc) * third[kk];
+            }
+            // Hessian of c = |p1 x p2|
+            double cH = 0;
+            if (j < 6 && k < 6) {
+                cH = (dot(Jc[j], Jc[k]) - cG[j] * cG[k]) / c;
+                if ((j < 3) != (k < 3)) {
+                    int ia = j < 3 ? j : k, ib = (j < 3 ? k : j) - 3;   // d2(a x b)/da_ia db_ib = e_ia x e_ib
+                    if (ia != ib) {
+                        int kk = 3 - ia - ib;
+                        cH += (((ib - ia + 3) % 3 == 1) ? 1.0 : -1.0) * nn[kk];
+                    }
+                }
+            }
+            double Hd = dH / c - dG[j] * cG[k] / (c * c) - dG[k] * cG[j] / (c * c) - det * cH / (c * c) + 2 * det * cG[j] * cG[k] / (c * c * c);
+            H[j * 9 + k] = k_contact * Gd[j] * Gd[k] + pe * Hd;
+        }
+    for (int j = 0; j < 9; j++) G[j] = pe * Gd[j];
+    return true;
+}
+// 3x3 block (row vertex a, col vertex b; vertex order f0, f1, f2, v) of the 12x12 expansion of the 9x9 over
+// (p1, p2, p) = (x_f1 - x_f0, x_f2 - x_f0, x_v - x_f0): f0 takes minus the sums (BaseScene.py:526-541)
+TSL_HD void contact_block(const double *H, int a, int b, double *Bk)
+{
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+        for (int s = 0; s < 3; s++) {
+            double v = 0;
+            for (int p = (a > 0 ? a - 1 : 0); p < (a > 0 ? a : 3); p++)
+                for (int q = (b > 0 ? b - 1 : 0); q < (b > 0 ? b : 3); q++) v += H[(p * 3 + r) * 9 + q * 3 + s];
+            Bk[3 * r + s] = ((a > 0) == (b > 0)) ? v : -v;
+        }
+}
+
+}  // namespace tsl
