@@ -79,6 +79,13 @@ int tsl_set_cloth_params(tsl_ctx *ctx, int cloth, double Kl, double Ka, double K
 /* topology read-back for tests / renderers: Cloth.f2v, counter_face, counter_point ([2NM][3] i32, host) */
 int tsl_get_cloth_topology(tsl_ctx *ctx, int cloth, int *f2v_host, int *counter_face_host, int *counter_point_host);
 
+/* Test hook for the one canonicalised decision of this library: Cloth.judge_angle / compute_angle
+ * (code/engine/model_fold_offset.py:116,135,144) evaluate a side test on neighbour entries the reference's mesher mis-wires; there the
+ * exact value is 0 and the reference's outcome is the sign of rounding noise.  The library treats those tests as "not negative";
+ * ov_host [2NM][3] (1 = negative, else not negative; NULL = canonical rule) lets a parity test inject the outcomes of a reference run
+ * so that every other term is compared on equal footing. */
+int tsl_set_side_test_override(tsl_ctx *ctx, int cloth, const signed char *ov_host);
+
 /* Elastic bodies: the neo-Hookean box (kind 0; code/engine/model_elastic_offset.py:11-93, init_pos :240-253) and the tactile pad / ball
  * (kind 1; code/engine/model_elastic_tactile.py:13-80, init_pos :215-229).  tets_host [n_cells][4] body-local vertex ids
  * (Elastic.F_vertices), B_host [n_cells][3][3] = F_B (inverse rest Ds), W_host [n_cells] = F_W (rest volume); mu, lam, alpha as the
@@ -154,12 +161,13 @@ int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, cons
 /* Grad.transfer_grad of the trajectory optimiser (code/engine/analytic_grad_single.py:217-255): tsl_step_backward plus
  *   z_frozen_out_dev [3 n_verts]  BaseScene.tmp_z_frozen of the second, "counting" assembly (code/engine/BaseScene.py:399-405;
  *                                 analytic_grad_single.py:240-243); may be NULL
- * and grad_kb_accum_dev may be NULL (no system-ID gradient). */
+ * grad_kb_accum_dev may be NULL (no system-ID gradient); clamp_angleref > 0 also clamps angleref_grad_t in place
+ * (clamp_grad, analytic_grad_single.py:177-185: +-1000 for both). */
 int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, const double *ref_angle_tm1,
                          double *pos_grad_t, double *pos_grad_tm1, double *pos_grad_tm2,
-                         const double *angleref_grad_t, double *angleref_grad_tm1,
-                         double *grad_kb_accum_dev, double *z_out_dev, double *z_frozen_out_dev, double clamp, double rel_tol,
-                         int max_iters, tsl_solve_stats *stats);
+                         double *angleref_grad_t, double *angleref_grad_tm1,
+                         double *grad_kb_accum_dev, double *z_out_dev, double *z_frozen_out_dev, double clamp, double clamp_angleref,
+                         double rel_tol, int max_iters, tsl_solve_stats *stats);
 
 /* Kinematic boundary of a pad (code/engine/gripper_single.py): gripper.get_vert_pos + update_bound + the scene's pushup
  * (:79-83, 157-161; Scene_folding.action, code/task_scene/Scene_folding.py:213-224) for the n_bound driven vertices of the body at

@@ -55,3 +55,21 @@ def test_agent_and_adam_semantics():
     for _ in range(9):
         opt.step(p, torch.ones((1, 1, 1)))
     assert abs(opt.lr - 5e-3) < 1e-15
+
+
+def test_gripper_pose_update_matches_reference(golden_dir):
+    """gripper.step_simple + get_rotmat (code/engine/gripper_single.py:85-128) against the emulated reference rollout of
+    Scene_folding: positions, quaternions (f64) and the float32 rotation matrices of frames 1 and 2"""
+    import os
+    import numpy as np
+    from thinshelllab_b200.engine.gripper_single import pose_step, quat_to_rotmat32
+    g = np.load(os.path.join(golden_dir, "folding.npz"))
+    pos, rot = g["gripper_pos0"][0].copy(), g["gripper_rot0"][0].copy()
+    traj = g["traj"]
+    for frame in (1, 2):
+        d = traj[frame, 0] - traj[frame - 1, 0]
+        pos, rot = pose_step(pos, rot, d[:3], d[3:])
+        assert np.abs(pos - g[f"f{frame}_gripper_pos"][0]).max() < 1e-15
+        assert np.abs(rot - g[f"f{frame}_gripper_rot"][0]).max() < 1e-15
+        R = quat_to_rotmat32(rot)
+        assert R.dtype == np.float32 and np.array_equal(R, g[f"f{frame}_gripper_rotmat"][0])

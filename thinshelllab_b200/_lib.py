@@ -50,8 +50,10 @@ SIGNATURES = {
     "tsl_add_cloth": (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _vp]),
     "tsl_set_cloth_params": (_i, [_vp, _i, _d, _d, _d, _d]),
     "tsl_get_cloth_topology": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "tsl_set_side_test_override": (_i, [_vp, _i, _vp]),
     "tsl_add_tets": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _d, _d, _d, _vp]),
     "tsl_set_tet_params": (_i, [_vp, _i, _d, _d]),
+    "tsl_set_side_test_override": (_i, [_vp, _i, _vp]),
     "tsl_add_tets": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _d, _d, _d, _vp]),
     "tsl_set_tet_params": (_i, [_vp, _i, _d, _d]),
     "tsl_set_surfaces": (_i, [_vp, _vp, _i, _vp, _i]),
@@ -67,7 +69,7 @@ SIGNATURES = {
     "tsl_step_forward": (_i, [_vp, _i, _d, C.POINTER(StepStatsC)]),
     "tsl_step_forward_host": (_i, [_vp, _vp, _vp, _i, _d, C.POINTER(StepStatsC)]),
     "tsl_step_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, C.POINTER(SolveStatsC)]),
-    "tsl_step_backward_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, C.POINTER(SolveStatsC)]),
+    "tsl_step_backward_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _i, C.POINTER(SolveStatsC)]),
     "tsl_gripper_apply": (_i, [_vp, _i, _i, _vp, _vp, _dp, C.POINTER(C.c_float)]),
     "tsl_gripper_gather": (_i, [_vp, _vp, _i, _i, _vp, _vp, C.POINTER(C.c_float), _d, _d, _dp]),
     "tsl_get_contact_blocks": (_i, [_vp, _ip, _vp, _vp, _vp]),

@@ -66,6 +66,8 @@ class ShellEngine:
         self.vel = torch.zeros((self.n_verts, 3), **f64)
         self.mass = torch.zeros((self.n_verts,), **f64)
         self.frozen = torch.zeros((3 * self.n_verts,), dtype=torch.int32, device=self.device)
+        self.border_flag = torch.zeros((self.n_verts,), dtype=torch.int32, device=self.device)
+        self.tet_bodies = []
         self.cloth_ref_angle = []
         self.cloth_shape = []
         self.n_bodies = 0
@@ -98,12 +100,33 @@ class ShellEngine:
     def set_cloth_params(self, cloth, Kl, Ka, Kb, k_angle):
         self._ck(self.L.tsl_set_cloth_params(self.ctx, cloth, Kl, Ka, Kb, k_angle))
 
+    def set_side_test_override(self, cloth, ov):
+        """test hook: ov [NF, 3] int8 with 1 = negative, or None for the canonical rule"""
+        if ov is None:
+            self._ck(self.L.tsl_set_side_test_override(self.ctx, cloth, C.c_void_p(0)))
+        else:
+            ov = np.ascontiguousarray(ov, np.int8)
+            self._ck(self.L.tsl_set_side_test_override(self.ctx, cloth, _np_ptr(ov)))
+
     def cloth_topology(self, cloth=0):
         N, M = self.cloth_shape[cloth][:2]
         nf = 2 * N * M
         f2v, cf, cp = (np.zeros((nf, 3), np.int32) for _ in range(3))
         self._ck(self.L.tsl_get_cloth_topology(self.ctx, cloth, _np_ptr(f2v), _np_ptr(cf), _np_ptr(cp)))
         return f2v, cf, cp
+
+    def add_tets(self, kind, v_offset, n_verts, tets, B, W, mu, lam, alpha=0.0, gravity=None):
+        """Elastic body: kind 0 = neo-Hookean box (model_elastic_offset.py), 1 = tactile pad / ball (model_elastic_tactile.py);
+        tets [nc, 4] body-local ids, B [nc, 3, 3] inverse rest Ds, W [nc] rest volumes.  Masses: fill self.mass."""
+        tets = np.ascontiguousarray(tets, np.int32); B = np.ascontiguousarray(B, np.float64); W = np.ascontiguousarray(W, np.float64)
+        g = None if gravity is None else np.ascontiguousarray(gravity, np.float64)
+        bid = self._ck(self.L.tsl_add_tets(self.ctx, int(kind), int(v_offset), int(n_verts), tets.shape[0], _np_ptr(tets), _np_ptr(B),
+                                           _np_ptr(W), float(mu), float(lam), float(alpha), _np_ptr(g) if g is not None else C.c_void_p(0)))
+        self.tet_bodies.append((int(kind), int(v_offset), int(n_verts)))
+        return bid
+
+    def set_tet_params(self, body, mu, lam):
+        self._ck(self.L.tsl_set_tet_params(self.ctx, body, float(mu), float(lam)))
 
     def set_surfaces(self, faces, bodies):
         faces = np.ascontiguousarray(faces, np.int32)
@@ -119,7 +142,7 @@ class ShellEngine:
 
     def finalize(self):
         self._ck(self.L.tsl_bind_state(self.ctx, _ptr(self.pos), _ptr(self.prev_pos), _ptr(self.vel), _ptr(self.mass),
-                                       _ptr(self.frozen), C.c_void_p(0)))
+                                       _ptr(self.frozen), _ptr(self.border_flag)))
         self._ck(self.L.tsl_finalize(self.ctx))
         self.finalized = True
 
@@ -180,6 +203,32 @@ class ShellEngine:
                                           max_iters, C.byref(st)))
         return st.iters, st.flags, st.rel_residual
 
+    def step_backward_ex(self, x_t, x_tm1, ref_angle_tm1, pg_t, pg_tm1, pg_tm2, ag_t, ag_tm1, grad_kb=None, z_out=None, z_frozen=None,
+                         clamp=1000.0, clamp_angleref=1000.0, rel_tol=1e-10, max_iters=20000):
+        """Grad.transfer_grad of the trajectory optimiser (analytic_grad_single.py:217-255); z_frozen receives tmp_z_frozen"""
+        self._sync_stream()
+        st = _lib.SolveStatsC()
+        self._ck(self.L.tsl_step_backward_ex(self.ctx, _ptr(x_t), _ptr(x_tm1), _ptr(ref_angle_tm1), _ptr(pg_t), _ptr(pg_tm1),
+                                             _ptr(pg_tm2), _ptr(ag_t), _ptr(ag_tm1), _ptr(grad_kb), _ptr(z_out), _ptr(z_frozen), clamp,
+                                             clamp_angleref, rel_tol, max_iters, C.byref(st)))
+        return st.iters, st.flags, st.rel_residual
+
+    def gripper_apply(self, v_offset, bound_idx, F_x, pos3, rotmat32):
+        """pos[v_offset + bound_idx] = pos3 + R F_x[bound_idx] (gripper.get_vert_pos + update_bound, gripper_single.py:79-83, 157-161)"""
+        self._sync_stream()
+        p = np.ascontiguousarray(pos3, np.float64); R = np.ascontiguousarray(rotmat32, np.float32)
+        self._ck(self.L.tsl_gripper_apply(self.ctx, int(v_offset), int(bound_idx.numel()), _ptr(bound_idx), _ptr(F_x),
+                                          p.ctypes.data_as(C.POINTER(C.c_double)), R.ctypes.data_as(C.POINTER(C.c_float))))
+
+    def gripper_gather(self, z_frozen, v_offset, bound_idx, F_x, rotmat32, clamp_pos=10.0, clamp_angle=100.0):
+        """(d_pos, d_angle) of gripper.gather_grad (gripper_single.py:133-150)"""
+        self._sync_stream()
+        R = np.ascontiguousarray(rotmat32, np.float32); out = np.zeros(6)
+        self._ck(self.L.tsl_gripper_gather(self.ctx, _ptr(z_frozen), int(v_offset), int(bound_idx.numel()), _ptr(bound_idx), _ptr(F_x),
+                                           R.ctypes.data_as(C.POINTER(C.c_float)), clamp_pos, clamp_angle,
+                                           out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
     # ---- introspection
     def residual(self):
         F = np.zeros(3 * self.n_verts)
@@ -193,7 +242,22 @@ class ShellEngine:
         self._ck(self.L.tsl_get_matrix_nnzb(self.ctx, C.byref(n)))
         rowptr = np.zeros(self.n_verts + 1, np.int32); colidx = np.zeros(n.value, np.int32); val = np.zeros((n.value, 3, 3))
         self._ck(self.L.tsl_get_matrix(self.ctx, _np_ptr(rowptr), _np_ptr(colidx), _np_ptr(val)))
-        return sp.bsr_matrix((val, colidx, rowptr), shape=(3 * self.n_verts, 3 * self.n_verts)).tocsr()
+        H = sp.bsr_matrix((val, colidx, rowptr), shape=(3 * self.n_verts, 3 * self.n_verts)).tocsr()
+        rows, cols, blocks = self.contact_blocks()
+        if rows.size:
+            # blocks outside the static pattern (contact against moving triangles)
+            r = (3 * rows[:, None, None] + np.arange(3)[None, :, None]) + np.zeros((1, 1, 3), np.int64)
+            c = (3 * cols[:, None, None] + np.arange(3)[None, None, :]) + np.zeros((1, 3, 1), np.int64)
+            H = H + sp.coo_matrix((blocks.ravel(), (r.ravel(), c.ravel())), shape=H.shape).tocsr()
+        return H
+
+    def contact_blocks(self):
+        n = C.c_int()
+        self._ck(self.L.tsl_get_contact_blocks(self.ctx, C.byref(n), C.c_void_p(0), C.c_void_p(0), C.c_void_p(0)))
+        rows = np.zeros(n.value, np.int32); cols = np.zeros(n.value, np.int32); val = np.zeros((n.value, 3, 3))
+        if n.value:
+            self._ck(self.L.tsl_get_contact_blocks(self.ctx, C.byref(n), _np_ptr(rows), _np_ptr(cols), _np_ptr(val)))
+        return rows, cols, val
 
     def projection(self, body):
         nv = self.n_verts

@@ -80,7 +80,7 @@ int tsl_destroy(tsl_ctx *ctx)
     for (int i = 0; i < 8; i++) cudaFree(ctx->bi[i]);
     cudaFree(ctx->minv32); cudaFree(ctx->minv64); cudaFree(ctx->F); cudaFree(ctx->sol); cudaFree(ctx->x1);
     for (auto &c : ctx->cloths) {
-        cudaFree(c.f2v); cudaFree(c.cf); cudaFree(c.cp); cudaFree(c.side_deg); cudaFree(c.hinge_face); cudaFree(c.hinge_l);
+        cudaFree(c.f2v); cudaFree(c.cf); cudaFree(c.cp); cudaFree(c.side_deg); cudaFree(c.side_ovr); cudaFree(c.hinge_face); cudaFree(c.hinge_l);
         cudaFree(c.tri_slot); cudaFree(c.hinge_slot); cudaFree(c.norm_dir); cudaFree(c.q1);
     }
     cudaFree(ctx->faces); cudaFree(ctx->vn); cudaFree(ctx->proj_flag); cudaFree(ctx->proj_dir); cudaFree(ctx->proj_idx); cudaFree(ctx->proj_w);
@@ -165,7 +165,7 @@ int tsl_add_cloth(tsl_ctx *ctx, int N, int M, int v_offset, double dx, double rh
         }
     c.NH = (int)hf.size();
     TRY(upload(ctx, &c.f2v, f2v)); TRY(upload(ctx, &c.cf, cf)); TRY(upload(ctx, &c.cp, cp));
-    TRY(upload(ctx, &c.side_deg, deg)); TRY(upload(ctx, &c.hinge_face, hf)); TRY(upload(ctx, &c.hinge_l, hl));
+    TRY(upload(ctx, &c.side_deg, deg)); TRY(upload(ctx, &c.side_ovr, std::vector<unsigned char>(c.NF, 0))); TRY(upload(ctx, &c.hinge_face, hf)); TRY(upload(ctx, &c.hinge_l, hl));
     CK(cudaMalloc(&c.norm_dir, sizeof(double) * 3 * c.NF));
     CK(cudaMalloc(&c.q1, sizeof(double) * 90));
     CK(cudaMemset(c.q1, 0, sizeof(double) * 90));
@@ -183,6 +183,21 @@ int tsl_set_cloth_params(tsl_ctx *ctx, int cloth, double Kl, double Ka, double K
     return TSL_OK;
 }
 
+// test hook: outcomes of the topologically degenerate side tests.  ov_host [NF][3]: 1 = negative, anything else = not
+// negative (the canonical rule); NULL restores the canonical rule everywhere.
+int tsl_set_side_test_override(tsl_ctx *ctx, int cloth, const signed char *ov_host)
+{
+    if (!ctx) return TSL_ERR_INVALID;
+    REQUIRE(cloth >= 0 && cloth < (int)ctx->cloths.size(), "bad cloth id");
+    ClothDev &c = ctx->cloths[cloth];
+    std::vector<unsigned char> bits(c.NF, 0);
+    if (ov_host)
+        for (int i = 0; i < c.NF; i++)
+            for (int l = 0; l < 3; l++) if (ov_host[3 * i + l] == 1) bits[i] |= (unsigned char)(1u << l);
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaMemcpy(c.side_ovr, bits.data(), bits.size(), cudaMemcpyHostToDevice));
+    return TSL_OK;
+}
 int tsl_get_cloth_topology(tsl_ctx *ctx, int cloth, int *f2v, int *cf, int *cp)
 {
     if (!ctx) return TSL_ERR_INVALID;
@@ -830,9 +845,9 @@ int tsl_step_forward_host(tsl_ctx *ctx, double *pos_host, double *vel_host, int 
 // Grad.transfer_grad: analytic_grad_system.py:115-160 (system identification, grad_kb) and analytic_grad_single.py:217-255
 // (trajectory optimisation: the same recurrence plus tmp_z_frozen, the sensitivity to the kinematically driven vertices)
 int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, const double *ref_angle_tm1,
-                         double *pg_t, double *pg_tm1, double *pg_tm2, const double *ag_t, double *ag_tm1,
-                         double *grad_kb_accum, double *z_out, double *z_frozen_out, double clamp, double rel_tol, int max_iters,
-                         tsl_solve_stats *stats)
+                         double *pg_t, double *pg_tm1, double *pg_tm2, double *ag_t, double *ag_tm1,
+                         double *grad_kb_accum, double *z_out, double *z_frozen_out, double clamp, double clamp_angleref, double rel_tol,
+                         int max_iters, tsl_solve_stats *stats)
 {
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
     StreamScope scope_(ctx);
@@ -845,6 +860,7 @@ int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, c
     size_t nb = sizeof(double) * n3, nfb = sizeof(double) * 3 * (size_t)c.NF;
     // clamp_grad(step)
     launch_clamp(ctx, pg_t, n3, clamp);
+    if (clamp_angleref > 0) launch_clamp(ctx, ag_t, 3 * c.NF, clamp_angleref);   // analytic_grad_single.py:182-185
     // copy_pos_only(step-1): pos = prev_pos = x_{t-1}; contact re-detection there (quirk Q7)
     CK(cudaMemcpyAsync(ctx->pos, x_tm1, nb, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(ctx->prev_pos, x_tm1, nb, cudaMemcpyDeviceToDevice, s));
@@ -885,8 +901,8 @@ int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, cons
 {
     if (!ctx) return TSL_ERR_INVALID;
     REQUIRE(grad_kb_accum, "tsl_step_backward: null pointer");
-    return tsl_step_backward_ex(ctx, x_t, x_tm1, ref_angle_tm1, pg_t, pg_tm1, pg_tm2, ag_t, ag_tm1, grad_kb_accum, z_out, nullptr, clamp,
-                                rel_tol, max_iters, stats);
+    return tsl_step_backward_ex(ctx, x_t, x_tm1, ref_angle_tm1, pg_t, pg_tm1, pg_tm2, const_cast<double *>(ag_t), ag_tm1, grad_kb_accum, z_out,
+                                nullptr, clamp, 0.0, rel_tol, max_iters, stats);
 }
 
 // ---------------------------------------------------------------------------------------------- kinematic boundary (gripper)

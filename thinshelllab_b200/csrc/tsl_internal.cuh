@@ -41,6 +41,8 @@ struct ClothDev {
     ClothParams P;
     int *f2v, *cf, *cp;          // [NF][3]
     unsigned char *side_deg;     // [NF] bit l set: the side test of (face, l) is topologically degenerate
+    unsigned char *side_ovr;     // [NF] bit l: outcome ("negative") of a degenerate side test; all zero = the canonical rule.
+                                 // Test hook (tsl_set_side_test_override): lets a parity test inject the rounding-noise signs of a reference run
     int *hinge_face, *hinge_l;   // [NH] hinges = (i, l) with cf[i][l] > i
     int *tri_slot;               // [NF][9]  padded block ids of the (l, m) blocks of a triangle
     int *hinge_slot;             // [NH][16] padded block ids of the (j, k) blocks of a hinge

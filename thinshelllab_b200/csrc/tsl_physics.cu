@@ -329,7 +329,7 @@ __device__ __forceinline__ FaceBend face_bend(const ClothDev &c, const double *p
 {
     FaceBend fb;
     d3 n = ld3(c.norm_dir, i);
-    unsigned deg = c.side_deg[i];
+    unsigned deg = c.side_deg[i], ovr = c.side_ovr[i];
 #pragma unroll
     for (int l = 0; l < 3; l++) {
         d3 p = f.p[l], a = f.p[(l + 1) % 3], b = f.p[(l + 2) % 3];
@@ -340,6 +340,7 @@ __device__ __forceinline__ FaceBend face_bend(const ClothDev &c, const double *p
         if (i2 != -1) {
             n2 = ld3(c.norm_dir, i2);
             if (!((deg >> l) & 1)) neg = dot(n2, f.p[(l + 1) % 2] - f.p[l]) < 0;
+            else neg = (ovr >> l) & 1;
         }
         bool judge = !neg;                      // Cloth.judge_angle: True for borders too
         d3 nd = judge ? -n : n;

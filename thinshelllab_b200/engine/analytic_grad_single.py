@@ -1,0 +1,81 @@
+"""analytic_grad_single.Grad on the B200 engine (code/engine/analytic_grad_single.py): the adjoint of a rollout with respect to
+the gripper trajectory.  Trajectory buffers are torch CUDA tensors; one tsl_step_backward_ex call per transfer_grad (adjoint solve,
+counting pass for tmp_z_frozen, friction / rest-angle lag terms, time recurrence) plus the gather over the driven vertices."""
+import numpy as np
+import torch
+
+from ..fields import TensorField
+
+
+class Grad:
+    def __init__(self, sys, tot_timestep, n_parts, friction_loss=False, f_loss_ratio=0.001, vertical_only=False):
+        e = sys.engine
+        self.tot_NV, self.n_part, self.tot_timestep = sys.tot_NV, n_parts, tot_timestep
+        f64 = dict(dtype=torch.float64, device=e.device)
+        NF = sys.cloths[0].NF
+        self.NF, self.cloth_cnt = NF, sys.cloth_cnt
+        self._pos_buffer = torch.zeros((tot_timestep, sys.tot_NV, 3), **f64)
+        self._pos_grad = torch.zeros((tot_timestep, sys.tot_NV, 3), **f64)
+        self._ref_angle_buffer = torch.zeros((tot_timestep, sys.cloth_cnt, NF, 3), **f64)
+        self._angleref_grad = torch.zeros((tot_timestep, sys.cloth_cnt, NF, 3), **f64)
+        self._gripper_pos_buffer = np.zeros((tot_timestep, n_parts, 3))
+        self._gripper_rot_buffer = np.zeros((tot_timestep, n_parts, 4))
+        self._gripper_grad = np.zeros((tot_timestep, n_parts, 6))
+        self._z = torch.zeros((3 * sys.tot_NV,), **f64)
+        self._z_frozen = torch.zeros((3 * sys.tot_NV,), **f64)
+        self.dt, self.damping = sys.dt, 1.0
+        self.friction_loss, self.f_loss_ratio, self.vertical_only = friction_loss, f_loss_ratio, vertical_only
+        self.clamp = 1000.0                   # clamp_grad (analytic_grad_single.py)
+        self.last_solve = None
+
+    pos_buffer = property(lambda self: TensorField(self._pos_buffer))
+    pos_grad = property(lambda self: TensorField(self._pos_grad))
+    ref_angle_buffer = property(lambda self: TensorField(self._ref_angle_buffer))
+    angleref_grad = property(lambda self: TensorField(self._angleref_grad))
+    gripper_pos_buffer = property(lambda self: TensorField(torch.from_numpy(self._gripper_pos_buffer)))
+    gripper_rot_buffer = property(lambda self: TensorField(torch.from_numpy(self._gripper_rot_buffer)))
+    gripper_grad = property(lambda self: TensorField(torch.from_numpy(self._gripper_grad)))
+    tmp_z_frozen = property(lambda self: TensorField(self._z_frozen))
+
+    def reset(self):
+        self._pos_buffer.zero_(); self._pos_grad.zero_(); self._angleref_grad.zero_()
+
+    def init_mass(self, sys):
+        pass                                  # the engine reads sys.mass directly
+
+    def copy_pos(self, sys, step):
+        """:38-51"""
+        self._pos_buffer[step].copy_(sys.engine.pos)
+        self._ref_angle_buffer[step, 0].copy_(sys.engine.cloth_ref_angle[0])
+        self._gripper_pos_buffer[step] = sys.gripper._pos
+        self._gripper_rot_buffer[step] = sys.gripper._rot
+
+    def get_loss_fold(self, sys, curve7, curve8):
+        """seed on the rest angles of the two crease rows of the last frame (analytic_grad_single.py:281-292; the loss of
+        training/trajopt_folding.py:130)"""
+        sel7, sel8 = sys._crease_hinges()
+        g = self._angleref_grad[self.tot_timestep - 1, 0]
+        g[sel7[0], sel7[1]] = curve7
+        g[sel8[0], sel8[1]] = curve8
+
+    def transfer_grad(self, step, sys, f_contact=None, rel_tol=1e-10, max_iters=20000):
+        pg_tm2 = self._pos_grad[step - 2] if step > 1 else None
+        self.last_solve = sys.engine.step_backward_ex(
+            self._pos_buffer[step], self._pos_buffer[step - 1], self._ref_angle_buffer[step - 1, 0],
+            self._pos_grad[step], self._pos_grad[step - 1], pg_tm2, self._angleref_grad[step, 0], self._angleref_grad[step - 1, 0],
+            None, self._z, self._z_frozen, clamp=self.clamp, clamp_angleref=self.clamp, rel_tol=rel_tol, max_iters=max_iters)
+        if step > 0:
+            self.get_gripper_grad(step, sys)
+        return self.last_solve
+
+    def get_gripper_grad(self, step, sys):
+        """:118-135: pose of frame `step`, gather over the driven vertices"""
+        sys.gripper.set(self._gripper_pos_buffer, self._gripper_rot_buffer, step)
+        sys.gripper.get_rotmat()
+        sys.gripper.gather_grad(self._z_frozen, sys)
+        for j in range(self.n_part):
+            if self.vertical_only:
+                self._gripper_grad[step, j, 2] = sys.gripper._d_pos[j][2]
+            else:
+                self._gripper_grad[step, j, :3] = sys.gripper._d_pos[j]
+                self._gripper_grad[step, j, 3:] = sys.gripper._d_angle[j]
