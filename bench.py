@@ -164,6 +164,64 @@ def secondary_50k(args, dev):
     return out
 
 
+def secondary_solids(args, dev):
+    """BASELINE.json configs[0] (Scene_folding: cloth strip + table + tactile pad on a gripper, T = 3 rollout + trajectory adjoint, the
+    state of tests/golden/folding.npz) and a configs[3]-style scene (316 x 316 = 200 k-triangle sheet on the table with the volumetric
+    tactile pad pressed into it; contacts against moving triangles), one GPU, state resident in HBM"""
+    import torch
+    from thinshelllab_b200.agent.traj_opt_single import agent_trajopt
+    from thinshelllab_b200.engine.analytic_grad_single import Grad
+    from thinshelllab_b200.synthetic import pad_sheet_scene
+    from thinshelllab_b200.task_scene.Scene_folding import Scene
+    g = np.load(os.path.join(ROOT, "tests", "golden", "folding.npz"))
+    out = {}
+
+    def rollout(s, T, traj, reps):
+        e = s.engine
+        NVc = s.cloths[0].NV
+        agent = agent_trajopt(T, 1, max_moving_dist=0.001)
+        agent.traj.from_numpy(traj)
+        grad = Grad(s, T, 1)
+        res = None
+        for rep in range(reps + 1):              # first repetition = warm-up (graph capture, allocations)
+            s.reset()
+            grad.reset()
+            torch.cuda.synchronize()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            grad.copy_pos(s, 0)
+            newton = krylov = 0
+            for frame in range(1, T):
+                agent.get_action(frame)
+                s.action(frame, agent.delta_pos, agent.delta_rot)
+                st = s.time_step()
+                newton += st.newton_iters; krylov += st.linear_iters
+                grad.copy_pos(s, frame)
+            grad._pos_grad[T - 1, :NVc, 2] = 1.0
+            bi = 0
+            for j in range(T - 1, 0, -1):
+                bi += grad.transfer_grad(j, s, rel_tol=args.adjoint_tol)[0]
+            ev1.record()
+            torch.cuda.synchronize()
+            ms = ev0.elapsed_time(ev1)
+            res = {"steps": T - 1, "ms_per_step": ms / (T - 1), "tri_steps_per_s": s.cloths[0].NF * (T - 1) / (ms * 1e-3), "newton_iters": newton,
+                   "pcg_iters": krylov, "bicgstab_iters": bi, "contacts_last_step": int(st.n_contacts), "converged_last_step": bool(st.converged)}
+        return res
+
+    s = Scene(g, device=dev)
+    out["configs[0] Scene_folding fwd + trajectory adjoint"] = dict(scene="cloth 15x3 (90 tris) + frozen table + tactile pad (1365 tets) on a gripper",
+                                                                    **rollout(s, int(g["T"]), g["traj"], 2))
+    del s
+    N, T = 316, 4
+    s = pad_sheet_scene(N, g, device=dev)
+    traj = np.zeros((T, 1, 6)); traj[:, 0, 2] = -1.5e-4 * np.arange(T)
+    out["configs[3] 200k-tri sheet + tactile pad, fwd + trajectory adjoint"] = dict(
+        scene=f"sheet {N}x{N} ({2 * N * N} tris) resting on a frozen table, tactile pad (1365 tets) pressed 0.15 mm per step into it", **rollout(s, T, traj, 1))
+    del s
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -316,6 +374,10 @@ def run_ours(args, rank, world):
     }
     if world == 1 and N != 158 and not args.no_secondary:
         out["config"]["baseline_configs_50k"] = secondary_50k(args, dev)
+        try:
+            out["config"]["baseline_configs_solids"] = secondary_solids(args, dev)
+        except Exception as ex:                  # a secondary measurement must not take the headline line down with it
+            out["config"]["baseline_configs_solids"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
         tris, times, threads = oracle_fwd_bwd(args.cpu_sample_n, 1, threads=os.cpu_count())
         out["cpu_baseline"] = {"value": tris / times[0], "unit": "tri-steps/s", "cores": threads, "kind": "port",

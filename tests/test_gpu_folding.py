@@ -207,3 +207,45 @@ def test_tet_terms_on_gpu_match_reference(golden_dir):
         assert flags == 0 and rr < 1e-7, (name, iters, flags, rr)
         H = e.matrix()
         assert _rel(H @ x.cpu().numpy(), e.residual()) < 1e-5
+
+
+@pytest.mark.parametrize("N", [48])
+def test_sheet_with_tactile_pad_rollout(golden, N):
+    """BASELINE configs[3]-style scene (sheet on a frozen table, volumetric tactile pad pressed into it by a kinematic gripper):
+    every step converges, the pad really touches the sheet (constraints in both directions), the converged state is a fixed
+    point of the REFERENCE's own projected-Newton iteration (its matrix, direct solve: step below 10x its stopping threshold),
+    and the trajectory adjoint runs through (finite gripper gradient, BiCGStab converged)."""
+    import scipy.sparse.linalg as spla
+    from thinshelllab_b200.synthetic import pad_sheet_scene
+    s = pad_sheet_scene(N, golden)
+    e = s.engine
+    T = 6
+    NVc = s.cloths[0].NV
+    agent = agent_trajopt(T, 1, max_moving_dist=0.001)
+    traj = np.zeros((T, 1, 6)); traj[:, 0, 2] = -1.5e-4 * np.arange(T)
+    agent.traj.from_numpy(traj)
+    grad = Grad(s, T, 1)
+    grad.copy_pos(s, 0)
+    for frame in range(1, T):
+        agent.get_action(frame)
+        s.action(frame, agent.delta_pos, agent.delta_rot)
+        vel0 = e.vel.clone()
+        st = s.time_step()
+        assert st.converged, (frame, st)
+        grad.copy_pos(s, frame)
+    c = e.constraints()
+    pad0 = s.elastics[1].offset
+    assert (c["idx"][:, 3] >= pad0).sum() > 0 and ((c["idx"][:, 3] < NVc) & (c["idx"][:, 0] >= pad0)).sum() > 0
+    # fixed point of the reference iteration: p = H_ref^-1 F at the converged state (the step's potential uses the velocity at
+    # the start of the step)
+    vel1 = e.vel.clone(); e.vel.copy_(vel0)
+    e.assemble(_lib.ASM_RESIDUAL | _lib.ASM_HESSIAN | _lib.ASM_SPD | _lib.ASM_F64)
+    p = spla.spsolve(e.matrix().tocsc(), e.residual())
+    assert np.abs(p).max() / s.dt < 1e-6
+    e.vel.copy_(vel1)
+    grad._pos_grad[T - 1, :NVc, 2] = 1.0
+    for j in range(T - 1, 0, -1):
+        it, flags, rr = grad.transfer_grad(j, s, rel_tol=1e-8)
+        assert flags == 0 and rr < 1e-7, (j, it, flags, rr)
+    gg = grad._gripper_grad
+    assert np.isfinite(gg).all() and np.abs(gg[1:, 0, 2]).max() > 0

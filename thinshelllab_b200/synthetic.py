@@ -47,3 +47,39 @@ def sheet_scene(N, device="cuda:0", pinned_vertices=(), **kw):
     s.engine.cloth_ref_angle[0].zero_()     # a flat sheet: no pre-creased rows (Scene_bouncing's init_ref_angle_bridge is scene specific)
     s.spec = sp
     return s
+
+
+def pad_sheet_state(N, pad, dx=0.002, dt=5e-3, Kb=100.0, k_angle=3.14, k_contact=10000.0, mu=0.5, gap=2e-4):
+    """BASELINE.json configs[3]-style scene as a state mapping for task_scene.Scene_folding.Scene: an N x N sheet resting on a frozen
+    table with a tactile pad (volumetric, kinematic gripper) hovering `gap` above its centre, ready to be pressed into it.
+    `pad` holds the pad's arrays with the key names of oracle/gen_goldens.py:gen_folding (pad_tets, pad_F_B, pad_F_W, pad_mu, pad_lam,
+    pad_alpha, gripper_F_x, gripper_bound_idx, and faces / mass / frozen restricted to the pad through pad_offset / body_f)."""
+    sp = sheet_spec(N, dx=dx, dt=dt, bump=0.0, noise=0.0, z0=0.0004, k_contact=k_contact, mu=mu)
+    NVc, NFc = (N + 1) ** 2, 2 * N * N
+    tpos, tfaces, tmass = sp["table_pos"], sp["table_faces"], sp["table_mass"]
+    po, pn = int(pad["pad_offset"]), int(pad["pad_nverts"])
+    Fx = np.asarray(pad["gripper_F_x"], np.float64)[0]
+    pf0, pf1 = (int(v) for v in np.asarray(pad["body_f"])[2])
+    pfaces = np.asarray(pad["faces"])[pf0:pf1] - po
+    gpos = np.array([[0.0, 0.0, 0.0004 + 0.0004 + gap - Fx[:, 2].min()]])
+    ppos = gpos + Fx
+    to, pno = NVc, NVc + tpos.shape[0]
+    pos0 = np.concatenate([sp["cloth_pos"], tpos, ppos])
+    mass = np.concatenate([np.full(NVc, 40.0 * dx * dx), tmass, np.asarray(pad["mass"])[po:po + pn]])
+    frozen = np.zeros((pos0.shape[0], 3), np.int32)
+    frozen[to:pno] = 1
+    frozen[pno:] = np.asarray(pad["frozen"]).reshape(-1, 3)[po:po + pn]
+    return dict(dt=dt, k_contact=k_contact, eps_contact=sp["eps_contact"], eps_v=sp["eps_v"], mu=mu, Kb=Kb, k_angle=k_angle, cloth_N=N, cloth_M=N,
+                cloth_dx=dx, cloth_mass=40.0 * dx * dx, pos0=pos0, vel0=np.zeros_like(pos0), mass=mass, frozen=frozen.reshape(-1),
+                _cloth_faces=None, _table_faces=tfaces + to, _pad_faces=pfaces + pno, ref_angle0=np.zeros((NFc, 3)),
+                border_flag=np.zeros(pos0.shape[0], np.int32), gravity=np.array([0.0, 0.0, -9.8]),
+                table_offset=to, table_nverts=tpos.shape[0], pad_tets=pad["pad_tets"], pad_offset=pno, pad_nverts=pn, pad_F_B=pad["pad_F_B"],
+                pad_F_W=pad["pad_F_W"], pad_mu=pad["pad_mu"], pad_lam=pad["pad_lam"], pad_alpha=pad["pad_alpha"], pad_gravity=np.zeros(3),
+                gripper_pos0=gpos, gripper_F_x=pad["gripper_F_x"], gripper_bound_idx=pad["gripper_bound_idx"],
+                max_n_constraints=4 * NVc + 4096, grid_n=sp["grid_n"], n_tris=NFc)
+
+
+def pad_sheet_scene(N, pad, device="cuda:0", **kw):
+    from .task_scene.Scene_folding import Scene
+    st = pad_sheet_state(N, pad, **kw)
+    return Scene(st, device=device, max_newton=200)

@@ -31,7 +31,8 @@ class _ElasticView:
 
     def _set(self, k, v):
         self._p[k] = v
-        self._s.engine.set_tet_params(self._bid, self._p["mu"], self._p["lam"])
+        if self._bid >= 0:
+            self._s.engine.set_tet_params(self._bid, self._p["mu"], self._p["lam"])
 
     @property
     def F_x(self):
@@ -45,14 +46,15 @@ class Scene:
         self.dt = self.h = float(g["dt"])
         self.cloth_cnt, self.elastic_cnt, self.effector_cnt = 1, 2, 2
         self.k_contact, self.eps_contact, self.eps_v = float(g["k_contact"]), float(g["eps_contact"]), float(g["eps_v"])
-        self.max_n_constraints, self.damping = 10000, 1.0
+        self.max_n_constraints, self.damping = int(g["max_n_constraints"]) if "max_n_constraints" in g else 10000, 1.0
         self.max_newton = max_newton
         N, M, dx = int(g["cloth_N"]), int(g["cloth_M"]), float(g["cloth_dx"])
         self.cloth_N, self.cloth_M = N, M
         self.tot_NV = int(g["pos0"].shape[0])
         gravity = tuple(float(v) for v in g["gravity"])
         e = self.engine = ShellEngine(self.tot_NV, self.dt, k_contact=self.k_contact, eps_contact=self.eps_contact, eps_v=self.eps_v,
-                                      damping=self.damping, gravity=gravity, max_n_constraints=self.max_n_constraints, device=device)
+                                      damping=self.damping, gravity=gravity, max_n_constraints=self.max_n_constraints,
+                                      grid_n=int(g["grid_n"]) if "grid_n" in g else 132, device=device)
         rho = float(g["cloth_mass"]) / (dx * dx)
         cid = e.add_cloth(N, M, 0, dx, rho, Kb=float(g["Kb"]), k_angle=float(g["k_angle"]))
         self.cloths = [_ClothView(self, cid, N, M, dx, 0, rho)]
@@ -61,16 +63,24 @@ class Scene:
         pos0 = np.asarray(g["pos0"], np.float64)
         to, tn = int(g["table_offset"]), int(g["table_nverts"])
         po, pn = int(g["pad_offset"]), int(g["pad_nverts"])
-        tB, tW = tet_rest(pos0[to:to + tn], np.asarray(g["table_tets"]))
-        b0 = e.add_tets(0, to, tn, g["table_tets"], tB, tW, float(g["table_mu"]), float(g["table_lam"]), 0.0, g["table_gravity"])
+        b0 = -1
+        if "table_tets" in g:                  # a frozen table only adds a constant to the energy: its cells are optional
+            tB, tW = tet_rest(pos0[to:to + tn], np.asarray(g["table_tets"]))
+            b0 = e.add_tets(0, to, tn, g["table_tets"], tB, tW, float(g["table_mu"]), float(g["table_lam"]), 0.0, g["table_gravity"])
         b1 = e.add_tets(1, po, pn, g["pad_tets"], g["pad_F_B"], g["pad_F_W"], float(g["pad_mu"]), float(g["pad_lam"]), float(g["pad_alpha"]),
                         g["pad_gravity"])
-        self.elastics = [_ElasticView(self, b0, to, tn, float(g["table_mu"]), float(g["table_lam"])),
+        self.elastics = [_ElasticView(self, b0, to, tn, float(g["table_mu"]) if b0 >= 0 else 0.0, float(g["table_lam"]) if b0 >= 0 else 0.0),
                          _ElasticView(self, b1, po, pn, float(g["pad_mu"]), float(g["pad_lam"]))]
         self.elastics[0].body_idx, self.elastics[1].body_idx = 1, 2
-        self.faces = np.ascontiguousarray(g["faces"], np.int32)
+        if "faces" in g:
+            self.faces = np.ascontiguousarray(g["faces"], np.int32)
+            bv, bf = np.asarray(g["body_v"]), np.asarray(g["body_f"])
+        else:                                  # synthetic scenes: cloth faces from the library's own topology + table + pad pieces
+            cf_, tf_, pf_ = e.cloth_topology(cid)[0], np.asarray(g["_table_faces"]), np.asarray(g["_pad_faces"])
+            self.faces = np.ascontiguousarray(np.concatenate([cf_, tf_, pf_]), np.int32)
+            n0, n1 = cf_.shape[0], cf_.shape[0] + tf_.shape[0]
+            bv = np.array([[0, to], [to, to + tn], [po, po + pn]]); bf = np.array([[0, n0], [n0, n1], [n1, self.faces.shape[0]]])
         self.tot_NF = self.faces.shape[0]
-        bv, bf = np.asarray(g["body_v"]), np.asarray(g["body_f"])
         self.body_list = [Body(int(bv[i, 0]), int(bv[i, 1]), int(bf[i, 0]), int(bf[i, 1])) for i in range(bv.shape[0])]
         e.set_surfaces(self.faces, [[b.v_start, b.v_end, b.f_start, b.f_end] for b in self.body_list])
         # Scene_folding.contact_analysis (:99-108): for every elastic j: cloth surface vs its vertices, its surface vs cloth vertices
