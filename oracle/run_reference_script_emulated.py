@@ -40,6 +40,19 @@ if "imageio" not in sys.modules:
         import imageio  # noqa: F401
     except Exception:
         sys.modules["imageio"] = types.ModuleType("imageio")
+if "open3d" not in sys.modules:
+    try:
+        import open3d  # noqa: F401
+    except Exception:
+        # readfile.save_cloth_mesh (PLY export for visualisation, out of scope) is the only user
+        class _Mesh:
+            def compute_vertex_normals(self):
+                pass
+        o3d = types.ModuleType("open3d")
+        o3d.geometry = types.SimpleNamespace(TriangleMesh=_Mesh)
+        o3d.utility = types.SimpleNamespace(Vector3iVector=lambda a: a, Vector3dVector=lambda a: a)
+        o3d.io = types.SimpleNamespace(write_triangle_mesh=lambda *a, **k: True)
+        sys.modules["open3d"] = o3d
 # no GPU in the build container: the reference's hard-wired "cuda:0" torch device (BaseScene.py:31, sparse_solver.py:11)
 # is forced to "cpu"; the arithmetic (fp64 torch tensors handed to the SuperLU stand-in) is unchanged
 import thinshelllab.engine.BaseScene as _bs  # noqa: E402

@@ -57,3 +57,75 @@ def test_unmodified_script_if_present(tmp_path):
     grad = float(re.search(r"now grad ([-0-9.e]+)", out.stdout).group(1))
     assert abs(reward - GOLD["total_reward"]) < 1e-8
     assert abs(grad - GOLD["now_grad"]) <= 1e-5 * abs(GOLD["now_grad"])
+
+
+# ---- trajectory optimisation driver (code/training/trajopt_folding.py:50-140): Scene_folding + analytic_grad_single + Adam_single
+GOLD_FOLD_PATH = os.path.join(ROOT, "tests", "golden", "trajopt_folding_T3.json")
+
+
+def _gold_fold():
+    if not os.path.exists(GOLD_FOLD_PATH):
+        pytest.skip("no golden log of the emulated reference run of trajopt_folding.py")
+    return json.load(open(GOLD_FOLD_PATH))
+
+
+def test_folding_driver_call_sequence_matches_reference_run():
+    """the statements of trajopt_folding.py's optimisation loop, through the module names the script imports: the reward of the second
+    iteration depends on the whole chain forward -> adjoint -> gripper gradient -> Adam step -> fix_action -> forward"""
+    gold = _gold_fold()
+    from thinshelllab_b200 import compat
+    compat.install()
+    from thinshelllab.agent.traj_opt_single import agent_trajopt
+    from thinshelllab.engine.analytic_grad_single import Grad
+    from thinshelllab.engine.geometry import projection_query
+    from thinshelllab.optimizer.optim import Adam_single
+    from thinshelllab.task_scene.Scene_folding import Scene
+    T, lr, iters = gold["args"]["tot_step"], gold["args"]["lr"], gold["args"]["iter"]
+    sys_ = Scene(cloth_size=0.1)
+    sys_.cloths[0].Kb[None] = 400.0
+    analy_grad = Grad(sys_, T, sys_.elastic_cnt - 1)
+    adam = Adam_single((T, sys_.elastic_cnt - 1, 6), lr, 0.9, 0.9999, 1e-8)
+    agent = agent_trajopt(T, sys_.elastic_cnt - 1, max_moving_dist=0.001)
+    sys_.init_all()
+    analy_grad.init_mass(sys_)
+    sys_.reset()
+    sys_.mu_cloth_elastic[None] = 5.0
+    adam.reset()
+    rewards = []
+    for i in range(iters):
+        analy_grad.copy_pos(sys_, 0)
+        for frame in range(1, T):
+            agent.get_action(frame)
+            sys_.action(frame, agent.delta_pos, agent.delta_rot)
+            sys_.time_step(projection_query, frame)
+            analy_grad.copy_pos(sys_, frame)
+        rewards.append(sys_.compute_reward(1.0, -1.0))
+        analy_grad.get_loss_fold(sys_, 1.0, -1.0)
+        for j in range(T - 1, 0, -1):
+            analy_grad.transfer_grad(j, sys_, projection_query)
+        sys_.reset()
+        adam.step(agent.traj, analy_grad.gripper_grad)
+        agent.fix_action(0.015)
+        analy_grad.reset()
+    for mine, ref in zip(rewards, gold["total_reward"]):
+        assert abs(mine - ref) <= 1e-5 * max(abs(ref), 1e-3), (rewards, gold["total_reward"])
+    if "final_traj" in gold:
+        import numpy as np
+        assert np.abs(agent.traj.to_numpy() - np.array(gold["final_traj"])).max() <= 1e-5 * max(np.abs(gold["final_traj"]).max(), 1e-12)
+
+
+def test_unmodified_folding_script_if_present(tmp_path):
+    gold = _gold_fold()
+    script = os.path.join(ROOT, "baseline", "_ref", "trajopt_folding.py")
+    if not os.path.exists(script):
+        pytest.skip("the reference script is not part of this repository (git-ignored copy absent)")
+    env = dict(os.environ, TSL_WORKDIR=str(tmp_path))
+    a = gold["args"]
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_reference_script.py"), script, "--l", "0", "--r", "1", "--iter", str(a["iter"]),
+                          "--tot_step", str(a["tot_step"])], capture_output=True, text=True, env=env, timeout=900)
+    assert out.returncode == 0, out.stderr[-2000:]
+    last = [ln for ln in out.stdout.splitlines() if ln.startswith("total_reward:")][-1]
+    rewards = [float(x) for x in re.findall(r"(-?\d+\.\d+(?:e[-+]?\d+)?)", last.replace("np.float64(", ""))]
+    assert len(rewards) == len(gold["total_reward"])
+    for mine, ref in zip(rewards, gold["total_reward"]):
+        assert abs(mine - ref) <= 1e-5 * max(abs(ref), 1e-3), (rewards, gold["total_reward"])

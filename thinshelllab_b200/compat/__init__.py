@@ -47,9 +47,9 @@ class _Renderer:
 def install():
     from .. import fields  # noqa: F401
     from ..agent import traj_opt_single
-    from ..engine import analytic_grad_system, geometry
+    from ..engine import analytic_grad_single, analytic_grad_system, geometry, gripper_single, readfile
     from ..optimizer import optim
-    from ..task_scene import Scene_bouncing
+    from ..task_scene import Scene_bouncing, Scene_folding
 
     # ---- third-party modules the scripts import at top level
     if not _have("taichi"):
@@ -71,6 +71,10 @@ def install():
         "thinshelllab.task_scene.Scene_bouncing": Scene_bouncing,
         "thinshelllab.engine.geometry": geometry,
         "thinshelllab.engine.analytic_grad_system": analytic_grad_system,
+        "thinshelllab.engine.analytic_grad_single": analytic_grad_single,
+        "thinshelllab.engine.gripper_single": gripper_single,
+        "thinshelllab.engine.readfile": readfile,
+        "thinshelllab.task_scene.Scene_folding": Scene_folding,
         "thinshelllab.agent.traj_opt_single": traj_opt_single,
         "thinshelllab.optimizer.optim": optim,
     }

@@ -7,6 +7,8 @@ Mesh generation and asset loading (data/tactile.*, Cloth.init_fold) are cold-pat
 constructed from arrays -- what `Scene.init_all(); Scene.reset()` leaves in the reference's fields (positions, masses, frozen
 flags, faces, cells with their rest matrices, gripper frame).  tests/golden/folding.npz holds one such state, written by
 oracle/gen_goldens.py from the reference itself."""
+import os
+
 import numpy as np
 import torch
 
@@ -39,9 +41,23 @@ class _ElasticView:
         return TensorField(self._s.engine.pos[self.offset:self.offset + self.n_verts])
 
 
+_DEFAULT_STATE = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "folding.npz")
+
+
 class Scene:
-    def __init__(self, state, *, device="cuda:0", max_newton=50):
-        """state: mapping with the keys of tests/golden/folding.npz (see oracle/gen_goldens.py:gen_folding)"""
+    def __init__(self, cloth_size=0.06, device="cuda:0", *, state=None, max_newton=50):
+        """reference signature: Scene(cloth_size=0.06, device="cuda:0") (code/task_scene/Scene_folding.py:27).  The scene arrays come
+        from `state` (a mapping with the keys of tests/golden/folding.npz, see oracle/gen_goldens.py:gen_folding; also accepted as the
+        first positional argument), else from the file named by TSL_SCENE_STATE, else -- for cloth_size = 0.1, the size every
+        reference driver uses -- from the state shipped with the tests."""
+        if state is None and hasattr(cloth_size, "keys"):
+            state, cloth_size = cloth_size, None
+        if state is None:
+            path = os.environ.get("TSL_SCENE_STATE", _DEFAULT_STATE)
+            state = np.load(path)
+            if cloth_size is not None and "cloth_size" in state and abs(float(state["cloth_size"]) - float(cloth_size)) > 1e-12:
+                raise NotImplementedError(f"Scene_folding: no scene state for cloth_size={cloth_size} ({path} holds {float(state['cloth_size'])}); "
+                                          "mesh generation is not part of this build -- dump the reference scene's arrays and pass state=")
         g = state
         self.dt = self.h = float(g["dt"])
         self.cloth_cnt, self.elastic_cnt, self.effector_cnt = 1, 2, 2
