@@ -169,6 +169,13 @@ int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, c
                          double *grad_kb_accum_dev, double *z_out_dev, double *z_frozen_out_dev, double clamp, double clamp_angleref,
                          double rel_tol, int max_iters, tsl_solve_stats *stats);
 
+/* Material-parameter sensitivities of the elastic bodies at the bound positions: d_mu_dev, d_lam_dev [n_verts][3] f64 (overwritten) =
+ * Elastic.compute_deri pushed up into BaseScene.d_mu / d_lam (code/engine/model_elastic_offset.py:423-438,
+ * code/engine/model_elastic_tactile.py:329-347, code/engine/BaseScene.py:1523-1525); if z_dev [3 n_verts] is given, out2_host [2] =
+ * sum over the free DOFs of z d_mu and z d_lam = one step's contribution to Grad.grad_mu / grad_lam
+ * (code/engine/analytic_grad_system.py:69-75).  Call after tsl_step_backward* of the same step (positions x_t are still bound). */
+int tsl_elastic_param_grad(tsl_ctx *ctx, const double *z_dev, double *d_mu_dev, double *d_lam_dev, double *out2_host);
+
 /* Kinematic boundary of a pad (code/engine/gripper_single.py): gripper.get_vert_pos + update_bound + the scene's pushup
  * (:79-83, 157-161; Scene_folding.action, code/task_scene/Scene_folding.py:213-224) for the n_bound driven vertices of the body at
  * v_offset: pos[v_offset + bound_idx[i]] = p + R F_x[bound_idx[i]].  bound_idx_dev [n_bound] i32, Fx_dev [body verts][3] f64 (device),

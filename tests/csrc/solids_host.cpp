@@ -25,6 +25,23 @@ void host_tets(int kind, double mu, double lam, double alpha, int nc, const int 
         for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) tet_block(H9, kind, a, b, blocks + ((size_t)c * 16 + a * 4 + b) * 9);
     }
 }
+// Elastic.compute_deri per cell: gmu, glam [nc][4][3]
+void host_tets_deri(int kind, double mu, double lam, double alpha, int nc, const int *tets, const double *B, const double *W, const double *pos,
+                    double *gmu, double *glam)
+{
+    TetParams P = { kind, mu, lam, alpha };
+    for (int c = 0; c < nc; c++) {
+        d3 x[4], a[4], b[4];
+        for (int q = 0; q < 4; q++) x[q] = ld3(pos, tets[4 * c + q]);
+        double F[9];
+        tet_F(x, B + 9 * c, F);
+        tet_deri(P, F, B + 9 * c, W[c], a, b);
+        for (int q = 0; q < 4; q++) {
+            gmu[12 * c + 3 * q] = a[q].x; gmu[12 * c + 3 * q + 1] = a[q].y; gmu[12 * c + 3 * q + 2] = a[q].z;
+            glam[12 * c + 3 * q] = b[q].x; glam[12 * c + 3 * q + 1] = b[q].y; glam[12 * c + 3 * q + 2] = b[q].z;
+        }
+    }
+}
 void host_spd9(double *M, int K) { spd_project<9>(M, K); }
 void host_spd3(double *M, int K) { spd_project<3>(M, K); }
 // normal part of one constraint over (x0, x1, x2, xv): returns active, G[9], H[81] (projected if spd), blocks [4][4][9]

@@ -200,6 +200,13 @@ def test_tet_terms_on_gpu_match_reference(golden_dir):
             e.assemble(_lib.ASM_HESSIAN | _lib.ASM_F64 | (_lib.ASM_SPD if spd else 0))
             ref = g[f"H_spd{spd}"]
             assert np.abs(e.matrix().toarray() - ref).max() <= 1e-9 * np.abs(ref).max(), (name, spd)
+        # Elastic.compute_deri and the masked dot of Grad.get_parameters_grad
+        z = torch.from_numpy(np.random.default_rng(5).standard_normal(3 * nv)).to(e.device)
+        d_mu, d_lam, (gm, gl) = e.elastic_param_grad(z)
+        assert _rel(d_mu.cpu().numpy(), g["d_mu"]) < 1e-11 and _rel(d_lam.cpu().numpy(), g["d_lam"]) < 1e-11
+        zz = z.cpu().numpy()
+        assert abs(gm - (zz * g["d_mu"].ravel()).sum()) <= 1e-10 * np.abs(zz * g["d_mu"].ravel()).sum()
+        assert abs(gl - (zz * g["d_lam"].ravel()).sum()) <= 1e-10 * np.abs(zz * g["d_lam"].ravel()).sum()
         # forward solve through the engine's own Newton matrix (clamped = projected cells): PCG converges
         e.assemble(_lib.ASM_RESIDUAL | _lib.ASM_HESSIAN | _lib.ASM_NEWTON | _lib.ASM_SPD)
         F = torch.from_numpy(e.residual()).to(e.device)

@@ -64,6 +64,23 @@ def test_tet_element_functions_match_reference(host, golden_dir, name):
     assert np.abs(F - g["F_f"]).max() <= 1e-11 * np.abs(g["F_f"]).max()
 
 
+@pytest.mark.parametrize("name", ["box_4x3x3", "tactile"])
+def test_tet_parameter_derivatives_match_reference(host, golden_dir, name):
+    """Elastic.compute_deri (model_elastic_offset.py:423-438 / model_elastic_tactile.py:329-347)"""
+    g = np.load(os.path.join(golden_dir, f"tet_{name}.npz"))
+    kind = 1 if str(g["kind"]) == "tactile" else 0
+    tets = np.ascontiguousarray(g["tets"], np.int32)
+    B = np.ascontiguousarray(g["F_B"]); W = np.ascontiguousarray(g["F_W"]); pos = np.ascontiguousarray(g["pos"])
+    nc, nv = tets.shape[0], pos.shape[0]
+    gm = np.zeros((nc, 4, 3)); gl = np.zeros((nc, 4, 3))
+    host.host_tets_deri(kind, C.c_double(g["mu"]), C.c_double(g["lam"]), C.c_double(g["alpha"]), nc, tets.ctypes.data_as(C.c_void_p),
+                        _d(B), _d(W), _d(pos), _d(gm), _d(gl))
+    dm = np.zeros((nv, 3)); dl = np.zeros((nv, 3))
+    np.add.at(dm, tets.ravel(), gm.reshape(-1, 3)); np.add.at(dl, tets.ravel(), gl.reshape(-1, 3))
+    assert np.abs(dm - g["d_mu"]).max() <= 1e-11 * np.abs(g["d_mu"]).max()
+    assert np.abs(dl - g["d_lam"]).max() <= 1e-11 * max(np.abs(g["d_lam"]).max(), 1e-300)
+
+
 def test_spd_projector_matches_reference(host, golden_dir):
     g = np.load(os.path.join(golden_dir, "spd_projector.npz"))
     n9 = 0

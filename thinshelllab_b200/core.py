@@ -213,6 +213,14 @@ class ShellEngine:
                                              clamp_angleref, rel_tol, max_iters, C.byref(st)))
         return st.iters, st.flags, st.rel_residual
 
+    def elastic_param_grad(self, z=None):
+        """(d_mu, d_lam [n_verts, 3] CUDA tensors, (sum z d_mu, sum z d_lam) over the free DOFs or None) at the bound positions"""
+        self._sync_stream()
+        d_mu = torch.empty((self.n_verts, 3), dtype=torch.float64, device=self.device); d_lam = torch.empty_like(d_mu)
+        out = (C.c_double * 2)()
+        self._ck(self.L.tsl_elastic_param_grad(self.ctx, _ptr(z), _ptr(d_mu), _ptr(d_lam), out))
+        return d_mu, d_lam, ((out[0], out[1]) if z is not None else None)
+
     def gripper_apply(self, v_offset, bound_idx, F_x, pos3, rotmat32):
         """pos[v_offset + bound_idx] = pos3 + R F_x[bound_idx] (gripper.get_vert_pos + update_bound, gripper_single.py:79-83, 157-161)"""
         self._sync_stream()

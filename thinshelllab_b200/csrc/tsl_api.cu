@@ -905,6 +905,24 @@ int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, cons
                                 nullptr, clamp, 0.0, rel_tol, max_iters, stats);
 }
 
+// BaseScene.get_paramters_grad (elastic part, code/engine/BaseScene.py:1523-1525) + Grad.get_parameters_grad
+// (code/engine/analytic_grad_system.py:69-75) at the bound positions
+int tsl_elastic_param_grad(tsl_ctx *ctx, const double *z_dev, double *d_mu_dev, double *d_lam_dev, double *out2_host)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    REQUIRE(d_mu_dev && d_lam_dev, "tsl_elastic_param_grad: null pointer");
+    REQUIRE(!z_dev || out2_host, "tsl_elastic_param_grad: out2_host missing");
+    StreamScope scope_(ctx);
+    launch_tets_param_grad(ctx, ctx->pos, z_dev, d_mu_dev, d_lam_dev, ctx->red_out + 2);
+    if (z_dev) {
+        CK(cudaMemcpyAsync(ctx->red_host + 2, ctx->red_out + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        out2_host[0] = ctx->red_host[2]; out2_host[1] = ctx->red_host[3];
+    }
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- kinematic boundary (gripper)
 // gripper.get_vert_pos + update_bound + pushup (code/engine/gripper_single.py:79-83, 157-161; Scene_folding.action :213-224):
 // pos[v_offset + bound_idx[i]] = p + R F_x[bound_idx[i]], R in fp32 as the reference stores it (rotmat is an f32 field)

@@ -629,6 +629,33 @@ __global__ void k_hessian_contact(ContactDev con, int nc, ContactParams cp, cons
     add_block(S, diag_pb[idx[3]], idx[3], idx[3], frozen, B);
 }
 
+// Elastic.compute_deri (model_elastic_offset.py:423-438, model_elastic_tactile.py:329-347): d_mu, d_lam [n_verts][3], accumulated
+__global__ void __launch_bounds__(128) k_tets_deri(TetDev t, const double *__restrict__ pos, double *d_mu, double *d_lam)
+{
+    int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= t.nc) return;
+    d3 x[4], gm[4], gl[4];
+    int v[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) { v[q] = t.offset + t.tets[4 * c + q]; x[q] = ld3(pos, v[q]); }
+    double Fm[9];
+    tet_F(x, t.B + 9 * c, Fm);
+    tet_deri(t.P, Fm, t.B + 9 * c, t.W[c], gm, gl);
+#pragma unroll
+    for (int q = 0; q < 4; q++) { red_add3(d_mu, v[q], gm[q]); red_add3(d_lam, v[q], gl[q]); }
+}
+// sum over the free DOFs of z * d  (Grad.get_parameters_grad, analytic_grad_system.py:69-79), two right-hand sides at once
+__global__ void __launch_bounds__(256) k_masked_dot2(int n, const double *__restrict__ z, const int *__restrict__ frozen, const double *__restrict__ a,
+                                                     const double *__restrict__ b, double *out2)
+{
+    double sa = 0, sb = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (!frozen[i]) { sa += z[i] * a[i]; sb += z[i] * b[i]; }
+    sa = block_sum(sa);
+    sb = block_sum(sb);
+    if (threadIdx.x == 0) { out2[0] = sa; out2[1] = sb; }
+}
+
 // cell Hessian of a tetrahedral body: reduced 9x9 by the reference's nine unit perturbations, optionally through
 // SPD_Projector(9, K=20), expanded to the 16 blocks of the cell (Elastic.compute_Hessian, model_elastic_offset.py:95-167,
 // model_elastic_tactile.py:82-124).  One thread per cell; the 9x9 lives in local memory (bodies are a few thousand cells).
@@ -992,8 +1019,22 @@ void launch_hessian_counting(tsl_ctx *ctx, const double *pos, const double *z, d
     Sink<double> S = { nullptr, z, zf };
     launch_hessian_elements<double>(ctx, pos, S, nullptr, 0, 0, 0);
 }
-// Elastic.compute_deri (model_elastic_offset.py:423-438, model_elastic_tactile.py:329-347) is not on the system-ID path
-// built here (grad_kb only).
+void launch_tets_param_grad(tsl_ctx *ctx, const double *pos, const double *z, double *d_mu, double *d_lam, double *out2_dev)
+{
+    int n = ctx->cfg.n_verts;
+    k_fill_zero<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(d_mu, 3LL * n);
+    k_fill_zero<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(d_lam, 3LL * n);
+    ctx->launches += 2;
+    for (auto &t : ctx->tets) {
+        k_tets_deri<<<GRID(t.nc, 128), 128, 0, ctx->stream>>>(t, pos, d_mu, d_lam);
+        ctx->launches++;
+    }
+    if (z) {
+        // one block: deterministic order; the bodies are small and this runs once per backward step
+        k_masked_dot2<<<1, 256, 0, ctx->stream>>>(3 * n, z, ctx->frozen, d_mu, d_lam, out2_dev);
+        ctx->launches++;
+    }
+}
 void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alpha, double *pos)
 {
     int n = 3 * ctx->cfg.n_verts;

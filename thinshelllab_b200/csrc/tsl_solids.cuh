@@ -188,6 +188,36 @@ TSL_HD void tet_grad(const TetParams &t, const double *F, const double *B, doubl
         g[3] = g[3] - g[i];
     }
 }
+// d(elastic force)/d(mu) and /d(lam) on the 4 vertices (Elastic.compute_deri, model_elastic_offset.py:423-438 /
+// model_elastic_tactile.py:329-347).  The reference splits the stress as P = P1 + P2 with P1 / mu and P2 / lam taken as the
+// derivatives; for the tactile model that split is mu (F - J F^-T) + lam (J - 1) J F^-T (its own, not the alpha form of the force).
+TSL_HD void tet_deri(const TetParams &t, const double *F, const double *B, double W, d3 *gmu, d3 *glam)
+{
+    double Fi[9], P1[9], P2[9], H1[9], H2[9];
+    m3inv(F, Fi);
+    double J = m3det(F);
+    if (t.kind == 0) {
+        if (J < 0.01) J = 0.01;
+        double lj = log(J);
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) { P1[3 * i + j] = t.mu * (F[3 * i + j] - Fi[3 * j + i]); P2[3 * i + j] = t.lam * lj * Fi[3 * j + i]; }
+    } else {
+#pragma unroll
+        for (int i = 0; i < 3; i++)
+#pragma unroll
+            for (int j = 0; j < 3; j++) { P1[3 * i + j] = t.mu * (F[3 * i + j] - J * Fi[3 * j + i]); P2[3 * i + j] = t.lam * (J - 1) * J * Fi[3 * j + i]; }
+    }
+    m3mul_bt(P1, B, H1); m3mul_bt(P2, B, H2);
+    gmu[3] = mk(0, 0, 0); glam[3] = mk(0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        gmu[i] = mk(-W * H1[i] / t.mu, -W * H1[3 + i] / t.mu, -W * H1[6 + i] / t.mu);
+        glam[i] = mk(-W * H2[i] / t.lam, -W * H2[3 + i] / t.lam, -W * H2[6 + i] / t.lam);
+        gmu[3] = gmu[3] - gmu[i]; glam[3] = glam[3] - glam[i];
+    }
+}
 // reduced 9x9 Hessian over (vertex n < 3, dim): H9[(n,dim)][(i,j)] = d2E / dx_{n,dim} dx_{i,j}, built from the 9 unit
 // perturbations of Ds exactly as the reference does (dP for dF = e_dim e_n^T B)
 TSL_HD void tet_H9(const TetParams &t, const double *F, const double *B, double W, double *H9)

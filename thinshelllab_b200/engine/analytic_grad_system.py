@@ -54,4 +54,9 @@ class Grad:
             self._pos_buffer[step], self._pos_buffer[step - 1], self._ref_angle_buffer[step - 1, 0],
             self._pos_grad[step], self._pos_grad[step - 1], pg_tm2, self._angleref_grad[step, 0], self._angleref_grad[step - 1, 0],
             self._grad_kb, self._z, clamp=self.clamp, rel_tol=rel_tol, max_iters=max_iters)
+        if self.count_mu_lam_grad and sys.engine.tet_bodies:
+            # Grad.get_parameters_grad (:69-75): grad_mu / grad_lam += sum over free DOFs of z d_mu / z d_lam
+            _, _, (gm, gl) = sys.engine.elastic_param_grad(self._z)
+            self.grad_mu[None] = self.grad_mu[None] + gm
+            self.grad_lam[None] = self.grad_lam[None] + gl
         return self.last_solve
