@@ -166,14 +166,18 @@ def secondary_50k(args, dev):
 
 def secondary_solids(args, dev):
     """BASELINE.json configs[0] (Scene_folding: cloth strip + table + tactile pad on a gripper, T = 3 rollout + trajectory adjoint, the
-    state of tests/golden/folding.npz) and a configs[3]-style scene (316 x 316 = 200 k-triangle sheet on the table with the volumetric
+    scene state of thinshelllab_b200/data/scene_folding_cloth0p1.npz) and a configs[3]-style scene (316 x 316 = 200 k-triangle sheet on the table with the volumetric
     tactile pad pressed into it; contacts against moving triangles), one GPU, state resident in HBM"""
     import torch
     from thinshelllab_b200.agent.traj_opt_single import agent_trajopt
     from thinshelllab_b200.engine.analytic_grad_single import Grad
     from thinshelllab_b200.synthetic import pad_sheet_scene
     from thinshelllab_b200.task_scene.Scene_folding import Scene
-    g = np.load(os.path.join(ROOT, "tests", "golden", "folding.npz"))
+    g = np.load(os.path.join(ROOT, "thinshelllab_b200", "data", "scene_folding_cloth0p1.npz"))
+    T0 = 3
+    traj0 = np.zeros((T0, 1, 6))
+    for i in range(1, T0):                       # the press-and-tilt trajectory of the golden run (oracle/gen_goldens.py:gen_folding)
+        traj0[i, 0] = [2e-4 * i, -1e-4 * i, -4e-4 * i, 2e-3 * i, 1e-2 * i, -3e-3 * i]
     out = {}
 
     def rollout(s, T, traj, reps):
@@ -210,7 +214,7 @@ def secondary_solids(args, dev):
 
     s = Scene(g, device=dev)
     out["configs[0] Scene_folding fwd + trajectory adjoint"] = dict(scene="cloth 15x3 (90 tris) + frozen table + tactile pad (1365 tets) on a gripper",
-                                                                    **rollout(s, int(g["T"]), g["traj"], 2))
+                                                                    **rollout(s, T0, traj0, 2))
     del s
     N, T = 316, 4
     s = pad_sheet_scene(N, g, device=dev)

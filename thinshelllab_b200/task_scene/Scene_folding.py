@@ -41,7 +41,7 @@ class _ElasticView:
         return TensorField(self._s.engine.pos[self.offset:self.offset + self.n_verts])
 
 
-_DEFAULT_STATE = os.path.join(os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))), "tests", "golden", "folding.npz")
+_DEFAULT_STATE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "scene_folding_cloth0p1.npz")
 
 
 class Scene:
@@ -49,7 +49,7 @@ class Scene:
         """reference signature: Scene(cloth_size=0.06, device="cuda:0") (code/task_scene/Scene_folding.py:27).  The scene arrays come
         from `state` (a mapping with the keys of tests/golden/folding.npz, see oracle/gen_goldens.py:gen_folding; also accepted as the
         first positional argument), else from the file named by TSL_SCENE_STATE, else -- for cloth_size = 0.1, the size every
-        reference driver uses -- from the state shipped with the tests."""
+        reference driver uses -- from thinshelllab_b200/data/scene_folding_cloth0p1.npz (tools/make_scene_state.py)."""
         if state is None and hasattr(cloth_size, "keys"):
             state, cloth_size = cloth_size, None
         if state is None:
