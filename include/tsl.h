@@ -187,6 +187,19 @@ int tsl_gripper_apply(tsl_ctx *ctx, int v_offset, int n_bound, const int *bound_
 int tsl_gripper_gather(tsl_ctx *ctx, const double *z_frozen_dev, int v_offset, int n_bound, const int *bound_idx_dev,
                        const double *Fx_dev, const float *rotmat9_host, double clamp_pos, double clamp_angle, double *out6_host);
 
+/* ---- strip partition over the GPUs of one node (forward step) ------------------------------------------------
+ * One process and one context per GPU.  The context of rank r describes the grid rows [first owned - ghost_lo_rows, last owned +
+ * ghost_hi_rows] of a longer sheet (cloth rows are contiguous in vertex numbering; 2 ghost rows on every inner side, 0 on the outer
+ * sides of the first / last rank) in its own coordinate frame, plus whatever frozen bodies lie under that strip.  After tsl_dist_init,
+ * tsl_step_forward / tsl_energy / tsl_solve (fp32 PCG) act on the global sheet: assembly is local (every element touching an owned
+ * vertex is present), the preconditioner is the local multigrid cycle (block-Jacobi over the strips), and NCCL carries the ghost rows of
+ * the PCG direction (send/recv with the two neighbours per iteration), the PCG scalars (p.Ap; (r.z, |r|^2) as one message) and the
+ * Newton driver's energy / |p|_inf / F.p.  The reference has no multi-GPU path; this is north_star's partition.
+ * tsl_dist_unique_id: 128-byte ncclUniqueId made by rank 0, to be broadcast by the caller (torch.distributed). */
+int tsl_dist_unique_id(void *out128_host);
+int tsl_dist_init(tsl_ctx *ctx, const void *id128_host, int rank, int world, int ghost_lo_rows, int ghost_hi_rows);
+int tsl_dist_stats(tsl_ctx *ctx, long long *halo_msgs_out, long long *allreduces_out);
+
 /* ---- introspection used by the parity tests and the benchmark ---------------------------------- */
 int tsl_get_residual(tsl_ctx *ctx, double *F_host);                     /* BaseScene.F [3 n_verts] */
 int tsl_get_matrix_nnzb(tsl_ctx *ctx, int *nnzb_out);                   /* number of 3x3 blocks (unpadded) */

@@ -146,6 +146,27 @@ class ShellEngine:
         self._ck(self.L.tsl_finalize(self.ctx))
         self.finalized = True
 
+    def dist_init(self, rank, world, ghost_lo_rows, ghost_hi_rows):
+        """strip partition (include/tsl.h: tsl_dist_init).  The ncclUniqueId is made by rank 0 and broadcast through the
+        torch.distributed process group the caller has already initialised (backend nccl)."""
+        import torch.distributed as dist
+        buf = (C.c_ubyte * 128)()
+        if world > 1:
+            t = torch.zeros(128, dtype=torch.uint8, device=self.device)
+            if rank == 0:
+                self._ck(self.L.tsl_dist_unique_id(buf))
+                t.copy_(torch.frombuffer(bytearray(buf), dtype=torch.uint8))
+            dist.broadcast(t, 0)
+            raw = bytes(t.cpu().numpy().tobytes())
+            buf = (C.c_ubyte * 128).from_buffer_copy(raw)
+        self._ck(self.L.tsl_dist_init(self.ctx, buf, int(rank), int(world), int(ghost_lo_rows), int(ghost_hi_rows)))
+        self.dist = (int(rank), int(world), int(ghost_lo_rows), int(ghost_hi_rows))
+
+    def dist_stats(self):
+        a, b = C.c_longlong(), C.c_longlong()
+        self._ck(self.L.tsl_dist_stats(self.ctx, C.byref(a), C.byref(b)))
+        return {"halo_exchanges": a.value, "allreduces": b.value}
+
     def reset_contact_state(self):
         self._ck(self.L.tsl_reset_contact_state(self.ctx))
 

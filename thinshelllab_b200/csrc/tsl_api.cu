@@ -508,6 +508,7 @@ int tsl_contact_detect(tsl_ctx *ctx, int *n_out)
 static int energy_sync(tsl_ctx *ctx, double *out)
 {
     launch_energy(ctx, ctx->pos, ctx->red_out);
+    TRY(dist_allreduce(ctx, ctx->red_out, 1));               // strip partition: every rank summed the elements it owns
     CK(cudaMemcpyAsync(ctx->red_host, ctx->red_out, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     *out = ctx->red_host[0];
@@ -725,6 +726,10 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         if (fnorm_prev > 0 && fnorm > 0) eta = std::min(0.1, std::max(1e-3, 0.9 * (fnorm / fnorm_prev) * (fnorm / fnorm_prev)));
         fnorm_prev = fnorm;
         CK(cudaMemcpyAsync(ctx->x1, ctx->pos, sizeof(double) * n3, cudaMemcpyDeviceToDevice, s));
+        if (ctx->newton_mode != 0 && (ss.flags & 1) && ctx->dist.on) {
+            ctx->err = "strip partition: the negative-curvature move of the Newton driver is not partitioned (use Newton mode 0 or 2)";
+            return TSL_ERR_UNSUPPORTED;
+        }
         if (ctx->newton_mode != 0 && (ss.flags & 1)) {
             // ---- negative curvature at PCG iteration ss.iters: x_k is in sol, p_k in cg_p
             st.flags |= 1;
@@ -779,7 +784,9 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         }
         st.flags |= (ss.flags & 2);
         launch_absmax(ctx, ctx->sol, n3, ctx->red_out + 1);
-        launch_dot(ctx, ctx->F, ctx->sol, n3, ctx->red_out + 3);
+        launch_dot(ctx, ctx->F, ctx->sol, n3, ctx->red_out + 3);   // (F is zero on ghost rows: owned DOFs only)
+        TRY(dist_allreduce(ctx, ctx->red_out + 1, 1, true));
+        TRY(dist_allreduce(ctx, ctx->red_out + 3, 1));
         CK(cudaMemcpyAsync(ctx->red_host + 1, ctx->red_out + 1, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
         CK(cudaStreamSynchronize(s));
         double p_norm = ctx->red_host[1];

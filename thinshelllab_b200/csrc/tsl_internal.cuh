@@ -117,10 +117,10 @@ struct MgDev {
 // iteration index in any kernel argument: a one-thread "rotate" kernel at the end of every iteration moves the
 // freshly accumulated sums into place, so one captured CUDA graph serves every iteration.
 struct KrylovScalars {
-    // PCG
+    // PCG (pq | rz_new, rr_new adjacent: the strip-partitioned solve all-reduces them as one message)
     double pq;            // p.Ap of the current iteration
-    double rz, rz_new;    // r.z before / after the update
-    double rr, rr_new;    // |r|^2 before / after the update
+    double rz_new, rr_new;   // r.z and |r|^2 after the update
+    double rz, rr;        // r.z and |r|^2 before the update
     // BiCGStab
     double rho, rho_old, rho_next;   // rhat.r of this / the previous / the next iteration
     double rhv, ts, tt;              // rhat.v, t.s, t.t
@@ -128,6 +128,19 @@ struct KrylovScalars {
     double rr0;           // |b|^2 (host side only)
     int flags;            // bit0 negative curvature / breakdown (iteration frozen)
     int iter;             // iterations completed
+};
+
+// Strip partition of the cloth grid over the ranks of one node: this context holds the
+// grid rows [first owned row - ghost_lo, last owned row + ghost_hi] of a longer sheet; rows are contiguous in vertex numbering.
+struct DistCtx {
+    bool on = false;
+    int rank = 0, world = 1;
+    void *comm = nullptr;          // ncclComm_t
+    int row_len = 0;               // vertices per grid row (M + 1)
+    int ghost_lo = 0, ghost_hi = 0;   // ghost rows below / above the owned rows
+    int own0 = 0, own1 = 0x7fffffff;  // owned cloth vertices [own0, own1) (local ids)
+    int nvc = 0;                   // cloth vertices of this context
+    long long halo_msgs = 0, allreduces = 0;
 };
 
 struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; const void *key = nullptr; };
@@ -208,4 +221,5 @@ struct tsl_ctx {
     double *d_kb = nullptr;                      // [n_verts][3]
     double *adj_rhs = nullptr, *adj_z = nullptr; // [3 n_verts]
     int error_flag_host = 0; int *error_flag = nullptr;   // device-side "unsupported" flags
+    tsl::DistCtx dist;
 };

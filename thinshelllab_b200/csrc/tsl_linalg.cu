@@ -90,7 +90,7 @@ __global__ void __launch_bounds__(256) k_spmv_dots(int n_rows, const int *__rest
 // fp32 only perturbs the system consistently.
 __global__ void __launch_bounds__(256) k_spmv_mixed(int n_rows, const int *__restrict__ slice_base, const int *__restrict__ colidx,
                                                     const float *__restrict__ val, const double *__restrict__ x, double *__restrict__ y,
-                                                    double *acc_xy, double *yc)
+                                                    double *acc_xy, double *yc, int own0, int own1)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     double xy = 0;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(256) k_spmv_mixed(int n_rows, const int *__res
             yc[3 * row] = 0; yc[3 * row + 1] = 0; yc[3 * row + 2] = 0;
         }
         y[3 * row] = a0; y[3 * row + 1] = a1; y[3 * row + 2] = a2;
-        xy = x[3 * row] * a0 + x[3 * row + 1] * a1 + x[3 * row + 2] * a2;
+        if (row >= own0 && row < own1) xy = x[3 * row] * a0 + x[3 * row + 1] * a1 + x[3 * row + 2] * a2;   // strip partition: owned rows only
     }
     block_atomic_sum2(xy, 0.0, acc_xy, nullptr);
 }
@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(256) k_pcg_init(int n_rows, int n_alloc, const
 // Optionally also the first Chebyshev step of the V-cycle's level 0 on the new residual (mg_d = c D^-1 r, mg_x0 = mg_d).
 __global__ void __launch_bounds__(256) k_pcg_update(int n_rows, const double *__restrict__ p, const double *__restrict__ q,
                                                     double *x, double *r, float *r32, KrylovScalars *ks,
-                                                    const float *__restrict__ mg_dinv, float *mg_d, float *mg_x0, const float *__restrict__ mg_coef)
+                                                    const float *__restrict__ mg_dinv, float *mg_d, float *mg_x0, const float *__restrict__ mg_coef,
+                                                    int own0, int own1)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     double pq = ks->pq, rz = ks->rz;
@@ -243,6 +244,7 @@ __global__ void __launch_bounds__(256) k_pcg_update(int n_rows, const double *__
     if (row < n_rows) {
         double alpha = rz / pq;
         double r0 = r[3 * row] - alpha * q[3 * row], r1 = r[3 * row + 1] - alpha * q[3 * row + 1], r2 = r[3 * row + 2] - alpha * q[3 * row + 2];
+        if (row < own0 || row >= own1) r0 = r1 = r2 = 0.0;      // strip partition: the residual of a ghost row belongs to its owner
         x[3 * row] += alpha * p[3 * row]; x[3 * row + 1] += alpha * p[3 * row + 1]; x[3 * row + 2] += alpha * p[3 * row + 2];
         r[3 * row] = r0; r[3 * row + 1] = r1; r[3 * row + 2] = r2;
         float f0 = (float)r0, f1 = (float)r1, f2 = (float)r2;
@@ -342,13 +344,17 @@ static int pcg_iteration_body(tsl_ctx *ctx, const float *opval)
     KrylovScalars *ks = ctx->ks;
     cudaStream_t s = ctx->stream;
     double *yc = side_pass<float>(ctx, ctx->cside32, ctx->cg_p);
-    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, &ks->pq, yc);
+    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, opval, ctx->cg_p, ctx->cg_q, &ks->pq, yc, ctx->dist.own0, ctx->dist.own1);
+    TRYR(dist_allreduce(ctx, &ks->pq, 1));
     const float *mg_dinv, *mg_coef; float *mg_d, *mg_x0;
     mg_first_step_targets(ctx, &mg_dinv, &mg_d, &mg_x0, &mg_coef);
-    k_pcg_update<<<GRID(n, 256), 256, 0, s>>>(n, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ctx->cg_r32, ks, mg_dinv, mg_d, mg_x0, mg_coef);
+    k_pcg_update<<<GRID(n, 256), 256, 0, s>>>(n, ctx->cg_p, ctx->cg_q, ctx->cg_x, ctx->cg_r, ctx->cg_r32, ks, mg_dinv, mg_d, mg_x0, mg_coef,
+                                                  ctx->dist.own0, ctx->dist.own1);
     ctx->launches += 2;
     TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, &ks->rz_new, mg_dinv != nullptr));
+    TRYR(dist_allreduce(ctx, &ks->rz_new, 2));                 // (r.z, |r|^2): one 16-byte message
     k_pcg_direction<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, 0, ctx->cg_z, ctx->cg_p, ks);
+    TRYR(dist_halo(ctx, ctx->cg_p));                           // ghost rows of the new direction from their owners
     k_pcg_rotate<<<1, 1, 0, s>>>(0, ks);
     ctx->launches += 2;
     return TSL_OK;
@@ -376,7 +382,9 @@ static int pcg_start_body(tsl_ctx *ctx, const double *rhs)
     k_pcg_init<<<GRID(nr, 256), 256, 0, s>>>(n, nr, rhs, ctx->cg_x, ctx->cg_r, ctx->cg_r32, ctx->ks);
     ctx->launches++;
     TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, &ctx->ks->rz_new));
+    TRYR(dist_allreduce(ctx, &ctx->ks->rz_new, 2));
     k_pcg_direction<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, 1, ctx->cg_z, ctx->cg_p, ctx->ks);
+    TRYR(dist_halo(ctx, ctx->cg_p));
     k_pcg_rotate<<<1, 1, 0, s>>>(1, ctx->ks);
     ctx->launches += 2;
     return TSL_OK;
@@ -426,7 +434,7 @@ int probe_curvature(tsl_ctx *ctx, const float *opval, const double *dir, double 
     int n = ctx->n_solve;
     cudaStream_t s = ctx->stream;
     CK(cudaMemsetAsync(&ctx->ks->pq, 0, sizeof(double), s));
-    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, opval, dir, ctx->cg_q, &ctx->ks->pq, nullptr);
+    k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, opval, dir, ctx->cg_q, &ctx->ks->pq, nullptr, 0, 0x7fffffff);
     ctx->launches++;
     CK(cudaMemcpyAsync(&ctx->ks_host->pq, &ctx->ks->pq, sizeof(double), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
@@ -448,7 +456,7 @@ int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out)
     CK(cudaEventRecord(e0, s));
     for (int it = 0; it < iters; it++) {
         if (what == 1) {
-            k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32, ctx->cg_p, ctx->cg_q, &ctx->ks->pq, nullptr);
+            k_spmv_mixed<<<GRID(n, 256), 256, 0, s>>>(n, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32, ctx->cg_p, ctx->cg_q, &ctx->ks->pq, nullptr, 0, 0x7fffffff);
             ctx->launches++;
         } else if (what == 5) TRYR(mg_apply(ctx, ctx->cg_r32, ctx->cg_z, nullptr));
         else if (what == 6) TRYR(mg_setup_replay(ctx));

@@ -104,11 +104,15 @@ __global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_v
                                                 const double *__restrict__ prev_pos, const double *__restrict__ vel,
                                                 const double *__restrict__ mass, d3 g, double dt,
                                                 ContactDev con, int nc, ContactParams cp, TetSet ts, const double *__restrict__ vgrav,
+                                                int own0, int own1, int nvc,
                                                 double *partial, unsigned int *ticket, double *out)
 {
+    // strip partition: a cloth vertex / triangle (by its first vertex) / constraint (by its query vertex) is counted by the rank
+    // that owns it; [own0, own1) = everything when the context is not partitioned
     double E = 0;
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int i = tid; i < n_verts; i += nth) {
+        if (i < nvc && (i < own0 || i >= own1)) continue;
         d3 x = ld3(pos, i), xp = ld3(prev_pos, i), v = ld3(vel, i);
         double m = mass[i];
         d3 X = x - xp - dt * v;
@@ -130,6 +134,7 @@ __global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_v
     if (n_cloth > 0)
         for (int i = tid; i < c.NF; i += nth) {
             FaceV f = load_face(c, pos, i);
+            if (f.v[0] < own0 || f.v[0] >= own1) continue;
             double area = 0.5 * norm(cross(f.p[1] - f.p[0], f.p[2] - f.p[0]));
             double V = rest_area(c.P);
             E += c.P.Ka * (1 - area / V) * (1 - area / V) * V;
@@ -148,6 +153,7 @@ __global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_v
         }
     for (int i = tid; i < nc; i += nth) {
         const int *idx = con.idx + 4 * i;
+        if (idx[3] < nvc && (idx[3] < own0 || idx[3] >= own1)) continue;
         d3 x0 = ld3(pos, idx[0]), x1 = ld3(pos, idx[1]), x2 = ld3(pos, idx[2]), xv = ld3(pos, idx[3]);
         d3 p1 = x1 - x0, p2 = x2 - x0, p = xv - x0;
         d3 cr = cross(p1, p2);
@@ -932,6 +938,7 @@ void launch_energy(tsl_ctx *ctx, const double *pos, double *out_dev)
     d3 g = mk(ctx->cfg.gravity[0], ctx->cfg.gravity[1], ctx->cfg.gravity[2]);
     k_energy<<<ctx->red_blocks, 256, 0, ctx->stream>>>(c, (int)ctx->cloths.size(), ctx->cfg.n_verts, pos, ctx->prev_pos, ctx->vel,
                                                         ctx->mass, g, ctx->cfg.dt, ctx->con, ctx->nc, cp, tet_set(ctx), ctx->vgrav,
+                                                        ctx->dist.own0, ctx->dist.own1, ctx->dist.on ? ctx->dist.nvc : 0,
                                                         ctx->red_partial, ctx->red_ticket, out_dev);
     ctx->launches++;
 }
@@ -956,6 +963,7 @@ void launch_residual(tsl_ctx *ctx, const double *pos)
     }
     k_mask_frozen<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(3 * n, ctx->frozen, ctx->F);
     ctx->launches++;
+    if (ctx->dist.on) launch_zero_ghost(ctx, ctx->F);      // ghost rows only saw part of their elements: the owner has them complete
 }
 void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kb)
 {   // Cloth.compute_deri_Kb: d_kb = -(bending gradient) / Kb

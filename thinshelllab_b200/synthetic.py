@@ -83,3 +83,58 @@ def pad_sheet_scene(N, pad, device="cuda:0", **kw):
     from .task_scene.Scene_folding import Scene
     st = pad_sheet_state(N, pad, **kw)
     return Scene(st, device=device, max_newton=200)
+
+
+# ------------------------------------------------------------------------------------------------ strip partition
+def strip_spec(R, M, rank, world, dx=0.002, dt=5e-3, seed=0, z0=0.0003, bump=0.25, noise=0.01, k_contact=40000.0, mu=0.5, ghost=2):
+    """Rank `rank` of `world` of a sheet of world*R vertex rows x (M+1) columns cut into strips of R rows (R even keeps the
+    alternating triangulation of Cloth.init_mesh aligned across strips): the local rows are the owned ones plus `ghost` rows on every
+    inner side, expressed in a frame centred on the strip, over a frozen table slab that covers the strip.  world = 1 is the whole
+    sheet on one GPU (the reference of the partition's parity test).  Start state as sheet_spec: flat + bump + seeded noise, defined on
+    the GLOBAL grid so that every partition sees the same sheet."""
+    assert R % 2 == 0 or world == 1, "strips must start on an even grid row"
+    G = world * R
+    g_lo = ghost if rank > 0 else 0
+    g_hi = ghost if rank < world - 1 else 0
+    a, b = rank * R - g_lo, (rank + 1) * R + g_hi                      # local rows [a, b) of the global grid
+    rows = b - a
+    rng = np.random.default_rng(seed)
+    nz = rng.uniform(-noise * dx, noise * dx, (G, M + 1, 3))
+    i, j = np.meshgrid(np.arange(a, b), np.arange(M + 1), indexing="ij")
+    xg = i * dx - 0.5 * (G - 1) * dx
+    xc = 0.5 * (xg[0, 0] + xg[-1, 0])                                    # local frame: strip centred at x = 0
+    cpos = np.stack([xg - xc, j * dx - 0.5 * M * dx, z0 + bump * dx * (1 + np.sin(2 * np.pi * i / 32.0) * np.cos(2 * np.pi * j / 32.0))], -1)
+    cpos = (cpos + nz[a:b]).reshape(-1, 3)
+    sx, sy = (rows - 1) * dx + 0.02, M * dx + 0.02
+    tdx = 0.003
+    tnx, tny = int(np.ceil(sx / tdx)) + 1, int(np.ceil(sy / tdx)) + 1
+    Len = tdx * (max(tnx, tny) - 1)
+    toff = (-0.5 * (tnx - 1) * tdx, -0.5 * (tny - 1) * tdx, -tdx)
+    grid_n = max(132, 2 * int(np.ceil((0.5 * max((tnx - 1) * tdx, (tny - 1) * tdx) + 0.01) / 0.003)) + 2)
+    return dict(R=R, M=M, rank=rank, world=world, rows=rows, ghost_lo=g_lo, ghost_hi=g_hi, dx=dx, dt=dt, cloth_pos=cpos, x_shift=xc,
+                table_size=Len, table_N=(tnx, tny, 2), table_offset=toff, grid_n=grid_n, k_contact=k_contact, mu=mu,
+                max_n_constraints=rows * (M + 1) + 16, n_tris_owned=None, own0=g_lo * (M + 1), own1=(rows - g_hi) * (M + 1),
+                n_tris_global=2 * (G - 1) * M)
+
+
+def strip_scene(R, M, rank, world, device="cuda:0", **kw):
+    """the local scene of one rank of the strip-partitioned sheet; engine.dist_init is called here (needs an initialised
+    torch.distributed NCCL group when world > 1)"""
+    import torch
+
+    from .task_scene.Scene_bouncing import Scene
+    sp = strip_spec(R, M, rank, world, **kw)
+    rows = sp["rows"]
+    s = Scene(cloth_size=(rows - 1) * sp["dx"], cloth_N=rows - 1, cloth_M=M, dt=sp["dt"], table_size=sp["table_size"], table_N=sp["table_N"],
+              table_offset=sp["table_offset"], cloth_offset=(0.0, 0.0, 0.0), reset_offset=(0.0, 0.0, 0.0), k_contact=sp["k_contact"],
+              max_n_constraints=sp["max_n_constraints"], grid_n=sp["grid_n"], device=device)
+    s.mu_cloth_elastic[None] = sp["mu"]
+    s.init_all()
+    NV = rows * (M + 1)
+    s.engine.pos[:NV] = torch.from_numpy(sp["cloth_pos"]).to(s.engine.device)
+    s.engine.prev_pos.copy_(s.engine.pos)
+    s.engine.vel.zero_()
+    s.engine.cloth_ref_angle[0].zero_()
+    s.engine.dist_init(rank, world, sp["ghost_lo"], sp["ghost_hi"])
+    s.spec = sp
+    return s
