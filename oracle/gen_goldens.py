@@ -440,6 +440,55 @@ def gen_folding(T=3, tag="folding"):
     print("wrote", tag)
 
 
+def gen_trajopt_folding(T=3, iters=2, lr=0.001):
+    """the optimisation loop of training/trajopt_folding.py:50-140, statement by statement, with the reference's own engine, agent and
+    optimiser under the emulation; records what the script does not print (gripper gradient, trajectory after every Adam step)"""
+    import json
+    from thinshelllab.task_scene.Scene_folding import Scene
+    from thinshelllab.engine.geometry import projection_query
+    from thinshelllab.engine.analytic_grad_single import Grad
+    from thinshelllab.agent.traj_opt_single import agent_trajopt
+    from thinshelllab.optimizer.optim import Adam_single
+    sys_ = Scene(cloth_size=0.1)
+    sys_.device = "cpu"; sys_.H.device = "cpu"
+    sys_.cloths[0].Kb[None] = 400.0
+    analy_grad = Grad(sys_, T, sys_.elastic_cnt - 1)
+    adam = Adam_single((T, sys_.elastic_cnt - 1, 6), lr, 0.9, 0.9999, 1e-8)
+    agent = agent_trajopt(T, sys_.elastic_cnt - 1, max_moving_dist=0.001)
+    sys_.init_all()
+    analy_grad.init_mass(sys_)
+    sys_.reset()
+    sys_.mu_cloth_elastic[None] = 5.0
+    adam.reset()
+    out = dict(what="optimisation loop of the reference's training/trajopt_folding.py (statements :73-140, --tot_step 3 --iter 2 --lr 0.001) run with "
+                    "the reference's own Scene_folding / Grad / agent_trajopt / Adam_single under the Taichi emulation shim (SuperLU in place of CuPy spsolve)",
+               generated_by="python oracle/gen_goldens.py trajopt_folding", args=dict(tot_step=T, iter=iters, lr=lr, Kb=400.0, mu_cloth_elastic=5.0),
+               total_reward=[], gripper_grad=[], traj_after_step=[])
+    t0 = time.time()
+    for i in range(iters):
+        analy_grad.copy_pos(sys_, 0)
+        for frame in range(1, T):
+            agent.get_action(frame)
+            sys_.action(frame, agent.delta_pos, agent.delta_rot)
+            sys_.time_step(projection_query, frame)
+            analy_grad.copy_pos(sys_, frame)
+        out["total_reward"].append(float(sys_.compute_reward(1.0, -1.0)))
+        analy_grad.get_loss_fold(sys_, 1.0, -1.0)
+        for j in range(T - 1, 0, -1):
+            analy_grad.transfer_grad(j, sys_, projection_query)
+        out["gripper_grad"].append(analy_grad.gripper_grad.to_numpy().tolist())
+        sys_.reset()
+        adam.step(agent.traj, analy_grad.gripper_grad)
+        agent.fix_action(0.015)
+        analy_grad.reset()
+        out["traj_after_step"].append(agent.traj.to_numpy().tolist())
+        print(f"iter {i} reward {out['total_reward'][-1]} t {time.time() - t0:.0f}s", flush=True)
+        out["final_traj"] = out["traj_after_step"][-1]
+        with open(os.path.join(OUT, "trajopt_folding_T3.json"), "w") as fh:
+            json.dump(out, fh, indent=1)
+    print("wrote trajopt_folding_T3.json")
+
+
 if __name__ == "__main__":
     what = sys.argv[1:] or ["cloth", "spd"]
     if "cloth" in what:
@@ -452,3 +501,5 @@ if __name__ == "__main__":
         gen_bouncing()
     if "folding" in what:
         gen_folding()
+    if "trajopt_folding" in what:
+        gen_trajopt_folding()

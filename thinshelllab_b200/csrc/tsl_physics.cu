@@ -693,15 +693,35 @@ __global__ void __launch_bounds__(64) k_hessian_tets(TetDev t, const double *__r
 template <typename T>
 __global__ void __launch_bounds__(64) k_hessian_contact_general(ContactDev con, int nc, ContactParams cp, const double *__restrict__ pos,
                                                                 const int *__restrict__ frozen, const int *__restrict__ diag_pb,
-                                                                Sink<T> S, T *side, int spd)
+                                                                Sink<T> S, T *side, int spd, int newton_model)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= nc) return;
     const int *idx = con.idx + 4 * i;
     d3 x0 = ld3(pos, idx[0]), x1 = ld3(pos, idx[1]), x2 = ld3(pos, idx[2]), xv = ld3(pos, idx[3]);
     double G[9], H[81];
-    bool active = contact_normal_full(x1 - x0, x2 - x0, xv - x0, cp.k_contact, cp.eps_contact, G, H);
-    if (active && spd) spd_project<9>(H, 20);
+    bool active;
+    bool tri_frozen = true;
+    for (int q = 0; q < 3; q++) for (int a = 0; a < 3; a++) tri_frozen = tri_frozen && frozen[3 * idx[q] + a];
+    if (newton_model && tri_frozen && !S.zf) {
+        // forward Newton matrix, triangle of a frozen body (most constraints of a sheet lying on the table): only the (v, v) block
+        // survives the frozen mask and d is linear in x_v, so the normal part is k n n^T -- no 9x9 needed (as k_hessian_contact)
+        d3 cr = cross(x1 - x0, x2 - x0);
+        double c = norm(cr);
+        active = dot(cr, xv - x0) / c < cp.eps_contact;
+#pragma unroll
+        for (int q = 0; q < 81; q++) H[q] = 0;
+        if (active) {
+            double n[3] = { cr.x / c, cr.y / c, cr.z / c };
+#pragma unroll
+            for (int r = 0; r < 3; r++)
+#pragma unroll
+                for (int q = 0; q < 3; q++) H[(6 + r) * 9 + 6 + q] = cp.k_contact * n[r] * n[q];
+        }
+    } else {
+        active = contact_normal_full(x1 - x0, x2 - x0, xv - x0, cp.k_contact, cp.eps_contact, G, H);
+        if (active && spd) spd_project<9>(H, 20);
+    }
     const double *w = con.w + 3 * i, *Tm = con.T + 6 * i, *dx0 = con.dx0 + 3 * i;
     d3 dx = xv - (w[0] * x0 + w[1] * x1 + w[2] * x2) - mk(dx0[0], dx0[1], dx0[2]);
     double u[2] = { Tm[0] * dx.x + Tm[1] * dx.y + Tm[2] * dx.z, Tm[3] * dx.x + Tm[4] * dx.y + Tm[5] * dx.z };
@@ -999,7 +1019,7 @@ static void launch_hessian_elements(tsl_ctx *ctx, const double *pos, Sink<T> S, 
     }
     if (ctx->nc > 0) {
         if (ctx->general_contact)
-            k_hessian_contact_general<T><<<GRID(ctx->nc, 64), 64, 0, ctx->stream>>>(ctx->con, ctx->nc, cp, pos, ctx->frozen, ctx->A.diag_pb, S, side, spd | newton_model);
+            k_hessian_contact_general<T><<<GRID(ctx->nc, 64), 64, 0, ctx->stream>>>(ctx->con, ctx->nc, cp, pos, ctx->frozen, ctx->A.diag_pb, S, side, spd | newton_model, newton_model);
         else
             k_hessian_contact<T><<<GRID(ctx->nc, 128), 128, 0, ctx->stream>>>(ctx->con, ctx->nc, cp, pos, ctx->frozen, ctx->A.diag_pb, S, spd | newton_model, ctx->error_flag);
         ctx->launches++;
