@@ -45,3 +45,35 @@ def test_single_process_passthrough():
     from thinshelllab_b200 import dist as td
     assert td.world() == 1
     assert td.aggregate(7, [1.5, 2.5]) == (7.0, [1.5, 2.5])
+
+
+def test_strip_partition_geometry_tiles_the_global_sheet():
+    """synthetic.strip_spec (host side of the strip partition): the owned rows of all ranks tile the global
+    sheet, ghost rows replicate the neighbours' first / last owned rows (what tsl_dist.cu's halo exchange moves), strips start on even
+    grid rows (the alternating triangulation of Cloth.init_mesh stays aligned) and every strip's table slab covers it"""
+    import numpy as np
+    from thinshelllab_b200.synthetic import strip_spec
+    R, M, world = 16, 24, 4
+    glob = strip_spec(world * R, M, 0, 1)
+    gx = glob["cloth_pos"].copy(); gx[:, 0] += glob["x_shift"]
+    row = M + 1
+    specs = [strip_spec(R, M, r, world) for r in range(world)]
+    owned = []
+    for r, sp in enumerate(specs):
+        x = sp["cloth_pos"].copy(); x[:, 0] += sp["x_shift"]
+        assert sp["ghost_lo"] == (2 if r > 0 else 0) and sp["ghost_hi"] == (2 if r < world - 1 else 0)
+        assert (r * R - sp["ghost_lo"]) % 2 == 0
+        assert sp["own1"] - sp["own0"] == R * row and sp["rows"] == R + sp["ghost_lo"] + sp["ghost_hi"]
+        owned.append(x[sp["own0"]:sp["own1"]])
+        if r > 0:      # my lower ghost rows = the lower neighbour's last owned rows (send offset rows_local - 2 ghost_hi there)
+            nb = specs[r - 1]; y = nb["cloth_pos"].copy(); y[:, 0] += nb["x_shift"]
+            lo = (nb["rows"] - 2 * nb["ghost_hi"]) * row
+            assert np.abs(x[:sp["ghost_lo"] * row] - y[lo:lo + nb["ghost_hi"] * row]).max() < 1e-15
+        if r < world - 1:
+            nb = specs[r + 1]; y = nb["cloth_pos"].copy(); y[:, 0] += nb["x_shift"]
+            assert np.abs(x[(sp["rows"] - sp["ghost_hi"]) * row:] - y[nb["ghost_lo"] * row:2 * nb["ghost_lo"] * row]).max() < 1e-15
+        tnx, tny, _ = sp["table_N"]
+        ext = np.abs(sp["cloth_pos"][:, :2]).max(0)
+        assert ext[0] <= 0.5 * (tnx - 1) * 0.003 and ext[1] <= 0.5 * (tny - 1) * 0.003
+    assert np.abs(np.concatenate(owned) - gx).max() < 1e-15
+    assert specs[0]["n_tris_global"] == 2 * (world * R - 1) * M
