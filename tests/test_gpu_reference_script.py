@@ -111,7 +111,8 @@ def test_folding_driver_call_sequence_matches_reference_run():
         assert abs(mine - ref) <= 1e-5 * max(abs(ref), 1e-3), (rewards, gold["total_reward"])
     if "final_traj" in gold:
         import numpy as np
-        assert np.abs(agent.traj.to_numpy() - np.array(gold["final_traj"])).max() <= 1e-5 * max(np.abs(gold["final_traj"]).max(), 1e-12)
+        # (1e-9 m / rad absolute: the golden trajectory is exactly zero, see the golden's note)
+        assert np.abs(agent.traj.to_numpy() - np.array(gold["final_traj"])).max() <= 1e-5 * np.abs(gold["final_traj"]).max() + 1e-9
 
 
 def test_unmodified_folding_script_if_present(tmp_path):
