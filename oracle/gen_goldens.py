@@ -319,18 +319,23 @@ def gen_bouncing(T=4, use_reset=False, tag="bouncing"):
     print("wrote", tag)
 
 
-def gen_folding(T=3, tag="folding"):
+def gen_folding(T=3, tag="folding", forming=False):
     """config 0: Scene_folding forward rollout + trajectory adjoint, following training/trajopt_folding.py:50-133
-    (cloth 15x3 + frozen table + tactile pad on a kinematic gripper)"""
+    (cloth 15x3 + frozen table + tactile pad on a kinematic gripper).  forming=True: the same for Scene_forming
+    (training/trajopt_forming.py:45-141: cloth 15x7, k_contact 20000, Kb 200, position loss get_loss_push)"""
     import scipy.sparse as sp
-    from thinshelllab.task_scene.Scene_folding import Scene
+    if forming:
+        from thinshelllab.task_scene.Scene_forming import Scene
+    else:
+        from thinshelllab.task_scene.Scene_folding import Scene
     from thinshelllab.engine.geometry import projection_query
     from thinshelllab.engine.analytic_grad_single import Grad
     from thinshelllab.agent.traj_opt_single import agent_trajopt
     from cupyx.scipy.sparse import linalg as fake_linalg
     s = Scene(cloth_size=0.1)
     s.device = "cpu"; s.H.device = "cpu"
-    s.cloths[0].Kb[None] = 400.0
+    Kb = 200.0 if forming else 400.0
+    s.cloths[0].Kb[None] = Kb
     g = Grad(s, T, s.elastic_cnt - 1)
     agent = agent_trajopt(T, s.elastic_cnt - 1, max_moving_dist=0.001)
     s.init_all()
@@ -342,7 +347,7 @@ def gen_folding(T=3, tag="folding"):
         traj[i, 0] = [2e-4 * i, -1e-4 * i, -4e-4 * i, 2e-3 * i, 1e-2 * i, -3e-3 * i]
     agent.traj.from_numpy(traj)
     pad = s.elastics[1]
-    out = dict(T=T, dt=s.dt, k_contact=s.k_contact, eps_contact=s.eps_contact, eps_v=s.eps_v, mu=5.0, Kb=400.0,
+    out = dict(T=T, dt=s.dt, k_contact=s.k_contact, eps_contact=s.eps_contact, eps_v=s.eps_v, mu=5.0, Kb=Kb,
                k_angle=s.cloths[0].k_angle[None], cloth_N=s.cloths[0].N, cloth_M=s.cloths[0].M, cloth_dx=s.cloths[0].dx,
                cloth_mass=s.cloths[0].mass, cloth_size=0.1, traj=traj,
                pos0=s.pos.to_numpy(), vel0=s.vel.to_numpy(), mass=s.mass.to_numpy(), frozen=s.frozen.to_numpy(),
@@ -408,13 +413,20 @@ def gen_folding(T=3, tag="folding"):
         out[f"f{frame}_ref_angle"] = s.cloths[0].ref_angle.to_numpy()
         g.copy_pos(s, frame)
         np.savez_compressed(os.path.join(OUT, f"{tag}_partial.npz"), **out)
-    out["reward"] = s.compute_reward(1.0, -1.0)
-    g.get_loss_fold(s, 1.0, -1.0)
-    # a position loss on the last frame as well, so that the adjoint right-hand side is not almost empty
-    pg = g.pos_grad.to_numpy()
     NVc = s.cloths[0].NV
-    pg[T - 1, :NVc, 2] = 1.0
-    g.pos_grad.from_numpy(pg)
+    if forming:
+        target = out["pos0"][:NVc].copy()
+        target[:, 2] -= 1e-3
+        out["target_pos"] = target
+        out["reward"] = s.compute_reward(target)
+        g.get_loss_push(s, target)
+    else:
+        out["reward"] = s.compute_reward(1.0, -1.0)
+        g.get_loss_fold(s, 1.0, -1.0)
+        # a position loss on the last frame as well, so that the adjoint right-hand side is not almost empty
+        pg = g.pos_grad.to_numpy()
+        pg[T - 1, :NVc, 2] = 1.0
+        g.pos_grad.from_numpy(pg)
     out["pos_grad_seed"] = g.pos_grad.to_numpy()
     out["angleref_grad_seed"] = g.angleref_grad.to_numpy()
     for j in range(T - 1, 0, -1):
@@ -501,5 +513,7 @@ if __name__ == "__main__":
         gen_bouncing()
     if "folding" in what:
         gen_folding()
+    if "forming" in what:
+        gen_folding(tag="forming", forming=True)
     if "trajopt_folding" in what:
         gen_trajopt_folding()

@@ -95,8 +95,17 @@ def _check_contacts(e, g, frame):
         assert np.abs(c[k][order_c] - ref).max() <= tol * max(np.abs(ref).max(), 1.0), k
 
 
+@pytest.mark.parametrize("forced,inject", [(True, True), (False, False)])
+def test_forming_forward_and_adjoint_match_reference(golden_dir, forced, inject):
+    """Scene_forming (cloth 15 x 7, k_contact 20000, Kb 200, position loss of training/trajopt_forming.py) through the same checks"""
+    path = os.path.join(golden_dir, "forming.npz")
+    if not os.path.exists(path):
+        pytest.skip("tests/golden/forming.npz not generated (oracle/gen_goldens.py forming)")
+    test_folding_forward_and_adjoint_match_reference(np.load(path), forced, inject, forming=True)
+
+
 @pytest.mark.parametrize("forced,inject", [(True, True), (True, False), (False, False)])
-def test_folding_forward_and_adjoint_match_reference(golden, forced, inject):
+def test_folding_forward_and_adjoint_match_reference(golden, forced, inject, forming=False):
     """forced: every frame starts from the reference's own previous frame (after this rollout's frame was checked to lie within
     3e-7 m of it), so that each term of every frame is compared on identical inputs; free-running: the rollout feeds itself and
     only the step results are compared.
@@ -107,10 +116,14 @@ def test_folding_forward_and_adjoint_match_reference(golden, forced, inject):
     g = golden
     T = int(g["T"])
     R = _Report()
-    s = Scene(g)
+    if forming:
+        from thinshelllab_b200.task_scene.Scene_forming import Scene as SceneCls
+    else:
+        SceneCls = Scene
+    s = SceneCls(g)
     e = s.engine
     NVc = s.cloths[0].NV
-    assert e.sizes()["n_verts"] == 502
+    assert e.sizes()["n_verts"] == g["pos0"].shape[0]
     agent = agent_trajopt(T, 1, max_moving_dist=0.001)
     agent.traj.from_numpy(g["traj"])
     grad = Grad(s, T, 1)
@@ -151,11 +164,16 @@ def test_folding_forward_and_adjoint_match_reference(golden, forced, inject):
             e.pos.copy_(torch.from_numpy(g[f"f{frame}_pos"])); e.vel.copy_(torch.from_numpy(g[f"f{frame}_vel"]))
             e.cloth_ref_angle[0].copy_(torch.from_numpy(g[f"f{frame}_ref_angle"]))
         grad.copy_pos(s, frame)
-    R.chk("reward", abs(s.compute_reward(1.0, -1.0) - float(g["reward"])), 1e-4)
-    # ---- adjoint sweep (training/trajopt_folding.py:130-133 with the seeds of the golden run)
-    grad.get_loss_fold(s, 1.0, -1.0)
-    grad._pos_grad[T - 1, :NVc, 2] = 1.0
-    assert np.array_equal(grad._pos_grad.cpu().numpy(), g["pos_grad_seed"])
+    # ---- adjoint sweep (training/trajopt_folding.py:130-133 / trajopt_forming.py:133-136 with the seeds of the golden run)
+    if forming:
+        R.chk("reward", abs(s.compute_reward(g["target_pos"]) - float(g["reward"])) / abs(float(g["reward"])), 1e-5)
+        grad.get_loss_push(s, g["target_pos"])
+        R.chk("pos_grad seed", _rel(grad._pos_grad.cpu().numpy(), g["pos_grad_seed"]), 1e-15 if forced else 1e-3)
+    else:
+        R.chk("reward", abs(s.compute_reward(1.0, -1.0) - float(g["reward"])), 1e-4)
+        grad.get_loss_fold(s, 1.0, -1.0)
+        grad._pos_grad[T - 1, :NVc, 2] = 1.0
+        assert np.array_equal(grad._pos_grad.cpu().numpy(), g["pos_grad_seed"])
     assert np.array_equal(grad._angleref_grad.cpu().numpy(), g["angleref_grad_seed"])
     for j in range(T - 1, 0, -1):
         d1 = _d1_dofs(e, g["pos_buffer"][j, :NVc], inject)

@@ -49,7 +49,7 @@ def install():
     from ..agent import traj_opt_single
     from ..engine import analytic_grad_single, analytic_grad_system, geometry, gripper_single, readfile
     from ..optimizer import optim
-    from ..task_scene import Scene_bouncing, Scene_folding
+    from ..task_scene import Scene_bouncing, Scene_folding, Scene_forming
 
     # ---- third-party modules the scripts import at top level
     if not _have("taichi"):
@@ -75,6 +75,7 @@ def install():
         "thinshelllab.engine.gripper_single": gripper_single,
         "thinshelllab.engine.readfile": readfile,
         "thinshelllab.task_scene.Scene_folding": Scene_folding,
+        "thinshelllab.task_scene.Scene_forming": Scene_forming,
         "thinshelllab.agent.traj_opt_single": traj_opt_single,
         "thinshelllab.optimizer.optim": optim,
     }

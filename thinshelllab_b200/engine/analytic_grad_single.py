@@ -58,6 +58,13 @@ class Grad:
         g[sel7[0], sel7[1]] = curve7
         g[sel8[0], sel8[1]] = curve8
 
+    def get_loss_push(self, sys, target_pos):
+        """:297-300: d/dx of the squared distance of the last frame's cloth to the target shape"""
+        c = sys.cloths[0]
+        t = torch.as_tensor(np.asarray(target_pos, np.float64), device=self._pos_grad.device)
+        T = self.tot_timestep
+        self._pos_grad[T - 1, c.offset:c.offset + c.NV] = 2.0 * (self._pos_buffer[T - 1, c.offset:c.offset + c.NV] - t)
+
     def transfer_grad(self, step, sys, f_contact=None, rel_tol=1e-10, max_iters=20000):
         pg_tm2 = self._pos_grad[step - 2] if step > 1 else None
         self.last_solve = sys.engine.step_backward_ex(

@@ -45,6 +45,8 @@ _DEFAULT_STATE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__
 
 
 class Scene:
+    DEFAULT_STATE = _DEFAULT_STATE
+
     def __init__(self, cloth_size=0.06, device="cuda:0", *, state=None, max_newton=50):
         """reference signature: Scene(cloth_size=0.06, device="cuda:0") (code/task_scene/Scene_folding.py:27).  The scene arrays come
         from `state` (a mapping with the keys of tests/golden/folding.npz, see oracle/gen_goldens.py:gen_folding; also accepted as the
@@ -53,7 +55,7 @@ class Scene:
         if state is None and hasattr(cloth_size, "keys"):
             state, cloth_size = cloth_size, None
         if state is None:
-            path = os.environ.get("TSL_SCENE_STATE", _DEFAULT_STATE)
+            path = os.environ.get("TSL_SCENE_STATE", self.DEFAULT_STATE)
             state = np.load(path)
             if cloth_size is not None and "cloth_size" in state and abs(float(state["cloth_size"]) - float(cloth_size)) > 1e-12:
                 raise NotImplementedError(f"Scene_folding: no scene state for cloth_size={cloth_size} ({path} holds {float(state['cloth_size'])}); "
