@@ -562,6 +562,7 @@ int tsl_solve(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int ma
 {
     if (!ctx || !ctx->finalized || !rhs || !x) return TSL_ERR_INVALID;
     StreamScope scope_(ctx);
+    if (ctx->last_f64 && ctx->dist.on && ctx->dist.world > 1) { ctx->err = "the fp64 BiCGStab solve is not partitioned over GPUs in this build"; return TSL_ERR_UNSUPPORTED; }
     if (ctx->last_f64) return solve_bicgstab64(ctx, rhs, x, rel_tol, max_iters, st);
     return solve_pcg32(ctx, ctx->A.val32, rhs, x, rel_tol, max_iters, st);
 }
@@ -860,6 +861,7 @@ int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, c
     StreamScope scope_(ctx);
     REQUIRE(x_t && x_tm1 && ref_angle_tm1 && pg_t && pg_tm1 && ag_t && ag_tm1, "tsl_step_backward: null pointer");
     REQUIRE(ctx->cloths.size() == 1, "tsl_step_backward needs one cloth");
+    if (ctx->dist.on && ctx->dist.world > 1) { ctx->err = "the adjoint step is not partitioned over GPUs in this build"; return TSL_ERR_UNSUPPORTED; }
     TRY(ensure_f64(ctx));
     int nv = ctx->cfg.n_verts, n3 = 3 * nv;
     cudaStream_t s = ctx->stream;
