@@ -57,7 +57,8 @@ typedef struct tsl_step_stats {
 
 typedef struct tsl_solve_stats {
     int iters;
-    int flags;                  /* as tsl_step_stats.flags */
+    int flags;                  /* bit0 breakdown / divergence, bit1 iteration cap hit, bit3 the adjoint solve fell back from the multigrid to
+                                   the block-Jacobi preconditioner (and converged unless bit0 / bit1 are set too) */
     double rel_residual;        /* |b - A x|_2 / |b|_2 as tracked by the recurrence */
 } tsl_solve_stats;
 

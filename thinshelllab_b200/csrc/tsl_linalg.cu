@@ -655,7 +655,7 @@ int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol,
         rr = rr0;
         if (!(rr0 == rr0)) { ctx->err = "BiCGStab: NaN residual"; return TSL_ERR_NUMERIC; }
         if (rr0 <= rel_tol * rel_tol * rr00 || rr00 == 0) break;
-        bool poisoned = false;
+        bool poisoned = false, diverged = false;
         while (it < max_iters) {
             int chunk = std::min(check_every, max_iters - it);
             for (int k = 0; k < chunk; k++, it++) TRYR(replay(ctx, ctx->g_bicg, key, [&]() { return bicg_iteration_body(ctx); }));
@@ -663,6 +663,7 @@ int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol,
             CK(cudaStreamSynchronize(s));
             rr = ctx->ks_host->rr;
             if (!(rr == rr)) { poisoned = true; break; }       // dx is poisoned: drop this cycle's correction
+            if (rr > 1e12 * rr00) { poisoned = true; diverged = true; break; }   // the preconditioned iteration diverges: give up on it
             if (ctx->ks_host->flags & 1) break;                // breakdown: dx holds the last good iterate
             if (rr <= rel_tol * rel_tol * rr00) break;
         }
@@ -680,6 +681,7 @@ int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol,
         rr = ctx->ks_host->rr;
         if (!(rr == rr)) { ctx->err = "BiCGStab produced NaN"; return TSL_ERR_NUMERIC; }
         if (rr <= rel_tol * rel_tol * rr00) break;
+        if (diverged) { flags |= 1; break; }
         if (it >= max_iters) { flags |= 2; break; }
         if (++restarts > max_restarts) { flags |= 1; break; }
     }
