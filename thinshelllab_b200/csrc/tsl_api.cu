@@ -470,10 +470,6 @@ int tsl_finalize(tsl_ctx *ctx)
     TRY(contact_alloc(ctx));
     TRY(linalg_alloc(ctx));
     TRY(mg_alloc(ctx));
-    // tetrahedral bodies: the largest eigenvalues of D^-1 A sit on a few stiff cells and ten power iterations from a random start
-    // under-estimate them by more than 2x (measured on Scene_forming: the Chebyshev smoother then amplifies those modes and the
-    // adjoint BiCGStab diverges; with 4x the estimate it converges).  A wider interval costs smoothing efficiency, not correctness.
-    if (!ctx->tets.empty()) ctx->mg.safety = 4.f;
     if (const char *e = getenv("TSL_PRECOND")) ctx->precond = atoi(e);
     if (const char *e = getenv("TSL_NEWTON_MODE")) ctx->newton_mode = atoi(e);
     if (const char *e = getenv("TSL_PROBE")) ctx->probe = atoi(e);
@@ -562,9 +558,11 @@ int tsl_assemble(tsl_ctx *ctx, int flags)
     return TSL_OK;
 }
 
-// adjoint solve with a safety net: if the multigrid-preconditioned BiCGStab breaks down or diverges (seen on Scene_forming, where
-// the cycle of the clamped Newton matrix is not a contraction for the un-projected adjoint matrix), the solve is redone with the
-// block-Jacobi preconditioner, which only needs the diagonal blocks to be invertible.  flags bit3 reports the fallback.
+// adjoint solve with a safety net: if the multigrid-preconditioned BiCGStab breaks down, diverges or stalls, the solve is redone with
+// the block-Jacobi preconditioner, which only needs the diagonal blocks to be invertible.  flags bit3 reports the fallback.
+// (Seen on Scene_forming: with tetrahedral bodies the largest eigenvalues of D^-1 A sit on a few stiff cells, ten power iterations
+// under-estimate them by more than 2x, the Chebyshev smoother then amplifies those modes and the cycle is not a contraction; 4x the
+// estimate cures that state but makes the cycle too weak elsewhere -- measured, tools/adjoint_probe.py -- so the estimate stays.)
 static int solve_adjoint64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
 {
     tsl_solve_stats s0;

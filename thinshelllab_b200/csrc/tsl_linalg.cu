@@ -664,6 +664,8 @@ int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol,
             rr = ctx->ks_host->rr;
             if (!(rr == rr)) { poisoned = true; break; }       // dx is poisoned: drop this cycle's correction
             if (rr > 1e12 * rr00) { poisoned = true; diverged = true; break; }   // the preconditioned iteration diverges: give up on it
+            // a working multigrid cycle gains orders of magnitude within tens of iterations: no progress after 200 = not a contraction
+            if (ctx->precond != 0 && ctx->mg.n_levels > 0 && it >= 200 && rr > 1e-2 * rr00) { diverged = true; break; }
             if (ctx->ks_host->flags & 1) break;                // breakdown: dx holds the last good iterate
             if (rr <= rel_tol * rel_tol * rr00) break;
         }
