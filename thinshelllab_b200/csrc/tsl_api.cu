@@ -560,9 +560,10 @@ int tsl_assemble(tsl_ctx *ctx, int flags)
 
 // adjoint solve with a safety net: if the multigrid-preconditioned BiCGStab breaks down, diverges or stalls, the solve is redone with
 // the block-Jacobi preconditioner, which only needs the diagonal blocks to be invertible.  flags bit3 reports the fallback.
-// (Seen on Scene_forming: with tetrahedral bodies the largest eigenvalues of D^-1 A sit on a few stiff cells, ten power iterations
-// under-estimate them by more than 2x, the Chebyshev smoother then amplifies those modes and the cycle is not a contraction; 4x the
-// estimate cures that state but makes the cycle too weak elsewhere -- measured, tools/adjoint_probe.py -- so the estimate stays.)
+// (Seen on the second frame of Scene_forming, tools/adjoint_probe.py: the cycle built from the clamped Newton matrix stalls on the
+// un-projected adjoint matrix there although a 4x wider Chebyshev interval converges; widening it for every scene makes the cycle too
+// weak elsewhere.  mg_setup now also estimates lambda_max on the solids alone, which cut the forward PCG counts of Scene_folding /
+// Scene_forming by a third, but that state still needs the fallback.)
 static int solve_adjoint64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
 {
     tsl_solve_stats s0;

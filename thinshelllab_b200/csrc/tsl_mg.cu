@@ -653,13 +653,20 @@ __global__ void k_fill_hash(int n, float *v, unsigned seed)
 }
 // Chebyshev coefficients of every level from the power-iteration norms; also the scale of the next warm start
 __global__ void k_mg_coeffs(int n_levels, const double *__restrict__ pow_acc, int k_last, float safety, float ratio, float coarse_ratio,
-                            int degree, int coarse_degree, float *coef, float *powc, float *lmax_out)
+                            int degree, int coarse_degree, float *coef, float *powc, float *lmax_out, int extra_slot)
 {
     int l = threadIdx.x;
     if (l >= n_levels) return;
     double n1 = pow_acc[l * 16 + k_last], n0 = pow_acc[l * 16 + k_last - 1];
     double lam = sqrt(n1 / n0);
     if (!(lam > 1e-6) || !(lam < 1e6)) lam = 4.0;             // degenerate level (e.g. everything masked): any finite value
+    if (l == 0 && extra_slot >= 0) {
+        // second estimate from a start vector confined to the non-cloth rows (tetrahedral bodies): their stiffest cells carry the
+        // largest eigenvalues of D^-1 A, which ten iterations from a vector spread over the whole system under-estimate
+        double m1 = pow_acc[extra_slot * 16 + k_last], m0 = pow_acc[extra_slot * 16 + k_last - 1];
+        double lam2 = sqrt(m1 / m0);
+        if (lam2 > lam && lam2 < 1e6) lam = lam2;
+    }
     double lmax = safety * lam;
     bool coarsest = (l == n_levels - 1);
     double lmin = lmax / (coarsest ? coarse_ratio : ratio);
@@ -803,8 +810,19 @@ int mg_setup(tsl_ctx *ctx)
         for (int k = 0; k < its; k++)
             launch_step(ctx, l, nullptr, L.pv[k & 1], L.pv[(k & 1) ^ 1], nullptr, mg.powc + 4 * l + 2, mg.pow_acc + 16 * l + k, 2);
     }
+    int extra_slot = -1;
+    if (!ctx->tets.empty() && mg.n_levels < TSL_MG_MAX_LEVELS && ctx->n_solve > c.offset + c.NV) {
+        // the sliced-ELL matrix has no cloth <-> solid blocks (contacts live in the side buffer), so the iteration stays on the solids
+        extra_slot = TSL_MG_MAX_LEVELS - 1;
+        MgLevel &L = mg.lev[0];
+        k_fill_hash<<<GRID(3 * L.nrows, 256), 256, 0, s>>>(3 * L.nrows, L.pv[0], 0x51ed270bu);
+        CK(cudaMemsetAsync(L.pv[0] + 3 * (size_t)c.offset, 0, sizeof(float) * 3 * (size_t)c.NV, s));
+        ctx->launches++;
+        for (int k = 0; k < its; k++)
+            launch_step(ctx, 0, nullptr, L.pv[k & 1], L.pv[(k & 1) ^ 1], nullptr, mg.powc + 2, mg.pow_acc + 16 * extra_slot + k, 2);
+    }
     k_mg_coeffs<<<1, 32, 0, s>>>(mg.n_levels, mg.pow_acc, its - 1, mg.safety, mg.ratio, mg.coarse_ratio, mg.degree, mg.coarse_degree,
-                                 mg.coef, mg.powc, mg.lmax);
+                                 mg.coef, mg.powc, mg.lmax, extra_slot);
     ctx->launches++;
     mg.setups++;
     CK(cudaGetLastError());
