@@ -1,15 +1,17 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json metric: element-updates/sec per implicit fwd+bwd step; HBM GB/s vs peak.
 
-One "step" = one implicit forward time step of the sheet (contact query, Newton with block-Jacobi PCG, line search) plus
-one adjoint step for it (contact re-detection, un-projected fp64 Hessian, BiCGStab solve, parameter gradient dL/dKb).
+One "step" = one implicit forward time step of the sheet (contact query, Newton with multigrid-preconditioned PCG, line search) plus
+one adjoint step for it (contact re-detection, un-projected fp64 Hessian, multigrid-preconditioned BiCGStab solve, parameter gradient dL/dKb).
 `value` = triangles x steps / device time with state resident in HBM; `e2e` = the same through the host-buffer C-ABI entry
 point (tsl_step_forward_host) + host-side loss seed / gradient read-back, copies inside the timed region.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--sheet-n 707] [--impl reference]
 
-N > 1 (torchrun): one independent sheet per rank (replicas, weak scaling, no data-path collective) -- the strip-partitioned
-solver of SURVEY.md section 8e is not implemented yet; the JSON line says so in config.parallelism.
+N > 1 (torchrun): one independent sheet per rank (replicas, weak scaling, no data-path collective).  The strip partition of ONE sheet
+over the GPUs (tsl_dist_init, NCCL halo exchange + all-reduced Krylov scalars) exists for the forward step and is
+exact but, lacking a coarse space across strips, slower than one GPU (tools/bench_partition.py,
+profiles/r1_partition_2gpu.md): the benchmark keeps replicas and says so in config.parallelism.
 """
 import argparse
 import json
@@ -356,7 +358,7 @@ def run_ours(args, rank, world):
         "config": {"workload": f"sheet {N}x{N} ({n_tris} tris, dx 2 mm) landing on a frozen table, Scene_bouncing physics, fwd + adjoint (dL/dKb) per step"
                                + (" -- the 1 M-triangle sheet of BASELINE configs[4] / north_star on ONE GPU (largest single-GPU configuration; configs[1] and [2] are in baseline_configs_50k)" if N == 707 else ""),
                    "sheet_n": N, "n_tris": n_tris, "n_verts": V, "nnzb": sz["nnzb"], "nnzb_padded": sz["nnzb_padded"], "n_solve": Vs, "nnzb_solve": Bs,
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (element partition not implemented in round 1)",
+                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (the strip partition of one sheet is exact but not yet faster than one GPU: DESIGN.md section 6)",
                    "l2": "matrix %.0f MB > 126 MB L2" % (sz["bytes_matrix_f32"] / 1e6) if sz["bytes_matrix_f32"] > 126e6 else
                          "working set %.0f MB fits the 126 MB L2: roofline fraction can exceed 1" % (sz["bytes_matrix_f32"] / 1e6),
                    "solver": "Newton (exact / clamped / blended matrix, line search) + multigrid-preconditioned PCG; adjoint: multigrid-preconditioned BiCGStab fp64",
