@@ -74,7 +74,6 @@ int tsl_destroy(tsl_ctx *ctx)
     // device memory is released with the process / context; explicit frees for the large arrays
     cudaStreamSynchronize(ctx->stream);
     tsl::graphs_invalidate(ctx);
-    tsl::dist_destroy(ctx);
     tsl::mg_free(ctx);
     cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->A.val32m); cudaFree(ctx->A.val32t); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
     cudaFree(ctx->cg_x); cudaFree(ctx->cg_r); cudaFree(ctx->cg_z); cudaFree(ctx->cg_p); cudaFree(ctx->cg_q); cudaFree(ctx->cg_r32); cudaFree(ctx->ncdir);

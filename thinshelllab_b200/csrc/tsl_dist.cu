@@ -71,13 +71,6 @@ int dist_halo(tsl_ctx *ctx, double *v)
     return TSL_OK;
 }
 
-void dist_destroy(tsl_ctx *ctx)
-{
-    if (ctx->dist.comm && nccl().CommDestroy) nccl().CommDestroy((ncclComm_t)ctx->dist.comm);
-    ctx->dist.comm = nullptr;
-    ctx->dist.on = false;
-}
-
 __global__ void k_zero_ghost(int n3, int lo3, int hi3, double *v)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;

@@ -47,8 +47,7 @@ int mg_setup_replay(tsl_ctx *ctx);   // mg_setup through a captured graph after 
 // tsl_dist.cu: collectives of the strip-partitioned solve (no-ops returning TSL_OK when the context is not partitioned)
 int dist_allreduce(tsl_ctx *ctx, double *dev, int n, bool max_op = false);   // in place, on ctx->stream
 int dist_halo(tsl_ctx *ctx, double *vec3);                                   // ghost rows of a [3 n_rows] vector <- the neighbours' owned rows
-void launch_zero_ghost(tsl_ctx *ctx, double *vec3);
-void dist_destroy(tsl_ctx *ctx);                          // zero the ghost rows of a [3 n_rows] vector
+void launch_zero_ghost(tsl_ctx *ctx, double *vec3);                          // zero the ghost rows of a [3 n_rows] vector
 
 // tsl_mg.cu
 int mg_alloc(tsl_ctx *ctx);
