@@ -56,10 +56,10 @@ typedef struct tsl_step_stats {
 } tsl_step_stats;
 
 typedef struct tsl_solve_stats {
-    int iters;
-    int flags;                  /* bit0 breakdown / divergence, bit1 iteration cap hit, bit3 the adjoint solve fell back from the multigrid to
+    int iters;                  /* Krylov iterations; 0 = the adjoint system was solved directly (dense LU, see TSL_OPT_DIRECT_MAX_DOF) */
+    int flags;                  /* bit0 breakdown / stall, bit1 iteration cap hit, bit3 the adjoint solve fell back from the multigrid to
                                    the block-Jacobi preconditioner (and converged unless bit0 / bit1 are set too) */
-    double rel_residual;        /* |b - A x|_2 / |b|_2 as tracked by the recurrence */
+    double rel_residual;        /* forward PCG: |b - A x|_2 / |b|_2 of the recurrence; adjoint: of the TRUE residual */
 } tsl_solve_stats;
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -134,7 +134,10 @@ int tsl_energy(tsl_ctx *ctx, double *energy_out);
 #define TSL_ASM_NEWTON 32
 int tsl_assemble(tsl_ctx *ctx, int flags);
 /* SparseMatrix.solve (code/engine/sparse_solver.py:85-105): x = H^-1 b with the last assembled Hessian.
- * fp32 Hessian: block-Jacobi PCG (fp32 vectors, fp64 reductions); fp64 Hessian: block-Jacobi BiCGStab (fp64).
+ * fp32 Hessian (forward Newton matrix): PCG with fp64 vectors, preconditioned by one geometric-multigrid V-cycle over the cloth grid
+ * (TSL_OPT_PRECOND = 0: block-Jacobi).  fp64 Hessian (the reference's un-projected, non-symmetric adjoint matrix): dense LU with
+ * partial pivoting up to TSL_OPT_DIRECT_MAX_DOF unknowns, FGMRES(m) with the same V-cycle as flexible right preconditioner above;
+ * returns TSL_ERR_NUMERIC when the requested tolerance is not reached (a direct solver never leaves that to the caller).
  * rhs_dev / x_dev: [3 n_verts] f64 device. */
 int tsl_solve(tsl_ctx *ctx, const double *rhs_dev, double *x_dev, double rel_tol, int max_iters, tsl_solve_stats *stats);
 /* BaseScene.time_step(f_contact, frame) with Scene_bouncing.timestep_finish
@@ -238,12 +241,17 @@ int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out);
  *       local minimum than the reference's path), 2 = solve with the blend A_e + theta (A_c - A_e), theta the smallest of
  *       0, 1/16, ..., 1 that PCG accepts (default: fewest iterations measured; reproduces the reference's Scene_bouncing
  *       rollout like the others; on buckling steps it may settle in another local minimum than mode 0);
- * TSL_OPT_GRAPHS: 1 = replay the solver iterations as captured CUDA graphs (default), 0 = eager launches. */
-enum tsl_option { TSL_OPT_PRECOND = 0, TSL_OPT_MG_DEGREE = 1, TSL_OPT_MG_COARSE_DEGREE = 2, TSL_OPT_MG_RATIO = 3, TSL_OPT_MG_SAFETY = 4, TSL_OPT_GRAPHS = 5, TSL_OPT_NEWTON_MODE = 6 };
+ * TSL_OPT_GRAPHS: 1 = replay the solver iterations as captured CUDA graphs (default), 0 = eager launches.
+ * TSL_OPT_ADJOINT_SOLVER: 0 = automatic (dense LU when 3 * solved vertices <= TSL_OPT_DIRECT_MAX_DOF, default 12288, else FGMRES),
+ *   1 = dense LU, 2 = FGMRES(TSL_OPT_GMRES_M, default 50), 3 = BiCGStab (the round-1 solver, kept for comparison). */
+enum tsl_option { TSL_OPT_PRECOND = 0, TSL_OPT_MG_DEGREE = 1, TSL_OPT_MG_COARSE_DEGREE = 2, TSL_OPT_MG_RATIO = 3, TSL_OPT_MG_SAFETY = 4, TSL_OPT_GRAPHS = 5, TSL_OPT_NEWTON_MODE = 6,
+                  TSL_OPT_ADJOINT_SOLVER = 7, TSL_OPT_DIRECT_MAX_DOF = 8, TSL_OPT_GMRES_M = 9 };
 int tsl_set_option(tsl_ctx *ctx, int key, double value);
 /* multigrid level read-back for tests: dims_host[3] = n0, n1, number of levels; lmax_host[1]; val_host [25][9][n0*n1] f32
  * (5x5 stencil of 3x3 blocks, slot-major; level 0 returns the stencil copy of the cloth block).  Any pointer may be NULL. */
 int tsl_mg_get_level(tsl_ctx *ctx, int level, int *dims_host, float *lmax_host, float *val_host);
+/* test hook of the dense LU behind the direct adjoint solve: x = A^-1 b for a host matrix (column-major [n][n]), factorised on the GPU */
+int tsl_dense_solve_host(tsl_ctx *ctx, int n, const double *A_host, const double *b_host, double *x_host);
 /* z = M^-1 b with the preconditioner built by the last tsl_assemble / step (b, z: [3 n_verts] f64 device) */
 int tsl_precond_apply(tsl_ctx *ctx, const double *b_dev, double *z_dev);
 /* number of kernels this library has launched since creation (bench.py's gpu_launches) */

@@ -145,9 +145,39 @@ def test_linear_solvers(golden):
     rhs = np.random.default_rng(0).standard_normal(F.shape)
     rhs[e.frozen.cpu().numpy() != 0] = 0
     ref = spla.spsolve(H, rhs)
-    x, (iters, flags, rr) = e.solve(torch.from_numpy(rhs).to(e.device), rel_tol=1e-10, max_iters=2000)
-    assert flags == 0 and rr < 1e-9, (iters, flags, rr)      # (BiCGStab on a random right-hand side: 100-800 iterations)
+    rhs_d = torch.from_numpy(rhs).to(e.device)
+    # default: 3.3 k unknowns -> dense LU with partial pivoting (a direct solve, like the reference's; iters == 0)
+    x, (iters, flags, rr) = e.solve(rhs_d, rel_tol=1e-10, max_iters=2000)
+    assert flags == 0 and iters == 0 and rr < 1e-13, (iters, flags, rr)
+    assert _rel(x.cpu().numpy(), ref) < 1e-9
+    # the large-system path on the same matrix: FGMRES with the multigrid V-cycle as flexible right preconditioner
+    e.set_option(_lib.OPT_ADJOINT_SOLVER, _lib.ADJ_FGMRES)
+    x, (iters, flags, rr) = e.solve(rhs_d, rel_tol=1e-10, max_iters=2000)
+    assert (flags & 3) == 0 and iters > 0 and rr < 1e-9, (iters, flags, rr)
     assert _rel(x.cpu().numpy(), ref) < 1e-7
+    # short restart length: restarts from the true residual must still converge
+    e.set_option(_lib.OPT_GMRES_M, 20)
+    x, (iters, flags, rr) = e.solve(rhs_d, rel_tol=1e-10, max_iters=8000)
+    assert (flags & 3) == 0 and rr < 1e-9, (iters, flags, rr)
+    assert _rel(x.cpu().numpy(), ref) < 1e-7
+    # an unconverged adjoint solve is an error, never a silently wrong gradient
+    with pytest.raises(_lib.TslError) as ei:
+        e.solve(rhs_d, rel_tol=1e-10, max_iters=3)
+    assert ei.value.code == _lib.ERR_NUMERIC
+
+
+@pytest.mark.parametrize("n", [3, 64, 97, 500, 1300])
+def test_dense_lu_against_numpy(n):
+    """the dense LU behind the direct adjoint solve (tsl_dense.cu) on random, badly scaled matrices that need pivoting"""
+    s = Scene(cloth_size=0.06, cloth_N=4, cloth_M=4)
+    s.init_all()
+    rng = np.random.default_rng(n)
+    A = rng.standard_normal((n, n)) * np.exp(rng.uniform(-6, 6, (n, 1)))
+    A[0, 0] = 0.0
+    b = rng.standard_normal(n)
+    x = s.engine.dense_solve(A, b)
+    ref = np.linalg.solve(A, b)
+    assert np.abs(x - ref).max() <= 1e-8 * np.abs(ref).max(), np.abs(x - ref).max() / np.abs(ref).max()
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2])

@@ -53,9 +53,6 @@ SIGNATURES = {
     "tsl_set_side_test_override": (_i, [_vp, _i, _vp]),
     "tsl_add_tets": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _d, _d, _d, _vp]),
     "tsl_set_tet_params": (_i, [_vp, _i, _d, _d]),
-    "tsl_set_side_test_override": (_i, [_vp, _i, _vp]),
-    "tsl_add_tets": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _d, _d, _d, _vp]),
-    "tsl_set_tet_params": (_i, [_vp, _i, _d, _d]),
     "tsl_set_surfaces": (_i, [_vp, _vp, _i, _vp, _i]),
     "tsl_add_contact_pair": (_i, [_vp, _i, _i, _i, _d]),
     "tsl_set_contact_mu": (_i, [_vp, _i, _d]),
@@ -87,10 +84,14 @@ SIGNATURES = {
     "tsl_set_option": (_i, [_vp, _i, _d]),
     "tsl_mg_get_level": (_i, [_vp, _i, _vp, _vp, _vp]),
     "tsl_precond_apply": (_i, [_vp, _vp, _vp]),
+    "tsl_dense_solve_host": (_i, [_vp, _i, _vp, _vp, _vp]),
     "tsl_launch_count": (C.c_longlong, [_vp]),
 }
 
 OPT_PRECOND, OPT_MG_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_RATIO, OPT_MG_SAFETY, OPT_GRAPHS, OPT_NEWTON_MODE = 0, 1, 2, 3, 4, 5, 6
+OPT_ADJOINT_SOLVER, OPT_DIRECT_MAX_DOF, OPT_GMRES_M = 7, 8, 9
+ADJ_AUTO, ADJ_DIRECT, ADJ_FGMRES, ADJ_BICGSTAB = 0, 1, 2, 3
+ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NUMERIC = -1, -2, -3, -4, -5
 ASM_RESIDUAL, ASM_HESSIAN, ASM_SPD, ASM_SYM, ASM_F64, ASM_NEWTON = 1, 2, 4, 8, 16, 32
 
 _LIB = None

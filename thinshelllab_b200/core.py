@@ -334,5 +334,12 @@ class ShellEngine:
         self._ck(self.L.tsl_precond_apply(self.ctx, _ptr(b), _ptr(z)))
         return z
 
+    def dense_solve(self, A, b):
+        """test hook of the dense LU behind the direct adjoint solve: x = A^-1 b (host arrays, factorised on the GPU)"""
+        A = np.asfortranarray(A, np.float64); b = np.ascontiguousarray(b, np.float64)
+        x = np.zeros_like(b)
+        self._ck(self.L.tsl_dense_solve_host(self.ctx, int(b.shape[0]), _np_ptr(A), _np_ptr(b), _np_ptr(x)))
+        return x
+
     def launch_count(self):
         return int(self.L.tsl_launch_count(self.ctx))

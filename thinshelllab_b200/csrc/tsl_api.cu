@@ -22,6 +22,7 @@ struct StreamScope {
     explicit StreamScope(tsl_ctx *ctx) : c(ctx)
     {
         if (!c) return;
+        cudaSetDevice(c->device);                // a second context on another device may have changed the current one
         cudaEventRecord(c->ev_in, c->user_stream);
         cudaStreamWaitEvent(c->stream, c->ev_in, 0);
     }
@@ -58,6 +59,7 @@ int tsl_create(const tsl_config *cfg, tsl_ctx **out)
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return TSL_ERR_CUDA;   // no CPU fallback: fail loudly
     tsl_ctx *ctx = new tsl_ctx();
     ctx->cfg = *cfg;
+    cudaGetDevice(&ctx->device);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_in, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_out, cudaEventDisableTiming) != cudaSuccess) { delete ctx; return TSL_ERR_CUDA; }
@@ -71,8 +73,11 @@ int tsl_create(const tsl_config *cfg, tsl_ctx **out)
 int tsl_destroy(tsl_ctx *ctx)
 {
     if (!ctx) return TSL_ERR_INVALID;
-    // device memory is released with the process / context; explicit frees for the large arrays
+    cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    tsl::dist_destroy(ctx);
+    tsl::dense_free(ctx);
+    cudaFree(ctx->gm_V); cudaFree(ctx->gm_Z); cudaFree(ctx->gm_h); if (ctx->gm_h_host) cudaFreeHost(ctx->gm_h_host);
     tsl::graphs_invalidate(ctx);
     tsl::mg_free(ctx);
     cudaFree(ctx->A.val32); cudaFree(ctx->A.val32c); cudaFree(ctx->A.val32m); cudaFree(ctx->A.val32t); cudaFree(ctx->cg_r64tmp); cudaFree(ctx->A.val64); cudaFree(ctx->A.colidx); cudaFree(ctx->A.slice_base); cudaFree(ctx->A.diag_pb);
@@ -558,29 +563,48 @@ int tsl_assemble(tsl_ctx *ctx, int flags)
     return TSL_OK;
 }
 
-// adjoint solve with a safety net: if the multigrid-preconditioned BiCGStab breaks down, diverges or stalls, the solve is redone with
-// the block-Jacobi preconditioner, which only needs the diagonal blocks to be invertible.  flags bit3 reports the fallback.
-// (Seen on the second frame of Scene_forming, tools/adjoint_probe.py: the cycle built from the clamped Newton matrix stalls on the
-// un-projected adjoint matrix there although a 4x wider Chebyshev interval converges; widening it for every scene makes the cycle too
-// weak elsewhere.  mg_setup now also estimates lambda_max on the solids alone, which cut the forward PCG counts of Scene_folding /
-// Scene_forming by a third, but that state still needs the fallback.)
+// Adjoint solve H z = b on the reference's un-projected, non-symmetric fp64 Hessian.  The reference factorises (sparse QR,
+// code/engine/sparse_solver.py:85-105), so its gradient never hinges on an iteration converging; here
+//   * up to direct_max_dof unknowns (every task scene of the reference): dense LU with partial pivoting + iterative refinement
+//     (tsl_dense.cu) -- exact, deterministic, st->iters = 0;
+//   * above: FGMRES(m) with the multigrid V-cycle as flexible right preconditioner (monotone residual, true-residual restarts);
+//     if that stalls, the same with the fp64 block-Jacobi preconditioner (flags bit3).
+// An unconverged result is an error (TSL_ERR_NUMERIC), never a silently wrong gradient.
 static int solve_adjoint64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
 {
     tsl_solve_stats s0;
     memset(&s0, 0, sizeof(s0));
-    const bool mg = ctx->precond != 0 && ctx->mg.n_levels > 0;
-    TRY(solve_bicgstab64(ctx, rhs, x, rel_tol, mg ? std::min(max_iters, 800) : max_iters, &s0));
-    if (mg && ((s0.flags & 3) || !(s0.rel_residual <= 10 * rel_tol))) {
-        int first_iters = s0.iters;
-        int saved = ctx->precond;
-        ctx->precond = 0;
-        int rc = solve_bicgstab64(ctx, rhs, x, rel_tol, max_iters, &s0);
-        ctx->precond = saved;
-        if (rc != TSL_OK) return rc;
-        s0.iters += first_iters;
-        s0.flags |= 8;
+    int mode = ctx->adjoint_solver;
+    if (mode == 0) mode = (3LL * ctx->n_solve <= ctx->direct_max_dof) ? 1 : 2;
+    if (mode == 1) {
+        TRY(solve_dense64(ctx, rhs, x, &s0));
+    } else {
+        const bool mg = ctx->precond != 0 && ctx->mg.n_levels > 0;
+        auto run = [&](tsl_solve_stats *o) {
+            return mode == 3 ? solve_bicgstab64(ctx, rhs, x, rel_tol, mg ? std::min(max_iters, 800) : max_iters, o)
+                             : solve_fgmres64(ctx, rhs, x, rel_tol, max_iters, o);
+        };
+        TRY(run(&s0));
+        if (mg && ((s0.flags & 3) || !(s0.rel_residual <= 10 * rel_tol)) && s0.iters < max_iters) {
+            int first_iters = s0.iters;
+            int saved = ctx->precond;
+            ctx->precond = 0;
+            int rc = mode == 3 ? solve_bicgstab64(ctx, rhs, x, rel_tol, max_iters - first_iters, &s0)
+                               : solve_fgmres64(ctx, rhs, x, rel_tol, max_iters - first_iters, &s0);
+            ctx->precond = saved;
+            if (rc != TSL_OK) return rc;
+            s0.iters += first_iters;
+            s0.flags |= 8;
+        }
     }
     if (st) *st = s0;
+    if ((s0.flags & 3) || !(s0.rel_residual <= std::max(10 * rel_tol, 1e-13))) {
+        char buf[160];
+        snprintf(buf, sizeof(buf), "adjoint solve did not converge: %d iterations, flags %d, relative residual %.3e (tolerance %.1e)", s0.iters, s0.flags,
+                 s0.rel_residual, rel_tol);
+        ctx->err = buf;
+        return TSL_ERR_NUMERIC;
+    }
     return TSL_OK;
 }
 
@@ -1160,6 +1184,9 @@ int tsl_set_option(tsl_ctx *ctx, int key, double value)
     case TSL_OPT_MG_SAFETY: REQUIRE(value >= 1, "mg safety must be >= 1"); ctx->mg.safety = (float)value; break;
     case TSL_OPT_GRAPHS: ctx->use_graphs = (int)value; break;
     case TSL_OPT_NEWTON_MODE: ctx->newton_mode = (int)value; break;
+    case TSL_OPT_ADJOINT_SOLVER: REQUIRE(value >= 0 && value <= 3, "adjoint solver: 0 auto, 1 dense LU, 2 FGMRES, 3 BiCGStab"); ctx->adjoint_solver = (int)value; break;
+    case TSL_OPT_DIRECT_MAX_DOF: REQUIRE(value >= 0 && value <= 46000, "direct_max_dof out of range"); ctx->direct_max_dof = (int)value; break;
+    case TSL_OPT_GMRES_M: REQUIRE(value >= 2 && value <= 400, "FGMRES restart length out of range"); ctx->gmres_m = (int)value; break;
     default: ctx->err = "tsl_set_option: unknown key"; return TSL_ERR_INVALID;
     }
     cudaStreamSynchronize(ctx->stream);
@@ -1170,6 +1197,12 @@ int tsl_mg_get_level(tsl_ctx *ctx, int level, int *dims, float *lmax, float *val
 {
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
     return mg_get_level(ctx, level, dims, lmax, val_host);
+}
+int tsl_dense_solve_host(tsl_ctx *ctx, int n, const double *A_host, const double *b_host, double *x_host)
+{
+    if (!ctx || !ctx->finalized || n <= 0 || !A_host || !b_host || !x_host) return TSL_ERR_INVALID;
+    StreamScope scope_(ctx);
+    return dense_solve_host(ctx, n, A_host, b_host, x_host);
 }
 int tsl_precond_apply(tsl_ctx *ctx, const double *b_dev, double *z_dev)
 {

@@ -17,6 +17,7 @@ struct NcclApi {
     ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*CommAbort)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -33,7 +34,7 @@ static NcclApi &nccl()
     if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
     if (!h) return api;
 #define SYM(field, name) api.field = (decltype(api.field))dlsym(h, name)
-    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+    SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy"); SYM(CommAbort, "ncclCommAbort");
     SYM(AllReduce, "ncclAllReduce"); SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(GroupStart, "ncclGroupStart");
     SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
 #undef SYM
@@ -69,6 +70,19 @@ int dist_halo(tsl_ctx *ctx, double *v)
     NCK(nccl().GroupEnd());
     ctx->dist.halo_msgs++;
     return TSL_OK;
+}
+
+// tsl_destroy: the stream is idle (synchronised by the caller), every collective this rank enqueued has completed, so the communicator
+// can be torn down without waiting for the peers.  ncclCommAbort does exactly that; ncclCommDestroy may block at interpreter exit when a
+// peer process has already gone.
+void dist_destroy(tsl_ctx *ctx)
+{
+    if (ctx->dist.comm) {
+        if (nccl().CommAbort) nccl().CommAbort((ncclComm_t)ctx->dist.comm);
+        else if (nccl().CommDestroy) nccl().CommDestroy((ncclComm_t)ctx->dist.comm);
+    }
+    ctx->dist.comm = nullptr;
+    ctx->dist.on = false;
 }
 
 __global__ void k_zero_ghost(int n3, int lo3, int hi3, double *v)

@@ -145,6 +145,9 @@ struct DistCtx {
 
 struct GraphSlot { cudaGraphExec_t exec = nullptr; long long launches = 0; const void *key = nullptr; };
 
+// dense fp64 LU of the adjoint matrix (tsl_dense.cu): column-major A[i + j * lda], allocated on first use
+struct DenseLU { double *A = nullptr; int *ipiv = nullptr; int *info = nullptr; int cap = 0, lda = 0; };
+
 }  // namespace tsl
 
 struct tsl_ctx {
@@ -221,5 +224,13 @@ struct tsl_ctx {
     double *d_kb = nullptr;                      // [n_verts][3]
     double *adj_rhs = nullptr, *adj_z = nullptr; // [3 n_verts]
     int error_flag_host = 0; int *error_flag = nullptr;   // device-side "unsupported" flags
+    // adjoint solve: dense LU below direct_max_dof unknowns, FGMRES(gmres_m) above
+    int adjoint_solver = 0;                      // 0 auto, 1 dense LU, 2 FGMRES, 3 BiCGStab (round-1 solver, kept for comparison)
+    int direct_max_dof = 12288;
+    int gmres_m = 50, gm_cap_m = 0;
+    tsl::DenseLU dense;
+    double *gm_V = nullptr, *gm_Z = nullptr;     // FGMRES bases [gmres_m + 1] / [gmres_m] x [3 n_rows_pad]
+    double *gm_h = nullptr, *gm_h_host = nullptr;   // Gram-Schmidt coefficients (device / pinned)
+    int device = 0;                              // CUDA device the context lives on (tsl_create)
     tsl::DistCtx dist;
 };

@@ -38,16 +38,27 @@ void launch_blend(tsl_ctx *ctx, const float *a, const float *b, float t, float *
 int solve_pcg32(tsl_ctx *ctx, const float *opval, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st);
 // adjoint solve: right-preconditioned BiCGStab in fp64 on A.val64, restarted on breakdown
 int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st);
+// adjoint solve: FGMRES(m) in fp64 on A.val64 (+ contact side blocks), flexible right preconditioning by the fp32 V-cycle
+int solve_fgmres64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st);
+int adjoint_residual64(tsl_ctx *ctx, const double *rhs, const double *x, double *res, double *rr_out);
+void adjoint_apply_minv_tail(tsl_ctx *ctx, int r0, int r1, const double *in, double *out);
+void adjoint_axpy64(tsl_ctx *ctx, int n, const double *dx, double *x);
 int bench_pcg_iterations(tsl_ctx *ctx, int iters, int what, float *ms_out);
 int precond_apply_f64io(tsl_ctx *ctx, const double *in, double *out);
 int probe_curvature(tsl_ctx *ctx, const float *opval, const double *dir, double *out);
 void graphs_invalidate(tsl_ctx *ctx);
 int mg_setup_replay(tsl_ctx *ctx);   // mg_setup through a captured graph after the first (cold) call
 
+// tsl_dense.cu: dense fp64 LU (direct path of the adjoint solve)
+int solve_dense64(tsl_ctx *ctx, const double *rhs, double *x, tsl_solve_stats *st);
+int dense_solve_host(tsl_ctx *ctx, int n, const double *A_host, const double *b_host, double *x_host);
+void dense_free(tsl_ctx *ctx);
+
 // tsl_dist.cu: collectives of the strip-partitioned solve (no-ops returning TSL_OK when the context is not partitioned)
 int dist_allreduce(tsl_ctx *ctx, double *dev, int n, bool max_op = false);   // in place, on ctx->stream
 int dist_halo(tsl_ctx *ctx, double *vec3);                                   // ghost rows of a [3 n_rows] vector <- the neighbours' owned rows
 void launch_zero_ghost(tsl_ctx *ctx, double *vec3);                          // zero the ghost rows of a [3 n_rows] vector
+void dist_destroy(tsl_ctx *ctx);                                             // releases the NCCL communicator (tsl_destroy)
 
 // tsl_mg.cu
 int mg_alloc(tsl_ctx *ctx);

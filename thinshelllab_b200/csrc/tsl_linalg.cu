@@ -11,6 +11,7 @@
 // HBM-bound: the SpMV streams 40 B (fp32) / 76 B (fp64) per 3x3 block in full-line transactions
 // (see SellMatrix), gathers the direction vector through L1/L2, and fuses the dot products it feeds.
 #include <algorithm>
+#include <cmath>
 
 #include "tsl_internal.cuh"
 #include "tsl_kernels.cuh"
@@ -688,6 +689,213 @@ int solve_bicgstab64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol,
         if (++restarts > max_restarts) { flags |= 1; break; }
     }
     if (st) { st->iters = it; st->flags = flags; st->rel_residual = rr00 > 0 ? sqrt(rr / rr00) : 0.0; }
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------ helpers shared with tsl_dense.cu
+// res = rhs - A x over ALL rows with the fp64 adjoint operator (sliced ELL + contact side blocks); *rr_out = |res|^2 (synchronises)
+int adjoint_residual64(tsl_ctx *ctx, const double *rhs, const double *x, double *res, double *rr_out)
+{
+    int n = ctx->cfg.n_verts;
+    cudaStream_t s = ctx->stream;
+    const SellMatrix &A = ctx->A;
+    CK(cudaMemsetAsync(&ctx->ks->rr, 0, sizeof(double), s));
+    double *yc = side_pass<double>(ctx, ctx->cside64, x);
+    k_residual64<<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, rhs, x, res, &ctx->ks->rr, yc);
+    ctx->launches++;
+    CK(cudaMemcpyAsync(&ctx->ks_host->rr, &ctx->ks->rr, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    *rr_out = ctx->ks_host->rr;
+    return TSL_OK;
+}
+__global__ void k_apply_minv64_range(int r0, int r1, const double *__restrict__ minv, const double *__restrict__ in, double *out)
+{
+    int row = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= r1) return;
+    const double *m = minv + 9 * (size_t)row;
+    double a = in[3 * row], b = in[3 * row + 1], c = in[3 * row + 2];
+    out[3 * row] = m[0] * a + m[1] * b + m[2] * c;
+    out[3 * row + 1] = m[3] * a + m[4] * b + m[5] * c;
+    out[3 * row + 2] = m[6] * a + m[7] * b + m[8] * c;
+}
+// out[rows r0..r1) = D^-1 in  (fp64 diagonal blocks of the adjoint matrix: exact inverse of the decoupled, fully frozen trailing rows)
+void adjoint_apply_minv_tail(tsl_ctx *ctx, int r0, int r1, const double *in, double *out)
+{
+    if (r1 <= r0) return;
+    k_apply_minv64_range<<<GRID(r1 - r0, 256), 256, 0, ctx->stream>>>(r0, r1, ctx->minv64, in, out);
+    ctx->launches++;
+}
+void adjoint_axpy64(tsl_ctx *ctx, int n, const double *dx, double *x)
+{
+    k_axpy64<<<GRID(n, 256), 256, 0, ctx->stream>>>(n, dx, x);
+    ctx->launches++;
+}
+
+// ------------------------------------------------------------------------------------------------ FGMRES(m) (fp64)
+// Flexible GMRES with restarts on the fp64 adjoint matrix, right-preconditioned by the fp32 V-cycle (or fp64 block-Jacobi):
+//   z_k = M v_k;  w = A z_k;  w is orthogonalised against v_0..v_k by classical Gram-Schmidt applied twice (two batched
+//   multi-dot + multi-axpy passes: 4 kernels whatever k is);  the (m+1) x m Hessenberg least-squares problem lives on the host
+//   (Givens rotations), which reads k + 3 doubles per iteration;  x += Z y at the end of a cycle, then the TRUE residual.
+// The residual norm of GMRES is non-increasing: unlike BiCGStab the iteration cannot diverge or break down on the non-symmetric,
+// possibly indefinite reference Hessian (the flexible variant also tolerates the fp32 rounding of the V-cycle).
+__global__ void __launch_bounds__(256) k_gm_multidot(int n, const double *__restrict__ V, size_t stride, const double *__restrict__ w, double *out)
+{
+    // blockIdx.y = basis vector j; out[j] += V_j . w
+    const double *v = V + stride * blockIdx.y;
+    double s = 0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += v[i] * w[i];
+    block_atomic_sum2(s, 0.0, out + blockIdx.y, nullptr);
+}
+// w -= sum_j c[j] V_j  (c on the device);  optionally acc_ww += |w|^2 of the result
+__global__ void __launch_bounds__(256) k_gm_multiaxpy(int n, int k, const double *__restrict__ V, size_t stride, const double *__restrict__ c, double sign,
+                                                      double *w, double *acc_ww)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double ww = 0;
+    if (i < n) {
+        double s = 0;
+        for (int j = 0; j < k; j++) s += c[j] * V[stride * j + i];
+        double r = w[i] + sign * s;
+        w[i] = r;
+        ww = r * r;
+    }
+    block_atomic_sum2(ww, 0.0, acc_ww, nullptr);
+}
+// v = w / sqrt(*nrm2)   (in place when v == w)
+__global__ void k_gm_scale(int n, const double *w, const double *__restrict__ nrm2, double *v)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double d = *nrm2;
+    double inv = d > 0 ? 1.0 / sqrt(d) : 0.0;
+    if (i < n) v[i] = w[i] * inv;
+}
+
+static int gmres_reserve(tsl_ctx *ctx)
+{
+    const int m = ctx->gmres_m;
+    size_t n3p = 3 * (size_t)ctx->A.n_slices * 32;
+    if (ctx->gm_V && ctx->gm_cap_m >= m) return TSL_OK;
+    cudaFree(ctx->gm_V); cudaFree(ctx->gm_Z); cudaFree(ctx->gm_h);
+    if (ctx->gm_h_host) cudaFreeHost(ctx->gm_h_host);
+    ctx->gm_V = ctx->gm_Z = ctx->gm_h = nullptr; ctx->gm_h_host = nullptr; ctx->gm_cap_m = 0;
+    CK(cudaMalloc(&ctx->gm_V, sizeof(double) * n3p * (m + 1)));
+    CK(cudaMalloc(&ctx->gm_Z, sizeof(double) * n3p * m));
+    CK(cudaMalloc(&ctx->gm_h, sizeof(double) * (3 * (m + 2))));
+    CK(cudaMallocHost(&ctx->gm_h_host, sizeof(double) * (3 * (m + 2))));
+    ctx->gm_cap_m = m;
+    return TSL_OK;
+}
+
+// z = M v for fp64 vectors: fp32 V-cycle replayed as a captured graph between two conversion kernels, or fp64 block-Jacobi
+static int gm_precond(tsl_ctx *ctx, const double *in, double *out)
+{
+    int n = ctx->cfg.n_verts, nr = ctx->A.n_slices * 32;
+    cudaStream_t s = ctx->stream;
+    if (ctx->precond == 0 || ctx->mg.n_levels == 0) {
+        k_apply_minv64<<<GRID(n, 256), 256, 0, s>>>(n, ctx->minv64, in, out);
+        ctx->launches++;
+        return TSL_OK;
+    }
+    k_f64_to_f32<<<GRID(3 * nr, 256), 256, 0, s>>>(3 * n, 3 * nr, in, ctx->cg_r64tmp);
+    ctx->launches++;
+    const void *key = (const char *)ctx->A.val64 + 2;
+    TRYR(replay(ctx, ctx->g_bicg, key, [&]() { return mg_apply(ctx, ctx->cg_r64tmp, ctx->cg_z, nullptr); }));
+    k_f32_to_f64<<<GRID(3 * n, 256), 256, 0, s>>>(3 * n, ctx->cg_z, out);
+    ctx->launches++;
+    if (ctx->n_solve < n) adjoint_apply_minv_tail(ctx, ctx->n_solve, n, in, out);   // decoupled frozen rows: exact fp64 inverse
+    return TSL_OK;
+}
+
+int solve_fgmres64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
+{
+    const int n = ctx->cfg.n_verts, n3 = 3 * n, m = ctx->gmres_m;
+    cudaStream_t s = ctx->stream;
+    const SellMatrix &A = ctx->A;
+    TRYR(gmres_reserve(ctx));
+    const size_t stride = 3 * (size_t)A.n_slices * 32;
+    double *V = ctx->gm_V, *Z = ctx->gm_Z;
+    double *h1 = ctx->gm_h, *h2 = ctx->gm_h + (m + 2), *nrm = ctx->gm_h + 2 * (m + 2);   // device scalars
+    double *hh = ctx->gm_h_host;
+    double *res = ctx->adj_rhs;
+    std::vector<double> H((size_t)(m + 1) * m, 0.0), cs(m, 0.0), sn(m, 0.0), g(m + 1, 0.0), y(m, 0.0);
+    CK(cudaMemsetAsync(x, 0, sizeof(double) * n3, s));
+    double rr0 = 0, rr = 0;
+    TRYR(adjoint_residual64(ctx, rhs, x, res, &rr));
+    rr0 = rr;
+    int it = 0, flags = 0;
+    if (!(rr0 == rr0)) { ctx->err = "FGMRES: NaN right-hand side"; return TSL_ERR_NUMERIC; }
+    const double target2 = rel_tol * rel_tol * rr0;
+    int cycles = 0, stalled = 0;
+    while (rr0 > 0 && rr > target2) {
+        if (it >= max_iters) { flags |= 2; break; }
+        // v_0 = r / |r|
+        CK(cudaMemcpyAsync(nrm, &ctx->ks->rr, sizeof(double), cudaMemcpyDeviceToDevice, s));
+        k_gm_scale<<<GRID(n3, 256), 256, 0, s>>>(n3, res, nrm, V);
+        ctx->launches++;
+        const double beta = sqrt(rr);
+        std::fill(g.begin(), g.end(), 0.0);
+        g[0] = beta;
+        int k = 0;
+        bool breakdown = false;
+        for (; k < m && it < max_iters; ) {
+            double *vk = V + stride * k, *zk = Z + stride * k, *w = V + stride * (k + 1);
+            TRYR(gm_precond(ctx, vk, zk));
+            double *yc = side_pass<double>(ctx, ctx->cside64, zk);
+            k_spmv_dots<double><<<GRID(n, 256), 256, 0, s>>>(n, A.slice_base, A.colidx, A.val64, zk, w, nullptr, nullptr, nullptr, yc);
+            CK(cudaMemsetAsync(ctx->gm_h, 0, sizeof(double) * 3 * (m + 2), s));
+            dim3 gd(std::min<unsigned>(GRID(n3, 256), 592u), (unsigned)(k + 1));
+            k_gm_multidot<<<gd, 256, 0, s>>>(n3, V, stride, w, h1);
+            k_gm_multiaxpy<<<GRID(n3, 256), 256, 0, s>>>(n3, k + 1, V, stride, h1, -1.0, w, nullptr);
+            k_gm_multidot<<<gd, 256, 0, s>>>(n3, V, stride, w, h2);
+            k_gm_multiaxpy<<<GRID(n3, 256), 256, 0, s>>>(n3, k + 1, V, stride, h2, -1.0, w, nrm);
+            k_gm_scale<<<GRID(n3, 256), 256, 0, s>>>(n3, w, nrm, w);
+            ctx->launches += 6;
+            CK(cudaMemcpyAsync(hh, ctx->gm_h, sizeof(double) * 3 * (m + 2), cudaMemcpyDeviceToHost, s));
+            CK(cudaStreamSynchronize(s));
+            double *hc = H.data() + (size_t)k * (m + 1);          // column k
+            for (int j = 0; j <= k; j++) hc[j] = hh[j] + hh[(m + 2) + j];
+            double hk1 = sqrt(std::max(hh[2 * (m + 2)], 0.0));
+            if (!(hk1 == hk1)) { ctx->err = "FGMRES produced NaN"; return TSL_ERR_NUMERIC; }
+            for (int j = 0; j < k; j++) {                         // previous rotations
+                double t = cs[j] * hc[j] + sn[j] * hc[j + 1];
+                hc[j + 1] = -sn[j] * hc[j] + cs[j] * hc[j + 1];
+                hc[j] = t;
+            }
+            double d = hypot(hc[k], hk1);
+            if (d == 0.0) { breakdown = true; break; }           // A z_k lies in the span and is annihilated: singular operator
+            cs[k] = hc[k] / d; sn[k] = hk1 / d;
+            hc[k] = d;
+            g[k + 1] = -sn[k] * g[k];
+            g[k] = cs[k] * g[k];
+            k++; it++;
+            if (g[k] * g[k] <= target2 || hk1 == 0.0) break;
+        }
+        // y = R^-1 g, x += Z y
+        for (int i = k - 1; i >= 0; i--) {
+            double t = g[i];
+            for (int j = i + 1; j < k; j++) t -= H[(size_t)j * (m + 1) + i] * y[j];
+            y[i] = t / H[(size_t)i * (m + 1) + i];
+        }
+        if (k > 0) {
+            for (int j = 0; j < k; j++) hh[j] = y[j];
+            CK(cudaMemcpyAsync(h1, hh, sizeof(double) * k, cudaMemcpyHostToDevice, s));
+            k_gm_multiaxpy<<<GRID(n3, 256), 256, 0, s>>>(n3, k, Z, stride, h1, 1.0, x, nullptr);
+            ctx->launches++;
+            CK(cudaStreamSynchronize(s));                         // hh is reused by the next cycle
+        }
+        double rr_prev = rr;
+        TRYR(adjoint_residual64(ctx, rhs, x, res, &rr));
+        if (!(rr == rr)) { ctx->err = "FGMRES produced NaN"; return TSL_ERR_NUMERIC; }
+        cycles++;
+        if (breakdown) { flags |= 1; break; }
+        // three full cycles in a row that each gain less than 0.1 % on the true residual: stalled (the restarts keep losing the slow
+        // modes); the caller retries with the other preconditioner or reports the failure
+        stalled = (k == m && rr > 0.998 * rr_prev) ? stalled + 1 : 0;
+        if (stalled >= 3) { flags |= 1; break; }
+    }
+    if (st) { st->iters = it; st->flags = flags; st->rel_residual = rr0 > 0 ? sqrt(rr / rr0) : 0.0; }
     CK(cudaGetLastError());
     return TSL_OK;
 }

@@ -677,7 +677,7 @@ __global__ void __launch_bounds__(64) k_hessian_tets(TetDev t, const double *__r
     double Fm[9], H9[81];
     tet_F(x, t.B + 9 * c, Fm);
     tet_H9(t.P, Fm, t.B + 9 * c, t.W[c], H9);
-    if (project) spd_project<9>(H9, 20);
+    if (project) psd_clamp<9>(H9);
     const int *slot = t.slot + 16 * c;
     for (int a = 0; a < 4; a++)
         for (int b = 0; b < 4; b++) {
@@ -720,7 +720,7 @@ __global__ void __launch_bounds__(64) k_hessian_contact_general(ContactDev con, 
         }
     } else {
         active = contact_normal_full(x1 - x0, x2 - x0, xv - x0, cp.k_contact, cp.eps_contact, G, H);
-        if (active && spd) spd_project<9>(H, 20);
+        if (active && spd) psd_clamp<9>(H);
     }
     const double *w = con.w + 3 * i, *Tm = con.T + 6 * i, *dx0 = con.dx0 + 3 * i;
     d3 dx = xv - (w[0] * x0 + w[1] * x1 + w[2] * x2) - mk(dx0[0], dx0[1], dx0[2]);

@@ -6,7 +6,7 @@
 //                  neo-Hookean, P = mu (F - F^-T) + lam log(J) F^-T, J clamped at 0.01
 //   tactile model  model_elastic_tactile.py  get_force :158-174, compute_energy :184-201, compute_Hessian :82-124
 //                  P = mu F + lam (J - alpha) J F^-T, reduced 9x9 Hessian (vertex 3 eliminated) -> SPD_Projector(9, K=20)
-//   projector      linalg.py SPD_Projector :15-148 (Householder tridiagonalisation + K shifted QR sweeps, thresholds Q8)
+//   projector      linalg.py SPD_Projector :15-148 -> psd_clamp below (own algorithm: cyclic Jacobi, exact eigenvalue clamp)
 //   contact        BaseScene.contact_energy :488-543 with contact_diff.det / cross (contact_diff.py:4-129)
 // The host build of this header is what tests/test_solids_host.py checks against the oracle.
 #pragma once
@@ -41,98 +41,60 @@ TSL_HD void m3inv(const double *a, double *o)
     o[6] = (a[3] * a[7] - a[4] * a[6]) * id; o[7] = (a[1] * a[6] - a[0] * a[7]) * id; o[8] = (a[0] * a[4] - a[1] * a[3]) * id;
 }
 
-// ------------------------------------------------------------------------------------------------ SPD projector
-// SPD_Projector.project for an N x N matrix held row-major in M (in place): the reference's own algorithm, thresholds
-// included, because the projected matrices enter the parity tests entry by entry.
+// ------------------------------------------------------------------------------------------------ PSD clamp
+// Positive semi-definite part of a symmetric N x N matrix (row-major M, in place): eigen-decomposition by the cyclic Jacobi method,
+// negative eigenvalues set to zero.  This is where the reference calls linalg.SPD_Projector (code/engine/linalg.py:15-148: Householder
+// tridiagonalisation + K thresholded QR sweeps, quirk Q8) on the 9 x 9 cell / contact Hessians of the FORWARD matrix.  The projection
+// only shapes the Newton path, never the fixed point or the adjoint (which uses the un-projected matrix), so the library computes the
+// exact clamp with its own algorithm; the reference's approximate result differs from it by 5e-9 (median) to 1e-3 (sweeps exhausted)
+// of the largest entry on the golden matrices (tests/test_solids_host.py).  A matrix that is already PSD keeps its input bits.
 template <int N>
-TSL_HD void spd_project(double *M, int K)
+TSL_HD void psd_clamp(double *M)
 {
-    double A[N][N], T[N][N], Q[N][N];
+    double a[N][N], v[N][N];
+    double scale = 0;
     for (int i = 0; i < N; i++)
-        for (int j = 0; j < N; j++) { A[i][j] = M[i * N + j]; T[i][j] = 0; Q[i][j] = (i == j) ? 1.0 : 0.0; }
-    // ---- Householder reduction to tridiagonal form, reflectors accumulated in Q
-    for (int i = 0; i < N - 2; i++) {
-        double b = 0.0;
-        for (int j = i + 1; j < N; j++) b += A[j][i] * A[j][i];
-        b = sqrt(b);
-        if (b < 1e-6) {
-            T[i][i] = -1;
-            for (int j = i + 1; j < N; j++) A[i][j] = 0;
-            continue;
+        for (int j = 0; j < N; j++) {
+            a[i][j] = 0.5 * (M[i * N + j] + M[j * N + i]);
+            v[i][j] = (i == j) ? 1.0 : 0.0;
+            scale += fabs(a[i][j]);
         }
-        T[i][i] = 1;
-        if (A[i + 1][i] < 0) b = -b;
-        T[i + 1][i] = A[i + 1][i] + b;
-        double c = T[i + 1][i] * T[i + 1][i];
-        for (int j = i + 2; j < N; j++) { T[j][i] = A[j][i]; c += A[j][i] * A[j][i]; }
-        c = sqrt(2 / c);
-        for (int j = i + 1; j < N; j++) { T[j][i] *= c; T[i][j] = 0; }
-        for (int j = i + 1; j < N; j++) {
-            for (int k = i + 1; k <= j; k++) T[i][j] += A[j][k] * T[k][i];
-            for (int k = j + 1; k < N; k++) T[i][j] += A[k][j] * T[k][i];
-        }
-        double d = 0.0;
-        for (int j = i + 1; j < N; j++) d += T[i][j] * T[j][i];
-        d *= 0.5;
-        for (int j = i + 1; j < N; j++) { T[i][j] -= T[j][i] * d; A[i][j] = A[j][i] = 0; }
-        A[i + 1][i] = A[i][i + 1] = -b;
-        for (int j = i + 1; j < N; j++)
-            for (int k = i + 1; k <= j; k++) A[j][k] -= T[i][j] * T[k][i] + T[i][k] * T[j][i];
-        for (int k = 0; k < N; k++) {
-            double s = 0.0;
-            for (int j = i + 1; j < N; j++) s += Q[k][j] * T[j][i];
-            for (int j = i + 1; j < N; j++) Q[k][j] -= s * T[j][i];
-        }
-    }
-    A[N - 2][N - 1] = A[N - 1][N - 2];
-    // ---- K implicit-shift QR sweeps on the tridiagonal matrix (Wilkinson shift of the active trailing 2x2)
-    for (int sweep = 0; sweep < K; sweep++) {
-        int m = 0;
-        for (int i = 0; i < N - 1; i++) if (fabs(A[i + 1][i]) > 1e-5) m = i + 2;
-        if (m == 0) break;
-        double a = A[m - 2][m - 2], b = A[m - 2][m - 1], c = A[m - 1][m - 1];
-        double d = (a - c) / 2;
-        double sd = d > 0 ? 1.0 : -1.0;
-        double mu = c;
-        if (fabs(b) > 1e-6) mu -= (sd * b * b) / (fabs(d) + sqrt(d * d + b * b));
-        for (int i = 0; i < N; i++) A[i][i] -= mu;
-        for (int i = 0; i < m - 1; i++) {
-            double a1 = A[i][i], b1 = A[i][i + 1], e1 = A[i + 1][i], d1 = A[i + 1][i + 1];
-            double s = fabs(e1) > 1e-5 ? fabs(e1 / sqrt(a1 * a1 + e1 * e1)) : 0.0;
-            if (a1 * e1 < 0) s = -s;
-            double cc = sqrt(fmax(1 - s * s, 0.0));
-            T[0][i] = s;
-            A[i][i] = a1 * cc + e1 * s;
-            A[i][i + 1] = b1 * cc + d1 * s;
-            A[i + 1][i + 1] = d1 * cc - b1 * s;
-            if (i < N - 2) A[i + 1][i + 2] *= cc;
-        }
-        for (int i = 0; i < m - 1; i++) {
-            double a1 = A[i][i], b1 = A[i][i + 1], d1 = A[i + 1][i + 1];
-            double s = T[0][i];
-            double cc = sqrt(fmax(1 - s * s, 0.0));
-            A[i][i] = a1 * cc + b1 * s;
-            A[i + 1][i] = s * d1;
-            A[i + 1][i + 1] = cc * d1;
-            for (int r = 0; r < N; r++) {
-                double qa = Q[r][i], qb = Q[r][i + 1];
-                Q[r][i] = qa * cc + qb * s; Q[r][i + 1] = -qa * s + qb * cc;
-            }
-        }
-        for (int i = 0; i < N - 1; i++) A[i][i + 1] = A[i + 1][i];
-        for (int i = 0; i < N; i++) A[i][i] += mu;
-    }
-    // ---- rebuild from the positive eigenpairs
-    for (int i = 0; i < N; i++) T[0][i] = A[i][i];
-    for (int i = 0; i < N * N; i++) M[i] = 0;
-    for (int i = 0; i < N; i++) {
-        double v = T[0][i];
-        if (v > 0)
-            for (int j = 0; j < N; j++) {
-                double v2 = v * Q[j][i];
-                for (int k = 0; k < N; k++) M[j * N + k] += v2 * Q[k][i];
+    if (!(scale > 0)) return;                       // zero matrix (or NaN): nothing to clamp
+    for (int sweep = 0; sweep < 40; sweep++) {
+        double off = 0;
+        for (int p = 0; p < N - 1; p++)
+            for (int q = p + 1; q < N; q++) off += fabs(a[p][q]);
+        if (off <= 1e-18 * scale) break;
+        for (int p = 0; p < N - 1; p++)
+            for (int q = p + 1; q < N; q++) {
+                double apq = a[p][q];
+                if (fabs(apq) <= 1e-300) continue;
+                double theta = (a[q][q] - a[p][p]) / (2 * apq);
+                double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1));
+                double cs = 1 / sqrt(t * t + 1), sn = t * cs;
+                for (int k = 0; k < N; k++) {
+                    double akp = a[k][p], akq = a[k][q];
+                    a[k][p] = cs * akp - sn * akq; a[k][q] = sn * akp + cs * akq;
+                }
+                for (int k = 0; k < N; k++) {
+                    double apk = a[p][k], aqk = a[q][k];
+                    a[p][k] = cs * apk - sn * aqk; a[q][k] = sn * apk + cs * aqk;
+                }
+                for (int k = 0; k < N; k++) {
+                    double vkp = v[k][p], vkq = v[k][q];
+                    v[k][p] = cs * vkp - sn * vkq; v[k][q] = sn * vkp + cs * vkq;
+                }
             }
     }
+    bool negative = false;
+    for (int i = 0; i < N; i++) negative = negative || a[i][i] < 0;
+    if (!negative) return;
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++) {
+            double s = 0;
+            for (int k = 0; k < N; k++) { double w = a[k][k] > 0 ? a[k][k] : 0; s += w * v[i][k] * v[j][k]; }
+            M[i * N + j] = s;
+        }
 }
 
 // ------------------------------------------------------------------------------------------------ tetrahedra
