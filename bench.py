@@ -1,17 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json metric: element-updates/sec per implicit fwd+bwd step; HBM GB/s vs peak.
 
-One "step" = one implicit forward time step of the sheet (contact query, Newton with multigrid-preconditioned PCG, line search) plus
-one adjoint step for it (contact re-detection, un-projected fp64 Hessian, multigrid-preconditioned BiCGStab solve, parameter gradient dL/dKb).
-`value` = triangles x steps / device time with state resident in HBM; `e2e` = the same through the host-buffer C-ABI entry
+Workload (both arms, every N): the DROP of a square sheet on a frozen table (thinshelllab_b200.synthetic.DROP: released 0.6 mm above
+the table, outside the 0.4 mm contact gap; Scene_bouncing physics, dt 5 ms).  One "step" = one implicit forward time step (contact
+query, Newton with multigrid-preconditioned PCG, line search) plus one adjoint step for it (contact re-detection, un-projected fp64
+Hessian, adjoint solve, dL/dKb).  The timed window is FIXED: steps 0 .. K-1 of the drop from the initial state (warm-up steps run
+the same steps first, then the state is restored), so the number does not depend on where a landing is cut; Newton / PCG totals and
+ms per Newton iteration / per PCG iteration are first-class fields of the line.
+
+`value` = triangles x steps / device time with state resident in HBM; `e2e` = the same window through the host-buffer C-ABI entry
 point (tsl_step_forward_host) + host-side loss seed / gradient read-back, copies inside the timed region.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--sheet-n 707] [--impl reference]
 
-N > 1 (torchrun): one independent sheet per rank (replicas, weak scaling, no data-path collective).  The strip partition of ONE sheet
-over the GPUs (tsl_dist_init, NCCL halo exchange + all-reduced Krylov scalars) exists for the forward step and is
-exact but, lacking a coarse space across strips, slower than one GPU (tools/bench_partition.py,
-profiles/r1_partition_2gpu.md): the benchmark keeps replicas and says so in config.parallelism.
+N > 1 (torchrun): N replicas of the same sheet (same seed), weak scaling, no data-path collective (DESIGN.md section 6 says why the
+strip partition of one sheet is opt-in).  --impl reference: the CPU oracle (restatement of the reference, fp64, SuperLU) on the host
+cores, same config object, each step a bounded sample (a sub-sheet of the same drop, see cpu_baseline.sample).
 """
 import argparse
 import json
@@ -30,6 +34,8 @@ sys.path.insert(0, ROOT)
 if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
     del os.environ["NCCL_DEBUG"]
 
+METRIC = "tri_steps_per_s (implicit fwd+bwd step)"
+UNIT = "tri-steps/s"
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the roofline kernel from the committed ncu --set full capture
 # (profiles/), keyed by sheet size; None where no capture exists
@@ -42,6 +48,15 @@ def _peaks():
             return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
     except Exception:
         return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def workload_config(N):
+    """the `config` object of BOTH arms (the driver compares them)"""
+    n_tris = 2 * N * N
+    tag = {158: "BASELINE configs[1] / [2]", 316: "BASELINE configs[3] sheet size", 707: "the 1 M-triangle sheet of BASELINE configs[4] / north_star"}.get(N, "custom size")
+    return {"workload": f"sheet {N}x{N} ({n_tris} tris, dx 2 mm) dropped 0.6 mm onto a frozen table, Scene_bouncing physics, dt 5 ms; "
+                        f"window = steps 0..K-1 of the drop, forward + adjoint (dL/dKb) per step; {tag}",
+            "sheet_n": N, "n_tris": n_tris, "window": "steps 0..K-1 from the initial state (state restored after warm-up)"}
 
 
 class ClockSampler(threading.Thread):
@@ -76,27 +91,38 @@ class ClockSampler(threading.Thread):
 
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
-def oracle_fwd_bwd(sample_n, steps, threads=None):
-    """times `steps` fwd+bwd steps of the CPU oracle on a sample_n x sample_n sheet (each from the same initial state)."""
+def oracle_window(sample_n, steps, budget_s, threads=None):
+    """steps 0..steps-1 of the drop on a sample_n x sample_n sheet with the CPU oracle, forward + adjoint per step, stopping early when
+    `budget_s` seconds of wall clock are spent.  Returns (tris, [seconds per completed step], threads, [newton iterations per step])."""
     from oracle import tsl_oracle as orc
-    from thinshelllab_b200.synthetic import sheet_spec
+    from thinshelllab_b200.synthetic import DROP, sheet_spec
     if threads:
         orc.lib().orc_set_num_threads(int(threads))
-    sp = sheet_spec(sample_n)
-    times = []
+    sp = sheet_spec(sample_n, **DROP)
+    o = orc.OracleScene(sample_n, sample_n, sp["dx"], sp["dt"], sp["table_pos"], sp["table_faces"], sp["table_mass"], k_contact=sp["k_contact"],
+                        mu=sp["mu"], max_n_constraints=sp["max_n_constraints"], grid_n=sp["grid_n"])
+    o.pos[:o.NVc] = sp["cloth_pos"]; o.prev_pos[:] = o.pos
+    times, newton = [], []
+    t_start = time.perf_counter()
     for _ in range(steps):
-        o = orc.OracleScene(sample_n, sample_n, sp["dx"], sp["dt"], sp["table_pos"], sp["table_faces"], sp["table_mass"], k_contact=sp["k_contact"],
-                            mu=sp["mu"], max_n_constraints=sp["max_n_constraints"], grid_n=sp["grid_n"])
-        o.pos[:o.NVc] = sp["cloth_pos"]; o.prev_pos[:] = o.pos
         g = orc.OracleGrad(o, 2)
         t0 = time.perf_counter()
         g.copy_pos(0)
-        o.time_step()
+        newton.append(o.time_step())
         g.copy_pos(1)
         g.pos_grad[1, :o.NVc, 2] = 1.0
         g.transfer_grad(1)
+        # transfer_grad leaves the scene at (x_t, x_{t-1}); the next forward step starts from x_t with its own velocity
+        o.pos[:] = g.pos_buffer[1]
         times.append(time.perf_counter() - t0)
-    return sp["n_tris"], times, orc.lib().orc_num_threads()
+        if time.perf_counter() - t_start > budget_s:
+            break
+    return sp["n_tris"], times, orc.lib().orc_num_threads(), newton
+
+
+def _cpu_sample_text(n, tris, times, newton, kind="window"):
+    return (f"{n}x{n} sub-sheet ({tris} tris) of the same drop, steps 0..{len(times) - 1} forward + adjoint "
+            f"({int(np.sum(newton))} Newton iterations), CPU oracle (fp64 restatement of the reference, SuperLU direct solves, OpenMP assembly)")
 
 
 def run_reference(args, rank):
@@ -104,72 +130,86 @@ def run_reference(args, rank):
         return
     n = args.cpu_sample_n
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())       # torchrun pins it to 1: the CPU arm uses every host core
-    for _ in range(args.warmup):
-        pass                                    # the CPU arm has no warm-up state worth paying ~25 s per step for
-    tris, times, threads = oracle_fwd_bwd(n, max(1, args.steps), threads=os.cpu_count())
+    want = args.warmup + args.steps
+    # no warm-up state exists on the CPU: the W + K launched steps are all timed; when the wall-clock bound cuts the window short the
+    # throughput is that of the steps completed (steps_run)
+    tris, times, threads, newton = oracle_window(n, want, args.cpu_budget_s, threads=os.cpu_count())
     T = float(np.sum(times))
     val = tris * len(times) / T
-    sample = f"{n}x{n} sheet ({tris} tris) over the table, {len(times)} fwd+bwd step(s) from the bench's initial-state generator; SuperLU direct solves"
+    sample = _cpu_sample_text(n, tris, times, newton)
     print(json.dumps({
-        "impl": "reference", "metric": "tri_steps_per_s (implicit fwd+bwd step)", "value": val, "unit": "tri-steps/s", "n_gpus": args.gpus,
-        "steps": len(times), "warmup": 0, "ms_per_step": 1e3 * T / len(times), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"sheet {args.sheet_n}x{args.sheet_n} fwd+bwd (CPU arm runs the bounded sample below)", "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "tri-steps/s", "cores": threads, "kind": "port", "sample": sample,
-                         "note": "CPU oracle (restatement of the reference sources, pinned to goldens); Taichi/CuPy cannot be installed here"},
-        "e2e": {"value": val, "unit": "tri-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "steps_run": len(times), "ms_per_step": 1e3 * T / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.sheet_n),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "newton_iters": [int(x) for x in newton],
+                         "note": "CPU oracle = restatement of the reference sources pinned to goldens made by the reference itself under "
+                                 "a Taichi emulation; Taichi / CuPy cannot be installed in this image, the reference's dense-backed "
+                                 "SparseMatrix needs 92 GB at 50 k triangles"},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
+def _fixed_window(s, g, e, NVc, steps, adjoint_tol, snap):
+    """steps 0..steps-1 from the snapshot `snap`, device resident; returns (ms, per-step stats)"""
+    import torch
+    e.pos.copy_(snap[0]); e.prev_pos.copy_(snap[0]); e.vel.copy_(snap[1]); e.cloth_ref_angle[0].copy_(snap[2]); e.reset_contact_state()
+    stats = []
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(steps):
+        g.copy_pos(s, 0)
+        st = s.time_step()
+        g.copy_pos(s, 1)
+        g._pos_grad.zero_(); g._angleref_grad.zero_()
+        g._pos_grad[1, :NVc, 2] = 1.0                      # loss seed: dL/dz = 1 on the cloth (cf. Grad.get_loss_slide_simple)
+        its, flags, rr = g.transfer_grad(1, s, rel_tol=adjoint_tol)
+        stats.append((st.newton_iters, st.linear_iters, st.linesearch_evals, st.n_contacts, its, st.flags, flags, int(st.converged)))
+    ev1.record()
+    torch.cuda.synchronize()
+    return ev0.elapsed_time(ev1), stats
+
+
 def secondary_50k(args, dev):
-    """BASELINE.json configs[1] / configs[2] (50 k-triangle sheet, forward only and forward + adjoint) on one GPU, state resident in
-    HBM: reported inside config, next to the 1 M-triangle headline"""
+    """BASELINE.json configs[1] / configs[2] (50 k-triangle sheet, forward only and forward + adjoint), same drop window, one GPU"""
     import torch
     from thinshelllab_b200.engine.analytic_grad_system import Grad
-    from thinshelllab_b200.synthetic import sheet_scene
-    N = 158
-    s = sheet_scene(N, device=dev)
-    if args.newton_mode >= 0:
-        from thinshelllab_b200 import _lib as _l
-        s.engine.set_option(_l.OPT_NEWTON_MODE, args.newton_mode)
+    from thinshelllab_b200.synthetic import DROP, sheet_scene
+    N, K = 158, 10
+    s = sheet_scene(N, device=dev, **DROP)
     e, NVc, g = s.engine, s.cloths[0].NV, Grad(s, 2, 0)
-
-    def fwd():
-        g.copy_pos(s, 0)
-        s.time_step()
-        g.copy_pos(s, 1)
-
-    def bwd():
-        g._pos_grad.zero_(); g._angleref_grad.zero_()
-        g._pos_grad[1, :NVc, 2] = 1.0
-        g.transfer_grad(1, s, rel_tol=args.adjoint_tol)
-
-    for _ in range(3):
-        fwd(); bwd()
     snap = (e.pos.clone(), e.vel.clone(), e.cloth_ref_angle[0].clone())
+    _fixed_window(s, g, e, NVc, 3, args.adjoint_tol, snap)              # warm-up
     out = {}
-    for name, with_bwd in (("configs[1] forward only", False), ("configs[2] forward + adjoint", True)):
-        e.pos.copy_(snap[0]); e.prev_pos.copy_(snap[0]); e.vel.copy_(snap[1]); e.cloth_ref_angle[0].copy_(snap[2]); e.reset_contact_state()
-        torch.cuda.synchronize()
-        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ev0.record()
-        for _ in range(3):
-            fwd()
-            if with_bwd:
-                bwd()
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1)
-        out[name] = {"sheet": "158x158 (49928 tris)", "steps": 3, "ms_per_step": ms / 3, "tri_steps_per_s": 2 * N * N * 3 / (ms * 1e-3)}
+    ms, stats = _fixed_window(s, g, e, NVc, K, args.adjoint_tol, snap)
+    st = np.array(stats, dtype=np.float64)
+    out["configs[2] forward + adjoint"] = {"sheet": "158x158 (49928 tris)", "window": f"steps 0..{K - 1} of the drop", "ms_per_step": ms / K,
+                                           "tri_steps_per_s": 2 * N * N * K / (ms * 1e-3), "newton_iters": int(st[:, 0].sum()),
+                                           "pcg_iters": int(st[:, 1].sum()), "adjoint_iters": int(st[:, 4].sum())}
+    # forward only
+    e.pos.copy_(snap[0]); e.prev_pos.copy_(snap[0]); e.vel.copy_(snap[1]); e.cloth_ref_angle[0].copy_(snap[2]); e.reset_contact_state()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    nw = 0
+    for _ in range(K):
+        nw += s.time_step().newton_iters
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    out["configs[1] forward only"] = {"sheet": "158x158 (49928 tris)", "window": f"steps 0..{K - 1} of the drop", "ms_per_step": ms / K,
+                                      "tri_steps_per_s": 2 * N * N * K / (ms * 1e-3), "newton_iters": int(nw)}
     del s, g
     torch.cuda.empty_cache()
     return out
 
 
 def secondary_solids(args, dev):
-    """BASELINE.json configs[0] (Scene_folding: cloth strip + table + tactile pad on a gripper, T = 3 rollout + trajectory adjoint, the
-    scene state of thinshelllab_b200/data/scene_folding_cloth0p1.npz) and a configs[3]-style scene (316 x 316 = 200 k-triangle sheet on the table with the volumetric
-    tactile pad pressed into it; contacts against moving triangles), one GPU, state resident in HBM"""
+    """BASELINE.json configs[0] (Scene_folding: cloth strip + table + tactile pad on a gripper, T = 3 rollout + trajectory adjoint) and a
+    configs[3]-style scene (316 x 316 = 200 k-triangle sheet on the table with the volumetric tactile pad pressed into it; contacts
+    against moving triangles), one GPU, state resident in HBM"""
     import torch
     from thinshelllab_b200.agent.traj_opt_single import agent_trajopt
     from thinshelllab_b200.engine.analytic_grad_single import Grad
@@ -183,7 +223,6 @@ def secondary_solids(args, dev):
     out = {}
 
     def rollout(s, T, traj, reps):
-        e = s.engine
         NVc = s.cloths[0].NV
         agent = agent_trajopt(T, 1, max_moving_dist=0.001)
         agent.traj.from_numpy(traj)
@@ -211,7 +250,7 @@ def secondary_solids(args, dev):
             torch.cuda.synchronize()
             ms = ev0.elapsed_time(ev1)
             res = {"steps": T - 1, "ms_per_step": ms / (T - 1), "tri_steps_per_s": s.cloths[0].NF * (T - 1) / (ms * 1e-3), "newton_iters": newton,
-                   "pcg_iters": krylov, "bicgstab_iters": bi, "contacts_last_step": int(st.n_contacts), "converged_last_step": bool(st.converged)}
+                   "pcg_iters": krylov, "adjoint_iters (0 = dense LU)": bi, "contacts_last_step": int(st.n_contacts), "converged_last_step": bool(st.converged)}
         return res
 
     s = Scene(g, device=dev)
@@ -232,14 +271,14 @@ def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
     from thinshelllab_b200.engine.analytic_grad_system import Grad
-    from thinshelllab_b200.synthetic import sheet_scene
+    from thinshelllab_b200.synthetic import DROP, sheet_scene
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     N = args.sheet_n
-    s = sheet_scene(N, device=dev, seed=rank)
+    s = sheet_scene(N, device=dev, **DROP)                    # the same sheet (seed 0) on every rank
     e = s.engine
     if args.newton_mode >= 0:
         from thinshelllab_b200 import _lib as _l
@@ -253,17 +292,7 @@ def run_ours(args, rank, world):
             dist.barrier()
         torch.cuda.synchronize()
 
-    stats = []
-
-    def fwd_bwd_device():
-        g.copy_pos(s, 0)
-        st = s.time_step()
-        g.copy_pos(s, 1)
-        g._pos_grad.zero_(); g._angleref_grad.zero_()
-        g._pos_grad[1, :NVc, 2] = 1.0                      # loss seed: Grad.get_loss_slide-style dL/dz = 1 on the cloth
-        its, flags, rr = g.transfer_grad(1, s, rel_tol=args.adjoint_tol)
-        stats.append((st.newton_iters, st.linear_iters, st.linesearch_evals, st.n_contacts, its, st.flags, flags))
-
+    snap = (e.pos.clone(), e.vel.clone(), e.cloth_ref_angle[0].clone())
     # host buffers of the e2e path
     pos_h = torch.empty((e.n_verts, 3), dtype=torch.float64).pin_memory()
     vel_h = torch.empty((e.n_verts, 3), dtype=torch.float64).pin_memory()
@@ -273,41 +302,28 @@ def run_ours(args, rank, world):
     def fwd_bwd_host():
         g._pos_buffer[0].copy_(pos_h, non_blocking=True)    # x_{t-1} travels with the step's inputs
         g._ref_angle_buffer[0, 0].copy_(e.cloth_ref_angle[0])
-        st = e.step_forward_host(pos_h, vel_h)             # H2D pos, vel -> step -> D2H pos, vel
+        e.step_forward_host(pos_h, vel_h)                   # H2D pos, vel -> step -> D2H pos, vel
         g.copy_pos(s, 1)
         g._pos_grad.zero_(); g._angleref_grad.zero_()
         g._pos_grad[1].copy_(seed_h, non_blocking=True)     # H2D loss seed
         g.transfer_grad(1, s, rel_tol=args.adjoint_tol)
         pg_h.copy_(g._pos_grad[0], non_blocking=True)       # D2H dL/dx_{t-1}
-        kb = g.grad_kb[None]                                # D2H dL/dKb (8 bytes, syncs)
-        return kb
+        return g.grad_kb[None]                              # D2H dL/dKb (8 bytes, syncs)
 
-    for _ in range(args.warmup):
-        fwd_bwd_device()
-    stats.clear()
-    # both timed regions run the SAME physical steps: snapshot the state after warm-up
-    snap = (e.pos.clone(), e.vel.clone(), e.cloth_ref_angle[0].clone())
-
-    def restore():
-        e.pos.copy_(snap[0]); e.prev_pos.copy_(snap[0]); e.vel.copy_(snap[1]); e.cloth_ref_angle[0].copy_(snap[2])
-        e.reset_contact_state()
-    restore()
+    # warm-up: the first W steps of the same window (graph capture, allocations, clocks), then the state is restored
+    if args.warmup > 0:
+        _fixed_window(s, g, e, NVc, args.warmup, args.adjoint_tol, snap)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
     l0 = e.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for _ in range(args.steps):
-        fwd_bwd_device()
-    ev1.record()
+    ms, stats = _fixed_window(s, g, e, NVc, args.steps, args.adjoint_tol, snap)
     barrier()
-    ms = ev0.elapsed_time(ev1)
     launches = e.launch_count() - l0
     clocks = sampler.stop() if rank == 0 else None
-    # e2e
-    restore()
+    # e2e: the same window through host buffers
+    e.pos.copy_(snap[0]); e.prev_pos.copy_(snap[0]); e.vel.copy_(snap[1]); e.cloth_ref_angle[0].copy_(snap[2]); e.reset_contact_state()
     pos_h.copy_(e.pos); vel_h.copy_(e.vel)
     barrier()
     t0 = time.perf_counter()
@@ -317,8 +333,7 @@ def run_ours(args, rank, world):
     ms_e2e = 1e3 * (time.perf_counter() - t0)
     from thinshelllab_b200 import dist as tdist
     units, (ms, ms_e2e) = tdist.aggregate(n_tris * args.steps, [ms, ms_e2e], device=dev)   # SUM of units, MAX of times
-    # ---- roofline of the dominant kernel class (fine-level block-sparse matrix pass: PCG SpMV and the V-cycle's fine
-    # smoother / residual kernels stream the same bytes), timed live with CUDA events on the launching stream inside libtsl
+    # ---- rooflines, timed live with CUDA events on the launching stream inside libtsl (tsl_bench_kernel), at the state the window left
     from thinshelllab_b200 import _lib
     e.assemble(_lib.ASM_RESIDUAL | _lib.ASM_HESSIAN | _lib.ASM_NEWTON | _lib.ASM_SPD)
     sz = e.sizes()
@@ -351,43 +366,56 @@ def run_ours(args, rank, world):
     value = units / (ms * 1e-3)
     e2e = units / (ms_e2e * 1e-3)
     nb = e.n_verts * 24
+    tot_newton, tot_pcg = float(st[:, 0].sum()), float(st[:, 1].sum())
+
+    def rl(us, bytes_):
+        return {"us": us, "algorithmic_bytes": bytes_, "achieved_GBps": bytes_ / (us * 1e-6) / 1e9, "frac": bytes_ / (us * 1e-6) / 1e9 / peak}
+
+    cfg = workload_config(N)
     out = {
-        "metric": "tri_steps_per_s (implicit fwd+bwd step)", "value": value, "unit": "tri-steps/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64 (state, energy, residual, contact, adjoint matrix and solve) + f32 (forward Newton matrix, PCG vectors, multigrid)", "data": "synthetic",
-        "config": {"workload": f"sheet {N}x{N} ({n_tris} tris, dx 2 mm) landing on a frozen table, Scene_bouncing physics, fwd + adjoint (dL/dKb) per step"
-                               + (" -- the 1 M-triangle sheet of BASELINE configs[4] / north_star on ONE GPU (largest single-GPU configuration; configs[1] and [2] are in baseline_configs_50k)" if N == 707 else ""),
-                   "sheet_n": N, "n_tris": n_tris, "n_verts": V, "nnzb": sz["nnzb"], "nnzb_padded": sz["nnzb_padded"], "n_solve": Vs, "nnzb_solve": Bs,
-                   "parallelism": "single GPU" if world == 1 else f"{world} independent replicas (the strip partition of one sheet is exact but not yet faster than one GPU: DESIGN.md section 6)",
+        "dtype": "f64 (state, energy, residual, contact, adjoint matrix and solve) + f32 (forward Newton matrix, multigrid)", "data": "synthetic",
+        "config": cfg,
+        "work": {"newton_iters": int(tot_newton), "pcg_iters": int(tot_pcg), "linesearch_evals": int(st[:, 2].sum()), "adjoint_iters": int(st[:, 4].sum()),
+                 "ms_per_newton_iter": ms / max(tot_newton, 1), "ms_per_pcg_iter_incl_everything": ms / max(tot_pcg, 1),
+                 "unconverged_steps": int((st[:, 7] == 0).sum()),
+                 "per_step": [{"newton": int(r[0]), "pcg": int(r[1]), "adjoint": int(r[4]), "contacts": int(r[3])} for r in st],
+                 "flags": {"pcg_negative_curvature_steps": int((st[:, 5].astype(int) & 1).sum()), "krylov_cap_hit": int(((st[:, 5].astype(int)) & 2).sum() // 2),
+                           "adjoint_fallbacks": int(((st[:, 6].astype(int)) & 8).sum() // 8)}},
+        "system": {"n_verts": V, "nnzb": sz["nnzb"], "nnzb_padded": sz["nnzb_padded"], "n_solve": Vs, "nnzb_solve": Bs,
+                   "parallelism": "single GPU" if world == 1 else f"{world} replicas of the same sheet (no data-path collective; the strip partition of one sheet is opt-in: DESIGN.md section 6)",
                    "l2": "matrix %.0f MB > 126 MB L2" % (sz["bytes_matrix_f32"] / 1e6) if sz["bytes_matrix_f32"] > 126e6 else
-                         "working set %.0f MB fits the 126 MB L2: roofline fraction can exceed 1" % (sz["bytes_matrix_f32"] / 1e6),
-                   "solver": "Newton (exact / clamped / blended matrix, line search) + multigrid-preconditioned PCG; adjoint: multigrid-preconditioned BiCGStab fp64",
-                   "newton_mode": ("library default" if args.newton_mode < 0 else args.newton_mode),
-                   "per_step_mean": {"newton_iters": st[:, 0].mean(), "pcg_iters": st[:, 1].mean(), "linesearch_evals": st[:, 2].mean(),
-                                     "contacts": st[:, 3].mean(), "bicgstab_iters": st[:, 4].mean()},
-                   "per_step": [{"newton": int(r[0]), "pcg": int(r[1]), "bicgstab": int(r[4]), "contacts": int(r[3])} for r in st],
-                   "flags": {"pcg_negative_curvature_steps": int((st[:, 5].astype(int) & 1).sum()), "krylov_cap_hit": int(((st[:, 5].astype(int) | st[:, 6].astype(int)) & 2).sum() // 2)}},
+                         "working set %.0f MB fits the 126 MB L2: roofline fractions can exceed 1" % (sz["bytes_matrix_f32"] / 1e6),
+                   "solver": "Newton (exact / clamped / blended matrix, line search) + multigrid-preconditioned PCG; adjoint: dense LU below 12288 unknowns, multigrid-FGMRES(50) fp64 above",
+                   "newton_mode": ("library default" if args.newton_mode < 0 else args.newton_mode)},
         "clocks": clocks,
-        "e2e": {"value": e2e, "unit": "tri-steps/s", "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 4 * nb, "d2h_bytes_per_step": 3 * nb + 8},
+        "e2e": {"value": e2e, "unit": UNIT, "ms_per_step": ms_e2e / args.steps, "h2d_bytes_per_step": 4 * nb, "d2h_bytes_per_step": 3 * nb + 8},
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "kernel": "k_spmv_mixed (fine-level sliced-ELL matrix pass of PCG, fp32 matrix x fp64 vector + fused dot; k_cheb_step_sell / k_mg_residual_sell stream the same matrix)",
                      "achieved": spmv_bytes / (ms_spmv * 1e-3) / 1e9, "peak": peak,
                      "peak_source": peak_src, "unit": "GB/s", "frac": spmv_bytes / (ms_spmv * 1e-3) / 1e9 / peak, "traffic": TRAFFIC.get(N),
                      "us_per_launch": 1e3 * ms_spmv, "algorithmic_bytes_per_launch": spmv_bytes,
-                     "pcg_iteration": {"us": 1e3 * ms_pcg, "algorithmic_bytes": pcg_bytes, "achieved": pcg_bytes / (ms_pcg * 1e-3) / 1e9,
-                                       "frac": pcg_bytes / (ms_pcg * 1e-3) / 1e9 / peak, "note": "one captured CUDA graph: SpMV + update + V-cycle + direction"},
-                     "other_us": {"vcycle": 1e3 * ms_vcycle, "mg_setup": 1e3 * ms_setup, "hessian": 1e3 * ms_hess, "residual": 1e3 * ms_resid, "energy": 1e3 * ms_energy}},
+                     "pcg_iteration": dict(rl(1e3 * ms_pcg, pcg_bytes), note="one captured CUDA graph: SpMV + update + V-cycle + direction"),
+                     # SURVEY 8d algorithmic bytes: Hessian 280 B/tri, residual 82 B/tri, energy 76 B/tri
+                     "assembly": {"hessian (one Newton-model matrix)": rl(1e3 * ms_hess, 280.0 * n_tris), "residual": rl(1e3 * ms_resid, 82.0 * n_tris),
+                                  "energy": rl(1e3 * ms_energy, 76.0 * n_tris)},
+                     "other_us": {"vcycle": 1e3 * ms_vcycle, "mg_setup": 1e3 * ms_setup}},
     }
     if world == 1 and N != 158 and not args.no_secondary:
-        out["config"]["baseline_configs_50k"] = secondary_50k(args, dev)
+        out["secondary"] = {}
         try:
-            out["config"]["baseline_configs_solids"] = secondary_solids(args, dev)
+            out["secondary"]["baseline_configs_50k"] = secondary_50k(args, dev)
         except Exception as ex:                  # a secondary measurement must not take the headline line down with it
-            out["config"]["baseline_configs_solids"] = {"error": repr(ex)}
+            out["secondary"]["baseline_configs_50k"] = {"error": repr(ex)}
+        try:
+            out["secondary"]["baseline_configs_solids"] = secondary_solids(args, dev)
+        except Exception as ex:
+            out["secondary"]["baseline_configs_solids"] = {"error": repr(ex)}
     if world == 1 and not args.no_cpu_baseline:
-        tris, times, threads = oracle_fwd_bwd(args.cpu_sample_n, 1, threads=os.cpu_count())
-        out["cpu_baseline"] = {"value": tris / times[0], "unit": "tri-steps/s", "cores": threads, "kind": "port",
-                               "sample": f"{args.cpu_sample_n}x{args.cpu_sample_n} sheet ({tris} tris), 1 fwd+bwd step, CPU oracle (fp64, SuperLU direct solves; not Taichi)"}
+        tris, times, threads, newton = oracle_window(args.cpu_sample_n, 2, 25.0, threads=os.cpu_count())
+        out["cpu_baseline"] = {"value": tris * len(times) / float(np.sum(times)), "unit": UNIT, "cores": threads, "kind": "port",
+                               "sample": _cpu_sample_text(args.cpu_sample_n, tris, times, newton)}
     print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
@@ -396,14 +424,15 @@ def run_ours(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--sheet-n", type=int, default=707, help="sheet is N x N quads: 158 -> 50k tris, 316 -> 200k, 707 -> 1M")
     ap.add_argument("--cpu-sample-n", type=int, default=32)
+    ap.add_argument("--cpu-budget-s", type=float, default=150.0, help="wall-clock bound of the CPU arm's window")
     ap.add_argument("--adjoint-tol", type=float, default=1e-8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the 50 k-triangle configs[1] / configs[2] measurement")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the 50 k-triangle / solids secondary measurements")
     ap.add_argument("--newton-mode", type=int, default=-1, help="TSL_OPT_NEWTON_MODE of the forward solve (-1: library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -598,7 +598,7 @@ static int solve_adjoint64(tsl_ctx *ctx, const double *rhs, double *x, double re
         }
     }
     if (st) *st = s0;
-    if ((s0.flags & 3) || !(s0.rel_residual <= std::max(10 * rel_tol, 1e-13))) {
+    if ((s0.flags & 3) || !(s0.rel_residual <= std::max(10 * rel_tol, mode == 1 ? 1e-9 : 1e-13))) {
         char buf[160];
         snprintf(buf, sizeof(buf), "adjoint solve did not converge: %d iterations, flags %d, relative residual %.3e (tolerance %.1e)", s0.iters, s0.flags,
                  s0.rel_residual, rel_tol);

@@ -1,8 +1,9 @@
 """Rank plumbing of the multi-GPU runs (one process per GPU, torch.distributed).
 
-Round-1 status of the element partition: not implemented -- N ranks simulate N independent sheets
-("replicas", weak scaling, no data-path collective).  What is shared across ranks is only the measurement protocol:
-barrier, device-side timing, MAX over ranks of the elapsed time, SUM of the units processed."""
+The element partition itself (strips of grid rows, NCCL halo rows + all-reduced Krylov scalars) lives in
+libtsl (tsl_dist_init, csrc/tsl_dist.cu) and is driven through ShellEngine.dist_init / synthetic.strip_scene.  This module holds
+what every multi-rank run shares: barrier, MAX over ranks of device-side elapsed times, SUM of the units processed, and the
+round-robin dealing of independent sheets for replica runs."""
 import torch
 import torch.distributed as dist
 

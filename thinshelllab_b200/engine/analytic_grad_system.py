@@ -32,7 +32,8 @@ class Grad:
     def reset(self):
         self._pos_buffer.zero_(); self._pos_grad.zero_()
         self._grad_kb.zero_()
-        # the reference's system Grad.reset leaves angleref_grad untouched (analytic_grad_system.py:33-39)
+        # analytic_grad_system.py:33-39 also clears the other parameter gradients (and leaves angleref_grad untouched)
+        self.grad_mu[None] = 0.0; self.grad_lam[None] = 0.0; self.grad_friction_coef[None] = 0.0
 
     def init_mass(self, sys):
         pass                                  # the engine reads sys.mass directly

@@ -20,16 +20,17 @@ class Body:
 class _ClothView:
     """the attributes of engine.model_fold_offset.Cloth that drivers touch"""
 
-    def __init__(self, scene, cid, N, M, dx, offset, rho):
+    def __init__(self, scene, cid, N, M, dx, offset, rho, Kl=1000.0, Ka=1000.0, Kb=100.0, k_angle=3.14):
         self._s, self._cid = scene, cid
         self.N, self.M, self.dx, self.offset = N, M, dx, offset
         self.NV, self.NF = (N + 1) * (M + 1), 2 * N * M
         self.mass = rho * dx * dx
-        self._p = dict(Kl=1000.0, Ka=1000.0, Kb=100.0, k_angle=3.14)
-        self.Kl = Scalar(1000.0, lambda v: self._set("Kl", v))
-        self.Ka = Scalar(1000.0, lambda v: self._set("Ka", v))
-        self.Kb = Scalar(100.0, lambda v: self._set("Kb", v))
-        self.k_angle = Scalar(3.14, lambda v: self._set("k_angle", v))
+        # the Scalars read back exactly what the engine simulates with
+        self._p = dict(Kl=Kl, Ka=Ka, Kb=Kb, k_angle=k_angle)
+        self.Kl = Scalar(Kl, lambda v: self._set("Kl", v))
+        self.Ka = Scalar(Ka, lambda v: self._set("Ka", v))
+        self.Kb = Scalar(Kb, lambda v: self._set("Kb", v))
+        self.k_angle = Scalar(k_angle, lambda v: self._set("k_angle", v))
 
     def _set(self, k, v):
         self._p[k] = v

@@ -75,8 +75,7 @@ class Scene:
                                       grid_n=int(g["grid_n"]) if "grid_n" in g else 132, device=device)
         rho = float(g["cloth_mass"]) / (dx * dx)
         cid = e.add_cloth(N, M, 0, dx, rho, Kb=float(g["Kb"]), k_angle=float(g["k_angle"]))
-        self.cloths = [_ClothView(self, cid, N, M, dx, 0, rho)]
-        self.cloths[0]._p.update(Kb=float(g["Kb"]), k_angle=float(g["k_angle"]))
+        self.cloths = [_ClothView(self, cid, N, M, dx, 0, rho, Kb=float(g["Kb"]), k_angle=float(g["k_angle"]))]
         self.cloths[0].body_idx = 0
         pos0 = np.asarray(g["pos0"], np.float64)
         to, tn = int(g["table_offset"]), int(g["table_nverts"])
