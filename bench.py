@@ -1,10 +1,10 @@
 #!/usr/bin/env python
 """bench.py -- BASELINE.json metric: element-updates/sec per implicit fwd+bwd step; HBM GB/s vs peak.
 
-Workload (both arms, every N): the DROP of a square sheet on a frozen table (thinshelllab_b200.synthetic.DROP: released 0.6 mm above
-the table, outside the 0.4 mm contact gap; Scene_bouncing physics, dt 5 ms).  One "step" = one implicit forward time step (contact
+Workload (both arms, every N): the LANDING of a square sheet on a frozen table (thinshelllab_b200.synthetic.LANDING: released 0.3 mm above
+the table, inside the 0.4 mm contact gap; Scene_bouncing physics, dt 5 ms).  One "step" = one implicit forward time step (contact
 query, Newton with multigrid-preconditioned PCG, line search) plus one adjoint step for it (contact re-detection, un-projected fp64
-Hessian, adjoint solve, dL/dKb).  The timed window is FIXED: steps 0 .. K-1 of the drop from the initial state (warm-up steps run
+Hessian, adjoint solve, dL/dKb).  The timed window is FIXED: steps 0 .. K-1 of the landing from the initial state (warm-up steps run
 the same steps first, then the state is restored), so the number does not depend on where a landing is cut; Newton / PCG totals and
 ms per Newton iteration / per PCG iteration are first-class fields of the line.
 
@@ -15,7 +15,7 @@ point (tsl_step_forward_host) + host-side loss seed / gradient read-back, copies
 
 N > 1 (torchrun): N replicas of the same sheet (same seed), weak scaling, no data-path collective (DESIGN.md section 6 says why the
 strip partition of one sheet is opt-in).  --impl reference: the CPU oracle (restatement of the reference, fp64, SuperLU) on the host
-cores, same config object, each step a bounded sample (a sub-sheet of the same drop, see cpu_baseline.sample).
+cores, same config object, each step a bounded sample (a sub-sheet of the same landing, see cpu_baseline.sample).
 """
 import argparse
 import json
@@ -54,8 +54,8 @@ def workload_config(N):
     """the `config` object of BOTH arms (the driver compares them)"""
     n_tris = 2 * N * N
     tag = {158: "BASELINE configs[1] / [2]", 316: "BASELINE configs[3] sheet size", 707: "the 1 M-triangle sheet of BASELINE configs[4] / north_star"}.get(N, "custom size")
-    return {"workload": f"sheet {N}x{N} ({n_tris} tris, dx 2 mm) dropped 0.6 mm onto a frozen table, Scene_bouncing physics, dt 5 ms; "
-                        f"window = steps 0..K-1 of the drop, forward + adjoint (dL/dKb) per step; {tag}",
+    return {"workload": f"sheet {N}x{N} ({n_tris} tris, dx 2 mm) released 0.3 mm above a frozen table (landing), Scene_bouncing physics, dt 5 ms; "
+                        f"window = steps 0..K-1 of the landing, forward + adjoint (dL/dKb) per step; {tag}",
             "sheet_n": N, "n_tris": n_tris, "window": "steps 0..K-1 from the initial state (state restored after warm-up)"}
 
 
@@ -92,13 +92,13 @@ class ClockSampler(threading.Thread):
 
 # ------------------------------------------------------------------------------------------------ CPU arm (oracle)
 def oracle_window(sample_n, steps, budget_s, threads=None):
-    """steps 0..steps-1 of the drop on a sample_n x sample_n sheet with the CPU oracle, forward + adjoint per step, stopping early when
+    """steps 0..steps-1 of the landing on a sample_n x sample_n sheet with the CPU oracle, forward + adjoint per step, stopping early when
     `budget_s` seconds of wall clock are spent.  Returns (tris, [seconds per completed step], threads, [newton iterations per step])."""
     from oracle import tsl_oracle as orc
-    from thinshelllab_b200.synthetic import DROP, sheet_spec
+    from thinshelllab_b200.synthetic import LANDING, sheet_spec
     if threads:
         orc.lib().orc_set_num_threads(int(threads))
-    sp = sheet_spec(sample_n, **DROP)
+    sp = sheet_spec(sample_n, **LANDING)
     o = orc.OracleScene(sample_n, sample_n, sp["dx"], sp["dt"], sp["table_pos"], sp["table_faces"], sp["table_mass"], k_contact=sp["k_contact"],
                         mu=sp["mu"], max_n_constraints=sp["max_n_constraints"], grid_n=sp["grid_n"])
     o.pos[:o.NVc] = sp["cloth_pos"]; o.prev_pos[:] = o.pos
@@ -121,7 +121,7 @@ def oracle_window(sample_n, steps, budget_s, threads=None):
 
 
 def _cpu_sample_text(n, tris, times, newton, kind="window"):
-    return (f"{n}x{n} sub-sheet ({tris} tris) of the same drop, steps 0..{len(times) - 1} forward + adjoint "
+    return (f"{n}x{n} sub-sheet ({tris} tris) of the same landing, steps 0..{len(times) - 1} forward + adjoint "
             f"({int(np.sum(newton))} Newton iterations), CPU oracle (fp64 restatement of the reference, SuperLU direct solves, OpenMP assembly)")
 
 
@@ -176,16 +176,16 @@ def secondary_50k(args, dev):
     """BASELINE.json configs[1] / configs[2] (50 k-triangle sheet, forward only and forward + adjoint), same drop window, one GPU"""
     import torch
     from thinshelllab_b200.engine.analytic_grad_system import Grad
-    from thinshelllab_b200.synthetic import DROP, sheet_scene
+    from thinshelllab_b200.synthetic import LANDING, sheet_scene
     N, K = 158, 10
-    s = sheet_scene(N, device=dev, **DROP)
+    s = sheet_scene(N, device=dev, **LANDING)
     e, NVc, g = s.engine, s.cloths[0].NV, Grad(s, 2, 0)
     snap = (e.pos.clone(), e.vel.clone(), e.cloth_ref_angle[0].clone())
     _fixed_window(s, g, e, NVc, 3, args.adjoint_tol, snap)              # warm-up
     out = {}
     ms, stats = _fixed_window(s, g, e, NVc, K, args.adjoint_tol, snap)
     st = np.array(stats, dtype=np.float64)
-    out["configs[2] forward + adjoint"] = {"sheet": "158x158 (49928 tris)", "window": f"steps 0..{K - 1} of the drop", "ms_per_step": ms / K,
+    out["configs[2] forward + adjoint"] = {"sheet": "158x158 (49928 tris)", "window": f"steps 0..{K - 1} of the landing", "ms_per_step": ms / K,
                                            "tri_steps_per_s": 2 * N * N * K / (ms * 1e-3), "newton_iters": int(st[:, 0].sum()),
                                            "pcg_iters": int(st[:, 1].sum()), "adjoint_iters": int(st[:, 4].sum())}
     # forward only
@@ -199,7 +199,7 @@ def secondary_50k(args, dev):
     ev1.record()
     torch.cuda.synchronize()
     ms = ev0.elapsed_time(ev1)
-    out["configs[1] forward only"] = {"sheet": "158x158 (49928 tris)", "window": f"steps 0..{K - 1} of the drop", "ms_per_step": ms / K,
+    out["configs[1] forward only"] = {"sheet": "158x158 (49928 tris)", "window": f"steps 0..{K - 1} of the landing", "ms_per_step": ms / K,
                                       "tri_steps_per_s": 2 * N * N * K / (ms * 1e-3), "newton_iters": int(nw)}
     del s, g
     torch.cuda.empty_cache()
@@ -271,14 +271,14 @@ def run_ours(args, rank, world):
     import torch
     import torch.distributed as dist
     from thinshelllab_b200.engine.analytic_grad_system import Grad
-    from thinshelllab_b200.synthetic import DROP, sheet_scene
+    from thinshelllab_b200.synthetic import LANDING, sheet_scene
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
     dev = f"cuda:{local}"
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     N = args.sheet_n
-    s = sheet_scene(N, device=dev, **DROP)                    # the same sheet (seed 0) on every rank
+    s = sheet_scene(N, device=dev, **LANDING)                    # the same sheet (seed 0) on every rank
     e = s.engine
     if args.newton_mode >= 0:
         from thinshelllab_b200 import _lib as _l

@@ -227,8 +227,9 @@ typedef struct tsl_sizes {
 int tsl_get_sizes(tsl_ctx *ctx, tsl_sizes *out);
 /* benchmark hooks: run `iters` PCG iterations (no convergence test) on the last fp32 Hessian, and time
  * one kernel class with CUDA events on the context's stream; ms_out = average per launch.
- * what: 0 = PCG iteration (SpMV + vector kernels + preconditioner), 1 = SpMV only, 2 = energy, 3 = residual, 4 = Hessian,
- * 5 = preconditioner application (one V-cycle), 6 = multigrid setup (Galerkin products + eigenvalue estimates) */
+ * what: 0 = PCG iteration (SpMV + vector kernels + preconditioner), 1 = SpMV only, 2 = energy, 3 = residual, 4 = Hessian (BOTH
+ * forward Newton matrices, exact + clamped, as one Newton iteration assembles them), 5 = preconditioner application (one V-cycle),
+ * 6 = multigrid setup (Galerkin products + eigenvalue estimates), 7 = one forward Newton matrix through the element-scatter kernels */
 int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out);
 /* solver options (the reference has none: its solve is a direct factorisation, code/engine/sparse_solver.py:85-105).
  * TSL_OPT_PRECOND: 0 = block-Jacobi, 1 = geometric multigrid V-cycle over the cloth grid (default);
@@ -243,9 +244,12 @@ int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out);
  *       rollout like the others; on buckling steps it may settle in another local minimum than mode 0);
  * TSL_OPT_GRAPHS: 1 = replay the solver iterations as captured CUDA graphs (default), 0 = eager launches.
  * TSL_OPT_ADJOINT_SOLVER: 0 = automatic (dense LU when 3 * solved vertices <= TSL_OPT_DIRECT_MAX_DOF, default 12288, else FGMRES),
- *   1 = dense LU, 2 = FGMRES(TSL_OPT_GMRES_M, default 50), 3 = BiCGStab (the round-1 solver, kept for comparison). */
+ *   1 = dense LU, 2 = FGMRES(TSL_OPT_GMRES_M, default 50), 3 = BiCGStab (the round-1 solver, kept for comparison).
+ * TSL_OPT_FAST_ASSEMBLY: 1 (default for single-cloth scenes) = the cloth rows of the forward Newton matrices come from the
+ *   owner-computes grid kernel (no atomics, deterministic, exact + clamped matrix in one pass); 0 = element scatter with atomics;
+ *   2 = also the fp64 residual and energy by tiles (deterministic; slower than the element kernels, which are fp64-math bound). */
 enum tsl_option { TSL_OPT_PRECOND = 0, TSL_OPT_MG_DEGREE = 1, TSL_OPT_MG_COARSE_DEGREE = 2, TSL_OPT_MG_RATIO = 3, TSL_OPT_MG_SAFETY = 4, TSL_OPT_GRAPHS = 5, TSL_OPT_NEWTON_MODE = 6,
-                  TSL_OPT_ADJOINT_SOLVER = 7, TSL_OPT_DIRECT_MAX_DOF = 8, TSL_OPT_GMRES_M = 9 };
+                  TSL_OPT_ADJOINT_SOLVER = 7, TSL_OPT_DIRECT_MAX_DOF = 8, TSL_OPT_GMRES_M = 9, TSL_OPT_FAST_ASSEMBLY = 10 };
 int tsl_set_option(tsl_ctx *ctx, int key, double value);
 /* multigrid level read-back for tests: dims_host[3] = n0, n1, number of levels; lmax_host[1]; val_host [25][9][n0*n1] f32
  * (5x5 stencil of 3x3 blocks, slot-major; level 0 returns the stencil copy of the cloth block).  Any pointer may be NULL. */

@@ -2,10 +2,10 @@
 """Golden fixtures at the BASELINE.json sizes from the tier-2 CPU oracle (oracle/tsl_oracle.py: the C restatement of the reference,
 itself pinned to the tier-1 goldens by tests/test_oracle_golden.py).  TEST INFRASTRUCTURE ONLY.
 
-    python oracle/gen_sheet_goldens.py 158        # configs[1] / [2]: T = 5 rollout of the drop + 4 adjoint steps   (~15-40 min here)
+    python oracle/gen_sheet_goldens.py 158        # configs[1] / [2]: T = 5 rollout of the landing + 4 adjoint steps   (~15-40 min here)
 
-Writes tests/golden/sheet<N>_drop.npz: per frame the cloth positions, constraint count and a hash of the sorted constraint index
-set; the adjoint sweep's pos_grad[0], grad_kb and |z| per step.  The scenario is bench.py's (thinshelllab_b200.synthetic.DROP)."""
+Writes tests/golden/sheet<N>_landing.npz: per frame the cloth positions, constraint count and a hash of the sorted constraint index
+set; the adjoint sweep's pos_grad[0], grad_kb and |z| per step.  The scenario is bench.py's (thinshelllab_b200.synthetic.LANDING)."""
 import hashlib
 import os
 import sys
@@ -16,7 +16,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from oracle import tsl_oracle as orc  # noqa: E402
-from thinshelllab_b200.synthetic import DROP, sheet_spec  # noqa: E402
+from thinshelllab_b200.synthetic import LANDING, sheet_spec  # noqa: E402
 
 
 def idx_hash(idx):
@@ -25,7 +25,7 @@ def idx_hash(idx):
 
 
 def main(N, T=5):
-    sp = sheet_spec(N, **DROP)
+    sp = sheet_spec(N, **LANDING)
     o = orc.OracleScene(N, N, sp["dx"], sp["dt"], sp["table_pos"], sp["table_faces"], sp["table_mass"], Kb=100.0, k_angle=3.14,
                         k_contact=sp["k_contact"], eps_contact=sp["eps_contact"], eps_v=sp["eps_v"], mu=sp["mu"],
                         max_n_constraints=sp["max_n_constraints"], grid_n=sp["grid_n"])
@@ -33,7 +33,7 @@ def main(N, T=5):
     o.pos[:NVc] = sp["cloth_pos"]; o.prev_pos[:] = o.pos
     g = orc.OracleGrad(o, T)
     g.copy_pos(0)
-    out = dict(N=N, T=T, dx=sp["dx"], dt=sp["dt"], z0=DROP["z0"], pos_f0=o.pos[:NVc].copy())
+    out = dict(N=N, T=T, dx=sp["dx"], dt=sp["dt"], z0=LANDING["z0"], pos_f0=o.pos[:NVc].copy())
     for f in range(1, T):
         t0 = time.time()
         log = []
@@ -59,7 +59,7 @@ def main(N, T=5):
         print(f"adjoint {j}: |z| {out[f'z_norm_b{j}']:.6e} grad_kb {g.grad_kb:.12e} ({time.time() - t0:.0f} s)", flush=True)
     out["pos_grad0"] = g.pos_grad[0, :NVc].copy()
     out["grad_kb"] = g.grad_kb
-    path = os.path.join(ROOT, "tests", "golden", f"sheet{N}_drop.npz")
+    path = os.path.join(ROOT, "tests", "golden", f"sheet{N}_landing.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 

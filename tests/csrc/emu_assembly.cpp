@@ -102,3 +102,25 @@ extern "C" int emu_hessian_rows(int N, int M, int offset, int n_extra, const dou
     }
     return bad;
 }
+
+// cloth residual (rows [offset, offset + NV) of F, [3 nv]) and cloth energy through the fp64 tile kernels
+extern "C" double emu_residual_energy_rows(int N, int M, int offset, int nv, const double *pos, const double *prev_pos, const double *vel,
+                                           const double *ref_angle, double Kl, double Ka, double Kb, double dx, double dt, double mass,
+                                           const double *gravity, double *F)
+{
+    GridTables T;
+    if (!build_grid_tables(T)) return -1;
+    c_gt = T;
+    ClothGrid64 G;
+    G.N = N; G.M = M; G.NV = (N + 1) * (M + 1); G.offset = offset;
+    G.Kl = Kl; G.Ka = Ka; G.Kb = Kb; G.dx = dx; G.dt = dt; G.mass = mass;
+    for (int k = 0; k < 3; k++) G.g[k] = gravity[k];
+    dim3 grid((M + 1 + TSL_TJ - 1) / TSL_TJ, (N + 1 + TSL_TI - 1) / TSL_TI);
+    emu_launch(grid, dim3(128), k_residual_rows, G, pos, prev_pos, vel, (const double *)nullptr, ref_angle, F);
+    std::vector<double> partial(grid.x * grid.y + 1, 0.0);
+    unsigned int ticket = 0;
+    double E = 0;
+    emu_launch(grid, dim3(128), k_energy_rows, G, pos, prev_pos, vel, (const double *)nullptr, ref_angle, partial.data(), &ticket, &E);
+    (void)nv;
+    return ticket == 0 ? E : -1e300;
+}

@@ -51,3 +51,92 @@ def test_dense_lu_flags_singular_matrix():
     b = np.ones(n); x = np.zeros(n)
     Af = np.asfortranarray(A)
     assert L.emu_lu_solve(n, Af.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), 64) == 1
+
+
+@pytest.mark.parametrize("N,M,offset,seed", [(5, 4, 0, 0), (9, 37, 0, 1), (6, 66, 40, 2)])
+def test_owner_computes_hessian_rows_match_the_oracle_twin(N, M, offset, seed):
+    """k_hessian_rows (tsl_assembly_kernels.cuh: one thread per matrix block, tiles of 4 x 32 grid vertices, hinge gradients staged in
+    shared memory, contribution lists from the tables read off the reference's mesher) against the oracle's CPU twin of the forward
+    Newton matrices (exact and clamped), on grids that span several tiles, with a frozen DOF and a non-zero row offset"""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import tsl_oracle as orc
+    L = _build("emu_assembly")
+    rng = np.random.default_rng(seed)
+    dx, dt = 0.002, 5e-3
+    NV = (N + 1) * (M + 1)
+    tpos = np.array([[1., 1., -1.], [1.1, 1., -1.], [1., 1.1, -1.]])
+    o = orc.OracleScene(N, M, dx, dt, tpos, np.array([[0, 1, 2]], np.int32), np.ones(3))
+    i, j = np.meshgrid(np.arange(N + 1), np.arange(M + 1), indexing="ij")
+    p = np.stack([i * dx, j * dx, 0.0 * i], -1).reshape(-1, 3).astype(float)
+    p += rng.uniform(-0.3 * dx, 0.3 * dx, p.shape)                 # strong in-plane noise: compressed and stretched elements
+    p[:, 2] += 0.5 * dx * np.sin(i.ravel() * 0.9) * np.cos(j.ravel() * 0.7)
+    o.pos[:NV] = p; o.prev_pos[:] = o.pos
+    o.frozen[3 * 5 + 1] = 1
+    o.nc = 0
+    o._build_pattern()
+    ref = {}
+    for name, pf in (("e", 0), ("c", 3)):
+        o.hessian_mode = "psd"; orc.lib().orc_set_psd_flags(pf)
+        o.compute_residual_and_hessian(spd=True)
+        ref[name] = o.matrix().toarray()[:3 * NV, :3 * NV]
+    orc.lib().orc_set_psd_flags(3)
+    nv = offset + NV + 3
+    pos = np.zeros((nv, 3)); pos[offset:offset + NV] = p; pos[:offset] = 7.0
+    frozen = np.zeros(3 * nv, np.int32); frozen[3 * offset:3 * (offset + NV)] = o.frozen[:3 * NV]
+    oe = np.zeros((3 * nv, 3 * nv)); oc = np.zeros((3 * nv, 3 * nv))
+    L.emu_hessian_rows.argtypes = [C.c_int] * 4 + [C.c_void_p, C.c_void_p] + [C.c_double] * 5 + [C.c_void_p, C.c_void_p]
+    bad = L.emu_hessian_rows(N, M, offset, 3, pos.ctypes.data, frozen.ctypes.data, 1000.0, 1000.0, 100.0, dx, o.cloth_mass / dt ** 2,
+                             oe.ctypes.data, oc.ctypes.data)
+    assert bad == 0                                                   # padding slots untouched
+    a, b = 3 * offset, 3 * (offset + NV)
+    for name, out in (("e", oe), ("c", oc)):
+        assert np.abs(out[a:b, a:b] - ref[name]).max() <= 2e-6 * np.abs(ref[name]).max(), name
+        out[a:b, a:b] = 0
+        assert not out.any()                                          # nothing written outside the cloth rows
+
+
+@pytest.mark.parametrize("N,M,offset,seed", [(5, 4, 0, 0), (9, 37, 0, 1), (6, 66, 40, 2)])
+def test_owner_computes_residual_and_energy_match_the_oracle(N, M, offset, seed):
+    """k_residual_rows / k_energy_rows (fp64 tile kernels) against the oracle's Cloth.compute_residual / compute_energy restatement:
+    wavy sheets with non-zero rest angles, velocities and a previous position"""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import tsl_oracle as orc
+    L = _build("emu_assembly")
+    rng = np.random.default_rng(seed)
+    dx, dt = 0.002, 5e-3
+    NV, NF = (N + 1) * (M + 1), 2 * N * M
+    tpos = np.array([[1., 1., -1.], [1.1, 1., -1.], [1., 1.1, -1.]])
+    o = orc.OracleScene(N, M, dx, dt, tpos, np.array([[0, 1, 2]], np.int32), np.ones(3))
+    i, j = np.meshgrid(np.arange(N + 1), np.arange(M + 1), indexing="ij")
+    p = np.stack([i * dx, j * dx, 0.0 * i], -1).reshape(-1, 3).astype(float)
+    p += rng.uniform(-0.2 * dx, 0.2 * dx, p.shape)
+    p[:, 2] += 0.7 * dx * np.sin(i.ravel() * 0.9) * np.cos(j.ravel() * 0.7)       # both signs of the dihedral angles
+    o.pos[:NV] = p
+    o.prev_pos[:NV] = p + rng.uniform(-1e-5, 1e-5, p.shape)
+    o.vel[:NV] = rng.uniform(-1e-2, 1e-2, p.shape)
+    o.ref_angle[:] = rng.uniform(-0.3, 0.3, (NF, 3))
+    o.nc = 0
+    o._bind()
+    Lo = orc.lib()
+    Lo.orc_cloth_normals(o.cloth); Lo.orc_cloth_prepare_bending(o.cloth)
+    Fb = np.zeros((NV, 3))
+    Lo.orc_cloth_residual(o.cloth, orc._d(Fb), 15)
+    E_ref = Lo.orc_cloth_energy(o.cloth, None)
+    nv = offset + NV + 3
+    def emb(a, fill=0.0):
+        out = np.full((nv, 3), fill); out[offset:offset + NV] = a[:NV]; return out
+    pos, prev, vel = emb(o.pos, 7.0), emb(o.prev_pos, 7.0), emb(o.vel)
+    F = np.full(3 * nv, 123.0)
+    L.emu_residual_energy_rows.restype = C.c_double
+    L.emu_residual_energy_rows.argtypes = [C.c_int] * 4 + [C.c_void_p] * 4 + [C.c_double] * 6 + [C.c_void_p, C.c_void_p]
+    grav = np.array([0.0, 0.0, -9.8])
+    ra = np.ascontiguousarray(o.ref_angle)
+    E = L.emu_residual_energy_rows(N, M, offset, nv, pos.ctypes.data, prev.ctypes.data, vel.ctypes.data, ra.ctypes.data, 1000.0, 1000.0, 100.0,
+                                   dx, dt, o.cloth_mass, grav.ctypes.data, F.ctypes.data)
+    assert abs(E - E_ref) <= 1e-12 * abs(E_ref), (E, E_ref)
+    Fc = F.reshape(-1, 3)[offset:offset + NV]
+    assert np.abs(Fc - Fb).max() <= 1e-11 * np.abs(Fb).max()
+    F.reshape(-1, 3)[offset:offset + NV] = 123.0
+    assert np.all(F == 123.0)                                         # only the cloth rows are written

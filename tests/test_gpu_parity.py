@@ -370,3 +370,35 @@ def test_sheet_50k_first_iteration_and_properties():
     m = s2.cloths[0].mass
     net = F.sum(0) - np.array([0, 0, 9.8 * m * s2.cloths[0].NV])     # remove -m g
     assert np.abs(net).max() < 1e-9 * np.abs(F).sum()
+
+
+def test_owner_computes_assembly_matches_scatter_and_is_deterministic():
+    """the forward Newton matrices from the owner-computes grid kernel (tsl_assembly.cu: no atomics, both matrices in one pass) against
+    the element-scatter kernels on a 100 x 100 sheet in contact with the table; two assemblies are bit-identical"""
+    s = sheet_scene(100)
+    e = s.engine
+    for _ in range(2):
+        s.time_step()                                # a deformed state with contacts
+    assert e.contact_detect() > 1000
+    mats = {}
+    for fast in (1, 0):
+        e.set_option(_lib.OPT_FAST_ASSEMBLY, fast)
+        for name, fl in (("e", 0), ("c", _lib.ASM_SPD)):
+            e.assemble(_lib.ASM_HESSIAN | _lib.ASM_NEWTON | fl)
+            mats[(fast, name)] = e.matrix()
+    for name in ("e", "c"):
+        D = (mats[(1, name)] - mats[(0, name)]).tocoo()
+        assert np.abs(D.data).max() <= 2e-6 * np.abs(mats[(0, name)].data).max(), name
+    e.set_option(_lib.OPT_FAST_ASSEMBLY, 1)
+    e.assemble(_lib.ASM_HESSIAN | _lib.ASM_NEWTON)
+    again = e.matrix()
+    assert np.array_equal(again.data, mats[(1, "e")].data) and np.array_equal(again.indices, mats[(1, "e")].indices)
+    # level 2: the fp64 residual and energy by tiles (deterministic) against the element kernels
+    e.assemble(_lib.ASM_RESIDUAL)
+    F0, E0 = e.residual(), e.energy()
+    e.set_option(_lib.OPT_FAST_ASSEMBLY, 2)
+    e.assemble(_lib.ASM_RESIDUAL)
+    F2, E2 = e.residual(), e.energy()
+    assert _rel(F2, F0) < 1e-11 and abs(E2 - E0) <= 1e-12 * abs(E0)
+    e.assemble(_lib.ASM_RESIDUAL)
+    assert np.array_equal(e.residual(), F2) and e.energy() == E2

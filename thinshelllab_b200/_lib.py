@@ -89,7 +89,7 @@ SIGNATURES = {
 }
 
 OPT_PRECOND, OPT_MG_DEGREE, OPT_MG_COARSE_DEGREE, OPT_MG_RATIO, OPT_MG_SAFETY, OPT_GRAPHS, OPT_NEWTON_MODE = 0, 1, 2, 3, 4, 5, 6
-OPT_ADJOINT_SOLVER, OPT_DIRECT_MAX_DOF, OPT_GMRES_M = 7, 8, 9
+OPT_ADJOINT_SOLVER, OPT_DIRECT_MAX_DOF, OPT_GMRES_M, OPT_FAST_ASSEMBLY = 7, 8, 9, 10
 ADJ_AUTO, ADJ_DIRECT, ADJ_FGMRES, ADJ_BICGSTAB = 0, 1, 2, 3
 ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_UNSUPPORTED, ERR_NUMERIC = -1, -2, -3, -4, -5
 ASM_RESIDUAL, ASM_HESSIAN, ASM_SPD, ASM_SYM, ASM_F64, ASM_NEWTON = 1, 2, 4, 8, 16, 32

@@ -77,6 +77,7 @@ int tsl_destroy(tsl_ctx *ctx)
     cudaStreamSynchronize(ctx->stream);
     tsl::dist_destroy(ctx);
     tsl::dense_free(ctx);
+    cudaFree(ctx->egrid_partial); cudaFree(ctx->egrid_ticket);
     cudaFree(ctx->gm_V); cudaFree(ctx->gm_Z); cudaFree(ctx->gm_h); if (ctx->gm_h_host) cudaFreeHost(ctx->gm_h_host);
     tsl::graphs_invalidate(ctx);
     tsl::mg_free(ctx);
@@ -475,6 +476,7 @@ int tsl_finalize(tsl_ctx *ctx)
     TRY(contact_alloc(ctx));
     TRY(linalg_alloc(ctx));
     TRY(mg_alloc(ctx));
+    TRY(assembly_init(ctx));
     if (const char *e = getenv("TSL_PRECOND")) ctx->precond = atoi(e);
     if (const char *e = getenv("TSL_NEWTON_MODE")) ctx->newton_mode = atoi(e);
     if (const char *e = getenv("TSL_PROBE")) ctx->probe = atoi(e);
@@ -552,9 +554,16 @@ int tsl_assemble(tsl_ctx *ctx, int flags)
     if (flags & TSL_ASM_HESSIAN) {
         bool f64 = (flags & TSL_ASM_F64) != 0;
         if (f64) TRY(ensure_f64(ctx));
-        launch_hessian(ctx, ctx->pos, f64, (flags & TSL_ASM_SPD) ? 1 : 0, (flags & TSL_ASM_SYM) ? 1 : 0, (flags & TSL_ASM_NEWTON) ? 1 : 0);
-        // the preconditioner hierarchy always comes from the clamped (positive definite) Newton matrix at the same state
-        launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);
+        if (!f64 && (flags & TSL_ASM_NEWTON)) {
+            // both forward Newton matrices leave one pass: A_e -> val32, A_c -> val32c; TSL_ASM_SPD asks for the clamped one in val32
+            launch_hessian_newton_pair(ctx, ctx->pos);
+            if (flags & TSL_ASM_SPD)
+                CK(cudaMemcpyAsync(ctx->A.val32, ctx->A.val32c, sizeof(float) * 9 * (size_t)ctx->A.nnzb_pad, cudaMemcpyDeviceToDevice, ctx->stream));
+        } else {
+            launch_hessian(ctx, ctx->pos, f64, (flags & TSL_ASM_SPD) ? 1 : 0, (flags & TSL_ASM_SYM) ? 1 : 0, (flags & TSL_ASM_NEWTON) ? 1 : 0);
+            // the preconditioner hierarchy always comes from the clamped (positive definite) Newton matrix at the same state
+            launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);
+        }
         TRY(mg_setup_replay(ctx));
         if (f64) launch_block_jacobi64(ctx);
         ctx->last_f64 = f64;
@@ -570,12 +579,17 @@ int tsl_assemble(tsl_ctx *ctx, int flags)
 //   * above: FGMRES(m) with the multigrid V-cycle as flexible right preconditioner (monotone residual, true-residual restarts);
 //     if that stalls, the same with the fp64 block-Jacobi preconditioner (flags bit3).
 // An unconverged result is an error (TSL_ERR_NUMERIC), never a silently wrong gradient.
+static int adjoint_mode(tsl_ctx *ctx)
+{
+    int mode = ctx->adjoint_solver;
+    if (mode == 0) mode = (3LL * ctx->n_solve <= ctx->direct_max_dof) ? 1 : 2;
+    return mode;
+}
 static int solve_adjoint64(tsl_ctx *ctx, const double *rhs, double *x, double rel_tol, int max_iters, tsl_solve_stats *st)
 {
     tsl_solve_stats s0;
     memset(&s0, 0, sizeof(s0));
-    int mode = ctx->adjoint_solver;
-    if (mode == 0) mode = (3LL * ctx->n_solve <= ctx->direct_max_dof) ? 1 : 2;
+    const int mode = adjoint_mode(ctx);
     if (mode == 1) {
         TRY(solve_dense64(ctx, rhs, x, &s0));
     } else {
@@ -682,8 +696,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
         if (ctx->newton_mode == 0) {
             // ---- projected-Newton fallback with back-off (the path closest to the reference's own iteration)
             const bool try_exact = (skip == 0);
-            launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                     // A_c -> val32c
-            if (try_exact) launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);     // A_e -> val32
+            launch_hessian_newton_pair(ctx, ctx->pos);                               // A_e -> val32, A_c -> val32c
             // hierarchy: rebuilt every few iterations, or as soon as the Krylov count drifts away from what a fresh one gave
             if (!keep_hierarchy(age, last_pcg, fresh_pcg, st.delta)) {
                 TRY(mg_setup_replay(ctx));
@@ -717,8 +730,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
             // ---- blended operator A_theta = A_e + theta (A_c - A_e): the smallest theta in {0, 1/16, 1/8, ..., 1} for which PCG
             // meets no negative curvature (the clamped matrix over-stiffens every compressed element, the blend only as
             // much as definiteness needs)
-            launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                     // A_c -> val32c
-            launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);                    // A_e -> val32
+            launch_hessian_newton_pair(ctx, ctx->pos);                               // A_e -> val32, A_c -> val32c
             if (!keep_hierarchy(age, last_pcg, fresh_pcg, st.delta)) {
                 TRY(mg_setup_replay(ctx));
                 age = 0;
@@ -755,10 +767,9 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
             if (age == 0) fresh_pcg = ss.iters;
             age++;
         } else {
-        launch_hessian(ctx, ctx->pos, false, 0, 0, 1, false);                    // A_e -> val32
+        launch_hessian_newton_pair(ctx, ctx->pos);                               // A_e -> val32, A_c -> val32c
         // hierarchy: rebuilt every few iterations, or as soon as the Krylov count drifts away from what a fresh one gave
         if (!keep_hierarchy(age, last_pcg, fresh_pcg, st.delta)) {
-            launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);                 // A_c -> val32c
             TRY(mg_setup_replay(ctx));
             age = 0;
         }
@@ -825,7 +836,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
             fallback = true;
             t1 = now_ms();
             if (age > 1) {                    // the stored A_c is stale as an OPERATOR: rebuild it (and the hierarchy) for this state
-                launch_hessian(ctx, ctx->x1, false, 1, 0, 1, true);
+                launch_hessian_newton_pair(ctx, ctx->x1);
                 TRY(mg_setup_replay(ctx));
                 age = 1;
             }
@@ -933,9 +944,11 @@ int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, c
     if (grad_kb_accum) launch_cloth_param_deri(ctx, c, ctx->pos, ctx->d_kb);
     // H = reference Hessian without projection, fp64
     launch_hessian(ctx, ctx->pos, true, 0, 0, 0);
-    // preconditioner: multigrid hierarchy of the clamped Newton matrix at x_t
-    launch_hessian(ctx, ctx->pos, false, 1, 0, 1, true);
-    TRY(mg_setup_replay(ctx));
+    // preconditioner of the iterative path: multigrid hierarchy of the clamped Newton matrix at x_t (the direct path needs none)
+    if (adjoint_mode(ctx) != 1) {
+        launch_hessian_newton_pair(ctx, ctx->pos);
+        TRY(mg_setup_replay(ctx));
+    }
     launch_block_jacobi64(ctx);
     ctx->last_f64 = true;
     TRY(check_device_flags(ctx));
@@ -1161,7 +1174,8 @@ int tsl_bench_kernel(tsl_ctx *ctx, int what, int iters, float *ms_out)
     for (int i = 0; i < iters; i++) {
         if (what == 2) launch_energy(ctx, ctx->pos, ctx->red_out);
         else if (what == 3) launch_residual(ctx, ctx->pos);
-        else if (what == 4) launch_hessian(ctx, ctx->pos, false, 0, 0, 1);
+        else if (what == 4) launch_hessian_newton_pair(ctx, ctx->pos);       // BOTH forward Newton matrices (A_e, A_c)
+        else if (what == 7) launch_hessian(ctx, ctx->pos, false, 0, 0, 1);   // one matrix through the scatter (atomics) kernels
         else { ctx->err = "tsl_bench_kernel: unknown kernel class"; return TSL_ERR_INVALID; }
     }
     CK(cudaEventRecord(e1, ctx->stream));
@@ -1186,6 +1200,10 @@ int tsl_set_option(tsl_ctx *ctx, int key, double value)
     case TSL_OPT_NEWTON_MODE: ctx->newton_mode = (int)value; break;
     case TSL_OPT_ADJOINT_SOLVER: REQUIRE(value >= 0 && value <= 3, "adjoint solver: 0 auto, 1 dense LU, 2 FGMRES, 3 BiCGStab"); ctx->adjoint_solver = (int)value; break;
     case TSL_OPT_DIRECT_MAX_DOF: REQUIRE(value >= 0 && value <= 46000, "direct_max_dof out of range"); ctx->direct_max_dof = (int)value; break;
+    case TSL_OPT_FAST_ASSEMBLY:
+        if (value != 0 && !ctx->finalized) { ctx->err = "TSL_OPT_FAST_ASSEMBLY: set after tsl_finalize"; return TSL_ERR_INVALID; }
+        if (value != 0) { TRY(assembly_init(ctx)); if (ctx->fast_assembly) ctx->fast_assembly = (int)value; } else ctx->fast_assembly = 0;
+        break;
     case TSL_OPT_GMRES_M: REQUIRE(value >= 2 && value <= 400, "FGMRES restart length out of range"); ctx->gmres_m = (int)value; break;
     default: ctx->err = "tsl_set_option: unknown key"; return TSL_ERR_INVALID;
     }

@@ -52,6 +52,24 @@ TSL_HD double hinge_theta_abs(d3 n1, d3 n2)
     return 2 * sqrt(fabs(1.0 - ct)) / sqrt(1 + ct);
 }
 
+// gradient of the hinge angle w.r.t. its 4 vertices (Cloth.compute_bending_grad, :379-402), written on
+// vertex identities: p0 opposite in face 1, (p1,p2) shared edge, p3 opposite in face 2.
+TSL_HD void hinge_grad(d3 p0, d3 p1, d3 p2, d3 p3, d3 n1, d3 n2, d3 &ga, d3 &gb, d3 &gc, d3 &gd)
+{
+    double A1 = norm(cross(p1 - p0, p2 - p0));      // 2 * area of face 1
+    double A2 = norm(cross(p1 - p3, p2 - p3));
+    double l12 = norm(p2 - p1);
+    double l02 = norm(p0 - p2), l01 = norm(p0 - p1), l32 = norm(p3 - p2), l31 = norm(p3 - p1);
+    double h1_p0 = A1 / l12, h1_p1 = A1 / l02, h1_p2 = A1 / l01;
+    double h2_p3 = A2 / l12, h2_p1 = A2 / l32, h2_p2 = A2 / l31;
+    double c1_p1 = dot(p0 - p1, p2 - p1) / (l01 * l12), c1_p2 = dot(p0 - p2, p1 - p2) / (l02 * l12);
+    double c2_p1 = dot(p3 - p1, p2 - p1) / (l31 * l12), c2_p2 = dot(p3 - p2, p1 - p2) / (l32 * l12);
+    ga = (-1.0 / h1_p0) * n1;
+    gd = (-1.0 / h2_p3) * n2;
+    gb = (c1_p2 / h1_p1) * n1 + (c2_p2 / h2_p1) * n2;
+    gc = (c1_p1 / h1_p2) * n1 + (c2_p1 / h2_p2) * n2;
+}
+
 // ---------------------------------------------------------------------------------------------
 // edge spring (model_fold_offset.py:260-266, 288-294, 476-499): 3x3 block of one edge, delta = x_a - x_b.
 // The off-diagonal of the "second derivative of l" carries the reference's + sign (Q15).

@@ -55,6 +55,9 @@ struct GridTables {
     // hinge on the edge (type, parity of its anchor): offsets of the hinge vertices pt0..pt3 (opposite in the owner face, shared
     // edge start / end, opposite in the neighbour face -- the order of k_hessian_hinge) from the edge anchor
     signed char hin_v[3][2][4][2];
+    // owner face of that hinge (the (face i, slot l) with counter_face[i][l] > i): quad offset from the edge anchor, triangle in the
+    // quad, local slot l -- ref_angle[i][l] and the side test of compute_angle (Q3) are indexed by them
+    signed char hin_owner[3][2][4];
     // gather lists of the block (v, v + (di, dj)), slot = (di + 2) * 5 + (dj + 2), for a vertex v of parity p
     unsigned char n_tri[2][25], n_hin[2][25];
     struct TriE { signed char qi, qj; unsigned char t, a, b; } tri[2][25][TSL_GT_MAX_TRI];          // quad anchor = v + (qi, qj); block (local a, local b)
@@ -108,6 +111,13 @@ inline bool build_grid_tables(GridTables &T)
             if (!grid_edge_key(h.pt[1], h.pt[2], M, &h.type, &h.anchor)) { ok = false; continue; }
             hinges.push_back(h);
             int ai = h.anchor / W, aj = h.anchor % W, par = (ai + aj) & 1;
+            {
+                int own[4] = { (i / 2) / M - ai, (i / 2) % M - aj, i & 1, l };
+                for (int q = 0; q < 4; q++) {
+                    if (!hin_set[h.type][par]) T.hin_owner[h.type][par][q] = (signed char)own[q];
+                    else ok = ok && T.hin_owner[h.type][par][q] == own[q];
+                }
+            }
             for (int q = 0; q < 4; q++) {
                 int di = h.pt[q] / W - ai, dj = h.pt[q] % W - aj;
                 if (!hin_set[h.type][par]) { T.hin_v[h.type][par][q][0] = (signed char)di; T.hin_v[h.type][par][q][1] = (signed char)dj; }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "../../include/tsl.h"
@@ -232,5 +233,10 @@ struct tsl_ctx {
     double *gm_V = nullptr, *gm_Z = nullptr;     // FGMRES bases [gmres_m + 1] / [gmres_m] x [3 n_rows_pad]
     double *gm_h = nullptr, *gm_h_host = nullptr;   // Gram-Schmidt coefficients (device / pinned)
     int device = 0;                              // CUDA device the context lives on (tsl_create)
+    // owner-computes assembly of the cloth rows (tsl_assembly.cu), single-cloth scenes: 0 off, 1 the forward Newton matrices (default),
+    // 2 also the fp64 residual and energy by tiles (deterministic, but slower than the element kernels: fp64 sqrt / div / acos bound)
+    int fast_assembly = 0;
+    std::vector<std::pair<long long, long long>> zero_ranges;   // value ranges [a, b) of the slices holding rows of other bodies
+    double *egrid_partial = nullptr; unsigned int *egrid_ticket = nullptr; int egrid_blocks = 0;   // per-tile partials of k_energy_rows (+1: result)
     tsl::DistCtx dist;
 };

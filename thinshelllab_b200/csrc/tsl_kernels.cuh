@@ -25,6 +25,15 @@ void launch_contact_backprop(tsl_ctx *ctx, const double *pos, const double *z, d
 void launch_clamp(tsl_ctx *ctx, double *a, int n, double lim);
 void launch_adjoint_tail(tsl_ctx *ctx, const double *z, const double *d_kb, double *pg_tm1, double *pg_tm2, double *grad_kb_accum);
 
+// forward Newton matrices A_e -> A.val32 and A_c -> A.val32c in one pass (owner-computes cloth rows + the other bodies' elements)
+void launch_hessian_newton_pair(tsl_ctx *ctx, const double *pos);
+
+// tsl_assembly.cu: owner-computes cloth rows on the structured grid
+int assembly_init(tsl_ctx *ctx);
+void launch_hessian_rows(tsl_ctx *ctx, const double *pos, float *val_e, float *val_c);
+void launch_residual_rows(tsl_ctx *ctx, const double *pos);
+void launch_energy_rows(tsl_ctx *ctx, const double *pos, double *out_dev);
+
 // tsl_contact.cu
 int contact_alloc(tsl_ctx *ctx);
 int contact_detect(tsl_ctx *ctx, const double *pos, const double *prev_pos);

@@ -69,24 +69,6 @@ __device__ __forceinline__ double signed_theta(const FaceV &f1, d3 n1, d3 n2, in
     }
     return th;
 }
-// gradient of the hinge angle w.r.t. its 4 vertices (Cloth.compute_bending_grad, :379-402), written on
-// vertex identities: p0 opposite in face 1, (p1,p2) shared edge, p3 opposite in face 2.
-__device__ __forceinline__ void hinge_grad(d3 p0, d3 p1, d3 p2, d3 p3, d3 n1, d3 n2, d3 &ga, d3 &gb, d3 &gc, d3 &gd)
-{
-    double A1 = norm(cross(p1 - p0, p2 - p0));      // 2 * area of face 1
-    double A2 = norm(cross(p1 - p3, p2 - p3));
-    double l12 = norm(p2 - p1);
-    double l02 = norm(p0 - p2), l01 = norm(p0 - p1), l32 = norm(p3 - p2), l31 = norm(p3 - p1);
-    double h1_p0 = A1 / l12, h1_p1 = A1 / l02, h1_p2 = A1 / l01;
-    double h2_p3 = A2 / l12, h2_p1 = A2 / l32, h2_p2 = A2 / l31;
-    double c1_p1 = dot(p0 - p1, p2 - p1) / (l01 * l12), c1_p2 = dot(p0 - p2, p1 - p2) / (l02 * l12);
-    double c2_p1 = dot(p3 - p1, p2 - p1) / (l31 * l12), c2_p2 = dot(p3 - p2, p1 - p2) / (l32 * l12);
-    ga = (-1.0 / h1_p0) * n1;
-    gd = (-1.0 / h2_p3) * n2;
-    gb = (c1_p2 / h1_p1) * n1 + (c2_p2 / h2_p1) * n2;
-    gc = (c1_p1 / h1_p2) * n1 + (c2_p1 / h2_p2) * n2;
-}
-
 // ------------------------------------------------------------------------------------------------ normals
 __global__ void k_face_normals(ClothDev c, const double *__restrict__ pos)
 {
@@ -104,7 +86,7 @@ __global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_v
                                                 const double *__restrict__ prev_pos, const double *__restrict__ vel,
                                                 const double *__restrict__ mass, d3 g, double dt,
                                                 ContactDev con, int nc, ContactParams cp, TetSet ts, const double *__restrict__ vgrav,
-                                                int own0, int own1, int nvc,
+                                                int own0, int own1, int nvc, int vskip0, int vskip1, const double *add_in,
                                                 double *partial, unsigned int *ticket, double *out)
 {
     // strip partition: a cloth vertex / triangle (by its first vertex) / constraint (by its query vertex) is counted by the rank
@@ -113,6 +95,7 @@ __global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_v
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     for (int i = tid; i < n_verts; i += nth) {
         if (i < nvc && (i < own0 || i >= own1)) continue;
+        if (i >= vskip0 && i < vskip1) continue;          // cloth vertices already counted by k_energy_rows
         d3 x = ld3(pos, i), xp = ld3(prev_pos, i), v = ld3(vel, i);
         double m = mass[i];
         d3 X = x - xp - dt * v;
@@ -165,6 +148,7 @@ __global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_v
         E += con.k[i] * fr_f0(cp, sqrt(u0 * u0 + u1 * u1));
     }
     E = block_sum(E);
+    if (add_in && blockIdx.x == 0 && threadIdx.x == 0) E += *add_in;     // the cloth part (k_energy_rows), added once
     grid_sum_finish(E, partial, ticket, out);
 }
 
@@ -177,11 +161,12 @@ __device__ __forceinline__ void red_add3(double *F, int v, d3 g)
 // model_elastic_offset.py:212-214 with zero internal force for the frozen box).  Overwrites F.
 __global__ void k_residual_vertex(int n_verts, const double *__restrict__ pos, const double *__restrict__ prev_pos,
                                   const double *__restrict__ vel, const double *__restrict__ mass, d3 g, const double *__restrict__ vgrav,
-                                  double dt, double *F)
+                                  double dt, double *F, int vskip0, int vskip1)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 3 * n_verts) return;
     int v = i / 3, k = i - 3 * v;
+    if (v >= vskip0 && v < vskip1) return;                 // cloth rows are written by k_residual_rows
     double m = mass[v];
     F[i] = m * (pos[i] - prev_pos[i] - vel[i] * dt) / (dt * dt) - m * (vgrav ? vgrav[i] : comp(g, k));
 }
@@ -577,10 +562,10 @@ __global__ void __launch_bounds__(128) k_hessian_hinge(ClothDev c, const double 
 
 // mass diagonal m/dt^2 on every DOF, frozen or not (Q6; model_fold_offset.py:468-470, model_elastic_offset.py:97-99)
 template <typename T>
-__global__ void k_hessian_mass(int n_verts, const double *__restrict__ mass, double dt, const int *__restrict__ diag_pb, T *val)
+__global__ void k_hessian_mass(int n_verts, const double *__restrict__ mass, double dt, const int *__restrict__ diag_pb, T *val, int skip0, int skip1)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= n_verts) return;
+    if (v >= n_verts || (v >= skip0 && v < skip1)) return;      // [skip0, skip1): rows whose mass the cloth-row kernel already wrote
     long long base = sell_addr(diag_pb[v], v & 31, 0);
     T m = (T)(mass[v] / (dt * dt));
     atomicAdd(val + base + 0 * 32, m); atomicAdd(val + base + 4 * 32, m); atomicAdd(val + base + 8 * 32, m);
@@ -956,9 +941,20 @@ void launch_energy(tsl_ctx *ctx, const double *pos, double *out_dev)
     ClothDev c = ctx->cloths.empty() ? ClothDev() : ctx->cloths[0];
     ContactParams cp = { ctx->cfg.k_contact, ctx->cfg.eps_contact, ctx->cfg.eps_v, ctx->cfg.dt };
     d3 g = mk(ctx->cfg.gravity[0], ctx->cfg.gravity[1], ctx->cfg.gravity[2]);
+    const bool fast = ctx->fast_assembly >= 2 && !ctx->dist.on;
+    if (fast) {
+        // cloth part by tiles (tsl_assembly.cu); the rest (other bodies' vertices, cells, contacts) below adds it in
+        double *cloth_E = ctx->egrid_partial + ctx->egrid_blocks;
+        launch_energy_rows(ctx, pos, cloth_E);
+        k_energy<<<ctx->red_blocks, 256, 0, ctx->stream>>>(c, 0, ctx->cfg.n_verts, pos, ctx->prev_pos, ctx->vel, ctx->mass, g, ctx->cfg.dt, ctx->con, ctx->nc, cp,
+                                                            tet_set(ctx), ctx->vgrav, 0, 0x7fffffff, 0, c.offset, c.offset + c.NV, cloth_E,
+                                                            ctx->red_partial, ctx->red_ticket, out_dev);
+        ctx->launches++;
+        return;
+    }
     k_energy<<<ctx->red_blocks, 256, 0, ctx->stream>>>(c, (int)ctx->cloths.size(), ctx->cfg.n_verts, pos, ctx->prev_pos, ctx->vel,
                                                         ctx->mass, g, ctx->cfg.dt, ctx->con, ctx->nc, cp, tet_set(ctx), ctx->vgrav,
-                                                        ctx->dist.own0, ctx->dist.own1, ctx->dist.on ? ctx->dist.nvc : 0,
+                                                        ctx->dist.own0, ctx->dist.own1, ctx->dist.on ? ctx->dist.nvc : 0, 0, 0, nullptr,
                                                         ctx->red_partial, ctx->red_ticket, out_dev);
     ctx->launches++;
 }
@@ -967,11 +963,21 @@ void launch_residual(tsl_ctx *ctx, const double *pos)
     int n = ctx->cfg.n_verts;
     d3 g = mk(ctx->cfg.gravity[0], ctx->cfg.gravity[1], ctx->cfg.gravity[2]);
     ContactParams cp = { ctx->cfg.k_contact, ctx->cfg.eps_contact, ctx->cfg.eps_v, ctx->cfg.dt };
-    k_residual_vertex<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(n, pos, ctx->prev_pos, ctx->vel, ctx->mass, g, ctx->vgrav, ctx->cfg.dt, ctx->F);
-    ctx->launches++;
-    for (auto &c : ctx->cloths) {
-        k_residual_cloth<<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, ctx->F, 14, 1.0);
+    const bool fast = ctx->fast_assembly >= 2 && !ctx->dist.on;
+    if (fast) {
+        const ClothDev &c = ctx->cloths[0];
+        if (n > c.NV) {
+            k_residual_vertex<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(n, pos, ctx->prev_pos, ctx->vel, ctx->mass, g, ctx->vgrav, ctx->cfg.dt, ctx->F, c.offset, c.offset + c.NV);
+            ctx->launches++;
+        }
+        launch_residual_rows(ctx, pos);
+    } else {
+        k_residual_vertex<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(n, pos, ctx->prev_pos, ctx->vel, ctx->mass, g, ctx->vgrav, ctx->cfg.dt, ctx->F, 0, 0);
         ctx->launches++;
+        for (auto &c : ctx->cloths) {
+            k_residual_cloth<<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, ctx->F, 14, 1.0);
+            ctx->launches++;
+        }
     }
     for (auto &t : ctx->tets) {
         k_residual_tets<<<GRID(t.nc, 128), 128, 0, ctx->stream>>>(t, pos, ctx->F, 1.0);
@@ -1030,10 +1036,45 @@ static void launch_hessian_t(tsl_ctx *ctx, const double *pos, T *val, T *side, i
 {
     int n = ctx->cfg.n_verts;
     cudaMemsetAsync(val, 0, sizeof(T) * 9 * (size_t)ctx->A.nnzb_pad, ctx->stream);
-    k_hessian_mass<T><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, ctx->mass, ctx->cfg.dt, ctx->A.diag_pb, val);
+    k_hessian_mass<T><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, ctx->mass, ctx->cfg.dt, ctx->A.diag_pb, val, 0, 0);
     ctx->launches++;
     Sink<T> S = { val, nullptr, nullptr };
     launch_hessian_elements<T>(ctx, pos, S, side, spd, sym, newton_model);
+}
+// The two forward Newton matrices of one Newton iteration: exact -> A.val32, clamped -> A.val32c.
+// Single-cloth scenes: the cloth rows of both leave one owner-computes pass (tsl_assembly.cu); tetrahedral bodies and contacts
+// are added per matrix by the element kernels above.  Otherwise: two scatter assemblies.
+void launch_hessian_newton_pair(tsl_ctx *ctx, const double *pos)
+{
+    if (!ctx->fast_assembly) {
+        launch_hessian_t<float>(ctx, pos, ctx->A.val32c, ctx->cside32, 1, 0, 1);
+        launch_hessian_t<float>(ctx, pos, ctx->A.val32, ctx->cside32, 0, 0, 1);
+        return;
+    }
+    const int n = ctx->cfg.n_verts;
+    const ClothDev &c = ctx->cloths[0];
+    ContactParams cp = { ctx->cfg.k_contact, ctx->cfg.eps_contact, ctx->cfg.eps_v, ctx->cfg.dt };
+    launch_hessian_rows(ctx, pos, ctx->A.val32, ctx->A.val32c);
+    for (int pass = 0; pass < 2; pass++) {
+        float *val = pass == 0 ? ctx->A.val32c : ctx->A.val32;
+        const int spd = pass == 0 ? 1 : 0;
+        if (n > c.NV) {
+            k_hessian_mass<float><<<GRID(n, 256), 256, 0, ctx->stream>>>(n, ctx->mass, ctx->cfg.dt, ctx->A.diag_pb, val, c.offset, c.offset + c.NV);
+            ctx->launches++;
+        }
+        Sink<float> S = { val, nullptr, nullptr };
+        for (auto &t : ctx->tets) {
+            k_hessian_tets<float><<<GRID(t.nc, 64), 64, 0, ctx->stream>>>(t, pos, ctx->frozen, S, spd);
+            ctx->launches++;
+        }
+        if (ctx->nc > 0) {
+            if (ctx->general_contact)
+                k_hessian_contact_general<float><<<GRID(ctx->nc, 64), 64, 0, ctx->stream>>>(ctx->con, ctx->nc, cp, pos, ctx->frozen, ctx->A.diag_pb, S, ctx->cside32, 1, 1);
+            else
+                k_hessian_contact<float><<<GRID(ctx->nc, 128), 128, 0, ctx->stream>>>(ctx->con, ctx->nc, cp, pos, ctx->frozen, ctx->A.diag_pb, S, 1, ctx->error_flag);
+            ctx->launches++;
+        }
+    }
 }
 void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model, bool into_clamped)
 {
