@@ -215,7 +215,6 @@ def secondary_solids(args, dev):
     from thinshelllab_b200.engine.analytic_grad_single import Grad
     from thinshelllab_b200.synthetic import pad_sheet_scene
     from thinshelllab_b200.task_scene.Scene_folding import Scene
-    g = np.load(os.path.join(ROOT, "thinshelllab_b200", "data", "scene_folding_cloth0p1.npz"))
     T0 = 3
     traj0 = np.zeros((T0, 1, 6))
     for i in range(1, T0):                       # the press-and-tilt trajectory of the golden run (oracle/gen_goldens.py:gen_folding)
@@ -253,12 +252,13 @@ def secondary_solids(args, dev):
                    "pcg_iters": krylov, "adjoint_iters (0 = dense LU)": bi, "contacts_last_step": int(st.n_contacts), "converged_last_step": bool(st.converged)}
         return res
 
-    s = Scene(g, device=dev)
+    s = Scene(cloth_size=0.1, device=dev)
+    s.cloths[0].Kb[None] = 400.0; s.mu_cloth_elastic[None] = 5.0           # training/trajopt_folding.py:52-56
     out["configs[0] Scene_folding fwd + trajectory adjoint"] = dict(scene="cloth 15x3 (90 tris) + frozen table + tactile pad (1365 tets) on a gripper",
                                                                     **rollout(s, T0, traj0, 2))
     del s
     N, T = 316, 4
-    s = pad_sheet_scene(N, g, device=dev)
+    s = pad_sheet_scene(N, device=dev)
     traj = np.zeros((T, 1, 6)); traj[:, 0, 2] = -1.5e-4 * np.arange(T)
     out["configs[3] 200k-tri sheet + tactile pad, fwd + trajectory adjoint"] = dict(
         scene=f"sheet {N}x{N} ({2 * N * N} tris) resting on a frozen table, tactile pad (1365 tets) pressed 0.15 mm per step into it", **rollout(s, T, traj, 1))

@@ -77,6 +77,9 @@ int tsl_add_cloth(tsl_ctx *ctx, int N, int M, int v_offset, double dx, double rh
                   double Kl, double Ka, double Kb, double k_angle, double *ref_angle_dev);
 /* Cloth.Kl/Ka/Kb/k_angle[None] = ...  (scripts set sys.cloths[0].Kb[None], trajopt_bouncing.py:46) */
 int tsl_set_cloth_params(tsl_ctx *ctx, int cloth, double Kl, double Ka, double Kb, double k_angle);
+/* Cloth.update_ref_angle / init_ref_angle at the bound positions (code/engine/model_fold_offset.py:176-185, 788-797): plastic flow of
+ * the rest angles beyond k_angle.  time_step does this at the end of every step; scene construction calls it once on the folded strip. */
+int tsl_cloth_update_ref_angle(tsl_ctx *ctx, int cloth);
 /* topology read-back for tests / renderers: Cloth.f2v, counter_face, counter_point ([2NM][3] i32, host) */
 int tsl_get_cloth_topology(tsl_ctx *ctx, int cloth, int *f2v_host, int *counter_face_host, int *counter_point_host);
 

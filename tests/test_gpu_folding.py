@@ -277,3 +277,31 @@ def test_sheet_with_tactile_pad_rollout(golden, N):
         assert (flags & 3) == 0 and rr < 1e-7, (j, it, flags, rr)
     gg = grad._gripper_grad
     assert np.isfinite(gg).all() and np.abs(gg[1:, 0, 2]).max() > 0
+
+
+@pytest.mark.parametrize("tag", ["folding", "forming"])
+def test_scene_built_by_the_product_reproduces_the_reference_scene(golden_dir, tag):
+    """Scene(cloth_size=0.1) constructs itself (engine/scene_builder.py + the TetGen assets + tsl_cloth_update_ref_angle): initial state,
+    plastic rest angles of the folded strip and the first frame of the reference's own rollout"""
+    g = np.load(os.path.join(golden_dir, f"{tag}.npz"))
+    if tag == "forming":
+        from thinshelllab_b200.task_scene.Scene_forming import Scene as SceneCls
+    else:
+        SceneCls = Scene
+    s = SceneCls(cloth_size=0.1)
+    s.cloths[0].Kb[None] = float(g["Kb"])
+    s.mu_cloth_elastic[None] = float(g["mu"])
+    s.init_all(); s.reset()
+    e = s.engine
+    assert np.abs(e.pos.cpu().numpy() - g["pos0"]).max() == 0.0
+    assert np.abs(e.mass.cpu().numpy() - g["mass"]).max() <= 1e-14 * g["mass"].max()
+    assert np.array_equal(e.frozen.cpu().numpy(), g["frozen"]) and np.array_equal(s.faces, g["faces"])
+    assert np.abs(e.cloth_ref_angle[0].cpu().numpy() - g["ref_angle0"]).max() < 1e-12
+    T = int(g["T"])
+    agent = agent_trajopt(T, 1, max_moving_dist=0.001)
+    agent.traj.from_numpy(g["traj"])
+    agent.get_action(1)
+    s.action(1, agent.delta_pos, agent.delta_rot)
+    st = s.time_step()
+    assert st.converged and st.n_contacts == int(g["f1_nc"])
+    assert np.abs(e.pos.cpu().numpy() - g["f1_pos"]).max() < 3e-7

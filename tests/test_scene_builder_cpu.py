@@ -1,0 +1,49 @@
+"""Scene construction (thinshelllab_b200/engine/scene_builder.py, engine/readfile.py: cold path, numpy) against the arrays the
+REFERENCE produced for the same scenes (tests/golden/folding.npz, forming.npz: dumps of Scene.init_all(); Scene.reset() under the
+Taichi emulation, oracle/gen_goldens.py:gen_folding): positions, masses, frozen flags, surface triangles with their orientation,
+tetrahedral cells and rest matrices, the gripper frame."""
+import os
+
+import numpy as np
+import pytest
+
+from thinshelllab_b200.engine import readfile
+from thinshelllab_b200.engine.scene_builder import TactileBody, folding_state
+
+
+def test_tetgen_readers_match_the_reference_mesh(golden_dir):
+    g = np.load(os.path.join(golden_dir, "folding.npz"))
+    n, ox = readfile.read_node()
+    m, cells = readfile.read_ele()
+    k, faces = readfile.read_smesh()
+    assert (n, m, k) == (276, 1365, 200)
+    assert np.array_equal(np.asarray(ox), g["pad_F_ox"]) and np.array_equal(np.asarray(cells), g["pad_tets"])
+    nb, _ = readfile.read_node("../data/ball.node")
+    assert nb == 100                                      # data/ball.*: the ball of Scene_balancing (BASELINE configs[3])
+    ball = TactileBody(1.0, name="ball").init((0.0, 0.0, 0.0), False)
+    assert ball.F_W.min() > 0 and abs(ball.F_m.sum() - ball.F_W.sum() * ball.density) < 1e-12
+
+
+@pytest.mark.parametrize("tag,forming", [("folding", False), ("forming", True)])
+def test_scene_state_matches_the_reference(golden_dir, tag, forming):
+    g = np.load(os.path.join(golden_dir, f"{tag}.npz"))
+    st = folding_state(cloth_size=0.1, forming=forming)
+    exact = ("pos0", "vel0", "frozen", "pad_F_B", "pad_f2v", "pad_is_surface", "gripper_pos0", "gripper_F_x", "gripper_bound_idx", "table_tets",
+             "pad_tets", "border_flag", "gravity", "pad_gravity", "table_gravity", "cloth_dx", "pad_mu", "pad_lam", "pad_alpha", "table_mu", "table_lam")
+    for k in exact:
+        assert np.array_equal(np.asarray(st[k]), np.asarray(g[k])), k
+    for k in ("mass", "pad_F_W", "cloth_mass"):
+        assert np.abs(np.asarray(st[k]) - g[k]).max() <= 1e-14 * np.abs(g[k]).max(), k
+    for k in ("k_contact", "eps_contact", "eps_v", "dt", "k_angle", "cloth_N", "cloth_M"):
+        assert float(st[k]) == float(g[k]), k
+    assert int(st["table_offset"]) == int(g["table_offset"]) and int(st["pad_offset"]) == int(g["pad_offset"])
+    nfc = int(g["body_f"][0][1])
+    faces = np.concatenate([g["faces"][:nfc], st["_table_faces"], st["_pad_faces"]])      # (cloth faces come from the library's mesher)
+    assert np.array_equal(faces, g["faces"])
+
+
+def test_other_cloth_sizes_build():
+    for size in (0.06, 0.08):
+        st = folding_state(cloth_size=size)
+        assert st["pos0"].shape[0] == 64 + 162 + 276 and np.isfinite(st["pos0"]).all()
+        assert abs(st["cloth_dx"] - size / 15) < 1e-18

@@ -49,6 +49,7 @@ SIGNATURES = {
     "tsl_set_stream": (_i, [_vp, _vp]),
     "tsl_add_cloth": (_i, [_vp, _i, _i, _i, _d, _d, _d, _d, _d, _d, _vp]),
     "tsl_set_cloth_params": (_i, [_vp, _i, _d, _d, _d, _d]),
+    "tsl_cloth_update_ref_angle": (_i, [_vp, _i]),
     "tsl_get_cloth_topology": (_i, [_vp, _i, _vp, _vp, _vp]),
     "tsl_set_side_test_override": (_i, [_vp, _i, _vp]),
     "tsl_add_tets": (_i, [_vp, _i, _i, _i, _i, _vp, _vp, _vp, _d, _d, _d, _vp]),

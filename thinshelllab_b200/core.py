@@ -100,6 +100,11 @@ class ShellEngine:
     def set_cloth_params(self, cloth, Kl, Ka, Kb, k_angle):
         self._ck(self.L.tsl_set_cloth_params(self.ctx, cloth, Kl, Ka, Kb, k_angle))
 
+    def update_ref_angle(self, cloth=0):
+        """Cloth.update_ref_angle / init_ref_angle at the bound positions (plastic flow beyond k_angle)"""
+        self._sync_stream()
+        self._ck(self.L.tsl_cloth_update_ref_angle(self.ctx, int(cloth)))
+
     def set_side_test_override(self, cloth, ov):
         """test hook: ov [NF, 3] int8 with 1 = negative, or None for the canonical rule"""
         if ov is None:

@@ -189,6 +189,16 @@ int tsl_set_cloth_params(tsl_ctx *ctx, int cloth, double Kl, double Ka, double K
     return TSL_OK;
 }
 
+int tsl_cloth_update_ref_angle(tsl_ctx *ctx, int cloth)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    REQUIRE(cloth >= 0 && cloth < (int)ctx->cloths.size(), "bad cloth id");
+    StreamScope scope_(ctx);
+    launch_update_ref_angle(ctx, ctx->cloths[cloth]);
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+
 // test hook: outcomes of the topologically degenerate side tests.  ov_host [NF][3]: 1 = negative, anything else = not
 // negative (the canonical rule); NULL restores the canonical rule everywhere.
 int tsl_set_side_test_override(tsl_ctx *ctx, int cloth, const signed char *ov_host)

@@ -1,0 +1,137 @@
+"""Scene construction on the host (cold path, numpy): what `Scene.__init__(); Scene.init_all(); Scene.reset()` leave in the reference's
+fields, built from the mesh assets and the scenes' own formulas -- positions, masses, frozen flags, surface triangles, tetrahedral
+cells with their rest matrices, the gripper frame -- as the `state` mapping the B200 scene classes consume.
+
+Mirrors (cited per function): Cloth.__init__ / init_pos_offset* (code/engine/model_fold_offset.py:11-32, 826-868), the tactile
+Elastic (code/engine/model_elastic_tactile.py:13-79, 215-229, 260-325), the box Elastic (code/engine/model_elastic_offset.py via
+meshes.box_body), gripper.init_kernel (code/engine/gripper_single.py:51-78), BaseScene.__init__ / init_property / init_faces
+(code/engine/BaseScene.py:30-135, 330-383) and the scenes' init_objects / init / set_frozen_kernel
+(code/task_scene/Scene_folding.py:37-127, Scene_forming.py).  Rest angles (Cloth.init_ref_angle) are computed by the library
+(tsl_cloth_update_ref_angle) when the scene object binds the state."""
+import numpy as np
+
+from ..meshes import box_body
+from . import readfile
+
+
+class TactileBody:
+    """model_elastic_tactile.Elastic(dt, offset, ratio): the pad / ball mesh from TetGen files, scaled by `ratio`"""
+
+    def __init__(self, ratio, name="tactile", E=300000.0, nu=0.2, density=2000.0):
+        self.ratio, self.density = float(ratio), float(density)
+        self.mu = E / (2 * (1 + nu))
+        self.lam = E * nu / ((1 + nu) * (1 - 2 * nu))
+        self.alpha = 1 + self.mu / self.lam
+        n, ox = readfile.read_node(f"../data/{name}.node")
+        _, cells = readfile.read_ele(f"../data/{name}.ele")
+        _, f2v = readfile.read_smesh(f"../data/{name}.face")
+        self.F_ox = np.asarray(ox, np.float64)
+        self.tets = np.asarray(cells, np.int32)
+        self.f2v_file = np.asarray(f2v, np.int32)
+        self.n_verts, self.n_cells, self.n_surfaces = n, self.tets.shape[0], self.f2v_file.shape[0]
+        self.is_surface = np.zeros(n, bool)                    # count() :302-311
+        self.is_surface[self.f2v_file.reshape(-1)] = True
+        r = np.linalg.norm(self.F_ox, axis=1)
+        self.bottom = (self.F_ox[:, 2] < 0.001) & self.is_surface                    # is_bottom :253-254
+        self.inner_circle = (r < 0.0076) & self.is_surface                            # is_inner_circle :257-258
+        self.surf = (r > 0.0148) & self.is_surface                                    # is_surf :261-262
+
+    def init(self, offset, flip):
+        """Elastic.init -> init_pos + init_surface_indices (:215-229, 264-291): world positions, B = Ds^-1, W = |det Ds| / 6, lumped
+        masses, surface triangles oriented outwards (inwards on the inner circle)"""
+        off = np.asarray(offset, np.float64)
+        x = self.ratio * self.F_ox
+        if flip:
+            x = -x
+        self.F_x = x + off
+        Ds = np.stack([self.F_x[self.tets[:, i]] - self.F_x[self.tets[:, 3]] for i in range(3)], -1)
+        self.F_B = np.linalg.inv(Ds)
+        self.F_W = np.abs(np.linalg.det(Ds)) / 6
+        self.F_m = np.zeros(self.n_verts)
+        np.add.at(self.F_m, self.tets.reshape(-1), np.repeat(self.F_W / 4 * self.density, 4))
+        f = self.f2v_file.copy()
+        p1, p2, p3 = self.F_x[f[:, 0]], self.F_x[f[:, 1]], self.F_x[f[:, 2]]
+        n = np.cross(p2 - p1, p3 - p1)
+        n /= np.linalg.norm(n, axis=1, keepdims=True)
+        inner = off + np.array([0.0, 0.0, (-0.002 if flip else 0.002) * self.ratio])
+        towards = np.einsum("ij,ij->i", n, inner[None] - p1) > 0
+        all_inner = self.inner_circle[f].all(1)
+        swap = towards != all_inner                            # swap when (towards and not inner) or (not towards and inner)
+        f[swap, 1], f[swap, 2] = self.f2v_file[swap, 2], self.f2v_file[swap, 1]
+        self.f2v = f
+        return self
+
+
+def cloth_positions_flat(N, M, dx, offset):
+    """Cloth.init_pos_offset (:826-831)"""
+    i, j = np.meshgrid(np.arange(N + 1), np.arange(M + 1), indexing="ij")
+    return np.stack([i * dx + offset[0], j * dx + offset[1], np.full(i.shape, offset[2], np.float64)], -1).reshape(-1, 3)
+
+
+def cloth_positions_fold(N, M, dx, offset, half_curv_num):
+    """Cloth.init_pos_offset_fold (:841-861): the strip folded back over itself through a half circle (3.1415 as the reference has it)"""
+    ox, oy, oz = offset
+    r = dx
+    if half_curv_num != 2:
+        r = dx * (half_curv_num * 2 - 1) / 3.1415
+    L, R = 7 - half_curv_num + 1, 7 + half_curv_num
+    pos = np.zeros((N + 1, M + 1, 3))
+    for i in range(N + 1):
+        for j in range(M + 1):
+            if i <= L:
+                pos[i, j] = [(15 - i) * dx + ox, j * dx + oy, oz + 2 * r]
+            if L + 1 <= i <= R - 1:
+                x = (15 - L) * dx
+                ang = (i - L) / (half_curv_num * 2 - 1) * 3.1415
+                pos[i, j] = [x - r * np.sin(ang) + ox, j * dx + oy, oz + r * (1 + np.cos(ang))]
+            if i >= R:
+                pos[i, j] = [i * dx + ox, j * dx + oy, oz]
+    return pos.reshape(-1, 3)
+
+
+def pad_scene_state(*, cloth_size, cloth_N, cloth_M, cloth_pos, dt=5e-3, k_contact, eps_contact=0.0004, eps_v=0.01, max_n_constraints=10000,
+                    rho=40.0, Kb=100.0, k_angle=3.14, mu=1.0, gravity=(0.0, 0.0, 0.0), table=(0.07, 9, 9, 2, (-0.035, -0.035, -0.00875)),
+                    pad_ratio=0.015 / 0.03, pad_pos=None, pinned_last_row=True, init_ref_angle=True, cloth_topology=None):
+    """state of a one-cloth / table / one-pad scene (Scene_folding, Scene_forming): BaseScene.__init__ + init_objects + init +
+    init_property + set_frozen_kernel.  cloth_topology: f2v [NF,3] of the cloth (the library's, ShellEngine.cloth_topology)."""
+    dx = cloth_size / cloth_N
+    NVc = (cloth_N + 1) * (cloth_M + 1)
+    tpos, ttets, tfaces, tmass = box_body(table[0], table[1], table[2], table[3], table[4])
+    to, tn = NVc, tpos.shape[0]
+    pad = TactileBody(pad_ratio).init(pad_pos, True)
+    po, pn = to + tn, pad.n_verts
+    pos0 = np.concatenate([cloth_pos, tpos, pad.F_x])
+    mass = np.concatenate([np.full(NVc, rho * dx * dx), tmass, pad.F_m])
+    frozen = np.zeros((pos0.shape[0], 3), np.int32)
+    frozen[to:to + tn] = 1
+    frozen[po:po + pn][pad.bottom | pad.inner_circle] = 1
+    if pinned_last_row:
+        frozen[cloth_N * (cloth_M + 1):NVc] = 1
+    st = dict(dt=dt, k_contact=float(k_contact), eps_contact=eps_contact, eps_v=eps_v, mu=mu, Kb=Kb, k_angle=k_angle, cloth_N=cloth_N, cloth_M=cloth_M,
+              cloth_dx=dx, cloth_mass=rho * dx * dx, cloth_size=cloth_size, max_n_constraints=max_n_constraints,
+              pos0=pos0, vel0=np.zeros_like(pos0), mass=mass, frozen=frozen.reshape(-1), border_flag=np.zeros(pos0.shape[0], np.int32),
+              gravity=np.asarray(gravity, np.float64), ref_angle0=np.zeros((2 * cloth_N * cloth_M, 3)), init_ref_angle=bool(init_ref_angle),
+              table_tets=ttets, table_offset=to, table_nverts=tn, table_mu=5e5 / 2, table_lam=0.0,                    # box Elastic: E = 5e5, nu = 0 (model_elastic_offset.py:13-15)
+              table_gravity=np.asarray(gravity, np.float64),
+              pad_tets=pad.tets, pad_offset=po, pad_nverts=pn, pad_F_ox=pad.F_ox, pad_ratio=pad.ratio, pad_f2v=pad.f2v,
+              pad_is_surface=pad.is_surface.astype(np.int32), pad_F_B=pad.F_B, pad_F_W=pad.F_W, pad_mu=pad.mu, pad_lam=pad.lam, pad_alpha=pad.alpha,
+              pad_gravity=np.zeros(3),
+              gripper_pos0=np.asarray(pad_pos, np.float64)[None], gripper_rot0=np.array([[1.0, 0.0, 0.0, 0.0]]),
+              gripper_F_x=(pad.F_x - np.asarray(pad_pos, np.float64))[None],                     # gripper.init_kernel :55-60
+              gripper_bound_idx=np.nonzero(pad.bottom | pad.inner_circle)[0].astype(np.int32),    # :62-68
+              gripper_surface_idx=np.nonzero(pad.surf & ~(pad.bottom | pad.inner_circle))[0].astype(np.int32),
+              _table_faces=tfaces + to, _pad_faces=pad.f2v + po)
+    return st
+
+
+def folding_state(cloth_size=0.06, forming=False, Kb=100.0):
+    """Scene_folding (cloth 15 x 3, half_curve_num 2, k_contact 10000, k_angle 0.5) / Scene_forming (15 x 7, 3, 20000, 3.14)"""
+    N, M = 15, (7 if forming else 3)
+    hc = 3 if forming else 2
+    dx = cloth_size / N
+    cpos = cloth_positions_fold(N, M, dx, (-0.07, -0.02, 0.00035) if forming else (-0.07, -0.01, 0.0004), hc)
+    r = dx * (hc * 2 - 1) / 3.1415
+    x = -0.07 + (7 + hc) / 16 * 0.1 - r * 0.86 + (0.01 if forming else 0.005)
+    pad_pos = (x, 0.0, 2 * r + (0.00785 if forming else 0.0079))
+    return pad_scene_state(cloth_size=cloth_size, cloth_N=N, cloth_M=M, cloth_pos=cpos, k_contact=20000.0 if forming else 10000.0, Kb=Kb,
+                           k_angle=3.14 if forming else 0.5, pad_pos=pad_pos)

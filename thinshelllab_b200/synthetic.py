@@ -68,8 +68,11 @@ def pad_sheet_state(N, pad, dx=0.002, dt=5e-3, Kb=100.0, k_angle=3.14, k_contact
     tpos, tfaces, tmass = sp["table_pos"], sp["table_faces"], sp["table_mass"]
     po, pn = int(pad["pad_offset"]), int(pad["pad_nverts"])
     Fx = np.asarray(pad["gripper_F_x"], np.float64)[0]
-    pf0, pf1 = (int(v) for v in np.asarray(pad["body_f"])[2])
-    pfaces = np.asarray(pad["faces"])[pf0:pf1] - po
+    if "faces" in pad:                          # a reference-made state (tests/golden/folding.npz)
+        pf0, pf1 = (int(v) for v in np.asarray(pad["body_f"])[2])
+        pfaces = np.asarray(pad["faces"])[pf0:pf1] - po
+    else:                                       # engine/scene_builder.folding_state
+        pfaces = np.asarray(pad["_pad_faces"]) - po
     gpos = np.array([[0.0, 0.0, 0.0004 + 0.0004 + gap - Fx[:, 2].min()]])
     ppos = gpos + Fx
     to, pno = NVc, NVc + tpos.shape[0]
@@ -88,8 +91,11 @@ def pad_sheet_state(N, pad, dx=0.002, dt=5e-3, Kb=100.0, k_angle=3.14, k_contact
                 max_n_constraints=4 * NVc + 4096, grid_n=sp["grid_n"], n_tris=NFc)
 
 
-def pad_sheet_scene(N, pad, device="cuda:0", **kw):
+def pad_sheet_scene(N, pad=None, device="cuda:0", **kw):
     from .task_scene.Scene_folding import Scene
+    if pad is None:
+        from .engine.scene_builder import folding_state
+        pad = folding_state(cloth_size=0.1)
     st = pad_sheet_state(N, pad, **kw)
     return Scene(st, device=device, max_newton=200)
 

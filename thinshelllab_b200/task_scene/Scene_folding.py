@@ -3,10 +3,10 @@ frozen neo-Hookean table and one tactile pad whose bottom / inner-circle vertice
 (cloth faces against pad and table vertices, pad and table faces against cloth vertices, contact_analysis :99-108), so constraint
 triangles move and the general contact path of libtsl is exercised.
 
-Mesh generation and asset loading (data/tactile.*, Cloth.init_fold) are cold-path and outside this build's scope: the scene is
-constructed from arrays -- what `Scene.init_all(); Scene.reset()` leaves in the reference's fields (positions, masses, frozen
-flags, faces, cells with their rest matrices, gripper frame).  tests/golden/folding.npz holds one such state, written by
-oracle/gen_goldens.py from the reference itself."""
+Construction (cold path): engine/scene_builder.py builds what `Scene.init_all(); Scene.reset()` leave in the reference's fields --
+the folded strip (Cloth.init_fold), the box table, the tactile pad from the TetGen assets (data/tactile.*), masses, frozen flags,
+surface triangles, the gripper frame -- for any cloth_size; tests/test_scene_builder_cpu.py pins it to the arrays the reference itself
+produced (tests/golden/folding.npz, forming.npz).  A `state` mapping with the same keys can be passed instead (synthetic scenes)."""
 import os
 
 import numpy as np
@@ -41,25 +41,18 @@ class _ElasticView:
         return TensorField(self._s.engine.pos[self.offset:self.offset + self.n_verts])
 
 
-_DEFAULT_STATE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "scene_folding_cloth0p1.npz")
-
-
 class Scene:
-    DEFAULT_STATE = _DEFAULT_STATE
+    FORMING = False                            # Scene_forming subclasses with True (15 x 7 strip, k_contact 20000)
 
     def __init__(self, cloth_size=0.06, device="cuda:0", *, state=None, max_newton=50):
-        """reference signature: Scene(cloth_size=0.06, device="cuda:0") (code/task_scene/Scene_folding.py:27).  The scene arrays come
-        from `state` (a mapping with the keys of tests/golden/folding.npz, see oracle/gen_goldens.py:gen_folding; also accepted as the
-        first positional argument), else from the file named by TSL_SCENE_STATE, else -- for cloth_size = 0.1, the size every
-        reference driver uses -- from thinshelllab_b200/data/scene_folding_cloth0p1.npz (tools/make_scene_state.py)."""
+        """reference signature: Scene(cloth_size=0.06, device="cuda:0") (code/task_scene/Scene_folding.py:27).  The scene is built by
+        engine/scene_builder.folding_state(cloth_size); a ready `state` mapping (keys of tests/golden/folding.npz, see
+        oracle/gen_goldens.py:gen_folding) may be passed instead, also as the first positional argument (synthetic scenes, tests)."""
         if state is None and hasattr(cloth_size, "keys"):
             state, cloth_size = cloth_size, None
         if state is None:
-            path = os.environ.get("TSL_SCENE_STATE", self.DEFAULT_STATE)
-            state = np.load(path)
-            if cloth_size is not None and "cloth_size" in state and abs(float(state["cloth_size"]) - float(cloth_size)) > 1e-12:
-                raise NotImplementedError(f"Scene_folding: no scene state for cloth_size={cloth_size} ({path} holds {float(state['cloth_size'])}); "
-                                          "mesh generation is not part of this build -- dump the reference scene's arrays and pass state=")
+            from ..engine.scene_builder import folding_state
+            state = folding_state(cloth_size=float(cloth_size), forming=self.FORMING)
         g = state
         self.dt = self.h = float(g["dt"])
         self.cloth_cnt, self.elastic_cnt, self.effector_cnt = 1, 2, 2
@@ -116,6 +109,12 @@ class Scene:
         self.gripper = gripper(self, [po], g["gripper_F_x"], g["gripper_bound_idx"], self._gpos0)
         self.gravity = np.array(gravity)
         e.finalize()
+        if "init_ref_angle" in g and bool(g["init_ref_angle"]):
+            # Cloth.init_fold -> init_ref_angle (model_fold_offset.py:1053-1057, 788-797): plastic flow of the folded strip's rest angles
+            e.pos.copy_(torch.from_numpy(self._pos0)); e.prev_pos.copy_(e.pos)
+            e.cloth_ref_angle[0].zero_()
+            e.update_ref_angle(0)
+            self._ref0 = e.cloth_ref_angle[0].cpu().numpy().copy()
         self.reset()
 
     def _set_mu(self, v):

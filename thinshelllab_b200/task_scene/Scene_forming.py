@@ -1,8 +1,6 @@
 """Scene_forming on the B200 engine (code/task_scene/Scene_forming.py): the Scene_folding layout -- cloth strip pinned along its last row,
 frozen table, one tactile pad on a gripper, contacts both ways -- with a 15 x 7 strip, k_contact = 20000 and a position reward
 (:127-133).  Everything on the hot path is shared with Scene_folding; only the scene arrays and the reward differ."""
-import os
-
 import numpy as np
 import torch
 
@@ -11,7 +9,7 @@ from .Scene_folding import Scene as _FoldingScene
 
 
 class Scene(_FoldingScene):
-    DEFAULT_STATE = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "data", "scene_forming_cloth0p1.npz")
+    FORMING = True                             # engine/scene_builder.folding_state(forming=True): 15 x 7 strip, half_curve_num 3, k_contact 20000
 
     def compute_reward(self, target_pos):
         """:127-133: minus the squared distance of the cloth to the target shape"""

@@ -14,7 +14,7 @@ from thinshelllab_b200.synthetic import pad_sheet_scene  # noqa: E402
 
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 316
 T = 1 + (int(sys.argv[2]) if len(sys.argv) > 2 else 2)
-g = np.load(os.path.join(ROOT, "thinshelllab_b200", "data", "scene_folding_cloth0p1.npz"))
+g = None   # pad arrays from engine/scene_builder.folding_state
 s = pad_sheet_scene(N, g)
 agent = agent_trajopt(T, 1, max_moving_dist=0.001)
 traj = np.zeros((T, 1, 6)); traj[:, 0, 2] = -1.5e-4 * np.arange(T)
