@@ -204,7 +204,13 @@ int tsl_gripper_gather(tsl_ctx *ctx, const double *z_frozen_dev, int v_offset, i
  * Newton driver's energy / |p|_inf / F.p.  The reference has no multi-GPU path; this is north_star's partition.
  * tsl_dist_unique_id: 128-byte ncclUniqueId made by rank 0, to be broadcast by the caller (torch.distributed). */
 int tsl_dist_unique_id(void *out128_host);
-int tsl_dist_init(tsl_ctx *ctx, const void *id128_host, int rank, int world, int ghost_lo_rows, int ghost_hi_rows);
+/* Geometry rules, checked (TSL_ERR_INVALID): ghost rows are 2 on an inner side and 0 on the outer side of the first / last strip; a strip
+ * owns at least 2 rows; first_row_global -- the global grid row of the context's local row 0 (ghost rows included) -- is EVEN (the
+ * mesher picks triangle diagonals from row parity, so an odd start would triangulate differently from the single-GPU sheet); all strips
+ * have the same row length and tile the sheet without gaps (verified across ranks at init, so that the halo exchange cannot hang).
+ * Bodies other than the cloth are rank-local (each rank describes the part of the table under its strip): a body replicated on several
+ * ranks would be counted once per rank in the all-reduced energy. */
+int tsl_dist_init(tsl_ctx *ctx, const void *id128_host, int rank, int world, int ghost_lo_rows, int ghost_hi_rows, int first_row_global);
 int tsl_dist_stats(tsl_ctx *ctx, long long *halo_msgs_out, long long *allreduces_out);
 
 /* ---- introspection used by the parity tests and the benchmark ---------------------------------- */

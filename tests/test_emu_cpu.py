@@ -53,7 +53,7 @@ def test_dense_lu_flags_singular_matrix():
     assert L.emu_lu_solve(n, Af.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p), x.ctypes.data_as(C.c_void_p), 64) == 1
 
 
-@pytest.mark.parametrize("N,M,offset,seed", [(5, 4, 0, 0), (9, 37, 0, 1), (6, 66, 40, 2)])
+@pytest.mark.parametrize("N,M,offset,seed", [(5, 4, 0, 0), (9, 37, 0, 1), (6, 66, 40, 2), (15, 3, 0, 3), (7, 2, 0, 4), (4, 1, 32, 5)])
 def test_owner_computes_hessian_rows_match_the_oracle_twin(N, M, offset, seed):
     """k_hessian_rows (tsl_assembly_kernels.cuh: one thread per matrix block, tiles of 4 x 32 grid vertices, hinge gradients staged in
     shared memory, contribution lists from the tables read off the reference's mesher) against the oracle's CPU twin of the forward
@@ -140,3 +140,55 @@ def test_owner_computes_residual_and_energy_match_the_oracle(N, M, offset, seed)
     assert np.abs(Fc - Fb).max() <= 1e-11 * np.abs(Fb).max()
     F.reshape(-1, 3)[offset:offset + NV] = 123.0
     assert np.all(F == 123.0)                                         # only the cloth rows are written
+
+
+@pytest.mark.parametrize("n0f,n1f,emf,emc", [(13, 21, 0, 0), (12, 35, 1, 1), (7, 9, 1, 0)])
+def test_tiled_galerkin_matches_the_entrywise_kernel(n0f, n1f, emf, emc):
+    """k_galerkin_tiled (fine stencil rows staged in shared memory per tile of 2 x 8 coarse vertices) against k_galerkin (one thread
+    per coarse entry), odd and even grid sizes, row-major and element-major levels"""
+    L = _build("emu_mg")
+    rng = np.random.default_rng(n0f * 100 + n1f)
+    nvf = n0f * n1f
+    vf = rng.standard_normal((nvf, 25, 9)).astype(np.float32)
+    # entries that point outside the grid hold zeros (as the fine levels are built)
+    for v in range(nvf):
+        i, j = divmod(v, n1f)
+        for s in range(25):
+            ii, jj = i + s // 5 - 2, j + s % 5 - 2
+            if not (0 <= ii < n0f and 0 <= jj < n1f):
+                vf[v, s] = 0
+    nvc = ((n0f - 1) // 2 + 1) * ((n1f - 1) // 2 + 1)
+    ref = np.zeros((nvc, 225), np.float32); out = np.zeros((nvc, 225), np.float32)
+    L.emu_galerkin_pair(n0f, n1f, emf, emc, vf.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert np.abs(ref).max() > 1 and np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()
+
+
+@pytest.mark.parametrize("N,M,off", [(12, 20, 0), (9, 33, 40)])
+def test_tiled_galerkin_from_the_sliced_ell_matrix(N, M, off):
+    """k_galerkin_sell_tiled (level 0 -> 1 straight from the sliced-ELL matrix, frozen DOFs masked out) against k_sell_to_stencil +
+    k_galerkin<MASK>, on the cloth's own block pattern with extra rows before / after the cloth"""
+    import scipy.sparse as sp
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    from oracle import tsl_oracle as orc
+    L = _build("emu_mg")
+    rng = np.random.default_rng(N)
+    n0f, n1f = N + 1, M + 1
+    NV = n0f * n1f
+    f2v, cf, cp = orc.cloth_mesh(N, M)
+    hi, hl = np.nonzero(cf > np.arange(2 * N * M)[:, None])
+    hinge = np.stack([f2v[hi, hl], f2v[hi, (hl + 1) % 3], f2v[hi, (hl + 2) % 3], f2v[cf[hi, hl], cp[hi, hl]]], 1)
+    r = np.concatenate([st[:, a] for st in (f2v, hinge) for a in range(st.shape[1]) for b in range(st.shape[1])])
+    c = np.concatenate([st[:, b] for st in (f2v, hinge) for a in range(st.shape[1]) for b in range(st.shape[1])])
+    nv = off + NV + 5
+    A = sp.csr_matrix((np.ones(r.size), (r + off, c + off)), shape=(nv, nv)) + sp.identity(nv, format="csr")
+    A.sum_duplicates(); A.sort_indices()
+    rowptr, colidx = A.indptr.astype(np.int32), A.indices.astype(np.int32)
+    blocks = rng.standard_normal((colidx.size, 9)).astype(np.float32)
+    mask = np.zeros(3 * NV, np.int32)
+    mask[rng.integers(0, 3 * NV, 25)] = 1
+    nvc = ((n0f - 1) // 2 + 1) * ((n1f - 1) // 2 + 1)
+    ref = np.zeros((nvc, 225), np.float32); out = np.zeros((nvc, 225), np.float32)
+    L.emu_galerkin_sell(off, n0f, n1f, nv, rowptr.ctypes.data_as(C.c_void_p), colidx.ctypes.data_as(C.c_void_p), blocks.ctypes.data_as(C.c_void_p),
+                        mask.ctypes.data_as(C.c_void_p), ref.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert np.abs(ref).max() > 1 and np.abs(out - ref).max() <= 1e-5 * np.abs(ref).max()

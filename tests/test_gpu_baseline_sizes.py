@@ -125,7 +125,7 @@ def test_sheet316_with_pad_pressed_steps(golden_dir):
     from thinshelllab_b200.engine.analytic_grad_single import Grad as GradT
     from thinshelllab_b200.synthetic import pad_sheet_scene, sheet_spec
     pad = np.load(os.path.join(golden_dir, "folding.npz"))
-    N, T = 316, 3
+    N, T = 316, 5
     s = pad_sheet_scene(N, pad)
     e = s.engine
     NVc = s.cloths[0].NV
@@ -156,7 +156,7 @@ def test_sheet316_with_pad_pressed_steps(golden_dir):
         c = e.constraints()
         table = (c["idx"][:, 3] < NVc) & (c["idx"][:, 0] >= to) & (c["idx"][:, 0] < to + tn)
         assert sorted(map(tuple, c["idx"][table])) == sorted(map(tuple, o.c_idx[:o.nc])), f
-        touching = (c["idx"][:, 3] >= pad0).sum() + ((c["idx"][:, 3] < NVc) & (c["idx"][:, 0] >= pad0)).sum()
+        touching = (c["idx"][:, 3] >= pad0).sum() + ((c["idx"][:, 3] < NVc) & (c["idx"][:, 0] >= pad0)).sum()   # pad vertex / cloth face + cloth vertex / pad face
         print(f"316 x 316 + pad step {f}: newton {st.newton_iters} pcg {st.linear_iters} contacts {st.n_contacts} (cloth/table {int(table.sum())}, with the pad {int(touching)})")
         grad.copy_pos(s, f)
     assert o.nc > 10000 and touching > 0                        # the sheet lies on the table and the pad presses into it
@@ -174,7 +174,7 @@ def test_sheet707_first_iteration_vs_oracle():
     e = s.engine
     o = _oracle_for(s)
     o.calc_vn(); o.projection_query(); o.contact_analysis(); o._build_pattern()
-    assert e.contact_detect() == o.nc and o.nc > 100000
+    assert e.contact_detect() == o.nc and o.nc > 10000
     _same_sets(e, o)
     E_o = o.compute_energy()
     assert abs(e.energy() - E_o) <= 1e-12 * abs(E_o)

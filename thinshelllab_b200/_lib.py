@@ -73,7 +73,7 @@ SIGNATURES = {
     "tsl_gripper_gather": (_i, [_vp, _vp, _i, _i, _vp, _vp, C.POINTER(C.c_float), _d, _d, _dp]),
     "tsl_get_contact_blocks": (_i, [_vp, _ip, _vp, _vp, _vp]),
     "tsl_dist_unique_id": (_i, [_vp]),
-    "tsl_dist_init": (_i, [_vp, _vp, _i, _i, _i, _i]),
+    "tsl_dist_init": (_i, [_vp, _vp, _i, _i, _i, _i, _i]),
     "tsl_dist_stats": (_i, [_vp, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]),
     "tsl_get_residual": (_i, [_vp, _vp]),
     "tsl_get_matrix_nnzb": (_i, [_vp, _ip]),

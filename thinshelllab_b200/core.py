@@ -151,7 +151,7 @@ class ShellEngine:
         self._ck(self.L.tsl_finalize(self.ctx))
         self.finalized = True
 
-    def dist_init(self, rank, world, ghost_lo_rows, ghost_hi_rows):
+    def dist_init(self, rank, world, ghost_lo_rows, ghost_hi_rows, first_row_global=0):
         """strip partition (include/tsl.h: tsl_dist_init).  The ncclUniqueId is made by rank 0 and broadcast through the
         torch.distributed process group the caller has already initialised (backend nccl)."""
         import torch.distributed as dist
@@ -164,7 +164,7 @@ class ShellEngine:
             dist.broadcast(t, 0)
             raw = bytes(t.cpu().numpy().tobytes())
             buf = (C.c_ubyte * 128).from_buffer_copy(raw)
-        self._ck(self.L.tsl_dist_init(self.ctx, buf, int(rank), int(world), int(ghost_lo_rows), int(ghost_hi_rows)))
+        self._ck(self.L.tsl_dist_init(self.ctx, buf, int(rank), int(world), int(ghost_lo_rows), int(ghost_hi_rows), int(first_row_global)))
         self.dist = (int(rank), int(world), int(ghost_lo_rows), int(ghost_hi_rows))
 
     def dist_stats(self):

@@ -219,12 +219,11 @@ __global__ void __launch_bounds__(256) k_hessian_rows(ClothGrid G, const double 
         if (pb >= b1) continue;
         const int col = colidx[pb];
         if (col == row && pb != diag_pb[row]) continue;                      // ELL padding: stays zero
-        const int dcol = col - row;
-        // dcol = di * W + dj with |dj| <= 2
-        const int q_ = dcol + 2 * W + 2;
-        if (q_ < 0) continue;
-        const int di = q_ / W - 2, dj = q_ - (di + 2) * W - 2;
-        if (di < -2 || di > 2 || dj < -2 || dj > 2 || i + di < 0 || i + di > G.N || j + dj < 0 || j + dj > G.M) continue;
+        const int u = col - G.offset;
+        if (u < 0 || u >= G.NV) continue;
+        const int ui = u / W, uj = u - ui * W;                                // (exact for every grid width, also W < 5)
+        const int di = ui - i, dj = uj - j;
+        if (di < -2 || di > 2 || dj < -2 || dj > 2) continue;
         const int slot = (di + 2) * 5 + (dj + 2);
         float Be[9], Bc[9];
 #pragma unroll

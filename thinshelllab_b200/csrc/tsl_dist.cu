@@ -6,6 +6,8 @@
 //   * energy, |p|_inf and F.p of the Newton driver (one scalar each per line-search trial / iteration).
 // NCCL is resolved at run time from the libnccl.so.2 the process already holds (torch's), so libtsl has no link dependency on it.
 #include <dlfcn.h>
+#include <algorithm>
+#include <vector>
 #include <nccl.h>
 
 #include "tsl_internal.cuh"
@@ -114,12 +116,19 @@ int tsl_dist_unique_id(void *out128_host)
     return TSL_OK;
 }
 
-int tsl_dist_init(tsl_ctx *ctx, const void *id128_host, int rank, int world, int ghost_lo_rows, int ghost_hi_rows)
+int tsl_dist_init(tsl_ctx *ctx, const void *id128_host, int rank, int world, int ghost_lo_rows, int ghost_hi_rows, int first_row_global)
 {
     if (!ctx || !id128_host) return TSL_ERR_INVALID;
     if (ctx->cloths.size() != 1 || ctx->cloths[0].offset != 0) { ctx->err = "tsl_dist_init: needs exactly one cloth at vertex offset 0"; return TSL_ERR_INVALID; }
-    if (world < 1 || rank < 0 || rank >= world || ghost_lo_rows < 0 || ghost_hi_rows < 0) { ctx->err = "tsl_dist_init: bad arguments"; return TSL_ERR_INVALID; }
-    if ((rank == 0 && ghost_lo_rows != 0) || (rank == world - 1 && ghost_hi_rows != 0)) { ctx->err = "tsl_dist_init: the outer strips have no outer ghost rows"; return TSL_ERR_INVALID; }
+    if (world < 1 || rank < 0 || rank >= world) { ctx->err = "tsl_dist_init: bad rank / world"; return TSL_ERR_INVALID; }
+    // a hinge reaches two grid rows: exactly 2 ghost rows on an inner side, none on an outer side
+    if ((ghost_lo_rows != 0 && ghost_lo_rows != 2) || (ghost_hi_rows != 0 && ghost_hi_rows != 2)) { ctx->err = "tsl_dist_init: ghost rows must be 0 or 2"; return TSL_ERR_INVALID; }
+    if ((rank == 0) != (ghost_lo_rows == 0) || (rank == world - 1) != (ghost_hi_rows == 0)) {
+        ctx->err = "tsl_dist_init: inner sides need 2 ghost rows, the outer sides of the first / last strip none"; return TSL_ERR_INVALID;
+    }
+    // Cloth.init_mesh picks the diagonal of quad (i, j) from the parity of i + j: the local mesh (built from LOCAL row indices) is the
+    // global triangulation only if local row 0 is an even global row
+    if (first_row_global < 0 || (first_row_global & 1)) { ctx->err = "tsl_dist_init: the strip's first local row must be an even global row (triangulation parity)"; return TSL_ERR_INVALID; }
     if (!nccl().ok) { ctx->err = "tsl_dist_init: libnccl.so.2 not found in this process"; return TSL_ERR_UNSUPPORTED; }
     const ClothDev &c = ctx->cloths[0];
     DistCtx &d = ctx->dist;
@@ -127,8 +136,9 @@ int tsl_dist_init(tsl_ctx *ctx, const void *id128_host, int rank, int world, int
     d.row_len = c.M + 1;
     d.nvc = c.NV;
     d.ghost_lo = ghost_lo_rows; d.ghost_hi = ghost_hi_rows;
-    int rows_local = c.N + 1;
-    if (ghost_lo_rows + ghost_hi_rows >= rows_local) { ctx->err = "tsl_dist_init: strip has no owned rows"; return TSL_ERR_INVALID; }
+    int rows_local = c.N + 1, rows_owned = rows_local - ghost_lo_rows - ghost_hi_rows;
+    // the halo exchange sends the first / last `ghost` OWNED rows: a strip must own at least as many rows as it lends
+    if (rows_owned < std::max(2, std::max(ghost_lo_rows, ghost_hi_rows))) { ctx->err = "tsl_dist_init: a strip must own at least 2 grid rows"; return TSL_ERR_INVALID; }
     d.own0 = ghost_lo_rows * d.row_len;
     d.own1 = (rows_local - ghost_hi_rows) * d.row_len;
     if (world > 1) {
@@ -137,6 +147,26 @@ int tsl_dist_init(tsl_ctx *ctx, const void *id128_host, int rank, int world, int
         ncclComm_t comm;
         NCK(nccl().CommInitRank(&comm, world, id, rank));
         d.comm = comm;
+        // every rank publishes (row length, first owned global row, owned rows): the strips must tile the sheet without gaps, with
+        // equal row length -- otherwise the send / recv counts of the halo exchange would not match and NCCL would hang
+        std::vector<double> mine(3 * (size_t)world, 0.0);
+        mine[3 * rank] = d.row_len; mine[3 * rank + 1] = first_row_global + ghost_lo_rows; mine[3 * rank + 2] = rows_owned;
+        double *buf = nullptr;
+        if (cudaMalloc(&buf, sizeof(double) * mine.size()) != cudaSuccess) { ctx->err = "tsl_dist_init: cudaMalloc"; return TSL_ERR_CUDA; }
+        cudaMemcpyAsync(buf, mine.data(), sizeof(double) * mine.size(), cudaMemcpyHostToDevice, ctx->stream);
+        ncclResult_t r = nccl().AllReduce(buf, buf, mine.size(), ncclDouble, ncclSum, comm, ctx->stream);
+        cudaMemcpyAsync(mine.data(), buf, sizeof(double) * mine.size(), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        cudaFree(buf);
+        if (r != ncclSuccess) { ctx->err = "tsl_dist_init: all-reduce of the strip geometry failed"; return TSL_ERR_CUDA; }
+        for (int q = 0; q < world; q++) {
+            if (mine[3 * q] != d.row_len) { ctx->err = "tsl_dist_init: strips have different row lengths"; dist_destroy(ctx); return TSL_ERR_INVALID; }
+            if (q > 0 && mine[3 * q + 1] != mine[3 * (q - 1) + 1] + mine[3 * (q - 1) + 2]) {
+                ctx->err = "tsl_dist_init: strips do not tile the sheet (first owned row of a rank != end of the previous rank's rows)";
+                dist_destroy(ctx);
+                return TSL_ERR_INVALID;
+            }
+        }
     }
     d.on = true;
     // the NCCL calls of an iteration are captured into its CUDA graph like the kernels (measured on 2 B200: same results, 22 % faster

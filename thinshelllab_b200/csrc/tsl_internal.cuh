@@ -108,6 +108,7 @@ struct MgDev {
     double *pow_acc = nullptr;             // device [levels][16]: |v_k|^2 of the power iteration
     float *lmax = nullptr;                 // device [levels]: estimate (diagnostic read-back)
     int setups = 0;
+    int tiled_galerkin = 1;                // Galerkin products by shared-memory tiles (TSL_MG_TILED=0: one thread per coarse entry)
     int pair_threads = 1;                  // element-major levels: 2 threads per vertex (TSL_MG_PAIR=0: one)
     int tail_level = -1;                   // first level of the fused single-block tail of the V-cycle (-1: none)
     int degree = 2, coarse_degree = 8;

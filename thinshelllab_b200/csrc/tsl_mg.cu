@@ -18,6 +18,7 @@
 // launch-latency bound.
 #include "tsl_internal.cuh"
 #include "tsl_kernels.cuh"
+#include "tsl_mg_kernels.cuh"
 
 namespace tsl {
 
@@ -450,9 +451,6 @@ __global__ void __launch_bounds__(1024) k_vcycle_tail(TailArgs A)
 }
 
 // ------------------------------------------------------------------------------------------------ transfer operators
-// 1-D bilinear weight of fine index 2I + a (a in -1..1) towards coarse parent I of nc coarse points
-__device__ __forceinline__ float pw1(int a, int I, int nc) { return a == 0 ? 1.f : (a < 0 ? 0.5f : (I + 1 < nc ? 0.5f : 1.f)); }
-
 // b_c = P^T r_f.  off: first row of the grid inside the fine vectors (level 0: cloth vertex offset); mask: frozen
 // flags [3 * rows] of the fine vectors or nullptr (frozen DOFs do not take part in the coarse correction)
 // Optionally fused with the first Chebyshev step of the coarse level (zero guess: d = c D^-1 b, x = d), which only needs the
@@ -514,91 +512,6 @@ __global__ void k_prolong_add(int n0f, int n1f, int off, float *x_f, const int *
 }
 
 // ------------------------------------------------------------------------------------------------ setup kernels
-// stencil copy of the cloth block of the sliced-ELL matrix (input of the first Galerkin product)
-__global__ void k_sell_to_stencil(int off, int nvc, int n1, const int *__restrict__ slice_base, const int *__restrict__ colidx,
-                                  const float *__restrict__ val, const int *__restrict__ diag_pb, float *out, long long sv, long long se)
-{
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= nvc) return;
-    int row = off + v;
-    int S = row >> 5, lane = row & 31;
-    int i = v / n1, j = v - i * n1;
-    int b0 = slice_base[S], b1 = slice_base[S + 1];
-    int dpb = diag_pb[row];
-    for (int b = b0; b < b1; b += 32) {
-        int pb = b + lane;
-        int col = colidx[pb];
-        int cv = col - off;
-        if (cv < 0 || cv >= nvc) continue;
-        if (col == row && pb != dpb) continue;          // ELL padding (zero block pointing at the diagonal)
-        int ip = cv / n1, jp = cv - ip * n1;
-        int di = ip - i, dj = jp - j;
-        if (di < -2 || di > 2 || dj < -2 || dj > 2) continue;
-        int slot = (di + 2) * 5 + (dj + 2);
-        const float *src = val + (long long)b * 9 + lane;
-        float *dst = out + (size_t)v * sv + (size_t)(slot * 9) * se;
-#pragma unroll
-        for (int c = 0; c < 9; c++) dst[(size_t)c * se] = src[c * 32];
-    }
-}
-// A_c = P^T A_f P, one thread per (coarse vertex, coarse stencil slot).  mask: frozen flags of the fine grid's
-// DOFs ([3 * nvf], level 0 only) -- frozen DOFs are left out of the coarse spaces.
-template <bool MASK>
-__global__ void __launch_bounds__(128) k_galerkin(const float *__restrict__ val_f, int n0f, int n1f, long long svf, long long sef, const int *__restrict__ mask,
-                                                  float *val_c, int n0c, int n1c, long long svc, long long sec)
-{
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int nvc = n0c * n1c;
-    if (t >= nvc * 25) return;
-    // element-major coarse level: consecutive threads = consecutive vertices of one slot; row-major: consecutive slots
-    int cv, slot;
-    if (svc == 1) { slot = t / nvc; cv = t - slot * nvc; } else { cv = t / 25; slot = t - cv * 25; }
-    int I = cv / n1c, J = cv - I * n1c;
-    int Ip = I + slot / 5 - 2, Jp = J + slot % 5 - 2;
-    float acc[9];
-#pragma unroll
-    for (int c = 0; c < 9; c++) acc[c] = 0.f;
-    if ((unsigned)Ip < (unsigned)n0c && (unsigned)Jp < (unsigned)n1c) {
-        for (int a = -1; a <= 1; a++) {
-            int i = 2 * I + a;
-            if ((unsigned)i >= (unsigned)n0f) continue;
-            float wi = pw1(a, I, n0c);
-            for (int b = -1; b <= 1; b++) {
-                int j = 2 * J + b;
-                if ((unsigned)j >= (unsigned)n1f) continue;
-                float wr = wi * pw1(b, J, n1c);
-                int fv = i * n1f + j;
-                for (int ap = -1; ap <= 1; ap++) {
-                    int ip = 2 * Ip + ap;
-                    int di = ip - i;
-                    if ((unsigned)ip >= (unsigned)n0f || di < -2 || di > 2) continue;
-                    float wip = wr * pw1(ap, Ip, n0c);
-                    for (int bp = -1; bp <= 1; bp++) {
-                        int jp = 2 * Jp + bp;
-                        int dj = jp - j;
-                        if ((unsigned)jp >= (unsigned)n1f || dj < -2 || dj > 2) continue;
-                        float w = wip * pw1(bp, Jp, n1c);
-                        const float *src = val_f + (size_t)fv * svf + (size_t)(((di + 2) * 5 + (dj + 2)) * 9) * sef;
-                        if (MASK) {
-                            int fc = ip * n1f + jp;
-                            float mr[3], mc[3];
-#pragma unroll
-                            for (int q = 0; q < 3; q++) { mr[q] = mask[3 * fv + q] ? 0.f : w; mc[q] = mask[3 * fc + q] ? 0.f : 1.f; }
-#pragma unroll
-                            for (int c = 0; c < 9; c++) acc[c] += mr[c / 3] * mc[c % 3] * __ldg(src + (size_t)c * sef);
-                        } else {
-#pragma unroll
-                            for (int c = 0; c < 9; c++) acc[c] += w * __ldg(src + (size_t)c * sef);
-                        }
-                    }
-                }
-            }
-        }
-    }
-    float *dst = val_c + (size_t)cv * svc + (size_t)(slot * 9) * sec;
-#pragma unroll
-    for (int c = 0; c < 9; c++) dst[(size_t)c * sec] = acc[c];
-}
 __device__ __forceinline__ void inv3_guarded(const float *a, float *inv)
 {
     double c00 = (double)a[4] * a[8] - (double)a[5] * a[7], c01 = (double)a[5] * a[6] - (double)a[3] * a[8], c02 = (double)a[3] * a[7] - (double)a[4] * a[6];
@@ -731,6 +644,9 @@ int mg_alloc(tsl_ctx *ctx)
     for (int l = 0; l < TSL_MG_MAX_LEVELS; l++) { pc[4 * l] = 0; pc[4 * l + 1] = -1; pc[4 * l + 2] = 0; pc[4 * l + 3] = -1; }
     CK(cudaMemcpy(mg.powc, pc.data(), sizeof(float) * pc.size(), cudaMemcpyHostToDevice));
     mg.setups = 0;
+    { const char *e = getenv("TSL_MG_TILED"); mg.tiled_galerkin = e ? atoi(e) : 1; }
+    CK(cudaFuncSetAttribute(k_galerkin_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSL_GAL_SMEM));
+    CK(cudaFuncSetAttribute(k_galerkin_sell_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSL_GAL_SMEM));
     return TSL_OK;
 }
 
@@ -783,20 +699,32 @@ int mg_setup(tsl_ctx *ctx)
     MgLevel &L0 = mg.lev[0];
     k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32m, L0.dinv);
     ctx->launches++;
-    if (mg.n_levels > 1) {
-        // the pattern is static: every slot this kernel writes is rewritten on each setup, the others stay zero
-        k_sell_to_stencil<<<GRID(L0.nv, 128), 128, 0, s>>>(c.offset, L0.nv, L0.n1, A.slice_base, A.colidx, A.val32m, A.diag_pb, L0.val, L0.sv, L0.se);
-        ctx->launches++;
-    }
+    // Galerkin products, tiled (tsl_mg_kernels.cuh): level 0 -> 1 straight from the sliced-ELL snapshot (no stencil copy of the fine
+    // level), the others from the level's own stencil layout; TSL_MG_TILED=0 falls back to the entrywise kernels
     for (int l = 0; l + 1 < mg.n_levels; l++) {
         MgLevel &F = mg.lev[l], &C = mg.lev[l + 1];
-        long long nt = 25LL * C.nv;
-        if (l == 0)
-            k_galerkin<true><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.sv, F.se, ctx->frozen + 3 * (size_t)c.offset, C.val, C.n0, C.n1, C.sv, C.se);
-        else
-            k_galerkin<false><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.sv, F.se, nullptr, C.val, C.n0, C.n1, C.sv, C.se);
+        if (mg.tiled_galerkin) {
+            dim3 grid(GRID(C.n1, TSL_TCJ), GRID(C.n0, TSL_TCI));
+            if (l == 0)
+                k_galerkin_sell_tiled<<<grid, 256, TSL_GAL_SMEM, s>>>(c.offset, F.n0, F.n1, A.slice_base, A.colidx, A.val32m, A.diag_pb,
+                                                                     ctx->frozen + 3 * (size_t)c.offset, C.val, C.n0, C.n1, C.sv, C.se);
+            else
+                k_galerkin_tiled<<<grid, 256, TSL_GAL_SMEM, s>>>(F.val, F.n0, F.n1, F.sv, F.se, C.val, C.n0, C.n1, C.sv, C.se);
+            ctx->launches++;
+        } else {
+            if (l == 0) {
+                k_sell_to_stencil<<<GRID(L0.nv, 128), 128, 0, s>>>(c.offset, L0.nv, L0.n1, A.slice_base, A.colidx, A.val32m, A.diag_pb, L0.val, L0.sv, L0.se);
+                ctx->launches++;
+            }
+            long long nt = 25LL * C.nv;
+            if (l == 0)
+                k_galerkin<true><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.sv, F.se, ctx->frozen + 3 * (size_t)c.offset, C.val, C.n0, C.n1, C.sv, C.se);
+            else
+                k_galerkin<false><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.sv, F.se, nullptr, C.val, C.n0, C.n1, C.sv, C.se);
+            ctx->launches++;
+        }
         k_dinv_stencil<<<GRID(C.nv, 256), 256, 0, s>>>(C.nv, C.sv, C.se, C.val, C.dinv);
-        ctx->launches += 2;
+        ctx->launches++;
     }
     // lambda_max(D^-1 A) per level: 10 power iterations from a fixed pseudo-random vector.  (Warm-starting from the
     // previous setup's vector was measured to UNDER-estimate after the contact set changes -- the old dominant mode
@@ -922,6 +850,12 @@ int mg_get_level(tsl_ctx *ctx, int level, int *dims, float *lmax, float *val_hos
     MgDev &mg = ctx->mg;
     if (level < 0 || level >= mg.n_levels) { ctx->err = "mg_get_level: no such level"; return TSL_ERR_INVALID; }
     MgLevel &L = mg.lev[level];
+    if (level == 0 && val_host && mg.n_levels > 1) {
+        // the stencil copy of the fine level is no longer part of the setup (the tiled Galerkin product reads the sliced-ELL matrix): made on demand
+        const ClothDev &c = ctx->cloths[0];
+        k_sell_to_stencil<<<GRID(L.nv, 128), 128, 0, ctx->stream>>>(c.offset, L.nv, L.n1, ctx->A.slice_base, ctx->A.colidx, ctx->A.val32m, ctx->A.diag_pb,
+                                                                   L.val, L.sv, L.se);
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     if (dims) { dims[0] = L.n0; dims[1] = L.n1; dims[2] = mg.n_levels; }
     if (lmax) CK(cudaMemcpy(lmax, mg.lmax + level, sizeof(float), cudaMemcpyDeviceToHost));

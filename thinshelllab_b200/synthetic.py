@@ -128,7 +128,7 @@ def strip_spec(R, M, rank, world, dx=0.002, dt=5e-3, seed=0, z0=0.0003, bump=0.2
     grid_n = max(132, 2 * int(np.ceil((0.5 * max((tnx - 1) * tdx, (tny - 1) * tdx) + 0.01) / 0.003)) + 2)
     return dict(R=R, M=M, rank=rank, world=world, rows=rows, ghost_lo=g_lo, ghost_hi=g_hi, dx=dx, dt=dt, cloth_pos=cpos, x_shift=xc,
                 table_size=Len, table_N=(tnx, tny, 2), table_offset=toff, grid_n=grid_n, k_contact=k_contact, mu=mu,
-                max_n_constraints=rows * (M + 1) + 16, n_tris_owned=None, own0=g_lo * (M + 1), own1=(rows - g_hi) * (M + 1),
+                max_n_constraints=rows * (M + 1) + 16, n_tris_owned=None, first_row_global=a, own0=g_lo * (M + 1), own1=(rows - g_hi) * (M + 1),
                 n_tris_global=2 * (G - 1) * M)
 
 
@@ -150,6 +150,6 @@ def strip_scene(R, M, rank, world, device="cuda:0", **kw):
     s.engine.prev_pos.copy_(s.engine.pos)
     s.engine.vel.zero_()
     s.engine.cloth_ref_angle[0].zero_()
-    s.engine.dist_init(rank, world, sp["ghost_lo"], sp["ghost_hi"])
+    s.engine.dist_init(rank, world, sp["ghost_lo"], sp["ghost_hi"], sp["first_row_global"])
     s.spec = sp
     return s
