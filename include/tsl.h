@@ -183,6 +183,19 @@ int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, c
  * (code/engine/analytic_grad_system.py:69-75).  Call after tsl_step_backward* of the same step (positions x_t are still bound). */
 int tsl_elastic_param_grad(tsl_ctx *ctx, const double *z_dev, double *d_mu_dev, double *d_lam_dev, double *out2_host);
 
+/* Cloth.compute_deri (code/engine/model_fold_offset.py:1083-1129) pushed up into BaseScene.d_kl / d_ka / d_kb (BaseScene.get_paramters_grad,
+ * code/engine/BaseScene.py:1513-1521): dF/dKl, dF/dKa, dF/dKb per vertex at the bound positions, [n_verts][3] f64 device (rows outside
+ * the cloth are zeroed); any of the three pointers may be NULL. */
+int tsl_cloth_param_deri(tsl_ctx *ctx, int cloth, double *d_kl_dev, double *d_ka_dev, double *d_kb_dev);
+/* Friction-coefficient gradient of one adjoint step (Scene.contact_energy_backprop_friction, code/task_scene/Scene_sliding.py:140-177, called
+ * from Grad.transfer_grad, code/engine/analytic_grad_system.py:150-151): sum over the constraints of the contact pairs [pair_begin, pair_end)
+ * of the current set, and over their free DOFs, of z * w1 * (k f1(|u|) T^T u) / mu.  z_dev [3 n_verts] = the adjoint solution of the step. */
+int tsl_friction_coef_grad(tsl_ctx *ctx, const double *z_dev, int pair_begin, int pair_end, double *out_host);
+/* Elastic.get_force of one tetrahedral body at the bound positions (code/engine/model_elastic_tactile.py:145-164,
+ * model_elastic_offset.py:187-210): F_f [body verts][3] f64 device = internal force + m g (what gather_force / check_early_stop read,
+ * code/engine/BaseScene.py:1542-1585). */
+int tsl_elastic_force(tsl_ctx *ctx, int body, double *Ff_dev);
+
 /* Kinematic boundary of a pad (code/engine/gripper_single.py): gripper.get_vert_pos + update_bound + the scene's pushup
  * (:79-83, 157-161; Scene_folding.action, code/task_scene/Scene_folding.py:213-224) for the n_bound driven vertices of the body at
  * v_offset: pos[v_offset + bound_idx[i]] = p + R F_x[bound_idx[i]].  bound_idx_dev [n_bound] i32, Fx_dev [body verts][3] f64 (device),

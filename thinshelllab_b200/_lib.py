@@ -69,6 +69,9 @@ SIGNATURES = {
     "tsl_step_backward": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _i, C.POINTER(SolveStatsC)]),
     "tsl_step_backward_ex": (_i, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _d, _d, _d, _i, C.POINTER(SolveStatsC)]),
     "tsl_elastic_param_grad": (_i, [_vp, _vp, _vp, _vp, _dp]),
+    "tsl_cloth_param_deri": (_i, [_vp, _i, _vp, _vp, _vp]),
+    "tsl_friction_coef_grad": (_i, [_vp, _vp, _i, _i, _dp]),
+    "tsl_elastic_force": (_i, [_vp, _i, _vp]),
     "tsl_gripper_apply": (_i, [_vp, _i, _i, _vp, _vp, _dp, C.POINTER(C.c_float)]),
     "tsl_gripper_gather": (_i, [_vp, _vp, _i, _i, _vp, _vp, C.POINTER(C.c_float), _d, _d, _dp]),
     "tsl_get_contact_blocks": (_i, [_vp, _ip, _vp, _vp, _vp]),

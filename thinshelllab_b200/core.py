@@ -140,7 +140,9 @@ class ShellEngine:
         self._ck(self.L.tsl_set_surfaces(self.ctx, _np_ptr(faces), faces.shape[0], _np_ptr(bodies), bodies.shape[0]))
 
     def add_contact_pair(self, surface_body, v_start, v_end, mu):
-        return self._ck(self.L.tsl_add_contact_pair(self.ctx, surface_body, v_start, v_end, mu))
+        pid = self._ck(self.L.tsl_add_contact_pair(self.ctx, surface_body, v_start, v_end, mu))
+        self.__dict__.setdefault("_pairs_registered", []).append(pid)
+        return pid
 
     def set_contact_mu(self, pair, mu):
         self._ck(self.L.tsl_set_contact_mu(self.ctx, pair, mu))
@@ -246,6 +248,29 @@ class ShellEngine:
         out = (C.c_double * 2)()
         self._ck(self.L.tsl_elastic_param_grad(self.ctx, _ptr(z), _ptr(d_mu), _ptr(d_lam), out))
         return d_mu, d_lam, ((out[0], out[1]) if z is not None else None)
+
+    def cloth_param_deri(self, cloth=0, kl=True, ka=True, kb=True):
+        """(d_kl, d_ka, d_kb) [n_verts, 3] CUDA tensors (None where not requested): Cloth.compute_deri at the bound positions"""
+        self._sync_stream()
+        out = [torch.empty((self.n_verts, 3), dtype=torch.float64, device=self.device) if want else None for want in (kl, ka, kb)]
+        self._ck(self.L.tsl_cloth_param_deri(self.ctx, int(cloth), _ptr(out[0]), _ptr(out[1]), _ptr(out[2])))
+        return tuple(out)
+
+    def friction_coef_grad(self, z, pair_begin=0, pair_end=None):
+        """one adjoint step's contribution to Grad.grad_friction_coef (Scene.contact_energy_backprop_friction)"""
+        self._sync_stream()
+        out = C.c_double()
+        n_pairs = len(getattr(self, "_pairs_registered", [])) if pair_end is None else pair_end
+        self._ck(self.L.tsl_friction_coef_grad(self.ctx, _ptr(z), int(pair_begin), int(n_pairs), C.byref(out)))
+        return out.value
+
+    def elastic_force(self, body):
+        """Elastic.get_force of tetrahedral body `body`: F_f [body verts, 3] CUDA tensor"""
+        self._sync_stream()
+        nv = self.tet_bodies[body][2]
+        F = torch.empty((nv, 3), dtype=torch.float64, device=self.device)
+        self._ck(self.L.tsl_elastic_force(self.ctx, int(body), _ptr(F)))
+        return F
 
     def gripper_apply(self, v_offset, bound_idx, F_x, pos3, rotmat32):
         """pos[v_offset + bound_idx] = pos3 + R F_x[bound_idx] (gripper.get_vert_pos + update_bound, gripper_single.py:79-83, 157-161)"""

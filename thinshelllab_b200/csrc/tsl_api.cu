@@ -1005,6 +1005,42 @@ int tsl_elastic_param_grad(tsl_ctx *ctx, const double *z_dev, double *d_mu_dev, 
     return TSL_OK;
 }
 
+int tsl_cloth_param_deri(tsl_ctx *ctx, int cloth, double *d_kl_dev, double *d_ka_dev, double *d_kb_dev)
+{
+    if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
+    REQUIRE(cloth >= 0 && cloth < (int)ctx->cloths.size(), "bad cloth id");
+    StreamScope scope_(ctx);
+    launch_cloth_deri(ctx, ctx->cloths[cloth], ctx->pos, d_kl_dev, d_ka_dev, d_kb_dev);
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+int tsl_friction_coef_grad(tsl_ctx *ctx, const double *z_dev, int pair_begin, int pair_end, double *out_host)
+{
+    if (!ctx || !ctx->finalized || !z_dev || !out_host) return TSL_ERR_INVALID;
+    REQUIRE(pair_begin >= 0 && pair_begin <= pair_end && pair_end <= (int)ctx->pairs.size(), "tsl_friction_coef_grad: bad pair range");
+    REQUIRE(ctx->pair_start.size() == ctx->pairs.size() + 1, "tsl_friction_coef_grad: no contact set (call after a step or tsl_contact_detect)");
+    StreamScope scope_(ctx);
+    int c0 = ctx->pair_start[pair_begin], c1 = ctx->pair_start[pair_end];
+    *out_host = 0.0;
+    if (c1 > c0) {
+        launch_friction_coef_grad(ctx, ctx->pos, z_dev, c0, c1, ctx->red_out + 2);
+        CK(cudaMemcpyAsync(ctx->red_host + 2, ctx->red_out + 2, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *out_host = ctx->red_host[2];
+    }
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+int tsl_elastic_force(tsl_ctx *ctx, int body, double *Ff_dev)
+{
+    if (!ctx || !ctx->finalized || !Ff_dev) return TSL_ERR_INVALID;
+    REQUIRE(body >= 0 && body < (int)ctx->tets.size(), "bad tet body id");
+    StreamScope scope_(ctx);
+    launch_elastic_force(ctx, body, ctx->pos, Ff_dev);
+    CK(cudaGetLastError());
+    return TSL_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- kinematic boundary (gripper)
 // gripper.get_vert_pos + update_bound + pushup (code/engine/gripper_single.py:79-83, 157-161; Scene_folding.action :213-224):
 // pos[v_offset + bound_idx[i]] = p + R F_x[bound_idx[i]], R in fp32 as the reference stores it (rotmat is an f32 field)

@@ -301,9 +301,10 @@ int contact_detect(tsl_ctx *ctx, const double *pos, const double *prev_pos)
         }
     }
     // Scene.contact_analysis: the registered pairs in order
+    ctx->pair_start.assign(1, 0);
     for (auto &p : ctx->pairs) {
         int n = p.v_end - p.v_start;
-        if (n <= 0) continue;
+        if (n <= 0) { ctx->pair_start.push_back(ctx->nc); continue; }
         size_t off = (size_t)p.body * nv;
         k_contact_flag<<<GRID(n, 128), 128, 0, st>>>(p.v_start, p.v_end, pos, prev_pos, ctx->proj_flag + off, ctx->proj_dir + off,
                                                      ctx->proj_idx + 3 * off, ctx->proj_w + 3 * off, ctx->cfg.eps_contact, ctx->cflag);
@@ -325,6 +326,7 @@ int contact_detect(tsl_ctx *ctx, const double *pos, const double *prev_pos)
             ctx->launches++;
         }
         ctx->nc += count;
+        ctx->pair_start.push_back(ctx->nc);
     }
     if (ctx->nc_dev) CK(cudaMemcpyAsync(ctx->nc_dev, &ctx->nc, sizeof(int), cudaMemcpyHostToDevice, st));   // pageable source: staged before return
     CK(cudaGetLastError());

@@ -178,6 +178,7 @@ struct tsl_ctx {
     int *faces = nullptr;                       // [tot_nf][3]
     std::vector<tsl::SurfaceBody> bodies;
     std::vector<tsl::ContactPair> pairs;
+    std::vector<int> pair_start;                 // [pairs + 1] first constraint of every pair in the current set (contact_detect)
     double *vn = nullptr;                       // [n_verts][3]
     int *proj_flag = nullptr, *proj_dir = nullptr, *proj_idx = nullptr;   // [n_bodies][n_verts]([3])
     double *proj_w = nullptr;

@@ -11,6 +11,9 @@ void launch_residual(tsl_ctx *ctx, const double *pos);
 void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kb);
 // into_clamped: the fp32 result goes to A.val32c (multigrid hierarchy / fallback operator) instead of A.val32
 void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model, bool into_clamped = false);
+void launch_cloth_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kl, double *d_ka, double *d_kb);
+void launch_friction_coef_grad(tsl_ctx *ctx, const double *pos, const double *z, int c0, int c1, double *out_dev);
+void launch_elastic_force(tsl_ctx *ctx, int body, const double *pos, double *Ff);
 void launch_tets_param_grad(tsl_ctx *ctx, const double *pos, const double *z, double *d_mu, double *d_lam, double *out2_dev);
 void launch_hessian_counting(tsl_ctx *ctx, const double *pos, const double *z, double *zf);
 void launch_axpy_pos(tsl_ctx *ctx, const double *x1, const double *p, double alpha, double *pos);

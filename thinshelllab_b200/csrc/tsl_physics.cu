@@ -991,6 +991,66 @@ void launch_residual(tsl_ctx *ctx, const double *pos)
     ctx->launches++;
     if (ctx->dist.on) launch_zero_ghost(ctx, ctx->F);      // ghost rows only saw part of their elements: the owner has them complete
 }
+// Cloth.compute_deri: d_kl / d_ka / d_kb = -(edge / area / bending gradient) / K on the cloth rows, zero elsewhere
+void launch_cloth_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kl, double *d_ka, double *d_kb)
+{
+    int n = ctx->cfg.n_verts;
+    double *dst[3] = { d_kl, d_ka, d_kb };
+    const int mask[3] = { 2, 4, 8 };
+    const double K[3] = { c.P.Kl, c.P.Ka, c.P.Kb };
+    for (int q = 0; q < 3; q++) {
+        if (!dst[q]) continue;
+        k_fill_zero<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(dst[q], 3LL * n);
+        k_residual_cloth<<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, dst[q], mask[q], -1.0 / K[q]);
+        ctx->launches += 2;
+    }
+}
+// Scene.contact_energy_backprop_friction (Scene_sliding.py:140-177): d(friction force)/d(mu) . z over the constraints [c0, c1)
+__global__ void __launch_bounds__(256) k_friction_coef_grad(ContactDev con, int c0, int c1, ContactParams cp, const double *__restrict__ pos,
+                                                            const double *__restrict__ z, const int *__restrict__ frozen, double *out)
+{
+    double s = 0;
+    for (int i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+        const int *idx = con.idx + 4 * i;
+        const double *w = con.w + 3 * i, *T = con.T + 6 * i, *dx0 = con.dx0 + 3 * i;
+        d3 x0 = ld3(pos, idx[0]), x1 = ld3(pos, idx[1]), x2 = ld3(pos, idx[2]), xv = ld3(pos, idx[3]);
+        d3 dx = xv - (w[0] * x0 + w[1] * x1 + w[2] * x2) - mk(dx0[0], dx0[1], dx0[2]);
+        double u[2] = { T[0] * dx.x + T[1] * dx.y + T[2] * dx.z, T[3] * dx.x + T[4] * dx.y + T[5] * dx.z };
+        double r = sqrt(u[0] * u[0] + u[1] * u[1]);
+        double kf = con.k[i] * fr_f1(cp, r);
+        double g1[3];
+        for (int q = 0; q < 3; q++) g1[q] = kf * (u[0] * T[q] + u[1] * T[3 + q]);
+        double w1[4] = { w[0], w[1], w[2], -1.0 };
+        for (int i1 = 0; i1 < 4; i1++)
+            for (int j1 = 0; j1 < 3; j1++)
+                if (!frozen[3 * idx[i1] + j1]) s += z[3 * idx[i1] + j1] * (w1[i1] * g1[j1] / con.mu[i]);
+    }
+    s = block_sum(s);
+    if (threadIdx.x == 0) *out = s;
+}
+void launch_friction_coef_grad(tsl_ctx *ctx, const double *pos, const double *z, int c0, int c1, double *out_dev)
+{
+    ContactParams cp = { ctx->cfg.k_contact, ctx->cfg.eps_contact, ctx->cfg.eps_v, ctx->cfg.dt };
+    k_friction_coef_grad<<<1, 256, 0, ctx->stream>>>(ctx->con, c0, c1, cp, pos, z, ctx->frozen, out_dev);   // one block: deterministic order
+    ctx->launches++;
+}
+// Elastic.get_force: F_f = -dE/dx + m g on the body's own vertices
+__global__ void k_body_gravity(int nv, int offset, const double *__restrict__ mass, d3 g, double *Ff)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nv) return;
+    double m = mass[offset + i];
+    Ff[3 * i] = m * g.x; Ff[3 * i + 1] = m * g.y; Ff[3 * i + 2] = m * g.z;
+}
+void launch_elastic_force(tsl_ctx *ctx, int body, const double *pos, double *Ff)
+{
+    const TetDev &t = ctx->tets[body];
+    d3 g = mk(ctx->h_tet_gravity[3 * body], ctx->h_tet_gravity[3 * body + 1], ctx->h_tet_gravity[3 * body + 2]);
+    k_body_gravity<<<GRID(t.nv, 128), 128, 0, ctx->stream>>>(t.nv, t.offset, ctx->mass, g, Ff);
+    // k_residual_tets scatters +dE/dx at global vertex ids: shift the destination so that the body's first vertex lands on row 0
+    k_residual_tets<<<GRID(t.nc, 128), 128, 0, ctx->stream>>>(t, pos, Ff - 3 * (size_t)t.offset, -1.0);
+    ctx->launches += 2;
+}
 void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kb)
 {   // Cloth.compute_deri_Kb: d_kb = -(bending gradient) / Kb
     int n = ctx->cfg.n_verts;

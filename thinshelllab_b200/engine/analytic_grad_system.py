@@ -51,10 +51,16 @@ class Grad:
 
     def transfer_grad(self, step, sys, f_contact=None, rel_tol=1e-10, max_iters=20000):
         pg_tm2 = self._pos_grad[step - 2] if step > 1 else None
+        # (:147-152) with count_friction_grad the step feeds grad_friction_coef INSTEAD of the stiffness gradients
+        kb_acc = self._grad_kb if (self.count_kb_grad and not self.count_friction_grad) else torch.zeros_like(self._grad_kb)
         self.last_solve = sys.engine.step_backward(
             self._pos_buffer[step], self._pos_buffer[step - 1], self._ref_angle_buffer[step - 1, 0],
             self._pos_grad[step], self._pos_grad[step - 1], pg_tm2, self._angleref_grad[step, 0], self._angleref_grad[step - 1, 0],
-            self._grad_kb, self._z, clamp=self.clamp, rel_tol=rel_tol, max_iters=max_iters)
+            kb_acc, self._z, clamp=self.clamp, rel_tol=rel_tol, max_iters=max_iters)
+        if self.count_friction_grad:
+            # Scene.contact_energy_backprop_friction (code/task_scene/Scene_sliding.py:140-177)
+            self.grad_friction_coef[None] = self.grad_friction_coef[None] + sys.engine.friction_coef_grad(self._z)
+            return self.last_solve
         if self.count_mu_lam_grad and sys.engine.tet_bodies:
             # Grad.get_parameters_grad (:69-75): grad_mu / grad_lam += sum over free DOFs of z d_mu / z d_lam
             _, _, (gm, gl) = sys.engine.elastic_param_grad(self._z)

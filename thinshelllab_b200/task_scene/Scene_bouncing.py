@@ -6,6 +6,7 @@ import numpy as np
 import torch
 
 from ..core import ShellEngine
+from ..engine.BaseScene import SceneCommon
 from ..fields import Scalar, TensorField
 from ..meshes import box_body
 
@@ -54,7 +55,7 @@ class _ClothView:
         return TensorField(torch.from_numpy(self._s.engine.cloth_topology(self._cid)[0]))
 
 
-class Scene:
+class Scene(SceneCommon):
     """reference: Scene(cloth_size=0.06); extra keyword arguments expose the constants the reference hard-codes in
     init_scene_parameters so the same class serves the synthetic sheet sizes of BASELINE.json."""
 
@@ -64,7 +65,7 @@ class Scene:
                  grid_h=0.003, grid_n=132, device="cuda:0"):
         cloth_M = cloth_N if cloth_M is None else cloth_M
         self.dt = self.h = dt
-        self.cloth_cnt, self.elastic_cnt = 1, 1
+        self.cloth_cnt, self.elastic_cnt, self.effector_cnt = 1, 1, 1
         self.cloth_N, self.cloth_M, self.cloth_size = cloth_N, cloth_M, cloth_size
         self.k_contact, self.eps_contact, self.eps_v = k_contact, eps_contact, eps_v
         self.max_n_constraints, self.damping = max_n_constraints, 1.0

@@ -13,6 +13,7 @@ import numpy as np
 import torch
 
 from ..core import ShellEngine
+from ..engine.BaseScene import SceneCommon
 from ..engine.gripper_single import gripper
 from ..fields import Scalar, TensorField
 from .Scene_bouncing import Body, _ClothView
@@ -41,7 +42,7 @@ class _ElasticView:
         return TensorField(self._s.engine.pos[self.offset:self.offset + self.n_verts])
 
 
-class Scene:
+class Scene(SceneCommon):
     FORMING = False                            # Scene_forming subclasses with True (15 x 7 strip, k_contact 20000)
 
     def __init__(self, cloth_size=0.06, device="cuda:0", *, state=None, max_newton=50):
