@@ -517,3 +517,38 @@ if __name__ == "__main__":
         gen_folding(tag="forming", forming=True)
     if "trajopt_folding" in what:
         gen_trajopt_folding()
+
+
+def gen_scene_states():
+    """initial states of the multi-pad task scenes (Scene_lifting, Scene_pick) as the reference builds them: Scene(); init_all(); reset().
+    No time stepping (seconds).  Pins thinshelllab_b200/engine/scene_builder.py."""
+    import importlib
+    for tag in ("lifting", "pick"):
+        mod = importlib.import_module(f"thinshelllab.task_scene.Scene_{tag}")
+        s = mod.Scene(cloth_size=0.06)
+        s.device = "cpu"; s.H.device = "cpu"
+        s.init_all()
+        s.reset()
+        out = dict(dt=s.dt, k_contact=s.k_contact, eps_contact=s.eps_contact, eps_v=s.eps_v, max_n_constraints=s.max_n_constraints,
+                   cloth_N=s.cloths[0].N, cloth_M=s.cloths[0].M, cloth_dx=s.cloths[0].dx, cloth_mass=s.cloths[0].mass, k_angle=s.cloths[0].k_angle[None],
+                   Kb=s.cloths[0].Kb[None], pos0=s.pos.to_numpy(), vel0=s.vel.to_numpy(), mass=s.mass.to_numpy(), frozen=s.frozen.to_numpy(),
+                   faces=s.faces.to_numpy(), ref_angle0=s.cloths[0].ref_angle.to_numpy(), border_flag=s.border_flag.to_numpy(), gravity=s.gravity.to_numpy(),
+                   cloth_gravity=s.cloths[0].gravity.to_numpy(), n_elastics=len(s.elastics), effector_cnt=s.effector_cnt,
+                   body_v=np.array([[b.v_start, b.v_end] for b in s.body_list]), body_f=np.array([[b.f_start, b.f_end] for b in s.body_list]),
+                   gripper_pos0=s.gripper.pos.to_numpy(), gripper_rot0=s.gripper.rot.to_numpy(), gripper_F_x=s.gripper.F_x.to_numpy(),
+                   gripper_bound_idx=s.gripper.bound_idx.to_numpy())
+        for j, el in enumerate(s.elastics):
+            out[f"el{j}_offset"], out[f"el{j}_nverts"] = el.offset, el.n_verts
+            out[f"el{j}_tets"] = el.F_vertices.to_numpy()
+            out[f"el{j}_F_B"], out[f"el{j}_F_W"] = el.F_B.to_numpy(), el.F_W.to_numpy()
+            out[f"el{j}_mu"], out[f"el{j}_lam"] = el.mu[None], el.lam[None]
+            out[f"el{j}_gravity"] = el.gravity.to_numpy()
+            out[f"el{j}_tactile"] = int(hasattr(el, "alpha"))
+            if hasattr(el, "alpha"):
+                out[f"el{j}_alpha"] = el.alpha[None]
+        np.savez_compressed(os.path.join(OUT, f"scene_state_{tag}.npz"), **out)
+        print("wrote scene_state_" + tag, out["pos0"].shape, flush=True)
+
+
+if __name__ == "__main__" and "scene_states" in sys.argv[1:]:
+    gen_scene_states()

@@ -47,3 +47,24 @@ def test_other_cloth_sizes_build():
         st = folding_state(cloth_size=size)
         assert st["pos0"].shape[0] == 64 + 162 + 276 and np.isfinite(st["pos0"]).all()
         assert abs(st["cloth_dx"] - size / 15) < 1e-18
+
+
+def test_lifting_state_matches_the_reference(golden_dir):
+    """Scene_lifting (flat cloth + free heavy box + three pads on three gripper parts): engine/scene_builder.lifting_state against the
+    arrays Scene(); init_all(); reset() left in the reference (tests/golden/scene_state_lifting.npz, oracle/gen_goldens.py scene_states)"""
+    from thinshelllab_b200.engine.scene_builder import lifting_state
+    g = np.load(os.path.join(golden_dir, "scene_state_lifting.npz"))
+    st = lifting_state(0.06)
+    for k in ("pos0", "vel0", "frozen", "gripper_pos0", "gripper_F_x", "gripper_bound_idx", "border_flag"):
+        assert np.array_equal(np.asarray(st[k]), g[k]), k
+    assert np.abs(st["mass"] - g["mass"]).max() <= 1e-14 * g["mass"].max()
+    assert float(st["k_contact"]) == float(g["k_contact"]) and np.array_equal(st["gravity"], g["cloth_gravity"])
+    assert len(st["elastics"]) == int(g["n_elastics"])
+    for j, el in enumerate(st["elastics"]):
+        assert el["offset"] == int(g[f"el{j}_offset"]) and el["kind"] == int(g[f"el{j}_tactile"])
+        assert np.array_equal(el["tets"], g[f"el{j}_tets"]) and np.array_equal(el["gravity"], g[f"el{j}_gravity"])
+        assert np.abs(el["F_B"] - g[f"el{j}_F_B"]).max() <= 1e-13 * np.abs(g[f"el{j}_F_B"]).max()
+        assert np.abs(el["F_W"] - g[f"el{j}_F_W"]).max() <= 1e-13 * g[f"el{j}_F_W"].max()
+        assert float(el["mu"]) == float(g[f"el{j}_mu"]) and float(el["lam"]) == float(g[f"el{j}_lam"])
+    nfc = int(g["body_f"][0][1])
+    assert np.array_equal(np.concatenate([g["faces"][:nfc]] + st["elastic_faces"]), g["faces"])

@@ -47,9 +47,9 @@ class _Renderer:
 def install():
     from .. import fields  # noqa: F401
     from ..agent import traj_opt_single
-    from ..engine import analytic_grad_single, analytic_grad_system, geometry, gripper_single, readfile
+    from ..engine import BaseScene, analytic_grad_single, analytic_grad_system, geometry, gripper_single, readfile
     from ..optimizer import optim
-    from ..task_scene import Scene_bouncing, Scene_folding, Scene_forming
+    from ..task_scene import Scene_bouncing, Scene_folding, Scene_forming, Scene_lifting
 
     # ---- third-party modules the scripts import at top level
     if not _have("taichi"):
@@ -76,6 +76,8 @@ def install():
         "thinshelllab.engine.readfile": readfile,
         "thinshelllab.task_scene.Scene_folding": Scene_folding,
         "thinshelllab.task_scene.Scene_forming": Scene_forming,
+        "thinshelllab.task_scene.Scene_lifting": Scene_lifting,
+        "thinshelllab.engine.BaseScene": BaseScene,
         "thinshelllab.agent.traj_opt_single": traj_opt_single,
         "thinshelllab.optimizer.optim": optim,
     }

@@ -65,6 +65,25 @@ class Grad:
         T = self.tot_timestep
         self._pos_grad[T - 1, c.offset:c.offset + c.NV] = 2.0 * (self._pos_buffer[T - 1, c.offset:c.offset + c.NV] - t)
 
+    def get_loss_lift(self, sys):
+        """:303-312: d/dx of the squared distance of the carried box (elastics[0]) from its first-frame shape shifted by (-0.012, -0.012, 0)"""
+        b = sys.elastics[0]
+        T = self.tot_timestep
+        d = self._pos_buffer[T - 1, b.offset:b.offset + b.n_verts] - self._pos_buffer[0, b.offset:b.offset + b.n_verts]
+        d[:, 0] += 0.012; d[:, 1] += 0.012
+        self._pos_grad[T - 1, b.offset:b.offset + b.n_verts] = d
+
+    def apply_action_limit_grad(self, traj, max_dist):
+        """:504-516: penalty gradient on steps whose pose increment exceeds the agent's max_moving_dist"""
+        tr = traj.traj.to_numpy()
+        for step in range(1, self.tot_timestep):
+            for j in range(self.n_part):
+                dist = traj.calculate_dist(step, max_dist, j)
+                if dist > traj.max_moving_dist:
+                    d = tr[step, j] - tr[step - 1, j]
+                    self._gripper_grad[step, j, :3] += d[:3] * (dist - traj.max_moving_dist) * 10000000
+                    self._gripper_grad[step, j, 3:] += d[3:] * (dist - traj.max_moving_dist) * 100000
+
     def transfer_grad(self, step, sys, f_contact=None, rel_tol=1e-10, max_iters=20000):
         pg_tm2 = self._pos_grad[step - 2] if step > 1 else None
         self.last_solve = sys.engine.step_backward_ex(

@@ -135,3 +135,72 @@ def folding_state(cloth_size=0.06, forming=False, Kb=100.0):
     pad_pos = (x, 0.0, 2 * r + (0.00785 if forming else 0.0079))
     return pad_scene_state(cloth_size=cloth_size, cloth_N=N, cloth_M=M, cloth_pos=cpos, k_contact=20000.0 if forming else 10000.0, Kb=Kb,
                            k_angle=3.14 if forming else 0.5, pad_pos=pad_pos)
+
+
+# ------------------------------------------------------------------------------------------------ general one-cloth / many-bodies scenes
+def multi_body_state(*, cloth_N, cloth_M, cloth_size, cloth_pos, elastics, pad_poses, dt=5e-3, k_contact, eps_contact=0.0004, eps_v=0.01,
+                     max_n_constraints=10000, rho=40.0, Kb=100.0, k_angle=3.14, mu=1.0, cloth_gravity=(0.0, 0.0, 0.0), pinned_vertices=(),
+                     init_ref_angle=False, mu_per_elastic=None):
+    """state of a scene with one cloth and a list of elastic bodies (BaseScene.__init__ + init_objects + init + init_property +
+    set_frozen_kernel of Scene_lifting / Scene_pick).  elastics: list of dicts
+        dict(kind="box", pos, tets, faces, mass, mu, lam, gravity, frozen=True/False)
+        dict(kind="tactile", body=TactileBody (already .init()-ed), gravity)            -- driven by gripper part = its rank among the pads
+    pad_poses [n_pads][3]: gripper.init positions."""
+    dx = cloth_size / cloth_N
+    NVc = (cloth_N + 1) * (cloth_M + 1)
+    pos, mass, frozen = [np.asarray(cloth_pos, np.float64)], [np.full(NVc, rho * dx * dx)], [np.zeros((NVc, 3), np.int32)]
+    for v in pinned_vertices:
+        frozen[0][v] = 1
+    off = NVc
+    els, faces = [], []
+    for el in elastics:
+        if el["kind"] == "box":
+            p, tets, f, m = el["pos"], el["tets"], el["faces"], el["mass"]
+            B, W = tet_rest_np(p, tets)
+            fz = np.full((p.shape[0], 3), 1 if el.get("frozen", False) else 0, np.int32)
+            rec = dict(kind=0, offset=off, nverts=p.shape[0], tets=np.asarray(tets, np.int32), F_B=B, F_W=W, mu=el["mu"], lam=el["lam"], alpha=0.0,
+                       gravity=np.asarray(el["gravity"], np.float64), rest=p.copy())
+        else:
+            b = el["body"]
+            p, f, m = b.F_x, b.f2v, b.F_m
+            fz = np.zeros((b.n_verts, 3), np.int32)
+            fz[b.bottom | b.inner_circle] = 1
+            rec = dict(kind=1, offset=off, nverts=b.n_verts, tets=b.tets, F_B=b.F_B, F_W=b.F_W, mu=b.mu, lam=b.lam, alpha=b.alpha,
+                       gravity=np.asarray(el["gravity"], np.float64), bound_idx=np.nonzero(b.bottom | b.inner_circle)[0].astype(np.int32))
+        pos.append(p); mass.append(m); frozen.append(fz); faces.append(np.asarray(f, np.int32) + off)
+        els.append(rec)
+        off += rec["nverts"]
+    pads = [r for r in els if r["kind"] == 1]
+    pos0 = np.concatenate(pos)
+    st = dict(dt=dt, k_contact=float(k_contact), eps_contact=eps_contact, eps_v=eps_v, mu=mu, Kb=Kb, k_angle=k_angle, cloth_N=cloth_N, cloth_M=cloth_M,
+              cloth_dx=dx, cloth_mass=rho * dx * dx, cloth_size=cloth_size, max_n_constraints=max_n_constraints, pos0=pos0, vel0=np.zeros_like(pos0),
+              mass=np.concatenate(mass), frozen=np.concatenate(frozen).reshape(-1), border_flag=np.zeros(pos0.shape[0], np.int32),
+              gravity=np.asarray(cloth_gravity, np.float64), ref_angle0=np.zeros((2 * cloth_N * cloth_M, 3)), init_ref_angle=bool(init_ref_angle),
+              elastics=els, elastic_faces=faces, mu_per_elastic=mu_per_elastic,
+              gripper_pos0=np.asarray(pad_poses, np.float64), gripper_rot0=np.tile(np.array([1.0, 0.0, 0.0, 0.0]), (len(pads), 1)),
+              gripper_F_x=np.stack([pos0[r["offset"]:r["offset"] + r["nverts"]] - np.asarray(pad_poses[k], np.float64) for k, r in enumerate(pads)]),
+              gripper_bound_idx=pads[0]["bound_idx"] if pads else np.zeros(0, np.int32))
+    return st
+
+
+def tet_rest_np(rest, tets):
+    """Elastic.init_pos: B = Ds^-1, W = |det Ds| / 6 of the rest positions"""
+    tets = np.asarray(tets)
+    D = np.stack([rest[tets[:, i]] - rest[tets[:, 3]] for i in range(3)], -1)
+    return np.linalg.inv(D), np.abs(np.linalg.det(D)) / 6
+
+
+def lifting_state(cloth_size=0.06, Kb=100.0):
+    """Scene_lifting (code/task_scene/Scene_lifting.py:33-101, 136-151): a flat 15 x 15 cloth carrying a small heavy neo-Hookean box (free,
+    under gravity), one pad above and two below, each on its own gripper part; cloth and pads carry no gravity; k_contact 500"""
+    N = 15
+    dx = cloth_size / N
+    cpos = cloth_positions_flat(N, N, dx, (-0.03, -0.03, 0.0))
+    bpos, btets, bfaces, bmass = box_body(0.007, 5, 5, 5, (-0.025, -0.005, 0.0003), density=20000.0)
+    poses = [(0.01, 0.0, 0.0079), (0.0, -0.015, -0.0079), (0.0, 0.015, -0.0079)]
+    flips = [True, False, False]
+    els = [dict(kind="box", pos=bpos, tets=btets, faces=bfaces, mass=bmass, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, -9.8), frozen=False)]
+    for p, fl in zip(poses, flips):
+        els.append(dict(kind="tactile", body=TactileBody(0.015 / 0.03).init(p, fl), gravity=(0.0, 0.0, 0.0)))
+    return multi_body_state(cloth_N=N, cloth_M=N, cloth_size=cloth_size, cloth_pos=cpos, elastics=els, pad_poses=poses, k_contact=500.0, Kb=Kb,
+                            k_angle=3.14)

@@ -1,0 +1,110 @@
+"""One cloth + a list of elastic bodies (frozen or free boxes, tactile pads on gripper parts): the layout shared by the reference's
+Scene_lifting / Scene_pick / Scene_balancing / Scene_interact (code/task_scene/Scene_*.py).  The scene arrays come from
+engine/scene_builder.multi_body_state; contacts go both ways between the cloth and every elastic body (contact_analysis of those
+scenes), so constraint triangles move and the general contact path of libtsl is used."""
+import numpy as np
+import torch
+
+from ..core import ShellEngine
+from ..engine.BaseScene import SceneCommon
+from ..engine.gripper_single import gripper
+from ..fields import Scalar, TensorField
+from .Scene_bouncing import Body, _ClothView
+from .Scene_folding import _ElasticView
+
+
+class MultiBodyScene(SceneCommon):
+    max_newton = 50
+
+    def _build(self, g, device="cuda:0"):
+        self.dt = self.h = float(g["dt"])
+        els = g["elastics"]
+        pads = [r for r in els if r["kind"] == 1]
+        self.cloth_cnt, self.elastic_cnt = 1, len(els)
+        self.effector_cnt = self.elastic_cnt                       # BaseScene.__init__: effector_cnt defaults to elastic_cnt
+        self.k_contact, self.eps_contact, self.eps_v = float(g["k_contact"]), float(g["eps_contact"]), float(g["eps_v"])
+        self.max_n_constraints, self.damping = int(g["max_n_constraints"]), 1.0
+        N, M, dx = int(g["cloth_N"]), int(g["cloth_M"]), float(g["cloth_dx"])
+        self.cloth_N, self.cloth_M = N, M
+        pos0 = np.asarray(g["pos0"], np.float64)
+        self.tot_NV = pos0.shape[0]
+        gravity = tuple(float(v) for v in g["gravity"])            # the cloth's gravity; bodies carry their own
+        e = self.engine = ShellEngine(self.tot_NV, self.dt, k_contact=self.k_contact, eps_contact=self.eps_contact, eps_v=self.eps_v,
+                                      damping=self.damping, gravity=gravity, max_n_constraints=self.max_n_constraints, device=device)
+        rho = float(g["cloth_mass"]) / (dx * dx)
+        cid = e.add_cloth(N, M, 0, dx, rho, Kb=float(g["Kb"]), k_angle=float(g["k_angle"]))
+        self.cloths = [_ClothView(self, cid, N, M, dx, 0, rho, Kb=float(g["Kb"]), k_angle=float(g["k_angle"]))]
+        self.cloths[0].body_idx = 0
+        self.elastics = []
+        for j, r in enumerate(els):
+            bid = e.add_tets(int(r["kind"]), int(r["offset"]), int(r["nverts"]), r["tets"], r["F_B"], r["F_W"], float(r["mu"]), float(r["lam"]),
+                             float(r["alpha"]), r["gravity"])
+            v = _ElasticView(self, bid, int(r["offset"]), int(r["nverts"]), float(r["mu"]), float(r["lam"]))
+            v.body_idx = 1 + j
+            v.rest = r.get("rest")
+            self.elastics.append(v)
+        f2v = e.cloth_topology(cid)[0]
+        self.faces = np.ascontiguousarray(np.concatenate([f2v] + list(g["elastic_faces"])), np.int32)
+        self.tot_NF = self.faces.shape[0]
+        self.body_list, f0 = [Body(0, self.cloths[0].NV, 0, f2v.shape[0])], f2v.shape[0]
+        for r, fa in zip(els, g["elastic_faces"]):
+            self.body_list.append(Body(int(r["offset"]), int(r["offset"]) + int(r["nverts"]), f0, f0 + fa.shape[0]))
+            f0 += fa.shape[0]
+        e.set_surfaces(self.faces, [[b.v_start, b.v_end, b.f_start, b.f_end] for b in self.body_list])
+        # contact_analysis: for every elastic j: cloth surface vs its vertices, its surface vs the cloth vertices
+        self.mu_cloth_elastic = Scalar(float(g["mu"]), self._set_mu)
+        mu_fixed = g.get("mu_per_elastic") if hasattr(g, "get") else None
+        self._pairs = []
+        for j, el in enumerate(self.elastics):
+            fixed = None if mu_fixed is None else mu_fixed[j]
+            mu = self.mu_cloth_elastic[None] if fixed is None else fixed
+            self._pairs.append((e.add_contact_pair(0, el.offset, el.offset + el.n_verts, mu), fixed))
+            self._pairs.append((e.add_contact_pair(el.body_idx, 0, self.cloths[0].NV, mu), fixed))
+        e.mass.copy_(torch.from_numpy(np.asarray(g["mass"], np.float64)))
+        e.frozen.copy_(torch.from_numpy(np.asarray(g["frozen"], np.int32)))
+        self._pos0, self._vel0 = pos0, np.asarray(g["vel0"], np.float64)
+        self._ref0 = np.asarray(g["ref_angle0"], np.float64)
+        self._gpos0 = np.asarray(g["gripper_pos0"], np.float64)
+        self.gripper = gripper(self, [int(r["offset"]) for r in pads], g["gripper_F_x"], g["gripper_bound_idx"], self._gpos0)
+        self.gravity = np.array([0.0, 0.0, -9.8])
+        e.finalize()
+        if bool(g["init_ref_angle"]):
+            e.pos.copy_(torch.from_numpy(self._pos0)); e.prev_pos.copy_(e.pos)
+            e.cloth_ref_angle[0].zero_()
+            e.update_ref_angle(0)
+            self._ref0 = e.cloth_ref_angle[0].cpu().numpy().copy()
+        self.reset()
+
+    def _set_mu(self, v):
+        for p, fixed in getattr(self, "_pairs", []):
+            if fixed is None:
+                self.engine.set_contact_mu(p, v)
+
+    def _effectors(self):
+        pads = [el for el in self.elastics if el._bid >= 0 and self.engine.tet_bodies[el._bid][0] == 1]
+        return [(el._bid, self.gripper._bound_idx) for el in pads]
+
+    # ---- reference API
+    def init_all(self):
+        pass
+
+    def reset(self):
+        e = self.engine
+        e.pos.copy_(torch.from_numpy(self._pos0)); e.prev_pos.copy_(e.pos)
+        e.vel.copy_(torch.from_numpy(self._vel0))
+        e.cloth_ref_angle[0].copy_(torch.from_numpy(self._ref0))
+        self.gripper.init(self, self._gpos0)
+        e.reset_contact_state()
+
+    def action(self, step, delta_pos, delta_rot):
+        self.gripper.step_simple(delta_pos, delta_rot)
+        self.gripper.update_bound(self)
+
+    def time_step(self, f_contact=None, frame_idx=0, force_stick=True, tol=1e-7):
+        self.last_stats = self.engine.step_forward(self.max_newton, tol)
+        return self.last_stats
+
+    pos = property(lambda self: TensorField(self.engine.pos))
+    vel = property(lambda self: TensorField(self.engine.vel))
+    mass = property(lambda self: TensorField(self.engine.mass))
+    frozen = property(lambda self: TensorField(self.engine.frozen))
