@@ -87,6 +87,7 @@ def test_lifting_scene_state_rollout_and_adjoint(golden_dir):
         tp, tm = tr.copy(), tr.copy()
         tp[T - 1, part, comp] += h; tm[T - 1, part, comp] -= h
         fd = (_rollout(s, tp)[0] - _rollout(s, tm)[0]) / (2 * h)
-        an = gg[T - 1, part, comp]
-        print(f"Scene_lifting dL/dpose[{T - 1}, part {part}, {comp}]: adjoint {an:.6e}  finite difference {fd:.6e}")
-        assert abs(an - fd) <= 0.05 * max(abs(fd), abs(an)) + 1e-9, (part, comp, an, fd)
+        # gripper.gather_grad returns the MEAN over the driven vertices (d_pos /= n_bound, gripper_single.py:146-147): dL/dpose = n_bound x that
+        an = gg[T - 1, part, comp] * s.gripper.n_bound
+        print(f"Scene_lifting dL/dpose[{T - 1}, part {part}, {comp}]: adjoint x n_bound {an:.6e}  finite difference {fd:.6e}")
+        assert abs(an - fd) <= 0.01 * max(abs(fd), abs(an)) + 1e-9, (part, comp, an, fd)
