@@ -130,3 +130,47 @@ def test_unmodified_folding_script_if_present(tmp_path):
     assert len(rewards) == len(gold["total_reward"])
     for mine, ref in zip(rewards, gold["total_reward"]):
         assert abs(mine - ref) <= 1e-5 * max(abs(ref), 1e-3), (rewards, gold["total_reward"])
+
+
+def _run_script(name, tmp_path, extra):
+    script = os.path.join(ROOT, "baseline", "_ref", name)
+    if not os.path.exists(script):
+        pytest.skip("the reference script is not part of this repository (git-ignored copy absent)")
+    env = dict(os.environ, TSL_WORKDIR=str(tmp_path))
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "run_reference_script.py"), script] + extra,
+                         capture_output=True, text=True, env=env, timeout=1200)
+    assert out.returncode == 0, out.stderr[-3000:]
+    last = [ln for ln in out.stdout.splitlines() if ln.startswith("total_reward:")][-1]
+    return [float(x) for x in re.findall(r"(-?\d+\.\d+(?:e[-+]?\d+)?)", last.replace("np.float64(", ""))]
+
+
+def test_unmodified_forming_script_if_present(tmp_path):
+    """the reference's own training/trajopt_forming.py, unedited, on this engine: Scene_forming built by the product, get_loss_push,
+    trajectory adjoint, Adam step -- two optimisation iterations towards a target 1 mm below the initial strip"""
+    import numpy as np
+    from thinshelllab_b200.engine.scene_builder import folding_state
+    st = folding_state(cloth_size=0.1, forming=True)
+    target = st["pos0"][:16 * 8].copy()
+    target[:, 2] -= 1e-3
+    tpath = str(tmp_path / "target.npy")
+    np.save(tpath, target)
+    rewards = _run_script("trajopt_forming.py", tmp_path, ["--l", "0", "--r", "1", "--iter", "2", "--tot_step", "3", "--target_dir", tpath, "--lr", "2e-5"])
+    assert len(rewards) == 2 and all(np.isfinite(rewards)) and rewards[0] < 0
+    assert rewards[1] > rewards[0]                      # one (small: Adam's first step is lr x sign) step along the adjoint gradient moves the strip towards the target
+
+
+def test_unmodified_lifting_script_if_present(tmp_path):
+    """training/trajopt_lifting.py, unedited: Scene_lifting (free box, three pads on three gripper parts), get_loss_lift,
+    apply_action_limit_grad"""
+    import numpy as np
+    rewards = _run_script("trajopt_lifting.py", tmp_path, ["--l", "0", "--r", "1", "--iter", "2", "--tot_step", "3"])
+    assert len(rewards) == 2 and all(np.isfinite(rewards)) and rewards[0] < 0
+
+
+def test_unmodified_pick_fold_script_if_present(tmp_path):
+    """training/trajopt_pick_fold.py, unedited: Scene_pick (arched frozen table with friction 0.1, two pads on two gripper parts, bending
+    plasticity), agent.init_traj_pick_fold, compute_reward_pick_fold, get_loss_pick_fold (rest-angle seeds), the adjoint of frames
+    tot_step-1 .. 9 and apply_action_limit_grad"""
+    import numpy as np
+    rewards = _run_script("trajopt_pick_fold.py", tmp_path, ["--l", "0", "--r", "1", "--iter", "2", "--tot_step", "11", "--render", "1000"])
+    assert len(rewards) == 2 and all(np.isfinite(rewards))

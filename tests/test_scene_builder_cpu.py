@@ -49,12 +49,14 @@ def test_other_cloth_sizes_build():
         assert abs(st["cloth_dx"] - size / 15) < 1e-18
 
 
-def test_lifting_state_matches_the_reference(golden_dir):
-    """Scene_lifting (flat cloth + free heavy box + three pads on three gripper parts): engine/scene_builder.lifting_state against the
-    arrays Scene(); init_all(); reset() left in the reference (tests/golden/scene_state_lifting.npz, oracle/gen_goldens.py scene_states)"""
-    from thinshelllab_b200.engine.scene_builder import lifting_state
-    g = np.load(os.path.join(golden_dir, "scene_state_lifting.npz"))
-    st = lifting_state(0.06)
+@pytest.mark.parametrize("tag", ["lifting", "pick"])
+def test_multi_body_state_matches_the_reference(golden_dir, tag):
+    """Scene_lifting (flat cloth + free heavy box + three pads on three gripper parts) and Scene_pick (cloth on an arched frozen table +
+    two pads on two parts): engine/scene_builder.{lifting,pick}_state against the arrays Scene(); init_all(); reset() left in the
+    reference (tests/golden/scene_state_{lifting,pick}.npz, oracle/gen_goldens.py scene_states)"""
+    from thinshelllab_b200.engine import scene_builder
+    g = np.load(os.path.join(golden_dir, f"scene_state_{tag}.npz"))
+    st = getattr(scene_builder, f"{tag}_state")(0.06)
     for k in ("pos0", "vel0", "frozen", "gripper_pos0", "gripper_F_x", "gripper_bound_idx", "border_flag"):
         assert np.array_equal(np.asarray(st[k]), g[k]), k
     assert np.abs(st["mass"] - g["mass"]).max() <= 1e-14 * g["mass"].max()

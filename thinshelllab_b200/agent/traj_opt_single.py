@@ -32,6 +32,17 @@ class agent_trajopt:
                 if w < 1.0:
                     self._traj[i, j] = self._traj[i - 1, j] + d * w
 
+    def init_traj_pick_fold(self):
+        """:62-73: both pads press down 0.6 mm per frame for 8 frames, then hold"""
+        for i in range(min(8, self.tot_timestep)):
+            self._traj[i, 0, 2] = -0.0006 * i
+            self._traj[i, 1, 2] = -0.0006 * i
+            self._traj[i, 0, 0] = self._traj[i - 1, 0, 0]
+            self._traj[i, 1, 0] = self._traj[i - 1, 1, 0]
+        for i in range(8, min(50, self.tot_timestep)):
+            self._traj[i, :2, 2] = self._traj[i - 1, :2, 2]
+            self._traj[i, :2, 0] = self._traj[i - 1, :2, 0]
+
     def get_action(self, step):
         d = self._traj[step] - self._traj[step - 1]
         self._delta_pos.copy_(d[:, :3])

@@ -49,7 +49,7 @@ def install():
     from ..agent import traj_opt_single
     from ..engine import BaseScene, analytic_grad_single, analytic_grad_system, geometry, gripper_single, readfile
     from ..optimizer import optim
-    from ..task_scene import Scene_bouncing, Scene_folding, Scene_forming, Scene_lifting
+    from ..task_scene import Scene_bouncing, Scene_folding, Scene_forming, Scene_lifting, Scene_pick
 
     # ---- third-party modules the scripts import at top level
     if not _have("taichi"):
@@ -77,6 +77,7 @@ def install():
         "thinshelllab.task_scene.Scene_folding": Scene_folding,
         "thinshelllab.task_scene.Scene_forming": Scene_forming,
         "thinshelllab.task_scene.Scene_lifting": Scene_lifting,
+        "thinshelllab.task_scene.Scene_pick": Scene_pick,
         "thinshelllab.engine.BaseScene": BaseScene,
         "thinshelllab.agent.traj_opt_single": traj_opt_single,
         "thinshelllab.optimizer.optim": optim,

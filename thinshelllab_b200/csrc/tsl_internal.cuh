@@ -111,6 +111,11 @@ struct MgDev {
     int tiled_galerkin = 1;                // Galerkin products by shared-memory tiles (TSL_MG_TILED=0: one thread per coarse entry)
     int pair_threads = 1;                  // element-major levels: 2 threads per vertex (TSL_MG_PAIR=0: one)
     int tail_level = -1;                   // first level of the fused single-block tail of the V-cycle (-1: none)
+    // side streams of the hierarchy build: the eigenvalue iteration of level l only needs that level's operator, so it runs beside
+    // the Galerkin chain that is still producing the coarser levels (TSL_MG_FORK=0: everything on the context's stream)
+    int fork = 1;
+    cudaStream_t side[TSL_MG_MAX_LEVELS] = {};
+    cudaEvent_t ev_ready[TSL_MG_MAX_LEVELS] = {}, ev_done[TSL_MG_MAX_LEVELS] = {};
     int degree = 2, coarse_degree = 8;
     float ratio = 8.f, coarse_ratio = 200.f, safety = 1.2f;
 };

@@ -645,6 +645,13 @@ int mg_alloc(tsl_ctx *ctx)
     CK(cudaMemcpy(mg.powc, pc.data(), sizeof(float) * pc.size(), cudaMemcpyHostToDevice));
     mg.setups = 0;
     { const char *e = getenv("TSL_MG_TILED"); mg.tiled_galerkin = e ? atoi(e) : 1; }
+    { const char *e = getenv("TSL_MG_FORK"); mg.fork = e ? atoi(e) : 1; }
+    if (mg.fork)
+        for (int l = 0; l < mg.n_levels; l++) {
+            CK(cudaStreamCreateWithFlags(&mg.side[l], cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&mg.ev_ready[l], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&mg.ev_done[l], cudaEventDisableTiming));
+        }
     CK(cudaFuncSetAttribute(k_galerkin_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSL_GAL_SMEM));
     CK(cudaFuncSetAttribute(k_galerkin_sell_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSL_GAL_SMEM));
     return TSL_OK;
@@ -659,6 +666,12 @@ void mg_free(tsl_ctx *ctx)
         for (int q = 0; q < 2; q++) { cudaFree(L.x[q]); cudaFree(L.pv[q]); }
     }
     cudaFree(mg.coef); cudaFree(mg.powc); cudaFree(mg.pow_acc); cudaFree(mg.lmax);
+    for (int l = 0; l < TSL_MG_MAX_LEVELS; l++) {
+        if (mg.side[l]) cudaStreamDestroy(mg.side[l]);
+        if (mg.ev_ready[l]) cudaEventDestroy(mg.ev_ready[l]);
+        if (mg.ev_done[l]) cudaEventDestroy(mg.ev_done[l]);
+        mg.side[l] = nullptr; mg.ev_ready[l] = mg.ev_done[l] = nullptr;
+    }
     mg.n_levels = 0;
 }
 
@@ -699,6 +712,9 @@ int mg_setup(tsl_ctx *ctx)
     MgLevel &L0 = mg.lev[0];
     k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32m, L0.dinv);
     ctx->launches++;
+    const bool fork = mg.fork && mg.side[0];
+    CK(cudaMemsetAsync(mg.pow_acc, 0, sizeof(double) * TSL_MG_MAX_LEVELS * 16, s));
+    if (fork) CK(cudaEventRecord(mg.ev_ready[0], s));
     // Galerkin products, tiled (tsl_mg_kernels.cuh): level 0 -> 1 straight from the sliced-ELL snapshot (no stencil copy of the fine
     // level), the others from the level's own stencil layout; TSL_MG_TILED=0 falls back to the entrywise kernels
     for (int l = 0; l + 1 < mg.n_levels; l++) {
@@ -725,29 +741,36 @@ int mg_setup(tsl_ctx *ctx)
         }
         k_dinv_stencil<<<GRID(C.nv, 256), 256, 0, s>>>(C.nv, C.sv, C.se, C.val, C.dinv);
         ctx->launches++;
+        if (fork) CK(cudaEventRecord(mg.ev_ready[l + 1], s));
     }
     // lambda_max(D^-1 A) per level: 10 power iterations from a fixed pseudo-random vector.  (Warm-starting from the
     // previous setup's vector was measured to UNDER-estimate after the contact set changes -- the old dominant mode
     // has almost no overlap with the new one -- and an under-estimate is what the Chebyshev smoother cannot tolerate.)
-    CK(cudaMemsetAsync(mg.pow_acc, 0, sizeof(double) * TSL_MG_MAX_LEVELS * 16, s));
+    // The iteration of level l runs on its own side stream as soon as that level's operator exists (works the same inside a stream
+    // capture: the event edges become graph dependencies), so the latency-bound small levels and the bandwidth-bound fine level hide
+    // behind the Galerkin chain.
     const int its = 10;
+    int extra_slot = -1;
     for (int l = 0; l < mg.n_levels; l++) {
         MgLevel &L = mg.lev[l];
-        k_fill_hash<<<GRID(3 * L.nrows, 256), 256, 0, s>>>(3 * L.nrows, L.pv[0], 0x9e3779b9u * (l + 1));
+        cudaStream_t q = fork ? mg.side[l] : s;
+        if (fork) CK(cudaStreamWaitEvent(q, mg.ev_ready[l], 0));
+        ctx->stream = q;                                   // launch_step launches on the context's stream
+        k_fill_hash<<<GRID(3 * L.nrows, 256), 256, 0, q>>>(3 * L.nrows, L.pv[0], 0x9e3779b9u * (l + 1));
         ctx->launches++;
         for (int k = 0; k < its; k++)
             launch_step(ctx, l, nullptr, L.pv[k & 1], L.pv[(k & 1) ^ 1], nullptr, mg.powc + 4 * l + 2, mg.pow_acc + 16 * l + k, 2);
-    }
-    int extra_slot = -1;
-    if (!ctx->tets.empty() && mg.n_levels < TSL_MG_MAX_LEVELS && ctx->n_solve > c.offset + c.NV) {
-        // the sliced-ELL matrix has no cloth <-> solid blocks (contacts live in the side buffer), so the iteration stays on the solids
-        extra_slot = TSL_MG_MAX_LEVELS - 1;
-        MgLevel &L = mg.lev[0];
-        k_fill_hash<<<GRID(3 * L.nrows, 256), 256, 0, s>>>(3 * L.nrows, L.pv[0], 0x51ed270bu);
-        CK(cudaMemsetAsync(L.pv[0] + 3 * (size_t)c.offset, 0, sizeof(float) * 3 * (size_t)c.NV, s));
-        ctx->launches++;
-        for (int k = 0; k < its; k++)
-            launch_step(ctx, 0, nullptr, L.pv[k & 1], L.pv[(k & 1) ^ 1], nullptr, mg.powc + 2, mg.pow_acc + 16 * extra_slot + k, 2);
+        if (l == 0 && !ctx->tets.empty() && mg.n_levels < TSL_MG_MAX_LEVELS && ctx->n_solve > c.offset + c.NV) {
+            // the sliced-ELL matrix has no cloth <-> solid blocks (contacts live in the side buffer), so the iteration stays on the solids
+            extra_slot = TSL_MG_MAX_LEVELS - 1;
+            k_fill_hash<<<GRID(3 * L.nrows, 256), 256, 0, q>>>(3 * L.nrows, L.pv[0], 0x51ed270bu);
+            cudaMemsetAsync(L.pv[0] + 3 * (size_t)c.offset, 0, sizeof(float) * 3 * (size_t)c.NV, q);
+            ctx->launches++;
+            for (int k = 0; k < its; k++)
+                launch_step(ctx, 0, nullptr, L.pv[k & 1], L.pv[(k & 1) ^ 1], nullptr, mg.powc + 2, mg.pow_acc + 16 * extra_slot + k, 2);
+        }
+        ctx->stream = s;
+        if (fork) { CK(cudaEventRecord(mg.ev_done[l], q)); CK(cudaStreamWaitEvent(s, mg.ev_done[l], 0)); }
     }
     k_mg_coeffs<<<1, 32, 0, s>>>(mg.n_levels, mg.pow_acc, its - 1, mg.safety, mg.ratio, mg.coarse_ratio, mg.degree, mg.coarse_degree,
                                  mg.coef, mg.powc, mg.lmax, extra_slot);

@@ -65,6 +65,94 @@ class Grad:
         T = self.tot_timestep
         self._pos_grad[T - 1, c.offset:c.offset + c.NV] = 2.0 * (self._pos_buffer[T - 1, c.offset:c.offset + c.NV] - t)
 
+    # ---- the remaining loss seeds of analytic_grad_single.py:258-471 that apply to one-cloth scenes (plain writes into pos_grad /
+    # angleref_grad, as the reference's kernels)
+    def _cloth(self, sys):
+        c = sys.cloths[0]
+        return c, slice(c.offset, c.offset + c.NV)
+
+    def get_loss(self, sys):
+        """:258-262"""
+        c, sl = self._cloth(sys)
+        self._pos_grad[:, :c.NV, 0] = -1.0              # (the reference indexes the first NV rows, not offset + i)
+
+    def get_loss_sheet(self, sys):
+        """:264-268"""
+        c, sl = self._cloth(sys)
+        self._pos_grad[1:, :c.NV, 0] = 1.0
+
+    def get_loss_book(self, sys):
+        """:273-277"""
+        c, sl = self._cloth(sys)
+        self._pos_grad[1:, :c.NV, 0] = -1.0
+
+    def _row_is(self, sys, row):
+        c = sys.cloths[0]
+        return torch.nonzero((torch.arange(c.NV, device=self._pos_grad.device) // (c.M + 1)) == row).flatten() + c.offset
+
+    def get_loss_pick(self, sys):
+        """:324-327 (get_loss_card :384-388 is the same seed): lift grid row 8"""
+        self._pos_grad[:, self._row_is(sys, 8), 2] = -1.0
+
+    get_loss_card = get_loss_pick
+
+    def get_loss_pick_fold(self, sys):
+        """:373-382: rest angles of the crease between grid rows 7 and 9, every frame"""
+        _, s8 = sys._crease_hinges()
+        self._angleref_grad[:, 0, s8[0], s8[1]] = -1.0
+
+    def get_loss_slide_simple(self, sys):
+        """:390-393"""
+        c, sl = self._cloth(sys)
+        self._pos_grad[self.tot_timestep - 1, sl, 0] = 1.0
+
+    def get_loss_interact(self, sys):
+        """:408-420"""
+        c, sl = self._cloth(sys)
+        b = sys.elastics[3]
+        self._pos_grad[self.tot_timestep - 1, sl, 0] = 1.0
+        self._pos_grad[self.tot_timestep - 1, b.offset:b.offset + b.n_verts, 0] = -256.0 / 144.0
+
+    def get_loss_interact_1(self, sys):
+        """:422-426"""
+        b = sys.elastics[3]
+        self._pos_grad[self.tot_timestep - 1, b.offset:b.offset + b.n_verts, 0] = 1.0
+
+    def _loss_towards_cloth_vertex(self, sys, tt):
+        """get_loss_balance / get_loss_side (:428-463): the carried body elastics[0] follows cloth vertex tt in x, y on every frame
+        (the cloth-vertex entries are plain assignments in the reference's parallel loop: the last body vertex wins)"""
+        c = sys.cloths[0]
+        b = sys.elastics[0]
+        pb = self._pos_buffer
+        for j in range(1, self.tot_timestep):
+            d = pb[j, b.offset:b.offset + b.n_verts, :2] - pb[j, c.offset + tt, :2]
+            self._pos_grad[j, b.offset:b.offset + b.n_verts, :2] = 2 * d
+            self._pos_grad[j, c.offset + tt, :2] = -2 * d[-1]
+
+    def get_loss_balance(self, sys):
+        self._loss_towards_cloth_vertex(sys, (sys.cloth_N + 1) // 2 * (sys.cloth_M + 1) + (sys.cloth_M + 1) // 2)
+
+    def get_loss_side(self, sys):
+        self._loss_towards_cloth_vertex(sys, (sys.cloth_N + 1) // 4 * (sys.cloth_M + 1) + (sys.cloth_M + 1) // 2)
+
+    def get_loss_throwing(self, sys):
+        """:465-473"""
+        c = sys.cloths[0]
+        b = sys.elastics[0]
+        M = sys.cloth_M
+        self._pos_grad[1:, b.offset:b.offset + b.n_verts, 2] = -1.0
+        first = torch.arange(M, device=self._pos_grad.device) + c.offset
+        last = first + sys.cloth_N * (M + 1)
+        for rows in (first, last):
+            self._pos_grad[1:, rows, 2] = 20 * self._pos_buffer[1:, rows, 2]
+
+    def accumulate_gripper_grad(self, traj, max_dist):
+        """:491-502"""
+        for step in range(self.tot_timestep - 2, 1, -1):
+            for j in range(self.n_part):
+                if traj.calculate_dist(step + 1, max_dist, j) > traj.max_moving_dist - 0.00005:
+                    self._gripper_grad[step, j] += self._gripper_grad[step + 1, j]
+
     def get_loss_lift(self, sys):
         """:303-312: d/dx of the squared distance of the carried box (elastics[0]) from its first-frame shape shifted by (-0.012, -0.012, 0)"""
         b = sys.elastics[0]

@@ -204,3 +204,18 @@ def lifting_state(cloth_size=0.06, Kb=100.0):
         els.append(dict(kind="tactile", body=TactileBody(0.015 / 0.03).init(p, fl), gravity=(0.0, 0.0, 0.0)))
     return multi_body_state(cloth_N=N, cloth_M=N, cloth_size=cloth_size, cloth_pos=cpos, elastics=els, pad_poses=poses, k_contact=500.0, Kb=Kb,
                             k_angle=3.14)
+
+
+def pick_state(cloth_size=0.06, Kb=100.0):
+    """Scene_pick (code/task_scene/Scene_pick.py:30-100): a flat 16 x 16 cloth over an ARCHED frozen table (friction 0.1 against it), two
+    pads above on two gripper parts; gravity on the cloth; k_angle 0.5 (the task creases the cloth: training/trajopt_pick_fold.py)"""
+    N = 16
+    dx = cloth_size / N
+    cpos = cloth_positions_flat(N, N, dx, (-0.03, -0.03, 0.0004))
+    tpos, ttets, tfaces, tmass = box_body(0.06, 16, 16, 2, (-0.03, -0.03, -0.008), arch=0.004)
+    poses = [(-0.025, 0.0, 0.0079), (0.025, 0.0, 0.0079)]
+    els = [dict(kind="box", pos=tpos, tets=ttets, faces=tfaces, mass=tmass, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, -9.8), frozen=True)]
+    for p in poses:
+        els.append(dict(kind="tactile", body=TactileBody(0.015 / 0.03).init(p, True), gravity=(0.0, 0.0, 0.0)))
+    return multi_body_state(cloth_N=N, cloth_M=N, cloth_size=cloth_size, cloth_pos=cpos, elastics=els, pad_poses=poses, k_contact=10000.0, Kb=Kb,
+                            k_angle=0.5, cloth_gravity=(0.0, 0.0, -9.8), mu_per_elastic=[0.1, None, None])

@@ -7,12 +7,16 @@ matters: the contact query breaks distance ties by candidate order)."""
 import numpy as np
 
 
-def box_body(Len, Nx, Ny, Nz, offset, density=2000.0):
-    """returns pos [nv,3] f64, tets [nc,4] i32, faces [nf,3] i32 (body-local vertex ids), mass [nv] f64"""
+def box_body(Len, Nx, Ny, Nz, offset, density=2000.0, arch=0.0):
+    """returns pos [nv,3] f64, tets [nc,4] i32, faces [nf,3] i32 (body-local vertex ids), mass [nv] f64.
+    arch != 0: Elastic.init_pos_arch (model_elastic_offset.py:253-270) -- the rest shape is bent upwards by arch * sin(pi x / Lx)
+    (3.1415926 as the reference has it) before the rest matrices, volumes and masses are taken"""
     n = np.array([Nx, Ny, Nz], np.int64)
     dx = Len / (n.max() - 1)
     gx, gy, gz = np.meshgrid(np.arange(Nx), np.arange(Ny), np.arange(Nz), indexing="ij")
     rest = np.stack([gx, gy, gz], -1).reshape(-1, 3).astype(np.float64) * dx      # vertex id = (x*Ny + y)*Nz + z
+    if arch != 0.0:
+        rest[:, 2] += arch * np.sin(gx.reshape(-1).astype(np.float64) / float(Nx - 1) * 3.1415926)
     cx, cy, cz = np.meshgrid(np.arange(Nx - 1), np.arange(Ny - 1), np.arange(Nz - 1), indexing="ij")
     cube = np.stack([cx, cy, cz], -1).reshape(-1, 3)                               # cube id = (x*(Ny-1) + y)*(Nz-1) + z
     codes = np.array([[j, j ^ 1, j ^ 2, j ^ 4] for j in (0, 3, 5, 6)] + [[1, 2, 4, 7]])   # [5,4] corner codes

@@ -104,6 +104,35 @@ class MultiBodyScene(SceneCommon):
         self.last_stats = self.engine.step_forward(self.max_newton, tol)
         return self.last_stats
 
+    def _hinges_between_rows(self, r1, r2):
+        """(face, slot) of the hinges (counter_face[i][l] > i) whose own vertex f2v[i][l] lies in grid row r1 and whose opposite vertex in r2"""
+        c = self.cloths[0]
+        f2v, cf, cp = self.engine.cloth_topology(0)
+        hi, hl = np.nonzero(cf > np.arange(c.NF)[:, None])
+        own = f2v[hi, hl] // (c.M + 1)
+        opp = f2v[cf[hi, hl], cp[hi, hl]] // (c.M + 1)
+        sel = (own == r1) & (opp == r2)
+        return hi[sel], hl[sel]
+
+    def _crease_hinges(self):
+        return self._hinges_between_rows(6, 8), self._hinges_between_rows(7, 9)
+
+    def _hinge_angles(self, hi, hl):
+        """Cloth.compute_angle (code/engine/model_fold_offset.py:126-138) for a handful of hinges, on the host (rewards only)"""
+        c = self.cloths[0]
+        f2v, cf, cp = self.engine.cloth_topology(0)
+        x = self.engine.pos[c.offset:c.offset + c.NV].cpu().numpy()
+
+        def normal(f):
+            a, b, cc = x[f2v[f, 0]], x[f2v[f, 1]], x[f2v[f, 2]]
+            n = np.cross(b - a, cc - b)
+            return n / np.linalg.norm(n, axis=-1, keepdims=True)
+        n1, n2 = normal(hi), normal(cf[hi, hl])
+        ct = np.einsum("ij,ij->i", n1, n2)
+        th = np.where(ct < 0.999999, np.arccos(np.clip(ct, -1, 1)), 2 * np.sqrt(np.abs(1 - ct)) / np.sqrt(1 + ct))
+        e = x[f2v[hi, (hl + 1) % 2]] - x[f2v[hi, hl]]                  # `% 2` is the reference's (quirk Q3)
+        return np.where(np.einsum("ij,ij->i", n2, e) < 0, -th, th)
+
     pos = property(lambda self: TensorField(self.engine.pos))
     vel = property(lambda self: TensorField(self.engine.vel))
     mass = property(lambda self: TensorField(self.engine.mass))

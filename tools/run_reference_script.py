@@ -23,4 +23,8 @@ os.makedirs(os.path.join(work, "imgs"), exist_ok=True)
 os.chdir(os.path.join(work, "code"))
 sys.argv = [script] + sys.argv[2:]
 print(f"[run_reference_script] {script} in {work}", flush=True)
-runpy.run_path(script, run_name="__main__")
+with open(script) as f:
+    relative = any(ln.startswith("from ..") for ln in f)
+# some of the reference's drivers (trajopt_lifting.py, ...) import their package relatively ("from ..agent import ..."): they only run as
+# members of the package, so give them the package name they would have there; none of them guards on __name__
+runpy.run_path(script, run_name="thinshelllab.training." + os.path.splitext(os.path.basename(script))[0] if relative else "__main__")
