@@ -351,7 +351,7 @@ def gen_folding(T=3, tag="folding", forming=False):
                k_angle=s.cloths[0].k_angle[None], cloth_N=s.cloths[0].N, cloth_M=s.cloths[0].M, cloth_dx=s.cloths[0].dx,
                cloth_mass=s.cloths[0].mass, cloth_size=0.1, traj=traj,
                pos0=s.pos.to_numpy(), vel0=s.vel.to_numpy(), mass=s.mass.to_numpy(), frozen=s.frozen.to_numpy(),
-               faces=s.faces.to_numpy(), ref_angle0=s.cloths[0].ref_angle.to_numpy(), border_flag=s.border_flag.to_numpy(),
+               faces=s.faces.to_numpy(), ref_angle0=s.cloths[0].ref_angle.to_numpy(), n_cloths=len(s.cloths), damping=s.damping, border_flag=s.border_flag.to_numpy(),
                gravity=s.gravity.to_numpy(),
                table_tets=s.elastics[0].F_vertices.to_numpy(), table_offset=s.elastics[0].offset, table_nverts=s.elastics[0].n_verts,
                pad_tets=pad.F_vertices.to_numpy(), pad_offset=pad.offset, pad_nverts=pad.n_verts, pad_F_ox=pad.F_ox.to_numpy(),
@@ -520,10 +520,12 @@ if __name__ == "__main__":
 
 
 def gen_scene_states():
-    """initial states of the multi-pad task scenes (Scene_lifting, Scene_pick) as the reference builds them: Scene(); init_all(); reset().
+    """initial states of the multi-pad task scenes (Scene_lifting, Scene_pick, Scene_balancing, Scene_interact, Scene_card, Scene_sliding) as the reference builds them: Scene(); init_all(); reset().
     No time stepping (seconds).  Pins thinshelllab_b200/engine/scene_builder.py."""
     import importlib
-    for tag in ("lifting", "pick"):
+    ALL = ("lifting", "pick", "balancing", "interact", "card", "sliding")
+    tags = [t for t in ALL if t in sys.argv[2:]] or ALL
+    for tag in tags:
         mod = importlib.import_module(f"thinshelllab.task_scene.Scene_{tag}")
         s = mod.Scene(cloth_size=0.06)
         s.device = "cpu"; s.H.device = "cpu"
@@ -532,11 +534,15 @@ def gen_scene_states():
         out = dict(dt=s.dt, k_contact=s.k_contact, eps_contact=s.eps_contact, eps_v=s.eps_v, max_n_constraints=s.max_n_constraints,
                    cloth_N=s.cloths[0].N, cloth_M=s.cloths[0].M, cloth_dx=s.cloths[0].dx, cloth_mass=s.cloths[0].mass, k_angle=s.cloths[0].k_angle[None],
                    Kb=s.cloths[0].Kb[None], pos0=s.pos.to_numpy(), vel0=s.vel.to_numpy(), mass=s.mass.to_numpy(), frozen=s.frozen.to_numpy(),
-                   faces=s.faces.to_numpy(), ref_angle0=s.cloths[0].ref_angle.to_numpy(), border_flag=s.border_flag.to_numpy(), gravity=s.gravity.to_numpy(),
+                   faces=s.faces.to_numpy(), ref_angle0=s.cloths[0].ref_angle.to_numpy(), n_cloths=len(s.cloths), damping=s.damping, border_flag=s.border_flag.to_numpy(), gravity=s.gravity.to_numpy(),
                    cloth_gravity=s.cloths[0].gravity.to_numpy(), n_elastics=len(s.elastics), effector_cnt=s.effector_cnt,
                    body_v=np.array([[b.v_start, b.v_end] for b in s.body_list]), body_f=np.array([[b.f_start, b.f_end] for b in s.body_list]),
-                   gripper_pos0=s.gripper.pos.to_numpy(), gripper_rot0=s.gripper.rot.to_numpy(), gripper_F_x=s.gripper.F_x.to_numpy(),
-                   gripper_bound_idx=s.gripper.bound_idx.to_numpy())
+                   gripper_pos0=s.gripper.pos.to_numpy(), gripper_rot0=s.gripper.rot.to_numpy(), gripper_bound_idx=s.gripper.bound_idx.to_numpy())
+        if hasattr(s.gripper, "F_x_upper"):       # gripper_tactile: two pads per part
+            out.update(gripper_F_x_upper=s.gripper.F_x_upper.to_numpy(), gripper_F_x_lower=s.gripper.F_x_lower.to_numpy(),
+                       gripper_half_dist=s.gripper.half_gripper_dist.to_numpy(), gripper_surface_idx=s.gripper.surface_idx.to_numpy())
+        else:
+            out.update(gripper_F_x=s.gripper.F_x.to_numpy())
         for j, el in enumerate(s.elastics):
             out[f"el{j}_offset"], out[f"el{j}_nverts"] = el.offset, el.n_verts
             out[f"el{j}_tets"] = el.F_vertices.to_numpy()

@@ -82,11 +82,14 @@ def test_pick_scene_state_rollout_rewards_and_adjoint(golden_dir):
         assert flags == 0 and it == 0 and rr < 1e-9, (j, it, flags, rr)
     gg = grad._gripper_grad.copy()
     assert np.isfinite(gg).all() and np.abs(gg[1:]).max() > 0
-    for (part, comp) in ((0, 2), (1, 0)):
-        h = 2e-6
+    # finite differences of the rollout with respect to the pose of the last frame of part 0 (x, z, rotation about y).  The quaternion
+    # update of gripper.step_simple (gripper_single.py:99-110) adds (-d.v, s d + d x v) without the factor 1/2, so a delta_rot of d turns
+    # the pad by 2 d while gather_grad (:133-150) returns dL/d(angle): the reference's rotation gradient is half the derivative with
+    # respect to its own action, and so is ours.
+    for (part, comp, h, scale) in ((0, 2, 2e-6, 1.0), (0, 0, 2e-5, 1.0), (0, 4, 2e-4, 2.0)):
         tp, tm = tr.copy(), tr.copy()
         tp[T - 1, part, comp] += h; tm[T - 1, part, comp] -= h
         fd = (_rollout(s, tp)[0] - _rollout(s, tm)[0]) / (2 * h)
-        an = gg[T - 1, part, comp] * s.gripper.n_bound                  # gather_grad returns the mean over the driven vertices
-        print(f"Scene_pick dL/dpose[{T - 1}, part {part}, {comp}]: adjoint x n_bound {an:.6e}  finite difference {fd:.6e}")
-        assert abs(an - fd) <= 0.02 * max(abs(fd), abs(an)) + 1e-9, (part, comp, an, fd)
+        an = gg[T - 1, part, comp] * s.gripper.n_bound * scale          # gather_grad returns the mean over the driven vertices
+        print(f"Scene_pick dL/dpose[{T - 1}, part {part}, {comp}]: adjoint x n_bound x {scale:g} {an:.6e}  finite difference {fd:.6e}")
+        assert abs(an - fd) <= 0.03 * max(abs(fd), abs(an)) + 1e-9, (part, comp, an, fd)

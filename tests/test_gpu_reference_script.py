@@ -174,3 +174,41 @@ def test_unmodified_pick_fold_script_if_present(tmp_path):
     import numpy as np
     rewards = _run_script("trajopt_pick_fold.py", tmp_path, ["--l", "0", "--r", "1", "--iter", "2", "--tot_step", "11", "--render", "1000"])
     assert len(rewards) == 2 and all(np.isfinite(rewards))
+
+
+def test_unmodified_balancing_script_if_present(tmp_path):
+    """training/trajopt_balancing.py, unedited: Scene_balancing (TetGen ball, two-finger grippers), first a `--save` run that writes the
+    state directory with save_all (the data/balance_state the reference ships lacks rot.npy / state: load_all cannot read it there either),
+    then the optimisation run that load_all()s it at the start of every rollout; get_loss_balance, apply_action_limit_grad"""
+    import numpy as np
+    state = str(tmp_path / "balance_state")
+    common = ["--l", "0", "--r", "1", "--tot_step", "3", "--render", "1000", "--load_state", state]
+    _run_script("trajopt_balancing.py", tmp_path, common + ["--iter", "1", "--save"])
+    for name in ("F_x_upper.npy", "rot.npy", "half_gripper_dist.npy", "state", "border_flag.npy"):
+        assert os.path.exists(os.path.join(state, name)), name
+    rewards = _run_script("trajopt_balancing.py", tmp_path, common + ["--iter", "2"])
+    assert len(rewards) == 2 and all(np.isfinite(rewards)) and rewards[0] < 0
+
+
+def test_unmodified_interact_script_if_present(tmp_path):
+    """training/trajopt_interact.py --sep, unedited: Scene_interact (closing two-finger gripper, free box, elastic-elastic contact),
+    get_loss_interact, the adjoint of frames tot_step-1 .. 6, Adam with a discount"""
+    import numpy as np
+    rewards = _run_script("trajopt_interact.py", tmp_path, ["--l", "0", "--r", "1", "--iter", "2", "--tot_step", "8", "--sep", "--render", "1000"])
+    assert len(rewards) == 2 and all(np.isfinite(rewards))
+
+
+def test_unmodified_sliding_script_if_present(tmp_path):
+    """training/trajopt_silding.py, unedited: Scene_sliding (three cloths, cloth-cloth contact), analytic_grad_system.Grad with
+    count_friction_grad, agent.init_traj_slide, the update of mu_cloth_cloth"""
+    import numpy as np
+    rewards = _run_script("trajopt_silding.py", tmp_path, ["--l", "0", "--r", "1", "--iter", "2", "--tot_step", "8", "--mu", "0.5", "--lr", "1e-4"])
+    assert len(rewards) == 2 and all(np.isfinite(rewards))
+
+
+def test_unmodified_card_script_if_present(tmp_path):
+    """training/trajopt_card.py, unedited: Scene_card (three cards), agent.init_traj_card, get_loss_card, the Kb update (the driver
+    back-propagates frames above 50 only: with tot_step 6 this covers the rollout, the reward and the update arithmetic)"""
+    import numpy as np
+    rewards = _run_script("trajopt_card.py", tmp_path, ["--l", "0", "--r", "1", "--iter", "2", "--tot_step", "6"])
+    assert len(rewards) == 2 and all(np.isfinite(rewards))

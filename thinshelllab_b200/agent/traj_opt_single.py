@@ -43,6 +43,28 @@ class agent_trajopt:
             self._traj[i, :2, 2] = self._traj[i - 1, :2, 2]
             self._traj[i, :2, 0] = self._traj[i - 1, :2, 0]
 
+    def init_traj_card(self):
+        """:75-96: the two end pads close on the stack, then pad 0 lifts and (from frame 35) turns its end"""
+        t, T = self._traj, self.tot_timestep
+        for i in range(min(5, T)):
+            t[i, 0, 0] = t[i - 1, 0, 0] + 0.0003
+            t[i, 1, 0] = t[i - 1, 1, 0] - 0.0003
+        for lo, hi, dx, dz, dr in ((5, 20, 0.0001, 0.0003, 0.0), (20, 35, 0.0001, 0.0002, 0.0), (35, 50, 0.0002, 0.0005, 0.02)):
+            for i in range(lo, min(hi, T)):
+                t[i, 0, 0] = t[i - 1, 0, 0] + dx
+                t[i, 0, 2] = t[i - 1, 0, 2] + dz
+                t[i, 0, 4] = t[i - 1, 0, 4] + dr
+                t[i, 1, 0] = t[i - 1, 1, 0]
+
+    def init_traj_slide(self):
+        """:104-109: press down for 10 frames, then drag along -x"""
+        t, T = self._traj, self.tot_timestep
+        for i in range(min(10, T)):
+            t[i, 0, 2] = -0.00035 * i
+        for i in range(10, min(50, T)):
+            t[i, 0, 0] = t[i - 1, 0, 0] - 0.0005
+            t[i, 0, 2] = t[i - 1, 0, 2]
+
     def get_action(self, step):
         d = self._traj[step] - self._traj[step - 1]
         self._delta_pos.copy_(d[:, :3])

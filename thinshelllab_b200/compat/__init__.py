@@ -47,9 +47,9 @@ class _Renderer:
 def install():
     from .. import fields  # noqa: F401
     from ..agent import traj_opt_single
-    from ..engine import BaseScene, analytic_grad_single, analytic_grad_system, geometry, gripper_single, readfile
+    from ..engine import BaseScene, analytic_grad_single, analytic_grad_system, geometry, gripper_single, gripper_tactile, readfile
     from ..optimizer import optim
-    from ..task_scene import Scene_bouncing, Scene_folding, Scene_forming, Scene_lifting, Scene_pick
+    from ..task_scene import Scene_bouncing, Scene_folding, Scene_forming, Scene_lifting, Scene_pick, Scene_balancing, Scene_interact, Scene_card, Scene_sliding
 
     # ---- third-party modules the scripts import at top level
     if not _have("taichi"):
@@ -73,11 +73,16 @@ def install():
         "thinshelllab.engine.analytic_grad_system": analytic_grad_system,
         "thinshelllab.engine.analytic_grad_single": analytic_grad_single,
         "thinshelllab.engine.gripper_single": gripper_single,
+        "thinshelllab.engine.gripper_tactile": gripper_tactile,
         "thinshelllab.engine.readfile": readfile,
         "thinshelllab.task_scene.Scene_folding": Scene_folding,
         "thinshelllab.task_scene.Scene_forming": Scene_forming,
         "thinshelllab.task_scene.Scene_lifting": Scene_lifting,
         "thinshelllab.task_scene.Scene_pick": Scene_pick,
+        "thinshelllab.task_scene.Scene_balancing": Scene_balancing,
+        "thinshelllab.task_scene.Scene_interact": Scene_interact,
+        "thinshelllab.task_scene.Scene_card": Scene_card,
+        "thinshelllab.task_scene.Scene_sliding": Scene_sliding,
         "thinshelllab.engine.BaseScene": BaseScene,
         "thinshelllab.agent.traj_opt_single": traj_opt_single,
         "thinshelllab.optimizer.optim": optim,

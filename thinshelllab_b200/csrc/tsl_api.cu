@@ -144,7 +144,7 @@ int tsl_add_cloth(tsl_ctx *ctx, int N, int M, int v_offset, double dx, double rh
     if (!ctx) return TSL_ERR_INVALID;
     REQUIRE(!ctx->finalized, "tsl_add_cloth after tsl_finalize");
     REQUIRE(N >= 1 && M >= 1 && 2 * N * M >= 3 && ref_angle_dev, "tsl_add_cloth: bad arguments");
-    REQUIRE(ctx->cloths.empty(), "this build supports one cloth body per context");
+    REQUIRE((int)ctx->cloths.size() < TSL_MAX_CLOTHS, "tsl_add_cloth: too many cloths");
     ClothDev c;
     memset(&c, 0, sizeof(c));
     c.N = N; c.M = M; c.NV = (N + 1) * (M + 1); c.NF = 2 * N * M; c.offset = v_offset;
@@ -931,27 +931,36 @@ int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, c
     if (!ctx || !ctx->finalized) return TSL_ERR_INVALID;
     StreamScope scope_(ctx);
     REQUIRE(x_t && x_tm1 && ref_angle_tm1 && pg_t && pg_tm1 && ag_t && ag_tm1, "tsl_step_backward: null pointer");
-    REQUIRE(ctx->cloths.size() == 1, "tsl_step_backward needs one cloth");
+    REQUIRE(!ctx->cloths.empty(), "tsl_step_backward needs a cloth");
     if (ctx->dist.on && ctx->dist.world > 1) { ctx->err = "the adjoint step is not partitioned over GPUs in this build"; return TSL_ERR_UNSUPPORTED; }
     TRY(ensure_f64(ctx));
     int nv = ctx->cfg.n_verts, n3 = 3 * nv;
     cudaStream_t s = ctx->stream;
-    ClothDev &c = ctx->cloths[0];
-    size_t nb = sizeof(double) * n3, nfb = sizeof(double) * 3 * (size_t)c.NF;
+    // several cloths (Scene_card, Scene_sliding): ref_angle_tm1 / ag_t / ag_tm1 hold the cloths one after the other, [NF_c][3] each
+    size_t nb = sizeof(double) * n3;
+    int nf_all = 0;
+    for (auto &c : ctx->cloths) nf_all += c.NF;
     // clamp_grad(step)
     launch_clamp(ctx, pg_t, n3, clamp);
-    if (clamp_angleref > 0) launch_clamp(ctx, ag_t, 3 * c.NF, clamp_angleref);   // analytic_grad_single.py:182-185
+    if (clamp_angleref > 0) launch_clamp(ctx, ag_t, 3 * nf_all, clamp_angleref);   // analytic_grad_single.py:182-185
     // copy_pos_only(step-1): pos = prev_pos = x_{t-1}; contact re-detection there (quirk Q7)
     CK(cudaMemcpyAsync(ctx->pos, x_tm1, nb, cudaMemcpyDeviceToDevice, s));
     CK(cudaMemcpyAsync(ctx->prev_pos, x_tm1, nb, cudaMemcpyDeviceToDevice, s));
     TRY(contact_detect(ctx, ctx->pos, ctx->prev_pos));
     // copy_pos_and_refangle(step): pos = x_t, prev_pos = x_{t-1}, ref_angle = ref_angle[t-1]
     CK(cudaMemcpyAsync(ctx->pos, x_t, nb, cudaMemcpyDeviceToDevice, s));
-    CK(cudaMemcpyAsync(c.ref_angle, ref_angle_tm1, nfb, cudaMemcpyDeviceToDevice, s));
-    // ref_angle_backprop_a2ax: plastic rest-angle adjoint feeds pos_grad[t] before the solve
-    launch_refangle_a2ax(ctx, c, ctx->pos, ag_t, ag_tm1, pg_t);
-    // get_paramters_grad: d_kb = dF/dKb
-    if (grad_kb_accum) launch_cloth_param_deri(ctx, c, ctx->pos, ctx->d_kb);
+    {
+        size_t fo = 0;
+        for (size_t ci = 0; ci < ctx->cloths.size(); ci++) {
+            ClothDev &c = ctx->cloths[ci];
+            CK(cudaMemcpyAsync(c.ref_angle, ref_angle_tm1 + fo, sizeof(double) * 3 * (size_t)c.NF, cudaMemcpyDeviceToDevice, s));
+            // ref_angle_backprop_a2ax: plastic rest-angle adjoint feeds pos_grad[t] before the solve
+            launch_refangle_a2ax(ctx, c, ctx->pos, ag_t + fo, ag_tm1 + fo, pg_t);
+            // get_paramters_grad: d_kb = dF/dKb (every cloth adds its rows: Scene_card.get_paramters_grad)
+            if (grad_kb_accum) launch_cloth_param_deri(ctx, c, ctx->pos, ctx->d_kb, ci == 0);
+            fo += 3 * (size_t)c.NF;
+        }
+    }
     // H = reference Hessian without projection, fp64
     launch_hessian(ctx, ctx->pos, true, 0, 0, 0);
     // preconditioner of the iterative path: multigrid hierarchy of the clamped Newton matrix at x_t (the direct path needs none)
@@ -971,7 +980,10 @@ int tsl_step_backward_ex(tsl_ctx *ctx, const double *x_t, const double *x_tm1, c
     }
     // friction lag terms and rest-angle terms into step t-1, then the time recurrence and dL/dKb
     launch_contact_backprop(ctx, ctx->pos, z, pg_tm1);
-    launch_refangle_x2a(ctx, c, ctx->pos, z, ag_tm1);
+    {
+        size_t fo = 0;
+        for (auto &c : ctx->cloths) { launch_refangle_x2a(ctx, c, ctx->pos, z, ag_tm1 + fo); fo += 3 * (size_t)c.NF; }
+    }
     launch_adjoint_tail(ctx, z, grad_kb_accum ? ctx->d_kb : nullptr, pg_tm1, pg_tm2, grad_kb_accum);
     CK(cudaStreamSynchronize(s));
     CK(cudaGetLastError());

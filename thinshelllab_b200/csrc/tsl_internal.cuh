@@ -52,6 +52,9 @@ struct ClothDev {
     double *q1;                  // [9 + 81] c_i rows and mat_N of faces 0..2 (quirk Q1)
 };
 
+#define TSL_MAX_CLOTHS 4
+struct ClothSet { int n; ClothDev c[TSL_MAX_CLOTHS]; };      // by-value kernel argument (Scene_card / Scene_sliding stack three cloths)
+
 // tetrahedral body (Elastic of model_elastic_offset.py / model_elastic_tactile.py): vertex range [offset, offset + nv)
 #define TSL_MAX_TETS 8
 struct TetDev {

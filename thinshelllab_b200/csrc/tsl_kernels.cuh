@@ -8,7 +8,7 @@ namespace tsl {
 void launch_face_normals(tsl_ctx *ctx, const ClothDev &c, const double *pos);
 void launch_energy(tsl_ctx *ctx, const double *pos, double *out_dev);
 void launch_residual(tsl_ctx *ctx, const double *pos);
-void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kb);
+void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kb, bool zero = true);
 // into_clamped: the fp32 result goes to A.val32c (multigrid hierarchy / fallback operator) instead of A.val32
 void launch_hessian(tsl_ctx *ctx, const double *pos, bool f64, int spd, int sym, int newton_model, bool into_clamped = false);
 void launch_cloth_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kl, double *d_ka, double *d_kb);

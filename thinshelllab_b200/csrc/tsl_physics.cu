@@ -82,7 +82,7 @@ __global__ void k_face_normals(ClothDev c, const double *__restrict__ pos)
 // ------------------------------------------------------------------------------------------------ energy
 // BaseScene.compute_energy: Cloth.compute_energy (model_fold_offset.py:190-218) + per-vertex inertia/gravity of
 // every body + contact_energy(diff=False) (BaseScene.py:487-598), fused in one launch.
-__global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_verts, const double *__restrict__ pos,
+__global__ void __launch_bounds__(256) k_energy(ClothSet cs, int n_verts, const double *__restrict__ pos,
                                                 const double *__restrict__ prev_pos, const double *__restrict__ vel,
                                                 const double *__restrict__ mass, d3 g, double dt,
                                                 ContactDev con, int nc, ContactParams cp, TetSet ts, const double *__restrict__ vgrav,
@@ -114,7 +114,8 @@ __global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_v
             E += tet_energy(t.P, F, t.W[c]);
         }
     }
-    if (n_cloth > 0)
+    for (int ci = 0; ci < cs.n; ci++) {
+        const ClothDev &c = cs.c[ci];
         for (int i = tid; i < c.NF; i += nth) {
             FaceV f = load_face(c, pos, i);
             if (f.v[0] < own0 || f.v[0] >= own1) continue;
@@ -134,6 +135,7 @@ __global__ void __launch_bounds__(256) k_energy(ClothDev c, int n_cloth, int n_v
                 }
             }
         }
+    }
     for (int i = tid; i < nc; i += nth) {
         const int *idx = con.idx + 4 * i;
         if (idx[3] < nvc && (idx[3] < own0 || idx[3] >= own1)) continue;
@@ -938,21 +940,25 @@ static TetSet tet_set(tsl_ctx *ctx)
 }
 void launch_energy(tsl_ctx *ctx, const double *pos, double *out_dev)
 {
-    ClothDev c = ctx->cloths.empty() ? ClothDev() : ctx->cloths[0];
+    ClothSet cs;
+    cs.n = (int)ctx->cloths.size();
+    for (int q = 0; q < cs.n; q++) cs.c[q] = ctx->cloths[q];
     ContactParams cp = { ctx->cfg.k_contact, ctx->cfg.eps_contact, ctx->cfg.eps_v, ctx->cfg.dt };
     d3 g = mk(ctx->cfg.gravity[0], ctx->cfg.gravity[1], ctx->cfg.gravity[2]);
-    const bool fast = ctx->fast_assembly >= 2 && !ctx->dist.on;
+    const bool fast = ctx->fast_assembly >= 2 && !ctx->dist.on && cs.n == 1;
     if (fast) {
+        const ClothDev &c = cs.c[0];
+        ClothSet none; none.n = 0;
         // cloth part by tiles (tsl_assembly.cu); the rest (other bodies' vertices, cells, contacts) below adds it in
         double *cloth_E = ctx->egrid_partial + ctx->egrid_blocks;
         launch_energy_rows(ctx, pos, cloth_E);
-        k_energy<<<ctx->red_blocks, 256, 0, ctx->stream>>>(c, 0, ctx->cfg.n_verts, pos, ctx->prev_pos, ctx->vel, ctx->mass, g, ctx->cfg.dt, ctx->con, ctx->nc, cp,
+        k_energy<<<ctx->red_blocks, 256, 0, ctx->stream>>>(none, ctx->cfg.n_verts, pos, ctx->prev_pos, ctx->vel, ctx->mass, g, ctx->cfg.dt, ctx->con, ctx->nc, cp,
                                                             tet_set(ctx), ctx->vgrav, 0, 0x7fffffff, 0, c.offset, c.offset + c.NV, cloth_E,
                                                             ctx->red_partial, ctx->red_ticket, out_dev);
         ctx->launches++;
         return;
     }
-    k_energy<<<ctx->red_blocks, 256, 0, ctx->stream>>>(c, (int)ctx->cloths.size(), ctx->cfg.n_verts, pos, ctx->prev_pos, ctx->vel,
+    k_energy<<<ctx->red_blocks, 256, 0, ctx->stream>>>(cs, ctx->cfg.n_verts, pos, ctx->prev_pos, ctx->vel,
                                                         ctx->mass, g, ctx->cfg.dt, ctx->con, ctx->nc, cp, tet_set(ctx), ctx->vgrav,
                                                         ctx->dist.own0, ctx->dist.own1, ctx->dist.on ? ctx->dist.nvc : 0, 0, 0, nullptr,
                                                         ctx->red_partial, ctx->red_ticket, out_dev);
@@ -963,7 +969,7 @@ void launch_residual(tsl_ctx *ctx, const double *pos)
     int n = ctx->cfg.n_verts;
     d3 g = mk(ctx->cfg.gravity[0], ctx->cfg.gravity[1], ctx->cfg.gravity[2]);
     ContactParams cp = { ctx->cfg.k_contact, ctx->cfg.eps_contact, ctx->cfg.eps_v, ctx->cfg.dt };
-    const bool fast = ctx->fast_assembly >= 2 && !ctx->dist.on;
+    const bool fast = ctx->fast_assembly >= 2 && !ctx->dist.on && ctx->cloths.size() == 1;
     if (fast) {
         const ClothDev &c = ctx->cloths[0];
         if (n > c.NV) {
@@ -1051,12 +1057,12 @@ void launch_elastic_force(tsl_ctx *ctx, int body, const double *pos, double *Ff)
     k_residual_tets<<<GRID(t.nc, 128), 128, 0, ctx->stream>>>(t, pos, Ff - 3 * (size_t)t.offset, -1.0);
     ctx->launches += 2;
 }
-void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kb)
+void launch_cloth_param_deri(tsl_ctx *ctx, const ClothDev &c, const double *pos, double *d_kb, bool zero)
 {   // Cloth.compute_deri_Kb: d_kb = -(bending gradient) / Kb
     int n = ctx->cfg.n_verts;
-    k_fill_zero<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(d_kb, 3LL * n);
+    if (zero) { k_fill_zero<<<GRID(3 * n, 256), 256, 0, ctx->stream>>>(d_kb, 3LL * n); ctx->launches++; }
     k_residual_cloth<<<GRID(c.NF, 128), 128, 0, ctx->stream>>>(c, pos, d_kb, 8, -1.0 / c.P.Kb);
-    ctx->launches += 2;
+    ctx->launches += 1;
 }
 // elements of the Hessian into the sink S (matrix values, or the counting pass of the adjoint)
 template <typename T>
@@ -1106,7 +1112,7 @@ static void launch_hessian_t(tsl_ctx *ctx, const double *pos, T *val, T *side, i
 // are added per matrix by the element kernels above.  Otherwise: two scatter assemblies.
 void launch_hessian_newton_pair(tsl_ctx *ctx, const double *pos)
 {
-    if (!ctx->fast_assembly) {
+    if (!ctx->fast_assembly || ctx->cloths.size() != 1) {
         launch_hessian_t<float>(ctx, pos, ctx->A.val32c, ctx->cside32, 1, 0, 1);
         launch_hessian_t<float>(ctx, pos, ctx->A.val32, ctx->cside32, 0, 0, 1);
         return;

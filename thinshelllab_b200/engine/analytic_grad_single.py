@@ -46,7 +46,8 @@ class Grad:
     def copy_pos(self, sys, step):
         """:38-51"""
         self._pos_buffer[step].copy_(sys.engine.pos)
-        self._ref_angle_buffer[step, 0].copy_(sys.engine.cloth_ref_angle[0])
+        for k in range(self._ref_angle_buffer.shape[1]):
+            self._ref_angle_buffer[step, k].copy_(sys.engine.cloth_ref_angle[k])
         self._gripper_pos_buffer[step] = sys.gripper._pos
         self._gripper_rot_buffer[step] = sys.gripper._rot
 
@@ -175,8 +176,8 @@ class Grad:
     def transfer_grad(self, step, sys, f_contact=None, rel_tol=1e-10, max_iters=20000):
         pg_tm2 = self._pos_grad[step - 2] if step > 1 else None
         self.last_solve = sys.engine.step_backward_ex(
-            self._pos_buffer[step], self._pos_buffer[step - 1], self._ref_angle_buffer[step - 1, 0],
-            self._pos_grad[step], self._pos_grad[step - 1], pg_tm2, self._angleref_grad[step, 0], self._angleref_grad[step - 1, 0],
+            self._pos_buffer[step], self._pos_buffer[step - 1], self._ref_angle_buffer[step - 1],         # (every cloth, one after the other)
+            self._pos_grad[step], self._pos_grad[step - 1], pg_tm2, self._angleref_grad[step], self._angleref_grad[step - 1],
             None, self._z, self._z_frozen, clamp=self.clamp, clamp_angleref=self.clamp, rel_tol=rel_tol, max_iters=max_iters)
         if step > 0:
             self.get_gripper_grad(step, sys)

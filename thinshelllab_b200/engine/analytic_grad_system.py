@@ -40,7 +40,8 @@ class Grad:
 
     def copy_pos(self, sys, step):
         self._pos_buffer[step].copy_(sys.engine.pos)
-        self._ref_angle_buffer[step, 0].copy_(sys.engine.cloth_ref_angle[0])
+        for k in range(self._ref_angle_buffer.shape[1]):
+            self._ref_angle_buffer[step, k].copy_(sys.engine.cloth_ref_angle[k])
 
     def get_loss_table(self, sys):
         """analytic_grad_system.py:176-180 (row index uses cloth.N + 1, as the reference does)"""
@@ -49,17 +50,29 @@ class Grad:
         sel = torch.nonzero((row == 5) | (row == 10)).flatten() + c.offset
         self._pos_grad[1:, sel, 2] = -1.0
 
+    def get_loss_slide(self, sys, pos_grad=False):
+        """:171-173"""
+        c = sys.cloths[0]
+        self._pos_grad[1:, c.offset:c.offset + c.NV, 0] = 1.0
+
+    def get_loss_card(self, sys):
+        """:175-177"""
+        c = sys.cloths[0]
+        self._pos_grad[self.tot_timestep - 1, c.offset:c.offset + c.NV, 0] = 1.0
+
     def transfer_grad(self, step, sys, f_contact=None, rel_tol=1e-10, max_iters=20000):
         pg_tm2 = self._pos_grad[step - 2] if step > 1 else None
         # (:147-152) with count_friction_grad the step feeds grad_friction_coef INSTEAD of the stiffness gradients
         kb_acc = self._grad_kb if (self.count_kb_grad and not self.count_friction_grad) else torch.zeros_like(self._grad_kb)
         self.last_solve = sys.engine.step_backward(
-            self._pos_buffer[step], self._pos_buffer[step - 1], self._ref_angle_buffer[step - 1, 0],
-            self._pos_grad[step], self._pos_grad[step - 1], pg_tm2, self._angleref_grad[step, 0], self._angleref_grad[step - 1, 0],
+            self._pos_buffer[step], self._pos_buffer[step - 1], self._ref_angle_buffer[step - 1],        # (every cloth, one after the other)
+            self._pos_grad[step], self._pos_grad[step - 1], pg_tm2, self._angleref_grad[step], self._angleref_grad[step - 1],
             kb_acc, self._z, clamp=self.clamp, rel_tol=rel_tol, max_iters=max_iters)
         if self.count_friction_grad:
             # Scene.contact_energy_backprop_friction (code/task_scene/Scene_sliding.py:140-177)
-            self.grad_friction_coef[None] = self.grad_friction_coef[None] + sys.engine.friction_coef_grad(self._z)
+            # over the first nc1 constraints = the cloth-cloth pairs, which such a scene registers first; every pair otherwise
+            self.grad_friction_coef[None] = self.grad_friction_coef[None] + sys.engine.friction_coef_grad(
+                self._z, 0, getattr(sys, "n_cloth_cloth_pairs", None))
             return self.last_solve
         if self.count_mu_lam_grad and sys.engine.tet_bodies:
             # Grad.get_parameters_grad (:69-75): grad_mu / grad_lam += sum over free DOFs of z d_mu / z d_lam

@@ -140,21 +140,37 @@ def folding_state(cloth_size=0.06, forming=False, Kb=100.0):
 # ------------------------------------------------------------------------------------------------ general one-cloth / many-bodies scenes
 def multi_body_state(*, cloth_N, cloth_M, cloth_size, cloth_pos, elastics, pad_poses, dt=5e-3, k_contact, eps_contact=0.0004, eps_v=0.01,
                      max_n_constraints=10000, rho=40.0, Kb=100.0, k_angle=3.14, mu=1.0, cloth_gravity=(0.0, 0.0, 0.0), pinned_vertices=(),
-                     init_ref_angle=False, mu_per_elastic=None):
+                     init_ref_angle=False, mu_per_elastic=None, pad_part=None, pairs=None):
     """state of a scene with one cloth and a list of elastic bodies (BaseScene.__init__ + init_objects + init + init_property +
     set_frozen_kernel of Scene_lifting / Scene_pick).  elastics: list of dicts
         dict(kind="box", pos, tets, faces, mass, mu, lam, gravity, frozen=True/False)
         dict(kind="tactile", body=TactileBody (already .init()-ed), gravity)            -- driven by gripper part = its rank among the pads
-    pad_poses [n_pads][3]: gripper.init positions."""
+        dict(kind="mesh", rest, pos, tets, faces, density, mu, lam, gravity)             -- a TetGen body (the ball), free
+    pad_poses [n_parts][3]: gripper.init positions; pad_part[k] = gripper part driving pad k (default: pad k on part k; the two-finger
+    gripper of gripper_tactile.py has pads 2 j and 2 j + 1 on part j).
+    pairs: the scene's contact_analysis as a list of (surface body, vertex body, mu) in the reference's order (bodies: cloths first, then
+    elastics); mu is a number or "elastic" / "cloth" (follows mu_cloth_elastic / mu_cloth_cloth), optionally ("elastic", factor).
+    Default: every cloth against every elastic body both ways with mu_cloth_elastic (or mu_per_elastic[j])."""
     dx = cloth_size / cloth_N
     NVc = (cloth_N + 1) * (cloth_M + 1)
-    pos, mass, frozen = [np.asarray(cloth_pos, np.float64)], [np.full(NVc, rho * dx * dx)], [np.zeros((NVc, 3), np.int32)]
+    # several cloths (Scene_card, Scene_sliding): cloth_pos is a list of [NVc][3] arrays, the cloths share N, M and material
+    cloth_list = [np.asarray(cloth_pos, np.float64)] if np.ndim(cloth_pos[0][0]) == 0 else [np.asarray(p, np.float64) for p in cloth_pos]
+    n_cloths = len(cloth_list)
+    pos, mass, frozen = list(cloth_list), [np.full(NVc, rho * dx * dx)] * n_cloths, [np.zeros((NVc, 3), np.int32) for _ in range(n_cloths)]
     for v in pinned_vertices:
         frozen[0][v] = 1
-    off = NVc
+    off = NVc * n_cloths
     els, faces = [], []
     for el in elastics:
-        if el["kind"] == "box":
+        if el["kind"] == "mesh":
+            p, tets, f = el["pos"], np.asarray(el["tets"], np.int32), el["faces"]
+            B, W = tet_rest_np(el["rest"], tets)
+            m = np.zeros(p.shape[0])
+            np.add.at(m, tets.reshape(-1), np.repeat(W / 4 * el["density"], 4))          # Elastic.init_pos (:240-245)
+            fz = np.zeros((p.shape[0], 3), np.int32)
+            rec = dict(kind=0, offset=off, nverts=p.shape[0], tets=tets, F_B=B, F_W=W, mu=el["mu"], lam=el["lam"], alpha=0.0,
+                       gravity=np.asarray(el["gravity"], np.float64), rest=p.copy())
+        elif el["kind"] == "box":
             p, tets, f, m = el["pos"], el["tets"], el["faces"], el["mass"]
             B, W = tet_rest_np(p, tets)
             fz = np.full((p.shape[0], 3), 1 if el.get("frozen", False) else 0, np.int32)
@@ -172,14 +188,22 @@ def multi_body_state(*, cloth_N, cloth_M, cloth_size, cloth_pos, elastics, pad_p
         off += rec["nverts"]
     pads = [r for r in els if r["kind"] == 1]
     pos0 = np.concatenate(pos)
+    pad_part = list(range(len(pads))) if pad_part is None else [int(v) for v in pad_part]
+    n_parts = (max(pad_part) + 1) if pads else 0
     st = dict(dt=dt, k_contact=float(k_contact), eps_contact=eps_contact, eps_v=eps_v, mu=mu, Kb=Kb, k_angle=k_angle, cloth_N=cloth_N, cloth_M=cloth_M,
               cloth_dx=dx, cloth_mass=rho * dx * dx, cloth_size=cloth_size, max_n_constraints=max_n_constraints, pos0=pos0, vel0=np.zeros_like(pos0),
               mass=np.concatenate(mass), frozen=np.concatenate(frozen).reshape(-1), border_flag=np.zeros(pos0.shape[0], np.int32),
-              gravity=np.asarray(cloth_gravity, np.float64), ref_angle0=np.zeros((2 * cloth_N * cloth_M, 3)), init_ref_angle=bool(init_ref_angle),
+              gravity=np.asarray(cloth_gravity, np.float64), n_cloths=n_cloths,
+              ref_angle0=np.zeros((2 * cloth_N * cloth_M, 3)) if n_cloths == 1 else np.zeros((n_cloths, 2 * cloth_N * cloth_M, 3)),
+              init_ref_angle=bool(init_ref_angle),
               elastics=els, elastic_faces=faces, mu_per_elastic=mu_per_elastic,
-              gripper_pos0=np.asarray(pad_poses, np.float64), gripper_rot0=np.tile(np.array([1.0, 0.0, 0.0, 0.0]), (len(pads), 1)),
-              gripper_F_x=np.stack([pos0[r["offset"]:r["offset"] + r["nverts"]] - np.asarray(pad_poses[k], np.float64) for k, r in enumerate(pads)]),
+              gripper_pos0=np.asarray(pad_poses, np.float64), gripper_rot0=np.tile(np.array([1.0, 0.0, 0.0, 0.0]), (n_parts, 1)),
+              pad_part=np.asarray(pad_part, np.int32),
+              gripper_F_x=np.stack([pos0[r["offset"]:r["offset"] + r["nverts"]] - np.asarray(pad_poses[pad_part[k]], np.float64)
+                                    for k, r in enumerate(pads)]),
               gripper_bound_idx=pads[0]["bound_idx"] if pads else np.zeros(0, np.int32))
+    if pairs is not None:
+        st["pairs"] = pairs
     return st
 
 
@@ -219,3 +243,122 @@ def pick_state(cloth_size=0.06, Kb=100.0):
         els.append(dict(kind="tactile", body=TactileBody(0.015 / 0.03).init(p, True), gravity=(0.0, 0.0, 0.0)))
     return multi_body_state(cloth_N=N, cloth_M=N, cloth_size=cloth_size, cloth_pos=cpos, elastics=els, pad_poses=poses, k_contact=10000.0, Kb=Kb,
                             k_angle=0.5, cloth_gravity=(0.0, 0.0, -9.8), mu_per_elastic=[0.1, None, None])
+
+
+def ball_body(pos, inner=None):
+    """Elastic(load=True).init (code/engine/model_elastic_offset.py:40-49, 379-405): the TetGen ball of data/ball.*, NOT rescaled,
+    translated to `pos`; surface triangles re-oriented to point away from `pos` (init_normal)"""
+    from . import readfile
+    _, verts = readfile.read_node("../data/ball.node")
+    _, tets = readfile.read_ele("../data/ball.ele")
+    _, faces = readfile.read_smesh("../data/ball.face")
+    rest = np.asarray(verts, np.float64)
+    x = rest + np.asarray(pos, np.float64)
+    f = np.asarray(faces, np.int32).copy()
+    p1, p2, p3 = x[f[:, 0]], x[f[:, 1]], x[f[:, 2]]
+    n = np.cross(p2 - p1, p3 - p1)
+    n /= np.linalg.norm(n, axis=1, keepdims=True)
+    flip = np.einsum("ij,ij->i", n, np.asarray(pos if inner is None else inner, np.float64) - p1) > 0
+    f[flip, 1], f[flip, 2] = f[flip, 2].copy(), f[flip, 1].copy()
+    return rest, x, np.asarray(tets, np.int32), f
+
+
+def balancing_state(cloth_size=0.06, Kb=100.0):
+    """Scene_balancing (code/task_scene/Scene_balancing.py:27-96): a 15 x 7 cloth strip with the TetGen ball (free, density 10000, under
+    gravity) resting on it, held at both ends between an upper and a lower tactile pad of a two-finger gripper (gripper_tactile.py): two
+    parts, four pads; friction 0.2 against the ball; eps_contact 0.41 mm"""
+    N, M = 15, 7
+    dx = cloth_size / N
+    cpos = cloth_positions_flat(N, M, dx, (-0.03, -0.015, 0.0))
+    rest, bpos, btets, bfaces = ball_body((0.0, 0.0, 0.0039))
+    parts = [(0.023, 0.0, 0.0), (-0.023, 0.0, 0.0)]
+    pads = [((0.023, 0.0, 0.0079), True), ((0.023, 0.0, -0.0079), False), ((-0.023, 0.0, 0.0079), True), ((-0.023, 0.0, -0.0079), False)]
+    els = [dict(kind="mesh", rest=rest, pos=bpos, tets=btets, faces=bfaces, density=10000.0, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, -9.8))]
+    for p, fl in pads:
+        els.append(dict(kind="tactile", body=TactileBody(0.015 / 0.03).init(p, fl), gravity=(0.0, 0.0, 0.0)))
+    return multi_body_state(cloth_N=N, cloth_M=M, cloth_size=cloth_size, cloth_pos=cpos, elastics=els, pad_poses=parts, pad_part=[0, 0, 1, 1],
+                            k_contact=10000.0, eps_contact=0.00041, Kb=Kb, k_angle=3.14, cloth_gravity=(0.0, 0.0, -9.8),
+                            mu_per_elastic=[0.2, None, None, None, None])
+
+
+def interact_state(cloth_size=0.06, Kb=100.0, dense=10000.0):
+    """Scene_interact (code/task_scene/Scene_interact.py:28-104): a 15 x 15 cloth half on a frozen table, its free end between the two pads
+    of ONE two-finger gripper part (which closes by 0.6 mm per frame over the first frames: Scene.action), and a free 6 x 6 x 4 box lying
+    on the cloth; friction 0.2 against table and box, the box also touches the table (0.1); k_contact 30000"""
+    N = 15
+    dx = cloth_size / N
+    cpos = cloth_positions_flat(N, N, dx, (-0.045, -0.03, 0.0004))
+    tpos, ttets, tfaces, tmass = box_body(0.06, 16, 16, 2, (-0.03, -0.03, -0.004))
+    bpos, btets, bfaces, bmass = box_body(0.012, 6, 6, 4, (0.001, -0.006, 0.0008), density=dense)
+    els = [dict(kind="box", pos=tpos, tets=ttets, faces=tfaces, mass=tmass, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, -9.8), frozen=True),
+           dict(kind="tactile", body=TactileBody(0.015 / 0.03).init((-0.04, 0.0, 0.0083), True), gravity=(0.0, 0.0, 0.0)),
+           dict(kind="tactile", body=TactileBody(0.015 / 0.03).init((-0.04, 0.0, -0.0075), False), gravity=(0.0, 0.0, 0.0)),
+           dict(kind="box", pos=bpos, tets=btets, faces=bfaces, mass=bmass, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, -9.8), frozen=False)]
+    st = multi_body_state(cloth_N=N, cloth_M=N, cloth_size=cloth_size, cloth_pos=cpos, elastics=els, pad_poses=[(-0.04, 0.0, 0.0004)],
+                          pad_part=[0, 0], k_contact=30000.0, Kb=Kb, k_angle=3.14, cloth_gravity=(0.0, 0.0, -9.8),
+                          mu_per_elastic=[0.2, None, None, 0.2])
+    st["extra_pairs"] = [(1, 4, 0.1), (4, 1, 0.1)]       # (surface of body a, vertices of body b, mu): table <-> box (contact_analysis :99-102)
+    return st
+
+
+def card_state(cloth_size=0.06, Kb=100.0):
+    """Scene_card (code/task_scene/Scene_card.py:31-128): three stacked 12 x 8 cards on a frozen table, two pads at the ends turned by
+    +-90 degrees about y (their faces look along x) and one pad above; the pads only act on cloth vertices (one-way pairs, 10 x the
+    friction for cards 1 and 2), neighbouring cards touch each other with friction 0.1; k_contact 20000; damping 0.95"""
+    N, M = 12, 8
+    dx = cloth_size / N
+    cpos = [cloth_positions_flat(N, M, dx, (-0.02, -0.02, z)) for z in (0.01, 0.0104, 0.0108)]
+    tpos, ttets, tfaces, tmass = box_body(0.07, 9, 9, 2, (-0.025, -0.025, -0.00875))
+    poses = [(-0.0285, 0.0, 0.01), (0.0485, 0.0, 0.01), (0.01, 0.0, 0.0185)]
+    els = [dict(kind="box", pos=tpos, tets=ttets, faces=tfaces, mass=tmass, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, 0.0), frozen=True)]
+    for p, fl in zip(poses, (False, False, True)):
+        els.append(dict(kind="tactile", body=TactileBody(0.015 / 0.03).init(p, fl), gravity=(0.0, 0.0, 0.0)))
+    pairs = []
+    for i in range(3):
+        for j in range(3):
+            if abs(i - j) == 1:
+                pairs += [(i, j, 0.1), (j, i, 0.1)]
+    for i in range(3):
+        for j in range(4):
+            pairs.append((3 + j, i, "elastic" if i == 0 else ("elastic", 10.0)))
+    s2 = np.sqrt(2.0) * 0.5
+    st = multi_body_state(cloth_N=N, cloth_M=M, cloth_size=cloth_size, cloth_pos=cpos, elastics=els, pad_poses=poses, k_contact=20000.0, Kb=Kb,
+                          k_angle=3.14, pairs=pairs)
+    st["damping"] = 0.95
+    st["gripper_rot0"] = np.array([[s2, 0.0, s2, 0.0], [s2, 0.0, -s2, 0.0], [1.0, 0.0, 0.0, 0.0]])    # init :88-92, then update_all:
+    from .gripper_single import quat_to_rotmat32                  # every pad vertex to pos + R F_x (R held in float32 by the reference)
+    pads = [r for r in st["elastics"] if r["kind"] == 1]
+    for k, r in enumerate(pads):
+        R = quat_to_rotmat32(st["gripper_rot0"][k]).astype(np.float64)
+        st["pos0"][r["offset"]:r["offset"] + r["nverts"]] = np.asarray(poses[k]) + st["gripper_F_x"][k] @ R.T
+    return st
+
+
+def sliding_state(cloth_size=0.06, Kb=100.0):
+    """Scene_sliding (code/task_scene/Scene_sliding.py:23-100): three stacked 15 x 15 cloths on a frozen table (friction 0.4 against it),
+    one pad above (E 5e5 / nu 0.2 as every tactile pad); neighbouring cloths touch with the identified coefficient mu_cloth_cloth"""
+    N = 15
+    dx = cloth_size / N
+    cpos = [cloth_positions_flat(N, N, dx, (-0.03, -0.03, z)) for z in (0.0004, 0.0008, 0.0012)]
+    tpos, ttets, tfaces, tmass = box_body(0.1, 16, 16, 2, (-0.05, -0.05, -0.00666))
+    poses = [(0.0, 0.0, 0.0105)]
+    els = [dict(kind="box", pos=tpos, tets=ttets, faces=tfaces, mass=tmass, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, 0.0), frozen=True),
+           dict(kind="tactile", body=TactileBody(0.015 / 0.03).init(poses[0], True), gravity=(0.0, 0.0, 0.0))]
+    pad = els[1]["body"]                                           # Scene.__init__ :26-32: E 5e5, nu 0.2 for this pad
+    E, nu = 5e5, 0.2
+    pad.mu, pad.lam = E / (2 * (1 + nu)), E * nu / ((1 + nu) * (1 - 2 * nu))
+    pad.alpha = 1 + pad.mu / pad.lam
+    pairs = []
+    for i in range(3):
+        for j in range(3):
+            if abs(i - j) == 1:
+                pairs += [(i, j, "cloth"), (j, i, "cloth")]
+    n_cc = len(pairs)
+    for i in range(3):
+        for j in range(2):
+            mu = 0.4 if j == 0 else "elastic"
+            pairs += [(i, 3 + j, mu), (3 + j, i, mu)]
+    st = multi_body_state(cloth_N=N, cloth_M=N, cloth_size=cloth_size, cloth_pos=cpos, elastics=els, pad_poses=poses, k_contact=10000.0, Kb=Kb,
+                          k_angle=3.14, pairs=pairs)
+    st["n_cloth_cloth_pairs"] = n_cc
+    return st
