@@ -100,6 +100,39 @@ def pad_sheet_scene(N, pad=None, device="cuda:0", **kw):
     return Scene(st, device=device, max_newton=200)
 
 
+def config3_state(N, dx=0.002, dt=5e-3, Kb=100.0, k_contact=10000.0, mu=0.5, gap=2e-4, ball_xy=(0.03, 0.0)):
+    """BASELINE.json configs[3] as it names it: an N x N sheet + volumetric tactile AND ball contact (data/tactile.*, data/ball.*) -- the
+    sheet rests on a frozen table, a tactile pad on a one-part gripper hovers `gap` above its centre, the TetGen ball of Scene_balancing
+    (free, density 10000, under gravity) lies on the sheet beside it.  A state mapping for task_scene._multi_body.MultiBodyScene."""
+    from .engine.scene_builder import TactileBody, ball_body, multi_body_state
+    sp = sheet_spec(N, dx=dx, dt=dt, bump=0.0, noise=0.0, z0=0.0004, k_contact=k_contact, mu=mu)
+    tn = sp["table_N"][0]
+    tpos, ttets, tfaces, tmass = box_body(sp["table_size"], tn, tn, 2, sp["table_offset"])
+    pad = TactileBody(0.015 / 0.03)
+    pad_z = 0.0004 + 0.0004 + gap - (pad.init((0.0, 0.0, 0.0), True).F_x[:, 2].min())
+    pad = TactileBody(0.015 / 0.03).init((0.0, 0.0, pad_z), True)
+    rest, bpos, btets, bfaces = ball_body((ball_xy[0], ball_xy[1], 0.0004 + 0.0039))
+    els = [dict(kind="box", pos=tpos, tets=ttets, faces=tfaces, mass=tmass, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, -9.8), frozen=True),
+           dict(kind="tactile", body=pad, gravity=(0.0, 0.0, 0.0)),
+           dict(kind="mesh", rest=rest, pos=bpos, tets=btets, faces=bfaces, density=10000.0, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, -9.8))]
+    st = multi_body_state(cloth_N=N, cloth_M=N, cloth_size=N * dx, cloth_pos=sp["cloth_pos"], elastics=els, pad_poses=[(0.0, 0.0, pad_z)], dt=dt,
+                          k_contact=k_contact, Kb=Kb, k_angle=3.14, mu=mu, cloth_gravity=(0.0, 0.0, -9.8), max_n_constraints=4 * (N + 1) ** 2 + 4096)
+    st["grid_n"] = sp["grid_n"]
+    st["n_tris"] = 2 * N * N
+    return st
+
+
+def config3_scene(N, device="cuda:0", **kw):
+    from .task_scene._multi_body import MultiBodyScene
+
+    class Scene(MultiBodyScene):
+        max_newton = 200
+
+        def __init__(self, st):
+            self._build(st, device=device)
+    return Scene(config3_state(N, **kw))
+
+
 # ------------------------------------------------------------------------------------------------ strip partition (SURVEY.md section 8e)
 def strip_spec(R, M, rank, world, dx=0.002, dt=5e-3, seed=0, z0=0.0003, bump=0.25, noise=0.01, k_contact=40000.0, mu=0.5, ghost=2):
     """Rank `rank` of `world` of a sheet of world*R vertex rows x (M+1) columns cut into strips of R rows (R even keeps the

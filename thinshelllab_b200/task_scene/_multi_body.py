@@ -32,7 +32,8 @@ class MultiBodyScene(SceneCommon):
         self.tot_NV = pos0.shape[0]
         gravity = tuple(float(v) for v in g["gravity"])            # the cloths' gravity; bodies carry their own
         e = self.engine = ShellEngine(self.tot_NV, self.dt, k_contact=self.k_contact, eps_contact=self.eps_contact, eps_v=self.eps_v,
-                                      damping=self.damping, gravity=gravity, max_n_constraints=self.max_n_constraints, device=device)
+                                      damping=self.damping, gravity=gravity, max_n_constraints=self.max_n_constraints,
+                                      grid_n=int(g["grid_n"]) if "grid_n" in g else 132, device=device)
         rho = float(g["cloth_mass"]) / (dx * dx)
         NVc = (N + 1) * (M + 1)
         self.cloths = []
