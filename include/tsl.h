@@ -72,7 +72,9 @@ int tsl_set_stream(tsl_ctx *ctx, void *cuda_stream);
 /* ---- scene description (cold path) --------------------------------------------------------- */
 /* Cloth(N, dt, Len, tot_NV, rho, offset, is_square, M) + Cloth.init_mesh
  * (code/engine/model_fold_offset.py:11-106, 929-1018).  Returns the cloth id (>= 0).
- * ref_angle_dev: [2*N*M][3] f64 plastic rest angles, owned by the caller (Cloth.ref_angle). */
+ * ref_angle_dev: [2*N*M][3] f64 plastic rest angles, owned by the caller (Cloth.ref_angle).
+ * Up to 4 cloths per context (Scene_card / Scene_sliding stack three: code/task_scene/Scene_card.py:60-63); the multigrid hierarchy of
+ * the forward solve is built on the first cloth's grid, the others are smoothed on the fine level only. */
 int tsl_add_cloth(tsl_ctx *ctx, int N, int M, int v_offset, double dx, double rho,
                   double Kl, double Ka, double Kb, double k_angle, double *ref_angle_dev);
 /* Cloth.Kl/Ka/Kb/k_angle[None] = ...  (scripts set sys.cloths[0].Kb[None], trajopt_bouncing.py:46) */
@@ -153,10 +155,12 @@ int tsl_step_forward_host(tsl_ctx *ctx, double *pos_host, double *vel_host, int 
 /* analytic_grad_system.Grad.transfer_grad(step, sys, f_contact) (code/engine/analytic_grad_system.py:115-160)
  * for one step t.  Device pointers, f64:
  *   x_t, x_tm1            [n_verts][3]  pos_buffer[t], pos_buffer[t-1]
- *   ref_angle_tm1         [NF][3]       ref_angle_buffer[t-1] (cloth 0)
+ *   ref_angle_tm1         [NF][3]       ref_angle_buffer[t-1]; with several cloths: [cloth][NF_c][3], one after the other, likewise
+ *                                       angleref_grad_* (the layout of Grad.ref_angle_buffer[t] / angleref_grad[t])
  *   pos_grad_t/tm1/tm2    [n_verts][3]  pos_grad[t] (clamped + updated in place), pos_grad[t-1], pos_grad[t-2] (NULL if t < 2)
  *   angleref_grad_t/tm1   [NF][3]
- *   grad_kb_accum_dev     [1]           += sum_free z * d_kb   (Grad.get_parameters_grad :69-79)
+ *   grad_kb_accum_dev     [1]           += sum_free z * d_kb   (Grad.get_parameters_grad :69-79; d_kb over every cloth, each with its
+ *                                       own Kb: Scene_card.get_paramters_grad)
  *   z_out_dev             [3 n_verts]   adjoint solution (may be NULL)
  * clamp: +-1 (system-ID Grad, :104-108) or +-1000 (trajectory Grad). */
 int tsl_step_backward(tsl_ctx *ctx, const double *x_t, const double *x_tm1, const double *ref_angle_tm1,
