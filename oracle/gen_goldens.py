@@ -558,3 +558,4 @@ def gen_scene_states():
 
 if __name__ == "__main__" and "scene_states" in sys.argv[1:]:
     gen_scene_states()
+

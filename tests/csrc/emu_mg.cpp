@@ -20,7 +20,8 @@ extern "C" void emu_galerkin_pair(int n0f, int n1f, int elem_major_f, int elem_m
     emu_launch_seq(dim3((unsigned)((nt + 127) / 128)), dim3(128), k_galerkin<false>, (const float *)vf.data(), n0f, n1f, svf, sef, (const int *)nullptr,
                    c1.data(), n0c, n1c, svc, sec);
     dim3 grid((n1c + TSL_TCJ - 1) / TSL_TCJ, (n0c + TSL_TCI - 1) / TSL_TCI);
-    emu_launch(grid, dim3(256), k_galerkin_tiled, (const float *)vf.data(), n0f, n1f, svf, sef, c2.data(), n0c, n1c, svc, sec);
+    emu_launch(grid, dim3(256), k_galerkin_tiled<float>, (const float *)vf.data(), n0f, n1f, svf, sef, c2.data(), (float *)nullptr, n0c, n1c, svc, sec,
+               (const float *)nullptr);
     for (int v = 0; v < nvc; v++) for (int e = 0; e < 225; e++) {
         out_ref[(size_t)v * 225 + e] = c1[(size_t)v * svc + (size_t)e * sec];
         out_tiled[(size_t)v * 225 + e] = c2[(size_t)v * svc + (size_t)e * sec];
@@ -65,8 +66,8 @@ extern "C" void emu_galerkin_sell(int off, int n0f, int n1f, int nv, const int *
     emu_launch_seq(dim3((unsigned)((nt + 127) / 128)), dim3(128), k_galerkin<true>, (const float *)st.data(), n0f, n1f, 225LL, 1LL, mask_rel,
                    c1.data(), n0c, n1c, 1LL, (long long)nvcp);
     dim3 grid((n1c + TSL_TCJ - 1) / TSL_TCJ, (n0c + TSL_TCI - 1) / TSL_TCI);
-    emu_launch(grid, dim3(256), k_galerkin_sell_tiled, off, n0f, n1f, (const int *)slice_base.data(), (const int *)colpad.data(), (const float *)val.data(),
-               (const int *)diag.data(), mask_rel, c2.data(), n0c, n1c, 1LL, (long long)nvcp);
+    emu_launch(grid, dim3(256), k_galerkin_sell_tiled<float>, off, n0f, n1f, (const int *)slice_base.data(), (const int *)colpad.data(), (const float *)val.data(),
+               (const int *)diag.data(), mask_rel, c2.data(), (float *)nullptr, n0c, n1c, 1LL, (long long)nvcp, (const float *)nullptr);
     for (int v = 0; v < nvc; v++) for (int e = 0; e < 225; e++) {
         out_ref[(size_t)v * 225 + e] = c1[(size_t)v + (size_t)e * nvcp];
         out_tiled[(size_t)v * 225 + e] = c2[(size_t)v + (size_t)e * nvcp];

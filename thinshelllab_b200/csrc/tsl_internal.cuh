@@ -30,6 +30,7 @@ struct SellMatrix {
     float *val32 = nullptr;     // [nnzb_pad*9]  operator of the forward solve (exact or clamped Newton matrix)
     float *val32c = nullptr;    // [nnzb_pad*9]  clamped (positive definite) Newton matrix: fallback operator, source of the hierarchy
     float *val32t = nullptr;    // [nnzb_pad*9]  blended operator val32 + theta (val32c - val32) (Newton mode 2)
+    void *val16m = nullptr;     // [nnzb_pad*9]  fp16 snapshot (x MgDev::scale[0]) of val32c for the level-0 smoother (MgDev::use_half)
     float *val32m = nullptr;    // [nnzb_pad*9]  snapshot of val32c the current multigrid hierarchy was built from (level-0 smoother matrix)
     double *val64 = nullptr;    // [nnzb_pad*9], allocated on first fp64 assembly
     // host copies (pattern export, slot lookup at setup)
@@ -97,6 +98,8 @@ struct MgLevel {
     long long sv = 225, se = 1;            // layout of val: element (v, e) at val[v*sv + e*se] (row-major small levels, element-major large)
     int nrows = 0;                         // rows of the level's vectors (level 0: all matrix rows; else nv)
     float *val = nullptr;                  // stencil operator [225][nvp]  (level 0: stencil copy of the cloth block, Galerkin input only)
+    void *val16 = nullptr;                 // the same operator in fp16 x the level's scale (large levels when MgDev::use_half): what the smoother reads
+    int half = 0;                          // 1: the level's operator lives in val16 (level 0: SellMatrix::val16m)
     float *dinv = nullptr;                 // [nrows][9] inverse diagonal blocks
     float *x[2] = { nullptr, nullptr };    // iterate ping-pong [3 nrows]
     float *b = nullptr, *r = nullptr, *d = nullptr;   // right-hand side, residual, Chebyshev direction
@@ -116,6 +119,11 @@ struct MgDev {
     int tail_level = -1;                   // first level of the fused single-block tail of the V-cycle (-1: none)
     // side streams of the hierarchy build: the eigenvalue iteration of level l only needs that level's operator, so it runs beside
     // the Galerkin chain that is still producing the coarser levels (TSL_MG_FORK=0: everything on the context's stream)
+    // fp16 storage of the operators only the preconditioner reads (level-0 snapshot, element-major coarse levels): TSL_MG_HALF=0 keeps fp32
+    int use_half = 1;
+    int sell_split = 4;                    // warps per 32-row slice in the level-0 smoother kernels (TSL_MG_SELL_SPLIT = 1 / 2 / 4)
+    float *scale = nullptr;                // device [levels][2]: {s, 1 / s}, stored value = true value x s (power of two; fp32 levels: 1)
+    unsigned int *maxdiag = nullptr;       // device: bits of the largest diagonal entry of the level-0 matrix (>= every |entry| of a PSD matrix)
     int fork = 1;
     cudaStream_t side[TSL_MG_MAX_LEVELS] = {};
     cudaEvent_t ev_ready[TSL_MG_MAX_LEVELS] = {}, ev_done[TSL_MG_MAX_LEVELS] = {};

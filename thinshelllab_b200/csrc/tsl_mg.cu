@@ -17,6 +17,7 @@
 // synchronise with the host.  Bound: every kernel streams its level's matrix once (HBM / L2), the small levels are
 // launch-latency bound.
 #include "tsl_internal.cuh"
+#include <cuda_fp16.h>
 #include "tsl_kernels.cuh"
 #include "tsl_mg_kernels.cuh"
 
@@ -26,9 +27,11 @@ namespace tsl {
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ctx->err = std::string(#x) + ": " + cudaGetErrorString(e_); return TSL_ERR_CUDA; } } while (0)
 
 // ------------------------------------------------------------------------------------------------ row operators
-struct SellOp {
+template <class VT>
+struct SellOpT {
     const int *slice_base, *colidx;
-    const float *val;
+    const VT *val;
+    const float *sc;             // {scale, 1 / scale} of the stored values (NULL: stored = true value)
     __device__ __forceinline__ void mul(int row, const float *__restrict__ x, float &y0, float &y1, float &y2) const
     {
         int S = row >> 5, lane = row & 31;
@@ -37,15 +40,44 @@ struct SellOp {
 #pragma unroll 2
         for (int b = b0; b < b1; b += 32) {
             int col = __ldg(colidx + b + lane);
-            const float *v = val + (long long)b * 9 + lane;
+            const VT *v = val + (long long)b * 9 + lane;
             float x0 = x[3 * col], x1 = x[3 * col + 1], x2 = x[3 * col + 2];
-            a0 += __ldg(v) * x0 + __ldg(v + 32) * x1 + __ldg(v + 64) * x2;
-            a1 += __ldg(v + 96) * x0 + __ldg(v + 128) * x1 + __ldg(v + 160) * x2;
-            a2 += __ldg(v + 192) * x0 + __ldg(v + 224) * x1 + __ldg(v + 256) * x2;
+            a0 += mg_ld(v) * x0 + mg_ld(v + 32) * x1 + mg_ld(v + 64) * x2;
+            a1 += mg_ld(v + 96) * x0 + mg_ld(v + 128) * x1 + mg_ld(v + 160) * x2;
+            a2 += mg_ld(v + 192) * x0 + mg_ld(v + 224) * x1 + mg_ld(v + 256) * x2;
         }
-        y0 = a0; y1 = a1; y2 = a2;
+        const float is = sc ? sc[1] : 1.f;
+        y0 = a0 * is; y1 = a1 * is; y2 = a2 * is;
+    }
+    // the same row product by NT warps of a CTA (warp = part, lane = row of the CTA's slice): part p visits slice columns p, p + NT, ...
+    // and the parts meet in shared memory; every thread of the CTA must call it (barrier inside); the result is valid for part 0
+    template <int NT>
+    __device__ __forceinline__ void mul_split(int row, int part, const float *__restrict__ x, float &y0, float &y1, float &y2) const
+    {
+        int S = row >> 5, lane = row & 31;
+        int b0 = slice_base[S], b1 = slice_base[S + 1];
+        float a0 = 0, a1 = 0, a2 = 0;
+#pragma unroll 2
+        for (int b = b0 + 32 * part; b < b1; b += 32 * NT) {
+            int col = __ldg(colidx + b + lane);
+            const VT *v = val + (long long)b * 9 + lane;
+            float x0 = x[3 * col], x1 = x[3 * col + 1], x2 = x[3 * col + 2];
+            a0 += mg_ld(v) * x0 + mg_ld(v + 32) * x1 + mg_ld(v + 64) * x2;
+            a1 += mg_ld(v + 96) * x0 + mg_ld(v + 128) * x1 + mg_ld(v + 160) * x2;
+            a2 += mg_ld(v + 192) * x0 + mg_ld(v + 224) * x1 + mg_ld(v + 256) * x2;
+        }
+        __shared__ float sp[NT][3][32];
+        sp[part][0][lane] = a0; sp[part][1][lane] = a1; sp[part][2][lane] = a2;
+        __syncthreads();
+        if (part == 0) {
+#pragma unroll
+            for (int q = 1; q < NT; q++) { a0 += sp[q][0][lane]; a1 += sp[q][1][lane]; a2 += sp[q][2][lane]; }
+        }
+        const float is = sc ? sc[1] : 1.f;
+        y0 = a0 * is; y1 = a1 * is; y2 = a2 * is;
     }
 };
+typedef SellOpT<float> SellOp;
 // Stencil levels: one WARP per vertex.  The 225 values of a vertex row (25 slots x 3x3) are contiguous, so the warp
 // streams them with 8 fully coalesced loads; lane e handles element e = slot*9 + comp of each 32-chunk, multiplies by
 // the matching component of the neighbour's x and the three row sums are formed with a shuffle reduction.  (A
@@ -55,11 +87,14 @@ struct SellOp {
 //   small levels  (sv, se) = (225, 1): row-contiguous, one warp per vertex -- latency bound, wants few loads per thread;
 //   large levels  (sv, se) = (1, nvp): element-major, one THREAD per vertex with the 25 slots fully unrolled and
 //                 clamped neighbour indices -- 225 independent coalesced loads per thread, bandwidth bound.
-struct StencilOp {
-    const float *val;
+template <class VT>
+struct StencilOpT {
+    const VT *val;
     int n0, n1;
     long long sv, se;
+    const float *sc;             // {scale, 1 / scale} of the stored values (NULL: stored = true value)
 };
+typedef StencilOpT<float> StencilOp;
 __device__ __forceinline__ void stencil_row_warp(const StencilOp &A, int v, int lane, const float *__restrict__ x, float &y0, float &y1, float &y2)
 {
     int I = v / A.n1, J = v - I * A.n1;
@@ -123,10 +158,11 @@ __global__ void __launch_bounds__(256) k_cheb_first(int nrows, const float *__re
 // d = a d + c D^-1 (b - A x_in) ; x_out = x_in + d     (b == nullptr: b = 0; x_out == nullptr: not stored)
 // acc_mode 1: acc += b . x_out      acc_mode 2: acc += d . d
 // thread-per-vertex product for element-major levels
-__device__ __forceinline__ void stencil_row_thread(const StencilOp &A, int v, const float *__restrict__ x, float &y0, float &y1, float &y2)
+template <class VT>
+__device__ __forceinline__ void stencil_row_thread(const StencilOpT<VT> &A, int v, const float *__restrict__ x, float &y0, float &y1, float &y2)
 {
     int I = v / A.n1, J = v - I * A.n1;
-    const float *a = A.val + (size_t)v * A.sv;
+    const VT *a = A.val + (size_t)v * A.sv;
     const long long se = A.se;
     float a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
@@ -135,48 +171,62 @@ __device__ __forceinline__ void stencil_row_thread(const StencilOp &A, int v, co
         int ii = min(max(I + dI, 0), A.n0 - 1), jj = min(max(J + dJ, 0), A.n1 - 1);     // out-of-grid slots hold zeros
         int u = ii * A.n1 + jj;
         float x0 = x[3 * u], x1 = x[3 * u + 1], x2 = x[3 * u + 2];
-        const float *q = a + (size_t)(slot * 9) * se;
-        a0 += __ldg(q) * x0 + __ldg(q + se) * x1 + __ldg(q + 2 * se) * x2;
-        a1 += __ldg(q + 3 * se) * x0 + __ldg(q + 4 * se) * x1 + __ldg(q + 5 * se) * x2;
-        a2 += __ldg(q + 6 * se) * x0 + __ldg(q + 7 * se) * x1 + __ldg(q + 8 * se) * x2;
+        const VT *q = a + (size_t)(slot * 9) * se;
+        a0 += mg_ld(q) * x0 + mg_ld(q + se) * x1 + mg_ld(q + 2 * se) * x2;
+        a1 += mg_ld(q + 3 * se) * x0 + mg_ld(q + 4 * se) * x1 + mg_ld(q + 5 * se) * x2;
+        a2 += mg_ld(q + 6 * se) * x0 + mg_ld(q + 7 * se) * x1 + mg_ld(q + 8 * se) * x2;
     }
-    y0 = a0; y1 = a1; y2 = a2;
+    const float is = A.sc ? A.sc[1] : 1.f;
+    y0 = a0 * is; y1 = a1 * is; y2 = a2 * is;
 }
-// two threads per vertex (even / odd slots): a 354 x 354 level has only 125 k vertices = 41 % of the resident thread slots
-// of 148 SMs, so halving the work per thread doubles the loads in flight; partial sums are combined with one shuffle
-__device__ __forceinline__ void stencil_row_pair(const StencilOp &A, int v, int half, const float *__restrict__ x, float &y0, float &y1, float &y2)
+// NT threads per vertex (slots part, part + NT, ...): a 354 x 354 level has only 125 k vertices = 41 % of the resident thread slots of
+// 148 SMs and a 177 x 177 level 10 % -- these levels are bound by the LATENCY of the 25 dependent slot visits of a thread, not by bytes
+// (ncu, 177 x 177 with two threads per vertex: 13 resident warps per SM, 27 of 31 cycles per instruction on the long scoreboard), so the
+// work per thread is cut until the loads in flight cover the memory latency.  CTA = NT warps x 32 rows.
+template <class VT, int NT>
+__device__ __forceinline__ void stencil_row_split(const StencilOpT<VT> &A, int v, int part, const float *__restrict__ x, float &y0, float &y1, float &y2)
 {
     int I = v / A.n1, J = v - I * A.n1;
-    const float *a = A.val + (size_t)v * A.sv;
+    const VT *a = A.val + (size_t)v * A.sv;
     const long long se = A.se;
     float a0 = 0, a1 = 0, a2 = 0;
 #pragma unroll
-    for (int q = 0; q < 13; q++) {
-        int slot = 2 * q + half;
+    for (int q = 0; q < (25 + NT - 1) / NT; q++) {
+        int slot = NT * q + part;
         if (slot < 25) {
             int dI = slot / 5 - 2, dJ = slot - (slot / 5) * 5 - 2;
             int ii = min(max(I + dI, 0), A.n0 - 1), jj = min(max(J + dJ, 0), A.n1 - 1);
             int u = ii * A.n1 + jj;
             float x0 = x[3 * u], x1 = x[3 * u + 1], x2 = x[3 * u + 2];
-            const float *p = a + (size_t)(slot * 9) * se;
-            a0 += __ldg(p) * x0 + __ldg(p + se) * x1 + __ldg(p + 2 * se) * x2;
-            a1 += __ldg(p + 3 * se) * x0 + __ldg(p + 4 * se) * x1 + __ldg(p + 5 * se) * x2;
-            a2 += __ldg(p + 6 * se) * x0 + __ldg(p + 7 * se) * x1 + __ldg(p + 8 * se) * x2;
+            const VT *p = a + (size_t)(slot * 9) * se;
+            a0 += mg_ld(p) * x0 + mg_ld(p + se) * x1 + mg_ld(p + 2 * se) * x2;
+            a1 += mg_ld(p + 3 * se) * x0 + mg_ld(p + 4 * se) * x1 + mg_ld(p + 5 * se) * x2;
+            a2 += mg_ld(p + 6 * se) * x0 + mg_ld(p + 7 * se) * x1 + mg_ld(p + 8 * se) * x2;
         }
     }
-    a0 += __shfl_xor_sync(0xffffffffu, a0, 1); a1 += __shfl_xor_sync(0xffffffffu, a1, 1); a2 += __shfl_xor_sync(0xffffffffu, a2, 1);
-    y0 = a0; y1 = a1; y2 = a2;
+    // warp `part` of the CTA holds the partial sums of the CTA's 32 rows (lane = row): consecutive lanes read consecutive elements, so
+    // every load is a full line whatever NT is; the parts meet in shared memory
+    __shared__ float sp[NT][3][32];
+    const int lane = threadIdx.x & 31;
+    sp[part][0][lane] = a0; sp[part][1][lane] = a1; sp[part][2][lane] = a2;
+    __syncthreads();
+    if (part == 0) {
+#pragma unroll
+        for (int q = 1; q < NT; q++) { a0 += sp[q][0][lane]; a1 += sp[q][1][lane]; a2 += sp[q][2][lane]; }
+    }
+    const float is = A.sc ? A.sc[1] : 1.f;
+    y0 = a0 * is; y1 = a1 * is; y2 = a2 * is;
 }
-__global__ void __launch_bounds__(256) k_cheb_step_stencil_t2(StencilOp A, int nv, const float *__restrict__ dinv, const float *__restrict__ b,
+template <class VT, int NT>
+__global__ void __launch_bounds__(32 * NT) k_cheb_step_stencil_t2(StencilOpT<VT> A, int nv, const float *__restrict__ dinv, const float *__restrict__ b,
                                                               const float *__restrict__ x_in, float *d, float *x_out,
                                                               const float *__restrict__ coef, double *acc, int acc_mode)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = t >> 1, half = t & 1;
+    int row = blockIdx.x * 32 + (threadIdx.x & 31), half = threadIdx.x >> 5;
     double s = 0;
     float y0 = 0, y1 = 0, y2 = 0;
     bool live = row < nv;
-    stencil_row_pair(A, live ? row : nv - 1, half, x_in, y0, y1, y2);      // all lanes take part in the shuffle
+    stencil_row_split<VT, NT>(A, live ? row : nv - 1, half, x_in, y0, y1, y2);      // every thread reaches the barrier inside
     if (live && half == 0) {
         float a = coef[0], c = coef[1];
         float b0 = 0, b1 = 0, b2 = 0;
@@ -195,16 +245,17 @@ __global__ void __launch_bounds__(256) k_cheb_step_stencil_t2(StencilOp A, int n
     }
     if (acc) block_atomic_sum(s, acc);
 }
-__global__ void __launch_bounds__(256) k_mg_residual_stencil_t2(StencilOp A, int nv, const float *__restrict__ b, const float *__restrict__ x, float *r)
+template <class VT, int NT>
+__global__ void __launch_bounds__(32 * NT) k_mg_residual_stencil_t2(StencilOpT<VT> A, int nv, const float *__restrict__ b, const float *__restrict__ x, float *r)
 {
-    int t = blockIdx.x * blockDim.x + threadIdx.x;
-    int row = t >> 1, half = t & 1;
+    int row = blockIdx.x * 32 + (threadIdx.x & 31), half = threadIdx.x >> 5;
     float y0, y1, y2;
     bool live = row < nv;
-    stencil_row_pair(A, live ? row : nv - 1, half, x, y0, y1, y2);
+    stencil_row_split<VT, NT>(A, live ? row : nv - 1, half, x, y0, y1, y2);
     if (live && half == 0) { r[3 * row] = b[3 * row] - y0; r[3 * row + 1] = b[3 * row + 1] - y1; r[3 * row + 2] = b[3 * row + 2] - y2; }
 }
-__global__ void __launch_bounds__(128) k_cheb_step_stencil_t(StencilOp A, int nv, const float *__restrict__ dinv, const float *__restrict__ b,
+template <class VT>
+__global__ void __launch_bounds__(128) k_cheb_step_stencil_t(StencilOpT<VT> A, int nv, const float *__restrict__ dinv, const float *__restrict__ b,
                                                              const float *__restrict__ x_in, float *d, float *x_out,
                                                              const float *__restrict__ coef, double *acc, int acc_mode)
 {
@@ -230,7 +281,8 @@ __global__ void __launch_bounds__(128) k_cheb_step_stencil_t(StencilOp A, int nv
     }
     if (acc) block_atomic_sum(s, acc);
 }
-__global__ void __launch_bounds__(128) k_mg_residual_stencil_t(StencilOp A, int nv, const float *__restrict__ b, const float *__restrict__ x, float *r)
+template <class VT>
+__global__ void __launch_bounds__(128) k_mg_residual_stencil_t(StencilOpT<VT> A, int nv, const float *__restrict__ b, const float *__restrict__ x, float *r)
 {
     int row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= nv) return;
@@ -238,16 +290,20 @@ __global__ void __launch_bounds__(128) k_mg_residual_stencil_t(StencilOp A, int 
     stencil_row_thread(A, row, x, y0, y1, y2);
     r[3 * row] = b[3 * row] - y0; r[3 * row + 1] = b[3 * row + 1] - y1; r[3 * row + 2] = b[3 * row + 2] - y2;
 }
-__global__ void __launch_bounds__(256) k_cheb_step_sell(SellOp A, int nrows, const float *__restrict__ dinv, const float *__restrict__ b,
-                                                        const float *__restrict__ x_in, float *d, float *x_out,
-                                                        const float *__restrict__ coef, double *acc, int acc_mode)
+template <class VT, int NT>
+__global__ void __launch_bounds__(NT == 1 ? 256 : 32 * NT) k_cheb_step_sell(SellOpT<VT> A, int nrows, const float *__restrict__ dinv, const float *__restrict__ b,
+                                                                            const float *__restrict__ x_in, float *d, float *x_out,
+                                                                            const float *__restrict__ coef, double *acc, int acc_mode)
 {
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
+    // NT == 1: one thread per row; else CTA = one slice (32 rows) x NT warps splitting its columns (rows are allocated in whole slices)
+    int row = NT == 1 ? blockIdx.x * blockDim.x + threadIdx.x : blockIdx.x * 32 + (threadIdx.x & 31);
+    const int part = NT == 1 ? 0 : (threadIdx.x >> 5);
     double s = 0;
-    if (row < nrows) {
+    float y0 = 0, y1 = 0, y2 = 0;
+    if (NT > 1) A.template mul_split<NT>(row, part, x_in, y0, y1, y2);
+    if (row < nrows && part == 0) {
         float a = coef[0], c = coef[1];
-        float y0, y1, y2;
-        A.mul(row, x_in, y0, y1, y2);
+        if (NT == 1) A.mul(row, x_in, y0, y1, y2);
         float b0 = 0, b1 = 0, b2 = 0;
         if (b) { b0 = b[3 * row]; b1 = b[3 * row + 1]; b2 = b[3 * row + 2]; }
         float r0 = b0 - y0, r1 = b1 - y1, r2 = b2 - y2;
@@ -293,12 +349,15 @@ __global__ void __launch_bounds__(256) k_cheb_step_stencil(StencilOp A, int nv, 
     }
     if (acc) block_atomic_sum(s, acc);
 }
-__global__ void __launch_bounds__(256) k_mg_residual_sell(SellOp A, int nrows, const float *__restrict__ b, const float *__restrict__ x, float *r)
+template <class VT, int NT>
+__global__ void __launch_bounds__(NT == 1 ? 256 : 32 * NT) k_mg_residual_sell(SellOpT<VT> A, int nrows, const float *__restrict__ b, const float *__restrict__ x, float *r)
 {
-    int row = blockIdx.x * blockDim.x + threadIdx.x;
-    if (row >= nrows) return;
-    float y0, y1, y2;
-    A.mul(row, x, y0, y1, y2);
+    int row = NT == 1 ? blockIdx.x * blockDim.x + threadIdx.x : blockIdx.x * 32 + (threadIdx.x & 31);
+    const int part = NT == 1 ? 0 : (threadIdx.x >> 5);
+    float y0 = 0, y1 = 0, y2 = 0;
+    if (NT > 1) A.template mul_split<NT>(row, part, x, y0, y1, y2);
+    if (row >= nrows || part != 0) return;
+    if (NT == 1) A.mul(row, x, y0, y1, y2);
     r[3 * row] = b[3 * row] - y0; r[3 * row + 1] = b[3 * row + 1] - y1; r[3 * row + 2] = b[3 * row + 2] - y2;
 }
 __global__ void __launch_bounds__(256) k_mg_residual_stencil(StencilOp A, int nv, const float *__restrict__ b, const float *__restrict__ x, float *r)
@@ -528,18 +587,20 @@ __device__ __forceinline__ void inv3_guarded(const float *a, float *inv)
     inv[3] = (float)(c01 * id); inv[4] = (float)(((double)a[0] * a[8] - (double)a[2] * a[6]) * id); inv[5] = (float)(((double)a[2] * a[3] - (double)a[0] * a[5]) * id);
     inv[6] = (float)(c02 * id); inv[7] = (float)(((double)a[1] * a[6] - (double)a[0] * a[7]) * id); inv[8] = (float)(((double)a[0] * a[4] - (double)a[1] * a[3]) * id);
 }
-__global__ void k_dinv_stencil(int nv, long long sv, long long se, const float *__restrict__ val, float *dinv)
+template <class VT>
+__global__ void k_dinv_stencil(int nv, long long sv, long long se, const VT *__restrict__ val, const float *__restrict__ sc, float *dinv)
 {
     int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= nv) return;
     float a[9], inv[9];
+    const float is = sc ? sc[1] : 1.f;
 #pragma unroll
-    for (int c = 0; c < 9; c++) a[c] = val[(size_t)v * sv + (size_t)(12 * 9 + c) * se];
+    for (int c = 0; c < 9; c++) a[c] = mg_ld(val + (size_t)v * sv + (size_t)(12 * 9 + c) * se) * is;
     inv3_guarded(a, inv);
 #pragma unroll
     for (int c = 0; c < 9; c++) dinv[9 * (size_t)v + c] = inv[c];
 }
-__global__ void k_dinv_sell(int n_rows, int n_alloc, const int *__restrict__ diag_pb, const float *__restrict__ val, float *dinv)
+__global__ void k_dinv_sell(int n_rows, int n_alloc, const int *__restrict__ diag_pb, const float *__restrict__ val, float *dinv, unsigned int *maxdiag)
 {
     int r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_alloc) return;
@@ -549,12 +610,50 @@ __global__ void k_dinv_sell(int n_rows, int n_alloc, const int *__restrict__ dia
 #pragma unroll
         for (int c = 0; c < 9; c++) a[c] = val[base + c * 32];
         inv3_guarded(a, inv);
+        if (maxdiag) {
+            // positive floats order like their bit patterns; one atomic per warp
+            float m = fmaxf(fmaxf(a[0], a[4]), a[8]);
+            m = (m > 0.f && m < 3e38f) ? m : 0.f;
+            const unsigned act = __activemask();
+            const unsigned mm = __reduce_max_sync(act, __float_as_uint(m));
+            if ((int)(threadIdx.x & 31) == __ffs(act) - 1) atomicMax(maxdiag, mm);
+        }
     } else {
 #pragma unroll
         for (int c = 0; c < 9; c++) inv[c] = 0.f;
     }
 #pragma unroll
     for (int c = 0; c < 9; c++) dinv[9 * (size_t)r + c] = inv[c];
+}
+// scale of every fp16 level: the level-0 operator is positive semi-definite, so no entry exceeds its largest diagonal entry m; a
+// Galerkin product with bilinear P grows entries by at most (sum of a parent's weights)^2 = 16 per level.  s_l = 2^e / 16^l with
+// 2^e m <= 8192 keeps every stored value below 65504 with a factor 8 to spare; fp32 levels are stored unscaled.
+__global__ void k_mg_scales(int n_levels, unsigned half_mask, const unsigned int *__restrict__ maxdiag, float *scale)
+{
+    int l = threadIdx.x;
+    if (l >= n_levels) return;
+    float s = 1.f;
+    if (half_mask & (1u << l)) {
+        float m = __uint_as_float(*maxdiag);
+        if (!(m > 0.f) || !(m < 3e38f)) m = 1.f;
+        int e = (int)floorf(log2f(8192.f / m)) - 4 * l;
+        s = exp2f((float)max(min(e, 60), -60));
+    }
+    scale[2 * l] = s; scale[2 * l + 1] = 1.f / s;
+}
+__global__ void k_sell_to_half(long long n, const float *__restrict__ src, const float *__restrict__ sc, __half *dst)
+{
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const float s = sc[0];
+    // four values per thread: 16-byte loads, 8-byte stores
+    if (4 * i + 3 < n) {
+        float4 v = *reinterpret_cast<const float4 *>(src + 4 * i);
+        __half2 lo = __floats2half2_rn(v.x * s, v.y * s), hi = __floats2half2_rn(v.z * s, v.w * s);
+        uint2 o; o.x = *reinterpret_cast<unsigned *>(&lo); o.y = *reinterpret_cast<unsigned *>(&hi);
+        *reinterpret_cast<uint2 *>(dst + 4 * i) = o;
+    } else {
+        for (long long k = 4 * i; k < n; k++) dst[k] = __float2half_rn(src[k] * s);
+    }
 }
 __global__ void k_fill_hash(int n, float *v, unsigned seed)
 {
@@ -609,6 +708,8 @@ int mg_alloc(tsl_ctx *ctx)
     mg.cloth_offset = c.offset;
     int n0 = c.N + 1, n1 = c.M + 1;
     int nrows0 = ctx->A.n_slices * 32;
+    { const char *e = getenv("TSL_MG_HALF"); mg.use_half = e ? atoi(e) : 1; }
+    { const char *e = getenv("TSL_MG_SELL_SPLIT"); mg.sell_split = e ? atoi(e) : 4; if (mg.sell_split != 2 && mg.sell_split != 4) mg.sell_split = 1; }
     for (int l = 0; l < TSL_MG_MAX_LEVELS; l++) {
         MgLevel &L = mg.lev[l];
         L.n0 = n0; L.n1 = n1; L.nv = n0 * n1; L.nvp = pad32(L.nv);
@@ -617,6 +718,11 @@ int mg_alloc(tsl_ctx *ctx)
         size_t vb = sizeof(float) * 3 * (size_t)std::max(l == 0 ? nrows0 : L.nrows, 32);
         CK(cudaMalloc(&L.val, sizeof(float) * 225 * (size_t)L.nvp));
         CK(cudaMemset(L.val, 0, sizeof(float) * 225 * (size_t)L.nvp));
+        L.half = (mg.use_half && L.sv == 1) ? 1 : 0;                 // the bandwidth-bound (element-major) levels; small ones are latency-bound
+        if (L.half && l > 0) {
+            CK(cudaMalloc(&L.val16, sizeof(__half) * 225 * (size_t)L.nvp));
+            CK(cudaMemset(L.val16, 0, sizeof(__half) * 225 * (size_t)L.nvp));
+        }
         CK(cudaMalloc(&L.dinv, sizeof(float) * 9 * (size_t)std::max(l == 0 ? nrows0 : L.nrows, 32)));
         for (int q = 0; q < 2; q++) {
             CK(cudaMalloc(&L.x[q], vb)); CK(cudaMemset(L.x[q], 0, vb));
@@ -628,8 +734,20 @@ int mg_alloc(tsl_ctx *ctx)
         if (std::min(n0, n1) <= 6) break;
         n0 = (n0 - 1) / 2 + 1; n1 = (n1 - 1) / 2 + 1;
     }
+    {
+        std::vector<float> ones(2 * TSL_MG_MAX_LEVELS, 1.f);
+        CK(cudaMalloc(&mg.scale, sizeof(float) * ones.size()));
+        CK(cudaMemcpy(mg.scale, ones.data(), sizeof(float) * ones.size(), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&mg.maxdiag, sizeof(unsigned int)));
+        CK(cudaMemset(mg.maxdiag, 0, sizeof(unsigned int)));
+        if (mg.lev[0].half) {
+            CK(cudaMalloc(&ctx->A.val16m, sizeof(__half) * 9 * (size_t)ctx->A.nnzb_pad));
+            CK(cudaMemset(ctx->A.val16m, 0, sizeof(__half) * 9 * (size_t)ctx->A.nnzb_pad));
+        }
+    }
     // levels from tail_level on (<= 1024 vertices each, row-major, at most TSL_MG_TAIL_MAX of them) run in one fused kernel
-    { const char *e = getenv("TSL_MG_PAIR"); mg.pair_threads = e ? atoi(e) : 1; }
+    { const char *e = getenv("TSL_MG_PAIR"); mg.pair_threads = e ? atoi(e) : 1; }       // 0: one thread per vertex, 1: automatic split, 2 / 4 / 8: fixed
+    if (mg.pair_threads != 0 && mg.pair_threads != 1 && mg.pair_threads != 2 && mg.pair_threads != 4 && mg.pair_threads != 8 && mg.pair_threads != 16) mg.pair_threads = 1;
     mg.tail_level = -1;
     for (int l = 1; l < mg.n_levels; l++)
         if (mg.lev[l].nv <= 1024 && mg.n_levels - l <= TSL_MG_TAIL_MAX) { mg.tail_level = l; break; }
@@ -652,8 +770,8 @@ int mg_alloc(tsl_ctx *ctx)
             CK(cudaEventCreateWithFlags(&mg.ev_ready[l], cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&mg.ev_done[l], cudaEventDisableTiming));
         }
-    CK(cudaFuncSetAttribute(k_galerkin_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSL_GAL_SMEM));
-    CK(cudaFuncSetAttribute(k_galerkin_sell_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSL_GAL_SMEM));
+    CK(cudaFuncSetAttribute(k_galerkin_tiled<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSL_GAL_SMEM));
+    CK(cudaFuncSetAttribute(k_galerkin_sell_tiled<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TSL_GAL_SMEM));
     return TSL_OK;
 }
 
@@ -662,10 +780,12 @@ void mg_free(tsl_ctx *ctx)
     MgDev &mg = ctx->mg;
     for (int l = 0; l < mg.n_levels; l++) {
         MgLevel &L = mg.lev[l];
-        cudaFree(L.val); cudaFree(L.dinv); cudaFree(L.b); cudaFree(L.r); cudaFree(L.d);
+        cudaFree(L.val); cudaFree(L.val16); cudaFree(L.dinv); cudaFree(L.b); cudaFree(L.r); cudaFree(L.d);
+        L.val16 = nullptr;
         for (int q = 0; q < 2; q++) { cudaFree(L.x[q]); cudaFree(L.pv[q]); }
     }
-    cudaFree(mg.coef); cudaFree(mg.powc); cudaFree(mg.pow_acc); cudaFree(mg.lmax);
+    cudaFree(mg.coef); cudaFree(mg.powc); cudaFree(mg.pow_acc); cudaFree(mg.lmax); cudaFree(mg.scale); cudaFree(mg.maxdiag);
+    cudaFree(ctx->A.val16m); ctx->A.val16m = nullptr;
     for (int l = 0; l < TSL_MG_MAX_LEVELS; l++) {
         if (mg.side[l]) cudaStreamDestroy(mg.side[l]);
         if (mg.ev_ready[l]) cudaEventDestroy(mg.ev_ready[l]);
@@ -675,19 +795,60 @@ void mg_free(tsl_ctx *ctx)
     mg.n_levels = 0;
 }
 
-static SellOp sell_op(tsl_ctx *ctx, const float *val) { SellOp o; o.slice_base = ctx->A.slice_base; o.colidx = ctx->A.colidx; o.val = val; return o; }
-static StencilOp stencil_op(const MgLevel &L) { StencilOp o; o.val = L.val; o.n0 = L.n0; o.n1 = L.n1; o.sv = L.sv; o.se = L.se; return o; }
+static SellOp sell_op(tsl_ctx *ctx, const float *val) { SellOp o; o.slice_base = ctx->A.slice_base; o.colidx = ctx->A.colidx; o.val = val; o.sc = nullptr; return o; }
+static SellOpT<__half> sell_op16(tsl_ctx *ctx)
+{
+    SellOpT<__half> o; o.slice_base = ctx->A.slice_base; o.colidx = ctx->A.colidx; o.val = (const __half *)ctx->A.val16m; o.sc = ctx->mg.scale; return o;
+}
+// threads per vertex on an element-major level (TSL_MG_PAIR = 2 / 4 / 8 / 16 overrides)
+static int split_threads(tsl_ctx *ctx, const MgLevel &L)
+{
+    if (ctx->mg.pair_threads > 1) return ctx->mg.pair_threads;
+    return 16;                          // measured at 1 M triangles (levels 354^2, 177^2): PCG iteration 602 / 571 / 558 / 525 us for 2 / 4 / 8 / 16
+                                        // threads per vertex (the last two with the level-0 slices split over 4 warps: 543 / 525)
+}
+static StencilOp stencil_op(const MgLevel &L) { StencilOp o; o.val = L.val; o.n0 = L.n0; o.n1 = L.n1; o.sv = L.sv; o.se = L.se; o.sc = nullptr; return o; }
+static StencilOpT<__half> stencil_op16(tsl_ctx *ctx, int l)
+{
+    const MgLevel &L = ctx->mg.lev[l];
+    StencilOpT<__half> o; o.val = (const __half *)L.val16; o.n0 = L.n0; o.n1 = L.n1; o.sv = L.sv; o.se = L.se; o.sc = ctx->mg.scale + 2 * l; return o;
+}
 
 // d = a d + c D^-1 (b - A x_in), x_out = x_in + d on level l (level 0 smooths with the clamped matrix)
 static void launch_step(tsl_ctx *ctx, int l, const float *b, const float *x_in, float *d, float *x_out, const float *coef, double *acc, int mode)
 {
     MgLevel &L = ctx->mg.lev[l];
-    if (l == 0)
-        k_cheb_step_sell<<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32m), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
-    else if (L.sv == 1 && ctx->mg.pair_threads)
-        k_cheb_step_stencil_t2<<<GRID(2LL * L.nv, 256), 256, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    const int sn = ctx->mg.sell_split;
+    if (l == 0 && L.half && sn == 4)
+        k_cheb_step_sell<__half, 4><<<GRID(L.nrows, 32), 128, 0, ctx->stream>>>(sell_op16(ctx), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    else if (l == 0 && L.half && sn == 2)
+        k_cheb_step_sell<__half, 2><<<GRID(L.nrows, 32), 64, 0, ctx->stream>>>(sell_op16(ctx), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    else if (l == 0 && L.half)
+        k_cheb_step_sell<__half, 1><<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op16(ctx), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    else if (l == 0 && sn == 4)
+        k_cheb_step_sell<float, 4><<<GRID(L.nrows, 32), 128, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32m), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    else if (l == 0 && sn == 2)
+        k_cheb_step_sell<float, 2><<<GRID(L.nrows, 32), 64, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32m), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    else if (l == 0)
+        k_cheb_step_sell<float, 1><<<GRID(L.nrows, 256), 256, 0, ctx->stream>>>(sell_op(ctx, ctx->A.val32m), L.nrows, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    else if (L.sv == 1 && L.half && ctx->mg.pair_threads) {
+        const int nt = split_threads(ctx, L);
+        if (nt == 16) k_cheb_step_stencil_t2<__half, 16><<<GRID(L.nv, 32), 512, 0, ctx->stream>>>(stencil_op16(ctx, l), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        else if (nt == 8) k_cheb_step_stencil_t2<__half, 8><<<GRID(L.nv, 32), 256, 0, ctx->stream>>>(stencil_op16(ctx, l), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        else if (nt == 4) k_cheb_step_stencil_t2<__half, 4><<<GRID(L.nv, 32), 128, 0, ctx->stream>>>(stencil_op16(ctx, l), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        else k_cheb_step_stencil_t2<__half, 2><<<GRID(L.nv, 32), 64, 0, ctx->stream>>>(stencil_op16(ctx, l), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    }
+    else if (L.sv == 1 && L.half)
+        k_cheb_step_stencil_t<__half><<<GRID(L.nv, 128), 128, 0, ctx->stream>>>(stencil_op16(ctx, l), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    else if (L.sv == 1 && ctx->mg.pair_threads) {
+        const int nt = split_threads(ctx, L);
+        if (nt == 16) k_cheb_step_stencil_t2<float, 16><<<GRID(L.nv, 32), 512, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        else if (nt == 8) k_cheb_step_stencil_t2<float, 8><<<GRID(L.nv, 32), 256, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        else if (nt == 4) k_cheb_step_stencil_t2<float, 4><<<GRID(L.nv, 32), 128, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        else k_cheb_step_stencil_t2<float, 2><<<GRID(L.nv, 32), 64, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+    }
     else if (L.sv == 1)
-        k_cheb_step_stencil_t<<<GRID(L.nv, 128), 128, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
+        k_cheb_step_stencil_t<float><<<GRID(L.nv, 128), 128, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     else
         k_cheb_step_stencil<<<GRID(32LL * L.nv, 256), 256, 0, ctx->stream>>>(stencil_op(L), L.nv, L.dinv, b, x_in, d, x_out, coef, acc, mode);
     ctx->launches++;
@@ -701,31 +862,49 @@ int mg_setup(tsl_ctx *ctx)
     const SellMatrix &A = ctx->A;
     int nrows0 = A.n_slices * 32;
     // the hierarchy is built from (and its level-0 smoother keeps using) a snapshot, so that the caller may refresh
-    // A.val32c every Newton iteration while the preconditioner stays self-consistent until the next build
+    // A.val32c every Newton iteration while the preconditioner stays self-consistent until the next build.  The snapshot is fp16
+    // (A.val16m, scaled) when the level-0 operator is stored in half precision, else a plain fp32 copy (A.val32m).
+    const bool half0 = mg.n_levels > 0 && mg.lev[0].half;
     CK(cudaMemcpyAsync(A.val32m, A.val32c, sizeof(float) * 9 * (size_t)A.nnzb_pad, cudaMemcpyDeviceToDevice, s));
     if (mg.n_levels == 0) {          // no cloth: block-Jacobi only
-        k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32m, ctx->minv32);
+        k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32m, ctx->minv32, nullptr);
         ctx->launches++;
         return TSL_OK;
     }
     const ClothDev &c = ctx->cloths[0];
     MgLevel &L0 = mg.lev[0];
-    k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32m, L0.dinv);
+    unsigned half_mask = 0;
+    for (int l = 0; l < mg.n_levels; l++) if (mg.lev[l].half) half_mask |= 1u << l;
+    if (half_mask) CK(cudaMemsetAsync(mg.maxdiag, 0, sizeof(unsigned int), s));
+    k_dinv_sell<<<GRID(nrows0, 256), 256, 0, s>>>(A.n_rows, nrows0, A.diag_pb, A.val32m, L0.dinv, half_mask ? mg.maxdiag : nullptr);
     ctx->launches++;
+    if (half_mask) {
+        k_mg_scales<<<1, 32, 0, s>>>(mg.n_levels, half_mask, mg.maxdiag, mg.scale);
+        ctx->launches++;
+    }
+    if (half0) {
+        long long n = 9LL * A.nnzb_pad;
+        k_sell_to_half<<<GRID((n + 3) / 4, 256), 256, 0, s>>>(n, A.val32m, mg.scale, (__half *)A.val16m);
+        ctx->launches++;
+    }
     const bool fork = mg.fork && mg.side[0];
     CK(cudaMemsetAsync(mg.pow_acc, 0, sizeof(double) * TSL_MG_MAX_LEVELS * 16, s));
     if (fork) CK(cudaEventRecord(mg.ev_ready[0], s));
-    // Galerkin products, tiled (tsl_mg_kernels.cuh): level 0 -> 1 straight from the sliced-ELL snapshot (no stencil copy of the fine
-    // level), the others from the level's own stencil layout; TSL_MG_TILED=0 falls back to the entrywise kernels
+    // Galerkin products, tiled (tsl_mg_kernels.cuh), all in fp32: level 0 -> 1 straight from the sliced-ELL snapshot (no stencil copy of
+    // the fine level), the others from the level's own stencil layout; a level whose smoother reads fp16 gets that copy written in the
+    // same pass.  TSL_MG_TILED=0 (fp32 storage only) falls back to the entrywise kernels
     for (int l = 0; l + 1 < mg.n_levels; l++) {
         MgLevel &F = mg.lev[l], &C = mg.lev[l + 1];
-        if (mg.tiled_galerkin) {
+        const float *scC = mg.scale + 2 * (l + 1);
+        if (mg.tiled_galerkin || half_mask) {
             dim3 grid(GRID(C.n1, TSL_TCJ), GRID(C.n0, TSL_TCI));
+            const int *fz = ctx->frozen + 3 * (size_t)c.offset;
+            __half *h = C.half ? (__half *)C.val16 : nullptr;
             if (l == 0)
-                k_galerkin_sell_tiled<<<grid, 256, TSL_GAL_SMEM, s>>>(c.offset, F.n0, F.n1, A.slice_base, A.colidx, A.val32m, A.diag_pb,
-                                                                     ctx->frozen + 3 * (size_t)c.offset, C.val, C.n0, C.n1, C.sv, C.se);
+                k_galerkin_sell_tiled<__half><<<grid, 256, TSL_GAL_SMEM, s>>>(c.offset, F.n0, F.n1, A.slice_base, A.colidx, A.val32m, A.diag_pb, fz,
+                                                                             C.val, h, C.n0, C.n1, C.sv, C.se, scC);
             else
-                k_galerkin_tiled<<<grid, 256, TSL_GAL_SMEM, s>>>(F.val, F.n0, F.n1, F.sv, F.se, C.val, C.n0, C.n1, C.sv, C.se);
+                k_galerkin_tiled<__half><<<grid, 256, TSL_GAL_SMEM, s>>>(F.val, F.n0, F.n1, F.sv, F.se, C.val, h, C.n0, C.n1, C.sv, C.se, scC);
             ctx->launches++;
         } else {
             if (l == 0) {
@@ -739,7 +918,7 @@ int mg_setup(tsl_ctx *ctx)
                 k_galerkin<false><<<GRID(nt, 128), 128, 0, s>>>(F.val, F.n0, F.n1, F.sv, F.se, nullptr, C.val, C.n0, C.n1, C.sv, C.se);
             ctx->launches++;
         }
-        k_dinv_stencil<<<GRID(C.nv, 256), 256, 0, s>>>(C.nv, C.sv, C.se, C.val, C.dinv);
+        k_dinv_stencil<float><<<GRID(C.nv, 256), 256, 0, s>>>(C.nv, C.sv, C.se, C.val, nullptr, C.dinv);
         ctx->launches++;
         if (fork) CK(cudaEventRecord(mg.ev_ready[l + 1], s));
     }
@@ -821,9 +1000,18 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
     MgLevel &C = mg.lev[l + 1];
     int off = (l == 0) ? mg.cloth_offset : 0;
     const int *mask = (l == 0) ? ctx->frozen : nullptr;
-    if (l == 0) k_mg_residual_sell<<<GRID(L.nrows, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32m), L.nrows, b, cur, L.r);
-    else if (L.sv == 1 && mg.pair_threads) k_mg_residual_stencil_t2<<<GRID(2LL * L.nv, 256), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
-    else if (L.sv == 1) k_mg_residual_stencil_t<<<GRID(L.nv, 128), 128, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
+    // the residual that goes down to the coarse grid is taken with the fp32 operator (see tsl_mg_kernels.cuh)
+    if (l == 0 && mg.sell_split == 4) k_mg_residual_sell<float, 4><<<GRID(L.nrows, 32), 128, 0, s>>>(sell_op(ctx, ctx->A.val32m), L.nrows, b, cur, L.r);
+    else if (l == 0 && mg.sell_split == 2) k_mg_residual_sell<float, 2><<<GRID(L.nrows, 32), 64, 0, s>>>(sell_op(ctx, ctx->A.val32m), L.nrows, b, cur, L.r);
+    else if (l == 0) k_mg_residual_sell<float, 1><<<GRID(L.nrows, 256), 256, 0, s>>>(sell_op(ctx, ctx->A.val32m), L.nrows, b, cur, L.r);
+    else if (L.sv == 1 && mg.pair_threads) {
+        const int nt = split_threads(ctx, L);
+        if (nt == 16) k_mg_residual_stencil_t2<float, 16><<<GRID(L.nv, 32), 512, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
+        else if (nt == 8) k_mg_residual_stencil_t2<float, 8><<<GRID(L.nv, 32), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
+        else if (nt == 4) k_mg_residual_stencil_t2<float, 4><<<GRID(L.nv, 32), 128, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
+        else k_mg_residual_stencil_t2<float, 2><<<GRID(L.nv, 32), 64, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
+    }
+    else if (L.sv == 1) k_mg_residual_stencil_t<float><<<GRID(L.nv, 128), 128, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     else k_mg_residual_stencil<<<GRID(32LL * L.nv, 256), 256, 0, s>>>(stencil_op(L), L.nv, b, cur, L.r);
     const bool c_last = (l + 1 == mg.n_levels - 1);
     const bool fuse_first = (l + 1 != mg.tail_level) && ((c_last ? mg.coarse_degree : mg.degree) >= 2);

@@ -3,9 +3,22 @@
 #pragma once
 #ifndef TSL_CUDA_EMU
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #endif
 
 namespace tsl {
+
+// The SMOOTHER's matrix passes on the bandwidth-bound levels (level-0 snapshot, element-major coarse levels) may read an fp16 copy of the
+// operator, scaled by a power of two per level so that the largest entry stays far from 65504 (tsl_mg.cu: k_mg_scales): damping the
+// high-frequency error does not need more than 11 bits of the operator.  Everything that feeds a coarse-grid SOLVE -- the Galerkin
+// chain and the residual that is restricted -- stays in fp32: with all-fp16 operators the 1 M-triangle sheet at rest (lambda_min / a_ii
+// ~ 1e-3) needed 13 200 PCG iterations for a step that takes 60 (measured, profiles/README.md).  mg_ld / mg_st hide the storage type.
+__device__ __forceinline__ float mg_ld(const float *p) { return *p; }
+__device__ __forceinline__ void mg_st(float *p, float v) { *p = v; }
+#ifndef TSL_CUDA_EMU
+__device__ __forceinline__ float mg_ld(const __half *p) { return __half2float(*p); }
+__device__ __forceinline__ void mg_st(__half *p, float v) { *p = __float2half_rn(v); }
+#endif
 
 // 1-D bilinear weight of fine index 2I + a (a in -1..1) towards coarse parent I of nc coarse points
 __device__ __forceinline__ float pw1(int a, int I, int nc) { return a == 0 ? 1.f : (a < 0 ? 0.5f : (I + 1 < nc ? 0.5f : 1.f)); }
@@ -113,9 +126,11 @@ __global__ void __launch_bounds__(128) k_galerkin(const float *__restrict__ val_
 #endif
 
 // the Galerkin sums of one CTA from the staged fine rows sA[(fi * TFJ + fj) * 225 + slot * 9 + c]; fine window starts at (fi0, fj0)
-template <bool MASK>
+// val_c: the coarse operator in fp32 (the Galerkin chain and the residuals stay in fp32: the smooth modes a coarse level exists for live
+// on cancellations between entries that 11 bits do not preserve); val_h (optional): a scaled fp16 copy for the smoother's matrix passes
+template <bool MASK, class HT>
 __device__ __forceinline__ void galerkin_tile_compute(const float *sA, int fi0, int fj0, int I0, int J0, int n0f, int n1f, const int *__restrict__ mask,
-                                                      float *val_c, int n0c, int n1c, long long svc, long long sec)
+                                                      float *val_c, HT *val_h, int n0c, int n1c, long long svc, long long sec, float h_mul)
 {
     for (int item = threadIdx.x; item < TSL_TCI * TSL_TCJ * 25; item += blockDim.x) {
         // consecutive threads = consecutive J of one (I, slot): coalesced stores on element-major levels
@@ -162,15 +177,22 @@ __device__ __forceinline__ void galerkin_tile_compute(const float *sA, int fi0, 
                 }
             }
         }
-        float *dst = val_c + (size_t)(I * n1c + J) * svc + (size_t)(slot * 9) * sec;
+        const size_t o = (size_t)(I * n1c + J) * svc + (size_t)(slot * 9) * sec;
 #pragma unroll
-        for (int c = 0; c < 9; c++) dst[(size_t)c * sec] = acc[c];
+        for (int c = 0; c < 9; c++) val_c[o + (size_t)c * sec] = acc[c];
+        if (val_h) {
+#pragma unroll
+            for (int c = 0; c < 9; c++) mg_st(val_h + o + (size_t)c * sec, acc[c] * h_mul);
+        }
     }
 }
 
 // level l >= 1 -> l + 1: fine operator in the level's stencil layout (element (v, e) at val_f[v * svf + e * sef])
+// val_h / sc_c (optional): fp16 copy of the coarse operator, stored x sc_c[0]
+template <class HT>
 __global__ void __launch_bounds__(256) k_galerkin_tiled(const float *__restrict__ val_f, int n0f, int n1f, long long svf, long long sef,
-                                                        float *val_c, int n0c, int n1c, long long svc, long long sec)
+                                                        float *val_c, HT *val_h, int n0c, int n1c, long long svc, long long sec,
+                                                        const float *__restrict__ sc_c)
 {
     TSL_DYN_SMEM_F(sA);
     const int I0 = blockIdx.y * TSL_TCI, J0 = blockIdx.x * TSL_TCJ;
@@ -184,14 +206,15 @@ __global__ void __launch_bounds__(256) k_galerkin_tiled(const float *__restrict_
         sA[(size_t)(fi * TSL_TFJ + fj) * 225 + e] = v;
     }
     __syncthreads();
-    galerkin_tile_compute<false>(sA, fi0, fj0, I0, J0, n0f, n1f, nullptr, val_c, n0c, n1c, svc, sec);
+    galerkin_tile_compute<false, HT>(sA, fi0, fj0, I0, J0, n0f, n1f, nullptr, val_c, val_h, n0c, n1c, svc, sec, sc_c ? sc_c[0] : 1.f);
 }
 
 // level 0 -> 1 straight from the sliced-ELL matrix (no stencil copy of the fine level): rows [off, off + n0f * n1f) of the matrix are
 // the cloth grid; mask = frozen flags of those rows' DOFs (relative to `off`): frozen DOFs are left out of the coarse spaces
+template <class HT>
 __global__ void __launch_bounds__(256) k_galerkin_sell_tiled(int off, int n0f, int n1f, const int *__restrict__ slice_base, const int *__restrict__ colidx,
                                                              const float *__restrict__ val, const int *__restrict__ diag_pb, const int *__restrict__ mask,
-                                                             float *val_c, int n0c, int n1c, long long svc, long long sec)
+                                                             float *val_c, HT *val_h, int n0c, int n1c, long long svc, long long sec, const float *__restrict__ sc_c)
 {
     TSL_DYN_SMEM_F(sA);
     const int I0 = blockIdx.y * TSL_TCI, J0 = blockIdx.x * TSL_TCJ;
@@ -221,7 +244,7 @@ __global__ void __launch_bounds__(256) k_galerkin_sell_tiled(int off, int n0f, i
         for (int c = 0; c < 9; c++) dst[c] = src[c * 32];
     }
     __syncthreads();
-    galerkin_tile_compute<true>(sA, fi0, fj0, I0, J0, n0f, n1f, mask, val_c, n0c, n1c, svc, sec);
+    galerkin_tile_compute<true, HT>(sA, fi0, fj0, I0, J0, n0f, n1f, mask, val_c, val_h, n0c, n1c, svc, sec, sc_c ? sc_c[0] : 1.f);
 }
 
 }  // namespace tsl
