@@ -93,7 +93,7 @@ int tsl_destroy(tsl_ctx *ctx)
     cudaFree(ctx->cell_key); cudaFree(ctx->cell_key_sorted); cudaFree(ctx->face_id); cudaFree(ctx->face_id_sorted); cudaFree(ctx->cub_tmp);
     cudaFree(ctx->cflag); cudaFree(ctx->cscan);
     cudaFree(ctx->con.idx); cudaFree(ctx->con.w); cudaFree(ctx->con.k); cudaFree(ctx->con.mu); cudaFree(ctx->con.dx0); cudaFree(ctx->con.T); cudaFree(ctx->con.n);
-    cudaFree(ctx->ks); cudaFreeHost(ctx->ks_host); cudaFree(ctx->red_partial); cudaFree(ctx->red_ticket); cudaFree(ctx->red_out); cudaFreeHost(ctx->red_host);
+    cudaFree(ctx->ks); cudaFreeHost(ctx->ks_host); for (int q = 0; q < 2; q++) if (ctx->ks_ev[q]) cudaEventDestroy(ctx->ks_ev[q]); cudaFree(ctx->red_partial); cudaFree(ctx->red_ticket); cudaFree(ctx->red_out); cudaFreeHost(ctx->red_host);
     cudaFree(ctx->d_kb); cudaFree(ctx->adj_rhs); cudaFree(ctx->adj_z); cudaFree(ctx->error_flag); cudaFree(ctx->zero_border);
     for (auto &t : ctx->tets) { cudaFree(t.tets); cudaFree(t.B); cudaFree(t.W); cudaFree(t.slot); }
     cudaFree(ctx->nc_dev); cudaFree(ctx->cside32); cudaFree(ctx->cside64); cudaFree(ctx->yc); cudaFree(ctx->vgrav);

@@ -235,7 +235,9 @@ struct tsl_ctx {
     int newton_mode = 2;                         // 0 projected-Newton fallback, 1 negative-curvature moves, 2 blended operator
     float *cg_r64tmp = nullptr;                  // [3 n_rows_pad] fp32 staging of fp64 vectors for the V-cycle
     tsl::KrylovScalars *ks = nullptr;            // device
-    tsl::KrylovScalars *ks_host = nullptr;       // pinned
+    tsl::KrylovScalars *ks_host = nullptr;       // pinned [3]: [0] the solver's view, [1..2] read-back slots of the pipelined PCG checks
+    cudaEvent_t ks_ev[2] = { nullptr, nullptr };
+    int pcg_pipeline = 1;                        // check iteration k while k + 1 is already queued (TSL_PCG_PIPELINE=0: synchronise per iteration)
     // reductions
     double *red_partial = nullptr; unsigned int *red_ticket = nullptr; double *red_out = nullptr; double *red_host = nullptr;
     int red_blocks = 0;
