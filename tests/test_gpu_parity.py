@@ -402,3 +402,41 @@ def test_owner_computes_assembly_matches_scatter_and_is_deterministic():
     assert _rel(F2, F0) < 1e-11 and abs(E2 - E0) <= 1e-12 * abs(E0)
     e.assemble(_lib.ASM_RESIDUAL)
     assert np.array_equal(e.residual(), F2) and e.energy() == E2
+
+
+@pytest.mark.parametrize("N", [158, 316])
+def test_vcycle_variants_agree(N, monkeypatch):
+    """the multigrid V-cycle has build-time variants that must be the same preconditioner up to rounding: the small levels as separate
+    graph nodes or fused in one thread-block cluster (TSL_MG_TAIL), fp16 or fp32 operator copies for the smoother passes (TSL_MG_HALF),
+    1 or 16 / 4 warps per 32 rows on the large levels (TSL_MG_PAIR, TSL_MG_SELL_SPLIT).  Same clamped Newton system of a sheet in
+    contact, solved to 1e-11 by PCG with each variant: equal iteration counts (+-3) and solutions."""
+    from thinshelllab_b200.synthetic import LANDING, sheet_scene
+    variants = [dict(TSL_MG_TAIL="0", TSL_MG_HALF="0", TSL_MG_PAIR="0", TSL_MG_SELL_SPLIT="1"),       # the plain fp32 kernels of round 1
+                dict(TSL_MG_TAIL="0"), dict(TSL_MG_TAIL="1"), dict(TSL_MG_TAIL="8"), dict(TSL_MG_TAIL="16"), dict(TSL_MG_TAIL="16", TSL_MG_TAIL_NV="8000"),
+                dict(TSL_MG_HALF="0"), dict(TSL_MG_PAIR="2", TSL_MG_SELL_SPLIT="2")]
+    keys = sorted({k for v in variants for k in v})
+    res = []
+    for var in variants:
+        for k in keys:
+            monkeypatch.delenv(k, raising=False)
+        for k, v in var.items():
+            monkeypatch.setenv(k, v)
+        s = sheet_scene(N, **LANDING)
+        e = s.engine
+        for _ in range(2):
+            assert s.time_step().converged
+        e.prev_pos.copy_(e.pos)
+        e.contact_detect()
+        e.assemble(_lib.ASM_RESIDUAL | _lib.ASM_HESSIAN | _lib.ASM_NEWTON | _lib.ASM_SPD)
+        F = torch.from_numpy(e.residual()).to(e.device)
+        x, (iters, flags, rr) = e.solve(F, rel_tol=1e-11, max_iters=600)
+        assert flags == 0 and rr < 1e-10, (var, iters, flags, rr)
+        res.append((iters, x.cpu().numpy()))
+        del s, e
+        torch.cuda.empty_cache()
+    it0, x0 = res[0]
+    print(f"sheet {N}: PCG iterations per V-cycle variant {[r[0] for r in res]}")
+    for (iters, x), var in zip(res[1:], variants[1:]):
+        assert abs(iters - it0) <= 3, (var, iters, it0)
+        # (two solutions of a kappa ~ 1e6 system to a residual of 1e-11 agree to ~1e-5; identical preconditioners agree much closer)
+        assert np.abs(x - x0).max() <= 1e-3 * np.abs(x0).max(), (var, np.abs(x - x0).max(), np.abs(x0).max())

@@ -116,7 +116,8 @@ struct MgDev {
     int setups = 0;
     int tiled_galerkin = 1;                // Galerkin products by shared-memory tiles (TSL_MG_TILED=0: one thread per coarse entry)
     int pair_threads = 1;                  // element-major levels: 2 threads per vertex (TSL_MG_PAIR=0: one)
-    int tail_level = -1;                   // first level of the fused single-block tail of the V-cycle (-1: none)
+    int tail_level = -1;                   // first level of the fused tail of the V-cycle (-1: none)
+    int tail_cluster = 0;                  // thread blocks of the cluster that runs the tail (1: one block; 0: tail off)
     // side streams of the hierarchy build: the eigenvalue iteration of level l only needs that level's operator, so it runs beside
     // the Galerkin chain that is still producing the coarser levels (TSL_MG_FORK=0: everything on the context's stream)
     // fp16 storage of the operators only the preconditioner reads (level-0 snapshot, element-major coarse levels): TSL_MG_HALF=0 keeps fp32

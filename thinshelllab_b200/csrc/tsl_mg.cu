@@ -388,7 +388,7 @@ __global__ void __launch_bounds__(256) k_apply_dinv(int nrows, const float *__re
 // k_vcycle_tail runs the whole sub-cycle of those levels in ONE thread block (32 warps, one warp per vertex,
 // __syncthreads() between phases; the vectors live in L1/L2).  No __restrict__ / __ldg on vectors here: they are
 // rewritten between phases of the same kernel.
-#define TSL_MG_TAIL_MAX 4
+#define TSL_MG_TAIL_MAX 6
 struct TailLevel { const float *val, *dinv; float *x0, *x1, *b, *r, *d; int n0, n1, nv; };
 struct TailArgs { TailLevel lev[TSL_MG_TAIL_MAX]; int n; int degree, coarse_degree; const float *coef; int first_level; };
 
@@ -415,10 +415,35 @@ __device__ __forceinline__ void tail_row(const TailLevel &L, int v, int lane, co
     }
     y0 = a0; y1 = a1; y2 = a2;
 }
-// d = a d + c D^-1 (b - A x_in), x_out = x_in + d   (first: x_in = 0, no matrix pass)
-__device__ __forceinline__ void tail_step(const TailLevel &L, const float *b, const float *x_in, float *x_out, float a, float c, bool first)
+// The same sub-cycle runs either in ONE thread block (CL = false: barrier = __syncthreads) or in one thread-block CLUSTER (CL = true:
+// the work of a phase is dealt over every warp of the cluster, barrier = barrier.cluster with release / acquire, which also orders the
+// global-memory vectors the CTAs exchange).  A cluster of 16 SMs walks a 45 x 45 level in ~2.5 us per phase where a graph node costs
+// ~3.5 us before it does anything; one SM alone was measured slower than the nodes it replaces.
+struct TailGeo { int tid, nt, warp, nw, lane; };
+template <bool CL>
+__device__ __forceinline__ TailGeo tail_geo()
 {
-    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    TailGeo g;
+    unsigned rank = 0, nranks = 1;
+    if (CL) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+        asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(nranks));
+    }
+    g.tid = (int)(rank * blockDim.x + threadIdx.x); g.nt = (int)(nranks * blockDim.x);
+    g.warp = g.tid >> 5; g.nw = g.nt >> 5; g.lane = threadIdx.x & 31;
+    return g;
+}
+template <bool CL>
+__device__ __forceinline__ void tail_sync()
+{
+    if (CL) asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    else __syncthreads();
+}
+// d = a d + c D^-1 (b - A x_in), x_out = x_in + d   (first: x_in = 0, no matrix pass)
+template <bool CL>
+__device__ __forceinline__ void tail_step(const TailGeo &g, const TailLevel &L, const float *b, const float *x_in, float *x_out, float a, float c, bool first)
+{
+    const int warp = g.warp, lane = g.lane, nw = g.nw;
     for (int v = warp; v < L.nv; v += nw) {
         float y0 = 0, y1 = 0, y2 = 0;
         if (!first) tail_row(L, v, lane, x_in, y0, y1, y2);
@@ -431,12 +456,14 @@ __device__ __forceinline__ void tail_step(const TailLevel &L, const float *b, co
             x_out[3 * v + lane] = (first ? 0.f : x_in[3 * v + lane]) + dq;
         }
     }
-    __syncthreads();
+    tail_sync<CL>();
 }
+template <bool CL>
 __global__ void __launch_bounds__(1024) k_vcycle_tail(TailArgs A)
 {
     const int last = A.n - 1;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    const TailGeo g = tail_geo<CL>();
+    const int lane = g.lane, warp = g.warp, nw = g.nw;
     // ---- downward: pre-smooth, residual, restrict (the coarsest level is solved by the long sweep)
     for (int l = 0; l <= last; l++) {
         const TailLevel &L = A.lev[l];
@@ -445,7 +472,7 @@ __global__ void __launch_bounds__(1024) k_vcycle_tail(TailArgs A)
         for (int k = 0; k < deg; k++) {
             float *out = (k & 1) ? L.x1 : L.x0;
             const float *in = (k & 1) ? L.x0 : L.x1;
-            tail_step(L, L.b, in, out, coef[2 * k], coef[2 * k + 1], k == 0);
+            tail_step<CL>(g, L, L.b, in, out, coef[2 * k], coef[2 * k + 1], k == 0);
         }
         if (l == last) break;
         const float *cur = ((deg - 1) & 1) ? L.x1 : L.x0;
@@ -454,9 +481,9 @@ __global__ void __launch_bounds__(1024) k_vcycle_tail(TailArgs A)
             tail_row(L, v, lane, cur, y0, y1, y2);
             if (lane < 3) L.r[3 * v + lane] = L.b[3 * v + lane] - (lane == 0 ? y0 : (lane == 1 ? y1 : y2));
         }
-        __syncthreads();
+        tail_sync<CL>();
         const TailLevel &C = A.lev[l + 1];
-        for (int cv = threadIdx.x; cv < C.nv; cv += blockDim.x) {
+        for (int cv = g.tid; cv < C.nv; cv += g.nt) {
             int I = cv / C.n1, J = cv - I * C.n1;
             float s0 = 0, s1 = 0, s2 = 0;
             for (int a = -1; a <= 1; a++) {
@@ -473,7 +500,7 @@ __global__ void __launch_bounds__(1024) k_vcycle_tail(TailArgs A)
             }
             C.b[3 * cv] = s0; C.b[3 * cv + 1] = s1; C.b[3 * cv + 2] = s2;
         }
-        __syncthreads();
+        tail_sync<CL>();
     }
     // ---- upward: prolong, post-smooth
     for (int l = last - 1; l >= 0; l--) {
@@ -484,7 +511,7 @@ __global__ void __launch_bounds__(1024) k_vcycle_tail(TailArgs A)
         int steps_c = (l + 1 == last) ? cdeg : 2 * cdeg;
         const float *xc = ((steps_c - 1) & 1) ? C.x1 : C.x0;
         float *cur = ((A.degree - 1) & 1) ? L.x1 : L.x0;
-        for (int fv = threadIdx.x; fv < L.nv; fv += blockDim.x) {
+        for (int fv = g.tid; fv < L.nv; fv += g.nt) {
             int i = fv / L.n1, j = fv - i * L.n1;
             int I0 = i >> 1, J0 = j >> 1, nI = 1, nJ = 1;
             float wI = 1.f, wJ = 1.f;
@@ -499,12 +526,12 @@ __global__ void __launch_bounds__(1024) k_vcycle_tail(TailArgs A)
             float w = wI * wJ;
             cur[3 * fv] += w * s0; cur[3 * fv + 1] += w * s1; cur[3 * fv + 2] += w * s2;
         }
-        __syncthreads();
+        tail_sync<CL>();
         for (int k = 0; k < A.degree; k++) {
             int kk = A.degree + k;                 // continues the ping-pong of the pre-smoothing steps
             float *out = (kk & 1) ? L.x1 : L.x0;
             const float *in = (kk & 1) ? L.x0 : L.x1;
-            tail_step(L, L.b, in, out, coef[2 * k], coef[2 * k + 1], false);
+            tail_step<CL>(g, L, L.b, in, out, coef[2 * k], coef[2 * k + 1], false);
         }
     }
 }
@@ -748,12 +775,21 @@ int mg_alloc(tsl_ctx *ctx)
     // levels from tail_level on (<= 1024 vertices each, row-major, at most TSL_MG_TAIL_MAX of them) run in one fused kernel
     { const char *e = getenv("TSL_MG_PAIR"); mg.pair_threads = e ? atoi(e) : 1; }       // 0: one thread per vertex, 1: automatic split, 2 / 4 / 8: fixed
     if (mg.pair_threads != 0 && mg.pair_threads != 1 && mg.pair_threads != 2 && mg.pair_threads != 4 && mg.pair_threads != 8 && mg.pair_threads != 16) mg.pair_threads = 1;
+    // TSL_MG_TAIL = 0: off; 1: one thread block (levels <= 1024 vertices); N >= 2: one cluster of N thread blocks (N = 8 is portable, 16 needs
+    // the non-portable attribute), levels <= TSL_MG_TAIL_NV vertices (default 2100: from the 45 x 45 level down)
+    // Measured at 1 M / 50 k triangles (PCG iteration, profiles/README.md): separate graph nodes 524 / 128 us, one block 784 / -- us,
+    // cluster of 8: 614 / 184 us, of 16: 568 / 158 us -- a phase that ends in a cluster barrier and starts with an L2 round trip costs
+    // MORE than a ~3.5 us graph node, so the fused tail stays opt-in.
+    { const char *e = getenv("TSL_MG_TAIL"); mg.tail_cluster = e ? atoi(e) : 0; }
+    int tail_nv = mg.tail_cluster > 1 ? 2100 : 1024;
+    { const char *e = getenv("TSL_MG_TAIL_NV"); if (e) tail_nv = atoi(e); }
     mg.tail_level = -1;
     for (int l = 1; l < mg.n_levels; l++)
-        if (mg.lev[l].nv <= 1024 && mg.n_levels - l <= TSL_MG_TAIL_MAX) { mg.tail_level = l; break; }
-    // Measured (profiles/README.md): one SM walking 529 + 144 + 36 vertices through 16 dependent phases is SLOWER than the
-    // ~20 tiny graph nodes it replaces (PCG iteration 784 vs 645 us at 1 M triangles), so the fused tail is opt-in only.
-    { const char *e = getenv("TSL_MG_TAIL"); if (!e || atoi(e) == 0) mg.tail_level = -1; }
+        if (mg.lev[l].sv != 1 && mg.lev[l].nv <= tail_nv && mg.n_levels - l <= TSL_MG_TAIL_MAX) { mg.tail_level = l; break; }
+    if (mg.tail_cluster > 8) {
+        if (cudaFuncSetAttribute(k_vcycle_tail<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); mg.tail_cluster = 8; }
+    }
+    if (mg.tail_cluster == 0) mg.tail_level = -1;
     CK(cudaMalloc(&mg.coef, sizeof(float) * TSL_MG_MAX_LEVELS * TSL_MG_MAX_DEGREE * 2));
     CK(cudaMalloc(&mg.powc, sizeof(float) * TSL_MG_MAX_LEVELS * 4));
     CK(cudaMalloc(&mg.pow_acc, sizeof(double) * TSL_MG_MAX_LEVELS * 16));
@@ -974,7 +1010,16 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
             T.lev[q].val = Q.val; T.lev[q].dinv = Q.dinv; T.lev[q].x0 = Q.x[0]; T.lev[q].x1 = Q.x[1];
             T.lev[q].b = Q.b; T.lev[q].r = Q.r; T.lev[q].d = Q.d; T.lev[q].n0 = Q.n0; T.lev[q].n1 = Q.n1; T.lev[q].nv = Q.nv;
         }
-        k_vcycle_tail<<<1, 1024, 0, s>>>(T);
+        if (mg.tail_cluster > 1) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)mg.tail_cluster); cfg.blockDim = dim3(1024); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = (unsigned)mg.tail_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            cudaLaunchKernelEx(&cfg, k_vcycle_tail<true>, T);
+        } else
+            k_vcycle_tail<false><<<1, 1024, 0, s>>>(T);
         ctx->launches++;
         int steps = (T.n == 1) ? mg.coarse_degree : 2 * mg.degree;
         return ((steps - 1) & 1) ? L.x[1] : L.x[0];
