@@ -84,6 +84,8 @@ def test_galerkin_hierarchy_matches_scipy(N, pinned):
         assert abs(G - G.T).max() <= 2e-5 * abs(Al).max()
         if n0 * n1 > 3000:
             continue
+        if lev == nlev - 1 and 3 * n0 * n1 <= 120:
+            continue            # the coarsest level is solved exactly (dense inverse, tsl_mg.cu k_coarse_inverse): no smoother, no estimate
         # power-iteration estimate (times the safety factor) must not be below the true lambda_max(D^-1 A)
         Gb = G.tobsr((3, 3))
         D = np.zeros((n0 * n1, 3, 3))

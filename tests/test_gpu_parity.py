@@ -399,7 +399,7 @@ def test_owner_computes_assembly_matches_scatter_and_is_deterministic():
     e.set_option(_lib.OPT_FAST_ASSEMBLY, 2)
     e.assemble(_lib.ASM_RESIDUAL)
     F2, E2 = e.residual(), e.energy()
-    assert _rel(F2, F0) < 1e-11 and abs(E2 - E0) <= 1e-12 * abs(E0)
+    assert _rel(F2, F0) < 1e-10 and abs(E2 - E0) <= 1e-12 * abs(E0)       # (F0 is summed by fp64 atomics: its own run-to-run spread is ~1e-11)
     e.assemble(_lib.ASM_RESIDUAL)
     assert np.array_equal(e.residual(), F2) and e.energy() == E2
 
@@ -408,14 +408,17 @@ def test_owner_computes_assembly_matches_scatter_and_is_deterministic():
 def test_vcycle_variants_agree(N, monkeypatch):
     """the multigrid V-cycle has build-time variants that must be the same preconditioner up to rounding: the small levels as separate
     graph nodes or fused in one thread-block cluster (TSL_MG_TAIL), fp16 or fp32 operator copies for the smoother passes (TSL_MG_HALF),
-    1 or 16 / 4 warps per 32 rows on the large levels (TSL_MG_PAIR, TSL_MG_SELL_SPLIT).  Same clamped Newton system of a sheet in
+    1 or 16 / 4 warps per 32 rows on the large levels (TSL_MG_PAIR, TSL_MG_SELL_SPLIT), the coarsest level swept or solved exactly
+    (TSL_MG_DIRECT: that one is a slightly BETTER preconditioner, not the same).  Same clamped Newton system of a sheet in
     contact, solved to 1e-11 by PCG with each variant: equal iteration counts (+-3) and solutions."""
     from thinshelllab_b200.synthetic import LANDING, sheet_scene
-    variants = [dict(TSL_MG_TAIL="0", TSL_MG_HALF="0", TSL_MG_PAIR="0", TSL_MG_SELL_SPLIT="1"),       # the plain fp32 kernels of round 1
+    variants = [dict(TSL_MG_TAIL="0", TSL_MG_HALF="0", TSL_MG_PAIR="0", TSL_MG_SELL_SPLIT="1", TSL_MG_DIRECT="0"),       # the plain fp32 kernels of round 1
+                dict(TSL_MG_DIRECT="0"),
                 dict(TSL_MG_TAIL="0"), dict(TSL_MG_TAIL="1"), dict(TSL_MG_TAIL="8"), dict(TSL_MG_TAIL="16"), dict(TSL_MG_TAIL="16", TSL_MG_TAIL_NV="8000"),
                 dict(TSL_MG_HALF="0"), dict(TSL_MG_PAIR="2", TSL_MG_SELL_SPLIT="2")]
     keys = sorted({k for v in variants for k in v})
     res = []
+    state = None
     for var in variants:
         for k in keys:
             monkeypatch.delenv(k, raising=False)
@@ -423,13 +426,19 @@ def test_vcycle_variants_agree(N, monkeypatch):
             monkeypatch.setenv(k, v)
         s = sheet_scene(N, **LANDING)
         e = s.engine
-        for _ in range(2):
-            assert s.time_step().converged
-        e.prev_pos.copy_(e.pos)
+        if state is None:
+            # one state and one right-hand side for every variant (a different preconditioner means a different -- equally valid -- Newton
+            # path, and the residual of a converged step is rounding noise: neither may enter the comparison)
+            for _ in range(2):
+                assert s.time_step().converged
+            rhs = np.random.default_rng(5).standard_normal((e.n_verts, 3))
+            rhs[e.frozen.cpu().numpy().reshape(-1, 3) != 0] = 0
+            state = (e.pos.clone(), e.vel.clone(), torch.from_numpy(rhs).to(e.device))
+        e.pos.copy_(state[0]); e.prev_pos.copy_(state[0]); e.vel.copy_(state[1])
+        e.reset_contact_state()
         e.contact_detect()
-        e.assemble(_lib.ASM_RESIDUAL | _lib.ASM_HESSIAN | _lib.ASM_NEWTON | _lib.ASM_SPD)
-        F = torch.from_numpy(e.residual()).to(e.device)
-        x, (iters, flags, rr) = e.solve(F, rel_tol=1e-11, max_iters=600)
+        e.assemble(_lib.ASM_HESSIAN | _lib.ASM_NEWTON | _lib.ASM_SPD)
+        x, (iters, flags, rr) = e.solve(state[2].reshape(-1), rel_tol=1e-11, max_iters=600)
         assert flags == 0 and rr < 1e-10, (var, iters, flags, rr)
         res.append((iters, x.cpu().numpy()))
         del s, e

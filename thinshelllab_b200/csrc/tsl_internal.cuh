@@ -117,6 +117,10 @@ struct MgDev {
     int tiled_galerkin = 1;                // Galerkin products by shared-memory tiles (TSL_MG_TILED=0: one thread per coarse entry)
     int pair_threads = 1;                  // element-major levels: 2 threads per vertex (TSL_MG_PAIR=0: one)
     int tail_level = -1;                   // first level of the fused tail of the V-cycle (-1: none)
+    // coarsest level solved exactly: dense inverse of its (<= TSL_MG_DIRECT_MAX unknowns) operator, rebuilt with the hierarchy, applied by
+    // one matrix-vector kernel instead of coarse_degree Chebyshev launches (TSL_MG_DIRECT=0: the sweep)
+    int coarse_direct = 1;
+    float *coarse_inv = nullptr;           // device [n][n], n = 3 x vertices of the coarsest level
     int tail_cluster = 0;                  // thread blocks of the cluster that runs the tail (1: one block; 0: tail off)
     // side streams of the hierarchy build: the eigenvalue iteration of level l only needs that level's operator, so it runs beside
     // the Galerkin chain that is still producing the coarser levels (TSL_MG_FORK=0: everything on the context's stream)

@@ -682,6 +682,86 @@ __global__ void k_sell_to_half(long long n, const float *__restrict__ src, const
         for (long long k = 4 * i; k < n; k++) dst[k] = __float2half_rn(src[k] * s);
     }
 }
+// ---- exact solve on the coarsest level.  One thread block inverts the level's dense operator (n = 3 x vertices <= 120) by Gauss-Jordan
+// elimination on [A | I] in shared memory.  No pivoting: the operator is positive semi-definite; a DOF whose pivot has collapsed
+// (masked / frozen vertices leave zero rows and columns in the Galerkin product) is taken out, as inv3_guarded does for D^-1.
+#define TSL_MG_DIRECT_MAX 120
+__global__ void __launch_bounds__(1024) k_coarse_inverse(const float *__restrict__ val, int n0, int n1, float *inv)
+{
+    extern __shared__ float sm[];
+    const int nv = n0 * n1, n = 3 * nv, w = 2 * n;
+    float *M = sm;                       // [n][2 n]
+    float *d0 = sm + (size_t)n * w;      // [n] original diagonal
+    for (int t = threadIdx.x; t < n * w; t += blockDim.x) M[t] = 0.f;
+    __syncthreads();
+    for (int t = threadIdx.x; t < nv * 225; t += blockDim.x) {
+        int v = t / 225, e = t - v * 225, slot = e / 9, c = e - slot * 9;
+        int I = v / n1 + slot / 5 - 2, J = v % n1 + slot % 5 - 2;
+        if ((unsigned)I < (unsigned)n0 && (unsigned)J < (unsigned)n1) M[(size_t)(3 * v + c / 3) * w + 3 * (I * n1 + J) + c % 3] = val[(size_t)v * 225 + e];
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < n; t += blockDim.x) { M[(size_t)t * w + n + t] = 1.f; d0[t] = M[(size_t)t * w + t]; }
+    __syncthreads();
+    // block Gauss-Jordan, one vertex (3 x 3 pivot block) per step: nv sequential steps instead of 3 nv.  At step K the A part is already
+    // the identity left of column 3 K and the inverse part is still zero right of column n + 3 K + 2: only columns [3 K, n + 3 K + 3) move.
+    __shared__ float s_pi[9];
+    for (int K = 0; K < nv; K++) {
+        const int k0 = 3 * K, c_lo = k0, c_hi = n + k0 + 3;
+        if (threadIdx.x == 0) {
+            float a[9], iv[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) a[q] = M[(size_t)(k0 + q / 3) * w + k0 + q % 3];
+            // DOFs whose pivot has collapsed leave the system: the rest of the block is inverted on its own
+            bool dead[3];
+            for (int q = 0; q < 3; q++) dead[q] = !(a[4 * q] > 1e-6f * d0[k0 + q]) || !(d0[k0 + q] > 0.f);
+            for (int q = 0; q < 3; q++)
+                if (dead[q]) { for (int r = 0; r < 3; r++) { a[3 * q + r] = 0.f; a[3 * r + q] = 0.f; } a[4 * q] = 1.f; }
+            inv3_guarded(a, iv);
+            for (int q = 0; q < 3; q++)
+                if (dead[q]) { for (int r = 0; r < 3; r++) { iv[3 * q + r] = 0.f; iv[3 * r + q] = 0.f; } }
+#pragma unroll
+            for (int q = 0; q < 9; q++) s_pi[q] = iv[q];
+        }
+        __syncthreads();
+        // row block K <- P^-1 row block K (dead DOFs: zero rows); columns of the dead DOFs are zeroed in every row below
+        for (int c = c_lo + (int)threadIdx.x; c < c_hi; c += blockDim.x) {
+            float r0 = M[(size_t)k0 * w + c], r1 = M[(size_t)(k0 + 1) * w + c], r2 = M[(size_t)(k0 + 2) * w + c];
+            M[(size_t)k0 * w + c] = s_pi[0] * r0 + s_pi[1] * r1 + s_pi[2] * r2;
+            M[(size_t)(k0 + 1) * w + c] = s_pi[3] * r0 + s_pi[4] * r1 + s_pi[5] * r2;
+            M[(size_t)(k0 + 2) * w + c] = s_pi[6] * r0 + s_pi[7] * r1 + s_pi[8] * r2;
+        }
+        __syncthreads();
+        // every other row i: row_i -= sum_q A[i][k0 + q] row_{k0 + q}; a warp per row, lanes stride the active columns
+        for (int t = threadIdx.x; t < n * 32; t += blockDim.x) {
+            int i = t >> 5, lane = t & 31;
+            if (i >= k0 && i < k0 + 3) continue;
+            float f0 = M[(size_t)i * w + k0], f1 = M[(size_t)i * w + k0 + 1], f2 = M[(size_t)i * w + k0 + 2];
+            __syncwarp();
+            if (f0 != 0.f || f1 != 0.f || f2 != 0.f)
+                for (int c = c_lo + 3 + lane; c < c_hi; c += 32)
+                    M[(size_t)i * w + c] -= f0 * M[(size_t)k0 * w + c] + f1 * M[(size_t)(k0 + 1) * w + c] + f2 * M[(size_t)(k0 + 2) * w + c];
+            __syncwarp();
+            if (lane < 3) M[(size_t)i * w + k0 + lane] = 0.f;
+        }
+        __syncthreads();
+    }
+    // symmetrised inverse (rounding leaves it slightly unsymmetric; the preconditioner must be symmetric for PCG)
+    for (int t = threadIdx.x; t < n * n; t += blockDim.x) {
+        int i = t / n, j = t - i * n;
+        inv[t] = 0.5f * (M[(size_t)i * w + n + j] + M[(size_t)j * w + n + i]);
+    }
+}
+// x = inv b on the coarsest level (one warp per row)
+__global__ void __launch_bounds__(256) k_coarse_apply(int n, const float *__restrict__ inv, const float *__restrict__ b, float *x)
+{
+    int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (row >= n) return;
+    float a = 0.f;
+    for (int c = lane; c < n; c += 32) a += __ldg(inv + (size_t)row * n + c) * b[c];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+    if (lane == 0) x[row] = a;
+}
 __global__ void k_fill_hash(int n, float *v, unsigned seed)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -736,6 +816,7 @@ int mg_alloc(tsl_ctx *ctx)
     int n0 = c.N + 1, n1 = c.M + 1;
     int nrows0 = ctx->A.n_slices * 32;
     { const char *e = getenv("TSL_MG_HALF"); mg.use_half = e ? atoi(e) : 1; }
+    { const char *e = getenv("TSL_MG_DIRECT"); mg.coarse_direct = e ? atoi(e) : 1; }
     { const char *e = getenv("TSL_MG_SELL_SPLIT"); mg.sell_split = e ? atoi(e) : 4; if (mg.sell_split != 2 && mg.sell_split != 4) mg.sell_split = 1; }
     for (int l = 0; l < TSL_MG_MAX_LEVELS; l++) {
         MgLevel &L = mg.lev[l];
@@ -760,6 +841,15 @@ int mg_alloc(tsl_ctx *ctx)
         mg.n_levels = l + 1;
         if (std::min(n0, n1) <= 6) break;
         n0 = (n0 - 1) / 2 + 1; n1 = (n1 - 1) / 2 + 1;
+    }
+    {
+        const MgLevel &LL = mg.lev[mg.n_levels - 1];
+        const int n = 3 * LL.nv;
+        if (mg.coarse_direct && mg.n_levels > 1 && LL.sv != 1 && n <= TSL_MG_DIRECT_MAX) {
+            CK(cudaMalloc(&mg.coarse_inv, sizeof(float) * (size_t)n * n));
+            CK(cudaMemset(mg.coarse_inv, 0, sizeof(float) * (size_t)n * n));
+            CK(cudaFuncSetAttribute(k_coarse_inverse, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(sizeof(float) * ((size_t)n * 2 * n + n))));
+        } else mg.coarse_direct = 0;
     }
     {
         std::vector<float> ones(2 * TSL_MG_MAX_LEVELS, 1.f);
@@ -822,6 +912,7 @@ void mg_free(tsl_ctx *ctx)
     }
     cudaFree(mg.coef); cudaFree(mg.powc); cudaFree(mg.pow_acc); cudaFree(mg.lmax); cudaFree(mg.scale); cudaFree(mg.maxdiag);
     cudaFree(ctx->A.val16m); ctx->A.val16m = nullptr;
+    cudaFree(mg.coarse_inv); mg.coarse_inv = nullptr;
     for (int l = 0; l < TSL_MG_MAX_LEVELS; l++) {
         if (mg.side[l]) cudaStreamDestroy(mg.side[l]);
         if (mg.ev_ready[l]) cudaEventDestroy(mg.ev_ready[l]);
@@ -958,6 +1049,12 @@ int mg_setup(tsl_ctx *ctx)
         ctx->launches++;
         if (fork) CK(cudaEventRecord(mg.ev_ready[l + 1], s));
     }
+    if (mg.coarse_direct) {
+        const MgLevel &LL = mg.lev[mg.n_levels - 1];
+        const int n = 3 * LL.nv;
+        k_coarse_inverse<<<1, 1024, sizeof(float) * ((size_t)n * 2 * n + n), s>>>(LL.val, LL.n0, LL.n1, mg.coarse_inv);
+        ctx->launches++;
+    }
     // lambda_max(D^-1 A) per level: 10 power iterations from a fixed pseudo-random vector.  (Warm-starting from the
     // previous setup's vector was measured to UNDER-estimate after the contact set changes -- the old dominant mode
     // has almost no overlap with the new one -- and an under-estimate is what the Chebyshev smoother cannot tolerate.)
@@ -967,6 +1064,8 @@ int mg_setup(tsl_ctx *ctx)
     const int its = 10;
     int extra_slot = -1;
     for (int l = 0; l < mg.n_levels; l++) {
+        if (mg.coarse_direct && mg.tail_level < 0 && l == mg.n_levels - 1) continue;       // solved exactly: no smoother, no eigenvalue estimate
+                                                                                             // (the opt-in fused tail still sweeps it)
         MgLevel &L = mg.lev[l];
         cudaStream_t q = fork ? mg.side[l] : s;
         if (fork) CK(cudaStreamWaitEvent(q, mg.ev_ready[l], 0));
@@ -1026,6 +1125,12 @@ static float *vcycle_level(tsl_ctx *ctx, int l, const float *b, float *z_out, do
     }
     const float *coef = mg.coef + (size_t)l * TSL_MG_MAX_DEGREE * 2;
     const bool last = (l == mg.n_levels - 1);
+    if (last && l > 0 && mg.coarse_direct) {
+        const int n = 3 * L.nv;
+        k_coarse_apply<<<GRID(32 * n, 256), 256, 0, s>>>(n, mg.coarse_inv, b, L.x[0]);
+        ctx->launches++;
+        return L.x[0];
+    }
     const int deg = last ? mg.coarse_degree : mg.degree;
     // pre-smoothing (or the coarsest-grid sweep) from a zero guess
     float *cur = nullptr;
