@@ -208,8 +208,9 @@ def secondary_50k(args, dev):
 
 def secondary_solids(args, dev):
     """BASELINE.json configs[0] (Scene_folding: cloth strip + table + tactile pad on a gripper, T = 3 rollout + trajectory adjoint) and a
-    configs[3] (316 x 316 = 200 k-triangle sheet on the table with the volumetric tactile pad pressed into it and the free TetGen ball
-    lying on it: data/tactile.*, data/ball.*; contacts against moving triangles), one GPU, state resident in HBM"""
+    configs[3] (316 x 316 = 200 k-triangle sheet on the table, the free TetGen ball lying on it, its overhanging edge between the two
+    tactile pads of a two-finger gripper that closes and lifts: data/tactile.*, data/ball.*; contacts against moving triangles), one
+    GPU, state resident in HBM"""
     import torch
     from thinshelllab_b200.agent.traj_opt_single import agent_trajopt
     from thinshelllab_b200.engine.analytic_grad_single import Grad
@@ -257,12 +258,12 @@ def secondary_solids(args, dev):
     out["configs[0] Scene_folding fwd + trajectory adjoint"] = dict(scene="cloth 15x3 (90 tris) + frozen table + tactile pad (1365 tets) on a gripper",
                                                                     **rollout(s, T0, traj0, 2))
     del s
-    N, T = 316, 4
+    N, T = 316, 6
     s = config3_scene(N, device=dev)
-    traj = np.zeros((T, 1, 6)); traj[:, 0, 2] = -1.5e-4 * np.arange(T)
-    out["configs[3] 200k-tri sheet + tactile pad + ball, fwd + trajectory adjoint"] = dict(
-        scene=f"sheet {N}x{N} ({2 * N * N} tris) resting on a frozen table, tactile pad (1365 tets) pressed 0.15 mm per step into it, "
-              "free TetGen ball (295 tets) lying on the sheet", **rollout(s, T, traj, 1))
+    traj = np.zeros((T, 1, 6)); traj[:, 0, 2] = 1.5e-4 * np.maximum(np.arange(T) - 2, 0)
+    out["configs[3] 200k-tri sheet + ball + two pads gripping an edge, fwd + trajectory adjoint"] = dict(
+        scene=f"sheet {N}x{N} ({2 * N * N} tris) resting on a frozen table, free TetGen ball (295 tets) lying on it, the overhanging edge "
+              "between the two tactile pads (1365 tets each) of a two-finger gripper that closes 0.15 mm per frame and lifts", **rollout(s, T, traj, 1))
     del s
     torch.cuda.empty_cache()
     return out

@@ -185,30 +185,33 @@ def test_sheet316_with_pad_pressed_steps(golden_dir):
     assert np.isfinite(grad._gripper_grad).all() and np.abs(grad._gripper_grad[1:]).max() > 0
 
 
-def test_sheet316_config3_pad_and_ball():
-    """BASELINE configs[3] as named: 200 k-triangle sheet + volumetric tactile AND ball contact (data/tactile.*, data/ball.*).  The sheet
-    rests on the table, the pad is pressed into it while the free TetGen ball lies beside it; cloth / table constraints bit-exact against
-    the oracle's query at every step, every step converged, multigrid-FGMRES adjoint of the whole rollout."""
+def test_sheet316_config3_ball_and_gripped_edge():
+    """BASELINE configs[3]: 200 k-triangle sheet + the ball of data/ball.* lying on it + two tactile pads of data/tactile.*
+    gripping the overhanging edge (one two-finger gripper part that closes and lifts).  Cloth / table constraints bit-exact against the
+    oracle's query at every step, every step converged, multigrid-FGMRES adjoint of the whole rollout."""
     from thinshelllab_b200.agent.traj_opt_single import agent_trajopt
     from thinshelllab_b200.engine.analytic_grad_single import Grad as GradT
     from thinshelllab_b200.synthetic import config3_scene, sheet_spec
-    N, T = 316, 5
+    N, T = 316, 6
     s = config3_scene(N)
     e = s.engine
     NVc = s.cloths[0].NV
-    table, pad, ball = s.elastics
+    table, pad_up, pad_lo, ball = s.elastics
     to, tn = table.offset, table.n_verts
-    assert to == NVc and ball.n_verts == 100 and s.gripper.n_part == 1
+    assert to == NVc and ball.n_verts == 100 and s.gripper.n_part == 1 and s.enable_gripper
     sp = sheet_spec(N, bump=0.0, noise=0.0, z0=0.0004, k_contact=10000.0, mu=0.5)
-    o = orc.OracleScene(N, N, sp["dx"], sp["dt"], sp["table_pos"], sp["table_faces"], sp["table_mass"], Kb=100.0, k_angle=3.14, k_contact=10000.0,
-                        eps_contact=sp["eps_contact"], eps_v=sp["eps_v"], mu=0.5, max_n_constraints=sp["max_n_constraints"], grid_n=sp["grid_n"])
-    assert np.abs(o.pos[NVc:] - e.pos[to:to + tn].cpu().numpy()).max() == 0.0
+    tb = s.body_list[1]
+    tpos = e.pos[to:to + tn].cpu().numpy()
+    o = orc.OracleScene(N, N, sp["dx"], sp["dt"], tpos, s.faces[tb.f_start:tb.f_end] - to, e.mass[to:to + tn].cpu().numpy(), Kb=100.0, k_angle=3.14,
+                        k_contact=10000.0, eps_contact=sp["eps_contact"], eps_v=sp["eps_v"], mu=0.5, max_n_constraints=sp["max_n_constraints"], grid_n=sp["grid_n"])
+    assert np.abs(o.pos[NVc:] - tpos).max() == 0.0 and tpos[:, 0].max() < e.pos[:NVc, 0].max().item() - 0.015      # the edge overhangs
     agent = agent_trajopt(T, 1, max_moving_dist=0.001)
-    traj = np.zeros((T, 1, 6)); traj[:, 0, 2] = -1.5e-4 * np.arange(T)
+    traj = np.zeros((T, 1, 6)); traj[:, 0, 2] = 1.5e-4 * np.maximum(np.arange(T) - 2, 0)      # close (Scene.action), then lift the edge
     agent.traj.from_numpy(traj)
     grad = GradT(s, T, 1)
     grad.copy_pos(s, 0)
     z_ball0 = e.pos[ball.offset:ball.offset + ball.n_verts, 2].mean().item()
+    edge = torch.arange(N + 1, device=e.device) + N * (N + 1)                                   # the gripped row of vertices
     for f in range(1, T):
         agent.get_action(f)
         s.action(f, agent.delta_pos, agent.delta_rot)
@@ -216,23 +219,25 @@ def test_sheet316_config3_pad_and_ball():
         o.calc_vn(); o.projection_query(); o.contact_analysis()
         st = s.time_step()
         assert st.converged, (f, st)
-        c = e.constraints()
-        idx = c["idx"]
+        idx = e.constraints()["idx"]
         on_table = (idx[:, 3] < NVc) & (idx[:, 0] >= to) & (idx[:, 0] < to + tn)
         assert sorted(map(tuple, idx[on_table])) == sorted(map(tuple, o.c_idx[:o.nc])), f
-        with_pad = ((idx[:, 3] >= pad.offset) & (idx[:, 3] < ball.offset)).sum() + ((idx[:, 3] < NVc) & (idx[:, 0] >= pad.offset) & (idx[:, 0] < ball.offset)).sum()
+        with_pads = ((idx[:, 3] >= pad_up.offset) & (idx[:, 3] < ball.offset)).sum() + ((idx[:, 3] < NVc) & (idx[:, 0] >= pad_up.offset) & (idx[:, 0] < ball.offset)).sum()
         with_ball = (idx[:, 3] >= ball.offset).sum() + ((idx[:, 3] < NVc) & (idx[:, 0] >= ball.offset)).sum()
-        print(f"316 x 316 + pad + ball step {f}: newton {st.newton_iters} pcg {st.linear_iters} contacts {st.n_contacts} "
-              f"(cloth/table {int(on_table.sum())}, with the pad {int(with_pad)}, with the ball {int(with_ball)})")
+        print(f"316 x 316 + ball + gripped edge step {f}: newton {st.newton_iters} pcg {st.linear_iters} contacts {st.n_contacts} "
+              f"(cloth/table {int(on_table.sum())}, with the pads {int(with_pads)}, with the ball {int(with_ball)})")
         grad.copy_pos(s, f)
-    assert o.nc > 10000 and with_pad > 0 and with_ball > 0
+    assert o.nc > 10000 and with_pads > 0 and with_ball > 0
+    assert abs(s.gripper._half[0] + 4 * 1.5e-4) < 1e-15
     dz = e.pos[ball.offset:ball.offset + ball.n_verts, 2].mean().item() - z_ball0
     assert -4e-4 < dz < 0.0, dz                                  # the ball has settled into the sheet's contact gap, not fallen through
+    ze = e.pos[edge, 2]
+    assert ze.max().item() > ze.median().item() + 1e-3           # the free overhang has sagged ~3 mm in 25 ms; the fingers hold its middle up
     grad._pos_grad[T - 1, :NVc, 2] = 1.0
     for j in range(T - 1, 0, -1):
         it, flags, rr = grad.transfer_grad(j, s, rel_tol=1e-8)
         assert (flags & 3) == 0 and rr < 1e-7, (j, it, flags, rr)
-        print(f"316 x 316 + pad + ball adjoint step {j}: {it} iterations, rel residual {rr:.1e}")
+        print(f"316 x 316 + ball + gripped edge adjoint step {j}: {it} iterations, rel residual {rr:.1e}")
     assert np.isfinite(grad._gripper_grad).all() and np.abs(grad._gripper_grad[1:]).max() > 0
 
 

@@ -100,23 +100,34 @@ def pad_sheet_scene(N, pad=None, device="cuda:0", **kw):
     return Scene(st, device=device, max_newton=200)
 
 
-def config3_state(N, dx=0.002, dt=5e-3, Kb=100.0, k_contact=10000.0, mu=0.5, gap=2e-4, ball_xy=(0.03, 0.0)):
-    """BASELINE.json configs[3] as it names it: an N x N sheet + volumetric tactile AND ball contact (data/tactile.*, data/ball.*) -- the
-    sheet rests on a frozen table, a tactile pad on a one-part gripper hovers `gap` above its centre, the TetGen ball of Scene_balancing
-    (free, density 10000, under gravity) lies on the sheet beside it.  A state mapping for task_scene._multi_body.MultiBodyScene."""
+def config3_state(N, dx=0.002, dt=5e-3, Kb=100.0, k_contact=10000.0, mu=0.5, gap=2e-4, ball_xy=(0.03, 0.0), overhang=0.021):
+    """BASELINE.json configs[3]: an N x N sheet + the ball of data/ball.* resting on it + two tactile pads of data/tactile.*
+    gripping an edge (the Scene_balancing ingredients, scaled).  The sheet rests on a frozen table; its +x edge overhangs the table by
+    `overhang` and sits between the upper and the lower pad of one two-finger gripper part (engine/gripper_tactile.py), each `gap` away
+    from the sheet, ready to close and lift; the TetGen ball (free, density 10000, under gravity) lies on the sheet.  A state mapping for
+    task_scene._multi_body.MultiBodyScene."""
     from .engine.scene_builder import TactileBody, ball_body, multi_body_state
     sp = sheet_spec(N, dx=dx, dt=dt, bump=0.0, noise=0.0, z0=0.0004, k_contact=k_contact, mu=mu)
     tn = sp["table_N"][0]
-    tpos, ttets, tfaces, tmass = box_body(sp["table_size"], tn, tn, 2, sp["table_offset"])
-    pad = TactileBody(0.015 / 0.03)
-    pad_z = 0.0004 + 0.0004 + gap - (pad.init((0.0, 0.0, 0.0), True).F_x[:, 2].min())
-    pad = TactileBody(0.015 / 0.03).init((0.0, 0.0, pad_z), True)
-    rest, bpos, btets, bfaces = ball_body((ball_xy[0], ball_xy[1], 0.0004 + 0.0039))
+    tdx = sp["table_size"] / (tn - 1)
+    cut = int(np.ceil((overhang + 0.01) / tdx))                          # table columns dropped on the +x side (the table is 1 cm wider than the sheet)
+    tpos, ttets, tfaces, tmass = box_body(sp["table_size"], tn - cut, tn, 2, sp["table_offset"])
+    assert tpos[:, 0].max() < 0.5 * N * dx - overhang + tdx
+    zs = 0.0004                                                          # the sheet's plane
+    px = 0.5 * N * dx - 0.008                                            # pad axis 8 mm inside the overhanging edge
+    probe = TactileBody(0.015 / 0.03).init((0.0, 0.0, 0.0), True)
+    reach = -probe.F_x[:, 2].min()                                       # distance from a pad's pose to its sensing tip
+    pads = [TactileBody(0.015 / 0.03).init((px, 0.0, zs + 0.0004 + gap + reach), True),
+            TactileBody(0.015 / 0.03).init((px, 0.0, zs - 0.0004 - gap - reach), False)]
+    assert pads[1].F_x[:, 0].min() > tpos[:, 0].max()                    # the lower pad hangs beside the table, not inside it
+    rest, bpos, btets, bfaces = ball_body((ball_xy[0], ball_xy[1], zs + 0.0039))
     els = [dict(kind="box", pos=tpos, tets=ttets, faces=tfaces, mass=tmass, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, -9.8), frozen=True),
-           dict(kind="tactile", body=pad, gravity=(0.0, 0.0, 0.0)),
+           dict(kind="tactile", body=pads[0], gravity=(0.0, 0.0, 0.0)),
+           dict(kind="tactile", body=pads[1], gravity=(0.0, 0.0, 0.0)),
            dict(kind="mesh", rest=rest, pos=bpos, tets=btets, faces=bfaces, density=10000.0, mu=5e5 / 2, lam=0.0, gravity=(0.0, 0.0, -9.8))]
-    st = multi_body_state(cloth_N=N, cloth_M=N, cloth_size=N * dx, cloth_pos=sp["cloth_pos"], elastics=els, pad_poses=[(0.0, 0.0, pad_z)], dt=dt,
-                          k_contact=k_contact, Kb=Kb, k_angle=3.14, mu=mu, cloth_gravity=(0.0, 0.0, -9.8), max_n_constraints=4 * (N + 1) ** 2 + 4096)
+    st = multi_body_state(cloth_N=N, cloth_M=N, cloth_size=N * dx, cloth_pos=sp["cloth_pos"], elastics=els, pad_poses=[(px, 0.0, zs)], pad_part=[0, 0],
+                          dt=dt, k_contact=k_contact, Kb=Kb, k_angle=3.14, mu=mu, cloth_gravity=(0.0, 0.0, -9.8),
+                          max_n_constraints=4 * (N + 1) ** 2 + 4096)
     st["grid_n"] = sp["grid_n"]
     st["n_tris"] = 2 * N * N
     return st
@@ -130,6 +141,14 @@ def config3_scene(N, device="cuda:0", **kw):
 
         def __init__(self, st):
             self._build(st, device=device)
+
+        def action(self, step, delta_pos, delta_rot):
+            """the fingers close by 0.15 mm each over the first four frames (as Scene_interact.action does), then only move"""
+            if step < 5:
+                self.gripper.step(delta_pos, delta_rot, np.array([-1.5e-4]))
+            else:
+                self.gripper.step_simple(delta_pos, delta_rot)
+            self.gripper.update_bound(self)
     return Scene(config3_state(N, **kw))
 
 
