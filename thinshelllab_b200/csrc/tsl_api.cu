@@ -490,6 +490,7 @@ int tsl_finalize(tsl_ctx *ctx)
     if (const char *e = getenv("TSL_PRECOND")) ctx->precond = atoi(e);
     if (const char *e = getenv("TSL_NEWTON_MODE")) ctx->newton_mode = atoi(e);
     if (const char *e = getenv("TSL_PROBE")) ctx->probe = atoi(e);
+    if (const char *e = getenv("TSL_THETA_BACKOFF")) ctx->theta_backoff = atoi(e);
     ctx->finalized = true;
     return TSL_OK;
 }
@@ -691,6 +692,7 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
     const double len_scale = ctx->cloths.empty() ? 1e-3 : ctx->cloths[0].P.dx;
     double eta = 0.1, fnorm_prev = -1;
     double theta = 0.0, theta_used = 0.0;     // newton_mode 2: blend factor of the next / the last solve
+    int fails_prop = 0, hold = 0, backoff = 2; double floor_theta = 0.0;   // newton_mode 2: back-off of the lower-theta proposals (see below)
     bool have_ncdir = false;                  // ctx->ncdir holds a direction of negative curvature met in this step
     int skip = 0, back = 0;                   // newton_mode 0: exact attempts skipped after a failure (1, 3, 7, 8, ...)
     int age = refresh_every;                  // iterations since the hierarchy was built (forces a build at it == 1)
@@ -757,6 +759,14 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
                 TRY(probe_curvature(ctx, ctx->A.val32c, ctx->ncdir, &pAc));
                 while (theta < 1.0 && (1.0 - theta) * pAe + theta * pAc <= 0.0) theta = std::min(1.0, std::max(2.0 * theta, 1.0 / 16));
             }
+            // The driver proposes half the last successful theta (down to 0 = the exact matrix).  On a buckling step that proposal fails for
+            // dozens of Newton iterations in a row, and every failed attempt costs the 15-60 PCG iterations it takes to meet the negative
+            // curvature (measured at 1 M triangles: 70 % of the PCG iterations of the impact steps were spent in such attempts).  After two
+            // consecutive failed proposals theta is therefore HELD at the value that worked for `backoff` iterations (2, 4, ... 16) before
+            // the next lower proposal is tried; one successful proposal resets the back-off.
+            const bool holding = ctx->theta_backoff && hold > 0;
+            if (holding) { theta = std::max(theta, floor_theta); hold--; }
+            const double theta_first = theta;
             while (true) {
                 const float *op = ctx->A.val32;
                 if (theta >= 1.0) op = ctx->A.val32c;
@@ -769,6 +779,12 @@ int tsl_step_forward(tsl_ctx *ctx, int max_newton, double tol, tsl_step_stats *s
                 CK(cudaMemcpyAsync(ctx->ncdir, ctx->cg_p, sizeof(double) * 3 * (size_t)ctx->n_solve, cudaMemcpyDeviceToDevice, s));
                 have_ncdir = true;
                 theta = std::min(1.0, std::max(2.0 * theta, 1.0 / 16));
+            }
+            if (ctx->theta_backoff) {
+                if (holding) { if (theta > floor_theta) floor_theta = theta; }          // even the held value failed: hold the one that worked
+                else if (theta > theta_first) {                                           // a proposal failed
+                    if (++fails_prop >= 2) { floor_theta = theta; hold = backoff; backoff = std::min(2 * backoff, 16); }
+                } else { fails_prop = 0; backoff = 2; floor_theta = 0.0; }                // a proposal worked
             }
             fallback = theta > 0.0;
             theta_used = theta;

@@ -237,6 +237,7 @@ struct tsl_ctx {
     tsl::MgDev mg;
     int precond = 1;                             // 0 block-Jacobi, 1 multigrid V-cycle
     int probe = 0;                               // Newton mode 2: curvature probe before the solves (TSL_PROBE=1; measured: no gain)
+    int theta_backoff = 1;   // newton_mode 2: leave theta = 0 out for a while after repeated negative-curvature failures (TSL_THETA_BACKOFF=0: always try)
     int newton_mode = 2;                         // 0 projected-Newton fallback, 1 negative-curvature moves, 2 blended operator
     float *cg_r64tmp = nullptr;                  // [3 n_rows_pad] fp32 staging of fp64 vectors for the V-cycle
     tsl::KrylovScalars *ks = nullptr;            // device
