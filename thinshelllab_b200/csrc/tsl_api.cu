@@ -491,6 +491,7 @@ int tsl_finalize(tsl_ctx *ctx)
     if (const char *e = getenv("TSL_NEWTON_MODE")) ctx->newton_mode = atoi(e);
     if (const char *e = getenv("TSL_PROBE")) ctx->probe = atoi(e);
     if (const char *e = getenv("TSL_THETA_BACKOFF")) ctx->theta_backoff = atoi(e);
+    if (const char *e = getenv("TSL_GMRES_M")) { int v = atoi(e); if (v >= 2 && v <= 400) ctx->gmres_m = v; }
     ctx->finalized = true;
     return TSL_OK;
 }
